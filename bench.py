@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — image-pairs/s of the bi-temporal change-detection hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch of synthetic image pairs on every rank:
+``net_G(x1, x2)`` (libstcd_b200) + the evaluator's fused binarise/confusion-matrix kernel, then
+the int64[4] all-reduce of the matrix (the path's only collective).  Prints ONE JSON line (rank 0).
+
+* ``value``     pairs/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks.
+* ``e2e``       the same through the public API with pinned HOST buffers: H2D of the step's pairs
+                and labels, forward, metric, D2H of the uint8 change maps and the matrix.
+* ``roofline``  the dominant kernel (by device time, from a per-launch CUDA-event pass) against
+                the measured peak in MEASURED_PEAKS.json.
+* ``cpu_baseline``  the oracle's fp32 CPU forward (torch.nn.functional restatement of the
+                reference, oracle/nets.py) on this box's host cores, bounded sample, rank 0, N=1.
+``--impl reference`` times that CPU path alone with all host threads and prints the same line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# workload -> (net kind, ctor args, synth gain, H, W, per-GPU batch, binarise kind, config string)
+WORKLOADS = {
+    "siamunet_diff_256": dict(net="SiamUnet_diff", n_class=2, gain=0.8, h=256, w=256, batch=8, kind="argmax",
+                              desc="C1: SiamUnet_diff 256x256 RGB pairs, batch 8 per GPU"),
+    "siamunet_diff_256_b64": dict(net="SiamUnet_diff", n_class=2, gain=0.8, h=256, w=256, batch=64, kind="argmax",
+                                  desc="SiamUnet_diff 256x256 RGB pairs, batch 64 per GPU"),
+    "siamunet_conc_256": dict(net="SiamUnet_conc", n_class=2, gain=0.75, h=256, w=256, batch=8, kind="argmax",
+                              desc="SiamUnet_conc 256x256 RGB pairs, batch 8 per GPU"),
+}
+DEFAULT_WORKLOAD = "siamunet_diff_256_b64"
+
+
+def build_net(wl):
+    from stcd_b200 import siamunet, synth
+    cls = {"SiamUnet_diff": siamunet.SiamUnet_diff, "SiamUnet_conc": siamunet.SiamUnet_conc}[wl["net"]]
+    return synth.randomize_(cls(3, wl["n_class"]).eval(), gain=wl["gain"])
+
+
+def oracle_forward(wl, sd, x1, x2):
+    from oracle import nets
+    if wl["net"] == "SiamUnet_diff":
+        return nets.siamunet_forward(sd, x1, x2, "diff")
+    if wl["net"] == "SiamUnet_conc":
+        return nets.siamunet_forward(sd, x1, x2, "conc")
+    raise KeyError(wl["net"])
+
+
+def flops_per_pair(net, wl) -> float:
+    return 2.0 * net.lower(wl["h"], wl["w"]).macs_per_pair()
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(wl, seconds_target: float = 15.0, threads: int | None = None):
+    """The oracle's CPU forward + numpy confusion matrix on a bounded sample of the workload."""
+    from oracle import metric as ometric
+    from stcd_b200 import synth
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    net = build_net(wl)
+    sd = net.state_dict()
+    n = 2
+    x1, x2 = synth.image_pairs(n, wl["h"], wl["w"])
+    lab = synth.labels(n, wl["h"], wl["w"]).numpy()
+
+    def step():
+        with torch.no_grad():
+            y = oracle_forward(wl, sd, x1, x2)
+        y = y[-1] if isinstance(y, (list, tuple)) else y
+        ometric.confusion_matrix(ometric.binarise(y.numpy(), wl["kind"]), lab)
+
+    t0 = time.perf_counter()
+    step()                                   # warm-up (also sizes the sample)
+    t_one = time.perf_counter() - t0
+    reps = max(1, min(20, int(seconds_target / max(t_one, 1e-3))))
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return {"value": n / med, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": f"{reps} x {n} pairs of {wl['h']}x{wl['w']} (median), oracle/nets.py fp32 torch CPU + numpy bincount"}
+
+
+# ------------------------------------------------------------------------------------------ arms
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    from oracle import metric as ometric
+    from stcd_b200 import synth
+    net = build_net(wl)
+    sd = net.state_dict()
+    n = 2                                    # bounded sample per step
+    x1, x2 = synth.image_pairs(n, wl["h"], wl["w"])
+    lab = synth.labels(n, wl["h"], wl["w"]).numpy()
+
+    def step():
+        with torch.no_grad():
+            y = oracle_forward(wl, sd, x1, x2)
+        y = y[-1] if isinstance(y, (list, tuple)) else y
+        ometric.confusion_matrix(ometric.binarise(y.numpy(), wl["kind"]), lab)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    sample = f"{n} pairs per step, {args.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": "image-pairs/sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "batch_per_gpu": wl["batch"], "h": wl["h"], "w": wl["w"]},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args, wl, rank, world, local_rank):
+    import torch.distributed as dist
+    from stcd_b200 import synth
+    from stcd_b200.metric import SegmentationMetric
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — stcd_b200 has no CPU path (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, H, W = wl["batch"], wl["h"], wl["w"]
+    net = build_net(wl).to(dev)
+    net.chunk_pairs = args.chunk
+    fl_pair = flops_per_pair(net, wl)
+    metric = SegmentationMetric(2, dev)
+    n_sets = args.input_sets                 # rotate distinct batches: working set > L2 (126 MB)
+    hx1, hx2, hlab = [], [], []
+    for s in range(n_sets):
+        a, b = synth.image_pairs(B, H, W, seed=synth.DATA_SEED + 100 * rank + s)
+        hx1.append(a.pin_memory())
+        hx2.append(b.pin_memory())
+        hlab.append(synth.labels(B, H, W, seed=synth.DATA_SEED + 7 + 100 * rank + s).to(torch.uint8).pin_memory())
+    dx1 = [t.to(dev) for t in hx1]
+    dx2 = [t.to(dev) for t in hx2]
+    dlab = [t.to(dev) for t in hlab]
+    plan = net.plan_for(dx1[0])
+    logits = [torch.empty(s, dtype=torch.float32, device=dev) for s in plan.out_shapes(B)]
+    pred = torch.empty(B, H, W, dtype=torch.uint8, device=dev)
+    hpred = torch.empty(B, H, W, dtype=torch.uint8).pin_memory()
+    hcm = torch.empty(4, dtype=torch.int64).pin_memory()
+
+    def step(i):
+        s = i % n_sets
+        plan.forward(dx1[s], dx2[s], outs=logits)
+        metric.addLogits(logits[-1], dlab[s], kind=wl["kind"], pred_out=pred)
+        metric.allreduce()
+
+    def step_e2e(i):
+        s = i % n_sets
+        a = hx1[s].to(dev, non_blocking=True)
+        b = hx2[s].to(dev, non_blocking=True)
+        lab = hlab[s].to(dev, non_blocking=True)
+        y = net(a, b)
+        y = y[-1] if isinstance(y, (list, tuple)) else y
+        metric.addLogits(y, lab, kind=wl["kind"], pred_out=pred)
+        metric.allreduce()
+        hpred.copy_(pred, non_blocking=True)
+        hcm.copy_(metric.confusion_counts().reshape(-1), non_blocking=True)
+
+    def timed(fn, steps, warmup, sampler=None):
+        for i in range(warmup):
+            fn(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.__enter__()
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        if sampler is not None:
+            sampler.__exit__()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total = timed(step, args.steps, args.warmup, sampler)
+    metric.reset()
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    value = world * B * args.steps / (ms_total / 1e3)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+
+    # consistency check of the evaluator inside the run: counts sum to the pixels seen
+    torch.cuda.synchronize(dev)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        # ---- dominant kernel: per-launch CUDA-event pass (same inputs, after the timed region)
+        prof = plan.profile(dx1[0], dx2[0])
+        prof = [p for p in prof if p[1] > 0]
+        total_ms = sum(p[1] for p in prof)
+        top = max(prof, key=lambda p: p[1])
+        top_tf = 2.0 * top[2] / (top[1] * 1e-3) / 1e12 if top[2] else 0.0
+        step_tf = fl_pair * B / (ms_total / args.steps * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": round(top_tf, 2), "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                "frac": round(top_tf / peaks["tf_burst"], 4), "traffic": None,
+                "kernel": f"conv_gemm_kernel[{top[0]}]", "kernel_share_of_step": round(top[1] / total_ms, 4),
+                "peak_source": f"{peaks['src']} bf16 burst (kernel timed alone)",
+                "whole_step": {"achieved": round(step_tf, 2), "peak": peaks["tf_sust"],
+                               "frac": round(step_tf / peaks["tf_sust"], 4), "unit": "TFLOP/s",
+                               "flops_per_pair": fl_pair}}
+        out = {
+            "metric": "image-pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl["desc"], "batch_per_gpu": B, "global_batch": B * world, "h": H, "w": W,
+                       "parallelism": f"dp{world}", "chunk_pairs": args.chunk,
+                       "l2": f"{n_sets} distinct input batches rotated; activations per step exceed the 126 MB L2"},
+            "e2e": {"value": e2e, "unit": "pairs/s",
+                    "h2d_bytes_per_step": int(2 * B * 3 * H * W * 4 + B * H * W),
+                    "d2h_bytes_per_step": int(B * H * W + 32)},
+            "gpu_launches": int((plan.launches(B) + 1) * args.steps),
+            "clocks": sampler.summary() if sampler else None,
+            "roofline": roof,
+            "per_op_ms": [[n, round(ms, 4)] for n, ms, _ in prof],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--chunk", type=int, default=8, help="image pairs per pass through the layer stack")
+    ap.add_argument("--input-sets", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+    else:
+        if args.gpus > 1 and world == 1:
+            raise SystemExit("bench.py: launch N>1 with torch.distributed.run (one rank per GPU)")
+        run_ours(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,181 @@
+/*
+ * stcd_b200.h — C-ABI of libstcd_b200.so: B200 (sm_100a) bi-temporal change-detection
+ * inference + confusion-matrix evaluation.
+ *
+ * The reference (VCISwang/STCD) has no FFI of its own; the boundary it exposes is Python:
+ *   net_G(x1, x2)                       models/SiamUnet_diff.py:94, models/SNUNet.py:116,
+ *                                       segmentation_models_pytorch/decoders/unet/model.py:316
+ *   define_G(args, ...)                 models/networks.py:138-215
+ *   SegmentationMetric.addBatch(p, l)   train_stcd.py:572-588
+ * Each entry point below names the reference call it stands in for.  Plain pointers and sizes
+ * only — no torch types.  All `const void*` / `void*` data pointers are DEVICE pointers unless a
+ * function says "host"; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *
+ * Error convention: every int-returning function returns STCD_OK (0) or a negative/positive
+ * error code; stcd_last_error() gives a thread-local message (reference: Python exceptions,
+ * models/networks.py:214 NotImplementedError, train_stcd.py:587 assert).
+ *
+ * Threading: a plan is not re-entrant (one forward in flight per plan); distinct plans are
+ * independent.  All work is enqueued on the caller's stream.
+ */
+#ifndef STCD_B200_H_
+#define STCD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STCD_ABI_VERSION 1
+
+enum stcd_status {
+  STCD_OK = 0,
+  STCD_ERR_INVALID = 1,   /* bad argument / shape (reference: assert / ValueError) */
+  STCD_ERR_CUDA = 2,      /* a CUDA runtime / driver call failed */
+  STCD_ERR_NO_DEVICE = 3, /* no sm_100 device visible: the product path has NO CPU fallback */
+  STCD_ERR_STATE = 4      /* plan used before finalize / after destroy */
+};
+
+enum stcd_dtype { STCD_BF16 = 0, STCD_F32 = 1 };
+
+typedef struct stcd_plan stcd_plan;
+
+/* ------------------------------------------------------------------------------------------ */
+/* library                                                                                    */
+const char* stcd_last_error(void);
+int stcd_abi_version(void);
+/* number of visible CUDA devices with compute capability 10.x; 0 on a CPU-only host */
+int stcd_device_count(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* plan construction: the host side (Python mirror of the reference modules) lowers a         */
+/* reference nn.Module (its state_dict) into a list of fused ops on NHWC bf16 tensors.         */
+/* The batch is processed in chunks of `chunk_pairs` image pairs so that inter-layer           */
+/* activations stay resident in the 126 MB L2.                                                 */
+
+int stcd_plan_create(int device, int chunk_pairs, stcd_plan** out);
+void stcd_plan_destroy(stcd_plan* plan);
+
+/* Declare an activation tensor of img_mult*chunk_pairs images, NHWC. Returns id >= 0, or <0. */
+int stcd_plan_add_tensor(stcd_plan* plan, int img_mult, int h, int w, int c, int dtype);
+
+/* One K-block of the implicit GEMM: `kc` channels [c0, c0+kc) of source `src` (index into
+ * stcd_conv_desc.src), read at input pixel (i*src_sy + dy, j*src_sx + dx) of image (n + n_off) for
+ * tile pixel (i, j); multiplies weight columns [wk, wk+kc). Out-of-bounds pixels read as 0
+ * (= zero padding, nn.Conv2d padding=1: SiamUnet_diff.py:18). */
+typedef struct stcd_kentry {
+  int16_t src, dy, dx, c0;
+  int32_t n_off;
+  int32_t wk;
+} stcd_kentry;
+
+/* One output phase: tile pixel (i, j) -> output pixel (i*osy + oy, j*osx + ox). A stride-1
+ * conv has one phase; ConvTranspose2d(stride=2) (SiamUnet_diff.py:52) has four. */
+typedef struct stcd_phase {
+  int32_t k_begin, k_count; /* slice of the kentry array */
+  int32_t oy, ox;
+  int32_t w_row;            /* first row of this phase in the packed weight matrix */
+} stcd_phase;
+
+#define STCD_MAX_SRC 6
+#define STCD_MAX_PHASE 4
+
+typedef struct stcd_conv_desc {
+  /* A operand (activations): virtual concat of up to 6 sources (torch.cat, SNUNet.py:142) */
+  int32_t n_src;
+  int32_t src[STCD_MAX_SRC];      /* tensor ids */
+  int32_t src_sy[STCD_MAX_SRC];   /* per-source input coordinate stride (2 for a stride-2 conv) */
+  int32_t src_sx[STCD_MAX_SRC];
+  /* tile grid */
+  int32_t hg, wg;                 /* tile-pixel grid (= output dims / osy, osx) */
+  int32_t img_mult;               /* images in the grid = img_mult * chunk_pairs */
+  int32_t pair;                   /* 1: each CTA also accumulates image n + chunk_pairs (Siamese pair) */
+  /* B operand (weights), packed by the host: bf16 [w_rows][w_cols], K-major */
+  const uint16_t* weights;        /* HOST pointer, copied at add time */
+  int32_t w_rows, w_cols;
+  int32_t kc;                     /* channels per K-block: 16, 32 or 64 */
+  int32_t n_tile;                 /* GEMM N per CTA (multiple of 16, <= 256) */
+  int32_t cout;                   /* real output channels */
+  int32_t cout_pad;               /* padded to a multiple of n_tile */
+  int32_t n_phase;
+  stcd_phase phase[STCD_MAX_PHASE];
+  const stcd_kentry* kprog;       /* HOST pointer */
+  int32_t n_kentry;
+  int32_t osy, osx;               /* output coordinate stride */
+  /* epilogue: v = acc*scale + shift; [out_raw <- v]; [v = v*scale2 + shift2]; [v += res];
+   * [v = relu(v)]; out0 <- v; out_pool <- maxpool2x2(v); out_diff <- |v(n) - v(n+chunk)| */
+  const float* scale;             /* HOST, [cout_pad] */
+  const float* shift;             /* HOST, [cout_pad] */
+  const float* scale2;            /* HOST or NULL */
+  const float* shift2;            /* HOST or NULL */
+  int32_t relu;
+  int32_t res;                    /* tensor id or -1 */
+  int32_t out0, out0_coff;        /* tensor id or -1; channel offset inside out0 */
+  int32_t out_raw;                /* tensor id or -1 */
+  int32_t out_pool;               /* tensor id or -1 */
+  int32_t out_diff;               /* tensor id or -1 (needs pair=1) */
+  int32_t out_ext;                /* index into stcd_forward's outs[] for fp32 NCHW logits, or -1 */
+} stcd_conv_desc;
+
+/* returns op index >= 0, or <0 */
+int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* desc);
+
+/* x1, x2 (fp32 NCHW [n_pairs, cin, h, w], the reference's input layout: data/dataset.py:196-203)
+ * -> bf16 NHWC [2*chunk, h, w, c_pad] with the T1 images first, then the T2 images. */
+int stcd_plan_add_input_pack(stcd_plan* plan, int dst_tensor, int cin);
+
+/* allocate the workspace, upload weights, encode TMA descriptors */
+int stcd_plan_finalize(stcd_plan* plan);
+
+/* Diagnostics / layer-wise parity tests: synchronous copy between a HOST buffer and activation
+ * tensor `tensor_id` (bf16 NHWC [img_mult*chunk, h, w, c]); to_device != 0 writes the tensor.
+ * `bytes` must equal the tensor's size. */
+int stcd_plan_tensor_copy(stcd_plan* plan, int tensor_id, void* host, int64_t bytes, int to_device);
+
+/* bytes of device memory the plan owns (workspace + weights) */
+int64_t stcd_plan_workspace_bytes(const stcd_plan* plan);
+/* number of kernels one stcd_forward of n_pairs launches (for bench.py's gpu_launches) */
+int64_t stcd_plan_launches(const stcd_plan* plan, int n_pairs);
+
+/* ------------------------------------------------------------------------------------------ */
+/* reference-facing entry points                                                               */
+
+/* Replaces net_G(x1, x2) (SiamUnet_diff.py:94-181 etc.).  x1, x2: device fp32 NCHW
+ * [n_pairs, cin, H, W]; outs[k]: device fp32 NCHW buffers for the plan's external outputs
+ * (outs[n_outs-1] = full-resolution logits, like the reference's list-valued forwards). */
+int stcd_forward(stcd_plan* plan, const float* x1, const float* x2, int n_pairs,
+                 float* const* outs, int n_outs, void* stream);
+
+/* stcd_forward with every op bracketed by CUDA events (a measurement pass, not the product
+ * path): op_ms[i] receives the device time of op i summed over the chunks; n_ops must equal the
+ * number of ops added to the plan. Synchronises the stream. */
+int stcd_forward_profile(stcd_plan* plan, const float* x1, const float* x2, int n_pairs,
+                         float* const* outs, int n_outs, void* stream, float* op_ms, int n_ops);
+
+/* Same, HOST (ideally pinned) buffers: H2D of each chunk overlaps the previous chunk's compute,
+ * logits are copied back. Blocks until the results are in `outs_host`. */
+int stcd_forward_host(stcd_plan* plan, const float* x1_host, const float* x2_host, int n_pairs,
+                      float* const* outs_host, int n_outs);
+
+/* Replaces `pred = argmax / sigmoid>thr / raw>=thr` + SegmentationMetric.addBatch
+ * (train_stcd.py:477,483,572-588; models/evaluator.py:108-113). cm_dev: int64[num_class^2]
+ * device accumulator, rows = ground truth, cols = prediction (train_stcd.py:576). */
+enum stcd_pred_kind {
+  STCD_PRED_ARGMAX2 = 0,    /* logits fp32 [n,2,h,w]  -> (l1 > l0)   (torch.argmax ties -> 0) */
+  STCD_PRED_SIGMOID_GT = 1, /* logits fp32 [n,1,h,w]  -> sigmoid(x) > thr   (train_stcd.py:477,483) */
+  STCD_PRED_RAW_GE = 2,     /* logits fp32 [n,1,h,w]  -> x >= thr           (evaluator.py:111) */
+  STCD_PRED_U8 = 3,         /* class ids uint8 */
+  STCD_PRED_I32 = 4,        /* class ids int32 (pred.int(), train_stcd.py:483) */
+  STCD_PRED_I64 = 5         /* class ids int64 */
+};
+enum stcd_label_kind { STCD_LABEL_I64 = 0, STCD_LABEL_U8 = 1, STCD_LABEL_I32 = 2 };
+
+int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const void* label,
+                             int label_kind, int64_t n_img, int64_t pix_per_img, int num_class,
+                             int64_t* cm_dev, uint8_t* pred_out_or_null, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STCD_B200_H_ */

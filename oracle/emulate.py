@@ -1,0 +1,105 @@
+"""CPU emulator of a lowered Program (stcd_b200/lowering.py).  TEST INFRASTRUCTURE.
+
+Executes the op list exactly as csrc/conv_gemm.cuh does — NHWC tensors holding bf16 values,
+K-programs walked entry by entry, fp32 accumulation, the epilogue's rounding points — so that
+``tests/`` can check the HOST-side lowering (weight packing, K-programs, BN folding, phases,
+virtual concat) against the reference without a GPU, and the GPU kernels against this emulator
+to fp32-accumulation-order accuracy.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from stcd_b200 import lowering as L
+
+
+def _bf16(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _gather(src: torch.Tensor, rows: torch.Tensor, cols: torch.Tensor) -> torch.Tensor:
+    """src [N,h,w,c]; rows [hg], cols [wg] (may be out of range -> zeros, like TMA OOB fill)."""
+    h, w = src.shape[1], src.shape[2]
+    rv = (rows >= 0) & (rows < h)
+    cv = (cols >= 0) & (cols < w)
+    g = src[:, rows.clamp(0, h - 1)][:, :, cols.clamp(0, w - 1)]
+    return g * (rv[:, None] & cv[None, :]).to(src.dtype)[None, :, :, None]
+
+
+def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[torch.Tensor], n_valid: int) -> None:
+    wmat = L.bf16_bits_to_f32(op.weights)                       # [w_rows, w_cols]
+    n_img = chunk if op.pair else op.img_mult * chunk
+    n_m = 2 if op.pair else 1
+    ho, wo = op.hg * op.osy, op.wg * op.osx
+    scale = torch.from_numpy(op.scale)
+    shift = torch.from_numpy(op.shift)
+    ii = torch.arange(op.hg)
+    jj = torch.arange(op.wg)
+    full = [torch.zeros(n_img, ho, wo, op.cout_pad) for _ in range(n_m)]
+    for ph in op.phases:
+        for m in range(n_m):
+            acc = torch.zeros(n_img, op.hg, op.wg, op.cout_pad)
+            for e in op.kprog[ph.k_begin: ph.k_begin + ph.k_count]:
+                si = e.src
+                src = T[op.srcs[si]]
+                off = (e.stream + m) * chunk
+                a = _gather(src[off: off + n_img, :, :, e.c0: e.c0 + op.kc], ii * op.src_sy[si] + e.dy,
+                            jj * op.src_sx[si] + e.dx)
+                acc += a @ wmat[ph.w_row: ph.w_row + op.cout_pad, e.wk: e.wk + op.kc].T
+            full[m][:, ph.oy::op.osy, ph.ox::op.osx] = acc
+    vs = []
+    for m in range(n_m):
+        v = full[m] * scale + shift
+        sl = slice(m * chunk, m * chunk + n_img)
+        if op.out_raw is not None:
+            T[op.out_raw][sl, :, :, : op.cout] = _bf16(v[..., : op.cout])
+        if op.scale2 is not None:
+            v = v * torch.from_numpy(op.scale2) + torch.from_numpy(op.shift2)
+        if op.res is not None:
+            v[..., : op.cout] = v[..., : op.cout] + T[op.res][sl, :, :, : op.cout]
+        if op.relu:
+            v = torch.relu(v)
+        if op.out0 is not None:
+            T[op.out0][sl, :, :, op.out0_coff: op.out0_coff + op.cout] = _bf16(v[..., : op.cout])
+        if op.out_ext >= 0:
+            ext[op.out_ext][:n_valid] = v[:n_valid, :, :, : op.cout].permute(0, 3, 1, 2)
+        if op.out_pool is not None:
+            q = torch.maximum(torch.maximum(v[:, 0::2, 0::2], v[:, 0::2, 1::2]),
+                              torch.maximum(v[:, 1::2, 0::2], v[:, 1::2, 1::2]))
+            T[op.out_pool][sl, :, :, : op.cout] = _bf16(q[..., : op.cout])
+        vs.append(v)
+    if op.out_diff is not None:
+        T[op.out_diff][:n_img, :, :, : op.cout] = _bf16((vs[0] - vs[1]).abs()[..., : op.cout])
+
+
+def run_program(prog: L.Program, x1: torch.Tensor, x2: torch.Tensor, chunk: int | None = None,
+                keep: Dict[str, torch.Tensor] | None = None) -> List[torch.Tensor]:
+    """x1, x2: fp32 NCHW [B, cin, H, W] -> list of fp32 NCHW external outputs."""
+    n = x1.shape[0]
+    chunk = chunk or n
+    outs = [torch.zeros(n, e.channels, e.h, e.w) for e in prog.ext]
+    for start in range(0, n, chunk):
+        nv = min(chunk, n - start)
+        T = {name: torch.zeros(t.mult * chunk, t.h, t.w, t.c) for name, t in prog.tensors.items()}
+        ext = [torch.zeros(chunk, e.channels, e.h, e.w) for e in prog.ext]
+        for op in prog.ops:
+            if isinstance(op, L.InputPackSpec):
+                dst = T[op.dst]
+                dst[:nv, :, :, : op.cin] = _bf16(x1[start: start + nv].permute(0, 2, 3, 1))
+                dst[chunk: chunk + nv, :, :, : op.cin] = _bf16(x2[start: start + nv].permute(0, 2, 3, 1))
+            elif isinstance(op, L.ConvSpec):
+                run_conv(op, T, chunk, ext, nv)
+            else:
+                run_aux(op, T, chunk, ext, nv)
+        for k in range(len(outs)):
+            outs[k][start: start + nv] = ext[k][:nv]
+        if keep is not None:
+            keep.update(T)
+    return outs
+
+
+def run_aux(op, T, chunk, ext, nv):  # extended by later op kinds
+    raise TypeError(f"emulator: unknown op {op!r}")

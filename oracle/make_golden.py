@@ -1,0 +1,66 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference from /root/reference.
+
+Run in the build container (the reference cannot travel to the GPU box):
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden
+Each fixture stores the recipe (model, seeds, shapes, gain) and the reference's fp32 logits;
+weights and inputs are re-derived from the seeds by stcd_b200/synth.py, so fixtures stay small.
+TEST INFRASTRUCTURE.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from oracle import refimport
+from stcd_b200 import synth
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# name -> (reference module path, class, ctor args, gain, batch, H, W)
+CASES = {
+    "siamunet_diff": ("models.SiamUnet_diff", "SiamUnet_diff", (3, 2), 0.8, 2, 48, 32),
+    "siamunet_conc": ("models.SiamUnet_conc", "SiamUnet_conc", (3, 2), 0.75, 2, 32, 48),
+}
+
+
+def reference_net(case: str):
+    mod, cls, args, gain, *_ = CASES[case]
+    net = getattr(refimport.ref_module(mod), cls)(*args).eval()
+    synth.randomize_(net, seed=synth.WEIGHT_SEED, gain=gain)
+    return net
+
+
+def main() -> None:
+    os.makedirs(OUT, exist_ok=True)
+    for case, (mod, cls, args, gain, b, h, w) in CASES.items():
+        net = reference_net(case)
+        x1, x2 = synth.image_pairs(b, h, w)
+        with torch.no_grad():
+            y = net(x1, x2)
+        ys = y if isinstance(y, (list, tuple)) else [y]
+        arrays = {f"out{i}": t.numpy() for i, t in enumerate(ys)}
+        np.savez_compressed(os.path.join(OUT, f"{case}.npz"), gain=gain, batch=b, h=h, w=w,
+                            weight_seed=synth.WEIGHT_SEED, data_seed=synth.DATA_SEED,
+                            x1_sum=float(x1.double().sum()), n_out=len(ys), **arrays)
+        print(case, [tuple(t.shape) for t in ys], "std", float(ys[-1].std()))
+    # evaluator: the reference's SegmentationMetric on seeded predictions/labels
+    SM = refimport.segmentation_metric_class()
+    g = torch.Generator().manual_seed(7)
+    pred = (torch.rand(3, 1, 40, 56, generator=g) < 0.3).int()
+    label = (torch.rand(3, 1, 40, 56, generator=g) < 0.1).long()
+    m = SM(2)
+    m.addBatch(pred, label)
+    pred2 = (torch.rand(3, 1, 40, 56, generator=g) < 0.6).int()
+    m.addBatch(pred2, label)
+    np.savez_compressed(os.path.join(OUT, "segmentation_metric.npz"), pred=pred.numpy().astype(np.uint8), pred2=pred2.numpy().astype(np.uint8),
+                        label=label.numpy().astype(np.uint8), cm=m.confusionMatrix.numpy(),
+                        f1=m.F1score().numpy(), iou=m.IntersectionOverUnion().numpy(),
+                        oa=m.OverallAccuracy().numpy(), precision=m.Precision().numpy(), recall=m.Recall().numpy(),
+                        fwiou=m.Frequency_Weighted_Intersection_over_Union().numpy())
+    print("segmentation_metric", m.confusionMatrix.tolist())
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""Functional fp32 CPU restatements of the reference forwards (eval mode).  TEST INFRASTRUCTURE.
+
+Each function takes the reference module's ``state_dict`` and the image pair and returns what
+the reference's ``forward(x1, x2)`` returns.  They are written against the reference's forward
+code (cited per function) and pinned by tests/test_oracle.py against fixtures generated from
+the real reference (oracle/make_golden.py).
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+
+def _bn(sd: SD, name: str, x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    return F.batch_norm(x, sd[f"{name}.running_mean"], sd[f"{name}.running_var"], sd[f"{name}.weight"],
+                        sd[f"{name}.bias"], training=False, eps=eps)
+
+
+# ------------------------------------------------------------------------------------------
+# FC-Siam-diff / FC-Siam-conc
+def _siam_encoder(sd: SD, x: torch.Tensor) -> List[torch.Tensor]:
+    """models/SiamUnet_diff.py:99-119 (one stream): returns [x12, x22, x33, x43, x4p]."""
+    def cbr(name, t):
+        return F.relu(_bn(sd, f"bn{name}", F.conv2d(t, sd[f"conv{name}.weight"], sd[f"conv{name}.bias"], padding=1)))
+    feats = []
+    for names in (("11", "12"), ("21", "22"), ("31", "32", "33"), ("41", "42", "43")):
+        for n in names:
+            x = cbr(n, x)          # Dropout2d is identity in eval mode
+        feats.append(x)
+        x = F.max_pool2d(x, kernel_size=2, stride=2)
+    feats.append(x)
+    return feats
+
+
+def siamunet_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor, fusion: str) -> torch.Tensor:
+    """models/SiamUnet_diff.py:94-181 (fusion='diff') / models/SiamUnet_conc.py:94-183 ('conc')."""
+    f1 = _siam_encoder(sd, x1)
+    f2 = _siam_encoder(sd, x2)
+    x = f2[4]                      # the decoder's bottleneck comes from image 2 only (:143,148)
+
+    def dcbr(name, t):
+        return F.relu(_bn(sd, f"bn{name}", F.conv_transpose2d(t, sd[f"conv{name}.weight"], sd[f"conv{name}.bias"],
+                                                               padding=1)))
+    for lvl, names in ((4, ("43d", "42d", "41d")), (3, ("33d", "32d", "31d")), (2, ("22d", "21d")), (1, ("12d",))):
+        a, b = f1[lvl - 1], f2[lvl - 1]
+        x = F.conv_transpose2d(x, sd[f"upconv{lvl}.weight"], sd[f"upconv{lvl}.bias"], stride=2, padding=1,
+                               output_padding=1)
+        x = F.pad(x, (0, a.size(3) - x.size(3), 0, a.size(2) - x.size(2)), mode="replicate")
+        x = torch.cat((x, torch.abs(a - b)), 1) if fusion == "diff" else torch.cat((x, a, b), 1)
+        for n in names:
+            x = dcbr(n, x)
+    return F.conv_transpose2d(x, sd["conv11d.weight"], sd["conv11d.bias"], padding=1)
+
+
+# ------------------------------------------------------------------------------------------
+# SNUNet-CD (ECAM)
+def _nested(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    """conv_block_nested.forward, models/SNUNet.py:17-26: the residual is conv1's PRE-BN output."""
+    ident = F.conv2d(x, sd[f"{name}.conv1.weight"], sd[f"{name}.conv1.bias"], padding=1)
+    y = F.relu(_bn(sd, f"{name}.bn1", ident))
+    y = _bn(sd, f"{name}.bn2", F.conv2d(y, sd[f"{name}.conv2.weight"], sd[f"{name}.conv2.bias"], padding=1))
+    return F.relu(y + ident)
+
+
+def _up(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    """up.forward, models/SNUNet.py:29-43: ConvTranspose2d(C, C, 2, stride=2)."""
+    return F.conv_transpose2d(x, sd[f"{name}.up.weight"], sd[f"{name}.up.bias"], stride=2)
+
+
+def _channel_attention(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    """ChannelAttention.forward, models/SNUNet.py:46-59 (1x1 convs without bias)."""
+    def mlp(v):
+        return F.conv2d(F.relu(F.conv2d(v, sd[f"{name}.fc1.weight"])), sd[f"{name}.fc2.weight"])
+    return torch.sigmoid(mlp(F.adaptive_avg_pool2d(x, 1)) + mlp(F.adaptive_max_pool2d(x, 1)))
+
+
+def snunet_forward(sd: SD, xA: torch.Tensor, xB: torch.Tensor) -> torch.Tensor:
+    """SNUNet_ECAM.forward, models/SNUNet.py:116-152."""
+    pool = lambda t: F.max_pool2d(t, 2, 2)  # noqa: E731
+    x0_0A = _nested(sd, "conv0_0", xA)
+    x1_0A = _nested(sd, "conv1_0", pool(x0_0A))
+    x2_0A = _nested(sd, "conv2_0", pool(x1_0A))
+    x3_0A = _nested(sd, "conv3_0", pool(x2_0A))
+    x0_0B = _nested(sd, "conv0_0", xB)
+    x1_0B = _nested(sd, "conv1_0", pool(x0_0B))
+    x2_0B = _nested(sd, "conv2_0", pool(x1_0B))
+    x3_0B = _nested(sd, "conv3_0", pool(x2_0B))
+    x4_0B = _nested(sd, "conv4_0", pool(x3_0B))     # stream A's level 4 is commented out upstream (:123)
+
+    x0_1 = _nested(sd, "conv0_1", torch.cat([x0_0A, x0_0B, _up(sd, "Up1_0", x1_0B)], 1))
+    x1_1 = _nested(sd, "conv1_1", torch.cat([x1_0A, x1_0B, _up(sd, "Up2_0", x2_0B)], 1))
+    x0_2 = _nested(sd, "conv0_2", torch.cat([x0_0A, x0_0B, x0_1, _up(sd, "Up1_1", x1_1)], 1))
+    x2_1 = _nested(sd, "conv2_1", torch.cat([x2_0A, x2_0B, _up(sd, "Up3_0", x3_0B)], 1))
+    x1_2 = _nested(sd, "conv1_2", torch.cat([x1_0A, x1_0B, x1_1, _up(sd, "Up2_1", x2_1)], 1))
+    x0_3 = _nested(sd, "conv0_3", torch.cat([x0_0A, x0_0B, x0_1, x0_2, _up(sd, "Up1_2", x1_2)], 1))
+    x3_1 = _nested(sd, "conv3_1", torch.cat([x3_0A, x3_0B, _up(sd, "Up4_0", x4_0B)], 1))
+    x2_2 = _nested(sd, "conv2_2", torch.cat([x2_0A, x2_0B, x2_1, _up(sd, "Up3_1", x3_1)], 1))
+    x1_3 = _nested(sd, "conv1_3", torch.cat([x1_0A, x1_0B, x1_1, x1_2, _up(sd, "Up2_2", x2_2)], 1))
+    x0_4 = _nested(sd, "conv0_4", torch.cat([x0_0A, x0_0B, x0_1, x0_2, x0_3, _up(sd, "Up1_3", x1_3)], 1))
+
+    out = torch.cat([x0_1, x0_2, x0_3, x0_4], 1)
+    intra = x0_1 + x0_2 + x0_3 + x0_4
+    ca1 = _channel_attention(sd, "ca1", intra)
+    out = _channel_attention(sd, "ca", out) * (out + ca1.repeat(1, 4, 1, 1))
+    return F.conv2d(out, sd["conv_final.weight"], sd["conv_final.bias"])

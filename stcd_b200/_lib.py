@@ -1,0 +1,160 @@
+"""ctypes binding of libstcd_b200.so (include/stcd_b200.h) and its in-tree nvcc build.
+
+The library is built IN-TREE (``stcd_b200/libstcd_b200.so``) so it travels to the GPU box with the
+repo snapshot.  There is no CPU fallback: if the library is missing, or no sm_100 device is
+visible, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO_DIR = PKG_DIR.parent
+LIB_PATH = PKG_DIR / "libstcd_b200.so"
+CSRC = PKG_DIR / "csrc"
+HEADER = REPO_DIR / "include" / "stcd_b200.h"
+
+MAX_SRC = 6
+MAX_PHASE = 4
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+]
+
+
+class StcdError(RuntimeError):
+    pass
+
+
+def _sources():
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [HEADER]
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    return any(s.stat().st_mtime > t for s in _sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> stcd_b200/libstcd_b200.so"""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB_PATH), str(CSRC / "stcd_b200.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise StcdError(f"nvcc failed ({' '.join(cmd)}):\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+class KEntry(C.Structure):
+    _fields_ = [("src", C.c_int16), ("dy", C.c_int16), ("dx", C.c_int16), ("c0", C.c_int16),
+                ("n_off", C.c_int32), ("wk", C.c_int32)]
+
+
+class Phase(C.Structure):
+    _fields_ = [("k_begin", C.c_int32), ("k_count", C.c_int32), ("oy", C.c_int32), ("ox", C.c_int32),
+                ("w_row", C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("n_src", C.c_int32),
+        ("src", C.c_int32 * MAX_SRC),
+        ("src_sy", C.c_int32 * MAX_SRC),
+        ("src_sx", C.c_int32 * MAX_SRC),
+        ("hg", C.c_int32), ("wg", C.c_int32),
+        ("img_mult", C.c_int32),
+        ("pair", C.c_int32),
+        ("weights", C.POINTER(C.c_uint16)),
+        ("w_rows", C.c_int32), ("w_cols", C.c_int32),
+        ("kc", C.c_int32),
+        ("n_tile", C.c_int32),
+        ("cout", C.c_int32),
+        ("cout_pad", C.c_int32),
+        ("n_phase", C.c_int32),
+        ("phase", Phase * MAX_PHASE),
+        ("kprog", C.POINTER(KEntry)),
+        ("n_kentry", C.c_int32),
+        ("osy", C.c_int32), ("osx", C.c_int32),
+        ("scale", C.POINTER(C.c_float)),
+        ("shift", C.POINTER(C.c_float)),
+        ("scale2", C.POINTER(C.c_float)),
+        ("shift2", C.POINTER(C.c_float)),
+        ("relu", C.c_int32),
+        ("res", C.c_int32),
+        ("out0", C.c_int32), ("out0_coff", C.c_int32),
+        ("out_raw", C.c_int32),
+        ("out_pool", C.c_int32),
+        ("out_diff", C.c_int32),
+        ("out_ext", C.c_int32),
+    ]
+
+
+# every symbol include/stcd_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("stcd_last_error", C.c_char_p, []),
+    ("stcd_abi_version", C.c_int, []),
+    ("stcd_device_count", C.c_int, []),
+    ("stcd_plan_create", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ("stcd_plan_destroy", None, [C.c_void_p]),
+    ("stcd_plan_add_tensor", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("stcd_plan_add_conv", C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
+    ("stcd_plan_add_input_pack", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("stcd_plan_finalize", C.c_int, [C.c_void_p]),
+    ("stcd_plan_tensor_copy", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int]),
+    ("stcd_plan_workspace_bytes", C.c_int64, [C.c_void_p]),
+    ("stcd_plan_launches", C.c_int64, [C.c_void_p, C.c_int]),
+    ("stcd_forward", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    ("stcd_forward_profile", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p,
+                                       C.POINTER(C.c_float), C.c_int]),
+    ("stcd_forward_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int]),
+    ("stcd_confusion_add_batch", C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
+                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libstcd_b200.so (building it if nvcc is available and it is stale/missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if needs_build():
+        try:
+            build()
+        except (StcdError, FileNotFoundError) as e:
+            if not LIB_PATH.exists():
+                raise StcdError(f"libstcd_b200.so is missing and could not be built: {e}") from e
+    handle = C.CDLL(str(LIB_PATH))
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(handle, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if handle.stcd_abi_version() != 1:
+        raise StcdError("libstcd_b200.so ABI version mismatch")
+    _lib = handle
+    return handle
+
+
+def check(code: int, what: str = "") -> int:
+    if code != 0:
+        msg = lib().stcd_last_error().decode("utf-8", "replace")
+        raise StcdError(f"{what}: {msg} (code {code})" if what else f"{msg} (code {code})")
+    return code
+
+
+def check_id(value: int, what: str = "") -> int:
+    if value < 0:
+        msg = lib().stcd_last_error().decode("utf-8", "replace")
+        raise StcdError(f"{what}: {msg} (code {-value})")
+    return value

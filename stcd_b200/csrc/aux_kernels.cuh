@@ -1,0 +1,215 @@
+// Bandwidth kernels around the GEMM path: input packing (fp32 NCHW -> bf16 NHWC) and the
+// evaluator's binarise + confusion-matrix histogram (K9).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/stcd_b200.h"
+
+namespace stcd {
+
+// x1, x2: fp32 NCHW [n_valid, cin, h, w] -> dst bf16 NHWC [2*chunk, h, w, 16]; channels >= cin
+// are zero; T1 images occupy [0, chunk), T2 images [chunk, 2*chunk). One thread per pixel:
+// reads are coalesced per channel plane, each thread writes one 32-byte pixel.
+__global__ void __launch_bounds__(256) input_pack_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                         __nv_bfloat16* __restrict__ dst, int chunk, int n_valid,
+                                                         int cin, int hw) {
+  const size_t total = static_cast<size_t>(2) * chunk * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / hw);
+    const int pix = static_cast<int>(i - static_cast<size_t>(n) * hw);
+    const int s = n / chunk, b = n - s * chunk;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.f;
+    if (b < n_valid) {
+      const float* src = (s ? x2 : x1) + static_cast<size_t>(b) * cin * hw + pix;
+      for (int c = 0; c < cin; ++c) v[c] = __ldg(src + static_cast<size_t>(c) * hw);
+    }
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + i * 16);
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K9: pred/label -> confusion matrix.  cm[g*K + p] += #{label == g && pred == p}
+// (rows = ground truth, cols = prediction: train_stcd.py:576-578).
+// Thread-local counters -> warp REDUX -> one shared-memory row per warp -> 64-bit global
+// atomics, one set per CTA.  Integer arithmetic throughout: bit-exact.
+
+__device__ __forceinline__ int binarise_sigmoid_gt(float x, float thr) {
+  // the reference's fp32 expression, evaluated with IEEE ops: sigmoid(x) > thr (train_stcd.py:477,483)
+  const float s = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+  return s > thr ? 1 : 0;
+}
+
+template <int PK>
+__device__ __forceinline__ int pred_at(const void* pred, size_t n, size_t i, size_t pix, float thr) {
+  if (PK == STCD_PRED_ARGMAX2) {
+    const float* p = static_cast<const float*>(pred) + n * 2 * pix + i;
+    return (__ldg(p + pix) > __ldg(p)) ? 1 : 0;  // torch.argmax: first max wins ties -> class 0
+  } else if (PK == STCD_PRED_SIGMOID_GT) {
+    return binarise_sigmoid_gt(__ldg(static_cast<const float*>(pred) + n * pix + i), thr);
+  } else if (PK == STCD_PRED_RAW_GE) {
+    return (__ldg(static_cast<const float*>(pred) + n * pix + i) >= thr) ? 1 : 0;
+  } else if (PK == STCD_PRED_U8) {
+    return __ldg(static_cast<const uint8_t*>(pred) + n * pix + i);
+  } else if (PK == STCD_PRED_I32) {
+    return __ldg(static_cast<const int32_t*>(pred) + n * pix + i);
+  } else {
+    return static_cast<int>(__ldg(static_cast<const long long*>(pred) + n * pix + i));
+  }
+}
+
+template <int PK>
+__device__ __forceinline__ void pred4_at(const void* pred, size_t n, size_t i, size_t pix, float thr, int (&out)[4]) {
+  // i % 4 == 0, pix % 4 == 0, base pointers 16-byte aligned
+  if (PK == STCD_PRED_ARGMAX2) {
+    const float* p = static_cast<const float*>(pred) + n * 2 * pix + i;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + pix));
+    out[0] = b.x > a.x;
+    out[1] = b.y > a.y;
+    out[2] = b.z > a.z;
+    out[3] = b.w > a.w;
+  } else if (PK == STCD_PRED_SIGMOID_GT || PK == STCD_PRED_RAW_GE) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(pred) + n * pix + i));
+    const float x[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = (PK == STCD_PRED_SIGMOID_GT) ? binarise_sigmoid_gt(x[j], thr) : (x[j] >= thr);
+  } else if (PK == STCD_PRED_U8) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(pred) + n * pix + i));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = (w >> (8 * j)) & 0xff;
+  } else if (PK == STCD_PRED_I32) {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(static_cast<const int32_t*>(pred) + n * pix + i));
+    out[0] = a.x;
+    out[1] = a.y;
+    out[2] = a.z;
+    out[3] = a.w;
+  } else {
+    const longlong2* p = reinterpret_cast<const longlong2*>(static_cast<const long long*>(pred) + n * pix + i);
+    const longlong2 a = __ldg(p), b = __ldg(p + 1);
+    out[0] = static_cast<int>(a.x);
+    out[1] = static_cast<int>(a.y);
+    out[2] = static_cast<int>(b.x);
+    out[3] = static_cast<int>(b.y);
+  }
+}
+
+template <int LK>
+__device__ __forceinline__ long long label_at(const void* label, size_t idx) {
+  if (LK == STCD_LABEL_I64) return __ldg(static_cast<const long long*>(label) + idx);
+  if (LK == STCD_LABEL_U8) return __ldg(static_cast<const uint8_t*>(label) + idx);
+  return __ldg(static_cast<const int32_t*>(label) + idx);
+}
+template <int LK>
+__device__ __forceinline__ void label4_at(const void* label, size_t idx, long long (&out)[4]) {
+  if (LK == STCD_LABEL_I64) {
+    const longlong2* p = reinterpret_cast<const longlong2*>(static_cast<const long long*>(label) + idx);
+    const longlong2 a = __ldg(p), b = __ldg(p + 1);
+    out[0] = a.x;
+    out[1] = a.y;
+    out[2] = b.x;
+    out[3] = b.y;
+  } else if (LK == STCD_LABEL_U8) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(label) + idx));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = (w >> (8 * j)) & 0xff;
+  } else {
+    const int4 a = __ldg(reinterpret_cast<const int4*>(static_cast<const int32_t*>(label) + idx));
+    out[0] = a.x;
+    out[1] = a.y;
+    out[2] = a.z;
+    out[3] = a.w;
+  }
+}
+
+// num_class == 2 fast path. `vec` = 1 when pix % 4 == 0 and all pointers are 16-byte aligned.
+template <int PK, int LK>
+__global__ void __launch_bounds__(256) confusion2_kernel(const void* __restrict__ pred, const void* __restrict__ label,
+                                                         size_t n_img, size_t pix, float thr, int vec,
+                                                         unsigned long long* __restrict__ cm,
+                                                         uint8_t* __restrict__ pred_out) {
+  uint32_t c[4] = {0, 0, 0, 0};
+  const size_t tid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t nthr = static_cast<size_t>(gridDim.x) * blockDim.x;
+  if (vec) {
+    const size_t qpi = pix >> 2, nq = n_img * qpi;
+    for (size_t q = tid; q < nq; q += nthr) {
+      const size_t n = q / qpi, i = (q - n * qpi) << 2;
+      int pr[4];
+      long long lb[4];
+      pred4_at<PK>(pred, n, i, pix, thr, pr);
+      label4_at<LK>(label, n * pix + i, lb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = (lb[j] >= 0) && (lb[j] < 2) && (pr[j] >= 0) && (pr[j] < 2);
+        const int bin = static_cast<int>(lb[j]) * 2 + pr[j];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) c[b] += (ok && bin == b) ? 1u : 0u;
+      }
+      if (pred_out != nullptr) {
+        const uint32_t w = (pr[0] & 0xff) | ((pr[1] & 0xff) << 8) | ((pr[2] & 0xff) << 16) | ((pr[3] & 0xff) << 24);
+        *reinterpret_cast<uint32_t*>(pred_out + n * pix + i) = w;
+      }
+    }
+  } else {
+    const size_t ne = n_img * pix;
+    for (size_t e = tid; e < ne; e += nthr) {
+      const size_t n = e / pix, i = e - n * pix;
+      const int pr = pred_at<PK>(pred, n, i, pix, thr);
+      const long long lb = label_at<LK>(label, e);
+      const bool ok = (lb >= 0) && (lb < 2) && (pr >= 0) && (pr < 2);
+      const int bin = static_cast<int>(lb) * 2 + pr;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) c[b] += (ok && bin == b) ? 1u : 0u;
+      if (pred_out != nullptr) pred_out[e] = static_cast<uint8_t>(pr);
+    }
+  }
+  __shared__ uint32_t wsum[8][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const uint32_t s = __reduce_add_sync(0xffffffffu, c[b]);
+    if (lane == 0) wsum[warp][b] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    unsigned long long s = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) s += wsum[w][threadIdx.x];
+    if (s) atomicAdd(cm + threadIdx.x, s);
+  }
+}
+
+// generic num_class <= 32 (class-id predictions only): shared-memory histogram per CTA.
+template <int PK, int LK>
+__global__ void __launch_bounds__(256) confusionK_kernel(const void* __restrict__ pred, const void* __restrict__ label,
+                                                         size_t n_img, size_t pix, int K,
+                                                         unsigned long long* __restrict__ cm) {
+  __shared__ uint32_t hist[32 * 32];
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const size_t ne = n_img * pix;
+  for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < ne;
+       e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t n = e / pix, i = e - n * pix;
+    const int pr = pred_at<PK>(pred, n, i, pix, 0.f);
+    const long long lb = label_at<LK>(label, e);
+    if (lb >= 0 && lb < K && pr >= 0 && pr < K) atomicAdd(&hist[static_cast<int>(lb) * K + pr], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x)
+    if (hist[i]) atomicAdd(cm + i, static_cast<unsigned long long>(hist[i]));
+}
+
+}  // namespace stcd

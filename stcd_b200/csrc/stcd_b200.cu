@@ -1,0 +1,701 @@
+// libstcd_b200.so — plan executor + C-ABI (include/stcd_b200.h).
+//
+// A plan is a list of fused ops over NHWC bf16 activation tensors living in one device
+// workspace.  The host side (stcd_b200/lowering.py) lowers a reference nn.Module state_dict
+// into this list; this file owns memory, TMA descriptors and launches.  No CPU fallback: every
+// entry point that computes needs an sm_100 device and fails loudly without one.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/stcd_b200.h"
+#include "aux_kernels.cuh"
+#include "conv_gemm.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      return fail(STCD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+CUtensorMapSwizzle swizzle_for_kc(int kc) {
+  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Tensor {
+  int mult, h, w, c, dtype;
+  size_t bytes = 0, offset = 0;
+  void* ptr = nullptr;
+};
+
+struct ConvOp {
+  stcd_conv_desc d;
+  std::vector<uint16_t> weights;
+  std::vector<stcd_kentry> kprog;
+  std::vector<float> scale, shift, scale2, shift2;
+  // device side
+  size_t w_off = 0, k_off = 0, s_off = 0;  // offsets in the constant arena
+  stcd::TmapPack tm;
+  stcd::ConvParams p;
+  dim3 grid;
+  size_t smem = 0;
+  int mt = 1;
+};
+
+struct PackOp {
+  int dst, cin;
+};
+
+struct Op {
+  int kind;  // 0 conv, 1 input pack
+  int idx;
+};
+
+}  // namespace
+
+struct stcd_plan {
+  int device = 0;
+  int chunk = 0;
+  bool finalized = false;
+  std::vector<Tensor> tensors;
+  std::vector<ConvOp> convs;
+  std::vector<PackOp> packs;
+  std::vector<Op> ops;
+  uint8_t* workspace = nullptr;
+  size_t workspace_bytes = 0;
+  uint8_t* arena = nullptr;  // weights, K-programs, scale/shift
+  size_t arena_bytes = 0;
+  int n_ext = 0;
+  int in_c = 0, in_h = 0, in_w = 0;
+  std::vector<size_t> ext_elems;  // per external output: elements per image
+  // host-buffer path
+  cudaStream_t s_copy = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  float* stage_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  std::vector<float*> stage_out[2];
+};
+
+namespace {
+
+int check_sm100(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(STCD_ERR_NO_DEVICE, "no CUDA device visible: libstcd_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= n) return fail(STCD_ERR_INVALID, "device %d out of range (%d visible)", device, n);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(STCD_ERR_NO_DEVICE, "device %d is sm_%d%d; libstcd_b200 is built for sm_100a only", device, prop.major,
+                prop.minor);
+  return STCD_OK;
+}
+
+int encode_act_map(CUtensorMap* m, void* base, int n, int h, int w, int c, int kc, int sx, int sy) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(STCD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t gstr[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(stcd::kTileW * sx), (cuuint32_t)(stcd::kTileH * sy), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_for_kc(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(STCD_ERR_CUDA, "cuTensorMapEncodeTiled(act n=%d h=%d w=%d c=%d kc=%d s=%d,%d) -> %d", n, h, w, c, kc,
+                sx, sy, (int)r);
+  return STCD_OK;
+}
+
+int encode_w_map(CUtensorMap* m, void* base, int rows, int cols, int kc, int n_tile) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(STCD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)n_tile};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_for_kc(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(STCD_ERR_CUDA, "cuTensorMapEncodeTiled(weights %dx%d kc=%d n=%d) -> %d", rows, cols, kc, n_tile,
+                (int)r);
+  return STCD_OK;
+}
+
+bool valid_tensor(const stcd_plan* p, int id) { return id >= 0 && id < (int)p->tensors.size(); }
+
+int smem_budget_env() {
+  const char* e = getenv("STCD_SMEM_BUDGET");
+  return e ? atoi(e) : 0;
+}
+
+int launch_conv(const stcd_plan* plan, const ConvOp& op, int n_valid, float* const* outs, cudaStream_t st) {
+  stcd::ConvParams p = op.p;
+  p.n_valid = n_valid;
+  if (op.d.out_ext >= 0) {
+    p.out_f32 = outs[op.d.out_ext];
+    if (!p.out_f32) return fail(STCD_ERR_INVALID, "external output %d is NULL", op.d.out_ext);
+  }
+  if (op.mt == 2)
+    stcd::conv_gemm_kernel<2><<<op.grid, 128, op.smem, st>>>(op.tm, p);
+  else
+    stcd::conv_gemm_kernel<1><<<op.grid, 128, op.smem, st>>>(op.tm, p);
+  CUDA_TRY(cudaGetLastError());
+  (void)plan;
+  return STCD_OK;
+}
+
+int run_chunk(stcd_plan* plan, const float* x1, const float* x2, int n_valid, float* const* outs, cudaStream_t st,
+              cudaEvent_t* ev = nullptr) {
+  int op_i = 0;
+  if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
+  for (const Op& o : plan->ops) {
+    if (o.kind == 0) {
+      int r = launch_conv(plan, plan->convs[o.idx], n_valid, outs, st);
+      if (r) return r;
+    } else {
+      const PackOp& k = plan->packs[o.idx];
+      const Tensor& t = plan->tensors[k.dst];
+      const int hw = t.h * t.w;
+      const size_t total = (size_t)2 * plan->chunk * hw;
+      const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+      stcd::input_pack_kernel<<<blocks, 256, 0, st>>>(x1, x2, (__nv_bfloat16*)t.ptr, plan->chunk, n_valid, k.cin, hw);
+      CUDA_TRY(cudaGetLastError());
+    }
+    ++op_i;
+    if (ev) CUDA_TRY(cudaEventRecord(ev[op_i], st));
+  }
+  return STCD_OK;
+}
+
+}  // namespace
+
+// ================================================================================ C-ABI
+extern "C" {
+
+const char* stcd_last_error(void) { return g_err.c_str(); }
+int stcd_abi_version(void) { return STCD_ABI_VERSION; }
+
+int stcd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ++ok;
+  }
+  return ok;
+}
+
+int stcd_plan_create(int device, int chunk_pairs, stcd_plan** out) {
+  if (!out) return fail(STCD_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (chunk_pairs < 1 || chunk_pairs > 4096) return fail(STCD_ERR_INVALID, "chunk_pairs %d out of range", chunk_pairs);
+  int r = check_sm100(device);
+  if (r) return r;
+  stcd_plan* p = new stcd_plan();
+  p->device = device;
+  p->chunk = chunk_pairs;
+  *out = p;
+  return STCD_OK;
+}
+
+void stcd_plan_destroy(stcd_plan* plan) {
+  if (!plan) return;
+  cudaSetDevice(plan->device);
+  if (plan->workspace) cudaFree(plan->workspace);
+  if (plan->arena) cudaFree(plan->arena);
+  for (int b = 0; b < 2; ++b) {
+    for (int s = 0; s < 2; ++s)
+      if (plan->stage_in[b][s]) cudaFree(plan->stage_in[b][s]);
+    for (float* q : plan->stage_out[b])
+      if (q) cudaFree(q);
+    if (plan->ev_h2d[b]) cudaEventDestroy(plan->ev_h2d[b]);
+    if (plan->ev_comp[b]) cudaEventDestroy(plan->ev_comp[b]);
+    if (plan->ev_d2h[b]) cudaEventDestroy(plan->ev_d2h[b]);
+  }
+  if (plan->s_copy) cudaStreamDestroy(plan->s_copy);
+  if (plan->s_comp) cudaStreamDestroy(plan->s_comp);
+  if (plan->s_d2h) cudaStreamDestroy(plan->s_d2h);
+  delete plan;
+}
+
+int stcd_plan_add_tensor(stcd_plan* plan, int img_mult, int h, int w, int c, int dtype) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (img_mult < 1 || img_mult > 2 || h < 1 || w < 1 || c < 8 || (c % 8) != 0 || dtype != STCD_BF16)
+    return -fail(STCD_ERR_INVALID, "bad tensor decl mult=%d h=%d w=%d c=%d dtype=%d (c must be a multiple of 8, bf16)",
+                 img_mult, h, w, c, dtype);
+  Tensor t;
+  t.mult = img_mult;
+  t.h = h;
+  t.w = w;
+  t.c = c;
+  t.dtype = dtype;
+  t.bytes = (size_t)img_mult * plan->chunk * h * w * c * 2;
+  plan->tensors.push_back(t);
+  return (int)plan->tensors.size() - 1;
+}
+
+int stcd_plan_add_input_pack(stcd_plan* plan, int dst_tensor, int cin) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, dst_tensor)) return -fail(STCD_ERR_INVALID, "bad dst tensor %d", dst_tensor);
+  const Tensor& t = plan->tensors[dst_tensor];
+  if (t.mult != 2 || t.c != 16 || cin < 1 || cin > 16)
+    return -fail(STCD_ERR_INVALID, "input pack needs a [2*chunk, h, w, 16] tensor and cin <= 16 (got mult=%d c=%d cin=%d)",
+                 t.mult, t.c, cin);
+  plan->packs.push_back({dst_tensor, cin});
+  plan->ops.push_back({1, (int)plan->packs.size() - 1});
+  plan->in_c = cin;
+  plan->in_h = t.h;
+  plan->in_w = t.w;
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
+  if (!plan || !d) return -fail(STCD_ERR_STATE, "plan/desc is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (d->n_src < 1 || d->n_src > STCD_MAX_SRC) return -fail(STCD_ERR_INVALID, "n_src %d", d->n_src);
+  if (d->kc != 16 && d->kc != 32 && d->kc != 64) return -fail(STCD_ERR_INVALID, "kc %d must be 16/32/64", d->kc);
+  if (d->n_tile < 16 || d->n_tile > 256 || d->n_tile % 16) return -fail(STCD_ERR_INVALID, "n_tile %d", d->n_tile);
+  if (d->cout < 1 || d->cout_pad < d->cout || d->cout_pad % d->n_tile)
+    return -fail(STCD_ERR_INVALID, "cout %d / cout_pad %d / n_tile %d", d->cout, d->cout_pad, d->n_tile);
+  if (d->n_phase < 1 || d->n_phase > STCD_MAX_PHASE) return -fail(STCD_ERR_INVALID, "n_phase %d", d->n_phase);
+  if (!d->weights || !d->kprog || !d->scale || !d->shift) return -fail(STCD_ERR_INVALID, "NULL weights/kprog/scale/shift");
+  if ((d->scale2 == nullptr) != (d->shift2 == nullptr)) return -fail(STCD_ERR_INVALID, "scale2/shift2 must come together");
+  if (d->w_rows < d->n_phase * d->cout_pad || d->w_cols < d->kc || d->w_cols % 8)
+    return -fail(STCD_ERR_INVALID, "weight matrix %dx%d too small", d->w_rows, d->w_cols);
+  if (d->img_mult < 1 || d->img_mult > 2) return -fail(STCD_ERR_INVALID, "img_mult %d", d->img_mult);
+  if (d->pair && d->img_mult != 1) return -fail(STCD_ERR_INVALID, "pair ops iterate over chunk_pairs images (img_mult=1)");
+  if (d->out_diff >= 0 && !d->pair) return -fail(STCD_ERR_INVALID, "out_diff needs pair=1");
+  const int mt = d->pair ? 2 : 1;
+  if (mt * d->n_tile > 512) return -fail(STCD_ERR_INVALID, "accumulators need %d TMEM columns (> 512)", mt * d->n_tile);
+  if (d->hg < 1 || d->wg < 1 || d->osy < 1 || d->osx < 1) return -fail(STCD_ERR_INVALID, "bad grid/stride");
+  for (int s = 0; s < d->n_src; ++s) {
+    if (!valid_tensor(plan, d->src[s])) return -fail(STCD_ERR_INVALID, "bad src tensor %d", d->src[s]);
+    if (d->src_sy[s] < 1 || d->src_sy[s] > 8 || d->src_sx[s] < 1 || d->src_sx[s] > 8)
+      return -fail(STCD_ERR_INVALID, "bad src stride");
+  }
+  const int ho = d->hg * d->osy, wo = d->wg * d->osx;
+  const int out_imgs = (d->pair ? 2 : d->img_mult);
+  auto check_out = [&](int id, int hh, int ww, int coff, int mult, const char* name) -> int {
+    if (id < 0) return 0;
+    if (!valid_tensor(plan, id)) return fail(STCD_ERR_INVALID, "bad %s tensor %d", name, id);
+    const Tensor& t = plan->tensors[id];
+    if (t.h != hh || t.w != ww || t.c < coff + d->cout || t.mult != mult)
+      return fail(STCD_ERR_INVALID, "%s tensor %d is [%d*chunk,%d,%d,%d], op writes [%d*chunk,%d,%d,%d+%d]", name, id,
+                  t.mult, t.h, t.w, t.c, mult, hh, ww, coff, d->cout);
+    return 0;
+  };
+  const bool bf16_out = d->out0 >= 0 || d->out_raw >= 0 || d->out_pool >= 0 || d->out_diff >= 0 || d->res >= 0;
+  if (bf16_out && (d->cout % 8)) return -fail(STCD_ERR_INVALID, "bf16 outputs need cout %% 8 == 0 (cout=%d)", d->cout);
+  if (d->out0_coff % 8) return -fail(STCD_ERR_INVALID, "out0_coff must be a multiple of 8");
+  if (check_out(d->out0, ho, wo, d->out0_coff, out_imgs, "out0")) return -STCD_ERR_INVALID;
+  if (check_out(d->out_raw, ho, wo, 0, out_imgs, "out_raw")) return -STCD_ERR_INVALID;
+  if (check_out(d->res, ho, wo, 0, out_imgs, "res")) return -STCD_ERR_INVALID;
+  if (d->out_pool >= 0) {
+    if (d->osy != 1 || d->osx != 1 || d->n_phase != 1 || (ho % 2) || (wo % 2))
+      return -fail(STCD_ERR_INVALID, "fused 2x2 max-pool needs a stride-1 single-phase op with even output dims");
+    if (check_out(d->out_pool, ho / 2, wo / 2, 0, out_imgs, "out_pool")) return -STCD_ERR_INVALID;
+  }
+  if (check_out(d->out_diff, ho, wo, 0, 1, "out_diff")) return -STCD_ERR_INVALID;
+  if (d->out_ext >= 0 && (d->img_mult != 1 || d->pair)) return -fail(STCD_ERR_INVALID, "external outputs need img_mult=1");
+  if (d->n_kentry < 1) return -fail(STCD_ERR_INVALID, "empty K-program");
+  for (int ph = 0; ph < d->n_phase; ++ph) {
+    const stcd_phase& f = d->phase[ph];
+    if (f.k_begin < 0 || f.k_count < 1 || f.k_count > stcd::kMaxKProg || f.k_begin + f.k_count > d->n_kentry)
+      return -fail(STCD_ERR_INVALID, "phase %d K-program slice [%d,+%d) out of range", ph, f.k_begin, f.k_count);
+    if (f.oy < 0 || f.oy >= d->osy || f.ox < 0 || f.ox >= d->osx || f.w_row < 0 || f.w_row + d->cout_pad > d->w_rows)
+      return -fail(STCD_ERR_INVALID, "phase %d offsets out of range", ph);
+  }
+  for (int i = 0; i < d->n_kentry; ++i) {
+    const stcd_kentry& e = d->kprog[i];
+    if (e.src < 0 || e.src >= d->n_src) return -fail(STCD_ERR_INVALID, "kentry %d: src %d", i, e.src);
+    const Tensor& t = plan->tensors[d->src[e.src]];
+    if (e.c0 < 0 || e.c0 + d->kc > t.c) return -fail(STCD_ERR_INVALID, "kentry %d: channels [%d,+%d) of %d", i, e.c0, d->kc, t.c);
+    if (e.wk < 0 || e.wk + d->kc > d->w_cols) return -fail(STCD_ERR_INVALID, "kentry %d: wk %d", i, e.wk);
+    const int top = (d->pair ? 1 : d->img_mult - 1) * plan->chunk + plan->chunk - 1 + e.n_off;
+    if (e.n_off < 0 || top >= t.mult * plan->chunk) return -fail(STCD_ERR_INVALID, "kentry %d: image offset %d overruns source", i, e.n_off);
+  }
+
+  ConvOp op;
+  op.d = *d;
+  op.mt = mt;
+  op.weights.assign(d->weights, d->weights + (size_t)d->w_rows * d->w_cols);
+  op.kprog.assign(d->kprog, d->kprog + d->n_kentry);
+  op.scale.assign(d->scale, d->scale + d->cout_pad);
+  op.shift.assign(d->shift, d->shift + d->cout_pad);
+  if (d->scale2) {
+    op.scale2.assign(d->scale2, d->scale2 + d->cout_pad);
+    op.shift2.assign(d->shift2, d->shift2 + d->cout_pad);
+  }
+  op.d.weights = nullptr;
+  op.d.kprog = nullptr;
+  op.d.scale = op.d.shift = op.d.scale2 = op.d.shift2 = nullptr;
+  if (d->out_ext >= 0) {
+    plan->n_ext = std::max(plan->n_ext, d->out_ext + 1);
+    if ((int)plan->ext_elems.size() < plan->n_ext) plan->ext_elems.resize(plan->n_ext, 0);
+    plan->ext_elems[d->out_ext] = (size_t)d->cout * ho * wo;
+  }
+  plan->convs.push_back(std::move(op));
+  plan->ops.push_back({0, (int)plan->convs.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_finalize(stcd_plan* plan) {
+  if (!plan) return fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return fail(STCD_ERR_STATE, "plan already finalized");
+  CUDA_TRY(cudaSetDevice(plan->device));
+  // ---- activation workspace
+  size_t off = 0;
+  for (Tensor& t : plan->tensors) {
+    t.offset = off;
+    off += round_up(t.bytes, 1024);
+  }
+  plan->workspace_bytes = std::max<size_t>(off, 1024);
+  CUDA_TRY(cudaMalloc(&plan->workspace, plan->workspace_bytes));
+  CUDA_TRY(cudaMemset(plan->workspace, 0, plan->workspace_bytes));
+  for (Tensor& t : plan->tensors) t.ptr = plan->workspace + t.offset;
+  // ---- constant arena
+  size_t aoff = 0;
+  for (ConvOp& op : plan->convs) {
+    op.w_off = aoff;
+    aoff += round_up(op.weights.size() * 2, 1024);
+    op.k_off = aoff;
+    aoff += round_up(op.kprog.size() * sizeof(stcd_kentry), 256);
+    op.s_off = aoff;
+    aoff += round_up((size_t)op.d.cout_pad * 4 * 4, 256);
+  }
+  plan->arena_bytes = std::max<size_t>(aoff, 1024);
+  CUDA_TRY(cudaMalloc(&plan->arena, plan->arena_bytes));
+  std::vector<uint8_t> host(plan->arena_bytes, 0);
+  for (ConvOp& op : plan->convs) {
+    memcpy(host.data() + op.w_off, op.weights.data(), op.weights.size() * 2);
+    memcpy(host.data() + op.k_off, op.kprog.data(), op.kprog.size() * sizeof(stcd_kentry));
+    const size_t n = op.d.cout_pad;
+    memcpy(host.data() + op.s_off, op.scale.data(), n * 4);
+    memcpy(host.data() + op.s_off + n * 4, op.shift.data(), n * 4);
+    if (!op.scale2.empty()) {
+      memcpy(host.data() + op.s_off + n * 8, op.scale2.data(), n * 4);
+      memcpy(host.data() + op.s_off + n * 12, op.shift2.data(), n * 4);
+    }
+  }
+  CUDA_TRY(cudaMemcpy(plan->arena, host.data(), plan->arena_bytes, cudaMemcpyHostToDevice));
+
+  static_assert(sizeof(stcd_kentry) == sizeof(stcd::KEntry), "kentry layout");
+  CUDA_TRY(cudaFuncSetAttribute(stcd::conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192));
+  CUDA_TRY(cudaFuncSetAttribute(stcd::conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192));
+
+  const int budget_env = smem_budget_env();
+  for (ConvOp& op : plan->convs) {
+    const stcd_conv_desc& d = op.d;
+    memset(&op.tm, 0, sizeof(op.tm));
+    for (int s = 0; s < d.n_src; ++s) {
+      const Tensor& t = plan->tensors[d.src[s]];
+      int r = encode_act_map(&op.tm.src[s], t.ptr, t.mult * plan->chunk, t.h, t.w, t.c, d.kc, d.src_sx[s], d.src_sy[s]);
+      if (r) return r;
+    }
+    int r = encode_w_map(&op.tm.w, plan->arena + op.w_off, d.w_rows, d.w_cols, d.kc, d.n_tile);
+    if (r) return r;
+
+    stcd::ConvParams& p = op.p;
+    memset(&p, 0, sizeof(p));
+    p.hg = d.hg;
+    p.wg = d.wg;
+    p.tiles_x = (d.wg + stcd::kTileW - 1) / stcd::kTileW;
+    p.tiles_y = (d.hg + stcd::kTileH - 1) / stcd::kTileH;
+    p.n_img = (d.pair ? 1 : d.img_mult) * plan->chunk;
+    p.pair_off = d.pair ? plan->chunk : 0;
+    for (int s = 0; s < d.n_src; ++s) {
+      p.src_sy[s] = d.src_sy[s];
+      p.src_sx[s] = d.src_sx[s];
+    }
+    p.osy = d.osy;
+    p.osx = d.osx;
+    p.ho = d.hg * d.osy;
+    p.wo = d.wg * d.osx;
+    p.n_phase = d.n_phase;
+    int kmin = 1 << 30;
+    for (int ph = 0; ph < d.n_phase; ++ph) {
+      p.phase[ph] = {d.phase[ph].k_begin, d.phase[ph].k_count, d.phase[ph].oy, d.phase[ph].ox, d.phase[ph].w_row};
+      kmin = std::min(kmin, d.phase[ph].k_count);
+    }
+    p.kprog = reinterpret_cast<const stcd::KEntry*>(plan->arena + op.k_off);
+    p.kc = d.kc;
+    p.n_tile = d.n_tile;
+    p.cout = d.cout;
+    p.a_bytes = 128u * d.kc * 2;
+    p.b_bytes = (uint32_t)d.n_tile * d.kc * 2;
+    p.sub_bytes = op.mt * p.a_bytes + (uint32_t)round_up(p.b_bytes, 1024);
+    p.group = std::max(1, std::min(64 / d.kc, kmin));
+    const size_t stage_bytes = (size_t)p.sub_bytes * p.group;
+    size_t budget = budget_env > 0 ? (size_t)budget_env : (p.sub_bytes <= 16384 ? 64 * 1024 : 100 * 1024);
+    int stages = (int)(budget / stage_bytes);
+    stages = std::max(2, std::min(stages, 8));
+    p.stages = stages;
+    op.smem = stage_bytes * stages + 1024;
+    if (op.smem > 227 * 1024 - 8192) return fail(STCD_ERR_INVALID, "conv op needs %zu B of shared memory", op.smem);
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(op.mt * d.n_tile)) cols <<= 1;
+    p.tmem_cols = cols;
+    const float* sc = reinterpret_cast<const float*>(plan->arena + op.s_off);
+    p.scale = sc;
+    p.shift = sc + d.cout_pad;
+    if (!op.scale2.empty()) {
+      p.scale2 = sc + 2 * d.cout_pad;
+      p.shift2 = sc + 3 * d.cout_pad;
+    }
+    p.relu = d.relu;
+    if (d.res >= 0) {
+      p.res = (const __nv_bfloat16*)plan->tensors[d.res].ptr;
+      p.res_c = plan->tensors[d.res].c;
+    }
+    if (d.out0 >= 0) {
+      p.out0 = (__nv_bfloat16*)plan->tensors[d.out0].ptr;
+      p.out0_c = plan->tensors[d.out0].c;
+      p.out0_coff = d.out0_coff;
+    }
+    if (d.out_raw >= 0) {
+      p.out_raw = (__nv_bfloat16*)plan->tensors[d.out_raw].ptr;
+      p.out_raw_c = plan->tensors[d.out_raw].c;
+    }
+    if (d.out_pool >= 0) {
+      p.out_pool = (__nv_bfloat16*)plan->tensors[d.out_pool].ptr;
+      p.out_pool_c = plan->tensors[d.out_pool].c;
+    }
+    if (d.out_diff >= 0) {
+      p.out_diff = (__nv_bfloat16*)plan->tensors[d.out_diff].ptr;
+      p.out_diff_c = plan->tensors[d.out_diff].c;
+    }
+    op.grid = dim3((unsigned)(p.tiles_x * p.tiles_y * p.n_img * d.n_phase), (unsigned)(d.cout_pad / d.n_tile), 1);
+  }
+  plan->finalized = true;
+  return STCD_OK;
+}
+
+int stcd_plan_tensor_copy(stcd_plan* plan, int tensor_id, void* host, int64_t bytes, int to_device) {
+  if (!plan || !plan->finalized) return fail(STCD_ERR_STATE, "plan not finalized");
+  if (!valid_tensor(plan, tensor_id) || !host) return fail(STCD_ERR_INVALID, "bad tensor id %d / NULL host buffer", tensor_id);
+  const Tensor& t = plan->tensors[tensor_id];
+  if (bytes != (int64_t)t.bytes) return fail(STCD_ERR_INVALID, "tensor %d has %zu bytes, got %lld", tensor_id, t.bytes, (long long)bytes);
+  CUDA_TRY(cudaSetDevice(plan->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (to_device)
+    CUDA_TRY(cudaMemcpy(t.ptr, host, t.bytes, cudaMemcpyHostToDevice));
+  else
+    CUDA_TRY(cudaMemcpy(host, t.ptr, t.bytes, cudaMemcpyDeviceToHost));
+  return STCD_OK;
+}
+
+int64_t stcd_plan_workspace_bytes(const stcd_plan* plan) {
+  return plan ? (int64_t)(plan->workspace_bytes + plan->arena_bytes) : 0;
+}
+
+int64_t stcd_plan_launches(const stcd_plan* plan, int n_pairs) {
+  if (!plan || n_pairs < 1) return 0;
+  const int64_t chunks = (n_pairs + plan->chunk - 1) / plan->chunk;
+  return chunks * (int64_t)plan->ops.size();
+}
+
+int stcd_forward(stcd_plan* plan, const float* x1, const float* x2, int n_pairs, float* const* outs, int n_outs,
+                 void* stream) {
+  if (!plan || !plan->finalized) return fail(STCD_ERR_STATE, "plan not finalized");
+  if (!x1 || !x2 || n_pairs < 0) return fail(STCD_ERR_INVALID, "bad inputs");
+  if (n_outs != plan->n_ext || (n_outs > 0 && !outs)) return fail(STCD_ERR_INVALID, "plan has %d external outputs, got %d", plan->n_ext, n_outs);
+  CUDA_TRY(cudaSetDevice(plan->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t in_elems = (size_t)plan->in_c * plan->in_h * plan->in_w;
+  std::vector<float*> o(n_outs);
+  for (int start = 0; start < n_pairs; start += plan->chunk) {
+    const int nv = std::min(plan->chunk, n_pairs - start);
+    for (int k = 0; k < n_outs; ++k) o[k] = outs[k] ? outs[k] + (size_t)start * plan->ext_elems[k] : nullptr;
+    int r = run_chunk(plan, x1 + (size_t)start * in_elems, x2 + (size_t)start * in_elems, nv, o.data(), st);
+    if (r) return r;
+  }
+  return STCD_OK;
+}
+
+int stcd_forward_profile(stcd_plan* plan, const float* x1, const float* x2, int n_pairs, float* const* outs, int n_outs,
+                         void* stream, float* op_ms, int n_ops) {
+  if (!plan || !plan->finalized) return fail(STCD_ERR_STATE, "plan not finalized");
+  if (!x1 || !x2 || n_pairs < 0 || !op_ms) return fail(STCD_ERR_INVALID, "bad inputs");
+  if (n_ops != (int)plan->ops.size()) return fail(STCD_ERR_INVALID, "plan has %zu ops, got %d", plan->ops.size(), n_ops);
+  if (n_outs != plan->n_ext || (n_outs > 0 && !outs)) return fail(STCD_ERR_INVALID, "plan has %d external outputs, got %d", plan->n_ext, n_outs);
+  CUDA_TRY(cudaSetDevice(plan->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t in_elems = (size_t)plan->in_c * plan->in_h * plan->in_w;
+  std::vector<cudaEvent_t> ev(n_ops + 1);
+  for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+  for (int i = 0; i < n_ops; ++i) op_ms[i] = 0.f;
+  std::vector<float*> o(n_outs);
+  int rc = STCD_OK;
+  for (int start = 0; start < n_pairs && rc == STCD_OK; start += plan->chunk) {
+    const int nv = std::min(plan->chunk, n_pairs - start);
+    for (int k = 0; k < n_outs; ++k) o[k] = outs[k] ? outs[k] + (size_t)start * plan->ext_elems[k] : nullptr;
+    rc = run_chunk(plan, x1 + (size_t)start * in_elems, x2 + (size_t)start * in_elems, nv, o.data(), st, ev.data());
+    if (rc) break;
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+      rc = fail(STCD_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    for (int i = 0; i < n_ops; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      op_ms[i] += ms;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
+int stcd_forward_host(stcd_plan* plan, const float* x1h, const float* x2h, int n_pairs, float* const* outs_host,
+                      int n_outs) {
+  if (!plan || !plan->finalized) return fail(STCD_ERR_STATE, "plan not finalized");
+  if (!x1h || !x2h || n_pairs < 0) return fail(STCD_ERR_INVALID, "bad inputs");
+  if (n_outs != plan->n_ext || (n_outs > 0 && !outs_host)) return fail(STCD_ERR_INVALID, "plan has %d external outputs, got %d", plan->n_ext, n_outs);
+  CUDA_TRY(cudaSetDevice(plan->device));
+  const size_t in_elems = (size_t)plan->in_c * plan->in_h * plan->in_w;
+  const size_t in_bytes = in_elems * plan->chunk * sizeof(float);
+  if (!plan->s_copy) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_comp, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_d2h, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_h2d[b], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_comp[b], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_d2h[b], cudaEventDisableTiming));
+      for (int s = 0; s < 2; ++s) CUDA_TRY(cudaMalloc(&plan->stage_in[b][s], in_bytes));
+      plan->stage_out[b].assign(plan->n_ext, nullptr);
+      for (int k = 0; k < plan->n_ext; ++k)
+        CUDA_TRY(cudaMalloc(&plan->stage_out[b][k], plan->ext_elems[k] * plan->chunk * sizeof(float)));
+    }
+  }
+  int it = 0;
+  for (int start = 0; start < n_pairs; start += plan->chunk, ++it) {
+    const int b = it & 1;
+    const int nv = std::min(plan->chunk, n_pairs - start);
+    if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(plan->s_copy, plan->ev_comp[b], 0));  // staging buffer consumed
+    CUDA_TRY(cudaMemcpyAsync(plan->stage_in[b][0], x1h + (size_t)start * in_elems, in_elems * nv * sizeof(float),
+                             cudaMemcpyHostToDevice, plan->s_copy));
+    CUDA_TRY(cudaMemcpyAsync(plan->stage_in[b][1], x2h + (size_t)start * in_elems, in_elems * nv * sizeof(float),
+                             cudaMemcpyHostToDevice, plan->s_copy));
+    CUDA_TRY(cudaEventRecord(plan->ev_h2d[b], plan->s_copy));
+    CUDA_TRY(cudaStreamWaitEvent(plan->s_comp, plan->ev_h2d[b], 0));
+    if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(plan->s_comp, plan->ev_d2h[b], 0));  // output staging drained
+    int r = run_chunk(plan, plan->stage_in[b][0], plan->stage_in[b][1], nv, plan->stage_out[b].data(), plan->s_comp);
+    if (r) return r;
+    CUDA_TRY(cudaEventRecord(plan->ev_comp[b], plan->s_comp));
+    CUDA_TRY(cudaStreamWaitEvent(plan->s_d2h, plan->ev_comp[b], 0));
+    for (int k = 0; k < n_outs; ++k) {
+      if (!outs_host[k]) continue;
+      CUDA_TRY(cudaMemcpyAsync(outs_host[k] + (size_t)start * plan->ext_elems[k], plan->stage_out[b][k],
+                               plan->ext_elems[k] * nv * sizeof(float), cudaMemcpyDeviceToHost, plan->s_d2h));
+    }
+    CUDA_TRY(cudaEventRecord(plan->ev_d2h[b], plan->s_d2h));
+  }
+  CUDA_TRY(cudaStreamSynchronize(plan->s_copy));
+  CUDA_TRY(cudaStreamSynchronize(plan->s_comp));
+  CUDA_TRY(cudaStreamSynchronize(plan->s_d2h));
+  return STCD_OK;
+}
+
+int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const void* label, int label_kind,
+                             int64_t n_img, int64_t pix, int num_class, int64_t* cm_dev, uint8_t* pred_out,
+                             void* stream) {
+  if (!pred || !label || !cm_dev) return fail(STCD_ERR_INVALID, "NULL pointer");
+  if (n_img < 0 || pix < 0) return fail(STCD_ERR_INVALID, "negative size");
+  if (num_class < 2 || num_class > 32) return fail(STCD_ERR_INVALID, "num_class %d not in [2, 32]", num_class);
+  if (pred_kind < STCD_PRED_ARGMAX2 || pred_kind > STCD_PRED_I64) return fail(STCD_ERR_INVALID, "pred_kind %d", pred_kind);
+  if (label_kind < STCD_LABEL_I64 || label_kind > STCD_LABEL_I32) return fail(STCD_ERR_INVALID, "label_kind %d", label_kind);
+  if (num_class != 2 && pred_kind <= STCD_PRED_RAW_GE) return fail(STCD_ERR_INVALID, "binarising kinds need num_class == 2");
+  if (n_img == 0 || pix == 0) return STCD_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(STCD_ERR_NO_DEVICE, "no CUDA device visible: libstcd_b200 has no CPU fallback");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* cm = reinterpret_cast<unsigned long long*>(cm_dev);
+  const size_t ne = (size_t)n_img * pix;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(label) |
+                         reinterpret_cast<uintptr_t>(pred_out)) & 15) == 0;
+  const int vec = (aligned && (pix % 4 == 0)) ? 1 : 0;
+  const size_t work = vec ? ne / 4 : ne;
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((work + 255) / 256, 148 * 8));
+
+#define STCD_CM2(PK, LK)                                                                                      \
+  stcd::confusion2_kernel<PK, LK><<<blocks, 256, 0, st>>>(pred, label, (size_t)n_img, (size_t)pix, thr, vec, cm, pred_out)
+#define STCD_CMK(PK, LK) \
+  stcd::confusionK_kernel<PK, LK><<<blocks, 256, 0, st>>>(pred, label, (size_t)n_img, (size_t)pix, num_class, cm)
+#define STCD_DISPATCH_L(M, PK)                                      \
+  switch (label_kind) {                                             \
+    case STCD_LABEL_I64: M(PK, STCD_LABEL_I64); break;              \
+    case STCD_LABEL_U8: M(PK, STCD_LABEL_U8); break;                \
+    default: M(PK, STCD_LABEL_I32); break;                          \
+  }
+  if (num_class == 2) {
+    switch (pred_kind) {
+      case STCD_PRED_ARGMAX2: STCD_DISPATCH_L(STCD_CM2, STCD_PRED_ARGMAX2); break;
+      case STCD_PRED_SIGMOID_GT: STCD_DISPATCH_L(STCD_CM2, STCD_PRED_SIGMOID_GT); break;
+      case STCD_PRED_RAW_GE: STCD_DISPATCH_L(STCD_CM2, STCD_PRED_RAW_GE); break;
+      case STCD_PRED_U8: STCD_DISPATCH_L(STCD_CM2, STCD_PRED_U8); break;
+      case STCD_PRED_I32: STCD_DISPATCH_L(STCD_CM2, STCD_PRED_I32); break;
+      default: STCD_DISPATCH_L(STCD_CM2, STCD_PRED_I64); break;
+    }
+  } else {
+    switch (pred_kind) {
+      case STCD_PRED_U8: STCD_DISPATCH_L(STCD_CMK, STCD_PRED_U8); break;
+      case STCD_PRED_I32: STCD_DISPATCH_L(STCD_CMK, STCD_PRED_I32); break;
+      default: STCD_DISPATCH_L(STCD_CMK, STCD_PRED_I64); break;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return STCD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+"""The reference's model-selection API for the nets this library accelerates.
+
+Mirror of ``define_G`` / ``init_net`` / ``init_weights`` (models/networks.py:138-215, 119-135,
+85-116): same signatures, same registry keys (note ``SiamUnet_diff`` is registered as
+``"SiamUnet_abs"``, :148-149), same duck-typed ``args`` (only ``net_G``, ``n_class``,
+``embed_dim``, ``img_size`` are read), same re-initialisation (``normal``: Conv*/Linear* weights
+~ N(0, gain), biases 0, BatchNorm2d weight ~ N(1, gain)), same ``NotImplementedError`` for an
+unknown name.  The returned ``nn.Module`` has the reference's parameter names and
+``forward(x1, x2)`` contract, backed by libstcd_b200 instead of torch.nn.functional.
+"""
+from __future__ import annotations
+
+import torch
+from torch.nn import init
+
+from .siamunet import SiamUnet_conc, SiamUnet_diff
+
+# registry keys of models/networks.py:144-214 that this library does NOT implement (yet): asking for one
+# raises NotImplementedError like an unknown key does upstream, with the reason.
+_REFERENCE_ONLY = (
+    "Unet", "SiamUnet_sub", "SiamUnet_cross_conc", "DTCDSCN", "IFNet", "base_resnet18", "base_transformer_pos_s4",
+    "base_transformer_pos_s4_dd8", "base_transformer_pos_s4_dd8_dedim8", "ChangeFormerV1", "ChangeFormerV2",
+    "ChangeFormerV3", "ChangeFormerV4", "ChangeFormerV5", "ChangeFormerV6", "ChangeGNNV1", "ChangeGNNV2",
+    "ChangeGNNV2_sub", "ChangeGNNV2_abs", "ChangeGNNV2_conc", "GNN",
+)
+
+_REGISTRY = {
+    "SiamUnet_abs": lambda a: SiamUnet_diff(input_nbr=3, label_nbr=a.n_class),     # networks.py:148-149
+    "SiamUnet_conc": lambda a: SiamUnet_conc(input_nbr=3, label_nbr=a.n_class),    # networks.py:151-152
+}
+
+
+def register(name: str, ctor) -> None:
+    _REGISTRY[name] = ctor
+
+
+def init_weights(net, init_type="normal", init_gain=0.02):
+    """models/networks.py:85-116."""
+    def init_func(m):
+        classname = m.__class__.__name__
+        if hasattr(m, "weight") and (classname.find("Conv") != -1 or classname.find("Linear") != -1):
+            if init_type == "normal":
+                init.normal_(m.weight.data, 0.0, init_gain)
+            elif init_type == "xavier":
+                init.xavier_normal_(m.weight.data, gain=init_gain)
+            elif init_type == "kaiming":
+                init.kaiming_normal_(m.weight.data, a=0, mode="fan_in")
+            elif init_type == "orthogonal":
+                init.orthogonal_(m.weight.data, gain=init_gain)
+            else:
+                raise NotImplementedError("initialization method [%s] is not implemented" % init_type)
+            if hasattr(m, "bias") and m.bias is not None:
+                init.constant_(m.bias.data, 0.0)
+        elif classname.find("BatchNorm2d") != -1:
+            init.normal_(m.weight.data, 1.0, init_gain)
+            init.constant_(m.bias.data, 0.0)
+
+    print("initialize network with %s" % init_type)
+    net.apply(init_func)
+    if hasattr(net, "invalidate_plans"):
+        net.invalidate_plans()
+
+
+def init_net(net, init_type="normal", init_gain=0.02, gpu_ids=[]):  # noqa: B006 - the reference's signature
+    """models/networks.py:119-135."""
+    if len(gpu_ids) > 0:
+        assert torch.cuda.is_available()
+        net.to(gpu_ids[0])
+        if len(gpu_ids) > 1:
+            net = torch.nn.DataParallel(net, gpu_ids)
+    init_weights(net, init_type, init_gain=init_gain)
+    return net
+
+
+def define_G(args, init_type="normal", init_gain=0.02, gpu_ids=[]):  # noqa: B006
+    """models/networks.py:138-215."""
+    name = args.net_G
+    if name in _REGISTRY:
+        net = _REGISTRY[name](args)
+    elif name in _REFERENCE_ONLY:
+        raise NotImplementedError("Generator model name [%s] is served by the reference only; stcd_b200 accelerates %s"
+                                  % (name, sorted(_REGISTRY)))
+    else:
+        raise NotImplementedError("Generator model name [%s] is not recognized" % name)
+    return init_net(net, init_type, init_gain, gpu_ids)

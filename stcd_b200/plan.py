@@ -1,0 +1,200 @@
+"""Program -> libstcd_b200 plan (the device-side object behind ``net_G(x1, x2)``).
+
+``Plan`` hands a lowered ``Program`` (stcd_b200/lowering.py) to the C-ABI: it declares the
+activation tensors, adds each fused op, finalizes (workspace, weight upload, TMA descriptors)
+and then runs ``stcd_forward`` on device pointers or ``stcd_forward_host`` on host buffers.
+PyTorch appears only as the owner of the caller's device memory and stream.  There is no CPU
+path: constructing a Plan without an sm_100 device raises ``StcdError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .lowering import ConvSpec, InputPackSpec, Program
+
+
+def _fptr(a: Optional[np.ndarray]):
+    if a is None:
+        return C.cast(None, C.POINTER(C.c_float))
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Plan:
+    def __init__(self, prog: Program, chunk_pairs: int, device: int = 0):
+        self.lib = _lib.lib()
+        self.prog = prog
+        self.chunk = int(chunk_pairs)
+        self.device = int(device)
+        self._h = C.c_void_p()
+        _lib.check(self.lib.stcd_plan_create(self.device, self.chunk, C.byref(self._h)), "stcd_plan_create")
+        try:
+            self._build()
+        except Exception:
+            self.close()
+            raise
+
+    # ------------------------------------------------------------------ construction
+    def _build(self) -> None:
+        lib, h, prog = self.lib, self._h, self.prog
+        ids = {}
+        for name, t in prog.tensors.items():
+            ids[name] = _lib.check_id(lib.stcd_plan_add_tensor(h, t.mult, t.h, t.w, t.c, 0), f"tensor {name}")
+        self.tensor_ids = ids
+        for op in prog.ops:
+            if isinstance(op, InputPackSpec):
+                _lib.check_id(lib.stcd_plan_add_input_pack(h, ids[op.dst], op.cin), f"input pack {op.name}")
+            elif isinstance(op, ConvSpec):
+                self._add_conv(op)
+            else:
+                raise TypeError(f"unknown op {op!r}")
+        _lib.check(lib.stcd_plan_finalize(h), "stcd_plan_finalize")
+
+    def _add_conv(self, op: ConvSpec) -> None:
+        ids = self.tensor_ids
+        d = _lib.ConvDesc()
+        d.n_src = len(op.srcs)
+        for i, s in enumerate(op.srcs):
+            d.src[i] = ids[s]
+            d.src_sy[i] = op.src_sy[i]
+            d.src_sx[i] = op.src_sx[i]
+        d.hg, d.wg = op.hg, op.wg
+        d.img_mult = op.img_mult
+        d.pair = 1 if op.pair else 0
+        w = np.ascontiguousarray(op.weights, dtype=np.uint16)
+        d.weights = w.ctypes.data_as(C.POINTER(C.c_uint16))
+        d.w_rows, d.w_cols = w.shape
+        d.kc, d.n_tile, d.cout, d.cout_pad = op.kc, op.n_tile, op.cout, op.cout_pad
+        d.n_phase = len(op.phases)
+        for i, ph in enumerate(op.phases):
+            d.phase[i] = _lib.Phase(ph.k_begin, ph.k_count, ph.oy, ph.ox, ph.w_row)
+        kp = (_lib.KEntry * len(op.kprog))()
+        for i, e in enumerate(op.kprog):
+            kp[i] = _lib.KEntry(e.src, e.dy, e.dx, e.c0, e.stream * self.chunk, e.wk)
+        d.kprog = C.cast(kp, C.POINTER(_lib.KEntry))
+        d.n_kentry = len(op.kprog)
+        d.osy, d.osx = op.osy, op.osx
+        keep = [np.ascontiguousarray(op.scale, np.float32), np.ascontiguousarray(op.shift, np.float32),
+                None if op.scale2 is None else np.ascontiguousarray(op.scale2, np.float32),
+                None if op.shift2 is None else np.ascontiguousarray(op.shift2, np.float32)]
+        d.scale, d.shift, d.scale2, d.shift2 = (_fptr(a) for a in keep)
+        d.relu = 1 if op.relu else 0
+        tid = lambda n: -1 if n is None else ids[n]  # noqa: E731
+        d.res = tid(op.res)
+        d.out0, d.out0_coff = tid(op.out0), op.out0_coff
+        d.out_raw, d.out_pool, d.out_diff = tid(op.out_raw), tid(op.out_pool), tid(op.out_diff)
+        d.out_ext = op.out_ext
+        _lib.check_id(self.lib.stcd_plan_add_conv(self._h, C.byref(d)), f"conv {op.name}")
+
+    # ------------------------------------------------------------------ queries
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.stcd_plan_workspace_bytes(self._h))
+
+    def launches(self, n_pairs: int) -> int:
+        return int(self.lib.stcd_plan_launches(self._h, int(n_pairs)))
+
+    def out_shapes(self, n_pairs: int) -> List[tuple]:
+        return [(n_pairs, e.channels, e.h, e.w) for e in self.prog.ext]
+
+    # ------------------------------------------------------------------ execution
+    def _check_inputs(self, x1: torch.Tensor, x2: torch.Tensor) -> int:
+        p = self.prog
+        if x1.shape != x2.shape:
+            raise ValueError(f"x1 {tuple(x1.shape)} and x2 {tuple(x2.shape)} differ")
+        if x1.dim() != 4 or tuple(x1.shape[1:]) != (p.in_channels, p.h, p.w):
+            raise ValueError(f"plan was built for [B,{p.in_channels},{p.h},{p.w}] inputs, got {tuple(x1.shape)}")
+        if x1.dtype != torch.float32 or x2.dtype != torch.float32:
+            raise TypeError("inputs must be float32 (the reference's input dtype: data/dataset.py:196-203)")
+        return int(x1.shape[0])
+
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor, outs: Optional[Sequence[torch.Tensor]] = None
+                ) -> List[torch.Tensor]:
+        """Device tensors in, device fp32 NCHW tensors out; asynchronous on torch's current stream."""
+        n = self._check_inputs(x1, x2)
+        if not x1.is_cuda or not x2.is_cuda or x1.device.index != self.device or x2.device.index != self.device:
+            raise ValueError(f"inputs must live on cuda:{self.device}")
+        x1 = x1.contiguous()
+        x2 = x2.contiguous()
+        if outs is None:
+            outs = [torch.empty(s, dtype=torch.float32, device=x1.device) for s in self.out_shapes(n)]
+        ptrs = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        stream = torch.cuda.current_stream(x1.device).cuda_stream
+        _lib.check(self.lib.stcd_forward(self._h, x1.data_ptr(), x2.data_ptr(), n, ptrs, len(outs),
+                                         C.c_void_p(stream)), "stcd_forward")
+        return list(outs)
+
+    def forward_host(self, x1: torch.Tensor, x2: torch.Tensor, outs: Optional[Sequence[torch.Tensor]] = None
+                     ) -> List[torch.Tensor]:
+        """Host (ideally pinned) tensors in, host tensors out; blocks until the results have landed."""
+        n = self._check_inputs(x1, x2)
+        if x1.is_cuda or x2.is_cuda:
+            raise ValueError("forward_host takes host tensors")
+        x1 = x1.contiguous()
+        x2 = x2.contiguous()
+        if outs is None:
+            outs = [torch.empty(s, dtype=torch.float32).pin_memory() for s in self.out_shapes(n)]
+        ptrs = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        _lib.check(self.lib.stcd_forward_host(self._h, x1.data_ptr(), x2.data_ptr(), n, ptrs, len(outs)),
+                   "stcd_forward_host")
+        return list(outs)
+
+    def profile(self, x1: torch.Tensor, x2: torch.Tensor) -> List[tuple]:
+        """Measurement pass: [(op name, ms, reference-equivalent MACs for this batch)] per op, device
+        time from CUDA events around every launch (summed over chunks)."""
+        n = self._check_inputs(x1, x2)
+        outs = [torch.empty(s, dtype=torch.float32, device=x1.device) for s in self.out_shapes(n)]
+        ptrs = (C.c_void_p * max(1, len(outs)))(*[o.data_ptr() for o in outs])
+        n_ops = len(self.prog.ops)
+        ms = (C.c_float * n_ops)()
+        stream = torch.cuda.current_stream(x1.device).cuda_stream
+        _lib.check(self.lib.stcd_forward_profile(self._h, x1.data_ptr(), x2.data_ptr(), n, ptrs, len(outs),
+                                                 C.c_void_p(stream), ms, n_ops), "stcd_forward_profile")
+        return [(op.name, float(ms[i]), int(getattr(op, "macs_per_pair", 0)) * n) for i, op in enumerate(self.prog.ops)]
+
+    # ------------------------------------------------------------------ diagnostics
+    def read_tensor(self, name: str) -> torch.Tensor:
+        """Activation tensor `name` as fp32 [mult*chunk, h, w, c] on the host (synchronous)."""
+        t = self.prog.tensors[name]
+        buf = torch.empty(t.mult * self.chunk, t.h, t.w, t.c, dtype=torch.bfloat16)
+        _lib.check(self.lib.stcd_plan_tensor_copy(self._h, self.tensor_ids[name], C.c_void_p(buf.data_ptr()),
+                                                  buf.numel() * 2, 0), f"read tensor {name}")
+        return buf.to(torch.float32)
+
+    def write_tensor(self, name: str, value: torch.Tensor) -> None:
+        t = self.prog.tensors[name]
+        buf = value.to(torch.bfloat16).contiguous()
+        if tuple(buf.shape) != (t.mult * self.chunk, t.h, t.w, t.c):
+            raise ValueError(f"tensor {name} is {(t.mult * self.chunk, t.h, t.w, t.c)}, got {tuple(buf.shape)}")
+        _lib.check(self.lib.stcd_plan_tensor_copy(self._h, self.tensor_ids[name], C.c_void_p(buf.data_ptr()),
+                                                  buf.numel() * 2, 1), f"write tensor {name}")
+
+    def run_raw(self, n_valid: Optional[int] = None) -> List[torch.Tensor]:
+        """Run the op list on whatever the activation tensors hold (programs without an input
+        pack op: layer-wise tests).  Returns the external outputs (device tensors)."""
+        n = self.chunk if n_valid is None else n_valid
+        dev = torch.device("cuda", self.device)
+        outs = [torch.empty(s, dtype=torch.float32, device=dev) for s in self.out_shapes(n)]
+        ptrs = (C.c_void_p * max(1, len(outs)))(*[o.data_ptr() for o in outs])
+        dummy = torch.zeros(16, dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self.lib.stcd_forward(self._h, dummy.data_ptr(), dummy.data_ptr(), n, ptrs, len(outs),
+                                         C.c_void_p(stream)), "stcd_forward")
+        torch.cuda.synchronize(dev)
+        return outs
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.stcd_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass

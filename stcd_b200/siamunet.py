@@ -1,0 +1,191 @@
+"""FC-Siam-diff / FC-Siam-conc behind the reference's ``net_G(x1, x2)`` contract.
+
+Drop-in for ``models/SiamUnet_diff.py::SiamUnet_diff`` and ``models/SiamUnet_conc.py::SiamUnet_conc``
+(registry keys ``SiamUnet_abs`` / ``SiamUnet_conc``, models/networks.py:148-153): same ctor
+arguments, same parameter names (so a reference ``state_dict`` loads), same return type (one
+``[B, label_nbr, H, W]`` float32 tensor).  The forward lowers the eval-mode network to 25 fused
+launches of libstcd_b200 per chunk of image pairs:
+
+* both temporal images go through every encoder conv in ONE launch (Siamese pair tiles share
+  the weight tiles); folded BatchNorm + ReLU, the 2x2 max-pool and the ``|f1 - f2|`` skip are
+  written by the conv's epilogue (SiamUnet_diff.py:99-143,150);
+* ``torch.cat`` is never materialised: decoder convs read (up-conv, skip) as K-segments;
+* ``ConvTranspose2d(k3, s1, p1)`` is a conv with flipped/transposed weights, the stride-2
+  up-convs run as 4 output phases (SiamUnet_diff.py:52-90).
+
+Eval-mode semantics only (BatchNorm running statistics, Dropout2d = identity): this is the
+inference hot path; training stays with the reference.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import lowering as L
+
+# (name, cin, cout) of the encoder convs per stage; decoder: (name, cout) chains after each up-conv.
+_ENC: List[List[Tuple[str, int, int]]] = [
+    [("11", -1, 16), ("12", 16, 16)],
+    [("21", 16, 32), ("22", 32, 32)],
+    [("31", 32, 64), ("32", 64, 64), ("33", 64, 64)],
+    [("41", 64, 128), ("42", 128, 128), ("43", 128, 128)],
+]
+_DEC: List[Tuple[str, int, List[Tuple[str, int]]]] = [
+    ("4", 128, [("43d", 128), ("42d", 128), ("41d", 64)]),
+    ("3", 64, [("33d", 64), ("32d", 64), ("31d", 32)]),
+    ("2", 32, [("22d", 32), ("21d", 16)]),
+    ("1", 16, [("12d", 16), ("11d", -1)]),
+]
+
+
+def _skip_mult(fusion: str) -> int:
+    return {"diff": 1, "conc": 2}[fusion]
+
+
+class _SiamUnet(nn.Module):
+    fusion = "diff"
+
+    def __init__(self, input_nbr: int, label_nbr: int):
+        super().__init__()
+        self.input_nbr = input_nbr
+        self.label_nbr = label_nbr
+        for stage in _ENC:
+            for name, cin, cout in stage:
+                cin = input_nbr if cin < 0 else cin
+                setattr(self, f"conv{name}", nn.Conv2d(cin, cout, kernel_size=3, padding=1))
+                setattr(self, f"bn{name}", nn.BatchNorm2d(cout))
+        for lvl, cup, chain in _DEC:
+            setattr(self, f"upconv{lvl}", nn.ConvTranspose2d(cup, cup, kernel_size=3, padding=1, stride=2,
+                                                             output_padding=1))
+            cin = cup * (1 + _skip_mult(self.fusion))
+            for name, cout in chain:
+                cout = label_nbr if cout < 0 else cout
+                setattr(self, f"conv{name}", nn.ConvTranspose2d(cin, cout, kernel_size=3, padding=1))
+                if name != "11d":
+                    setattr(self, f"bn{name}", nn.BatchNorm2d(cout))
+                cin = cout
+        self._plans: Dict[tuple, object] = {}
+        self.chunk_pairs = 8
+
+    # weights changed (load_state_dict / .to / re-init): packed copies are stale
+    def _apply(self, fn, *a, **k):
+        self._plans = {}
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._plans = {}
+        return super().load_state_dict(*a, **k)
+
+    def invalidate_plans(self) -> None:
+        self._plans = {}
+
+    def lower(self, h: int, w: int) -> L.Program:
+        return lower_siamunet(self.state_dict(), self.fusion, self.input_nbr, self.label_nbr, h, w)
+
+    def plan_for(self, x: torch.Tensor):
+        from .plan import Plan
+        if self.training:
+            raise RuntimeError("stcd_b200 implements the eval-mode inference path; call .eval() first "
+                               "(training stays with the reference, models/trainer.py)")
+        if not x.is_cuda:
+            raise RuntimeError("stcd_b200 has no CPU path: move the module and its inputs to a B200 (cuda) device")
+        key = (x.device.index, int(x.shape[2]), int(x.shape[3]), self.chunk_pairs)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = Plan(self.lower(key[1], key[2]), self.chunk_pairs, device=key[0])
+            self._plans[key] = plan
+        return plan
+
+    @torch.no_grad()
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+        return self.plan_for(x1).forward(x1, x2)[0]
+
+
+class SiamUnet_diff(_SiamUnet):
+    """models/SiamUnet_diff.py:10-181."""
+    fusion = "diff"
+
+
+class SiamUnet_conc(_SiamUnet):
+    """models/SiamUnet_conc.py:10-183."""
+    fusion = "conc"
+
+
+# ------------------------------------------------------------------------------------------
+def lower_siamunet(sd: Dict[str, torch.Tensor], fusion: str, input_nbr: int, label_nbr: int, h: int, w: int
+                   ) -> L.Program:
+    """state_dict of the reference module -> fused-op Program (eval mode)."""
+    if h % 16 or w % 16:
+        # ReplicationPad2d (SiamUnet_diff.py:149) is a no-op exactly when H and W are multiples of 16
+        raise ValueError(f"SiamUnet lowering needs H and W divisible by 16 (got {h}x{w})")
+    if input_nbr > 16:
+        raise ValueError("input_nbr > 16 not supported by the input packer")
+    sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
+    p = L.Program(model=f"SiamUnet_{fusion}", in_channels=input_nbr, h=h, w=w)
+    p.tensor("in", 2, h, w, 16)
+    p.ops.append(L.InputPackSpec("pack", "in", input_nbr))
+
+    def bn_fold(name: str, cout: int):
+        return L.fold_bn(sd[f"conv{name}.bias"], L.bn_params(sd, f"bn{name}"), cout)
+
+    # ---------------- encoder: both streams per launch (pair tiles)
+    cur, cur_c = "in", input_nbr
+    hh, ww = h, w
+    skips: List[Tuple[str, int, int, int]] = []   # (tensor, channels, h, w)
+    for si, stage in enumerate(_ENC):
+        for li, (name, _, cout) in enumerate(stage):
+            last = li == len(stage) - 1
+            scale, shift = bn_fold(name, cout)
+            wt = sd[f"conv{name}.weight"]
+            out0 = out_pool = out_diff = None
+            if not last:
+                out0 = p.tensor(f"x{name}", 2, hh, ww, cout)
+            else:
+                out_pool = p.tensor(f"x{si + 1}p", 2, hh // 2, ww // 2, cout)
+                if fusion == "diff":
+                    out_diff = p.tensor(f"d{si + 1}", 1, hh, ww, cout)
+                    skips.append((out_diff, cout, hh, ww))
+                else:
+                    out0 = p.tensor(f"x{name}", 2, hh, ww, cout)
+                    skips.append((out0, cout, hh, ww))
+            L.add_conv(p, f"conv{name}", [L.Segment(cur, cur_c)], L.conv_taps(wt, pad=1), cout, hh, ww, 1,
+                       scale, shift, pair=True, relu=True, out0=out0, out_pool=out_pool, out_diff=out_diff,
+                       macs_per_pair=2 * hh * ww * 9 * cur_c * cout)
+            cur, cur_c = (out0 if not last else out_pool), cout
+        hh, ww = hh // 2, ww // 2
+
+    # ---------------- decoder: one stream; bottleneck = image 2 only (SiamUnet_diff.py:143,148)
+    cur_stream = 1
+    for (lvl, cup, chain), (skip, skip_c, sh, sw) in zip(_DEC, reversed(skips)):
+        wt = sd[f"upconv{lvl}.weight"]      # [cin, cout, 3, 3]
+        up = p.tensor(f"u{lvl}", 1, sh, sw, cup)
+        L.add_conv(p, f"upconv{lvl}", [L.Segment(cur, cur_c, stream=cur_stream)],
+                   L.convT_phase_taps(wt, stride=2, pad=1), cup, sh // 2, sw // 2, 1,
+                   np.ones(cup, np.float32), sd[f"upconv{lvl}.bias"].numpy().astype(np.float32),
+                   osy=2, osx=2, out0=up, macs_per_pair=(sh // 2) * (sw // 2) * 9 * cur_c * cup)
+        cur_stream = 0
+        if fusion == "diff":
+            segs = [L.Segment(up, cup), L.Segment(skip, skip_c)]
+        else:
+            segs = [L.Segment(up, cup), L.Segment(skip, skip_c, stream=0), L.Segment(skip, skip_c, stream=1)]
+        cur, cur_c = None, None
+        for name, cout in chain:
+            cout = label_nbr if cout < 0 else cout
+            wt = L.convT_as_conv_weight(sd[f"conv{name}.weight"])
+            cin = sum(s.c_real for s in segs)
+            if name == "11d":
+                L.add_conv(p, f"conv{name}", segs, L.conv_taps(wt, pad=1), cout, sh, sw, 1,
+                           np.ones(cout, np.float32), sd[f"conv{name}.bias"].numpy().astype(np.float32),
+                           out_ext=0, macs_per_pair=sh * sw * 9 * cin * cout)
+                p.ext.append(L.ExtOutput("logits", cout, sh, sw))
+            else:
+                scale, shift = bn_fold(name, cout)
+                out = p.tensor(f"x{name}", 1, sh, sw, cout)
+                L.add_conv(p, f"conv{name}", segs, L.conv_taps(wt, pad=1), cout, sh, sw, 1, scale, shift,
+                           relu=True, out0=out, macs_per_pair=sh * sw * 9 * cin * cout)
+                cur, cur_c = out, cout
+                segs = [L.Segment(out, cout)]
+    return p

@@ -1,0 +1,70 @@
+"""Seeded synthetic weights, image pairs and labels for parity tests and bench.py.
+
+There is no network for datasets or checkpoints, so every measurement runs on synthetic data
+of the reference's shapes: ``x1, x2 ~ randn(B, 3, H, W)`` like the reference's own smoke blocks
+(models/SNUNet.py:248-249) and labels ~ Bernoulli(p) int64 {0,1} (data/dataset.py:206-210).
+
+Weights: the module's constructor init, then BatchNorm running statistics and affine
+parameters are randomised so that eval-mode BatchNorm is a non-trivial affine map and
+activations stay O(1) through depth (with untouched running stats the logits
+of a random-init net are degenerate and a parity test on them says nothing).  Everything is
+drawn from a CPU ``torch.Generator`` so the same seed gives the same bits on every box.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.nn as nn
+
+WEIGHT_SEED = 1337           # the reference's seed (train_stcd.py:62-65)
+DATA_SEED = 1338
+
+
+@torch.no_grad()
+def randomize_(net: nn.Module, seed: int = WEIGHT_SEED, gain: float = 1.0) -> nn.Module:
+    """Re-draw every parameter/buffer of `net` in a fixed order from a seeded CPU generator."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    for name, m in net.named_modules():
+        if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d, nn.Linear)):
+            w = m.weight
+            if isinstance(m, nn.ConvTranspose2d):
+                fan_in = w.shape[0] * w[0, 0].numel() / max(1, m.stride[0] * m.stride[1]) / m.groups
+            elif isinstance(m, nn.Conv2d):
+                fan_in = w.shape[1] * w[0, 0].numel()
+            else:
+                fan_in = w.shape[1]
+            std = gain * (2.0 / max(1.0, fan_in)) ** 0.5
+            w.copy_(torch.randn(w.shape, generator=g) * std)
+            if m.bias is not None:
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+        elif isinstance(m, nn.BatchNorm2d):
+            m.weight.copy_(0.8 + 0.4 * torch.rand(m.weight.shape, generator=g))
+            m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+        elif isinstance(m, nn.LayerNorm):
+            m.weight.copy_(0.8 + 0.4 * torch.rand(m.weight.shape, generator=g))
+            m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    return net
+
+
+def image_pairs(batch: int, h: int, w: int, channels: int = 3, seed: int = DATA_SEED, correlated: float = 0.7
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 NCHW pairs.  T2 = correlated*T1 + noise: bi-temporal images are mostly unchanged, which
+    keeps the change map non-degenerate (a few % .. tens of % of pixels 'changed')."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x1 = torch.randn(batch, channels, h, w, generator=g)
+    n = torch.randn(batch, channels, h, w, generator=g)
+    x2 = correlated * x1 + (1.0 - correlated ** 2) ** 0.5 * n
+    return x1, x2
+
+
+def labels(batch: int, h: int, w: int, p: float = 0.05, seed: int = DATA_SEED + 1) -> torch.Tensor:
+    """int64 {0,1} [B, H, W] ~ Bernoulli(p) (LEVIR-CD-like change sparsity)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.rand(batch, h, w, generator=g) < p).to(torch.int64)
+
+
+def state_dict_cpu(net: nn.Module) -> Dict[str, torch.Tensor]:
+    return {k: v.detach().to("cpu").clone() for k, v in net.state_dict().items()}

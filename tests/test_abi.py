@@ -1,0 +1,59 @@
+"""The C-ABI library loads and exports every symbol include/stcd_b200.h declares; without a GPU
+every compute entry point fails loudly (no CPU fallback)."""
+import ctypes as C
+import re
+
+import pytest
+import torch
+
+from stcd_b200 import _lib
+
+
+def _declared_symbols():
+    text = _lib.HEADER.read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(stcd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    lib = _lib.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 14
+    bound = {n for n, _, _ in _lib.SYMBOLS}
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/stcd_b200.h but not exported"
+        assert name in bound, f"{name} has no ctypes signature in stcd_b200/_lib.py"
+    assert lib.stcd_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    # sizes the C side static_asserts / validates; a drifted ctypes mirror corrupts plans silently
+    assert C.sizeof(_lib.KEntry) == 16
+    assert C.sizeof(_lib.Phase) == 20
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_gpu_fails_loudly():
+    lib = _lib.lib()
+    assert lib.stcd_device_count() == 0
+    h = C.c_void_p()
+    rc = lib.stcd_plan_create(0, 4, C.byref(h))
+    assert rc == 3 and not h.value          # STCD_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.stcd_last_error()
+    cm = (C.c_int64 * 4)()
+    buf = (C.c_uint8 * 16)()
+    rc = lib.stcd_confusion_add_batch(buf, 3, 0.0, buf, 1, 1, 16, 2, cm, None, None)
+    assert rc == 3
+    from stcd_b200.metric import SegmentationMetric
+    with pytest.raises(_lib.StcdError):
+        SegmentationMetric(2)
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.lib()
+    cm = (C.c_int64 * 4)()
+    buf = (C.c_uint8 * 16)()
+    assert lib.stcd_confusion_add_batch(None, 3, 0.0, buf, 1, 1, 16, 2, cm, None, None) == 1
+    assert lib.stcd_confusion_add_batch(buf, 9, 0.0, buf, 1, 1, 16, 2, cm, None, None) == 1
+    assert lib.stcd_confusion_add_batch(buf, 0, 0.0, buf, 1, 1, 16, 3, cm, None, None) == 1
+    assert lib.stcd_forward(None, None, None, 1, None, 0, None) == 4      # STCD_ERR_STATE
