@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 1
+#define STCD_ABI_VERSION 2
 
 enum stcd_status {
   STCD_OK = 0,
@@ -57,29 +57,46 @@ int stcd_device_count(void);
 int stcd_plan_create(int device, int chunk_pairs, stcd_plan** out);
 void stcd_plan_destroy(stcd_plan* plan);
 
-/* Declare an activation tensor of img_mult*chunk_pairs images, NHWC. Returns id >= 0, or <0. */
+/* Declare an activation tensor of img_mult*chunk_pairs images, bf16 [img][c/8][h][w][8].
+ * Returns id >= 0, or <0. */
 int stcd_plan_add_tensor(stcd_plan* plan, int img_mult, int h, int w, int c, int dtype);
 
-/* One K-block of the implicit GEMM: `kc` channels [c0, c0+kc) of source `src` (index into
- * stcd_conv_desc.src), read at input pixel (i*src_sy + dy, j*src_sx + dx) of image (n + n_off) for
- * tile pixel (i, j); multiplies weight columns [wk, wk+kc). Out-of-bounds pixels read as 0
- * (= zero padding, nn.Conv2d padding=1: SiamUnet_diff.py:18). */
-typedef struct stcd_kentry {
-  int16_t src, dy, dx, c0;
+/* Activation tensors are stored channel-chunked: bf16 [img][c/8][h][w][8] ("NC8HW8"), so that a
+ * TMA box {8 ch, box_w px, box_h px, kc/8 chunks} lands in shared memory as the un-swizzled
+ * K-major core-matrix layout tcgen05.mma consumes, and a filter tap is just a byte offset into
+ * the box: a 3x3 conv reads its (16+2)x(8+2) halo ONCE per K-chunk instead of once per tap.
+ *
+ * One A-stage load of the implicit GEMM: channels [c0, c0+kc) of source `src` (index into
+ * stcd_conv_desc.src) over the pixel box whose origin is (ty*src_sy + by, tx*src_sx + bx) of image
+ * (n + n_off) for the tile at tile-pixel (ty, tx).  Out-of-bounds pixels read as 0 (= zero
+ * padding, nn.Conv2d padding=1: SiamUnet_diff.py:18).  The chunk feeds `n_taps` filter taps
+ * (stcd_tap entries [tap_begin, tap_begin + n_taps)). */
+typedef struct stcd_chunk {
+  int16_t src, c0;
+  int16_t by, bx;
   int32_t n_off;
-  int32_t wk;
-} stcd_kentry;
+  int16_t tap_begin, n_taps;
+} stcd_chunk;
+
+/* One filter tap inside a chunk's box: tile pixel (i, j) reads box pixel (i + ty, j + tx).
+ * Weight blocks are consumed in tap order: tap t of a phase multiplies weight block t. */
+typedef struct stcd_tap {
+  int16_t ty, tx;
+} stcd_tap;
 
 /* One output phase: tile pixel (i, j) -> output pixel (i*osy + oy, j*osx + ox). A stride-1
  * conv has one phase; ConvTranspose2d(stride=2) (SiamUnet_diff.py:52) has four. */
 typedef struct stcd_phase {
-  int32_t k_begin, k_count; /* slice of the kentry array */
+  int32_t chunk_begin, chunk_count; /* slice of the chunk array */
   int32_t oy, ox;
-  int32_t w_row;            /* first row of this phase in the packed weight matrix */
+  int32_t w_block;                  /* first weight block of this phase (per N tile) */
+  int32_t n_blocks;                 /* = number of taps summed over the phase's chunks */
 } stcd_phase;
 
 #define STCD_MAX_SRC 6
 #define STCD_MAX_PHASE 4
+#define STCD_TILE_H 16
+#define STCD_TILE_W 8
 
 typedef struct stcd_conv_desc {
   /* A operand (activations): virtual concat of up to 6 sources (torch.cat, SNUNet.py:142) */
@@ -87,21 +104,26 @@ typedef struct stcd_conv_desc {
   int32_t src[STCD_MAX_SRC];      /* tensor ids */
   int32_t src_sy[STCD_MAX_SRC];   /* per-source input coordinate stride (2 for a stride-2 conv) */
   int32_t src_sx[STCD_MAX_SRC];
+  int32_t src_ey[STCD_MAX_SRC];   /* per-source halo: box = (16 + ey) x (8 + ex) pixels (0 if stride > 1) */
+  int32_t src_ex[STCD_MAX_SRC];
   /* tile grid */
   int32_t hg, wg;                 /* tile-pixel grid (= output dims / osy, osx) */
   int32_t img_mult;               /* images in the grid = img_mult * chunk_pairs */
   int32_t pair;                   /* 1: each CTA also accumulates image n + chunk_pairs (Siamese pair) */
-  /* B operand (weights), packed by the host: bf16 [w_rows][w_cols], K-major */
+  /* B operand (weights), packed by the host in consumption order:
+   * bf16 [n_tiles][total blocks][kc/8][n_tile][8]  (block = one tap of one chunk) */
   const uint16_t* weights;        /* HOST pointer, copied at add time */
-  int32_t w_rows, w_cols;
-  int32_t kc;                     /* channels per K-block: 16, 32 or 64 */
+  int64_t w_elems;
+  int32_t kc;                     /* channels per chunk: 16, 32 or 64 */
   int32_t n_tile;                 /* GEMM N per CTA (multiple of 16, <= 256) */
   int32_t cout;                   /* real output channels */
   int32_t cout_pad;               /* padded to a multiple of n_tile */
   int32_t n_phase;
   stcd_phase phase[STCD_MAX_PHASE];
-  const stcd_kentry* kprog;       /* HOST pointer */
-  int32_t n_kentry;
+  const stcd_chunk* chunks;       /* HOST pointer */
+  int32_t n_chunks;
+  const stcd_tap* taps;           /* HOST pointer */
+  int32_t n_taps;
   int32_t osy, osx;               /* output coordinate stride */
   /* epilogue: v = acc*scale + shift; [out_raw <- v]; [v = v*scale2 + shift2]; [v += res];
    * [v = relu(v)]; out0 <- v; out_pool <- maxpool2x2(v); out_diff <- |v(n) - v(n+chunk)| */
@@ -122,14 +144,15 @@ typedef struct stcd_conv_desc {
 int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* desc);
 
 /* x1, x2 (fp32 NCHW [n_pairs, cin, h, w], the reference's input layout: data/dataset.py:196-203)
- * -> bf16 NHWC [2*chunk, h, w, c_pad] with the T1 images first, then the T2 images. */
+ * -> bf16 [2*chunk][2][h][w][8] (cin <= 8 real channels, 16 stored) with the T1 images first, then
+ * the T2 images. */
 int stcd_plan_add_input_pack(stcd_plan* plan, int dst_tensor, int cin);
 
 /* allocate the workspace, upload weights, encode TMA descriptors */
 int stcd_plan_finalize(stcd_plan* plan);
 
 /* Diagnostics / layer-wise parity tests: synchronous copy between a HOST buffer and activation
- * tensor `tensor_id` (bf16 NHWC [img_mult*chunk, h, w, c]); to_device != 0 writes the tensor.
+ * tensor `tensor_id` (bf16 [img_mult*chunk][c/8][h][w][8]); to_device != 0 writes the tensor.
  * `bytes` must equal the tensor's size. */
 int stcd_plan_tensor_copy(stcd_plan* plan, int tensor_id, void* host, int64_t bytes, int to_device);
 

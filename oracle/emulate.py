@@ -1,6 +1,6 @@
 """CPU emulator of a lowered Program (stcd_b200/lowering.py).  TEST INFRASTRUCTURE.
 
-Executes the op list exactly as csrc/conv_gemm.cuh does — NHWC tensors holding bf16 values,
+Executes the op list exactly as csrc/conv_ws.cuh does — logical NHWC tensors holding bf16 values,
 K-programs walked entry by entry, fp32 accumulation, the epilogue's rounding points — so that
 ``tests/`` can check the HOST-side lowering (weight packing, K-programs, BN folding, phases,
 virtual concat) against the reference without a GPU, and the GPU kernels against this emulator
@@ -30,9 +30,9 @@ def _gather(src: torch.Tensor, rows: torch.Tensor, cols: torch.Tensor) -> torch.
 
 
 def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[torch.Tensor], n_valid: int) -> None:
-    wmat = L.bf16_bits_to_f32(op.weights)                       # [w_rows, w_cols]
     n_img = chunk if op.pair else op.img_mult * chunk
     n_m = 2 if op.pair else 1
+    n_nt = op.cout_pad // op.n_tile
     ho, wo = op.hg * op.osy, op.wg * op.osx
     scale = torch.from_numpy(op.scale)
     shift = torch.from_numpy(op.shift)
@@ -42,13 +42,19 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
     for ph in op.phases:
         for m in range(n_m):
             acc = torch.zeros(n_img, op.hg, op.wg, op.cout_pad)
-            for e in op.kprog[ph.k_begin: ph.k_begin + ph.k_count]:
-                si = e.src
+            blk = ph.w_block
+            for ck in op.chunks[ph.chunk_begin: ph.chunk_begin + ph.chunk_count]:
+                si = ck.src
                 src = T[op.srcs[si]]
-                off = (e.stream + m) * chunk
-                a = _gather(src[off: off + n_img, :, :, e.c0: e.c0 + op.kc], ii * op.src_sy[si] + e.dy,
-                            jj * op.src_sx[si] + e.dx)
-                acc += a @ wmat[ph.w_row: ph.w_row + op.cout_pad, e.wk: e.wk + op.kc].T
+                off = (ck.stream + m) * chunk
+                sub = src[off: off + n_img, :, :, ck.c0: ck.c0 + op.kc]
+                for (ty, tx) in op.taps[ck.tap_begin: ck.tap_begin + ck.n_taps]:
+                    a = _gather(sub, ii * op.src_sy[si] + ck.by + ty * op.src_sy[si],
+                                jj * op.src_sx[si] + ck.bx + tx * op.src_sx[si])
+                    w = torch.cat([op.weight_block(nt, blk) for nt in range(n_nt)], 0)      # [cout_pad, kc]
+                    acc += a @ w.T
+                    blk += 1
+            assert blk == ph.w_block + ph.n_blocks
             full[m][:, ph.oy::op.osy, ph.ox::op.osx] = acc
     vs = []
     for m in range(n_m):

@@ -55,14 +55,18 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
-class KEntry(C.Structure):
-    _fields_ = [("src", C.c_int16), ("dy", C.c_int16), ("dx", C.c_int16), ("c0", C.c_int16),
-                ("n_off", C.c_int32), ("wk", C.c_int32)]
+class Chunk(C.Structure):
+    _fields_ = [("src", C.c_int16), ("c0", C.c_int16), ("by", C.c_int16), ("bx", C.c_int16),
+                ("n_off", C.c_int32), ("tap_begin", C.c_int16), ("n_taps", C.c_int16)]
+
+
+class Tap(C.Structure):
+    _fields_ = [("ty", C.c_int16), ("tx", C.c_int16)]
 
 
 class Phase(C.Structure):
-    _fields_ = [("k_begin", C.c_int32), ("k_count", C.c_int32), ("oy", C.c_int32), ("ox", C.c_int32),
-                ("w_row", C.c_int32)]
+    _fields_ = [("chunk_begin", C.c_int32), ("chunk_count", C.c_int32), ("oy", C.c_int32), ("ox", C.c_int32),
+                ("w_block", C.c_int32), ("n_blocks", C.c_int32)]
 
 
 class ConvDesc(C.Structure):
@@ -71,19 +75,23 @@ class ConvDesc(C.Structure):
         ("src", C.c_int32 * MAX_SRC),
         ("src_sy", C.c_int32 * MAX_SRC),
         ("src_sx", C.c_int32 * MAX_SRC),
+        ("src_ey", C.c_int32 * MAX_SRC),
+        ("src_ex", C.c_int32 * MAX_SRC),
         ("hg", C.c_int32), ("wg", C.c_int32),
         ("img_mult", C.c_int32),
         ("pair", C.c_int32),
         ("weights", C.POINTER(C.c_uint16)),
-        ("w_rows", C.c_int32), ("w_cols", C.c_int32),
+        ("w_elems", C.c_int64),
         ("kc", C.c_int32),
         ("n_tile", C.c_int32),
         ("cout", C.c_int32),
         ("cout_pad", C.c_int32),
         ("n_phase", C.c_int32),
         ("phase", Phase * MAX_PHASE),
-        ("kprog", C.POINTER(KEntry)),
-        ("n_kentry", C.c_int32),
+        ("chunks", C.POINTER(Chunk)),
+        ("n_chunks", C.c_int32),
+        ("taps", C.POINTER(Tap)),
+        ("n_taps", C.c_int32),
         ("osy", C.c_int32), ("osx", C.c_int32),
         ("scale", C.POINTER(C.c_float)),
         ("shift", C.POINTER(C.c_float)),
@@ -98,6 +106,8 @@ class ConvDesc(C.Structure):
         ("out_ext", C.c_int32),
     ]
 
+
+ABI_VERSION = 2
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -140,7 +150,7 @@ def lib() -> C.CDLL:
         fn = getattr(handle, name)
         fn.restype = restype
         fn.argtypes = argtypes
-    if handle.stcd_abi_version() != 1:
+    if handle.stcd_abi_version() != ABI_VERSION:
         raise StcdError("libstcd_b200.so ABI version mismatch")
     _lib = handle
     return handle

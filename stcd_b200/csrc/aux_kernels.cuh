@@ -9,9 +9,10 @@
 
 namespace stcd {
 
-// x1, x2: fp32 NCHW [n_valid, cin, h, w] -> dst bf16 NHWC [2*chunk, h, w, 16]; channels >= cin
-// are zero; T1 images occupy [0, chunk), T2 images [chunk, 2*chunk). One thread per pixel:
-// reads are coalesced per channel plane, each thread writes one 32-byte pixel.
+// x1, x2: fp32 NCHW [n_valid, cin, h, w] -> dst bf16 [2*chunk][2][h][w][8]; channels >= cin are
+// zero; T1 images occupy [0, chunk), T2 images [chunk, 2*chunk). One thread per pixel: reads are
+// coalesced per channel plane, each thread writes one 16-byte pixel chunk per channel plane (the
+// second plane only when cin > 8; it stays zero from plan creation otherwise).
 __global__ void __launch_bounds__(256) input_pack_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
                                                          __nv_bfloat16* __restrict__ dst, int chunk, int n_valid,
                                                          int cin, int hw) {
@@ -34,9 +35,9 @@ __global__ void __launch_bounds__(256) input_pack_kernel(const float* __restrict
       __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
       w[j] = *reinterpret_cast<uint32_t*>(&h);
     }
-    uint4* o = reinterpret_cast<uint4*>(dst + i * 16);
-    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    __nv_bfloat16* o = dst + (static_cast<size_t>(n) * 2 * hw + pix) * 8;
+    *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (cin > 8) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 

@@ -18,7 +18,7 @@
 
 #include "../../include/stcd_b200.h"
 #include "aux_kernels.cuh"
-#include "conv_gemm.cuh"
+#include "conv_ws.cuh"
 
 namespace {
 
@@ -57,10 +57,6 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-CUtensorMapSwizzle swizzle_for_kc(int kc) {
-  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-}
-
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Tensor {
@@ -72,10 +68,11 @@ struct Tensor {
 struct ConvOp {
   stcd_conv_desc d;
   std::vector<uint16_t> weights;
-  std::vector<stcd_kentry> kprog;
+  std::vector<stcd_chunk> chunks;
+  std::vector<stcd_tap> taps;
   std::vector<float> scale, shift, scale2, shift2;
   // device side
-  size_t w_off = 0, k_off = 0, s_off = 0;  // offsets in the constant arena
+  size_t w_off = 0, c_off = 0, t_off = 0, s_off = 0;  // offsets in the constant arena
   stcd::TmapPack tm;
   stcd::ConvParams p;
   dim3 grid;
@@ -133,41 +130,27 @@ int check_sm100(int device) {
   return STCD_OK;
 }
 
-int encode_act_map(CUtensorMap* m, void* base, int n, int h, int w, int c, int kc, int sx, int sy) {
+int encode_act_map(CUtensorMap* m, void* base, int n, int h, int w, int c, int kc, int sx, int sy, int ex, int ey) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(STCD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
-  cuuint64_t gdim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t gstr[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(stcd::kTileW * sx), (cuuint32_t)(stcd::kTileH * sy), 1};
-  cuuint32_t estr[4] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle_for_kc(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  // [img][c/8][h][w][8] bf16: dims fastest-first {8, w, h, c/8, img}
+  cuuint64_t gdim[5] = {8, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)(c / 8), (cuuint64_t)n};
+  cuuint64_t gstr[4] = {16, (cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)(c / 8) * h * w * 16};
+  cuuint32_t box[5] = {8, (cuuint32_t)((stcd::kTileW + ex) * sx), (cuuint32_t)((stcd::kTileH + ey) * sy), (cuuint32_t)(kc / 8), 1};
+  cuuint32_t estr[5] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return fail(STCD_ERR_CUDA, "cuTensorMapEncodeTiled(act n=%d h=%d w=%d c=%d kc=%d s=%d,%d) -> %d", n, h, w, c, kc,
-                sx, sy, (int)r);
-  return STCD_OK;
-}
-
-int encode_w_map(CUtensorMap* m, void* base, int rows, int cols, int kc, int n_tile) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return fail(STCD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)n_tile};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle_for_kc(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return fail(STCD_ERR_CUDA, "cuTensorMapEncodeTiled(weights %dx%d kc=%d n=%d) -> %d", rows, cols, kc, n_tile,
-                (int)r);
+    return fail(STCD_ERR_CUDA, "cuTensorMapEncodeTiled(act n=%d h=%d w=%d c=%d kc=%d s=%d,%d e=%d,%d) -> %d", n, h, w, c, kc,
+                sx, sy, ex, ey, (int)r);
   return STCD_OK;
 }
 
 bool valid_tensor(const stcd_plan* p, int id) { return id >= 0 && id < (int)p->tensors.size(); }
 
-int smem_budget_env() {
-  const char* e = getenv("STCD_SMEM_BUDGET");
-  return e ? atoi(e) : 0;
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 int launch_conv(const stcd_plan* plan, const ConvOp& op, int n_valid, float* const* outs, cudaStream_t st) {
@@ -177,10 +160,7 @@ int launch_conv(const stcd_plan* plan, const ConvOp& op, int n_valid, float* con
     p.out_f32 = outs[op.d.out_ext];
     if (!p.out_f32) return fail(STCD_ERR_INVALID, "external output %d is NULL", op.d.out_ext);
   }
-  if (op.mt == 2)
-    stcd::conv_gemm_kernel<2><<<op.grid, 128, op.smem, st>>>(op.tm, p);
-  else
-    stcd::conv_gemm_kernel<1><<<op.grid, 128, op.smem, st>>>(op.tm, p);
+  stcd::conv_ws_kernel<<<op.grid, stcd::kConvThreads, op.smem, st>>>(op.tm, p);
   CUDA_TRY(cudaGetLastError());
   (void)plan;
   return STCD_OK;
@@ -287,7 +267,7 @@ int stcd_plan_add_input_pack(stcd_plan* plan, int dst_tensor, int cin) {
   if (!valid_tensor(plan, dst_tensor)) return -fail(STCD_ERR_INVALID, "bad dst tensor %d", dst_tensor);
   const Tensor& t = plan->tensors[dst_tensor];
   if (t.mult != 2 || t.c != 16 || cin < 1 || cin > 16)
-    return -fail(STCD_ERR_INVALID, "input pack needs a [2*chunk, h, w, 16] tensor and cin <= 16 (got mult=%d c=%d cin=%d)",
+    return -fail(STCD_ERR_INVALID, "input pack needs a [2*chunk][2][h][w][8] tensor and cin <= 16 (got mult=%d c=%d cin=%d)",
                  t.mult, t.c, cin);
   plan->packs.push_back({dst_tensor, cin});
   plan->ops.push_back({1, (int)plan->packs.size() - 1});
@@ -306,20 +286,24 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
   if (d->cout < 1 || d->cout_pad < d->cout || d->cout_pad % d->n_tile)
     return -fail(STCD_ERR_INVALID, "cout %d / cout_pad %d / n_tile %d", d->cout, d->cout_pad, d->n_tile);
   if (d->n_phase < 1 || d->n_phase > STCD_MAX_PHASE) return -fail(STCD_ERR_INVALID, "n_phase %d", d->n_phase);
-  if (!d->weights || !d->kprog || !d->scale || !d->shift) return -fail(STCD_ERR_INVALID, "NULL weights/kprog/scale/shift");
+  if (!d->weights || !d->chunks || !d->taps || !d->scale || !d->shift)
+    return -fail(STCD_ERR_INVALID, "NULL weights/chunks/taps/scale/shift");
   if ((d->scale2 == nullptr) != (d->shift2 == nullptr)) return -fail(STCD_ERR_INVALID, "scale2/shift2 must come together");
-  if (d->w_rows < d->n_phase * d->cout_pad || d->w_cols < d->kc || d->w_cols % 8)
-    return -fail(STCD_ERR_INVALID, "weight matrix %dx%d too small", d->w_rows, d->w_cols);
   if (d->img_mult < 1 || d->img_mult > 2) return -fail(STCD_ERR_INVALID, "img_mult %d", d->img_mult);
   if (d->pair && d->img_mult != 1) return -fail(STCD_ERR_INVALID, "pair ops iterate over chunk_pairs images (img_mult=1)");
   if (d->out_diff >= 0 && !d->pair) return -fail(STCD_ERR_INVALID, "out_diff needs pair=1");
   const int mt = d->pair ? 2 : 1;
-  if (mt * d->n_tile > 512) return -fail(STCD_ERR_INVALID, "accumulators need %d TMEM columns (> 512)", mt * d->n_tile);
+  if (2 * mt * d->n_tile > 512)
+    return -fail(STCD_ERR_INVALID, "double-buffered accumulators need %d TMEM columns (> 512)", 2 * mt * d->n_tile);
   if (d->hg < 1 || d->wg < 1 || d->osy < 1 || d->osx < 1) return -fail(STCD_ERR_INVALID, "bad grid/stride");
   for (int s = 0; s < d->n_src; ++s) {
     if (!valid_tensor(plan, d->src[s])) return -fail(STCD_ERR_INVALID, "bad src tensor %d", d->src[s]);
     if (d->src_sy[s] < 1 || d->src_sy[s] > 8 || d->src_sx[s] < 1 || d->src_sx[s] > 8)
       return -fail(STCD_ERR_INVALID, "bad src stride");
+    if (d->src_ey[s] < 0 || d->src_ex[s] < 0 || d->src_ey[s] > 32 || d->src_ex[s] > 32)
+      return -fail(STCD_ERR_INVALID, "bad halo");
+    if ((d->src_sy[s] > 1 || d->src_sx[s] > 1) && (d->src_ey[s] || d->src_ex[s]))
+      return -fail(STCD_ERR_INVALID, "strided sources take one box per tap (halo must be 0)");
   }
   const int ho = d->hg * d->osy, wo = d->wg * d->osx;
   const int out_imgs = (d->pair ? 2 : d->img_mult);
@@ -345,29 +329,47 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
   }
   if (check_out(d->out_diff, ho, wo, 0, 1, "out_diff")) return -STCD_ERR_INVALID;
   if (d->out_ext >= 0 && (d->img_mult != 1 || d->pair)) return -fail(STCD_ERR_INVALID, "external outputs need img_mult=1");
-  if (d->n_kentry < 1) return -fail(STCD_ERR_INVALID, "empty K-program");
+  if (d->n_chunks < 1 || d->n_taps < 1) return -fail(STCD_ERR_INVALID, "empty K-program");
+  int blocks_total = 0;
   for (int ph = 0; ph < d->n_phase; ++ph) {
     const stcd_phase& f = d->phase[ph];
-    if (f.k_begin < 0 || f.k_count < 1 || f.k_count > stcd::kMaxKProg || f.k_begin + f.k_count > d->n_kentry)
-      return -fail(STCD_ERR_INVALID, "phase %d K-program slice [%d,+%d) out of range", ph, f.k_begin, f.k_count);
-    if (f.oy < 0 || f.oy >= d->osy || f.ox < 0 || f.ox >= d->osx || f.w_row < 0 || f.w_row + d->cout_pad > d->w_rows)
-      return -fail(STCD_ERR_INVALID, "phase %d offsets out of range", ph);
+    if (f.chunk_begin < 0 || f.chunk_count < 1 || f.chunk_count > stcd::kMaxChunks || f.chunk_begin + f.chunk_count > d->n_chunks)
+      return -fail(STCD_ERR_INVALID, "phase %d chunk slice [%d,+%d) out of range", ph, f.chunk_begin, f.chunk_count);
+    if (f.oy < 0 || f.oy >= d->osy || f.ox < 0 || f.ox >= d->osx) return -fail(STCD_ERR_INVALID, "phase %d offsets out of range", ph);
+    if (f.n_blocks < 1 || f.n_blocks > stcd::kMaxTaps || f.w_block != blocks_total)
+      return -fail(STCD_ERR_INVALID, "phase %d: n_blocks %d / w_block %d (expected %d)", ph, f.n_blocks, f.w_block, blocks_total);
+    int taps_seen = 0;
+    const int tap0 = d->chunks[f.chunk_begin].tap_begin;
+    for (int i = 0; i < f.chunk_count; ++i) {
+      const stcd_chunk& e = d->chunks[f.chunk_begin + i];
+      if (e.src < 0 || e.src >= d->n_src) return -fail(STCD_ERR_INVALID, "chunk %d: src %d", i, e.src);
+      const Tensor& t = plan->tensors[d->src[e.src]];
+      if (e.c0 < 0 || (e.c0 % 8) || e.c0 + d->kc > t.c)
+        return -fail(STCD_ERR_INVALID, "chunk %d: channels [%d,+%d) of %d", i, e.c0, d->kc, t.c);
+      const int top = (d->pair ? 1 : d->img_mult - 1) * plan->chunk + plan->chunk - 1 + e.n_off;
+      if (e.n_off < 0 || top >= t.mult * plan->chunk) return -fail(STCD_ERR_INVALID, "chunk %d: image offset %d overruns source", i, e.n_off);
+      if (e.n_taps < 1 || e.tap_begin != tap0 + taps_seen || e.tap_begin + e.n_taps > d->n_taps)
+        return -fail(STCD_ERR_INVALID, "chunk %d: taps [%d,+%d) not contiguous", i, e.tap_begin, e.n_taps);
+      for (int k = 0; k < e.n_taps; ++k) {
+        const stcd_tap& tp = d->taps[e.tap_begin + k];
+        if (tp.ty < 0 || tp.ty > d->src_ey[e.src] || tp.tx < 0 || tp.tx > d->src_ex[e.src])
+          return -fail(STCD_ERR_INVALID, "chunk %d tap %d: (%d,%d) outside the halo (%d,%d)", i, k, tp.ty, tp.tx,
+                       d->src_ey[e.src], d->src_ex[e.src]);
+      }
+      taps_seen += e.n_taps;
+    }
+    if (taps_seen != f.n_blocks) return -fail(STCD_ERR_INVALID, "phase %d: %d taps but n_blocks %d", ph, taps_seen, f.n_blocks);
+    blocks_total += f.n_blocks;
   }
-  for (int i = 0; i < d->n_kentry; ++i) {
-    const stcd_kentry& e = d->kprog[i];
-    if (e.src < 0 || e.src >= d->n_src) return -fail(STCD_ERR_INVALID, "kentry %d: src %d", i, e.src);
-    const Tensor& t = plan->tensors[d->src[e.src]];
-    if (e.c0 < 0 || e.c0 + d->kc > t.c) return -fail(STCD_ERR_INVALID, "kentry %d: channels [%d,+%d) of %d", i, e.c0, d->kc, t.c);
-    if (e.wk < 0 || e.wk + d->kc > d->w_cols) return -fail(STCD_ERR_INVALID, "kentry %d: wk %d", i, e.wk);
-    const int top = (d->pair ? 1 : d->img_mult - 1) * plan->chunk + plan->chunk - 1 + e.n_off;
-    if (e.n_off < 0 || top >= t.mult * plan->chunk) return -fail(STCD_ERR_INVALID, "kentry %d: image offset %d overruns source", i, e.n_off);
-  }
+  const int64_t need = (int64_t)(d->cout_pad / d->n_tile) * blocks_total * d->n_tile * d->kc;
+  if (d->w_elems != need) return -fail(STCD_ERR_INVALID, "weights: %lld elements, expected %lld", (long long)d->w_elems, (long long)need);
 
   ConvOp op;
   op.d = *d;
   op.mt = mt;
-  op.weights.assign(d->weights, d->weights + (size_t)d->w_rows * d->w_cols);
-  op.kprog.assign(d->kprog, d->kprog + d->n_kentry);
+  op.weights.assign(d->weights, d->weights + d->w_elems);
+  op.chunks.assign(d->chunks, d->chunks + d->n_chunks);
+  op.taps.assign(d->taps, d->taps + d->n_taps);
   op.scale.assign(d->scale, d->scale + d->cout_pad);
   op.shift.assign(d->shift, d->shift + d->cout_pad);
   if (d->scale2) {
@@ -375,7 +377,8 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
     op.shift2.assign(d->shift2, d->shift2 + d->cout_pad);
   }
   op.d.weights = nullptr;
-  op.d.kprog = nullptr;
+  op.d.chunks = nullptr;
+  op.d.taps = nullptr;
   op.d.scale = op.d.shift = op.d.scale2 = op.d.shift2 = nullptr;
   if (d->out_ext >= 0) {
     plan->n_ext = std::max(plan->n_ext, d->out_ext + 1);
@@ -406,8 +409,10 @@ int stcd_plan_finalize(stcd_plan* plan) {
   for (ConvOp& op : plan->convs) {
     op.w_off = aoff;
     aoff += round_up(op.weights.size() * 2, 1024);
-    op.k_off = aoff;
-    aoff += round_up(op.kprog.size() * sizeof(stcd_kentry), 256);
+    op.c_off = aoff;
+    aoff += round_up(op.chunks.size() * sizeof(stcd_chunk), 256);
+    op.t_off = aoff;
+    aoff += round_up(op.taps.size() * sizeof(stcd_tap), 256);
     op.s_off = aoff;
     aoff += round_up((size_t)op.d.cout_pad * 4 * 4, 256);
   }
@@ -416,7 +421,8 @@ int stcd_plan_finalize(stcd_plan* plan) {
   std::vector<uint8_t> host(plan->arena_bytes, 0);
   for (ConvOp& op : plan->convs) {
     memcpy(host.data() + op.w_off, op.weights.data(), op.weights.size() * 2);
-    memcpy(host.data() + op.k_off, op.kprog.data(), op.kprog.size() * sizeof(stcd_kentry));
+    memcpy(host.data() + op.c_off, op.chunks.data(), op.chunks.size() * sizeof(stcd_chunk));
+    memcpy(host.data() + op.t_off, op.taps.data(), op.taps.size() * sizeof(stcd_tap));
     const size_t n = op.d.cout_pad;
     memcpy(host.data() + op.s_off, op.scale.data(), n * 4);
     memcpy(host.data() + op.s_off + n * 4, op.shift.data(), n * 4);
@@ -427,62 +433,98 @@ int stcd_plan_finalize(stcd_plan* plan) {
   }
   CUDA_TRY(cudaMemcpy(plan->arena, host.data(), plan->arena_bytes, cudaMemcpyHostToDevice));
 
-  static_assert(sizeof(stcd_kentry) == sizeof(stcd::KEntry), "kentry layout");
-  CUDA_TRY(cudaFuncSetAttribute(stcd::conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192));
-  CUDA_TRY(cudaFuncSetAttribute(stcd::conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192));
+  static_assert(sizeof(stcd_chunk) == sizeof(stcd::Chunk), "chunk layout");
+  static_assert(sizeof(stcd_tap) == sizeof(stcd::Tap), "tap layout");
+  const size_t kSmemMax = 227 * 1024 - 12 * 1024;  // dynamic budget: static tables + barriers live beside it
+  CUDA_TRY(cudaFuncSetAttribute(stcd::conv_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  int n_sm = 148;
+  CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, plan->device));
 
-  const int budget_env = smem_budget_env();
+  const int force_occ = env_int("STCD_FORCE_OCC", 0);
+  const int force_stream = env_int("STCD_FORCE_WSTREAM", 0);
   for (ConvOp& op : plan->convs) {
     const stcd_conv_desc& d = op.d;
     memset(&op.tm, 0, sizeof(op.tm));
-    for (int s = 0; s < d.n_src; ++s) {
-      const Tensor& t = plan->tensors[d.src[s]];
-      int r = encode_act_map(&op.tm.src[s], t.ptr, t.mult * plan->chunk, t.h, t.w, t.c, d.kc, d.src_sx[s], d.src_sy[s]);
-      if (r) return r;
-    }
-    int r = encode_w_map(&op.tm.w, plan->arena + op.w_off, d.w_rows, d.w_cols, d.kc, d.n_tile);
-    if (r) return r;
-
     stcd::ConvParams& p = op.p;
     memset(&p, 0, sizeof(p));
+    size_t a_sub = 0;
+    for (int s = 0; s < d.n_src; ++s) {
+      const Tensor& t = plan->tensors[d.src[s]];
+      int r = encode_act_map(&op.tm.src[s], t.ptr, t.mult * plan->chunk, t.h, t.w, t.c, d.kc, d.src_sx[s], d.src_sy[s],
+                             d.src_ex[s], d.src_ey[s]);
+      if (r) return r;
+      p.src_sy[s] = d.src_sy[s];
+      p.src_sx[s] = d.src_sx[s];
+      p.src_pw[s] = stcd::kTileW + d.src_ex[s];
+      p.src_ph[s] = stcd::kTileH + d.src_ey[s];
+      a_sub = std::max(a_sub, (size_t)(d.kc / 8) * p.src_pw[s] * p.src_ph[s] * 16);
+    }
     p.hg = d.hg;
     p.wg = d.wg;
     p.tiles_x = (d.wg + stcd::kTileW - 1) / stcd::kTileW;
     p.tiles_y = (d.hg + stcd::kTileH - 1) / stcd::kTileH;
     p.n_img = (d.pair ? 1 : d.img_mult) * plan->chunk;
+    p.n_tiles = p.tiles_x * p.tiles_y * p.n_img;
     p.pair_off = d.pair ? plan->chunk : 0;
-    for (int s = 0; s < d.n_src; ++s) {
-      p.src_sy[s] = d.src_sy[s];
-      p.src_sx[s] = d.src_sx[s];
-    }
+    p.n_ntiles = d.cout_pad / d.n_tile;
     p.osy = d.osy;
     p.osx = d.osx;
     p.ho = d.hg * d.osy;
     p.wo = d.wg * d.osx;
     p.n_phase = d.n_phase;
-    int kmin = 1 << 30;
+    int max_blocks = 0, blocks_total = 0;
     for (int ph = 0; ph < d.n_phase; ++ph) {
-      p.phase[ph] = {d.phase[ph].k_begin, d.phase[ph].k_count, d.phase[ph].oy, d.phase[ph].ox, d.phase[ph].w_row};
-      kmin = std::min(kmin, d.phase[ph].k_count);
+      p.phase[ph] = {d.phase[ph].chunk_begin, d.phase[ph].chunk_count, d.phase[ph].oy, d.phase[ph].ox, d.phase[ph].w_block,
+                     d.phase[ph].n_blocks};
+      max_blocks = std::max(max_blocks, d.phase[ph].n_blocks);
+      blocks_total += d.phase[ph].n_blocks;
     }
-    p.kprog = reinterpret_cast<const stcd::KEntry*>(plan->arena + op.k_off);
+    p.blocks_per_ntile = blocks_total;
+    p.chunks = reinterpret_cast<const stcd::Chunk*>(plan->arena + op.c_off);
+    p.taps = reinterpret_cast<const stcd::Tap*>(plan->arena + op.t_off);
+    p.wpack = plan->arena + op.w_off;
     p.kc = d.kc;
     p.n_tile = d.n_tile;
     p.cout = d.cout;
-    p.a_bytes = 128u * d.kc * 2;
-    p.b_bytes = (uint32_t)d.n_tile * d.kc * 2;
-    p.sub_bytes = op.mt * p.a_bytes + (uint32_t)round_up(p.b_bytes, 1024);
-    p.group = std::max(1, std::min(64 / d.kc, kmin));
-    const size_t stage_bytes = (size_t)p.sub_bytes * p.group;
-    size_t budget = budget_env > 0 ? (size_t)budget_env : (p.sub_bytes <= 16384 ? 64 * 1024 : 100 * 1024);
-    int stages = (int)(budget / stage_bytes);
-    stages = std::max(2, std::min(stages, 8));
-    p.stages = stages;
-    op.smem = stage_bytes * stages + 1024;
-    if (op.smem > 227 * 1024 - 8192) return fail(STCD_ERR_INVALID, "conv op needs %zu B of shared memory", op.smem);
+    p.mt = op.mt;
+    p.wblk_bytes = (uint32_t)d.n_tile * d.kc * 2;
+    p.a_sub_bytes = (uint32_t)round_up(a_sub, 128);
+    p.a_stage_bytes = op.mt * p.a_sub_bytes;
+    p.acc_cols = op.mt * d.n_tile;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(op.mt * d.n_tile)) cols <<= 1;
+    while (cols < 2 * p.acc_cols) cols <<= 1;
     p.tmem_cols = cols;
+    // ---- shared-memory plan: weight-stationary when every block of a phase fits beside >= 2 A stages
+    const size_t w_all = (size_t)max_blocks * p.wblk_bytes;
+    const int groups = d.n_phase * p.n_ntiles;
+    int occ = 0;
+    for (int o = 2; o >= 1 && !occ; --o) {
+      if (force_occ && o != force_occ) continue;
+      if (cols * o > 512) continue;
+      const size_t budget = (o == 2 ? (kSmemMax - 2048) / 2 : kSmemMax) - 256;
+      const int min_stages = (o == 2) ? 3 : 2;
+      if (!force_stream && w_all + (size_t)min_stages * p.a_stage_bytes <= budget) {
+        occ = o;
+        p.w_resident = 1;
+        p.w_stages = 0;
+        p.a_stages = (int)std::min<size_t>(stcd::kMaxAStages, (budget - round_up(w_all, 128)) / p.a_stage_bytes);
+      } else if (o == 1) {
+        occ = 1;
+        p.w_resident = 0;
+        const size_t a_min = 3 * (size_t)p.a_stage_bytes;
+        if (a_min + 2 * (size_t)p.wblk_bytes > budget) return fail(STCD_ERR_INVALID, "conv op does not fit shared memory");
+        p.w_stages = (int)std::min<size_t>(std::min<size_t>(stcd::kMaxWStages, (size_t)max_blocks),
+                                           std::max<size_t>(2, (budget - a_min) / p.wblk_bytes));
+        p.a_stages = (int)std::min<size_t>(stcd::kMaxAStages,
+                                           (budget - round_up((size_t)p.w_stages * p.wblk_bytes, 128)) / p.a_stage_bytes);
+      }
+    }
+    if (!occ) return fail(STCD_ERR_INVALID, "conv op: no shared-memory plan (forced occupancy %d)", force_occ);
+    const size_t w_region = round_up(p.w_resident ? w_all : (size_t)p.w_stages * p.wblk_bytes, 128);
+    op.smem = w_region + (size_t)p.a_stages * p.a_stage_bytes + 128;
+    if (op.smem > kSmemMax) return fail(STCD_ERR_INVALID, "conv op needs %zu B of shared memory", op.smem);
+    const int ctas = std::max(1, (n_sm * occ) / groups);
+    op.grid = dim3((unsigned)std::min(p.n_tiles, ctas), (unsigned)groups, 1);
     const float* sc = reinterpret_cast<const float*>(plan->arena + op.s_off);
     p.scale = sc;
     p.shift = sc + d.cout_pad;
@@ -493,26 +535,25 @@ int stcd_plan_finalize(stcd_plan* plan) {
     p.relu = d.relu;
     if (d.res >= 0) {
       p.res = (const __nv_bfloat16*)plan->tensors[d.res].ptr;
-      p.res_c = plan->tensors[d.res].c;
+      p.res_c8 = plan->tensors[d.res].c / 8;
     }
     if (d.out0 >= 0) {
       p.out0 = (__nv_bfloat16*)plan->tensors[d.out0].ptr;
-      p.out0_c = plan->tensors[d.out0].c;
+      p.out0_c8 = plan->tensors[d.out0].c / 8;
       p.out0_coff = d.out0_coff;
     }
     if (d.out_raw >= 0) {
       p.out_raw = (__nv_bfloat16*)plan->tensors[d.out_raw].ptr;
-      p.out_raw_c = plan->tensors[d.out_raw].c;
+      p.out_raw_c8 = plan->tensors[d.out_raw].c / 8;
     }
     if (d.out_pool >= 0) {
       p.out_pool = (__nv_bfloat16*)plan->tensors[d.out_pool].ptr;
-      p.out_pool_c = plan->tensors[d.out_pool].c;
+      p.out_pool_c8 = plan->tensors[d.out_pool].c / 8;
     }
     if (d.out_diff >= 0) {
       p.out_diff = (__nv_bfloat16*)plan->tensors[d.out_diff].ptr;
-      p.out_diff_c = plan->tensors[d.out_diff].c;
+      p.out_diff_c8 = plan->tensors[d.out_diff].c / 8;
     }
-    op.grid = dim3((unsigned)(p.tiles_x * p.tiles_y * p.n_img * d.n_phase), (unsigned)(d.cout_pad / d.n_tile), 1);
   }
   plan->finalized = true;
   return STCD_OK;

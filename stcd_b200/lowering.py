@@ -1,9 +1,11 @@
 """Lowering of reference modules to the fused-op program libstcd_b200 executes.
 
-A *program* is a list of ops over NHWC bf16 tensors holding ``mult * chunk`` images (``mult`` = 2
+A *program* is a list of ops over bf16 activation tensors (logical NHWC here; stored
+channel-chunked [img][c/8][h][w][8] on the device) holding ``mult * chunk`` images (``mult`` = 2
 for tensors that carry both temporal streams: T1 images first, then T2 images).  The only
 compute op is the implicit-GEMM convolution (``ConvSpec``): its A operand is described by a
-K-program (list of ``KEntry``: which source tensor, which filter tap, which channel block),
+K-program (list of ``Chunk``: which source tensor, which channel block, which pixel box, and
+the filter taps that read that box),
 its B operand is a host-packed bf16 weight matrix, and its epilogue carries the folded
 BatchNorm, ReLU, residual add, Siamese ``|f1 - f2|`` and 2x2 max-pool.
 
@@ -19,8 +21,9 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-TILE_H, TILE_W = 8, 16
+TILE_H, TILE_W = 16, 8
 MAX_SRC = 6
+MAX_CHUNKS, MAX_TAPS = 128, 512
 
 
 def _bf16_bits(x: torch.Tensor) -> np.ndarray:
@@ -42,22 +45,26 @@ class TensorSpec:
 
 
 @dataclass
-class KEntry:
-    src: int      # index into ConvSpec.srcs
-    dy: int       # input row offset (un-strided source pixels)
-    dx: int
-    c0: int       # first channel of the block inside the source tensor
+class Chunk:
+    """One A-stage load: channels [c0, c0+kc) of source `src` over the box whose origin is
+    (ty*sy + by, tx*sx + bx) for the tile at tile-pixel (ty, tx); feeds taps [tap_begin, +n_taps)."""
+    src: int
+    c0: int
+    by: int
+    bx: int
     stream: int   # image offset in units of `chunk` (0: same image, 1: the T2 partner)
-    wk: int       # first weight column
+    tap_begin: int
+    n_taps: int
 
 
 @dataclass
 class Phase:
-    k_begin: int
-    k_count: int
+    chunk_begin: int
+    chunk_count: int
     oy: int
     ox: int
-    w_row: int
+    w_block: int
+    n_blocks: int
 
 
 @dataclass
@@ -66,17 +73,20 @@ class ConvSpec:
     srcs: List[str]
     src_sy: List[int]
     src_sx: List[int]
+    src_ey: List[int]
+    src_ex: List[int]
     hg: int
     wg: int
     img_mult: int
     pair: bool
-    weights: np.ndarray          # uint16 [w_rows, w_cols] (bf16 bits), K-major
+    weights: np.ndarray          # uint16 [n_ntiles, total blocks, kc/8, n_tile, 8] (bf16 bits)
     kc: int
     n_tile: int
     cout: int
     cout_pad: int
     phases: List[Phase]
-    kprog: List[KEntry]
+    chunks: List[Chunk]
+    taps: List[Tuple[int, int]]  # (ty, tx) inside the chunk's box; tap t of a phase <-> weight block t
     osy: int
     osx: int
     scale: np.ndarray            # float32 [cout_pad]
@@ -92,6 +102,11 @@ class ConvSpec:
     out_diff: Optional[str] = None
     out_ext: int = -1
     macs_per_pair: int = 0       # reference-equivalent MACs (for the roofline), per image pair
+
+    def weight_block(self, nt: int, block: int) -> torch.Tensor:
+        """fp32 [n_tile, kc] view of one packed weight block (for the emulator)."""
+        w = bf16_bits_to_f32(self.weights[nt, block])            # [kc/8, n_tile, 8]
+        return w.permute(1, 0, 2).reshape(self.n_tile, self.kc)
 
 
 @dataclass
@@ -187,6 +202,7 @@ def choose_kc(c_list: Sequence[int]) -> int:
 
 
 def choose_n_tile(cout: int, pair: bool) -> Tuple[int, int]:
+    """N per CTA: accumulators are double-buffered in TMEM (512 columns): 2 * (2 if pair else 1) * n_tile <= 512."""
     cp = (cout + 15) // 16 * 16
     limit = 128 if pair else 256
     if cp <= limit:
@@ -202,12 +218,15 @@ def _taps_to_gemm(
     phase_taps: Sequence[Tuple[int, int, List[Tuple[int, int, torch.Tensor]]]],
     cout: int,
     pair: bool,
-) -> Tuple[np.ndarray, int, int, int, List[Phase], List[KEntry], List[str]]:
-    """Build (weights, kc, n_tile, cout_pad, phases, kprog, srcs).
+):
+    """Build the K-program and the packed weights.
 
-    phase_taps: per phase (oy, ox, [(dy, dx, W[cout, cin_total])...]) where dy/dx are offsets in
-    tile-pixel units *before* the per-source stride is applied (the K entry stores
-    dy*1, the kernel adds tile_origin*stride), and cin_total indexes the concatenated segments.
+    phase_taps: per phase (oy, ox, [(dy, dx, W[cout, cin_total])...]): dy/dx are input offsets in
+    un-strided source pixels relative to (tile pixel * source stride); cin_total indexes the
+    concatenated segments.
+
+    Stride-1 sources load ONE box per (phase, channel chunk) that covers every tap of the phase
+    (halo reuse); strided sources load one box per tap.
     """
     srcs: List[str] = []
     for s in segs:
@@ -218,37 +237,65 @@ def _taps_to_gemm(
     stored_c = [prog.tensors[s.tensor].c for s in segs]
     kc = choose_kc(stored_c)
     n_tile, cout_pad = choose_n_tile(cout, pair)
+    n_nt = cout_pad // n_tile
+    sy = [1] * len(srcs)
+    sx = [1] * len(srcs)
+    for s in segs:
+        sy[srcs.index(s.tensor)] = s.sy
+        sx[srcs.index(s.tensor)] = s.sx
+    # halo extents per source: max over phases of the tap range (stride-1 sources only)
+    ey = [0] * len(srcs)
+    ex = [0] * len(srcs)
+    for (_, _, taps) in phase_taps:
+        dys = [t[0] for t in taps]
+        dxs = [t[1] for t in taps]
+        for i in range(len(srcs)):
+            if sy[i] == 1 and sx[i] == 1:
+                ey[i] = max(ey[i], max(dys) - min(dys))
+                ex[i] = max(ex[i], max(dxs) - min(dxs))
     phases: List[Phase] = []
-    kprog: List[KEntry] = []
-    cols: List[List[torch.Tensor]] = []
+    chunks: List[Chunk] = []
+    tap_list: List[Tuple[int, int]] = []
+    blocks: List[torch.Tensor] = []          # each [cout_pad, kc]
     for (oy, ox, taps) in phase_taps:
-        k_begin = len(kprog)
-        wk = 0
-        blocks: List[torch.Tensor] = []
-        for (dy, dx, wtap) in taps:
-            ci = 0
-            for s, sc in zip(segs, stored_c):
-                wseg = torch.zeros(cout_pad, sc, dtype=torch.float32)
-                wseg[:cout, : s.c_real] = wtap[:, ci: ci + s.c_real]
-                ci += s.c_real
-                for c0 in range(0, sc, kc):
-                    blk = wseg[:, c0: c0 + kc]
-                    if c0 >= s.c_real:  # pure padding block: contributes nothing, skip it
-                        continue
-                    kprog.append(KEntry(srcs.index(s.tensor), dy, dx, c0, s.stream, wk))
-                    blocks.append(blk)
-                    wk += kc
+        chunk_begin, w_block = len(chunks), len(blocks)
+        dy0 = min(t[0] for t in taps)
+        dx0 = min(t[1] for t in taps)
+        ci = 0
+        for s, sc in zip(segs, stored_c):
+            si = srcs.index(s.tensor)
+            halo = (sy[si] == 1 and sx[si] == 1)
+            for c0 in range(0, sc, kc):
+                if c0 >= s.c_real:      # pure padding chunk: contributes nothing
+                    continue
+
+                def wblock(wtap):
+                    blk = torch.zeros(cout_pad, kc, dtype=torch.float32)
+                    n_real = min(kc, s.c_real - c0)
+                    blk[:cout, :n_real] = wtap[:, ci + c0: ci + c0 + n_real]
+                    return blk
+
+                if halo:
+                    chunks.append(Chunk(si, c0, dy0, dx0, s.stream, len(tap_list), len(taps)))
+                    for (dy, dx, wtap) in taps:
+                        tap_list.append((dy - dy0, dx - dx0))
+                        blocks.append(wblock(wtap))
+                else:
+                    for (dy, dx, wtap) in taps:
+                        chunks.append(Chunk(si, c0, dy, dx, s.stream, len(tap_list), 1))
+                        tap_list.append((0, 0))
+                        blocks.append(wblock(wtap))
+            ci += s.c_real
+        for (_, _, wtap) in taps:
             if ci != wtap.shape[1]:
                 raise ValueError(f"{name}: weight has {wtap.shape[1]} input channels, segments give {ci}")
-        phases.append(Phase(k_begin, len(kprog) - k_begin, oy, ox, len(phases) * cout_pad))
-        cols.append(blocks)
-    w_cols = max(sum(b.shape[1] for b in blocks) for blocks in cols)
-    wmat = torch.zeros(len(phases) * cout_pad, w_cols, dtype=torch.float32)
-    for ph, blocks in enumerate(cols):
-        if blocks:
-            row = torch.cat(blocks, dim=1)
-            wmat[ph * cout_pad: (ph + 1) * cout_pad, : row.shape[1]] = row
-    return _bf16_bits(wmat), kc, n_tile, cout_pad, phases, kprog, srcs
+        phases.append(Phase(chunk_begin, len(chunks) - chunk_begin, oy, ox, w_block, len(blocks) - w_block))
+        if phases[-1].chunk_count > MAX_CHUNKS or phases[-1].n_blocks > MAX_TAPS:
+            raise ValueError(f"{name}: K-program too long ({phases[-1].chunk_count} chunks, {phases[-1].n_blocks} taps)")
+    wall = torch.stack(blocks, 0)                                    # [B, cout_pad, kc]
+    wall = wall.reshape(len(blocks), n_nt, n_tile, kc // 8, 8)       # [B, nt, n, k8, 8]
+    wall = wall.permute(1, 0, 3, 2, 4).contiguous()                  # [nt, B, k8, n, 8]
+    return _bf16_bits(wall), kc, n_tile, cout_pad, phases, chunks, tap_list, srcs, sy, sx, ey, ex
 
 
 def conv_taps(weight: torch.Tensor, pad: int, stride: int = 1) -> List[Tuple[int, int, List]]:
@@ -312,16 +359,11 @@ def add_conv(
     out_ext: int = -1,
     macs_per_pair: int = 0,
 ) -> ConvSpec:
-    wbits, kc, n_tile, cout_pad, phases, kprog, srcs = _taps_to_gemm(prog, name, segs, phase_taps, cout, pair)
-    sy = [1] * len(srcs)
-    sx = [1] * len(srcs)
-    for s in segs:
-        sy[srcs.index(s.tensor)] = s.sy
-        sx[srcs.index(s.tensor)] = s.sx
-    # K entries carry offsets in un-strided source pixels
+    wbits, kc, n_tile, cout_pad, phases, chunks, taps, srcs, sy, sx, ey, ex = _taps_to_gemm(
+        prog, name, segs, phase_taps, cout, pair)
     spec = ConvSpec(
-        name=name, srcs=srcs, src_sy=sy, src_sx=sx, hg=hg, wg=wg, img_mult=img_mult, pair=pair,
-        weights=wbits, kc=kc, n_tile=n_tile, cout=cout, cout_pad=cout_pad, phases=phases, kprog=kprog,
+        name=name, srcs=srcs, src_sy=sy, src_sx=sx, src_ey=ey, src_ex=ex, hg=hg, wg=wg, img_mult=img_mult, pair=pair,
+        weights=wbits, kc=kc, n_tile=n_tile, cout=cout, cout_pad=cout_pad, phases=phases, chunks=chunks, taps=taps,
         osy=osy, osx=osx, scale=_pad_vec(scale, cout_pad, 1.0), shift=_pad_vec(shift, cout_pad, 0.0),
         scale2=None if scale2 is None else _pad_vec(scale2, cout_pad, 1.0),
         shift2=None if shift2 is None else _pad_vec(shift2, cout_pad, 0.0),

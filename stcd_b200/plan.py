@@ -63,21 +63,28 @@ class Plan:
             d.src[i] = ids[s]
             d.src_sy[i] = op.src_sy[i]
             d.src_sx[i] = op.src_sx[i]
+            d.src_ey[i] = op.src_ey[i]
+            d.src_ex[i] = op.src_ex[i]
         d.hg, d.wg = op.hg, op.wg
         d.img_mult = op.img_mult
         d.pair = 1 if op.pair else 0
         w = np.ascontiguousarray(op.weights, dtype=np.uint16)
         d.weights = w.ctypes.data_as(C.POINTER(C.c_uint16))
-        d.w_rows, d.w_cols = w.shape
+        d.w_elems = w.size
         d.kc, d.n_tile, d.cout, d.cout_pad = op.kc, op.n_tile, op.cout, op.cout_pad
         d.n_phase = len(op.phases)
         for i, ph in enumerate(op.phases):
-            d.phase[i] = _lib.Phase(ph.k_begin, ph.k_count, ph.oy, ph.ox, ph.w_row)
-        kp = (_lib.KEntry * len(op.kprog))()
-        for i, e in enumerate(op.kprog):
-            kp[i] = _lib.KEntry(e.src, e.dy, e.dx, e.c0, e.stream * self.chunk, e.wk)
-        d.kprog = C.cast(kp, C.POINTER(_lib.KEntry))
-        d.n_kentry = len(op.kprog)
+            d.phase[i] = _lib.Phase(ph.chunk_begin, ph.chunk_count, ph.oy, ph.ox, ph.w_block, ph.n_blocks)
+        ck = (_lib.Chunk * len(op.chunks))()
+        for i, e in enumerate(op.chunks):
+            ck[i] = _lib.Chunk(e.src, e.c0, e.by, e.bx, e.stream * self.chunk, e.tap_begin, e.n_taps)
+        d.chunks = C.cast(ck, C.POINTER(_lib.Chunk))
+        d.n_chunks = len(op.chunks)
+        tp = (_lib.Tap * len(op.taps))()
+        for i, (ty, tx) in enumerate(op.taps):
+            tp[i] = _lib.Tap(ty, tx)
+        d.taps = C.cast(tp, C.POINTER(_lib.Tap))
+        d.n_taps = len(op.taps)
         d.osy, d.osx = op.osy, op.osx
         keep = [np.ascontiguousarray(op.scale, np.float32), np.ascontiguousarray(op.shift, np.float32),
                 None if op.scale2 is None else np.ascontiguousarray(op.scale2, np.float32),
@@ -159,18 +166,18 @@ class Plan:
 
     # ------------------------------------------------------------------ diagnostics
     def read_tensor(self, name: str) -> torch.Tensor:
-        """Activation tensor `name` as fp32 [mult*chunk, h, w, c] on the host (synchronous)."""
+        """Activation tensor `name` as fp32 logical NHWC [mult*chunk, h, w, c] on the host (synchronous)."""
         t = self.prog.tensors[name]
-        buf = torch.empty(t.mult * self.chunk, t.h, t.w, t.c, dtype=torch.bfloat16)
+        buf = torch.empty(t.mult * self.chunk, t.c // 8, t.h, t.w, 8, dtype=torch.bfloat16)   # device layout
         _lib.check(self.lib.stcd_plan_tensor_copy(self._h, self.tensor_ids[name], C.c_void_p(buf.data_ptr()),
                                                   buf.numel() * 2, 0), f"read tensor {name}")
-        return buf.to(torch.float32)
+        return buf.permute(0, 2, 3, 1, 4).reshape(t.mult * self.chunk, t.h, t.w, t.c).to(torch.float32)
 
     def write_tensor(self, name: str, value: torch.Tensor) -> None:
         t = self.prog.tensors[name]
-        buf = value.to(torch.bfloat16).contiguous()
-        if tuple(buf.shape) != (t.mult * self.chunk, t.h, t.w, t.c):
-            raise ValueError(f"tensor {name} is {(t.mult * self.chunk, t.h, t.w, t.c)}, got {tuple(buf.shape)}")
+        if tuple(value.shape) != (t.mult * self.chunk, t.h, t.w, t.c):
+            raise ValueError(f"tensor {name} is {(t.mult * self.chunk, t.h, t.w, t.c)}, got {tuple(value.shape)}")
+        buf = value.to(torch.bfloat16).reshape(t.mult * self.chunk, t.h, t.w, t.c // 8, 8).permute(0, 3, 1, 2, 4).contiguous()
         _lib.check(self.lib.stcd_plan_tensor_copy(self._h, self.tensor_ids[name], C.c_void_p(buf.data_ptr()),
                                                   buf.numel() * 2, 1), f"write tensor {name}")
 

@@ -23,13 +23,13 @@ def test_library_builds_and_exports_header_symbols():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/stcd_b200.h but not exported"
         assert name in bound, f"{name} has no ctypes signature in stcd_b200/_lib.py"
-    assert lib.stcd_abi_version() == 1
+    assert lib.stcd_abi_version() == _lib.ABI_VERSION
 
 
 def test_struct_layouts_match_header():
     # sizes the C side static_asserts / validates; a drifted ctypes mirror corrupts plans silently
-    assert C.sizeof(_lib.KEntry) == 16
-    assert C.sizeof(_lib.Phase) == 20
+    assert C.sizeof(_lib.Chunk) == 16 and C.sizeof(_lib.Tap) == 4
+    assert C.sizeof(_lib.Phase) == 24
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")

@@ -39,7 +39,7 @@ def test_program_structure_and_macs():
     assert abs(prog.macs_per_pair() / 1e9 - 4.228) < 0.001
     up = [o for o in convs if o.name.startswith("upconv")]
     assert all(len(o.phases) == 4 and o.osy == 2 and o.osx == 2 for o in up)
-    taps = sorted(ph.k_count * o.kc // 128 for o in up[:1] for ph in o.phases)
+    taps = sorted(ph.n_blocks * o.kc // 128 for o in up[:1] for ph in o.phases)
     assert taps == [1, 2, 2, 4]          # stride-2 ConvTranspose2d(k3): taps per output phase
     assert abs(siamunet.SiamUnet_conc(3, 2).eval().lower(256, 256).macs_per_pair() / 1e9 - 4.832) < 0.001
 
