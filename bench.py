@@ -35,11 +35,11 @@ import torch  # noqa: E402
 
 # workload -> (net kind, ctor args, synth gain, H, W, per-GPU batch, binarise kind, config string)
 WORKLOADS = {
-    "siamunet_diff_256": dict(net="SiamUnet_diff", n_class=2, gain=0.8, h=256, w=256, batch=8, kind="argmax",
+    "siamunet_diff_256": dict(net="SiamUnet_diff", n_class=2, h=256, w=256, batch=8, kind="argmax",
                               desc="C1: SiamUnet_diff 256x256 RGB pairs, batch 8 per GPU"),
-    "siamunet_diff_256_b64": dict(net="SiamUnet_diff", n_class=2, gain=0.8, h=256, w=256, batch=64, kind="argmax",
+    "siamunet_diff_256_b64": dict(net="SiamUnet_diff", n_class=2, h=256, w=256, batch=64, kind="argmax",
                                   desc="SiamUnet_diff 256x256 RGB pairs, batch 64 per GPU"),
-    "siamunet_conc_256": dict(net="SiamUnet_conc", n_class=2, gain=0.75, h=256, w=256, batch=8, kind="argmax",
+    "siamunet_conc_256": dict(net="SiamUnet_conc", n_class=2, h=256, w=256, batch=8, kind="argmax",
                               desc="SiamUnet_conc 256x256 RGB pairs, batch 8 per GPU"),
 }
 DEFAULT_WORKLOAD = "siamunet_diff_256_b64"
@@ -48,7 +48,7 @@ DEFAULT_WORKLOAD = "siamunet_diff_256_b64"
 def build_net(wl):
     from stcd_b200 import siamunet, synth
     cls = {"SiamUnet_diff": siamunet.SiamUnet_diff, "SiamUnet_conc": siamunet.SiamUnet_conc}[wl["net"]]
-    return synth.randomize_(cls(3, wl["n_class"]).eval(), gain=wl["gain"])
+    return synth.randomize_(cls(3, wl["n_class"]).eval(), gain=synth.GAINS[wl["net"]])
 
 
 def oracle_forward(wl, sd, x1, x2):

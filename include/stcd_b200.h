@@ -156,6 +156,12 @@ int stcd_plan_finalize(stcd_plan* plan);
  * `bytes` must equal the tensor's size. */
 int stcd_plan_tensor_copy(stcd_plan* plan, int tensor_id, void* host, int64_t bytes, int to_device);
 
+/* Diagnostics: launch geometry of conv op `op_index` (info[0..9] = grid.x, grid.y, dynamic smem,
+ * A stages, W stages, W resident, TMEM columns, tiles, A stage bytes, W block bytes) and, when the
+ * plan was finalized with STCD_TRACE=1 in the environment, 16 clock stamps per CTA of its last
+ * launch.  Returns the number of int64 words written to `host`, or -1. */
+int64_t stcd_plan_read_trace(stcd_plan* plan, int op_index, int64_t* host, int64_t max_words, int32_t* info);
+
 /* bytes of device memory the plan owns (workspace + weights) */
 int64_t stcd_plan_workspace_bytes(const stcd_plan* plan);
 /* number of kernels one stcd_forward of n_pairs launches (for bench.py's gpu_launches) */

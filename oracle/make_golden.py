@@ -20,8 +20,8 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 
 # name -> (reference module path, class, ctor args, gain, batch, H, W)
 CASES = {
-    "siamunet_diff": ("models.SiamUnet_diff", "SiamUnet_diff", (3, 2), 0.8, 2, 48, 32),
-    "siamunet_conc": ("models.SiamUnet_conc", "SiamUnet_conc", (3, 2), 0.75, 2, 32, 48),
+    "siamunet_diff": ("models.SiamUnet_diff", "SiamUnet_diff", (3, 2), synth.GAINS["SiamUnet_diff"], 2, 48, 32),
+    "siamunet_conc": ("models.SiamUnet_conc", "SiamUnet_conc", (3, 2), synth.GAINS["SiamUnet_conc"], 2, 32, 48),
 }
 
 

@@ -121,6 +121,7 @@ SYMBOLS = [
     ("stcd_plan_add_input_pack", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("stcd_plan_finalize", C.c_int, [C.c_void_p]),
     ("stcd_plan_tensor_copy", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int]),
+    ("stcd_plan_read_trace", C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     ("stcd_plan_workspace_bytes", C.c_int64, [C.c_void_p]),
     ("stcd_plan_launches", C.c_int64, [C.c_void_p, C.c_int]),
     ("stcd_forward", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),

@@ -3,25 +3,33 @@
 //   D[128 pixels x N channels] (TMEM, fp32) += A[128 x 16] * W[N x 16]^T   per filter tap and 16 channels
 //
 // Data layout.  Activations live in HBM as bf16 [img][c/8][h][w][8].  One TMA box
-// {8 ch, box_w, box_h, kc/8, 1 img} therefore lands in shared memory as [kc/8][box_h][box_w][8 ch]:
-// the un-swizzled K-major "core matrix" layout of tcgen05.mma (8 rows x 16 bytes contiguous), with
+// {(8 ch, box_w) merged, box_h, kc/8, 1 img} therefore lands in shared memory as
+// [kc/8][box_h][box_w][8 ch]: the un-swizzled K-major "core matrix" layout of tcgen05.mma
+// (8 rows x 16 bytes contiguous), with
 //   SBO (next 8 tile rows = next tile line)  = box_w * 16 bytes
 //   LBO (next 8 channels)                    = box_h * box_w * 16 bytes
 // A CTA tile is 16 x 8 output pixels (M = 128; 8 consecutive pixels of a line form a core matrix),
 // so the A operand of filter tap (ty, tx) is the SAME box at byte offset (ty*box_w + tx)*16: a 3x3
 // conv fetches its 18x10 halo once per K-chunk and issues 9 MMAs from it (L2->SM traffic 1.4x
 // instead of 9x).  Out-of-bounds box pixels are zero-filled by TMA (= the conv's zero padding).
-// Strided convs use element strides in the tensor map and one box per tap.
+// Strided convs use element strides in a 5-D tensor map and one box per tap.
 //
 // Weights are host-packed per (N tile, phase) in consumption order as [block][kc/8][n_tile][8]
 // (block = one tap of one chunk; SBO = 128 B, LBO = n_tile*16 B) and arrive by 1-D bulk copies:
 // either ALL blocks once per CTA (weight-stationary: the CTA then streams pixel tiles past them)
 // or through a ring when they do not fit.
 //
-// Warp roles (7 warps): 0 = A producer (TMA), 1 = W producer (bulk copy), 2 = MMA issuer
-// (one lane; also owns TMEM alloc/dealloc), 3..6 = epilogue (TMEM -> registers -> folded BN /
-// ReLU / residual / |f1-f2| / 2x2 max-pool -> global).  Accumulators are double-buffered in TMEM
-// so the epilogue of tile i overlaps the MMAs of tile i+1; CTAs are persistent over their tiles.
+// Warp roles (7 warps): 0 = A producer (TMA), 1 = W producer (bulk copy), 2 = MMA issuer (also
+// owns TMEM alloc/dealloc), 3..6 = epilogue (TMEM -> registers -> folded BN / ReLU / residual /
+// |f1-f2| / 2x2 max-pool -> global).  Accumulators are double-buffered in TMEM so the epilogue
+// of tile i overlaps the MMAs of tile i+1; CTAs are persistent over their tiles.
+//
+// Measured on B200 (tools/ubench, profiles/): a tcgen05.mma M=128 K=16 in SS mode costs ~45
+// cycles for N <= 64 (the 4 KB A read from shared memory), 64 for N=128 — and a single warp
+// retires one dependent SASS instruction every ~10 cycles, so the producer / issuer loops are
+// table-driven (everything tile-invariant is precomputed into shared memory at CTA start), run
+// by the whole warp in uniform control flow (descriptors stay in uniform registers) and only
+// the tcgen05 / TMA instructions themselves are issued by one elected lane.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -35,9 +43,23 @@ constexpr int kMaxSrc = 6;
 constexpr int kMaxPhase = 4;
 constexpr int kMaxAStages = 8;
 constexpr int kMaxWStages = 16;
-constexpr int kMaxChunks = 128;  // per phase
-constexpr int kMaxTaps = 512;    // per phase
+constexpr int kMaxChunks = 64;   // A-stage loads per phase
+constexpr int kMaxTaps = 320;    // weight blocks per phase
 constexpr int kConvThreads = 224;
+
+// epilogue features; a kernel instance either fixes them at compile time or (E_GENERIC) reads
+// them from ConvParams at run time
+enum : uint32_t {
+  E_RAW = 1u,     // out_raw <- acc*scale + shift
+  E_AFF2 = 2u,    // v = v*scale2 + shift2
+  E_RES = 4u,     // v += res
+  E_RELU = 8u,    // v = max(v, 0)
+  E_OUT0 = 16u,   // out0 <- v
+  E_POOL = 32u,   // out_pool <- maxpool2x2(v)
+  E_DIFF = 64u,   // out_diff <- |v(T1) - v(T2)|
+  E_F32 = 128u,   // out_f32 (NCHW fp32, external) <- v
+  E_GENERIC = 1u << 31
+};
 
 struct Chunk {
   int16_t src, c0;
@@ -60,6 +82,7 @@ struct ConvParams {
   int32_t hg, wg, tiles_x, tiles_y, n_img, pair_off, n_tiles;  // n_tiles = tiles_x*tiles_y*n_img
   int32_t n_ntiles;                                            // N tiles (grid.y = n_phase * n_ntiles)
   int32_t src_sy[kMaxSrc], src_sx[kMaxSrc], src_pw[kMaxSrc], src_ph[kMaxSrc];
+  int32_t src_merged[kMaxSrc];  // 1: 4-D map with (8 ch, x) merged into one dimension (stride-1 sources)
   int32_t osy, osx, ho, wo;
   int32_t n_phase;
   PhaseInfo phase[kMaxPhase];
@@ -87,6 +110,8 @@ struct ConvParams {
   int32_t out_diff_c8;
   float* out_f32;
   int32_t n_valid;
+  int32_t dbg;       // diagnostics (STCD_DBG): bit0 skip MMAs
+  long long* trace;  // diagnostics (STCD_TRACE=1): 16 clock stamps per CTA, else nullptr
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -105,21 +130,36 @@ __device__ __forceinline__ void unpack8_bf16(uint4 q, float* v) {
     v[2 * j + 1] = __high2float(h);
   }
 }
-// element offset of (img, channel-chunk c8, y, x) in a [img][C8][H][W][8] tensor
-__device__ __forceinline__ size_t nc8_off(int n, int c8, int C8, int H, int W, int y, int x) {
-  return (((static_cast<size_t>(n) * C8 + c8) * H + y) * W + x) * 8;
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t pool1_bf16x2(uint32_t a) {
+  a = max_bf16x2(a, __shfl_xor_sync(0xffffffffu, a, 1));
+  return max_bf16x2(a, __shfl_xor_sync(0xffffffffu, a, 8));
+}
+__device__ __forceinline__ uint4 pool4_bf16x2(uint4 q) {
+  return make_uint4(pool1_bf16x2(q.x), pool1_bf16x2(q.y), pool1_bf16x2(q.z), pool1_bf16x2(q.w));
 }
 
-// Un-swizzled K-major operand descriptor: start, LBO (K direction), SBO (M/N direction), bytes.
-__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
-  return d;                              // layout type 0 = no swizzle
-}
+// per-chunk tables, built once per CTA
+struct ChunkLoad {   // A producer
+  int32_t xm, ym;    // tile origin multipliers: coordinate = x0 * xm + xa, y0 * ym + ya
+  int32_t xa, ya;
+  int32_t c8, n_off;
+  uint32_t tx_bytes; // bytes of all MT boxes
+  int32_t src_merged;  // src | merged << 8
+};
+struct ChunkMma {    // MMA issuer
+  uint32_t a_hi;       // SBO | version
+  uint32_t a_lo_lbo;   // LBO << 16
+  uint32_t a_kstep16;  // 2 * LBO >> 4: A advance per K=16 step
+  uint32_t n_taps;
+};
 
+#define STCD_HAS(flag, runtime_expr) ((EPI & E_GENERIC) ? (runtime_expr) : ((EPI & (flag)) != 0))
+
+template <int MT, uint32_t EPI>
 __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_constant__ TmapPack tm,
                                                                   const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -127,11 +167,21 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
   __shared__ __align__(8) uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ Chunk s_chunks[kMaxChunks];
-  __shared__ Tap s_taps[kMaxTaps];
+  __shared__ __align__(16) ChunkLoad s_cload[kMaxChunks];
+  __shared__ __align__(16) ChunkMma s_cmma[kMaxChunks];
+  __shared__ __align__(8) uint2 s_tap[kMaxTaps];     // {A offset (16 B units), B address>>4 | W barrier slot << 16}
+  __shared__ __align__(16) float s_aff[4][256];      // scale, shift, scale2, shift2 of this CTA's N tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  long long* tr = p.trace ? p.trace + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+  const long long clk0 = clock64();
+#define STCD_STAMP(i) do { if (tr) tr[i] = clock64() - clk0; } while (0)
+  if (tr && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    tr[0] = static_cast<long long>(gt);
+  }
 
   const int ph = blockIdx.y / p.n_ntiles;
   const int nt = blockIdx.y - ph * p.n_ntiles;
@@ -144,11 +194,47 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
   const uint32_t w_region = (p.w_resident ? static_cast<uint32_t>(phase.n_blocks) : static_cast<uint32_t>(p.w_stages)) * p.wblk_bytes;
   uint8_t* smem_a = smem + ((w_region + 127u) & ~127u);
   const uint8_t* wsrc = p.wpack + (static_cast<size_t>(nt) * p.blocks_per_ntile + phase.w_block) * p.wblk_bytes;
+  const int w_per = (phase.n_blocks + kMaxWStages - 1) / kMaxWStages;  // resident mode: blocks per barrier slot
 
-  for (int i = threadIdx.x; i < phase.chunk_count; i += blockDim.x) s_chunks[i] = p.chunks[phase.chunk_begin + i];
+  // ---- tile-invariant tables
   {
     const int tap0 = p.chunks[phase.chunk_begin].tap_begin;
-    for (int i = threadIdx.x; i < phase.n_blocks; i += blockDim.x) s_taps[i] = p.taps[tap0 + i];
+    const uint32_t w_base16 = (smem_u32(smem_w) & 0x3FFFF) >> 4;
+    for (int c = threadIdx.x; c < phase.chunk_count; c += blockDim.x) {
+      const Chunk ch = p.chunks[phase.chunk_begin + c];
+      const int pw = p.src_pw[ch.src], phh = p.src_ph[ch.src];
+      const int merged = p.src_merged[ch.src];
+      ChunkLoad L;
+      L.xm = merged ? 8 : p.src_sx[ch.src];
+      L.ym = merged ? 1 : p.src_sy[ch.src];
+      L.xa = merged ? ch.bx * 8 : ch.bx;
+      L.ya = ch.by;
+      L.c8 = ch.c0 >> 3;
+      L.n_off = ch.n_off;
+      L.tx_bytes = static_cast<uint32_t>(MT) * (p.kc / 8) * phh * pw * 16u;
+      L.src_merged = ch.src | (merged << 8);
+      s_cload[c] = L;
+      ChunkMma M;
+      M.a_hi = (static_cast<uint32_t>(pw) & 0x3FFF) | (1u << 14);            // SBO = pw * 16 B; descriptor version 1
+      M.a_lo_lbo = (static_cast<uint32_t>(pw * phh) & 0x3FFF) << 16;          // LBO = pw * ph * 16 B
+      M.a_kstep16 = 2u * static_cast<uint32_t>(pw * phh);
+      M.n_taps = ch.n_taps;
+      s_cmma[c] = M;
+      for (int k = 0; k < ch.n_taps; ++k) {
+        const Tap tp = p.taps[ch.tap_begin + k];
+        const int blk = ch.tap_begin - tap0 + k;
+        uint2 e;
+        e.x = static_cast<uint32_t>(tp.ty * pw + tp.tx);
+        e.y = p.w_resident ? ((w_base16 + static_cast<uint32_t>(blk) * (p.wblk_bytes >> 4)) | (static_cast<uint32_t>(blk / w_per) << 16)) : 0u;
+        s_tap[blk] = e;
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) {
+    s_aff[0][i] = p.scale[n0 + i];
+    s_aff[1][i] = p.shift[n0 + i];
+    s_aff[2][i] = p.scale2 ? p.scale2[n0 + i] : 1.f;
+    s_aff[3][i] = p.shift2 ? p.shift2[n0 + i] : 0.f;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.a_stages; ++s) {
@@ -173,58 +259,73 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const int tap_base = s_chunks[0].tap_begin;  // taps of this phase are contiguous from here
+  if (threadIdx.x == 0) STCD_STAMP(1);
 
   if (warp == 0) {
     // ============================== A producer (TMA) ==============================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        int tile = blockIdx.x + t * gridDim.x;
-        const int tile_x = tile % p.tiles_x;
-        tile /= p.tiles_x;
-        const int tile_y = tile % p.tiles_y;
-        const int img = tile / p.tiles_y;
-        const int x0 = tile_x * kTileW, y0 = tile_y * kTileH;
-        for (int c = 0; c < phase.chunk_count; ++c, ++it) {
-          const Chunk ch = s_chunks[c];
-          const int s = it % p.a_stages;
-          const uint32_t par = (it / p.a_stages) & 1;
-          mbar_wait(&a_empty[s], par ^ 1);
-          const uint32_t box_bytes = static_cast<uint32_t>(p.kc / 8) * p.src_ph[ch.src] * p.src_pw[ch.src] * 16u;
-          mbar_expect_tx(&a_full[s], p.mt * box_bytes);
+    const bool leader = elect_one();
+    int s = 0;
+    uint32_t par = 1;  // parity to wait for on a_empty[s]: first pass through the ring never blocks
+    for (int t = 0; t < my_tiles; ++t) {
+      int tile = blockIdx.x + t * gridDim.x;
+      const int tile_x = tile % p.tiles_x;
+      tile /= p.tiles_x;
+      const int tile_y = tile % p.tiles_y;
+      const int img = tile / p.tiles_y;
+      const int x0 = tile_x * kTileW, y0 = tile_y * kTileH;
+      for (int c = 0; c < phase.chunk_count; ++c) {
+        const ChunkLoad L = s_cload[c];
+        mbar_wait_relaxed(&a_empty[s], par);
+        if (leader) {
+          mbar_expect_tx(&a_full[s], L.tx_bytes);
+          if (t == 0 && c == 0) STCD_STAMP(8);
           uint8_t* dst = smem_a + s * p.a_stage_bytes;
-          for (int m = 0; m < p.mt; ++m)
-            tma_load_5d(dst + m * p.a_sub_bytes, &tm.src[ch.src], &a_full[s], 0, x0 * p.src_sx[ch.src] + ch.bx,
-                        y0 * p.src_sy[ch.src] + ch.by, ch.c0 >> 3, img + ch.n_off + m * p.pair_off);
+          const CUtensorMap* map = &tm.src[L.src_merged & 0xff];
+          const int cx = x0 * L.xm + L.xa, cy = y0 * L.ym + L.ya, cn = img + L.n_off;
+          if (L.src_merged >> 8) {
+            tma_load_4d(dst, map, &a_full[s], cx, cy, L.c8, cn);
+            if (MT == 2) tma_load_4d(dst + p.a_sub_bytes, map, &a_full[s], cx, cy, L.c8, cn + p.pair_off);
+          } else {
+            tma_load_5d(dst, map, &a_full[s], 0, cx, cy, L.c8, cn);
+            if (MT == 2) tma_load_5d(dst + p.a_sub_bytes, map, &a_full[s], 0, cx, cy, L.c8, cn + p.pair_off);
+          }
+        }
+        if (++s == p.a_stages) {
+          s = 0;
+          par ^= 1;
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ============================== W producer (bulk copies) ==============================
-    if (lane == 0) {
-      if (p.w_resident) {
-        // everything once: barrier slot s covers blocks [s*per, (s+1)*per) so MMAs can start early
-        const int per = (phase.n_blocks + kMaxWStages - 1) / kMaxWStages;
+    const bool leader = elect_one();
+    if (p.w_resident) {
+      // everything once: barrier slot s covers blocks [s*per, (s+1)*per) so MMAs can start early
+      if (leader) {
         for (int s = 0; s < kMaxWStages; ++s) {
-          const int b0 = s * per, b1 = min(phase.n_blocks, b0 + per);
+          const int b0 = s * w_per, b1 = min(phase.n_blocks, b0 + w_per);
           if (b0 >= b1) break;
-          mbar_expect_tx(&w_full[s], static_cast<uint32_t>(b1 - b0) * p.wblk_bytes);
-          for (int b = b0; b < b1; ++b)
-            bulk_load(smem_w + static_cast<size_t>(b) * p.wblk_bytes, wsrc + static_cast<size_t>(b) * p.wblk_bytes,
-                      p.wblk_bytes, &w_full[s]);
+          const uint32_t bytes = static_cast<uint32_t>(b1 - b0) * p.wblk_bytes;
+          mbar_expect_tx(&w_full[s], bytes);
+          bulk_load(smem_w + static_cast<size_t>(b0) * p.wblk_bytes, wsrc + static_cast<size_t>(b0) * p.wblk_bytes, bytes,
+                    &w_full[s]);
         }
-      } else {
-        uint32_t it = 0;
-        for (int t = 0; t < my_tiles; ++t) {
-          for (int b = 0; b < phase.n_blocks; ++b, ++it) {
-            const int s = it % p.w_stages;
-            const uint32_t par = (it / p.w_stages) & 1;
-            mbar_wait(&w_empty[s], par ^ 1);
+      }
+    } else {
+      int s = 0;
+      uint32_t par = 1;
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int b = 0; b < phase.n_blocks; ++b) {
+          mbar_wait_relaxed(&w_empty[s], par);
+          if (leader) {
             mbar_expect_tx(&w_full[s], p.wblk_bytes);
             bulk_load(smem_w + static_cast<size_t>(s) * p.wblk_bytes, wsrc + static_cast<size_t>(b) * p.wblk_bytes,
                       p.wblk_bytes, &w_full[s]);
+          }
+          if (++s == p.w_stages) {
+            s = 0;
+            par ^= 1;
           }
         }
       }
@@ -232,71 +333,130 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     __syncwarp();
   } else if (warp == 2) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(p.n_tile);
-      const int ksteps = p.kc / 16;
-      const uint32_t w_lbo = static_cast<uint32_t>(p.n_tile) * 16u, w_sbo = 128u;
-      const int per = (phase.n_blocks + kMaxWStages - 1) / kMaxWStages;
-      uint32_t a_it = 0, w_it = 0;
-      int w_ready = 0;  // resident mode: barrier slots already waited for
-      for (int t = 0; t < my_tiles; ++t) {
-        const int acc = t & 1;
-        mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
+    const bool leader = elect_one() && !(p.dbg & 1);
+    const uint32_t idesc = make_idesc_bf16(p.n_tile);
+    const int ksteps = p.kc >> 4;                   // 1, 2 or 4
+    const int ks_shift = (ksteps == 4) ? 2 : (ksteps >> 1);
+    const uint32_t b_hi = (128u >> 4) | (1u << 14);                                   // SBO = 128 B, version 1
+    const uint32_t b_lo_lbo = (static_cast<uint32_t>(p.n_tile) & 0x3FFF) << 16;      // LBO = n_tile * 16 B
+    const uint32_t b_kstep16 = 2u * static_cast<uint32_t>(p.n_tile);
+    const uint32_t wblk16 = p.wblk_bytes >> 4;
+    const uint32_t w_base16 = (smem_u32(smem_w) & 0x3FFFF) >> 4;
+    const uint32_t a_ring16 = (smem_u32(smem_a) & 0x3FFFF) >> 4;
+    const uint32_t a_stage16 = p.a_stage_bytes >> 4;
+    const uint32_t a_sub16 = p.a_sub_bytes >> 4;
+    const bool resident = p.w_resident != 0;
+    int s = 0, ws = 0;
+    uint32_t a_par = 0, w_par = 0;
+    uint32_t a_base16 = a_ring16;
+    int w_ready = 0;  // resident mode: barrier slots already waited for
+    for (int t = 0; t < my_tiles; ++t) {
+      const int acc = t & 1;
+      mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + acc * p.acc_cols;
+      const uint32_t d1 = d0 + p.n_tile;
+      uint32_t accum = 0;
+      int blk = 0;
+      for (int c = 0; c < phase.chunk_count; ++c) {
+        const ChunkMma M = s_cmma[c];
+        mbar_wait(&a_full[s], a_par);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * p.acc_cols;
-        uint32_t first = 1;
-        int blk = 0;
-        for (int c = 0; c < phase.chunk_count; ++c, ++a_it) {
-          const Chunk ch = s_chunks[c];
-          const int s = a_it % p.a_stages;
-          mbar_wait(&a_full[s], (a_it / p.a_stages) & 1);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem_a + s * p.a_stage_bytes);
-          const uint32_t pw = p.src_pw[ch.src];
-          const uint32_t a_sbo = pw * 16u, a_lbo = pw * p.src_ph[ch.src] * 16u;
-          for (int k = 0; k < ch.n_taps; ++k, ++blk) {
-            const Tap tp = s_taps[ch.tap_begin - tap_base + k];
-            uint32_t b_base;
-            int ws = 0;
-            if (p.w_resident) {
-              const int need = blk / per;
-              while (w_ready <= need) {
+        if (t == 0 && c == 0 && leader) STCD_STAMP(2);
+        const uint32_t a_lo_base = M.a_lo_lbo + a_base16;
+        if (resident) {
+          if (t == 0) {  // first tile: weights may still be landing (slots arrive in order)
+            const int slot = static_cast<int>(s_tap[blk + M.n_taps - 1].y >> 16);
+            if (w_ready <= slot) {
+              while (w_ready <= slot) {
                 mbar_wait(&w_full[w_ready], 0);
                 ++w_ready;
               }
               tc_fence_after();
-              b_base = smem_u32(smem_w + static_cast<size_t>(blk) * p.wblk_bytes);
-            } else {
-              ws = w_it % p.w_stages;
-              mbar_wait(&w_full[ws], (w_it / p.w_stages) & 1);
-              tc_fence_after();
-              b_base = smem_u32(smem_w + static_cast<size_t>(ws) * p.wblk_bytes);
-              ++w_it;
             }
-            const uint32_t a_tap = a_base + (static_cast<uint32_t>(tp.ty) * pw + tp.tx) * 16u;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t bdesc = make_desc_nosw(b_base + ks * 2 * w_lbo, w_lbo, w_sbo);
-              for (int m = 0; m < p.mt; ++m) {
-                const uint32_t a_addr = a_tap + m * p.a_sub_bytes + ks * 2 * a_lbo;
-                const uint64_t adesc = make_desc_nosw(a_addr, a_lbo, a_sbo);
-                umma_bf16(d_tmem + m * p.n_tile, adesc, bdesc, idesc, first ? 0u : 1u);
-              }
-              first = 0;
-            }
-            if (!p.w_resident) umma_commit(&w_empty[ws]);
           }
-          umma_commit(&a_empty[s]);
+          // Lane i prepares the descriptors of MMA i of this chunk (tap = i / ksteps, K step =
+          // i % ksteps); the issue loop then only shuffles them out, so its instructions are
+          // independent of each other and pipeline instead of forming one latency chain.
+          const int n_mma = static_cast<int>(M.n_taps) << ks_shift;
+          for (int base = 0; base < n_mma; base += 32) {
+            const int i = base + lane;
+            uint32_t my_a = 0, my_b = 0;
+            if (i < n_mma) {
+              const int k = i >> ks_shift, ks = i & (ksteps - 1);
+              const uint2 te = s_tap[blk + k];
+              my_a = a_lo_base + te.x + ks * M.a_kstep16;
+              my_b = b_lo_lbo + (te.y & 0xFFFF) + ks * b_kstep16;
+            }
+            const int cnt = min(32, n_mma - base);
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) {
+              const uint32_t a_lo = __shfl_sync(0xffffffffu, my_a, j);
+              const uint32_t b_lo = __shfl_sync(0xffffffffu, my_b, j);
+              if (leader) {
+                umma_bf16_lohi(d0, a_lo, M.a_hi, b_lo, b_hi, idesc, accum);
+                if (MT == 2) umma_bf16_lohi(d1, a_lo + a_sub16, M.a_hi, b_lo, b_hi, idesc, accum);
+              }
+              accum = 1;
+            }
+          }
+          blk += M.n_taps;
+        } else {
+          for (uint32_t k = 0; k < M.n_taps; ++k, ++blk) {
+            const uint2 te = s_tap[blk];
+            mbar_wait(&w_full[ws], w_par);
+            tc_fence_after();
+            uint32_t b_lo = b_lo_lbo + w_base16 + static_cast<uint32_t>(ws) * wblk16;
+            uint32_t a_lo = a_lo_base + te.x;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              if (leader) {
+                umma_bf16_lohi(d0, a_lo, M.a_hi, b_lo, b_hi, idesc, accum);
+                if (MT == 2) umma_bf16_lohi(d1, a_lo + a_sub16, M.a_hi, b_lo, b_hi, idesc, accum);
+              }
+              accum = 1;
+              a_lo += M.a_kstep16;
+              b_lo += b_kstep16;
+            }
+            if (leader) umma_commit(&w_empty[ws]);
+            if (++ws == p.w_stages) {
+              ws = 0;
+              w_par ^= 1;
+            }
+          }
         }
+        if (leader) umma_commit(&a_empty[s]);
+        a_base16 += a_stage16;
+        if (++s == p.a_stages) {
+          s = 0;
+          a_par ^= 1;
+          a_base16 = a_ring16;
+        }
+      }
+      if (leader) {
         umma_commit(&acc_full[acc]);
+        if (t == 0) STCD_STAMP(4);
+        if (t == my_tiles - 1) STCD_STAMP(9);
       }
     }
     __syncwarp();
   } else {
     // ============================== epilogue (warps 3..6) ==============================
+    const bool has_raw = STCD_HAS(E_RAW, p.out_raw != nullptr);
+    const bool has_aff2 = STCD_HAS(E_AFF2, p.scale2 != nullptr);
+    const bool has_res = STCD_HAS(E_RES, p.res != nullptr);
+    const bool has_relu = STCD_HAS(E_RELU, p.relu != 0);
+    const bool has_out0 = STCD_HAS(E_OUT0, p.out0 != nullptr);
+    const bool has_pool = STCD_HAS(E_POOL, p.out_pool != nullptr);
+    const bool has_diff = (MT == 2) && STCD_HAS(E_DIFF, p.out_diff != nullptr);
+    const bool has_f32 = STCD_HAS(E_F32, p.out_f32 != nullptr);
+
     const int wq = warp & 3;  // TMEM lane quarter this warp may access
     const int ty = 4 * wq + (lane >> 3);
     const int tx = lane & 7;
-    const size_t img_pix = static_cast<size_t>(p.ho) * p.wo;
+    const uint32_t hw = static_cast<uint32_t>(p.ho) * p.wo;  // pixels per image plane
+    const uint32_t hw_pool = hw >> 2;
+    const int cg8 = n0 >> 3;  // first 8-channel group of this N tile
+    const size_t pair_imgs = static_cast<size_t>(p.pair_off);
     for (int t = 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
       const int tile_x = tile % p.tiles_x;
@@ -306,88 +466,154 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       const int gy = tile_y * kTileH + ty, gx = tile_x * kTileW + tx;
       const bool valid = (gy < p.hg) && (gx < p.wg);
       const int oy = gy * p.osy + phase.oy, ox = gx * p.osx + phase.ox;
+      const uint32_t pix = static_cast<uint32_t>(oy) * p.wo + ox;
+      const uint32_t pix_pool = static_cast<uint32_t>(oy >> 1) * (p.wo >> 1) + (ox >> 1);
+      // element pointers of (img, first channel group, pixel); image m=1 is pair_imgs images further
+      __nv_bfloat16* q_out0 = has_out0 ? p.out0 + ((static_cast<size_t>(img) * p.out0_c8 + (p.out0_coff >> 3) + cg8) * hw + pix) * 8 : nullptr;
+      __nv_bfloat16* q_raw = has_raw ? p.out_raw + ((static_cast<size_t>(img) * p.out_raw_c8 + cg8) * hw + pix) * 8 : nullptr;
+      const __nv_bfloat16* q_res = has_res ? p.res + ((static_cast<size_t>(img) * p.res_c8 + cg8) * hw + pix) * 8 : nullptr;
+      __nv_bfloat16* q_pool = has_pool ? p.out_pool + ((static_cast<size_t>(img) * p.out_pool_c8 + cg8) * hw_pool + pix_pool) * 8 : nullptr;
+      __nv_bfloat16* q_diff = has_diff ? p.out_diff + ((static_cast<size_t>(img) * p.out_diff_c8 + cg8) * hw + pix) * 8 : nullptr;
       const int acc = t & 1;
-      mbar_wait(&acc_full[acc], (t >> 1) & 1);
+      mbar_wait_relaxed(&acc_full[acc], (t >> 1) & 1);
       tc_fence_after();
+      if (t == 0 && threadIdx.x == 96) STCD_STAMP(5);
       const uint32_t tlane = tmem_base + acc * p.acc_cols + (static_cast<uint32_t>(wq * 32) << 16);
 
       for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
         const int ch = n0 + c0;
         if (ch >= p.cout) break;
-        const int nv = min(16, p.cout - ch);  // valid channels in this 16-group (bf16 outputs: 8 or 16)
-        float v[2][16];
+        const bool two = (p.cout - ch) > 8;  // both 8-channel groups of this 16-column step are real
+        uint32_t raw[MT][16];
+        tmem_ld16(tlane + c0, raw[0]);
+        if (MT == 2) tmem_ld16(tlane + p.n_tile + c0, raw[MT - 1]);
+        tmem_wait_ld();
+        float v[MT][16];
+        const size_t g_off = static_cast<size_t>(c0 >> 3) * hw * 8;            // channel-group offset (elements)
+        const size_t g_off_pool = static_cast<size_t>(c0 >> 3) * hw_pool * 8;
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          if (m >= p.mt) break;
-          uint32_t raw[16];
-          tmem_ld16(tlane + m * p.n_tile + c0, raw);
-          tmem_wait_ld();
-          const int n = img + m * p.pair_off;
+        for (int m = 0; m < MT; ++m) {
+          const size_t m_img = m ? pair_imgs : 0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[m][j] = fmaf(__uint_as_float(raw[j]), __ldg(p.scale + ch + j), __ldg(p.shift + ch + j));
-          if (p.out_raw != nullptr && valid) {
-            __nv_bfloat16* o = p.out_raw + nc8_off(n, ch >> 3, p.out_raw_c8, p.ho, p.wo, oy, ox);
+          for (int j = 0; j < 16; j += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(&s_aff[0][c0 + j]);
+            const float4 sh = *reinterpret_cast<const float4*>(&s_aff[1][c0 + j]);
+            v[m][j + 0] = fmaf(__uint_as_float(raw[m][j + 0]), sc.x, sh.x);
+            v[m][j + 1] = fmaf(__uint_as_float(raw[m][j + 1]), sc.y, sh.y);
+            v[m][j + 2] = fmaf(__uint_as_float(raw[m][j + 2]), sc.z, sh.z);
+            v[m][j + 3] = fmaf(__uint_as_float(raw[m][j + 3]), sc.w, sh.w);
+          }
+          if (has_raw && valid) {
+            __nv_bfloat16* o = q_raw + m_img * p.out_raw_c8 * hw * 8 + g_off;
             *reinterpret_cast<uint4*>(o) = pack8_bf16(v[m]);
-            if (nv > 8) *reinterpret_cast<uint4*>(o + img_pix * 8) = pack8_bf16(v[m] + 8);
+            if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(v[m] + 8);
           }
-          if (p.scale2 != nullptr) {
+          if (has_aff2) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[m][j] = fmaf(v[m][j], __ldg(p.scale2 + ch + j), __ldg(p.shift2 + ch + j));
+            for (int j = 0; j < 16; ++j) v[m][j] = fmaf(v[m][j], s_aff[2][c0 + j], s_aff[3][c0 + j]);
           }
-          if (p.res != nullptr && valid) {
-            const __nv_bfloat16* r = p.res + nc8_off(n, ch >> 3, p.res_c8, p.ho, p.wo, oy, ox);
+          if (has_res && valid) {
+            const __nv_bfloat16* r = q_res + m_img * p.res_c8 * hw * 8 + g_off;
             float rv[16];
             unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(r)), rv);
-            if (nv > 8) unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(r + img_pix * 8)), rv + 8);
+            if (two) {
+              unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(r + static_cast<size_t>(hw) * 8)), rv + 8);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[m][j] += (j < nv) ? rv[j] : 0.f;
+              for (int j = 8; j < 16; ++j) rv[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[m][j] += rv[j];
           }
-          if (p.relu) {
+          if (has_relu) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[m][j] = fmaxf(v[m][j], 0.f);
           }
-          if (p.out0 != nullptr && valid) {
-            __nv_bfloat16* o = p.out0 + nc8_off(n, (p.out0_coff + ch) >> 3, p.out0_c8, p.ho, p.wo, oy, ox);
-            *reinterpret_cast<uint4*>(o) = pack8_bf16(v[m]);
-            if (nv > 8) *reinterpret_cast<uint4*>(o + img_pix * 8) = pack8_bf16(v[m] + 8);
-          }
-          if (p.out_f32 != nullptr && valid && n < p.n_valid) {
-            for (int j = 0; j < nv; ++j)
-              p.out_f32[(static_cast<size_t>(n) * p.cout + ch + j) * img_pix + static_cast<size_t>(oy) * p.wo + ox] = v[m][j];
-          }
-          if (p.out_pool != nullptr) {
-            float q[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float a = fmaxf(v[m][j], __shfl_xor_sync(0xffffffffu, v[m][j], 1));
-              q[j] = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 8));
+          if (has_f32) {
+            const int n = img + m * p.pair_off;
+            if (valid && n < p.n_valid) {
+              const int nv = min(16, p.cout - ch);
+              float* o = p.out_f32 + (static_cast<size_t>(n) * p.cout + ch) * hw + pix;
+              for (int j = 0; j < nv; ++j) o[static_cast<size_t>(j) * hw] = v[m][j];
             }
-            if (valid && ((lane & 9) == 0)) {
-              __nv_bfloat16* o = p.out_pool + nc8_off(n, ch >> 3, p.out_pool_c8, p.ho >> 1, p.wo >> 1, oy >> 1, ox >> 1);
-              *reinterpret_cast<uint4*>(o) = pack8_bf16(q);
-              if (nv > 8) *reinterpret_cast<uint4*>(o + (img_pix >> 2) * 8) = pack8_bf16(q + 8);
+          }
+          if (has_out0 || has_pool) {
+            const uint4 lo = pack8_bf16(v[m]), hi = pack8_bf16(v[m] + 8);
+            if (has_out0 && valid) {
+              __nv_bfloat16* o = q_out0 + m_img * p.out0_c8 * hw * 8 + g_off;
+              *reinterpret_cast<uint4*>(o) = lo;
+              if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = hi;
+            }
+            if (has_pool) {
+              // max over the 2x2 window on the packed bf16 pairs (rounding is monotonic, so
+              // max(bf16(a), bf16(b)) == bf16(max(a, b))): lanes +1 (x) and +8 (y)
+              const uint4 plo = pool4_bf16x2(lo), phi = pool4_bf16x2(hi);
+              if (valid && ((lane & 9) == 0)) {
+                __nv_bfloat16* o = q_pool + m_img * p.out_pool_c8 * hw_pool * 8 + g_off_pool;
+                *reinterpret_cast<uint4*>(o) = plo;
+                if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw_pool) * 8) = phi;
+              }
             }
           }
         }
-        if (p.mt == 2 && p.out_diff != nullptr && valid) {
+        if (has_diff && valid) {
           float d[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) d[j] = fabsf(v[0][j] - v[1][j]);
-          __nv_bfloat16* o = p.out_diff + nc8_off(img, ch >> 3, p.out_diff_c8, p.ho, p.wo, oy, ox);
+          for (int j = 0; j < 16; ++j) d[j] = fabsf(v[0][j] - v[MT - 1][j]);
+          __nv_bfloat16* o = q_diff + g_off;
           *reinterpret_cast<uint4*>(o) = pack8_bf16(d);
-          if (nv > 8) *reinterpret_cast<uint4*>(o + img_pix * 8) = pack8_bf16(d + 8);
+          if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(d + 8);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (threadIdx.x == 96) {
+        if (t == 0) STCD_STAMP(6);
+        if (t == my_tiles - 1) STCD_STAMP(10);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    STCD_STAMP(7);
+    if (tr) tr[11] = my_tiles;
+  }
   if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+#undef STCD_HAS
+
+using ConvKernelFn = void (*)(const TmapPack, const ConvParams);
+
+struct ConvKernelEntry {
+  int mt;
+  uint32_t epi;
+  ConvKernelFn fn;
+};
+
+// Specialised instances for the epilogue combinations the lowered nets use; anything else runs the
+// generic instance (same code, epilogue features read from ConvParams at run time).
+#define STCD_CONV_INSTANCES(X)                      \
+  X(2, E_RELU | E_OUT0)                             \
+  X(2, E_RELU | E_POOL | E_DIFF)                    \
+  X(2, E_RELU | E_OUT0 | E_POOL)                    \
+  X(1, E_OUT0)                                      \
+  X(1, E_RELU | E_OUT0)                             \
+  X(1, E_F32)
+
+inline const ConvKernelEntry* conv_kernel_table(int* n) {
+  static const ConvKernelEntry table[] = {
+#define STCD_X(MT_, EPI_) {MT_, (EPI_), conv_ws_kernel<MT_, (EPI_)>},
+      STCD_CONV_INSTANCES(STCD_X)
+#undef STCD_X
+      {1, E_GENERIC, conv_ws_kernel<1, E_GENERIC>},
+      {2, E_GENERIC, conv_ws_kernel<2, E_GENERIC>},
+  };
+  *n = static_cast<int>(sizeof(table) / sizeof(table[0]));
+  return table;
 }
 
 }  // namespace stcd

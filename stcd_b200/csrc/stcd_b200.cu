@@ -78,6 +78,9 @@ struct ConvOp {
   dim3 grid;
   size_t smem = 0;
   int mt = 1;
+  uint32_t epi = 0;
+  stcd::ConvKernelFn fn = nullptr;
+  long long* trace = nullptr;
 };
 
 struct PackOp {
@@ -133,6 +136,20 @@ int check_sm100(int device) {
 int encode_act_map(CUtensorMap* m, void* base, int n, int h, int w, int c, int kc, int sx, int sy, int ex, int ey) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(STCD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  if (sx == 1 && sy == 1) {
+    // (8 ch, x) are contiguous in HBM and in the shared-memory operand layout alike: merge them into
+    // one dimension so a box row is (8 + ex) * 16 bytes instead of 16 (TMA cost is per box row).
+    cuuint64_t gdim[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)(c / 8), (cuuint64_t)n};
+    cuuint64_t gstr[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)(c / 8) * h * w * 16};
+    cuuint32_t box[4] = {(cuuint32_t)((stcd::kTileW + ex) * 8), (cuuint32_t)(stcd::kTileH + ey), (cuuint32_t)(kc / 8), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (box[0] > 256) return fail(STCD_ERR_INVALID, "halo %d too wide for one TMA box row", ex);
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return fail(STCD_ERR_CUDA, "cuTensorMapEncodeTiled(act4 n=%d h=%d w=%d c=%d kc=%d e=%d,%d) -> %d", n, h, w, c, kc, ex, ey, (int)r);
+    return STCD_OK;
+  }
   // [img][c/8][h][w][8] bf16: dims fastest-first {8, w, h, c/8, img}
   cuuint64_t gdim[5] = {8, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)(c / 8), (cuuint64_t)n};
   cuuint64_t gstr[4] = {16, (cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)(c / 8) * h * w * 16};
@@ -160,7 +177,7 @@ int launch_conv(const stcd_plan* plan, const ConvOp& op, int n_valid, float* con
     p.out_f32 = outs[op.d.out_ext];
     if (!p.out_f32) return fail(STCD_ERR_INVALID, "external output %d is NULL", op.d.out_ext);
   }
-  stcd::conv_ws_kernel<<<op.grid, stcd::kConvThreads, op.smem, st>>>(op.tm, p);
+  op.fn<<<op.grid, stcd::kConvThreads, op.smem, st>>>(op.tm, p);
   CUDA_TRY(cudaGetLastError());
   (void)plan;
   return STCD_OK;
@@ -227,6 +244,8 @@ int stcd_plan_create(int device, int chunk_pairs, stcd_plan** out) {
 void stcd_plan_destroy(stcd_plan* plan) {
   if (!plan) return;
   cudaSetDevice(plan->device);
+  for (ConvOp& op : plan->convs)
+    if (op.trace) cudaFree(op.trace);
   if (plan->workspace) cudaFree(plan->workspace);
   if (plan->arena) cudaFree(plan->arena);
   for (int b = 0; b < 2; ++b) {
@@ -436,7 +455,11 @@ int stcd_plan_finalize(stcd_plan* plan) {
   static_assert(sizeof(stcd_chunk) == sizeof(stcd::Chunk), "chunk layout");
   static_assert(sizeof(stcd_tap) == sizeof(stcd::Tap), "tap layout");
   const size_t kSmemMax = 227 * 1024 - 12 * 1024;  // dynamic budget: static tables + barriers live beside it
-  CUDA_TRY(cudaFuncSetAttribute(stcd::conv_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  int n_kernels = 0;
+  const stcd::ConvKernelEntry* kernels = stcd::conv_kernel_table(&n_kernels);
+  for (int i = 0; i < n_kernels; ++i)
+    CUDA_TRY(cudaFuncSetAttribute(kernels[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  const int force_generic = env_int("STCD_FORCE_GENERIC", 0);
   int n_sm = 148;
   CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, plan->device));
 
@@ -455,6 +478,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
       if (r) return r;
       p.src_sy[s] = d.src_sy[s];
       p.src_sx[s] = d.src_sx[s];
+      p.src_merged[s] = (d.src_sx[s] == 1 && d.src_sy[s] == 1) ? 1 : 0;
       p.src_pw[s] = stcd::kTileW + d.src_ex[s];
       p.src_ph[s] = stcd::kTileH + d.src_ey[s];
       a_sub = std::max(a_sub, (size_t)(d.kc / 8) * p.src_pw[s] * p.src_ph[s] * 16);
@@ -525,6 +549,13 @@ int stcd_plan_finalize(stcd_plan* plan) {
     if (op.smem > kSmemMax) return fail(STCD_ERR_INVALID, "conv op needs %zu B of shared memory", op.smem);
     const int ctas = std::max(1, (n_sm * occ) / groups);
     op.grid = dim3((unsigned)std::min(p.n_tiles, ctas), (unsigned)groups, 1);
+    p.dbg = env_int("STCD_DBG", 0);
+    if (env_int("STCD_TRACE", 0)) {
+      const size_t nb = (size_t)op.grid.x * op.grid.y * 16 * sizeof(long long);
+      CUDA_TRY(cudaMalloc(&op.trace, nb));
+      CUDA_TRY(cudaMemset(op.trace, 0, nb));
+      p.trace = op.trace;
+    }
     const float* sc = reinterpret_cast<const float*>(plan->arena + op.s_off);
     p.scale = sc;
     p.shift = sc + d.cout_pad;
@@ -533,6 +564,16 @@ int stcd_plan_finalize(stcd_plan* plan) {
       p.shift2 = sc + 3 * d.cout_pad;
     }
     p.relu = d.relu;
+    // epilogue features -> kernel instance (specialised when one exists, else the generic one)
+    op.epi = (d.out_raw >= 0 ? stcd::E_RAW : 0u) | (!op.scale2.empty() ? stcd::E_AFF2 : 0u) | (d.res >= 0 ? stcd::E_RES : 0u) |
+             (d.relu ? stcd::E_RELU : 0u) | (d.out0 >= 0 ? stcd::E_OUT0 : 0u) | (d.out_pool >= 0 ? stcd::E_POOL : 0u) |
+             (d.out_diff >= 0 ? stcd::E_DIFF : 0u) | (d.out_ext >= 0 ? stcd::E_F32 : 0u);
+    op.fn = nullptr;
+    for (int i = 0; i < n_kernels && !force_generic; ++i)
+      if (kernels[i].mt == op.mt && kernels[i].epi == op.epi) op.fn = kernels[i].fn;
+    for (int i = 0; i < n_kernels && !op.fn; ++i)
+      if (kernels[i].mt == op.mt && kernels[i].epi == stcd::E_GENERIC) op.fn = kernels[i].fn;
+    if (!op.fn) return fail(STCD_ERR_INVALID, "no conv kernel instance for mt=%d", op.mt);
     if (d.res >= 0) {
       p.res = (const __nv_bfloat16*)plan->tensors[d.res].ptr;
       p.res_c8 = plan->tensors[d.res].c / 8;
@@ -571,6 +612,20 @@ int stcd_plan_tensor_copy(stcd_plan* plan, int tensor_id, void* host, int64_t by
   else
     CUDA_TRY(cudaMemcpy(host, t.ptr, t.bytes, cudaMemcpyDeviceToHost));
   return STCD_OK;
+}
+
+int64_t stcd_plan_read_trace(stcd_plan* plan, int op_index, int64_t* host, int64_t max_words, int32_t* info) {
+  if (!plan || !plan->finalized || op_index < 0 || op_index >= (int)plan->ops.size() || plan->ops[op_index].kind != 0) return -1;
+  const ConvOp& op = plan->convs[plan->ops[op_index].idx];
+  if (info) {
+    info[0] = op.grid.x; info[1] = op.grid.y; info[2] = (int)op.smem; info[3] = op.p.a_stages; info[4] = op.p.w_stages;
+    info[5] = op.p.w_resident; info[6] = op.p.tmem_cols; info[7] = op.p.n_tiles; info[8] = op.p.a_stage_bytes; info[9] = op.p.wblk_bytes;
+  }
+  if (!op.trace || !host) return 0;
+  const int64_t n = std::min<int64_t>(max_words, (int64_t)op.grid.x * op.grid.y * 16);
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(host, op.trace, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return n;
 }
 
 int64_t stcd_plan_workspace_bytes(const stcd_plan* plan) {

@@ -13,7 +13,7 @@ from stcd_b200 import siamunet, synth
 
 pytestmark = pytest.mark.gpu
 BF16_TOL = 2e-2
-NETS = {"diff": (siamunet.SiamUnet_diff, 0.8), "conc": (siamunet.SiamUnet_conc, 0.75)}
+NETS = {"diff": (siamunet.SiamUnet_diff, synth.GAINS["SiamUnet_diff"]), "conc": (siamunet.SiamUnet_conc, synth.GAINS["SiamUnet_conc"])}
 
 
 def _net(fusion):

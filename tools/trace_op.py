@@ -1,0 +1,34 @@
+"""Per-CTA clock stamps of the conv ops of one SiamUnet_diff chunk (STCD_TRACE=1)."""
+import os, sys
+os.environ["STCD_TRACE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes as C
+import numpy as np
+import torch
+from stcd_b200 import siamunet, synth, _lib
+from stcd_b200.plan import Plan
+
+H = W = 256
+chunk = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+net = synth.randomize_(siamunet.SiamUnet_diff(3, 2).eval(), gain=synth.GAINS["SiamUnet_diff"])
+prog = net.lower(H, W)
+plan = Plan(prog, chunk)
+x1, x2 = synth.image_pairs(chunk, H, W)
+x1, x2 = x1.cuda(), x2.cuda()
+for _ in range(3):
+    plan.forward(x1, x2)
+torch.cuda.synchronize()
+lib = _lib.lib()
+names = ["gt", "setup", "mma:a0", "mma:w0", "mma:t0", "epi:t0beg", "epi:t0end", "exit", "prod:tma0", "mma:last", "epi:last", "tiles", "tap0", "tap1", "c0taps", "c0commit"]
+for i, op in enumerate(prog.ops):
+    info = (C.c_int32 * 10)()
+    buf = np.zeros(1 << 16, dtype=np.int64)
+    n = lib.stcd_plan_read_trace(plan._h, i, buf.ctypes.data, buf.size, info)
+    if n <= 0:
+        continue
+    t = buf[:n].reshape(-1, 16)
+    gt = t[:, 0]
+    span_us = (gt.max() - gt.min()) / 1e3
+    med = np.median(t, axis=0)
+    print(f"{op.name:8s} grid=({info[0]},{info[1]}) smem={info[2]} aS={info[3]} wS={info[4]} res={info[5]} tmem={info[6]} tiles={info[7]} aB={info[8]} wB={info[9]} start-span={span_us:.1f}us")
+    print("     median cycles: " + " ".join(f"{names[k]}={int(med[k])}" for k in (1, 8, 2, 3, 12, 13, 14, 15, 4, 5, 6, 9, 10, 7, 11)))
