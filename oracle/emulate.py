@@ -48,6 +48,8 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
                 src = T[op.srcs[si]]
                 off = (ck.stream + m) * chunk
                 sub = src[off: off + n_img, :, :, ck.c0: ck.c0 + op.kc]
+                if sub.shape[3] < op.kc:      # chunk overhangs the tensor's channels: TMA zero-fill
+                    sub = torch.nn.functional.pad(sub, (0, op.kc - sub.shape[3]))
                 for (ty, tx) in op.taps[ck.tap_begin: ck.tap_begin + ck.n_taps]:
                     a = _gather(sub, ii * op.src_sy[si] + ck.by + ty * op.src_sy[si],
                                 jj * op.src_sx[si] + ck.bx + tx * op.src_sx[si])

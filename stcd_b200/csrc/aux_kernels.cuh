@@ -9,13 +9,13 @@
 
 namespace stcd {
 
-// x1, x2: fp32 NCHW [n_valid, cin, h, w] -> dst bf16 [2*chunk][2][h][w][8]; channels >= cin are
-// zero; T1 images occupy [0, chunk), T2 images [chunk, 2*chunk). One thread per pixel: reads are
-// coalesced per channel plane, each thread writes one 16-byte pixel chunk per channel plane (the
-// second plane only when cin > 8; it stays zero from plan creation otherwise).
+// x1, x2: fp32 NCHW [n_valid, cin, h, w] -> dst bf16 [2*chunk][c8][h][w][8] (c8 = 1 or 2 channel
+// groups); channels >= cin are zero; T1 images occupy [0, chunk), T2 images [chunk, 2*chunk).
+// One thread per pixel: reads are coalesced per channel plane, each thread writes one 16-byte
+// pixel chunk per channel group (a warp writes 512 contiguous bytes).
 __global__ void __launch_bounds__(256) input_pack_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
                                                          __nv_bfloat16* __restrict__ dst, int chunk, int n_valid,
-                                                         int cin, int hw) {
+                                                         int cin, int c8, int hw) {
   const size_t total = static_cast<size_t>(2) * chunk * hw;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -27,7 +27,9 @@ __global__ void __launch_bounds__(256) input_pack_kernel(const float* __restrict
     for (int c = 0; c < 16; ++c) v[c] = 0.f;
     if (b < n_valid) {
       const float* src = (s ? x2 : x1) + static_cast<size_t>(b) * cin * hw + pix;
-      for (int c = 0; c < cin; ++c) v[c] = __ldg(src + static_cast<size_t>(c) * hw);
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < cin) v[c] = __ldg(src + static_cast<size_t>(c) * hw);
     }
     uint32_t w[8];
 #pragma unroll
@@ -35,9 +37,9 @@ __global__ void __launch_bounds__(256) input_pack_kernel(const float* __restrict
       __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
       w[j] = *reinterpret_cast<uint32_t*>(&h);
     }
-    __nv_bfloat16* o = dst + (static_cast<size_t>(n) * 2 * hw + pix) * 8;
+    __nv_bfloat16* o = dst + (static_cast<size_t>(n) * c8 * hw + pix) * 8;
     *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
-    if (cin > 8) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = make_uint4(w[4], w[5], w[6], w[7]);
+    if (c8 > 1) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 

@@ -84,7 +84,7 @@ struct ConvParams {
   int32_t src_sy[kMaxSrc], src_sx[kMaxSrc], src_pw[kMaxSrc], src_ph[kMaxSrc];
   int32_t src_merged[kMaxSrc];  // 1: 4-D map with (8 ch, x) merged into one dimension (stride-1 sources)
   int32_t osy, osx, ho, wo;
-  int32_t n_phase;
+  int32_t n_phase, n_src;
   PhaseInfo phase[kMaxPhase];
   const Chunk* chunks;
   const Tap* taps;
@@ -196,6 +196,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
   const uint8_t* wsrc = p.wpack + (static_cast<size_t>(nt) * p.blocks_per_ntile + phase.w_block) * p.wblk_bytes;
   const int w_per = (phase.n_blocks + kMaxWStages - 1) / kMaxWStages;  // resident mode: blocks per barrier slot
 
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < p.n_src; ++i) tma_prefetch_desc(&tm.src[i]);
+  }
   // ---- tile-invariant tables
   {
     const int tap0 = p.chunks[phase.chunk_begin].tap_begin;
@@ -260,12 +263,17 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   if (threadIdx.x == 0) STCD_STAMP(1);
+  // Programmatic dependent launch: everything above (tables, barriers, TMEM) and the weight loads
+  // below do not depend on the previous layer, so the next kernel may start its own prologue now;
+  // only the activation loads wait for the previous kernel to finish.
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ============================== A producer (TMA) ==============================
     const bool leader = elect_one();
     int s = 0;
     uint32_t par = 1;  // parity to wait for on a_empty[s]: first pass through the ring never blocks
+    pdl_wait();        // activations are written by the previous kernel(s)
     for (int t = 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
       const int tile_x = tile % p.tiles_x;

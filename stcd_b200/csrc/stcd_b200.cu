@@ -108,6 +108,7 @@ struct stcd_plan {
   size_t arena_bytes = 0;
   int n_ext = 0;
   int in_c = 0, in_h = 0, in_w = 0;
+  int pdl = 1;  // programmatic dependent launch between the conv kernels (STCD_PDL=0 disables)
   std::vector<size_t> ext_elems;  // per external output: elements per image
   // host-buffer path
   cudaStream_t s_copy = nullptr, s_comp = nullptr, s_d2h = nullptr;
@@ -177,8 +178,18 @@ int launch_conv(const stcd_plan* plan, const ConvOp& op, int n_valid, float* con
     p.out_f32 = outs[op.d.out_ext];
     if (!p.out_f32) return fail(STCD_ERR_INVALID, "external output %d is NULL", op.d.out_ext);
   }
-  op.fn<<<op.grid, stcd::kConvThreads, op.smem, st>>>(op.tm, p);
-  CUDA_TRY(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = op.grid;
+  cfg.blockDim = dim3(stcd::kConvThreads, 1, 1);
+  cfg.dynamicSmemBytes = op.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = plan->pdl ? 1 : 0;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, op.fn, op.tm, p));
   (void)plan;
   return STCD_OK;
 }
@@ -197,7 +208,7 @@ int run_chunk(stcd_plan* plan, const float* x1, const float* x2, int n_valid, fl
       const int hw = t.h * t.w;
       const size_t total = (size_t)2 * plan->chunk * hw;
       const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
-      stcd::input_pack_kernel<<<blocks, 256, 0, st>>>(x1, x2, (__nv_bfloat16*)t.ptr, plan->chunk, n_valid, k.cin, hw);
+      stcd::input_pack_kernel<<<blocks, 256, 0, st>>>(x1, x2, (__nv_bfloat16*)t.ptr, plan->chunk, n_valid, k.cin, t.c / 8, hw);
       CUDA_TRY(cudaGetLastError());
     }
     ++op_i;
@@ -285,8 +296,8 @@ int stcd_plan_add_input_pack(stcd_plan* plan, int dst_tensor, int cin) {
   if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
   if (!valid_tensor(plan, dst_tensor)) return -fail(STCD_ERR_INVALID, "bad dst tensor %d", dst_tensor);
   const Tensor& t = plan->tensors[dst_tensor];
-  if (t.mult != 2 || t.c != 16 || cin < 1 || cin > 16)
-    return -fail(STCD_ERR_INVALID, "input pack needs a [2*chunk][2][h][w][8] tensor and cin <= 16 (got mult=%d c=%d cin=%d)",
+  if (t.mult != 2 || (t.c != 8 && t.c != 16) || cin < 1 || cin > t.c)
+    return -fail(STCD_ERR_INVALID, "input pack needs a [2*chunk][1 or 2][h][w][8] tensor and cin <= its channels (got mult=%d c=%d cin=%d)",
                  t.mult, t.c, cin);
   plan->packs.push_back({dst_tensor, cin});
   plan->ops.push_back({1, (int)plan->packs.size() - 1});
@@ -363,7 +374,8 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
       const stcd_chunk& e = d->chunks[f.chunk_begin + i];
       if (e.src < 0 || e.src >= d->n_src) return -fail(STCD_ERR_INVALID, "chunk %d: src %d", i, e.src);
       const Tensor& t = plan->tensors[d->src[e.src]];
-      if (e.c0 < 0 || (e.c0 % 8) || e.c0 + d->kc > t.c)
+      // a chunk may overhang the tensor's last 8-channel group: TMA zero-fills the missing group
+      if (e.c0 < 0 || (e.c0 % 8) || e.c0 >= t.c || e.c0 + d->kc > (t.c + 15) / 16 * 16)
         return -fail(STCD_ERR_INVALID, "chunk %d: channels [%d,+%d) of %d", i, e.c0, d->kc, t.c);
       const int top = (d->pair ? 1 : d->img_mult - 1) * plan->chunk + plan->chunk - 1 + e.n_off;
       if (e.n_off < 0 || top >= t.mult * plan->chunk) return -fail(STCD_ERR_INVALID, "chunk %d: image offset %d overruns source", i, e.n_off);
@@ -458,7 +470,12 @@ int stcd_plan_finalize(stcd_plan* plan) {
   int n_kernels = 0;
   const stcd::ConvKernelEntry* kernels = stcd::conv_kernel_table(&n_kernels);
   for (int i = 0; i < n_kernels; ++i)
+  {
     CUDA_TRY(cudaFuncSetAttribute(kernels[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    // one shared-memory carve-out for every instance: consecutive launches never reconfigure the SM
+    CUDA_TRY(cudaFuncSetAttribute(kernels[i].fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
+  plan->pdl = env_int("STCD_PDL", 1);
   const int force_generic = env_int("STCD_FORCE_GENERIC", 0);
   int n_sm = 148;
   CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, plan->device));
@@ -496,6 +513,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
     p.ho = d.hg * d.osy;
     p.wo = d.wg * d.osx;
     p.n_phase = d.n_phase;
+    p.n_src = d.n_src;
     int max_blocks = 0, blocks_total = 0;
     for (int ph = 0; ph < d.n_phase; ++ph) {
       p.phase[ph] = {d.phase[ph].chunk_begin, d.phase[ph].chunk_count, d.phase[ph].oy, d.phase[ph].ox, d.phase[ph].w_block,

@@ -195,10 +195,12 @@ class Segment:
 
 
 def choose_kc(c_list: Sequence[int]) -> int:
+    """Channels per A-stage chunk.  Stored channel counts are multiples of 8; a count that is an odd
+    multiple of 8 is covered by a 16-channel chunk whose missing half TMA zero-fills."""
     for kc in (64, 32, 16):
-        if all(c % kc == 0 for c in c_list):
+        if all(((c + 15) // 16 * 16) % kc == 0 for c in c_list):
             return kc
-    raise ValueError(f"channel counts {list(c_list)} are not multiples of 16")
+    raise ValueError(f"channel counts {list(c_list)} are not multiples of 8")
 
 
 def choose_n_tile(cout: int, pair: bool) -> Tuple[int, int]:

@@ -125,7 +125,7 @@ def lower_siamunet(sd: Dict[str, torch.Tensor], fusion: str, input_nbr: int, lab
         raise ValueError("input_nbr > 16 not supported by the input packer")
     sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
     p = L.Program(model=f"SiamUnet_{fusion}", in_channels=input_nbr, h=h, w=w)
-    p.tensor("in", 2, h, w, 16)
+    p.tensor("in", 2, h, w, 8 if input_nbr <= 8 else 16)
     p.ops.append(L.InputPackSpec("pack", "in", input_nbr))
 
     def bn_fold(name: str, cout: int):
