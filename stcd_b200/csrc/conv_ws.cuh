@@ -93,6 +93,7 @@ struct ConvParams {
   uint32_t a_stage_bytes, a_sub_bytes, wblk_bytes, tmem_cols, acc_cols;
   const uint8_t* wpack;        // device: [n_ntiles][total blocks] blocks of wblk_bytes
   int32_t blocks_per_ntile;    // total blocks over all phases
+  uint32_t tab_bytes;          // dynamic shared memory reserved for the per-MMA descriptor table
   const float* scale;
   const float* shift;
   const float* scale2;
@@ -151,10 +152,8 @@ struct ChunkLoad {   // A producer
   int32_t src_merged;  // src | merged << 8
 };
 struct ChunkMma {    // MMA issuer
-  uint32_t a_hi;       // SBO | version
-  uint32_t a_lo_lbo;   // LBO << 16
-  uint32_t a_kstep16;  // 2 * LBO >> 4: A advance per K=16 step
-  uint32_t n_taps;
+  uint32_t a_hi;       // A descriptor high word: SBO | version
+  uint32_t n_mma;      // MMAs (per M tile) this chunk feeds = taps * K steps
 };
 
 #define STCD_HAS(flag, runtime_expr) ((EPI & E_GENERIC) ? (runtime_expr) : ((EPI & (flag)) != 0))
@@ -168,8 +167,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) ChunkLoad s_cload[kMaxChunks];
-  __shared__ __align__(16) ChunkMma s_cmma[kMaxChunks];
-  __shared__ __align__(8) uint2 s_tap[kMaxTaps];     // {A offset (16 B units), B address>>4 | W barrier slot << 16}
+  __shared__ __align__(8) ChunkMma s_cmma[kMaxChunks];
   __shared__ __align__(16) float s_aff[4][256];      // scale, shift, scale2, shift2 of this CTA's N tile
 
   const int warp = threadIdx.x >> 5;
@@ -190,9 +188,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
   const int my_tiles = (p.n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  uint8_t* smem_w = smem;  // W region first, then the A ring
+  // per-MMA descriptor table {A descriptor low word relative to the stage, B descriptor low word},
+  // one entry per (tap, K step) of this phase in issue order, then the W region, then the A ring
+  uint2* s_mma = reinterpret_cast<uint2*>(smem);
+  uint8_t* smem_w = smem + p.tab_bytes;
   const uint32_t w_region = (p.w_resident ? static_cast<uint32_t>(phase.n_blocks) : static_cast<uint32_t>(p.w_stages)) * p.wblk_bytes;
-  uint8_t* smem_a = smem + ((w_region + 127u) & ~127u);
+  uint8_t* smem_a = smem_w + ((w_region + 127u) & ~127u);
   const uint8_t* wsrc = p.wpack + (static_cast<size_t>(nt) * p.blocks_per_ntile + phase.w_block) * p.wblk_bytes;
   const int w_per = (phase.n_blocks + kMaxWStages - 1) / kMaxWStages;  // resident mode: blocks per barrier slot
 
@@ -217,19 +218,24 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       L.tx_bytes = static_cast<uint32_t>(MT) * (p.kc / 8) * phh * pw * 16u;
       L.src_merged = ch.src | (merged << 8);
       s_cload[c] = L;
+      const int ksteps = p.kc >> 4;
       ChunkMma M;
       M.a_hi = (static_cast<uint32_t>(pw) & 0x3FFF) | (1u << 14);            // SBO = pw * 16 B; descriptor version 1
-      M.a_lo_lbo = (static_cast<uint32_t>(pw * phh) & 0x3FFF) << 16;          // LBO = pw * ph * 16 B
-      M.a_kstep16 = 2u * static_cast<uint32_t>(pw * phh);
-      M.n_taps = ch.n_taps;
+      M.n_mma = static_cast<uint32_t>(ch.n_taps * ksteps);
       s_cmma[c] = M;
+      const uint32_t a_lo_lbo = (static_cast<uint32_t>(pw * phh) & 0x3FFF) << 16;   // LBO = pw * ph * 16 B
+      const uint32_t b_lo_lbo = (static_cast<uint32_t>(p.n_tile) & 0x3FFF) << 16;  // LBO = n_tile * 16 B
       for (int k = 0; k < ch.n_taps; ++k) {
         const Tap tp = p.taps[ch.tap_begin + k];
         const int blk = ch.tap_begin - tap0 + k;
-        uint2 e;
-        e.x = static_cast<uint32_t>(tp.ty * pw + tp.tx);
-        e.y = p.w_resident ? ((w_base16 + static_cast<uint32_t>(blk) * (p.wblk_bytes >> 4)) | (static_cast<uint32_t>(blk / w_per) << 16)) : 0u;
-        s_tap[blk] = e;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          uint2 e;
+          e.x = a_lo_lbo + static_cast<uint32_t>(tp.ty * pw + tp.tx) + static_cast<uint32_t>(ks) * 2u * (pw * phh);
+          // resident weights: absolute block address; streamed weights: offset inside the ring slot
+          e.y = b_lo_lbo + (p.w_resident ? w_base16 + static_cast<uint32_t>(blk) * (p.wblk_bytes >> 4) : 0u) +
+                static_cast<uint32_t>(ks) * 2u * p.n_tile;
+          s_mma[blk * ksteps + ks] = e;
+        }
       }
     }
   }
@@ -344,10 +350,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     const bool leader = elect_one() && !(p.dbg & 1);
     const uint32_t idesc = make_idesc_bf16(p.n_tile);
     const int ksteps = p.kc >> 4;                   // 1, 2 or 4
-    const int ks_shift = (ksteps == 4) ? 2 : (ksteps >> 1);
     const uint32_t b_hi = (128u >> 4) | (1u << 14);                                   // SBO = 128 B, version 1
-    const uint32_t b_lo_lbo = (static_cast<uint32_t>(p.n_tile) & 0x3FFF) << 16;      // LBO = n_tile * 16 B
-    const uint32_t b_kstep16 = 2u * static_cast<uint32_t>(p.n_tile);
     const uint32_t wblk16 = p.wblk_bytes >> 4;
     const uint32_t w_base16 = (smem_u32(smem_w) & 0x3FFFF) >> 4;
     const uint32_t a_ring16 = (smem_u32(smem_a) & 0x3FFFF) >> 4;
@@ -357,7 +360,15 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     int s = 0, ws = 0;
     uint32_t a_par = 0, w_par = 0;
     uint32_t a_base16 = a_ring16;
-    int w_ready = 0;  // resident mode: barrier slots already waited for
+    if (resident) {
+      // weights were requested before the dependency wait: they land while the previous kernel
+      // drains; take all of them before the first MMA so the issue loop never looks at them again
+      for (int i = 0; i < kMaxWStages; ++i) {
+        if (i * w_per >= phase.n_blocks) break;
+        mbar_wait(&w_full[i], 0);
+      }
+      tc_fence_after();
+    }
     for (int t = 0; t < my_tiles; ++t) {
       const int acc = t & 1;
       mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
@@ -365,42 +376,25 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       const uint32_t d0 = tmem_base + acc * p.acc_cols;
       const uint32_t d1 = d0 + p.n_tile;
       uint32_t accum = 0;
-      int blk = 0;
+      int mma_off = 0;
       for (int c = 0; c < phase.chunk_count; ++c) {
         const ChunkMma M = s_cmma[c];
+        const int n_mma = static_cast<int>(M.n_mma);
         mbar_wait(&a_full[s], a_par);
         tc_fence_after();
         if (t == 0 && c == 0 && leader) STCD_STAMP(2);
-        const uint32_t a_lo_base = M.a_lo_lbo + a_base16;
         if (resident) {
-          if (t == 0) {  // first tile: weights may still be landing (slots arrive in order)
-            const int slot = static_cast<int>(s_tap[blk + M.n_taps - 1].y >> 16);
-            if (w_ready <= slot) {
-              while (w_ready <= slot) {
-                mbar_wait(&w_full[w_ready], 0);
-                ++w_ready;
-              }
-              tc_fence_after();
-            }
-          }
-          // Lane i prepares the descriptors of MMA i of this chunk (tap = i / ksteps, K step =
-          // i % ksteps); the issue loop then only shuffles them out, so its instructions are
-          // independent of each other and pipeline instead of forming one latency chain.
-          const int n_mma = static_cast<int>(M.n_taps) << ks_shift;
+          // Lane i holds the descriptors of MMA i of this chunk; the issue loop only shuffles them
+          // out, so its instructions are independent and pipeline instead of forming one chain.
           for (int base = 0; base < n_mma; base += 32) {
-            const int i = base + lane;
-            uint32_t my_a = 0, my_b = 0;
-            if (i < n_mma) {
-              const int k = i >> ks_shift, ks = i & (ksteps - 1);
-              const uint2 te = s_tap[blk + k];
-              my_a = a_lo_base + te.x + ks * M.a_kstep16;
-              my_b = b_lo_lbo + (te.y & 0xFFFF) + ks * b_kstep16;
-            }
             const int cnt = min(32, n_mma - base);
+            uint2 my = make_uint2(0u, 0u);
+            if (lane < cnt) my = s_mma[mma_off + base + lane];
+            my.x += a_base16;
 #pragma unroll 4
             for (int j = 0; j < cnt; ++j) {
-              const uint32_t a_lo = __shfl_sync(0xffffffffu, my_a, j);
-              const uint32_t b_lo = __shfl_sync(0xffffffffu, my_b, j);
+              const uint32_t a_lo = __shfl_sync(0xffffffffu, my.x, j);
+              const uint32_t b_lo = __shfl_sync(0xffffffffu, my.y, j);
               if (leader) {
                 umma_bf16_lohi(d0, a_lo, M.a_hi, b_lo, b_hi, idesc, accum);
                 if (MT == 2) umma_bf16_lohi(d1, a_lo + a_sub16, M.a_hi, b_lo, b_hi, idesc, accum);
@@ -408,22 +402,18 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
               accum = 1;
             }
           }
-          blk += M.n_taps;
         } else {
-          for (uint32_t k = 0; k < M.n_taps; ++k, ++blk) {
-            const uint2 te = s_tap[blk];
+          for (int i = 0; i < n_mma; i += ksteps) {  // one weight block (tap) per ring slot
             mbar_wait(&w_full[ws], w_par);
             tc_fence_after();
-            uint32_t b_lo = b_lo_lbo + w_base16 + static_cast<uint32_t>(ws) * wblk16;
-            uint32_t a_lo = a_lo_base + te.x;
+            const uint32_t b_slot16 = w_base16 + static_cast<uint32_t>(ws) * wblk16;
             for (int ks = 0; ks < ksteps; ++ks) {
+              const uint2 e = s_mma[mma_off + i + ks];
               if (leader) {
-                umma_bf16_lohi(d0, a_lo, M.a_hi, b_lo, b_hi, idesc, accum);
-                if (MT == 2) umma_bf16_lohi(d1, a_lo + a_sub16, M.a_hi, b_lo, b_hi, idesc, accum);
+                umma_bf16_lohi(d0, e.x + a_base16, M.a_hi, e.y + b_slot16, b_hi, idesc, accum);
+                if (MT == 2) umma_bf16_lohi(d1, e.x + a_base16 + a_sub16, M.a_hi, e.y + b_slot16, b_hi, idesc, accum);
               }
               accum = 1;
-              a_lo += M.a_kstep16;
-              b_lo += b_kstep16;
             }
             if (leader) umma_commit(&w_empty[ws]);
             if (++ws == p.w_stages) {
@@ -432,6 +422,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             }
           }
         }
+        mma_off += n_mma;
         if (leader) umma_commit(&a_empty[s]);
         a_base16 += a_stage16;
         if (++s == p.a_stages) {

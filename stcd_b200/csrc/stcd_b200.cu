@@ -537,13 +537,14 @@ int stcd_plan_finalize(stcd_plan* plan) {
     while (cols < 2 * p.acc_cols) cols <<= 1;
     p.tmem_cols = cols;
     // ---- shared-memory plan: weight-stationary when every block of a phase fits beside >= 2 A stages
+    p.tab_bytes = (uint32_t)round_up((size_t)max_blocks * (d.kc / 16) * 8, 128);
     const size_t w_all = (size_t)max_blocks * p.wblk_bytes;
     const int groups = d.n_phase * p.n_ntiles;
     int occ = 0;
     for (int o = 2; o >= 1 && !occ; --o) {
       if (force_occ && o != force_occ) continue;
       if (cols * o > 512) continue;
-      const size_t budget = (o == 2 ? (kSmemMax - 2048) / 2 : kSmemMax) - 256;
+      const size_t budget = (o == 2 ? (kSmemMax - 2048) / 2 : kSmemMax) - 256 - p.tab_bytes;
       const int min_stages = (o == 2) ? 3 : 2;
       if (!force_stream && w_all + (size_t)min_stages * p.a_stage_bytes <= budget) {
         occ = o;
@@ -563,7 +564,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
     }
     if (!occ) return fail(STCD_ERR_INVALID, "conv op: no shared-memory plan (forced occupancy %d)", force_occ);
     const size_t w_region = round_up(p.w_resident ? w_all : (size_t)p.w_stages * p.wblk_bytes, 128);
-    op.smem = w_region + (size_t)p.a_stages * p.a_stage_bytes + 128;
+    op.smem = p.tab_bytes + w_region + (size_t)p.a_stages * p.a_stage_bytes + 128;
     if (op.smem > kSmemMax) return fail(STCD_ERR_INVALID, "conv op needs %zu B of shared memory", op.smem);
     const int ctas = std::max(1, (n_sm * occ) / groups);
     op.grid = dim3((unsigned)std::min(p.n_tiles, ctas), (unsigned)groups, 1);

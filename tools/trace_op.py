@@ -30,9 +30,13 @@ for i, op in enumerate(prog.ops):
     gt = t[:, 0]
     span_us = (gt.max() - gt.min()) / 1e3
     end_ns = (gt + t[:, 7] / 1.965).max()
-    if i > 0 and "prev_end" in globals() and prev_end:
-        print(f"     timeline: gap after previous op {(gt.min() - prev_end) / 1e3:6.1f} us, kernel {(end_ns - gt.min()) / 1e3:6.1f} us")
-    prev_end = end_ns
+    if "t_origin" not in globals():
+        t_origin = gt.min()
+        prev_end = 0
+    first_mma_ns = (gt + t[:, 2] / 1.965).min()
+    print(f"     timeline: start {(gt.min() - t_origin) / 1e3:7.1f} us  first-mma {(first_mma_ns - t_origin) / 1e3:7.1f}  end {(end_ns - t_origin) / 1e3:7.1f}  "
+          f"(start - prev end {(gt.min() - prev_end - t_origin) / 1e3 if prev_end else 0:6.1f}, first-mma - prev end {(first_mma_ns - prev_end - t_origin) / 1e3 if prev_end else 0:6.1f}, busy {(end_ns - max(first_mma_ns, prev_end + t_origin)) / 1e3:6.1f})")
+    prev_end = end_ns - t_origin
     med = np.median(t, axis=0)
     print(f"{op.name:8s} grid=({info[0]},{info[1]}) smem={info[2]} aS={info[3]} wS={info[4]} res={info[5]} tmem={info[6]} tiles={info[7]} aB={info[8]} wB={info[9]} start-span={span_us:.1f}us")
     print("     median cycles: " + " ".join(f"{names[k]}={int(med[k])}" for k in (1, 8, 2, 3, 12, 13, 14, 15, 4, 5, 6, 9, 10, 7, 11)))
