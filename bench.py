@@ -35,6 +35,8 @@ import torch  # noqa: E402
 
 # workload -> (net kind, ctor args, synth gain, H, W, per-GPU batch, binarise kind, config string)
 WORKLOADS = {
+    "snunet_256_b64": dict(net="SNUNet_ECAM", n_class=2, h=256, w=256, batch=64, kind="argmax",
+                           desc="C2: SNUNet-CD (ECAM) 256x256 RGB pairs, batch 64 per GPU, bf16"),
     "siamunet_diff_256": dict(net="SiamUnet_diff", n_class=2, h=256, w=256, batch=8, kind="argmax",
                               desc="C1: SiamUnet_diff 256x256 RGB pairs, batch 8 per GPU"),
     "siamunet_diff_256_b64": dict(net="SiamUnet_diff", n_class=2, h=256, w=256, batch=64, kind="argmax",
@@ -42,13 +44,13 @@ WORKLOADS = {
     "siamunet_conc_256": dict(net="SiamUnet_conc", n_class=2, h=256, w=256, batch=8, kind="argmax",
                               desc="SiamUnet_conc 256x256 RGB pairs, batch 8 per GPU"),
 }
-DEFAULT_WORKLOAD = "siamunet_diff_256_b64"
+DEFAULT_WORKLOAD = "snunet_256_b64"
 
 
 def build_net(wl):
-    from stcd_b200 import siamunet, synth
-    cls = {"SiamUnet_diff": siamunet.SiamUnet_diff, "SiamUnet_conc": siamunet.SiamUnet_conc}[wl["net"]]
-    return synth.randomize_(cls(3, wl["n_class"]).eval(), gain=synth.GAINS[wl["net"]])
+    from stcd_b200 import synth
+    from stcd_b200.networks import CLASSES
+    return synth.prepare_(CLASSES[wl["net"]](3, wl["n_class"]).eval(), wl["net"])
 
 
 def oracle_forward(wl, sd, x1, x2):
@@ -57,6 +59,8 @@ def oracle_forward(wl, sd, x1, x2):
         return nets.siamunet_forward(sd, x1, x2, "diff")
     if wl["net"] == "SiamUnet_conc":
         return nets.siamunet_forward(sd, x1, x2, "conc")
+    if wl["net"] == "SNUNet_ECAM":
+        return nets.snunet_forward(sd, x1, x2)
     raise KeyError(wl["net"])
 
 
@@ -325,7 +329,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--chunk", type=int, default=8, help="image pairs per pass through the layer stack")
+    ap.add_argument("--chunk", type=int, default=32, help="image pairs per pass through the layer stack")
     ap.add_argument("--input-sets", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 2
+#define STCD_ABI_VERSION 3
 
 enum stcd_status {
   STCD_OK = 0,
@@ -147,6 +147,24 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* desc);
  * -> bf16 [2*chunk][2][h][w][8] (cin <= 8 real channels, 16 stored) with the T1 images first, then
  * the T2 images. */
 int stcd_plan_add_input_pack(stcd_plan* plan, int dst_tensor, int cin);
+
+/* SNUNet's ECAM tail (models/SNUNet.py:144-149: two ChannelAttention blocks :46-59 + conv_final)
+ * over four activation tensors of `c` channels each, as one fused op writing external output
+ * `out_ext` (fp32 NCHW [n, n_class, h, w]).  All weight pointers are HOST fp32, copied at add time:
+ * ca_fc1 [r][4c], ca_fc2 [4c][r], ca1_fc1 [r1][c], ca1_fc2 [c][r1], w_final [n_class][4c],
+ * b_final [n_class].  Limits: c % 8 == 0, c <= 64, r, r1 <= 16, n_class <= 4. */
+typedef struct stcd_ecam_desc {
+  int32_t src[4];
+  int32_t c, n_class, r, r1;
+  const float* ca_fc1;
+  const float* ca_fc2;
+  const float* ca1_fc1;
+  const float* ca1_fc2;
+  const float* w_final;
+  const float* b_final;
+  int32_t out_ext;
+} stcd_ecam_desc;
+int stcd_plan_add_ecam_head(stcd_plan* plan, const stcd_ecam_desc* desc);
 
 /* allocate the workspace, upload weights, encode TMA descriptors */
 int stcd_plan_finalize(stcd_plan* plan);

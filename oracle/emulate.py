@@ -109,5 +109,28 @@ def run_program(prog: L.Program, x1: torch.Tensor, x2: torch.Tensor, chunk: int 
     return outs
 
 
-def run_aux(op, T, chunk, ext, nv):  # extended by later op kinds
+def run_ecam_head(op: L.EcamHeadSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[torch.Tensor], nv: int) -> None:
+    """csrc/aux_kernels.cuh ecam_stats_kernel + ecam_head_kernel: fp32 reductions over the bf16 level-0
+    tensors, fp32 MLPs, then a per-image 1x1 head (models/SNUNet.py:144-149)."""
+    xs = [T[s][:chunk] for s in op.srcs]                    # [chunk, h, w, C]
+    out = torch.cat(xs, 3)                                  # [chunk, h, w, 4C]
+    intra = xs[0] + xs[1] + xs[2] + xs[3]
+
+    def attention(t, fc1, fc2):
+        avg, mx = t.mean(dim=(1, 2)), t.amax(dim=(1, 2))    # [chunk, C']
+        mlp = lambda v: torch.relu(v @ torch.from_numpy(fc1).T) @ torch.from_numpy(fc2).T  # noqa: E731
+        return torch.sigmoid(mlp(avg) + mlp(mx))
+
+    ca = attention(out, op.ca_fc1, op.ca_fc2)               # [chunk, 4C]
+    ca1 = attention(intra, op.ca1_fc1, op.ca1_fc2)          # [chunk, C]
+    wf = torch.from_numpy(op.w_final)                       # [k, 4C]
+    w_eff = wf[None] * ca[:, None, :]                       # [chunk, k, 4C]
+    b_eff = torch.from_numpy(op.b_final)[None] + (w_eff * ca1.repeat(1, 4)[:, None, :]).sum(2)
+    y = torch.einsum("nhwc,nkc->nkhw", out, w_eff) + b_eff[:, :, None, None]
+    ext[op.out_ext][:nv] = y[:nv]
+
+
+def run_aux(op, T, chunk, ext, nv):
+    if isinstance(op, L.EcamHeadSpec):
+        return run_ecam_head(op, T, chunk, ext, nv)
     raise TypeError(f"emulator: unknown op {op!r}")

@@ -18,30 +18,30 @@ from stcd_b200 import synth
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
-# name -> (reference module path, class, ctor args, gain, batch, H, W)
+# name -> (reference module path, class (= harness family in synth.GAINS), ctor args, batch, H, W)
 CASES = {
-    "siamunet_diff": ("models.SiamUnet_diff", "SiamUnet_diff", (3, 2), synth.GAINS["SiamUnet_diff"], 2, 48, 32),
-    "siamunet_conc": ("models.SiamUnet_conc", "SiamUnet_conc", (3, 2), synth.GAINS["SiamUnet_conc"], 2, 32, 48),
+    "siamunet_diff": ("models.SiamUnet_diff", "SiamUnet_diff", (3, 2), 2, 48, 32),
+    "siamunet_conc": ("models.SiamUnet_conc", "SiamUnet_conc", (3, 2), 2, 32, 48),
+    "snunet": ("models.SNUNet", "SNUNet_ECAM", (3, 2), 2, 32, 48),
 }
 
 
 def reference_net(case: str):
-    mod, cls, args, gain, *_ = CASES[case]
+    mod, cls, args, *_ = CASES[case]
     net = getattr(refimport.ref_module(mod), cls)(*args).eval()
-    synth.randomize_(net, seed=synth.WEIGHT_SEED, gain=gain)
-    return net
+    return synth.prepare_(net, cls)
 
 
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
-    for case, (mod, cls, args, gain, b, h, w) in CASES.items():
+    for case, (mod, cls, args, b, h, w) in CASES.items():
         net = reference_net(case)
         x1, x2 = synth.image_pairs(b, h, w)
         with torch.no_grad():
             y = net(x1, x2)
         ys = y if isinstance(y, (list, tuple)) else [y]
         arrays = {f"out{i}": t.numpy() for i, t in enumerate(ys)}
-        np.savez_compressed(os.path.join(OUT, f"{case}.npz"), gain=gain, batch=b, h=h, w=w,
+        np.savez_compressed(os.path.join(OUT, f"{case}.npz"), gain=synth.GAINS[cls], batch=b, h=h, w=w,
                             weight_seed=synth.WEIGHT_SEED, data_seed=synth.DATA_SEED,
                             x1_sum=float(x1.double().sum()), n_out=len(ys), **arrays)
         print(case, [tuple(t.shape) for t in ys], "std", float(ys[-1].std()))

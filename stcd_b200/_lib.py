@@ -107,7 +107,18 @@ class ConvDesc(C.Structure):
     ]
 
 
-ABI_VERSION = 2
+class EcamDesc(C.Structure):
+    _fields_ = [
+        ("src", C.c_int32 * 4),
+        ("c", C.c_int32), ("n_class", C.c_int32), ("r", C.c_int32), ("r1", C.c_int32),
+        ("ca_fc1", C.POINTER(C.c_float)), ("ca_fc2", C.POINTER(C.c_float)),
+        ("ca1_fc1", C.POINTER(C.c_float)), ("ca1_fc2", C.POINTER(C.c_float)),
+        ("w_final", C.POINTER(C.c_float)), ("b_final", C.POINTER(C.c_float)),
+        ("out_ext", C.c_int32),
+    ]
+
+
+ABI_VERSION = 3
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -119,6 +130,7 @@ SYMBOLS = [
     ("stcd_plan_add_tensor", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("stcd_plan_add_conv", C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
     ("stcd_plan_add_input_pack", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("stcd_plan_add_ecam_head", C.c_int, [C.c_void_p, C.c_void_p]),
     ("stcd_plan_finalize", C.c_int, [C.c_void_p]),
     ("stcd_plan_tensor_copy", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int]),
     ("stcd_plan_read_trace", C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),

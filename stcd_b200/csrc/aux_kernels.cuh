@@ -215,4 +215,211 @@ __global__ void __launch_bounds__(256) confusionK_kernel(const void* __restrict_
     if (hist[i]) atomicAdd(cm + i, static_cast<unsigned long long>(hist[i]));
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K7: SNUNet ECAM tail (models/SNUNet.py:144-149) over the four level-0 node outputs x_k
+// (bf16 [img][C/8][h][w][8] each):
+//   out   = cat(x_0..x_3)                    (4C channels)
+//   intra = x_0 + x_1 + x_2 + x_3            (C channels)
+//   ca    = sigmoid(fc2(relu(fc1(avg(out)))) + fc2(relu(fc1(max(out)))))       [4C]   (ChannelAttention, :46-59)
+//   ca1   = the same block with its own weights on intra                       [C]
+//   y     = conv_final(ca * (out + ca1.repeat(4)))                             [n_class]
+// Pass 1 (ecam_stats_kernel) reduces sum/max per (image, channel) into per-block partials (fixed
+// order: deterministic); pass 2 (ecam_head_kernel) finishes the reduction, runs the two tiny MLPs
+// and applies the per-image 1x1 head  y = sum_c (Wf[k,c] ca[c]) out[c] + (bf[k] + sum_c Wf[k,c] ca[c] ca1[c % C]).
+// Both are HBM-bound: each reads the 4C bf16 channels of every pixel once.
+
+struct EcamParams {
+  const __nv_bfloat16* src[4];
+  int32_t c;         // channels per source (multiple of 8, <= 64)
+  int32_t hw;        // pixels per image
+  int32_t n_img;     // images in the workspace tensors (chunk)
+  int32_t n_valid;   // images to write
+  int32_t n_class;   // <= 4
+  int32_t r, r1;     // hidden units of ca / ca1 (<= 16)
+  int32_t ranges;    // partial blocks per image (pass 1 grid.x)
+  float* partial;    // [n_img][ranges][2][5C]: sums then maxes; index k*C + ch for out, 4C + ch for intra
+  const float* ca_fc1;   // [r][4C]
+  const float* ca_fc2;   // [4C][r]
+  const float* ca1_fc1;  // [r1][C]
+  const float* ca1_fc2;  // [C][r1]
+  const float* w_final;  // [n_class][4C]
+  const float* b_final;  // [n_class]
+  float* out;            // fp32 NCHW [n_valid][n_class][hw]
+};
+
+__device__ __forceinline__ void unpack8_bf16_f(uint4 q, float* v) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+    v[2 * j] = __low2float(h);
+    v[2 * j + 1] = __high2float(h);
+  }
+}
+
+// grid (ranges, C/8, n_img), 256 threads
+__global__ void __launch_bounds__(256) ecam_stats_kernel(const EcamParams p) {
+  const int r = blockIdx.x, g = blockIdx.y, n = blockIdx.z;
+  const int per = (p.hw + p.ranges - 1) / p.ranges;
+  const int p0 = r * per, p1 = min(p.hw, p0 + per);
+  float s[5][8], m[5][8];
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[k][j] = 0.f;
+      m[k][j] = -INFINITY;
+    }
+  const size_t base = (static_cast<size_t>(n) * (p.c >> 3) + g) * p.hw;
+  for (int px = p0 + threadIdx.x; px < p1; px += blockDim.x) {
+    float it[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) it[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v[8];
+      unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(p.src[k] + (base + px) * 8)), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[k][j] += v[j];
+        m[k][j] = fmaxf(m[k][j], v[j]);
+        it[j] += v[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[4][j] += it[j];
+      m[4][j] = fmaxf(m[4][j], it[j]);
+    }
+  }
+  __shared__ float sh_s[8][40], sh_m[8][40];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = s[k][j], b = m[k][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+      }
+      if (lane == 0) {
+        sh_s[warp][k * 8 + j] = a;
+        sh_m[warp][k * 8 + j] = b;
+      }
+    }
+  __syncthreads();
+  if (threadIdx.x < 40) {
+    float a = 0.f, b = -INFINITY;
+    for (int w = 0; w < 8; ++w) {
+      a += sh_s[w][threadIdx.x];
+      b = fmaxf(b, sh_m[w][threadIdx.x]);
+    }
+    const int k = threadIdx.x >> 3, j = threadIdx.x & 7;
+    const int c5 = 5 * p.c;
+    float* dst = p.partial + (static_cast<size_t>(n) * p.ranges + r) * 2 * c5;
+    dst[k * p.c + g * 8 + j] = a;
+    dst[c5 + k * p.c + g * 8 + j] = b;
+  }
+}
+
+constexpr int kEcamPixPerBlock = 2048;
+
+// grid (ceil(hw / kEcamPixPerBlock), n_valid), 256 threads
+__global__ void __launch_bounds__(256) ecam_head_kernel(const EcamParams p) {
+  __shared__ float s_avg[320], s_max[320];        // 5C <= 320
+  __shared__ float s_hid[4][16];                  // ca: avg, max; ca1: avg, max
+  __shared__ float s_ca[256], s_ca1[64];
+  __shared__ __align__(16) float s_w[4][256];     // per-image head weights
+  __shared__ float s_b[4];
+  const int n = blockIdx.y;
+  const int c = p.c, c4 = 4 * p.c, c5 = 5 * p.c;
+  for (int i = threadIdx.x; i < c5; i += blockDim.x) {
+    float a = 0.f, b = -INFINITY;
+    for (int r = 0; r < p.ranges; ++r) {
+      const float* src = p.partial + (static_cast<size_t>(n) * p.ranges + r) * 2 * c5;
+      a += src[i];
+      b = fmaxf(b, src[c5 + i]);
+    }
+    s_avg[i] = a / static_cast<float>(p.hw);
+    s_max[i] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * p.r) {                    // ca hidden layer: fc1 over the 4C out channels
+    const int u = threadIdx.x % p.r, which = threadIdx.x / p.r;
+    const float* v = which ? s_max : s_avg;
+    float a = 0.f;
+    for (int i = 0; i < c4; ++i) a = fmaf(p.ca_fc1[u * c4 + i], v[i], a);
+    s_hid[which][u] = fmaxf(a, 0.f);
+  } else if (threadIdx.x >= 32 && threadIdx.x < 32 + 2 * p.r1) {   // ca1 hidden layer over the C intra channels
+    const int t = threadIdx.x - 32;
+    const int u = t % p.r1, which = t / p.r1;
+    const float* v = (which ? s_max : s_avg) + c4;
+    float a = 0.f;
+    for (int i = 0; i < c; ++i) a = fmaf(p.ca1_fc1[u * c + i], v[i], a);
+    s_hid[2 + which][u] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c4 + c; i += blockDim.x) {
+    if (i < c4) {
+      float a = 0.f, b = 0.f;
+      for (int u = 0; u < p.r; ++u) {
+        a = fmaf(p.ca_fc2[i * p.r + u], s_hid[0][u], a);
+        b = fmaf(p.ca_fc2[i * p.r + u], s_hid[1][u], b);
+      }
+      s_ca[i] = 1.f / (1.f + expf(-(a + b)));
+    } else {
+      const int j = i - c4;
+      float a = 0.f, b = 0.f;
+      for (int u = 0; u < p.r1; ++u) {
+        a = fmaf(p.ca1_fc2[j * p.r1 + u], s_hid[2][u], a);
+        b = fmaf(p.ca1_fc2[j * p.r1 + u], s_hid[3][u], b);
+      }
+      s_ca1[j] = 1.f / (1.f + expf(-(a + b)));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.n_class * c4; i += blockDim.x) {
+    const int k = i / c4, ch = i - k * c4;
+    s_w[k][ch] = p.w_final[i] * s_ca[ch];
+  }
+  __syncthreads();
+  if (threadIdx.x < p.n_class) {
+    float a = p.b_final[threadIdx.x];
+    for (int ch = 0; ch < c4; ++ch) a = fmaf(s_w[threadIdx.x][ch], s_ca1[ch % c], a);
+    s_b[threadIdx.x] = a;
+  }
+  __syncthreads();
+  const int g8 = c >> 3;
+  const int px_end = min(p.hw, (static_cast<int>(blockIdx.x) + 1) * kEcamPixPerBlock);
+  for (int px = blockIdx.x * kEcamPixPerBlock + threadIdx.x; px < px_end; px += blockDim.x) {
+    float acc[4] = {s_b[0], s_b[1], s_b[2], s_b[3]};
+    for (int k = 0; k < 4; ++k) {
+      for (int g = 0; g < g8; ++g) {
+        float v[8];
+        unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(p.src[k] + ((static_cast<size_t>(n) * g8 + g) * p.hw + px) * 8)), v);
+        const int ch = k * c + g * 8;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q < p.n_class) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[q][ch]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&s_w[q][ch + 4]);
+            acc[q] = fmaf(v[0], w0.x, acc[q]);
+            acc[q] = fmaf(v[1], w0.y, acc[q]);
+            acc[q] = fmaf(v[2], w0.z, acc[q]);
+            acc[q] = fmaf(v[3], w0.w, acc[q]);
+            acc[q] = fmaf(v[4], w1.x, acc[q]);
+            acc[q] = fmaf(v[5], w1.y, acc[q]);
+            acc[q] = fmaf(v[6], w1.z, acc[q]);
+            acc[q] = fmaf(v[7], w1.w, acc[q]);
+          }
+        }
+      }
+    }
+    for (int q = 0; q < p.n_class; ++q) p.out[(static_cast<size_t>(n) * p.n_class + q) * p.hw + px] = acc[q];
+  }
+}
+
 }  // namespace stcd

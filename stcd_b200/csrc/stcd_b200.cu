@@ -87,8 +87,17 @@ struct PackOp {
   int dst, cin;
 };
 
+struct EcamOp {
+  stcd_ecam_desc d;
+  std::vector<float> w;     // ca_fc1 | ca_fc2 | ca1_fc1 | ca1_fc2 | w_final | b_final
+  float* w_dev = nullptr;
+  float* partial = nullptr;
+  stcd::EcamParams p;
+  int hw = 0;
+};
+
 struct Op {
-  int kind;  // 0 conv, 1 input pack
+  int kind;  // 0 conv, 1 input pack, 2 ECAM head
   int idx;
 };
 
@@ -101,6 +110,7 @@ struct stcd_plan {
   std::vector<Tensor> tensors;
   std::vector<ConvOp> convs;
   std::vector<PackOp> packs;
+  std::vector<EcamOp> ecams;
   std::vector<Op> ops;
   uint8_t* workspace = nullptr;
   size_t workspace_bytes = 0;
@@ -202,6 +212,16 @@ int run_chunk(stcd_plan* plan, const float* x1, const float* x2, int n_valid, fl
     if (o.kind == 0) {
       int r = launch_conv(plan, plan->convs[o.idx], n_valid, outs, st);
       if (r) return r;
+    } else if (o.kind == 2) {
+      const EcamOp& e = plan->ecams[o.idx];
+      stcd::EcamParams q = e.p;
+      q.n_valid = n_valid;
+      q.out = outs[e.d.out_ext];
+      if (!q.out) return fail(STCD_ERR_INVALID, "external output %d is NULL", e.d.out_ext);
+      stcd::ecam_stats_kernel<<<dim3(q.ranges, q.c / 8, n_valid), 256, 0, st>>>(q);
+      CUDA_TRY(cudaGetLastError());
+      stcd::ecam_head_kernel<<<dim3((e.hw + stcd::kEcamPixPerBlock - 1) / stcd::kEcamPixPerBlock, n_valid), 256, 0, st>>>(q);
+      CUDA_TRY(cudaGetLastError());
     } else {
       const PackOp& k = plan->packs[o.idx];
       const Tensor& t = plan->tensors[k.dst];
@@ -257,6 +277,10 @@ void stcd_plan_destroy(stcd_plan* plan) {
   cudaSetDevice(plan->device);
   for (ConvOp& op : plan->convs)
     if (op.trace) cudaFree(op.trace);
+  for (EcamOp& e : plan->ecams) {
+    if (e.w_dev) cudaFree(e.w_dev);
+    if (e.partial) cudaFree(e.partial);
+  }
   if (plan->workspace) cudaFree(plan->workspace);
   if (plan->arena) cudaFree(plan->arena);
   for (int b = 0; b < 2; ++b) {
@@ -418,6 +442,38 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
   }
   plan->convs.push_back(std::move(op));
   plan->ops.push_back({0, (int)plan->convs.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_ecam_head(stcd_plan* plan, const stcd_ecam_desc* d) {
+  if (!plan || !d) return -fail(STCD_ERR_STATE, "plan/desc is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (d->c < 8 || d->c > 64 || (d->c % 8) || d->n_class < 1 || d->n_class > 4 || d->r < 1 || d->r > 16 || d->r1 < 1 || d->r1 > 16)
+    return -fail(STCD_ERR_INVALID, "ecam head: c=%d n_class=%d r=%d r1=%d out of range", d->c, d->n_class, d->r, d->r1);
+  if (!d->ca_fc1 || !d->ca_fc2 || !d->ca1_fc1 || !d->ca1_fc2 || !d->w_final || !d->b_final || d->out_ext < 0)
+    return -fail(STCD_ERR_INVALID, "ecam head: NULL weights / bad out_ext");
+  int h = 0, w = 0;
+  for (int k = 0; k < 4; ++k) {
+    if (!valid_tensor(plan, d->src[k])) return -fail(STCD_ERR_INVALID, "ecam head: bad src tensor %d", d->src[k]);
+    const Tensor& t = plan->tensors[d->src[k]];
+    if (t.mult != 1 || t.c != d->c || (k && (t.h != h || t.w != w)))
+      return -fail(STCD_ERR_INVALID, "ecam head: src %d is [%d*chunk,%d,%d,%d], need [chunk,%d,%d,%d]", k, t.mult, t.h, t.w, t.c, h, w, d->c);
+    h = t.h;
+    w = t.w;
+  }
+  EcamOp e;
+  e.d = *d;
+  const int c4 = 4 * d->c;
+  const float* parts[6] = {d->ca_fc1, d->ca_fc2, d->ca1_fc1, d->ca1_fc2, d->w_final, d->b_final};
+  const size_t sizes[6] = {(size_t)d->r * c4, (size_t)c4 * d->r, (size_t)d->r1 * d->c, (size_t)d->c * d->r1, (size_t)d->n_class * c4, (size_t)d->n_class};
+  for (int i = 0; i < 6; ++i) e.w.insert(e.w.end(), parts[i], parts[i] + sizes[i]);
+  e.d.ca_fc1 = e.d.ca_fc2 = e.d.ca1_fc1 = e.d.ca1_fc2 = e.d.w_final = e.d.b_final = nullptr;
+  e.hw = h * w;
+  plan->n_ext = std::max(plan->n_ext, d->out_ext + 1);
+  if ((int)plan->ext_elems.size() < plan->n_ext) plan->ext_elems.resize(plan->n_ext, 0);
+  plan->ext_elems[d->out_ext] = (size_t)d->n_class * h * w;
+  plan->ecams.push_back(std::move(e));
+  plan->ops.push_back({2, (int)plan->ecams.size() - 1});
   return (int)plan->ops.size() - 1;
 }
 
@@ -615,6 +671,36 @@ int stcd_plan_finalize(stcd_plan* plan) {
       p.out_diff_c8 = plan->tensors[d.out_diff].c / 8;
     }
   }
+  for (EcamOp& e : plan->ecams) {
+    const stcd_ecam_desc& d = e.d;
+    const int c4 = 4 * d.c;
+    CUDA_TRY(cudaMalloc(&e.w_dev, e.w.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(e.w_dev, e.w.data(), e.w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    stcd::EcamParams& q = e.p;
+    memset(&q, 0, sizeof(q));
+    for (int k = 0; k < 4; ++k) q.src[k] = (const __nv_bfloat16*)plan->tensors[d.src[k]].ptr;
+    q.c = d.c;
+    q.hw = e.hw;
+    q.n_img = plan->chunk;
+    q.n_class = d.n_class;
+    q.r = d.r;
+    q.r1 = d.r1;
+    q.ranges = std::max(1, std::min(16, e.hw / 4096));
+    CUDA_TRY(cudaMalloc(&e.partial, (size_t)plan->chunk * q.ranges * 2 * 5 * d.c * sizeof(float)));
+    q.partial = e.partial;
+    const float* wp = e.w_dev;
+    q.ca_fc1 = wp;
+    wp += (size_t)d.r * c4;
+    q.ca_fc2 = wp;
+    wp += (size_t)c4 * d.r;
+    q.ca1_fc1 = wp;
+    wp += (size_t)d.r1 * d.c;
+    q.ca1_fc2 = wp;
+    wp += (size_t)d.c * d.r1;
+    q.w_final = wp;
+    wp += (size_t)d.n_class * c4;
+    q.b_final = wp;
+  }
   plan->finalized = true;
   return STCD_OK;
 }
@@ -654,7 +740,7 @@ int64_t stcd_plan_workspace_bytes(const stcd_plan* plan) {
 int64_t stcd_plan_launches(const stcd_plan* plan, int n_pairs) {
   if (!plan || n_pairs < 1) return 0;
   const int64_t chunks = (n_pairs + plan->chunk - 1) / plan->chunk;
-  return chunks * (int64_t)plan->ops.size();
+  return chunks * (int64_t)(plan->ops.size() + plan->ecams.size());  // an ECAM head op is two kernels
 }
 
 int stcd_forward(stcd_plan* plan, const float* x1, const float* x2, int n_pairs, float* const* outs, int n_outs,

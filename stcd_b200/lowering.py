@@ -374,3 +374,30 @@ def add_conv(
     )
     prog.ops.append(spec)
     return spec
+
+
+# ------------------------------------------------------------------------------------------
+# SNUNet ECAM tail (models/SNUNet.py:144-149) as ONE fused op over the four level-0 node outputs
+
+
+@dataclass
+class EcamHeadSpec:
+    """out = conv_final( ca(cat(x)) * (cat(x) + ca1(sum(x)).repeat(4)) )  for x = srcs (each C channels).
+
+    ca / ca1 are ``ChannelAttention`` blocks (models/SNUNet.py:46-59): sigmoid(fc2(relu(fc1(avgpool)))
+    + fc2(relu(fc1(maxpool)))) with bias-free 1x1 convs.  Per image the whole tail collapses to a 1x1
+    conv with per-image weights W'[k, c] = Wf[k, c] * ca[c] and bias b'[k] = bf[k] + sum_c W'[k, c] *
+    ca1[c % C]: pass 1 reduces avg/max per (image, channel), pass 2 applies the per-image head.
+    """
+    name: str
+    srcs: List[str]              # 4 tensors [chunk, h, w, C]
+    c: int                       # channels per source (32)
+    n_class: int
+    ca_fc1: np.ndarray           # float32 [r, 4C]
+    ca_fc2: np.ndarray           # float32 [4C, r]
+    ca1_fc1: np.ndarray          # float32 [r1, C]
+    ca1_fc2: np.ndarray          # float32 [C, r1]
+    w_final: np.ndarray          # float32 [n_class, 4C]
+    b_final: np.ndarray          # float32 [n_class]
+    out_ext: int = 0
+    macs_per_pair: int = 0

@@ -14,6 +14,7 @@ import torch
 from torch.nn import init
 
 from .siamunet import SiamUnet_conc, SiamUnet_diff
+from .snunet import SNUNet_ECAM
 
 # registry keys of models/networks.py:144-214 that this library does NOT implement (yet): asking for one
 # raises NotImplementedError like an unknown key does upstream, with the reason.
@@ -27,7 +28,12 @@ _REFERENCE_ONLY = (
 _REGISTRY = {
     "SiamUnet_abs": lambda a: SiamUnet_diff(input_nbr=3, label_nbr=a.n_class),     # networks.py:148-149
     "SiamUnet_conc": lambda a: SiamUnet_conc(input_nbr=3, label_nbr=a.n_class),    # networks.py:151-152
+    "SNUNet": lambda a: SNUNet_ECAM(in_ch=3, out_ch=a.n_class),                    # networks.py:168-169
 }
+
+
+# class name (= the reference's) -> drop-in wrapper; synth.GAINS / bench.py / the tests key on these names
+CLASSES = {"SiamUnet_diff": SiamUnet_diff, "SiamUnet_conc": SiamUnet_conc, "SNUNet_ECAM": SNUNet_ECAM}
 
 
 def register(name: str, ctor) -> None:

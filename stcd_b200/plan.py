@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .lowering import ConvSpec, InputPackSpec, Program
+from .lowering import ConvSpec, EcamHeadSpec, InputPackSpec, Program
 
 
 def _fptr(a: Optional[np.ndarray]):
@@ -51,6 +51,8 @@ class Plan:
                 _lib.check_id(lib.stcd_plan_add_input_pack(h, ids[op.dst], op.cin), f"input pack {op.name}")
             elif isinstance(op, ConvSpec):
                 self._add_conv(op)
+            elif isinstance(op, EcamHeadSpec):
+                self._add_ecam(op)
             else:
                 raise TypeError(f"unknown op {op!r}")
         _lib.check(lib.stcd_plan_finalize(h), "stcd_plan_finalize")
@@ -97,6 +99,18 @@ class Plan:
         d.out_raw, d.out_pool, d.out_diff = tid(op.out_raw), tid(op.out_pool), tid(op.out_diff)
         d.out_ext = op.out_ext
         _lib.check_id(self.lib.stcd_plan_add_conv(self._h, C.byref(d)), f"conv {op.name}")
+
+    def _add_ecam(self, op: EcamHeadSpec) -> None:
+        d = _lib.EcamDesc()
+        for i, s in enumerate(op.srcs):
+            d.src[i] = self.tensor_ids[s]
+        d.c, d.n_class = op.c, op.n_class
+        d.r, d.r1 = op.ca_fc1.shape[0], op.ca1_fc1.shape[0]
+        keep = [np.ascontiguousarray(a, np.float32) for a in
+                (op.ca_fc1, op.ca_fc2, op.ca1_fc1, op.ca1_fc2, op.w_final, op.b_final)]
+        d.ca_fc1, d.ca_fc2, d.ca1_fc1, d.ca1_fc2, d.w_final, d.b_final = (_fptr(a) for a in keep)
+        d.out_ext = op.out_ext
+        _lib.check_id(self.lib.stcd_plan_add_ecam_head(self._h, C.byref(d)), f"ecam head {op.name}")
 
     # ------------------------------------------------------------------ queries
     @property

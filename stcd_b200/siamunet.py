@@ -25,6 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import lowering as L
+from .module import PlannedModule
 
 # (name, cin, cout) of the encoder convs per stage; decoder: (name, cout) chains after each up-conv.
 _ENC: List[List[Tuple[str, int, int]]] = [
@@ -45,7 +46,7 @@ def _skip_mult(fusion: str) -> int:
     return {"diff": 1, "conc": 2}[fusion]
 
 
-class _SiamUnet(nn.Module):
+class _SiamUnet(PlannedModule):
     fusion = "diff"
 
     def __init__(self, input_nbr: int, label_nbr: int):
@@ -67,37 +68,9 @@ class _SiamUnet(nn.Module):
                 if name != "11d":
                     setattr(self, f"bn{name}", nn.BatchNorm2d(cout))
                 cin = cout
-        self._plans: Dict[tuple, object] = {}
-        self.chunk_pairs = 8
-
-    # weights changed (load_state_dict / .to / re-init): packed copies are stale
-    def _apply(self, fn, *a, **k):
-        self._plans = {}
-        return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._plans = {}
-        return super().load_state_dict(*a, **k)
-
-    def invalidate_plans(self) -> None:
-        self._plans = {}
 
     def lower(self, h: int, w: int) -> L.Program:
         return lower_siamunet(self.state_dict(), self.fusion, self.input_nbr, self.label_nbr, h, w)
-
-    def plan_for(self, x: torch.Tensor):
-        from .plan import Plan
-        if self.training:
-            raise RuntimeError("stcd_b200 implements the eval-mode inference path; call .eval() first "
-                               "(training stays with the reference, models/trainer.py)")
-        if not x.is_cuda:
-            raise RuntimeError("stcd_b200 has no CPU path: move the module and its inputs to a B200 (cuda) device")
-        key = (x.device.index, int(x.shape[2]), int(x.shape[3]), self.chunk_pairs)
-        plan = self._plans.get(key)
-        if plan is None:
-            plan = Plan(self.lower(key[1], key[2]), self.chunk_pairs, device=key[0])
-            self._plans[key] = plan
-        return plan
 
     @torch.no_grad()
     def forward(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:

@@ -24,7 +24,11 @@ DATA_SEED = 1338
 # the logits) while the bf16 path's error is RELATIVE (~1 % of the activation scale after ~24 fused
 # layers, 5-sigma tail over 1e5 logits), so the harness keeps the logit standard deviation near 0.2-0.3:
 # non-degenerate change maps (tens of % "changed") with the tolerance still meaningful.
-GAINS = {"SiamUnet_diff": 0.72, "SiamUnet_conc": 0.70}
+GAINS = {"SiamUnet_diff": 0.72, "SiamUnet_conc": 0.70, "SNUNet_ECAM": 0.6}
+# Head-bias offsets (parameter name, per-class values added after the random draw) that centre the
+# class margin of nets whose random-init margin is one-sided (SNUNet's post-ReLU features make class
+# 0 win everywhere): without it the change map is all-zero and pixel agreement says nothing.
+HEAD_BIAS = {"SNUNet_ECAM": ("conv_final.bias", [0.0, 0.95])}
 
 
 @torch.no_grad()
@@ -52,6 +56,20 @@ def randomize_(net: nn.Module, seed: int = WEIGHT_SEED, gain: float = 1.0) -> nn
         elif isinstance(m, nn.LayerNorm):
             m.weight.copy_(0.8 + 0.4 * torch.rand(m.weight.shape, generator=g))
             m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    return net
+
+
+@torch.no_grad()
+def prepare_(net: nn.Module, name: str, seed: int = WEIGHT_SEED) -> nn.Module:
+    """The harness' weights for net family `name` (works on our wrappers and on the reference modules
+    alike: same parameter names): seeded random draw at GAINS[name] + the HEAD_BIAS offset."""
+    randomize_(net, seed=seed, gain=GAINS[name])
+    if name in HEAD_BIAS:
+        pname, vals = HEAD_BIAS[name]
+        bias = dict(net.named_parameters())[pname]
+        bias.add_(torch.tensor(vals[: bias.numel()], dtype=bias.dtype))
+    if hasattr(net, "invalidate_plans"):
+        net.invalidate_plans()
     return net
 
 

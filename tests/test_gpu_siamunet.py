@@ -50,6 +50,7 @@ def test_forward_matches_golden(case, golden_dir):
     g = np.load(os.path.join(golden_dir, f"{case}.npz"))
     fusion = case.split("_")[1]
     net = synth.randomize_(NETS[fusion][0](3, 2).eval(), seed=int(g["weight_seed"]), gain=float(g["gain"])).cuda()
+    assert float(g["gain"]) == NETS[fusion][1]
     x1, x2 = synth.image_pairs(int(g["batch"]), int(g["h"]), int(g["w"]), seed=int(g["data_seed"]))
     y = net(x1.cuda(), x2.cuda()).cpu()
     ref = torch.from_numpy(g["out0"])

@@ -30,6 +30,29 @@ def test_siamunet_program_matches_oracle(fusion, cls, gain):
     assert 0.02 < (y[:, 1] > y[:, 0]).float().mean().item() < 0.98, "degenerate change map: parity would say nothing"
 
 
+def test_snunet_program_matches_oracle():
+    from stcd_b200 import snunet
+    net = synth.prepare_(snunet.SNUNet_ECAM(3, 2).eval(), "SNUNet_ECAM")
+    x1, x2 = synth.image_pairs(3, 32, 48)
+    with torch.no_grad():
+        y = nets.snunet_forward(net.state_dict(), x1, x2)
+    prog = net.lower(32, 48)
+    ye = emulate.run_program(prog, x1, x2, chunk=2)[0]
+    assert ye.shape == y.shape
+    assert (ye - y).abs().max().item() < BF16_TOL
+    margin = (y[:, 1] - y[:, 0]).abs()
+    agree = ((ye[:, 1] > ye[:, 0]) == (y[:, 1] > y[:, 0]))
+    assert agree[margin > BF16_TOL].float().mean().item() >= 0.999
+    assert 0.02 < (y[:, 1] > y[:, 0]).float().mean().item() < 0.98, "degenerate change map"
+    # structure: 15 nested blocks x 2 convs + 10 up-convs + pack + fused ECAM head
+    convs = [o for o in prog.ops if isinstance(o, L.ConvSpec)]
+    assert len(convs) == 40 and len(prog.ops) == 42
+    big = net.lower(256, 256)
+    # 46.603 GMAC per pair at 256x256 (conv 43.92 + convT 2.68; + 1x1 head)
+    assert abs(big.macs_per_pair() / 1e9 - 46.603) < 0.02
+    assert max(len(o.srcs) for o in convs) <= L.MAX_SRC
+
+
 def test_program_structure_and_macs():
     net = siamunet.SiamUnet_diff(3, 2).eval()
     prog = net.lower(256, 256)

@@ -14,14 +14,12 @@ from oracle import metric as ometric
 from oracle import nets, refimport
 from oracle.make_golden import CASES
 from stcd_b200 import synth
-from stcd_b200 import siamunet
+from stcd_b200.networks import CLASSES
 
 
 def _our_net(case):
-    mod, cls, args, gain, b, h, w = CASES[case]
-    net = {"SiamUnet_diff": siamunet.SiamUnet_diff, "SiamUnet_conc": siamunet.SiamUnet_conc}[cls](*args).eval()
-    synth.randomize_(net, seed=synth.WEIGHT_SEED, gain=gain)
-    return net
+    mod, cls, args, b, h, w = CASES[case]
+    return synth.prepare_(CLASSES[cls](*args).eval(), cls)
 
 
 def _oracle_forward(case, sd, x1, x2):
@@ -30,6 +28,8 @@ def _oracle_forward(case, sd, x1, x2):
         return [nets.siamunet_forward(sd, x1, x2, "diff")]
     if cls == "SiamUnet_conc":
         return [nets.siamunet_forward(sd, x1, x2, "conc")]
+    if cls == "SNUNet_ECAM":
+        return [nets.snunet_forward(sd, x1, x2)]
     raise KeyError(cls)
 
 
