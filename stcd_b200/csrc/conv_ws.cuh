@@ -449,6 +449,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     const bool has_diff = (MT == 2) && STCD_HAS(E_DIFF, p.out_diff != nullptr);
     const bool has_f32 = STCD_HAS(E_F32, p.out_f32 != nullptr);
 
+    // the residual is prefetched ahead of the accumulator wait, so this role reads global memory
+    // written by the previous kernel without going through the A producer's dependency wait
+    if (has_res) pdl_wait();
     const int wq = warp & 3;  // TMEM lane quarter this warp may access
     const int ty = 4 * wq + (lane >> 3);
     const int tx = lane & 7;
@@ -473,6 +476,20 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       const __nv_bfloat16* q_res = has_res ? p.res + ((static_cast<size_t>(img) * p.res_c8 + cg8) * hw + pix) * 8 : nullptr;
       __nv_bfloat16* q_pool = has_pool ? p.out_pool + ((static_cast<size_t>(img) * p.out_pool_c8 + cg8) * hw_pool + pix_pool) * 8 : nullptr;
       __nv_bfloat16* q_diff = has_diff ? p.out_diff + ((static_cast<size_t>(img) * p.out_diff_c8 + cg8) * hw + pix) * 8 : nullptr;
+      // the residual does not depend on the accumulator: fetch the first 16 channels before waiting
+      // for the MMAs and the next 16 while the current ones are processed (global-load latency
+      // would otherwise be exposed once per 16-column step)
+      uint4 r_cur[MT][2], r_nxt[MT][2];
+      auto load_res = [&](int c0, uint4 (&dst)[MT][2]) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const __nv_bfloat16* r = q_res + (m ? pair_imgs : 0) * p.res_c8 * hw * 8 + static_cast<size_t>(c0 >> 3) * hw * 8;
+          dst[m][0] = __ldg(reinterpret_cast<const uint4*>(r));
+          dst[m][1] = (p.cout - (n0 + c0) > 8) ? __ldg(reinterpret_cast<const uint4*>(r + static_cast<size_t>(hw) * 8))
+                                                : make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      if (has_res && valid) load_res(0, r_cur);
       const int acc = t & 1;
       mbar_wait_relaxed(&acc_full[acc], (t >> 1) & 1);
       tc_fence_after();
@@ -483,6 +500,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
         const int ch = n0 + c0;
         if (ch >= p.cout) break;
         const bool two = (p.cout - ch) > 8;  // both 8-channel groups of this 16-column step are real
+        if (has_res && valid && c0 + 16 < p.n_tile && ch + 16 < p.cout) load_res(c0 + 16, r_nxt);
         uint32_t raw[MT][16];
         tmem_ld16(tlane + c0, raw[0]);
         if (MT == 2) tmem_ld16(tlane + p.n_tile + c0, raw[MT - 1]);
@@ -512,15 +530,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             for (int j = 0; j < 16; ++j) v[m][j] = fmaf(v[m][j], s_aff[2][c0 + j], s_aff[3][c0 + j]);
           }
           if (has_res && valid) {
-            const __nv_bfloat16* r = q_res + m_img * p.res_c8 * hw * 8 + g_off;
             float rv[16];
-            unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(r)), rv);
-            if (two) {
-              unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(r + static_cast<size_t>(hw) * 8)), rv + 8);
-            } else {
-#pragma unroll
-              for (int j = 8; j < 16; ++j) rv[j] = 0.f;
-            }
+            unpack8_bf16(r_cur[m][0], rv);
+            unpack8_bf16(r_cur[m][1], rv + 8);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[m][j] += rv[j];
           }
@@ -562,6 +574,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
           __nv_bfloat16* o = q_diff + g_off;
           *reinterpret_cast<uint4*>(o) = pack8_bf16(d);
           if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(d + 8);
+        }
+        if (has_res) {
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            r_cur[m][0] = r_nxt[m][0];
+            r_cur[m][1] = r_nxt[m][1];
+          }
         }
       }
       tc_fence_before();

@@ -124,9 +124,8 @@ class SegmentationMetric(nn.Module):
     def allreduce(self, group=None):
         """Sum the integer matrix over the data-parallel ranks (NCCL on GPUs): the only collective
         of the path.  A no-op without an initialised process group."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self._cm, op=dist.ReduceOp.SUM, group=group)
+        from .parallel import allreduce_confusion
+        allreduce_confusion(self._cm, group)
         return self
 
     # ------------------------------------------------------------------ scores (train_stcd.py:523-570)
