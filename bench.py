@@ -43,6 +43,11 @@ WORKLOADS = {
                                   desc="SiamUnet_diff 256x256 RGB pairs, batch 64 per GPU"),
     "siamunet_conc_256": dict(net="SiamUnet_conc", n_class=2, h=256, w=256, batch=8, kind="argmax",
                               desc="SiamUnet_conc 256x256 RGB pairs, batch 8 per GPU"),
+    "segcd_r34_1024_b16": dict(net="SegCD", n_class=1, h=1024, w=1024, batch=16, kind="sigmoid", chunk=2, input_sets=2,
+                               desc="C3: smp SegCD (Unet, ResNet-34 Siamese encoder) 1024x1024 RGB pair tiles, batch 16 per GPU, "
+                                    "bf16, + confusion-matrix F1/IoU on sigmoid(change) > 0.5"),
+    "segcd_r34_256_b64": dict(net="SegCD", n_class=1, h=256, w=256, batch=64, kind="sigmoid", chunk=16,
+                              desc="smp SegCD (Unet, ResNet-34 Siamese encoder) 256x256 RGB pairs, batch 64 per GPU, bf16"),
 }
 DEFAULT_WORKLOAD = "snunet_256_b64"
 
@@ -50,6 +55,8 @@ DEFAULT_WORKLOAD = "snunet_256_b64"
 def build_net(wl):
     from stcd_b200 import synth
     from stcd_b200.networks import CLASSES
+    if wl["net"] == "SegCD":
+        return synth.prepare_(CLASSES["SegCD"]("resnet34", classes=wl["n_class"]).eval(), "SegCD")
     return synth.prepare_(CLASSES[wl["net"]](3, wl["n_class"]).eval(), wl["net"])
 
 
@@ -61,6 +68,8 @@ def oracle_forward(wl, sd, x1, x2):
         return nets.siamunet_forward(sd, x1, x2, "conc")
     if wl["net"] == "SNUNet_ECAM":
         return nets.snunet_forward(sd, x1, x2)
+    if wl["net"] == "SegCD":
+        return nets.segcd_forward(sd, x1, x2)
     raise KeyError(wl["net"])
 
 
@@ -136,7 +145,7 @@ def cpu_baseline(wl, seconds_target: float = 15.0, threads: int | None = None):
     torch.set_num_threads(threads)
     net = build_net(wl)
     sd = net.state_dict()
-    n = 2
+    n = 2 if wl["h"] * wl["w"] < 512 * 512 else 1
     x1, x2 = synth.image_pairs(n, wl["h"], wl["w"])
     lab = synth.labels(n, wl["h"], wl["w"]).numpy()
 
@@ -171,7 +180,7 @@ def run_reference(args, wl, rank, world):
     from stcd_b200 import synth
     net = build_net(wl)
     sd = net.state_dict()
-    n = 2                                    # bounded sample per step
+    n = 2 if wl["h"] * wl["w"] < 512 * 512 else 1   # bounded sample per step
     x1, x2 = synth.image_pairs(n, wl["h"], wl["w"])
     lab = synth.labels(n, wl["h"], wl["w"]).numpy()
 
@@ -329,13 +338,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--chunk", type=int, default=32, help="image pairs per pass through the layer stack")
-    ap.add_argument("--input-sets", type=int, default=4)
+    ap.add_argument("--chunk", type=int, default=0, help="image pairs per pass through the layer stack (0: the workload's default)")
+    ap.add_argument("--input-sets", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     wl = WORKLOADS[args.workload]
+    args.chunk = args.chunk or wl.get("chunk", 32)
+    args.input_sets = args.input_sets or wl.get("input_sets", 4)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 3
+#define STCD_ABI_VERSION 4
 
 enum stcd_status {
   STCD_OK = 0,
@@ -138,6 +138,12 @@ typedef struct stcd_conv_desc {
   int32_t out_pool;               /* tensor id or -1 */
   int32_t out_diff;               /* tensor id or -1 (needs pair=1) */
   int32_t out_ext;                /* index into stcd_forward's outs[] for fp32 NCHW logits, or -1 */
+  /* 1: out0 is stored space-to-depth, a [ho/2][wo/2] tensor of 4*cout channels: output pixel (y, x),
+   * channel c -> pixel (y/2, x/2), channel ((y%2)*2 + x%2)*cout + c.  Feature maps read only by
+   * stride-2 convs (torchvision BasicBlock conv1/downsample, models/resnet.py:59-60) and by the Unet
+   * decoder's skip path (decoders/unet/decoder.py:36-40) are stored this way so that every consumer is
+   * a stride-1 halo load over one parity class. */
+  int32_t out0_s2d;
 } stcd_conv_desc;
 
 /* returns op index >= 0, or <0 */
@@ -147,6 +153,29 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* desc);
  * -> bf16 [2*chunk][2][h][w][8] (cin <= 8 real channels, 16 stored) with the T1 images first, then
  * the T2 images. */
 int stcd_plan_add_input_pack(stcd_plan* plan, int dst_tensor, int cin);
+
+/* Space-to-depth variant for the 7x7 stride-2 ResNet stem (smp/encoders/resnet.py:50): x1, x2 fp32 NCHW
+ * [n_pairs, cin, 2h, 2w] -> bf16 [2*chunk][2][h][w][8] with channel (py*2 + px)*cin + c holding
+ * x[c][2y + py][2x + px] (4*cin <= 16); the stem then runs as a 4x4 stride-1 conv. */
+int stcd_plan_add_input_pack_s2d(stcd_plan* plan, int dst_tensor, int cin);
+
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (smp/encoders/resnet.py:51) over a feature map stored
+ * space-to-depth (src: [h][w] pixels x 4c channels = the (2h x 2w) map) -> dst [h][w] x c channels. */
+int stcd_plan_add_maxpool_s2d(stcd_plan* plan, int src_tensor, int dst_tensor, int c);
+
+/* SegCD's tail (segmentation_models_pytorch/decoders/unet/model.py:321-330) as one op over the decoder
+ * output `src` (bf16, both temporal streams: mult = 2, c channels): with head = Conv2d(c, 1, 3, padding=1)
+ * (base/heads.py:5-10), m1 = head(d1), m2 = head(d2), change = min(head(|d1 - d2|), |m1 - m2|).
+ * weight: HOST fp32 [9][c] (tap-major ky*3 + kx), copied at add time.  External outputs out_ext,
+ * out_ext + 1, out_ext + 2 = m1, m2, change (fp32 NCHW [n, 1, h, w]).  c in {8, 16, 24, 32}. */
+typedef struct stcd_seghead_desc {
+  int32_t src;
+  int32_t c;
+  const float* weight;
+  float bias;
+  int32_t out_ext;
+} stcd_seghead_desc;
+int stcd_plan_add_seg_head(stcd_plan* plan, const stcd_seghead_desc* desc);
 
 /* SNUNet's ECAM tail (models/SNUNet.py:144-149: two ChannelAttention blocks :46-59 + conv_final)
  * over four activation tensors of `c` channels each, as one fused op writing external output

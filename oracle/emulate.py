@@ -70,7 +70,14 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
             v[..., : op.cout] = v[..., : op.cout] + T[op.res][sl, :, :, : op.cout]
         if op.relu:
             v = torch.relu(v)
-        if op.out0 is not None:
+        if op.out0 is not None and op.out0_s2d:
+            # space-to-depth store: pixel (y, x), channel c -> pixel (y//2, x//2), channel ((y%2)*2 + x%2)*cout + c
+            q = _bf16(v[..., : op.cout])
+            for py in range(2):
+                for px in range(2):
+                    k = (py * 2 + px) * op.cout
+                    T[op.out0][sl, :, :, k: k + op.cout] = q[:, py::2, px::2]
+        elif op.out0 is not None:
             T[op.out0][sl, :, :, op.out0_coff: op.out0_coff + op.cout] = _bf16(v[..., : op.cout])
         if op.out_ext >= 0:
             ext[op.out_ext][:n_valid] = v[:n_valid, :, :, : op.cout].permute(0, 3, 1, 2)
@@ -94,7 +101,15 @@ def run_program(prog: L.Program, x1: torch.Tensor, x2: torch.Tensor, chunk: int 
         T = {name: torch.zeros(t.mult * chunk, t.h, t.w, t.c) for name, t in prog.tensors.items()}
         ext = [torch.zeros(chunk, e.channels, e.h, e.w) for e in prog.ext]
         for op in prog.ops:
-            if isinstance(op, L.InputPackSpec):
+            if isinstance(op, L.InputPackSpec) and op.s2d:
+                dst = T[op.dst]
+                for s_, xs in enumerate((x1, x2)):
+                    v = _bf16(xs[start: start + nv].permute(0, 2, 3, 1))
+                    for py in range(2):
+                        for px in range(2):
+                            k = (py * 2 + px) * op.cin
+                            dst[s_ * chunk: s_ * chunk + nv, :, :, k: k + op.cin] = v[:, py::2, px::2]
+            elif isinstance(op, L.InputPackSpec):
                 dst = T[op.dst]
                 dst[:nv, :, :, : op.cin] = _bf16(x1[start: start + nv].permute(0, 2, 3, 1))
                 dst[chunk: chunk + nv, :, :, : op.cin] = _bf16(x2[start: start + nv].permute(0, 2, 3, 1))
@@ -130,7 +145,43 @@ def run_ecam_head(op: L.EcamHeadSpec, T: Dict[str, torch.Tensor], chunk: int, ex
     ext[op.out_ext][:nv] = y[:nv]
 
 
+def _from_s2d(t: torch.Tensor, c: int) -> torch.Tensor:
+    """[n, h/2, w/2, 4c] space-to-depth -> [n, h, w, c]."""
+    n, h2, w2, _ = t.shape
+    full = torch.zeros(n, 2 * h2, 2 * w2, c)
+    for py in range(2):
+        for px in range(2):
+            k = (py * 2 + px) * c
+            full[:, py::2, px::2] = t[..., k: k + c]
+    return full
+
+
+def run_maxpool_s2d(op: L.MaxPoolS2DSpec, T: Dict[str, torch.Tensor]) -> None:
+    """csrc/aux_kernels.cuh maxpool3x3s2_s2d_kernel: max over bf16 values is exact."""
+    full = _from_s2d(T[op.src], op.c).permute(0, 3, 1, 2)
+    T[op.dst][..., : op.c] = torch.nn.functional.max_pool2d(full, 3, 2, 1).permute(0, 2, 3, 1)
+
+
+def run_seg_head(op: L.SegHeadSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[torch.Tensor], nv: int) -> None:
+    """csrc/aux_kernels.cuh segcd_head_kernel: fp32 3x3 conv (fp32 weights) over the bf16 decoder output of
+    both streams and over |d1 - d2| (exact in fp32), then change = min(head(|d1 - d2|), |m1 - m2|)."""
+    d = T[op.src][..., : op.c].permute(0, 3, 1, 2)
+    d1, d2 = d[:chunk], d[chunk: 2 * chunk]
+    w = torch.from_numpy(op.weight).reshape(3, 3, op.c).permute(2, 0, 1)[None]      # [1, c, 3, 3]
+    b = torch.tensor([op.bias])
+    head = lambda t: torch.nn.functional.conv2d(t, w, b, padding=1)  # noqa: E731
+    m1, m2 = head(d1), head(d2)
+    change = torch.minimum(head((d1 - d2).abs()), (m1 - m2).abs())
+    ext[op.out_ext][:nv] = m1[:nv]
+    ext[op.out_ext + 1][:nv] = m2[:nv]
+    ext[op.out_ext + 2][:nv] = change[:nv]
+
+
 def run_aux(op, T, chunk, ext, nv):
     if isinstance(op, L.EcamHeadSpec):
         return run_ecam_head(op, T, chunk, ext, nv)
+    if isinstance(op, L.MaxPoolS2DSpec):
+        return run_maxpool_s2d(op, T)
+    if isinstance(op, L.SegHeadSpec):
+        return run_seg_head(op, T, chunk, ext, nv)
     raise TypeError(f"emulator: unknown op {op!r}")

@@ -107,3 +107,52 @@ def snunet_forward(sd: SD, xA: torch.Tensor, xB: torch.Tensor) -> torch.Tensor:
     ca1 = _channel_attention(sd, "ca1", intra)
     out = _channel_attention(sd, "ca", out) * (out + ca1.repeat(1, 4, 1, 1))
     return F.conv2d(out, sd["conv_final.weight"], sd["conv_final.bias"])
+
+
+# ------------------------------------------------------------------------------------------
+# smp SegCD (Siamese Unet, ResNet BasicBlock encoder)
+def _basic_block(sd: SD, pre: str, x: torch.Tensor, stride: int) -> torch.Tensor:
+    """torchvision BasicBlock.forward (== models/resnet.py:57-75)."""
+    out = F.relu(_bn(sd, f"{pre}.bn1", F.conv2d(x, sd[f"{pre}.conv1.weight"], None, stride=stride, padding=1)))
+    out = _bn(sd, f"{pre}.bn2", F.conv2d(out, sd[f"{pre}.conv2.weight"], None, padding=1))
+    if f"{pre}.downsample.0.weight" in sd:
+        x = _bn(sd, f"{pre}.downsample.1", F.conv2d(x, sd[f"{pre}.downsample.0.weight"], None, stride=stride))
+    return F.relu(out + x)
+
+
+def _resnet_features(sd: SD, x: torch.Tensor, layers) -> List[torch.Tensor]:
+    """ResNetEncoder.forward, segmentation_models_pytorch/encoders/resnet.py:47-65."""
+    feats = [x]
+    x = F.relu(_bn(sd, "encoder.bn1", F.conv2d(x, sd["encoder.conv1.weight"], None, stride=2, padding=3)))
+    feats.append(x)
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    for li, n in enumerate(layers):
+        for b in range(n):
+            x = _basic_block(sd, f"encoder.layer{li + 1}.{b}", x, 2 if (b == 0 and li > 0) else 1)
+        feats.append(x)
+    return feats
+
+
+def _unet_decoder(sd: SD, feats: List[torch.Tensor], n_blocks: int) -> torch.Tensor:
+    """UnetDecoder.forward + DecoderBlock.forward, decoders/unet/decoder.py:108-123,35-43."""
+    feats = feats[1:][::-1]
+    x, skips = feats[0], feats[1:]
+    for i in range(n_blocks):
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        if i < len(skips):
+            x = torch.cat([x, skips[i]], dim=1)
+        for c in ("conv1", "conv2"):
+            pre = f"decoder.blocks.{i}.{c}"
+            x = F.relu(_bn(sd, f"{pre}.1", F.conv2d(x, sd[f"{pre}.0.weight"], None, padding=1)))
+    return x
+
+
+def segcd_forward(sd: SD, A: torch.Tensor, B: torch.Tensor, layers=(3, 4, 6, 3)):
+    """SegCD.forward, segmentation_models_pytorch/decoders/unet/model.py:316-332 -> (mask_t1, mask_t2, change)."""
+    n_blocks = sum(1 for k in sd if k.startswith("decoder.blocks.") and k.endswith(".conv1.0.weight"))
+    d1 = _unet_decoder(sd, _resnet_features(sd, A, layers), n_blocks)
+    d2 = _unet_decoder(sd, _resnet_features(sd, B, layers), n_blocks)
+    head = lambda t: F.conv2d(t, sd["segmentation_head.0.weight"], sd["segmentation_head.0.bias"], padding=1)  # noqa: E731
+    m1, m2 = head(d1), head(d2)
+    change = torch.min(head(torch.abs(d1 - d2)), torch.abs(m1 - m2))
+    return m1, m2, change

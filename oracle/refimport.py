@@ -34,6 +34,12 @@ class _Permissive:
         return _Permissive()
 
     def __getitem__(self, k):
+        return self.__dict__.setdefault("_items", {}).setdefault(k, _Permissive())
+
+    def __setitem__(self, k, v):
+        self.__dict__.setdefault("_items", {})[k] = v
+
+    def __deepcopy__(self, memo):
         return _Permissive()
 
     def __iter__(self):

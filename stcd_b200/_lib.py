@@ -104,7 +104,13 @@ class ConvDesc(C.Structure):
         ("out_pool", C.c_int32),
         ("out_diff", C.c_int32),
         ("out_ext", C.c_int32),
+        ("out0_s2d", C.c_int32),
     ]
+
+
+class SegHeadDesc(C.Structure):
+    _fields_ = [("src", C.c_int32), ("c", C.c_int32), ("weight", C.POINTER(C.c_float)), ("bias", C.c_float),
+                ("out_ext", C.c_int32)]
 
 
 class EcamDesc(C.Structure):
@@ -118,7 +124,7 @@ class EcamDesc(C.Structure):
     ]
 
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -130,6 +136,9 @@ SYMBOLS = [
     ("stcd_plan_add_tensor", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("stcd_plan_add_conv", C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
     ("stcd_plan_add_input_pack", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("stcd_plan_add_input_pack_s2d", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("stcd_plan_add_maxpool_s2d", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    ("stcd_plan_add_seg_head", C.c_int, [C.c_void_p, C.c_void_p]),
     ("stcd_plan_add_ecam_head", C.c_int, [C.c_void_p, C.c_void_p]),
     ("stcd_plan_finalize", C.c_int, [C.c_void_p]),
     ("stcd_plan_tensor_copy", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int]),

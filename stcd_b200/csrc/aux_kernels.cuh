@@ -258,6 +258,168 @@ __device__ __forceinline__ void unpack8_bf16_f(uint4 q, float* v) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Space-to-depth input pack for the 7x7 stride-2 ResNet stem: x1, x2 fp32 NCHW [n_valid, cin, 2h, 2w]
+// -> dst bf16 [2*chunk][2][h][w][8], channel (py*2 + px)*cin + c = x[c][2y + py][2x + px] (4*cin <= 16).
+// One thread per half-resolution pixel: each (c, py) row is read as one float2, so a warp reads 256
+// contiguous bytes per row and writes 2 x 512 contiguous bytes.  HBM-bound: 16*cin B read + 32 B written.
+__global__ void __launch_bounds__(256) input_pack_s2d_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                             __nv_bfloat16* __restrict__ dst, int chunk, int n_valid,
+                                                             int cin, int h, int w) {
+  const int hw = h * w;
+  const size_t total = static_cast<size_t>(2) * chunk * hw;
+  const size_t plane = static_cast<size_t>(4) * hw;   // full-resolution channel plane
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / hw);
+    const int pix = static_cast<int>(i - static_cast<size_t>(n) * hw);
+    const int y = pix / w, x = pix - y * w;
+    const int s = n / chunk, b = n - s * chunk;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.f;
+    if (b < n_valid) {
+      const float* src = (s ? x2 : x1) + static_cast<size_t>(b) * cin * plane + static_cast<size_t>(2 * y) * (2 * w) + 2 * x;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < cin) {
+#pragma unroll
+          for (int py = 0; py < 2; ++py) {
+            const float2 q = __ldg(reinterpret_cast<const float2*>(src + c * plane + static_cast<size_t>(py) * (2 * w)));
+            v[(py * 2 + 0) * cin + c] = q.x;
+            v[(py * 2 + 1) * cin + c] = q.y;
+          }
+        }
+      }
+    }
+    uint32_t wd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 hv = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      wd[j] = *reinterpret_cast<uint32_t*>(&hv);
+    }
+    __nv_bfloat16* o = dst + (static_cast<size_t>(n) * 2 * hw + pix) * 8;
+    *reinterpret_cast<uint4*>(o) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// MaxPool2d(3, stride 2, padding 1) over a map stored space-to-depth: src bf16 [n][4*c8][h][w][8] (group
+// cls*c8 + g, cls = py*2 + px, holds full-res pixel (2y + py, 2x + px)) -> dst bf16 [n][c8][h][w][8].
+// out(y, x) = max over full-res rows 2y-1..2y+1, cols 2x-1..2x+1 = parity-1 rows y-1 and y, parity-0 row y.
+// One thread per (pixel, 8-channel group); max on packed bf16 is exact.  HBM-bound: 4 reads + 1 write of
+// 16 B per thread at the algorithmic level (the 9 loads hit L1/L2 for the shared neighbours).
+__device__ __forceinline__ uint4 max8_bf16(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162 x0 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.x), *reinterpret_cast<const __nv_bfloat162*>(&b.x));
+  const __nv_bfloat162 x1 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.y), *reinterpret_cast<const __nv_bfloat162*>(&b.y));
+  const __nv_bfloat162 x2 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.z), *reinterpret_cast<const __nv_bfloat162*>(&b.z));
+  const __nv_bfloat162 x3 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a.w), *reinterpret_cast<const __nv_bfloat162*>(&b.w));
+  r.x = *reinterpret_cast<const uint32_t*>(&x0);
+  r.y = *reinterpret_cast<const uint32_t*>(&x1);
+  r.z = *reinterpret_cast<const uint32_t*>(&x2);
+  r.w = *reinterpret_cast<const uint32_t*>(&x3);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) maxpool3x3s2_s2d_kernel(const __nv_bfloat16* __restrict__ src,
+                                                               __nv_bfloat16* __restrict__ dst, int n_img, int c8, int dst_c8,
+                                                               int h, int w) {
+  const int hw = h * w;
+  const size_t total = static_cast<size_t>(n_img) * c8 * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int pix = static_cast<int>(i % hw);
+    const size_t r = i / hw;
+    const int g = static_cast<int>(r % c8);
+    const int n = static_cast<int>(r / c8);
+    const int y = pix / w, x = pix - y * w;
+    const __nv_bfloat16* base = src + (static_cast<size_t>(n) * 4 * c8 + g) * hw * 8;
+    const size_t cls = static_cast<size_t>(c8) * hw * 8;     // stride between parity classes
+    auto ld = [&](int k, int yy, int xx) { return __ldg(reinterpret_cast<const uint4*>(base + k * cls + (static_cast<size_t>(yy) * w + xx) * 8)); };
+    uint4 m = ld(0, y, x);                       // (2y, 2x)
+    m = max8_bf16(m, ld(1, y, x));               // (2y, 2x+1)
+    m = max8_bf16(m, ld(2, y, x));               // (2y+1, 2x)
+    m = max8_bf16(m, ld(3, y, x));               // (2y+1, 2x+1)
+    if (x > 0) {
+      m = max8_bf16(m, ld(1, y, x - 1));         // (2y, 2x-1)
+      m = max8_bf16(m, ld(3, y, x - 1));         // (2y+1, 2x-1)
+    }
+    if (y > 0) {
+      m = max8_bf16(m, ld(2, y - 1, x));         // (2y-1, 2x)
+      m = max8_bf16(m, ld(3, y - 1, x));         // (2y-1, 2x+1)
+      if (x > 0) m = max8_bf16(m, ld(3, y - 1, x - 1));
+    }
+    *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(n) * dst_c8 + g) * hw + pix) * 8) = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SegCD tail (decoders/unet/model.py:321-330): head = Conv2d(C, 1, 3, padding=1) applied to d1, d2 and
+// |d1 - d2|, then change = min(head(|d1 - d2|), |m1 - m2|).  d: bf16 [2*chunk][C/8][h][w][8] (T1 images then
+// T2 images).  A CTA stages a (16+2) x (32+2) pixel halo tile of both streams in shared memory (zero
+// padded), each thread computes 2 pixels x 3 convolutions in fp32 with fp32 weights.  HBM-bound at the
+// algorithmic level: 2 * C * 2 B read + 12 B written per pixel.
+constexpr int kHeadTW = 32, kHeadTH = 16;
+
+template <int C8>
+__global__ void __launch_bounds__(256) segcd_head_kernel(const __nv_bfloat16* __restrict__ d, const float* __restrict__ wgt,
+                                                         float bias, int chunk, int h, int w, float* __restrict__ m1,
+                                                         float* __restrict__ m2, float* __restrict__ change) {
+  constexpr int PW = kHeadTW + 2, PH = kHeadTH + 2;
+  __shared__ uint4 s_d[2][C8][PH][PW];
+  __shared__ float s_w[9 * C8 * 8];
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.x * kHeadTW, y0 = blockIdx.y * kHeadTH;
+  const size_t hw = static_cast<size_t>(h) * w;
+  for (int i = threadIdx.x; i < 9 * C8 * 8; i += blockDim.x) s_w[i] = wgt[i];
+  for (int i = threadIdx.x; i < 2 * C8 * PH * PW; i += blockDim.x) {
+    const int px = i % PW;
+    int r = i / PW;
+    const int py = r % PH;
+    r /= PH;
+    const int g = r % C8, s = r / C8;
+    const int yy = y0 + py - 1, xx = x0 + px - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+      v = __ldg(reinterpret_cast<const uint4*>(d + ((static_cast<size_t>(s * chunk + n) * C8 + g) * hw + static_cast<size_t>(yy) * w + xx) * 8));
+    s_d[s][g][py][px] = v;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty0 = (threadIdx.x >> 5) * 2;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int ty = ty0 + r;
+    float a1 = bias, a2 = bias, ad = bias;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int ky = k / 3, kx = k - ky * 3;
+#pragma unroll
+      for (int g = 0; g < C8; ++g) {
+        float v1[8], v2[8];
+        unpack8_bf16_f(s_d[0][g][ty + ky][tx + kx], v1);
+        unpack8_bf16_f(s_d[1][g][ty + ky][tx + kx], v2);
+        const float* wk = &s_w[(k * C8 + g) * 8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a1 = fmaf(v1[j], wk[j], a1);
+          a2 = fmaf(v2[j], wk[j], a2);
+          ad = fmaf(fabsf(v1[j] - v2[j]), wk[j], ad);
+        }
+      }
+    }
+    const int yy = y0 + ty, xx = x0 + tx;
+    if (yy < h && xx < w) {
+      const size_t o = static_cast<size_t>(n) * hw + static_cast<size_t>(yy) * w + xx;
+      m1[o] = a1;
+      m2[o] = a2;
+      change[o] = fminf(ad, fabsf(a1 - a2));
+    }
+  }
+}
+
 // grid (ranges, C/8, n_img), 256 threads
 __global__ void __launch_bounds__(256) ecam_stats_kernel(const EcamParams p) {
   const int r = blockIdx.x, g = blockIdx.y, n = blockIdx.z;

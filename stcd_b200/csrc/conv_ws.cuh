@@ -103,6 +103,7 @@ struct ConvParams {
   int32_t res_c8;
   __nv_bfloat16* out0;
   int32_t out0_c8, out0_coff;
+  int32_t out0_s2d;  // 1: out0 is stored space-to-depth ([ho/2][wo/2] pixels, 4*cout channels)
   __nv_bfloat16* out_raw;
   int32_t out_raw_c8;
   __nv_bfloat16* out_pool;
@@ -471,7 +472,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       const uint32_t pix = static_cast<uint32_t>(oy) * p.wo + ox;
       const uint32_t pix_pool = static_cast<uint32_t>(oy >> 1) * (p.wo >> 1) + (ox >> 1);
       // element pointers of (img, first channel group, pixel); image m=1 is pair_imgs images further
-      __nv_bfloat16* q_out0 = has_out0 ? p.out0 + ((static_cast<size_t>(img) * p.out0_c8 + (p.out0_coff >> 3) + cg8) * hw + pix) * 8 : nullptr;
+      // out0 may be stored space-to-depth: plane of hw/4 pixels, parity class (oy&1, ox&1) selects the channel block
+      const uint32_t hw0 = p.out0_s2d ? (hw >> 2) : hw;
+      const uint32_t pix0 = p.out0_s2d ? pix_pool : pix;
+      const uint32_t cg0 = p.out0_s2d ? static_cast<uint32_t>(((oy & 1) * 2 + (ox & 1)) * (p.cout >> 3)) : static_cast<uint32_t>(p.out0_coff >> 3);
+      __nv_bfloat16* q_out0 = has_out0 ? p.out0 + ((static_cast<size_t>(img) * p.out0_c8 + cg0 + cg8) * hw0 + pix0) * 8 : nullptr;
       __nv_bfloat16* q_raw = has_raw ? p.out_raw + ((static_cast<size_t>(img) * p.out_raw_c8 + cg8) * hw + pix) * 8 : nullptr;
       const __nv_bfloat16* q_res = has_res ? p.res + ((static_cast<size_t>(img) * p.res_c8 + cg8) * hw + pix) * 8 : nullptr;
       __nv_bfloat16* q_pool = has_pool ? p.out_pool + ((static_cast<size_t>(img) * p.out_pool_c8 + cg8) * hw_pool + pix_pool) * 8 : nullptr;
@@ -551,9 +556,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
           if (has_out0 || has_pool) {
             const uint4 lo = pack8_bf16(v[m]), hi = pack8_bf16(v[m] + 8);
             if (has_out0 && valid) {
-              __nv_bfloat16* o = q_out0 + m_img * p.out0_c8 * hw * 8 + g_off;
+              __nv_bfloat16* o = q_out0 + (m_img * p.out0_c8 + (c0 >> 3)) * hw0 * 8;
               *reinterpret_cast<uint4*>(o) = lo;
-              if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = hi;
+              if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw0) * 8) = hi;
             }
             if (has_pool) {
               // max over the 2x2 window on the packed bf16 pairs (rounding is monotonic, so

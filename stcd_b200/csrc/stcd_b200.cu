@@ -85,6 +85,18 @@ struct ConvOp {
 
 struct PackOp {
   int dst, cin;
+  int s2d = 0;
+};
+
+struct PoolOp {
+  int src, dst, c;
+};
+
+struct SegHeadOp {
+  int src, c, out_ext;
+  float bias;
+  std::vector<float> w;  // [9][c]
+  float* w_dev = nullptr;
 };
 
 struct EcamOp {
@@ -97,7 +109,7 @@ struct EcamOp {
 };
 
 struct Op {
-  int kind;  // 0 conv, 1 input pack, 2 ECAM head
+  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head
   int idx;
 };
 
@@ -111,6 +123,8 @@ struct stcd_plan {
   std::vector<ConvOp> convs;
   std::vector<PackOp> packs;
   std::vector<EcamOp> ecams;
+  std::vector<PoolOp> pools;
+  std::vector<SegHeadOp> heads;
   std::vector<Op> ops;
   uint8_t* workspace = nullptr;
   size_t workspace_bytes = 0;
@@ -222,13 +236,40 @@ int run_chunk(stcd_plan* plan, const float* x1, const float* x2, int n_valid, fl
       CUDA_TRY(cudaGetLastError());
       stcd::ecam_head_kernel<<<dim3((e.hw + stcd::kEcamPixPerBlock - 1) / stcd::kEcamPixPerBlock, n_valid), 256, 0, st>>>(q);
       CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 3) {
+      const PoolOp& k = plan->pools[o.idx];
+      const Tensor& ts = plan->tensors[k.src];
+      const Tensor& td = plan->tensors[k.dst];
+      const size_t total = (size_t)td.mult * plan->chunk * (k.c / 8) * td.h * td.w;
+      const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+      stcd::maxpool3x3s2_s2d_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr,
+                                                            td.mult * plan->chunk, k.c / 8, td.c / 8, td.h, td.w);
+      CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 4) {
+      const SegHeadOp& k = plan->heads[o.idx];
+      const Tensor& t = plan->tensors[k.src];
+      float* m1 = outs[k.out_ext];
+      float* m2 = outs[k.out_ext + 1];
+      float* ch = outs[k.out_ext + 2];
+      if (!m1 || !m2 || !ch) return fail(STCD_ERR_INVALID, "external outputs %d..%d must not be NULL", k.out_ext, k.out_ext + 2);
+      if (n_valid > 0) {
+        const dim3 grid((t.w + stcd::kHeadTW - 1) / stcd::kHeadTW, (t.h + stcd::kHeadTH - 1) / stcd::kHeadTH, n_valid);
+        if (k.c == 8)
+          stcd::segcd_head_kernel<1><<<grid, 256, 0, st>>>((const __nv_bfloat16*)t.ptr, k.w_dev, k.bias, plan->chunk, t.h, t.w, m1, m2, ch);
+        else
+          stcd::segcd_head_kernel<2><<<grid, 256, 0, st>>>((const __nv_bfloat16*)t.ptr, k.w_dev, k.bias, plan->chunk, t.h, t.w, m1, m2, ch);
+        CUDA_TRY(cudaGetLastError());
+      }
     } else {
       const PackOp& k = plan->packs[o.idx];
       const Tensor& t = plan->tensors[k.dst];
       const int hw = t.h * t.w;
       const size_t total = (size_t)2 * plan->chunk * hw;
       const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
-      stcd::input_pack_kernel<<<blocks, 256, 0, st>>>(x1, x2, (__nv_bfloat16*)t.ptr, plan->chunk, n_valid, k.cin, t.c / 8, hw);
+      if (k.s2d)
+        stcd::input_pack_s2d_kernel<<<blocks, 256, 0, st>>>(x1, x2, (__nv_bfloat16*)t.ptr, plan->chunk, n_valid, k.cin, t.h, t.w);
+      else
+        stcd::input_pack_kernel<<<blocks, 256, 0, st>>>(x1, x2, (__nv_bfloat16*)t.ptr, plan->chunk, n_valid, k.cin, t.c / 8, hw);
       CUDA_TRY(cudaGetLastError());
     }
     ++op_i;
@@ -281,6 +322,8 @@ void stcd_plan_destroy(stcd_plan* plan) {
     if (e.w_dev) cudaFree(e.w_dev);
     if (e.partial) cudaFree(e.partial);
   }
+  for (SegHeadOp& e : plan->heads)
+    if (e.w_dev) cudaFree(e.w_dev);
   if (plan->workspace) cudaFree(plan->workspace);
   if (plan->arena) cudaFree(plan->arena);
   for (int b = 0; b < 2; ++b) {
@@ -331,6 +374,62 @@ int stcd_plan_add_input_pack(stcd_plan* plan, int dst_tensor, int cin) {
   return (int)plan->ops.size() - 1;
 }
 
+int stcd_plan_add_input_pack_s2d(stcd_plan* plan, int dst_tensor, int cin) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, dst_tensor)) return -fail(STCD_ERR_INVALID, "bad dst tensor %d", dst_tensor);
+  const Tensor& t = plan->tensors[dst_tensor];
+  if (t.mult != 2 || t.c != 16 || cin < 1 || cin > 4)
+    return -fail(STCD_ERR_INVALID, "space-to-depth input pack needs a [2*chunk][2][h][w][8] tensor and cin <= 4 (got mult=%d c=%d cin=%d)",
+                 t.mult, t.c, cin);
+  PackOp k;
+  k.dst = dst_tensor;
+  k.cin = cin;
+  k.s2d = 1;
+  plan->packs.push_back(k);
+  plan->ops.push_back({1, (int)plan->packs.size() - 1});
+  plan->in_c = cin;
+  plan->in_h = 2 * t.h;
+  plan->in_w = 2 * t.w;
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_maxpool_s2d(stcd_plan* plan, int src_tensor, int dst_tensor, int c) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, src_tensor) || !valid_tensor(plan, dst_tensor)) return -fail(STCD_ERR_INVALID, "bad tensor id");
+  const Tensor& ts = plan->tensors[src_tensor];
+  const Tensor& td = plan->tensors[dst_tensor];
+  if (c < 8 || (c % 8) || ts.c != 4 * c || td.c < c || ts.h != td.h || ts.w != td.w || ts.mult != td.mult)
+    return -fail(STCD_ERR_INVALID, "max-pool: src [%d*chunk,%d,%d,%d] must be the space-to-depth form of dst [%d*chunk,%d,%d,%d] (c=%d)",
+                 ts.mult, ts.h, ts.w, ts.c, td.mult, td.h, td.w, td.c, c);
+  plan->pools.push_back({src_tensor, dst_tensor, c});
+  plan->ops.push_back({3, (int)plan->pools.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_seg_head(stcd_plan* plan, const stcd_seghead_desc* d) {
+  if (!plan || !d) return -fail(STCD_ERR_STATE, "plan/desc is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, d->src) || !d->weight || d->out_ext < 0) return -fail(STCD_ERR_INVALID, "seg head: bad src / NULL weight / out_ext");
+  const Tensor& t = plan->tensors[d->src];
+  if ((d->c != 8 && d->c != 16) || t.c != d->c || t.mult != 2)
+    return -fail(STCD_ERR_INVALID, "seg head: src is [%d*chunk,%d,%d,%d]; need both streams (mult 2) and c = %d in {8, 16}", t.mult, t.h,
+                 t.w, t.c, d->c);
+  SegHeadOp k;
+  k.src = d->src;
+  k.c = d->c;
+  k.out_ext = d->out_ext;
+  k.bias = d->bias;
+  k.w.assign(d->weight, d->weight + 9 * d->c);
+  plan->n_ext = std::max(plan->n_ext, d->out_ext + 3);
+  if ((int)plan->ext_elems.size() < plan->n_ext) plan->ext_elems.resize(plan->n_ext, 0);
+  for (int i = 0; i < 3; ++i) plan->ext_elems[d->out_ext + i] = (size_t)t.h * t.w;
+  plan->heads.push_back(std::move(k));
+  plan->ops.push_back({4, (int)plan->heads.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
 int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
   if (!plan || !d) return -fail(STCD_ERR_STATE, "plan/desc is NULL");
   if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
@@ -373,7 +472,14 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
   const bool bf16_out = d->out0 >= 0 || d->out_raw >= 0 || d->out_pool >= 0 || d->out_diff >= 0 || d->res >= 0;
   if (bf16_out && (d->cout % 8)) return -fail(STCD_ERR_INVALID, "bf16 outputs need cout %% 8 == 0 (cout=%d)", d->cout);
   if (d->out0_coff % 8) return -fail(STCD_ERR_INVALID, "out0_coff must be a multiple of 8");
-  if (check_out(d->out0, ho, wo, d->out0_coff, out_imgs, "out0")) return -STCD_ERR_INVALID;
+  if (d->out0_s2d) {
+    if (d->out0 < 0 || d->out0_coff || (ho % 2) || (wo % 2) || !valid_tensor(plan, d->out0))
+      return -fail(STCD_ERR_INVALID, "space-to-depth out0 needs a tensor, even output dims and no channel offset");
+    const Tensor& t = plan->tensors[d->out0];
+    if (t.h != ho / 2 || t.w != wo / 2 || t.c != 4 * d->cout || t.mult != out_imgs)
+      return -fail(STCD_ERR_INVALID, "space-to-depth out0 tensor is [%d*chunk,%d,%d,%d], op writes [%d*chunk,%d,%d,4*%d]", t.mult, t.h, t.w,
+                   t.c, out_imgs, ho / 2, wo / 2, d->cout);
+  } else if (check_out(d->out0, ho, wo, d->out0_coff, out_imgs, "out0")) return -STCD_ERR_INVALID;
   if (check_out(d->out_raw, ho, wo, 0, out_imgs, "out_raw")) return -STCD_ERR_INVALID;
   if (check_out(d->res, ho, wo, 0, out_imgs, "res")) return -STCD_ERR_INVALID;
   if (d->out_pool >= 0) {
@@ -657,6 +763,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
       p.out0 = (__nv_bfloat16*)plan->tensors[d.out0].ptr;
       p.out0_c8 = plan->tensors[d.out0].c / 8;
       p.out0_coff = d.out0_coff;
+      p.out0_s2d = d.out0_s2d;
     }
     if (d.out_raw >= 0) {
       p.out_raw = (__nv_bfloat16*)plan->tensors[d.out_raw].ptr;
@@ -670,6 +777,10 @@ int stcd_plan_finalize(stcd_plan* plan) {
       p.out_diff = (__nv_bfloat16*)plan->tensors[d.out_diff].ptr;
       p.out_diff_c8 = plan->tensors[d.out_diff].c / 8;
     }
+  }
+  for (SegHeadOp& k : plan->heads) {
+    CUDA_TRY(cudaMalloc(&k.w_dev, k.w.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(k.w_dev, k.w.data(), k.w.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   for (EcamOp& e : plan->ecams) {
     const stcd_ecam_desc& d = e.d;

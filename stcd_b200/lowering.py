@@ -102,6 +102,8 @@ class ConvSpec:
     out_diff: Optional[str] = None
     out_ext: int = -1
     macs_per_pair: int = 0       # reference-equivalent MACs (for the roofline), per image pair
+    out0_s2d: bool = False       # out0 is stored space-to-depth: pixel (y, x), channel c ->
+    #                              pixel (y//2, x//2), channel ((y%2)*2 + x%2) * cout + c
 
     def weight_block(self, nt: int, block: int) -> torch.Tensor:
         """fp32 [n_tile, kc] view of one packed weight block (for the emulator)."""
@@ -114,6 +116,38 @@ class InputPackSpec:
     name: str
     dst: str
     cin: int
+    s2d: bool = False            # space-to-depth: dst is [h/2, w/2] with channel (py*2 + px)*cin + c
+
+
+class SegTaps(list):
+    """Per-segment tap lists of one phase: element i is the list of (dy, dx, W[cout, c_real_i]) taps
+    that read segment i (an ordinary list of (dy, dx, W[cout, cin_total]) applies to every segment)."""
+
+
+@dataclass
+class MaxPoolS2DSpec:
+    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (torchvision ResNet stem;
+    segmentation_models_pytorch/encoders/resnet.py:51) reading a space-to-depth tensor
+    [n, h/2, w/2, 4c] and writing the pooled [n, h/2, w/2, c]."""
+    name: str
+    src: str
+    dst: str
+    c: int
+
+
+@dataclass
+class SegHeadSpec:
+    """SegCD's tail (segmentation_models_pytorch/decoders/unet/model.py:321-330) as ONE op over the
+    decoder output d (both temporal streams, c channels): m1 = head(d1), m2 = head(d2),
+    change = min(head(|d1 - d2|), |m1 - m2|) with head = Conv2d(c, 1, 3, padding=1)
+    (base/heads.py:5-10).  External outputs out_ext, out_ext+1, out_ext+2 = m1, m2, change."""
+    name: str
+    src: str
+    c: int
+    weight: np.ndarray           # float32 [9][c]  (tap-major: ky*3 + kx)
+    bias: float
+    out_ext: int = 0
+    macs_per_pair: int = 0
 
 
 @dataclass
@@ -192,6 +226,8 @@ class Segment:
     stream: int = 0
     sy: int = 1
     sx: int = 1
+    c_off: int = 0          # first channel of the segment inside `tensor` (multiple of 8)
+    c_store: int = -1       # stored width of the segment (default: the rest of the tensor)
 
 
 def choose_kc(c_list: Sequence[int]) -> int:
@@ -236,7 +272,10 @@ def _taps_to_gemm(
             srcs.append(s.tensor)
     if len(srcs) > MAX_SRC:
         raise ValueError(f"{name}: {len(srcs)} sources > {MAX_SRC}")
-    stored_c = [prog.tensors[s.tensor].c for s in segs]
+    stored_c = [(prog.tensors[s.tensor].c - s.c_off) if s.c_store < 0 else s.c_store for s in segs]
+    for s in segs:
+        if s.c_off % 8:
+            raise ValueError(f"{name}: segment channel offset {s.c_off} is not a multiple of 8")
     kc = choose_kc(stored_c)
     n_tile, cout_pad = choose_n_tile(cout, pair)
     n_nt = cout_pad // n_tile
@@ -245,28 +284,50 @@ def _taps_to_gemm(
     for s in segs:
         sy[srcs.index(s.tensor)] = s.sy
         sx[srcs.index(s.tensor)] = s.sx
-    # halo extents per source: max over phases of the tap range (stride-1 sources only)
+
+    # per phase, per segment: [(dy, dx, W[cout, c_real])]
+    def per_segment(taps):
+        if isinstance(taps, SegTaps):
+            if len(taps) != len(segs):
+                raise ValueError(f"{name}: {len(taps)} tap lists for {len(segs)} segments")
+            return [list(t) for t in taps]
+        out, ci = [], 0
+        for s in segs:
+            out.append([(dy, dx, w[:, ci: ci + s.c_real]) for (dy, dx, w) in taps])
+            ci += s.c_real
+        for (_, _, w) in taps:
+            if ci != w.shape[1]:
+                raise ValueError(f"{name}: weight has {w.shape[1]} input channels, segments give {ci}")
+        return out
+
+    seg_phase_taps = [(oy, ox, per_segment(taps)) for (oy, ox, taps) in phase_taps]
+    # halo extents per source: max over phases and segments of the tap range (stride-1 sources only)
     ey = [0] * len(srcs)
     ex = [0] * len(srcs)
-    for (_, _, taps) in phase_taps:
-        dys = [t[0] for t in taps]
-        dxs = [t[1] for t in taps]
-        for i in range(len(srcs)):
-            if sy[i] == 1 and sx[i] == 1:
+    for (_, _, staps) in seg_phase_taps:
+        for s, taps in zip(segs, staps):
+            i = srcs.index(s.tensor)
+            if taps and sy[i] == 1 and sx[i] == 1:
+                dys = [t[0] for t in taps]
+                dxs = [t[1] for t in taps]
                 ey[i] = max(ey[i], max(dys) - min(dys))
                 ex[i] = max(ex[i], max(dxs) - min(dxs))
     phases: List[Phase] = []
     chunks: List[Chunk] = []
     tap_list: List[Tuple[int, int]] = []
     blocks: List[torch.Tensor] = []          # each [cout_pad, kc]
-    for (oy, ox, taps) in phase_taps:
+    for (oy, ox, staps) in seg_phase_taps:
         chunk_begin, w_block = len(chunks), len(blocks)
-        dy0 = min(t[0] for t in taps)
-        dx0 = min(t[1] for t in taps)
-        ci = 0
-        for s, sc in zip(segs, stored_c):
+        for s, sc, taps in zip(segs, stored_c, staps):
+            if not taps:
+                continue
             si = srcs.index(s.tensor)
             halo = (sy[si] == 1 and sx[si] == 1)
+            dy0 = min(t[0] for t in taps)
+            dx0 = min(t[1] for t in taps)
+            for w in taps:
+                if w[2].shape[1] != s.c_real:
+                    raise ValueError(f"{name}: tap weight has {w[2].shape[1]} channels, segment has {s.c_real}")
             for c0 in range(0, sc, kc):
                 if c0 >= s.c_real:      # pure padding chunk: contributes nothing
                     continue
@@ -274,23 +335,19 @@ def _taps_to_gemm(
                 def wblock(wtap):
                     blk = torch.zeros(cout_pad, kc, dtype=torch.float32)
                     n_real = min(kc, s.c_real - c0)
-                    blk[:cout, :n_real] = wtap[:, ci + c0: ci + c0 + n_real]
+                    blk[:cout, :n_real] = wtap[:, c0: c0 + n_real]
                     return blk
 
                 if halo:
-                    chunks.append(Chunk(si, c0, dy0, dx0, s.stream, len(tap_list), len(taps)))
+                    chunks.append(Chunk(si, s.c_off + c0, dy0, dx0, s.stream, len(tap_list), len(taps)))
                     for (dy, dx, wtap) in taps:
                         tap_list.append((dy - dy0, dx - dx0))
                         blocks.append(wblock(wtap))
                 else:
                     for (dy, dx, wtap) in taps:
-                        chunks.append(Chunk(si, c0, dy, dx, s.stream, len(tap_list), 1))
+                        chunks.append(Chunk(si, s.c_off + c0, dy, dx, s.stream, len(tap_list), 1))
                         tap_list.append((0, 0))
                         blocks.append(wblock(wtap))
-            ci += s.c_real
-        for (_, _, wtap) in taps:
-            if ci != wtap.shape[1]:
-                raise ValueError(f"{name}: weight has {wtap.shape[1]} input channels, segments give {ci}")
         phases.append(Phase(chunk_begin, len(chunks) - chunk_begin, oy, ox, w_block, len(blocks) - w_block))
         if phases[-1].chunk_count > MAX_CHUNKS or phases[-1].n_blocks > MAX_TAPS:
             raise ValueError(f"{name}: K-program too long ({phases[-1].chunk_count} chunks, {phases[-1].n_blocks} taps)")
@@ -334,6 +391,46 @@ def convT_phase_taps(weight_t: torch.Tensor, stride: int, pad: int) -> List[Tupl
     return out
 
 
+def s2d_segments(tensor: str, c: int, stream: int = 0) -> List[Segment]:
+    """The four parity classes (py, px) of a space-to-depth tensor [n, h/2, w/2, 4c] as segments."""
+    return [Segment(tensor, c, stream=stream, c_off=k * c, c_store=c) for k in range(4)]
+
+
+def s2d_conv_taps(weight: torch.Tensor, pad: int, a: int = 0, b: int = 0) -> SegTaps:
+    """Taps of a conv whose source is stored space-to-depth (see ``s2d_segments``) and whose output
+    pixel (i, j) of the tile grid sits at full-resolution position (2i + a, 2j + b):
+    out(i, j) = sum_k W[ky, kx] * src_full(2i + a + ky - pad, 2j + b + kx - pad).
+    With a = b = 0 this is a stride-2 conv (torchvision BasicBlock conv1 / downsample,
+    models/resnet.py:59-60); with (a, b) in {0,1}^2 the four output phases of a stride-1 conv at the
+    source's full resolution (the skip half of smp's DecoderBlock.conv1, decoders/unet/decoder.py:35-40).
+    Full-res row r = 2i + a + ky - pad belongs to parity class r % 2 at half-res row i + r // 2."""
+    kh, kw = weight.shape[2], weight.shape[3]
+    out = SegTaps([[] for _ in range(4)])
+    for ky in range(kh):
+        ry = a + ky - pad
+        for kx in range(kw):
+            rx = b + kx - pad
+            out[(ry % 2) * 2 + (rx % 2)].append((ry // 2, rx // 2, weight[:, :, ky, kx].to(torch.float32)))
+    return out
+
+
+def up2_conv_taps(weight: torch.Tensor, pad: int, a: int, b: int) -> List[Tuple[int, int, torch.Tensor]]:
+    """Taps of a conv over the NEAREST 2x up-sampling of a low-resolution source
+    (F.interpolate(scale_factor=2, mode="nearest") + Conv2d, decoders/unet/decoder.py:36-40) for output
+    phase (a, b): up(y) = src(y // 2), so taps that land on the same source pixel merge and their
+    weights add (a 3x3 conv becomes 2x2 taps per phase: 4/9 of the MACs, and the up-sampled tensor is
+    never materialised)."""
+    kh, kw = weight.shape[2], weight.shape[3]
+    merged: Dict[Tuple[int, int], torch.Tensor] = {}
+    for ky in range(kh):
+        dy = (a + ky - pad) // 2
+        for kx in range(kw):
+            dx = (b + kx - pad) // 2
+            w = weight[:, :, ky, kx].to(torch.float32)
+            merged[(dy, dx)] = merged[(dy, dx)] + w if (dy, dx) in merged else w.clone()
+    return [(dy, dx, w) for (dy, dx), w in sorted(merged.items())]
+
+
 def add_conv(
     prog: Program,
     name: str,
@@ -360,6 +457,7 @@ def add_conv(
     out_diff: Optional[str] = None,
     out_ext: int = -1,
     macs_per_pair: int = 0,
+    out0_s2d: bool = False,
 ) -> ConvSpec:
     wbits, kc, n_tile, cout_pad, phases, chunks, taps, srcs, sy, sx, ey, ex = _taps_to_gemm(
         prog, name, segs, phase_taps, cout, pair)
@@ -370,7 +468,7 @@ def add_conv(
         scale2=None if scale2 is None else _pad_vec(scale2, cout_pad, 1.0),
         shift2=None if shift2 is None else _pad_vec(shift2, cout_pad, 0.0),
         relu=relu, res=res, out0=out0, out0_coff=out0_coff, out_raw=out_raw, out_pool=out_pool,
-        out_diff=out_diff, out_ext=out_ext, macs_per_pair=macs_per_pair,
+        out_diff=out_diff, out_ext=out_ext, macs_per_pair=macs_per_pair, out0_s2d=out0_s2d,
     )
     prog.ops.append(spec)
     return spec

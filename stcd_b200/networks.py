@@ -14,6 +14,7 @@ import torch
 from torch.nn import init
 
 from .siamunet import SiamUnet_conc, SiamUnet_diff
+from .segcd import SegCD
 from .snunet import SNUNet_ECAM
 
 # registry keys of models/networks.py:144-214 that this library does NOT implement (yet): asking for one
@@ -33,7 +34,7 @@ _REGISTRY = {
 
 
 # class name (= the reference's) -> drop-in wrapper; synth.GAINS / bench.py / the tests key on these names
-CLASSES = {"SiamUnet_diff": SiamUnet_diff, "SiamUnet_conc": SiamUnet_conc, "SNUNet_ECAM": SNUNet_ECAM}
+CLASSES = {"SiamUnet_diff": SiamUnet_diff, "SiamUnet_conc": SiamUnet_conc, "SNUNet_ECAM": SNUNet_ECAM, "SegCD": SegCD}
 
 
 def register(name: str, ctor) -> None:

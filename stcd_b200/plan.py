@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .lowering import ConvSpec, EcamHeadSpec, InputPackSpec, Program
+from .lowering import ConvSpec, EcamHeadSpec, InputPackSpec, MaxPoolS2DSpec, Program, SegHeadSpec
 
 
 def _fptr(a: Optional[np.ndarray]):
@@ -48,7 +48,16 @@ class Plan:
         self.tensor_ids = ids
         for op in prog.ops:
             if isinstance(op, InputPackSpec):
-                _lib.check_id(lib.stcd_plan_add_input_pack(h, ids[op.dst], op.cin), f"input pack {op.name}")
+                add = lib.stcd_plan_add_input_pack_s2d if op.s2d else lib.stcd_plan_add_input_pack
+                _lib.check_id(add(h, ids[op.dst], op.cin), f"input pack {op.name}")
+            elif isinstance(op, MaxPoolS2DSpec):
+                _lib.check_id(lib.stcd_plan_add_maxpool_s2d(h, ids[op.src], ids[op.dst], op.c), f"maxpool {op.name}")
+            elif isinstance(op, SegHeadSpec):
+                d = _lib.SegHeadDesc()
+                d.src, d.c, d.bias, d.out_ext = ids[op.src], op.c, float(op.bias), op.out_ext
+                wkeep = np.ascontiguousarray(op.weight, np.float32)
+                d.weight = _fptr(wkeep)
+                _lib.check_id(lib.stcd_plan_add_seg_head(h, C.byref(d)), f"seg head {op.name}")
             elif isinstance(op, ConvSpec):
                 self._add_conv(op)
             elif isinstance(op, EcamHeadSpec):
@@ -98,6 +107,7 @@ class Plan:
         d.out0, d.out0_coff = tid(op.out0), op.out0_coff
         d.out_raw, d.out_pool, d.out_diff = tid(op.out_raw), tid(op.out_pool), tid(op.out_diff)
         d.out_ext = op.out_ext
+        d.out0_s2d = 1 if op.out0_s2d else 0
         _lib.check_id(self.lib.stcd_plan_add_conv(self._h, C.byref(d)), f"conv {op.name}")
 
     def _add_ecam(self, op: EcamHeadSpec) -> None:

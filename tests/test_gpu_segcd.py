@@ -1,0 +1,126 @@
+"""smp.SegCD(resnet34)(A, B) on the GPU against the oracle, the emulator and the golden fixture generated
+from the unmodified reference (north-star tolerances: outputs within 2e-2 absolute on the bf16 path,
+binary change maps agreeing on >= 99.9 % of decided pixels)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import emulate, nets
+from stcd_b200 import segcd, synth
+from stcd_b200.metric import SegmentationMetric
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 2e-2
+
+
+def _net(name="resnet34"):
+    return synth.prepare_(segcd.SegCD(name).eval(), "SegCD")
+
+
+def _check(ys, refs):
+    assert len(ys) == 3
+    for y, ref in zip(ys, refs):
+        assert y.shape == ref.shape and y.dtype == torch.float32
+        assert (y.cpu() - ref).abs().max().item() < BF16_TOL
+    change, ref = ys[2].cpu(), refs[2]
+    agree = (change > 0) == (ref > 0)
+    assert agree[ref.abs() > BF16_TOL].float().mean().item() >= 0.999
+    assert agree.float().mean().item() >= 0.97
+
+
+@pytest.mark.parametrize("name", ["resnet34", "resnet18"])
+def test_forward_matches_oracle_and_emulator(name):
+    net = _net(name)
+    x1, x2 = synth.image_pairs(3, 64, 96)
+    layers = segcd._LAYERS[name]
+    with torch.no_grad():
+        ref = nets.segcd_forward(net.state_dict(), x1, x2, layers)
+    emu = emulate.run_program(net.lower(64, 96), x1, x2, chunk=2)
+    net = net.cuda()
+    net.chunk_pairs = 2                      # 3 pairs -> one full chunk + a ragged one
+    ys = net(x1.cuda(), x2.cuda())
+    assert isinstance(ys, tuple)
+    _check(ys, ref)
+    for y, e in zip(ys, emu):
+        assert (y.cpu() - e).abs().max().item() < 1.5e-2, "kernel vs emulator (same rounding points)"
+
+
+def test_forward_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "segcd_r34.npz"))
+    assert float(g["gain"]) == synth.GAINS["SegCD"] and int(g["n_out"]) == 3
+    net = _net().cuda()
+    x1, x2 = synth.image_pairs(int(g["batch"]), int(g["h"]), int(g["w"]), seed=int(g["data_seed"]))
+    ys = net(x1.cuda(), x2.cuda())
+    _check(ys, [torch.from_numpy(g[f"out{i}"]) for i in range(3)])
+
+
+def test_layerwise_against_emulator():
+    """Every intermediate tensor of the plan against the emulator: localises a wrong layer."""
+    net = _net()
+    x1, x2 = synth.image_pairs(2, 64, 64)
+    keep = {}
+    emulate.run_program(net.lower(64, 64), x1, x2, chunk=2, keep=keep)
+    net = net.cuda()
+    net.chunk_pairs = 2
+    net(x1.cuda(), x2.cuda())
+    torch.cuda.synchronize()
+    plan = net.plan_for(x1.cuda())
+    worst = {}
+    for name, t in plan.prog.tensors.items():
+        got = plan.read_tensor(name)
+        # same rounding points, different fp32 accumulation order: a few bf16 ulps (2^-8 relative each)
+        worst[name] = ((got - keep[name]).abs() / (1.0 + keep[name].abs())).max().item()
+    bad = {k: v for k, v in worst.items() if v > 3e-2}
+    assert not bad, bad
+
+
+def test_full_size_tile_and_properties():
+    """Config C3's tile size (1024x1024), 2 pairs: the first pair against the CPU oracle, then the
+    size-independent properties (determinism, batch-order equivariance, identical images -> no change)
+    and the evaluator fed by sigmoid(change) > 0.5 (train_stcd.py:477-492)."""
+    net = _net()
+    x1, x2 = synth.image_pairs(2, 1024, 1024)
+    with torch.no_grad():
+        ref = nets.segcd_forward(net.state_dict(), x1[:1], x2[:1])
+    net = net.cuda()
+    net.chunk_pairs = 1
+    a, b = x1.cuda(), x2.cuda()
+    ys = net(a, b)
+    _check([y[:1] for y in ys], ref)
+    ys2 = net(a, b)
+    assert all(torch.equal(u, v) for u, v in zip(ys, ys2)), "forward must be deterministic"
+    perm = torch.tensor([1, 0])
+    yp = net(a[perm], b[perm])
+    assert all(torch.equal(u, v[perm.cuda()]) for u, v in zip(yp, ys))
+    same = net(a, a)
+    assert torch.equal(same[0], same[1]), "shared weights: identical images give identical masks"
+    # |m1 - m2| == 0 and head(0) == bias: change = min(bias, 0)
+    bias = float(net.segmentation_head[0].bias[0])
+    assert torch.allclose(same[2], torch.full_like(same[2], min(bias, 0.0)), atol=1e-6)
+    label = synth.labels(2, 1024, 1024).cuda()
+    m = SegmentationMetric(2, "cuda:0")
+    m.addLogits(ys[2], label, kind="sigmoid", thr=0.5)
+    cm = m.confusion_counts().cpu().numpy()
+    pred = (torch.sigmoid(ys[2].cpu()) > 0.5).long()[:, 0]
+    want = np.bincount((2 * label.cpu() + pred).reshape(-1).numpy(), minlength=4).reshape(2, 2)
+    assert np.array_equal(cm, want) and cm.sum() == 2 * 1024 * 1024
+    plan = net.plan_for(a)
+    outs = plan.forward_host(x1.pin_memory(), x2.pin_memory())
+    assert all(torch.equal(o, y.cpu()) for o, y in zip(outs, ys)), "host-buffer path must equal the device path"
+
+
+def test_reference_calling_conventions():
+    import stcd_b200.smp as smp
+    net = smp.create_model("SegCD", "resnet34", None, classes=1).eval()
+    ref = _net()
+    net.load_state_dict(ref.state_dict())          # reference parameter names
+    x1, x2 = synth.image_pairs(1, 32, 64)
+    m1, m2, change = net.cuda()(x1.cuda(), x2.cuda())      # train_stcd.py:476 unpacks three
+    r = ref.cuda()(x1.cuda(), x2.cuda())
+    assert torch.equal(m1, r[0]) and torch.equal(change, r[2])
+    with pytest.raises(KeyError):
+        smp.create_model("nope")
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 3, 40, 40).cuda(), torch.zeros(1, 3, 40, 40).cuda())

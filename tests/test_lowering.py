@@ -53,6 +53,84 @@ def test_snunet_program_matches_oracle():
     assert max(len(o.srcs) for o in convs) <= L.MAX_SRC
 
 
+def test_segcd_program_matches_oracle():
+    """smp.SegCD(resnet34): space-to-depth stem, parity-class stride-2 convs, phase-decomposed nearest
+    up-sampling + virtual concat, fused head -- all host-side lowering, checked through the emulator."""
+    from stcd_b200 import segcd
+    net = synth.prepare_(segcd.SegCD("resnet34").eval(), "SegCD")
+    x1, x2 = synth.image_pairs(3, 64, 96)
+    with torch.no_grad():
+        y = nets.segcd_forward(net.state_dict(), x1, x2)
+    prog = net.lower(64, 96)
+    ye = emulate.run_program(prog, x1, x2, chunk=2)
+    assert len(ye) == 3
+    for a, b in zip(ye, y):
+        assert a.shape == b.shape and (a - b).abs().max().item() < BF16_TOL
+    change, change_e = y[2], ye[2]
+    agree = (change_e > 0) == (change > 0)          # sigmoid(x) > 0.5 (train_stcd.py:477) up to the fp32 rounding at 0
+    assert agree[change.abs() > BF16_TOL].float().mean().item() >= 0.999
+    assert 0.02 < (change > 0).float().mean().item() < 0.98, "degenerate change map"
+    convs = [o for o in prog.ops if isinstance(o, L.ConvSpec)]
+    # 1 stem + 16 blocks x 2 + 3 downsamples + 5 decoder blocks x 2 = 46 convs; + pack, max-pool, head
+    assert len(convs) == 46 and len(prog.ops) == 49
+    assert all(len(o.phases) == 4 for o in convs if o.name.startswith("decoder") and o.name.endswith("conv1"))
+    big = net.lower(1024, 1024)
+    # SURVEY.md §6 / App. C: 500.397 GFLOP per pair at 1024x1024 (encoder 153.1 + decoder 96.6 + head 0.45 GMAC)
+    assert abs(2 * big.macs_per_pair() / 1e9 - 500.397) < 0.5
+    with pytest.raises(ValueError):
+        net.lower(1000, 1024)
+    with pytest.raises(NotImplementedError):
+        segcd.SegCD("resnet50")
+
+
+def test_s2d_and_up2_tap_algebra():
+    """The tap rewrites behind the SegCD lowering equal the reference ops they replace (fp32, no rounding)."""
+    import torch.nn.functional as F
+    torch.manual_seed(2)
+    x = torch.randn(2, 5, 8, 12)
+    w = torch.randn(7, 5, 3, 3)
+
+    def s2d(t):        # [n, c, h, w] -> [n, 4c, h/2, w/2], channel (py*2+px)*c + ch
+        return torch.cat([t[:, :, py::2, px::2] for py in range(2) for px in range(2)], 1)
+
+    def run_taps(src, taps_per_seg, c, hg, wg):      # src [n, 4c or c, hg, wg] as class segments of c channels
+        out = 0
+        pad = F.pad(src, (2, 2, 2, 2))
+        for k, taps in enumerate(taps_per_seg):
+            for (dy, dx, wt) in taps:
+                out = out + torch.einsum("nchw,oc->nohw", pad[:, k * c: (k + 1) * c, 2 + dy: 2 + dy + hg, 2 + dx: 2 + dx + wg], wt)
+        return out
+
+    # stride-2 3x3 conv == parity-class taps over the space-to-depth tensor
+    want = F.conv2d(x, w, stride=2, padding=1)
+    got = run_taps(s2d(x), L.s2d_conv_taps(w, pad=1), 5, 4, 6)
+    assert (want - got).abs().max().item() < 1e-4
+    # 1x1 stride-2 conv: only class (0, 0)
+    w1 = torch.randn(7, 5, 1, 1)
+    taps = L.s2d_conv_taps(w1, pad=0)
+    assert [len(t) for t in taps] == [1, 0, 0, 0]
+    assert (F.conv2d(x, w1, stride=2) - run_taps(s2d(x), taps, 5, 4, 6)).abs().max().item() < 1e-4
+    # conv over nearest-upsampled low-res + full-res skip == 4 phases of (merged 2x2 taps, parity-class taps)
+    lo = torch.randn(2, 3, 4, 6)
+    wcat = torch.randn(7, 8, 3, 3)
+    want = F.conv2d(torch.cat([F.interpolate(lo, scale_factor=2, mode="nearest"), x], 1), wcat, padding=1)
+    got = torch.zeros_like(want)
+    for a in range(2):
+        for b in range(2):
+            up = L.up2_conv_taps(wcat[:, :3], 1, a, b)
+            assert len(up) == 4
+            got[:, :, a::2, b::2] = run_taps(lo, [up], 3, 4, 6) + run_taps(s2d(x), L.s2d_conv_taps(wcat[:, 3:], 1, a, b), 5, 4, 6)
+    assert (want - got).abs().max().item() < 1e-4
+    # 7x7 stride-2 stem == 4x4 conv over space-to-depth input
+    from stcd_b200.segcd import stem_s2d_taps
+    img = torch.randn(2, 3, 16, 24)
+    ws = torch.randn(6, 3, 7, 7)
+    (_, _, taps), = stem_s2d_taps(ws)
+    assert len(taps) == 16
+    got = run_taps(s2d(img), [taps], 12, 8, 12)
+    assert (F.conv2d(img, ws, stride=2, padding=3) - got).abs().max().item() < 1e-4
+
+
 def test_program_structure_and_macs():
     net = siamunet.SiamUnet_diff(3, 2).eval()
     prog = net.lower(256, 256)

@@ -30,6 +30,8 @@ def _oracle_forward(case, sd, x1, x2):
         return [nets.siamunet_forward(sd, x1, x2, "conc")]
     if cls == "SNUNet_ECAM":
         return [nets.snunet_forward(sd, x1, x2)]
+    if cls == "SegCD":
+        return list(nets.segcd_forward(sd, x1, x2))
     raise KeyError(cls)
 
 
