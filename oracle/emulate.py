@@ -57,7 +57,21 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
                     acc += a @ w.T
                     blk += 1
             assert blk == ph.w_block + ph.n_blocks
-            full[m][:, ph.oy::op.osy, ph.ox::op.osx] = acc
+            if op.fold_cs:
+                full[m] = acc          # columns = (phase, channel): scattered to pixels by the store below
+            else:
+                full[m][:, ph.oy::op.osy, ph.ox::op.osx] = acc
+    if op.fold_cs:
+        # phases folded into N: affine (+ReLU) per column, then column block p -> output pixel phase p
+        for m in range(n_m):
+            v = full[m] * scale + shift
+            if op.relu:
+                v = torch.relu(v)
+            sl = slice(m * chunk, m * chunk + n_img)
+            for p_ in range(op.osy * op.osx):
+                q = _bf16(v[..., p_ * op.fold_cs: p_ * op.fold_cs + op.fold_cout])
+                T[op.out0][sl, p_ // op.osx::op.osy, p_ % op.osx::op.osx, op.out0_coff: op.out0_coff + op.fold_cout] = q
+        return
     vs = []
     for m in range(n_m):
         v = full[m] * scale + shift

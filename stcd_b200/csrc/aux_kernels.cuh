@@ -264,9 +264,11 @@ __device__ __forceinline__ void unpack8_bf16_f(uint4 q, float* v) {
 // -> dst bf16 [2*chunk][2][h][w][8], channel (py*2 + px)*cin + c = x[c][2y + py][2x + px] (4*cin <= 16).
 // One thread per half-resolution pixel: each (c, py) row is read as one float2, so a warp reads 256
 // contiguous bytes per row and writes 2 x 512 contiguous bytes.  HBM-bound: 16*cin B read + 32 B written.
+template <int CIN>
 __global__ void __launch_bounds__(256) input_pack_s2d_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
                                                              __nv_bfloat16* __restrict__ dst, int chunk, int n_valid,
-                                                             int cin, int h, int w) {
+                                                             int h, int w) {
+  constexpr int cin = CIN;
   const int hw = h * w;
   const size_t total = static_cast<size_t>(2) * chunk * hw;
   const size_t plane = static_cast<size_t>(4) * hw;   // full-resolution channel plane
@@ -368,13 +370,13 @@ template <int C8>
 __global__ void __launch_bounds__(256) segcd_head_kernel(const __nv_bfloat16* __restrict__ d, const float* __restrict__ wgt,
                                                          float bias, int chunk, int h, int w, float* __restrict__ m1,
                                                          float* __restrict__ m2, float* __restrict__ change) {
-  constexpr int PW = kHeadTW + 2, PH = kHeadTH + 2;
+  constexpr int PW = kHeadTW + 2, PH = kHeadTH + 2, C = 8 * C8;
   __shared__ uint4 s_d[2][C8][PH][PW];
-  __shared__ float s_w[9 * C8 * 8];
+  __shared__ __align__(16) float s_w[9 * C];
   const int n = blockIdx.z;
   const int x0 = blockIdx.x * kHeadTW, y0 = blockIdx.y * kHeadTH;
   const size_t hw = static_cast<size_t>(h) * w;
-  for (int i = threadIdx.x; i < 9 * C8 * 8; i += blockDim.x) s_w[i] = wgt[i];
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = wgt[i];
   for (int i = threadIdx.x; i < 2 * C8 * PH * PW; i += blockDim.x) {
     const int px = i % PW;
     int r = i / PW;
@@ -388,34 +390,53 @@ __global__ void __launch_bounds__(256) segcd_head_kernel(const __nv_bfloat16* __
     s_d[s][g][py][px] = v;
   }
   __syncthreads();
+  // each thread: 2 vertically adjacent pixels (rows ty0, ty0 + 1).  Per filter column kx the 3 x C weights
+  // sit in registers; each of the 4 input rows is loaded and unpacked once and feeds both output rows.
   const int tx = threadIdx.x & 31, ty0 = (threadIdx.x >> 5) * 2;
+  float a1[2] = {bias, bias}, a2[2] = {bias, bias}, ad[2] = {bias, bias};
+#pragma unroll 1
+  for (int kx = 0; kx < 3; ++kx) {
+    float wk[3][C];
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int ty = ty0 + r;
-    float a1 = bias, a2 = bias, ad = bias;
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const int ky = k / 3, kx = k - ky * 3;
+      for (int j = 0; j < C; j += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(&s_w[(ky * 3 + kx) * C + j]);
+        wk[ky][j] = q.x;
+        wk[ky][j + 1] = q.y;
+        wk[ky][j + 2] = q.z;
+        wk[ky][j + 3] = q.w;
+      }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      float v1[C], v2[C];
 #pragma unroll
       for (int g = 0; g < C8; ++g) {
-        float v1[8], v2[8];
-        unpack8_bf16_f(s_d[0][g][ty + ky][tx + kx], v1);
-        unpack8_bf16_f(s_d[1][g][ty + ky][tx + kx], v2);
-        const float* wk = &s_w[(k * C8 + g) * 8];
+        unpack8_bf16_f(s_d[0][g][ty0 + rr][tx + kx], v1 + 8 * g);
+        unpack8_bf16_f(s_d[1][g][ty0 + rr][tx + kx], v2 + 8 * g);
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          a1 = fmaf(v1[j], wk[j], a1);
-          a2 = fmaf(v2[j], wk[j], a2);
-          ad = fmaf(fabsf(v1[j] - v2[j]), wk[j], ad);
+      for (int r = 0; r < 2; ++r) {
+        const int ky = rr - r;
+        if (ky >= 0 && ky < 3) {
+#pragma unroll
+          for (int j = 0; j < C; ++j) {
+            a1[r] = fmaf(v1[j], wk[ky][j], a1[r]);
+            a2[r] = fmaf(v2[j], wk[ky][j], a2[r]);
+            ad[r] = fmaf(fabsf(v1[j] - v2[j]), wk[ky][j], ad[r]);
+          }
         }
       }
     }
-    const int yy = y0 + ty, xx = x0 + tx;
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int yy = y0 + ty0 + r, xx = x0 + tx;
     if (yy < h && xx < w) {
       const size_t o = static_cast<size_t>(n) * hw + static_cast<size_t>(yy) * w + xx;
-      m1[o] = a1;
-      m2[o] = a2;
-      change[o] = fminf(ad, fabsf(a1 - a2));
+      m1[o] = a1[r];
+      m2[o] = a2[r];
+      change[o] = fminf(ad[r], fabsf(a1[r] - a2[r]));
     }
   }
 }

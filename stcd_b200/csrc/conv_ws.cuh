@@ -629,7 +629,10 @@ struct ConvKernelEntry {
   X(2, E_RAW | E_AFF2 | E_RELU | E_OUT0)            \
   X(1, E_RAW | E_AFF2 | E_RELU | E_OUT0)            \
   X(2, E_RES | E_RELU | E_OUT0 | E_POOL)            \
-  X(1, E_RES | E_RELU | E_OUT0)
+  X(1, E_RES | E_RELU | E_OUT0)                     \
+  /* SegCD: BasicBlock conv2 (+identity, ReLU) and the 1x1 downsample, Siamese pairs */ \
+  X(2, E_RES | E_RELU | E_OUT0)                     \
+  X(2, E_OUT0)
 
 inline const ConvKernelEntry* conv_kernel_table(int* n) {
   static const ConvKernelEntry table[] = {

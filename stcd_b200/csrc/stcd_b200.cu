@@ -266,9 +266,15 @@ int run_chunk(stcd_plan* plan, const float* x1, const float* x2, int n_valid, fl
       const int hw = t.h * t.w;
       const size_t total = (size_t)2 * plan->chunk * hw;
       const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
-      if (k.s2d)
-        stcd::input_pack_s2d_kernel<<<blocks, 256, 0, st>>>(x1, x2, (__nv_bfloat16*)t.ptr, plan->chunk, n_valid, k.cin, t.h, t.w);
-      else
+      if (k.s2d) {
+        __nv_bfloat16* dp = (__nv_bfloat16*)t.ptr;
+        switch (k.cin) {
+          case 1: stcd::input_pack_s2d_kernel<1><<<blocks, 256, 0, st>>>(x1, x2, dp, plan->chunk, n_valid, t.h, t.w); break;
+          case 2: stcd::input_pack_s2d_kernel<2><<<blocks, 256, 0, st>>>(x1, x2, dp, plan->chunk, n_valid, t.h, t.w); break;
+          case 3: stcd::input_pack_s2d_kernel<3><<<blocks, 256, 0, st>>>(x1, x2, dp, plan->chunk, n_valid, t.h, t.w); break;
+          default: stcd::input_pack_s2d_kernel<4><<<blocks, 256, 0, st>>>(x1, x2, dp, plan->chunk, n_valid, t.h, t.w); break;
+        }
+      } else
         stcd::input_pack_kernel<<<blocks, 256, 0, st>>>(x1, x2, (__nv_bfloat16*)t.ptr, plan->chunk, n_valid, k.cin, t.c / 8, hw);
       CUDA_TRY(cudaGetLastError());
     }

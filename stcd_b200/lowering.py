@@ -104,6 +104,8 @@ class ConvSpec:
     macs_per_pair: int = 0       # reference-equivalent MACs (for the roofline), per image pair
     out0_s2d: bool = False       # out0 is stored space-to-depth: pixel (y, x), channel c ->
     #                              pixel (y//2, x//2), channel ((y%2)*2 + x%2) * cout + c
+    fold_cs: int = 0             # > 0: the osy*osx output phases are folded into GEMM N: column p*fold_cs + c is
+    fold_cout: int = 0           # channel c (< fold_cout) of output pixel (i*osy + p//osx, j*osx + p%osx)
 
     def weight_block(self, nt: int, block: int) -> torch.Tensor:
         """fp32 [n_tile, kc] view of one packed weight block (for the emulator)."""
@@ -286,21 +288,7 @@ def _taps_to_gemm(
         sx[srcs.index(s.tensor)] = s.sx
 
     # per phase, per segment: [(dy, dx, W[cout, c_real])]
-    def per_segment(taps):
-        if isinstance(taps, SegTaps):
-            if len(taps) != len(segs):
-                raise ValueError(f"{name}: {len(taps)} tap lists for {len(segs)} segments")
-            return [list(t) for t in taps]
-        out, ci = [], 0
-        for s in segs:
-            out.append([(dy, dx, w[:, ci: ci + s.c_real]) for (dy, dx, w) in taps])
-            ci += s.c_real
-        for (_, _, w) in taps:
-            if ci != w.shape[1]:
-                raise ValueError(f"{name}: weight has {w.shape[1]} input channels, segments give {ci}")
-        return out
-
-    seg_phase_taps = [(oy, ox, per_segment(taps)) for (oy, ox, taps) in phase_taps]
+    seg_phase_taps = [(oy, ox, _split_taps(name, segs, taps)) for (oy, ox, taps) in phase_taps]
     # halo extents per source: max over phases and segments of the tap range (stride-1 sources only)
     ey = [0] * len(srcs)
     ex = [0] * len(srcs)
@@ -431,6 +419,61 @@ def up2_conv_taps(weight: torch.Tensor, pad: int, a: int, b: int) -> List[Tuple[
     return [(dy, dx, w) for (dy, dx), w in sorted(merged.items())]
 
 
+def mma_cycles(n: int) -> int:
+    """Measured cost of one SS-mode tcgen05.mma M=128 K=16 on B200 (tools/ubench/mma_rate.cu): for N <= 64 the
+    4 KB A-operand read from shared memory, not the math, sets the pace."""
+    return 45 if n <= 64 else (64 if n <= 128 else 128)
+
+
+def _split_taps(name: str, segs: Sequence[Segment], taps) -> List[list]:
+    """One phase's taps as per-segment lists [(dy, dx, W[cout, c_real])]."""
+    if isinstance(taps, SegTaps):
+        if len(taps) != len(segs):
+            raise ValueError(f"{name}: {len(taps)} tap lists for {len(segs)} segments")
+        return [list(t) for t in taps]
+    out, ci = [], 0
+    for s in segs:
+        out.append([(dy, dx, w[:, ci: ci + s.c_real]) for (dy, dx, w) in taps])
+        ci += s.c_real
+    for (_, _, w) in taps:
+        if ci != w.shape[1]:
+            raise ValueError(f"{name}: weight has {w.shape[1]} input channels, segments give {ci}")
+    return out
+
+
+def fold_phases(name: str, segs: Sequence[Segment], phase_taps, cout: int, osy: int, osx: int, pair: bool):
+    """Fold the osy*osx output phases of an up-sampling op into the GEMM N dimension.
+
+    Phase p = oy*osx + ox owns columns [p*cs, p*cs + cout) (cs = cout rounded up to 16).  Every distinct
+    (segment, input offset) becomes ONE tap whose weight block holds each phase's weights for that offset (zeros
+    for phases that do not read it): the A operand is fetched and multiplied once for all phases instead of
+    once per phase, and N grows from cout to P*cs -- which is what small-cout layers need, since an SS-mode
+    MMA costs the same 45 cycles for any N <= 64.  Returns (single-phase taps, cs, cost_folded, cost_unfolded)
+    in modelled MMA cycles per tile, so the caller can keep the per-phase form when folding does not pay
+    (wide layers, where the zero blocks cost more than the shared operand saves)."""
+    P = osy * osx
+    cs = (cout + 15) // 16 * 16
+    per_phase = [(oy * osx + ox, _split_taps(name, segs, taps)) for (oy, ox, taps) in phase_taps]
+    if sorted(p for p, _ in per_phase) != list(range(P)):
+        raise ValueError(f"{name}: folding needs exactly one tap list per output phase")
+    folded = SegTaps([[] for _ in segs])
+    k16 = [(s.c_real + 15) // 16 for s in segs]
+    cost_unf = 0
+    for si, s in enumerate(segs):
+        merged: Dict[Tuple[int, int], torch.Tensor] = {}
+        for p, staps in per_phase:
+            for (dy, dx, w) in staps[si]:
+                blk = merged.setdefault((dy, dx), torch.zeros(P * cs, s.c_real, dtype=torch.float32))
+                blk[p * cs: p * cs + cout] += w
+            cost_unf += len(staps[si]) * k16[si]
+        folded[si] = [(dy, dx, w) for (dy, dx), w in sorted(merged.items())]
+    n_unf, pad_unf = choose_n_tile(cout, pair)
+    n_f, pad_f = choose_n_tile(P * cs, pair)
+    cost_unf *= mma_cycles(n_unf) * (pad_unf // n_unf)
+    cost_f = sum(len(t) * k for t, k in zip(folded, k16)) * mma_cycles(n_f) * (pad_f // n_f)
+    return [(0, 0, folded)], cs, cost_f, cost_unf
+
+
 def add_conv(
     prog: Program,
     name: str,
@@ -458,7 +501,24 @@ def add_conv(
     out_ext: int = -1,
     macs_per_pair: int = 0,
     out0_s2d: bool = False,
+    fold: Optional[bool] = None,
 ) -> ConvSpec:
+    fold_cs = fold_cout = 0
+    plain_out = (res is None and out_raw is None and out_pool is None and out_diff is None and out_ext < 0
+                 and scale2 is None and not out0_s2d and out0 is not None)
+    if fold is not False and osy * osx > 1 and len(phase_taps) == osy * osx and plain_out:
+        f_taps, cs, cost_f, cost_unf = fold_phases(name, segs, phase_taps, cout, osy, osx, pair)
+        if fold or cost_f < cost_unf:
+            P = osy * osx
+            fold_cs, fold_cout = cs, cout
+            sc = np.ones(P * cs, np.float32)
+            sh = np.zeros(P * cs, np.float32)
+            for p_ in range(P):
+                sc[p_ * cs: p_ * cs + cout] = scale[:cout]
+                sh[p_ * cs: p_ * cs + cout] = shift[:cout]
+            phase_taps, cout, scale, shift = f_taps, P * cs, sc, sh
+    elif fold:
+        raise ValueError(f"{name}: phase folding needs an up-sampling op whose only output is out0")
     wbits, kc, n_tile, cout_pad, phases, chunks, taps, srcs, sy, sx, ey, ex = _taps_to_gemm(
         prog, name, segs, phase_taps, cout, pair)
     spec = ConvSpec(
@@ -469,6 +529,7 @@ def add_conv(
         shift2=None if shift2 is None else _pad_vec(shift2, cout_pad, 0.0),
         relu=relu, res=res, out0=out0, out0_coff=out0_coff, out_raw=out_raw, out_pool=out_pool,
         out_diff=out_diff, out_ext=out_ext, macs_per_pair=macs_per_pair, out0_s2d=out0_s2d,
+        fold_cs=fold_cs, fold_cout=fold_cout,
     )
     prog.ops.append(spec)
     return spec

@@ -37,10 +37,25 @@ def model(prog, B, clk=1.9e9, sms=148, hbm=6549e9):
     return rows, tot_m, tot_h
 
 if __name__ == "__main__":
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-    net = synth.randomize_(siamunet.SiamUnet_diff(3, 2).eval(), gain=synth.GAINS["SiamUnet_diff"])
-    rows, tm, th = model(net.lower(256, 256), B)
+    # usage: floor_model.py [net] [B] [H] [bench log with per_op_ms]
+    import json
+    from stcd_b200.networks import CLASSES
+    name = sys.argv[1] if len(sys.argv) > 1 else "SiamUnet_diff"
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    H = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+    net = CLASSES[name]("resnet34") if name == "SegCD" else CLASSES[name](3, 2)
+    prog = net.eval().lower(H, H)
+    meas = {}
+    if len(sys.argv) > 4:
+        line = [l for l in open(sys.argv[4]) if l.startswith("{")][-1]
+        meas = {n: ms for n, ms, *_ in json.loads(line)["per_op_ms"]}
+    rows, tm, th = model(prog, B)
+    print(f"{'op':34s} {'N':>4s} {'kc':>3s} {'tiles':>7s} {'mma us':>8s} {'hbm us':>8s} {'GFLOP':>8s} {'meas us':>8s} {'TF/s':>7s} {'x floor':>7s}")
+    tot = 0
     for r in rows:
-        print(f"{r[0]:9s} N={r[1]:3d} kc={r[2]:2d} tiles={r[3]:6d} mma={r[4]:7.1f}us hbm={r[5]:7.1f}us  gflop={r[6]:.2f}")
-    s = sum(max(r[4], r[5]) for r in rows)
-    print(f"sum mma {tm*1e6:.0f}us  sum hbm {th*1e6:.0f}us  sum max {s:.0f}us -> {B/s*1e6:.0f} pairs/s")
+        ms = meas.get(r[0])
+        fl = max(r[4], r[5])
+        extra = f" {ms * 1e3:8.1f} {r[6] / ms:7.1f} {ms * 1e3 / fl:7.2f}" if ms else ""
+        tot += ms or 0
+        print(f"{r[0]:34s} {r[1]:4d} {r[2]:3d} {r[3]:7d} {r[4]:8.1f} {r[5]:8.1f} {r[6]:8.1f}{extra}")
+    print(f"sum of floors: mma {tm * 1e6:.0f} us, hbm {th * 1e6:.0f} us, max-per-op {sum(max(r[4], r[5]) for r in rows):.0f} us; measured convs {tot * 1e3:.0f} us")

@@ -1,16 +1,23 @@
-"""One SiamUnet_diff forward (chunk pairs = argv[1], default 8) — the command ncu wraps."""
+"""One forward of a harness net — the command ncu wraps.
+usage: run_once.py [net=SiamUnet_diff] [pairs=8] [H=256] [chunk=pairs] [reps=1]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from stcd_b200 import siamunet, synth
+from stcd_b200 import synth
+from stcd_b200.networks import CLASSES
 
-chunk = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-net = synth.randomize_(siamunet.SiamUnet_diff(3, 2).eval(), gain=synth.GAINS["SiamUnet_diff"]).cuda()
+name = sys.argv[1] if len(sys.argv) > 1 else "SiamUnet_diff"
+pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+H = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+chunk = int(sys.argv[4]) if len(sys.argv) > 4 else pairs
+reps = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+net = CLASSES[name]("resnet34") if name == "SegCD" else CLASSES[name](3, 2)
+net = synth.prepare_(net.eval(), name).cuda()
 net.chunk_pairs = chunk
-x1, x2 = synth.image_pairs(chunk, 256, 256)
+x1, x2 = synth.image_pairs(pairs, H, H)
 x1, x2 = x1.cuda(), x2.cuda()
 for _ in range(reps):
     y = net(x1, x2)
 torch.cuda.synchronize()
+y = y[-1] if isinstance(y, (tuple, list)) else y
 print("ok", float(y.abs().mean()))
