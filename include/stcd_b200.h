@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 4
+#define STCD_ABI_VERSION 5
 
 enum stcd_status {
   STCD_OK = 0,
@@ -144,6 +144,13 @@ typedef struct stcd_conv_desc {
    * decoder's skip path (decoders/unet/decoder.py:36-40) are stored this way so that every consumer is
    * a stride-1 halo load over one parity class. */
   int32_t out0_s2d;
+  /* Phase folding for up-sampling ops (ConvTranspose2d stride 2: SNUNet.py:38, SiamUnet_diff.py:52; nearest x2 +
+   * conv: decoders/unet/decoder.py:36-40): fold_cs > 0 folds the osy*osx output phases into GEMM N.  The op then
+   * has ONE phase entry, cout = osy*osx*fold_cs columns, and column p*fold_cs + c (c < fold_cout) is channel c of
+   * output pixel (i*osy + p/osx, j*osx + p%osx): the A operand is fetched once for all phases and N grows from
+   * cout to 4*cout, which is what Cout <= 32 layers need (an SS-mode MMA costs the same for any N <= 64).
+   * Only the affine + ReLU + out0 epilogue is available in this mode.  fold_cs % 16 == 0. */
+  int32_t fold_cs, fold_cout;
 } stcd_conv_desc;
 
 /* returns op index >= 0, or <0 */

@@ -105,6 +105,7 @@ class ConvDesc(C.Structure):
         ("out_diff", C.c_int32),
         ("out_ext", C.c_int32),
         ("out0_s2d", C.c_int32),
+        ("fold_cs", C.c_int32), ("fold_cout", C.c_int32),
     ]
 
 
@@ -124,7 +125,7 @@ class EcamDesc(C.Structure):
     ]
 
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [

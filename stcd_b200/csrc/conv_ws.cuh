@@ -104,6 +104,7 @@ struct ConvParams {
   __nv_bfloat16* out0;
   int32_t out0_c8, out0_coff;
   int32_t out0_s2d;  // 1: out0 is stored space-to-depth ([ho/2][wo/2] pixels, 4*cout channels)
+  int32_t fold_cs, fold_cout;  // > 0: output phases folded into N (column p*fold_cs + c -> phase p, channel c)
   __nv_bfloat16* out_raw;
   int32_t out_raw_c8;
   __nv_bfloat16* out_pool;
@@ -556,9 +557,21 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
           if (has_out0 || has_pool) {
             const uint4 lo = pack8_bf16(v[m]), hi = pack8_bf16(v[m] + 8);
             if (has_out0 && valid) {
-              __nv_bfloat16* o = q_out0 + (m_img * p.out0_c8 + (c0 >> 3)) * hw0 * 8;
-              *reinterpret_cast<uint4*>(o) = lo;
-              if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw0) * 8) = hi;
+              if (p.fold_cs) {
+                // phases folded into N: this 16-column step belongs to phase fp, channels [chn, chn + 16)
+                const int fp = ch / p.fold_cs, chn = ch - fp * p.fold_cs;
+                if (chn < p.fold_cout) {
+                  const int fy = fp / p.osx;
+                  const uint32_t pixf = static_cast<uint32_t>(gy * p.osy + fy) * p.wo + (gx * p.osx + fp - fy * p.osx);
+                  __nv_bfloat16* o = p.out0 + (((static_cast<size_t>(img) + m_img) * p.out0_c8 + ((p.out0_coff + chn) >> 3)) * hw + pixf) * 8;
+                  *reinterpret_cast<uint4*>(o) = lo;
+                  if (p.fold_cout - chn > 8) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = hi;
+                }
+              } else {
+                __nv_bfloat16* o = q_out0 + (m_img * p.out0_c8 + (c0 >> 3)) * hw0 * 8;
+                *reinterpret_cast<uint4*>(o) = lo;
+                if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw0) * 8) = hi;
+              }
             }
             if (has_pool) {
               // max over the 2x2 window on the packed bf16 pairs (rounding is monotonic, so

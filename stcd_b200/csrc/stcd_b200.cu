@@ -466,11 +466,20 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
   }
   const int ho = d->hg * d->osy, wo = d->wg * d->osx;
   const int out_imgs = (d->pair ? 2 : d->img_mult);
+  if (d->fold_cs) {
+    const int P = d->osy * d->osx;
+    if (P < 2 || d->n_phase != 1 || d->fold_cs % 16 || d->cout != P * d->fold_cs || d->fold_cout < 8 || d->fold_cout > d->fold_cs ||
+        (d->fold_cout % 8))
+      return -fail(STCD_ERR_INVALID, "phase folding: need one phase entry, cout == osy*osx*fold_cs, fold_cs %% 16 == 0, fold_cout %% 8 == 0 "
+                   "(got osy=%d osx=%d n_phase=%d cout=%d fold_cs=%d fold_cout=%d)", d->osy, d->osx, d->n_phase, d->cout, d->fold_cs, d->fold_cout);
+    if (d->out0 < 0 || d->out0_s2d || d->out_raw >= 0 || d->res >= 0 || d->out_pool >= 0 || d->out_diff >= 0 || d->out_ext >= 0 || d->scale2)
+      return -fail(STCD_ERR_INVALID, "phase folding supports the affine + ReLU + out0 epilogue only");
+  }
   auto check_out = [&](int id, int hh, int ww, int coff, int mult, const char* name) -> int {
     if (id < 0) return 0;
     if (!valid_tensor(plan, id)) return fail(STCD_ERR_INVALID, "bad %s tensor %d", name, id);
     const Tensor& t = plan->tensors[id];
-    if (t.h != hh || t.w != ww || t.c < coff + d->cout || t.mult != mult)
+    if (t.h != hh || t.w != ww || t.c < coff + (d->fold_cs ? d->fold_cout : d->cout) || t.mult != mult)
       return fail(STCD_ERR_INVALID, "%s tensor %d is [%d*chunk,%d,%d,%d], op writes [%d*chunk,%d,%d,%d+%d]", name, id,
                   t.mult, t.h, t.w, t.c, mult, hh, ww, coff, d->cout);
     return 0;
@@ -770,6 +779,8 @@ int stcd_plan_finalize(stcd_plan* plan) {
       p.out0_c8 = plan->tensors[d.out0].c / 8;
       p.out0_coff = d.out0_coff;
       p.out0_s2d = d.out0_s2d;
+      p.fold_cs = d.fold_cs;
+      p.fold_cout = d.fold_cout;
     }
     if (d.out_raw >= 0) {
       p.out_raw = (__nv_bfloat16*)plan->tensors[d.out_raw].ptr;

@@ -108,6 +108,7 @@ class Plan:
         d.out_raw, d.out_pool, d.out_diff = tid(op.out_raw), tid(op.out_pool), tid(op.out_diff)
         d.out_ext = op.out_ext
         d.out0_s2d = 1 if op.out0_s2d else 0
+        d.fold_cs, d.fold_cout = op.fold_cs, op.fold_cout
         _lib.check_id(self.lib.stcd_plan_add_conv(self._h, C.byref(d)), f"conv {op.name}")
 
     def _add_ecam(self, op: EcamHeadSpec) -> None:
