@@ -46,6 +46,7 @@ constexpr int kMaxWStages = 16;
 constexpr int kMaxChunks = 64;   // A-stage loads per phase
 constexpr int kMaxTaps = 320;    // weight blocks per phase
 constexpr int kConvThreads = 224;
+constexpr int kFastMma = 36;     // per-chunk MMA offsets kept in the constant bank (9 taps x 4 K steps)
 
 // epilogue features; a kernel instance either fixes them at compile time or (E_GENERIC) reads
 // them from ConvParams at run time
@@ -79,7 +80,8 @@ struct TmapPack {
 };
 
 struct ConvParams {
-  int32_t hg, wg, tiles_x, tiles_y, n_img, pair_off, n_tiles;  // n_tiles = tiles_x*tiles_y*n_img
+  int32_t hg, wg, tiles_x, tiles_y, n_img, n_tiles;  // n_img = base images; n_tiles = tiles_x*tiles_y*n_img
+  int32_t m_off[4];  // image offset of sub-tile m (M tiles a CTA accumulates side by side): T2 partner and/or other images
   int32_t n_ntiles;                                            // N tiles (grid.y = n_phase * n_ntiles)
   int32_t src_sy[kMaxSrc], src_sx[kMaxSrc], src_pw[kMaxSrc], src_ph[kMaxSrc];
   int32_t src_merged[kMaxSrc];  // 1: 4-D map with (8 ch, x) merged into one dimension (stride-1 sources)
@@ -113,6 +115,15 @@ struct ConvParams {
   int32_t out_diff_c8;
   float* out_f32;
   int32_t n_valid;
+  // Fast issue path for "regular" phases (every chunk has the same tap list and box geometry, e.g.
+  // any stride-1 3x3 conv): the per-MMA operand offsets live here, in the constant bank, so the
+  // issue loop reads them with uniform loads and never leaves the uniform datapath.
+  int32_t f_regular[kMaxPhase];      // 1: use f_off
+  int32_t f_nmma[kMaxPhase];         // MMAs per chunk and M tile = taps * K steps (<= kFastMma)
+  uint32_t f_a_hi[kMaxPhase];        // A descriptor high word (SBO | version)
+  uint32_t f_a_lo_lbo[kMaxPhase];    // A descriptor LBO field
+  uint32_t f_b_chunk16[kMaxPhase];   // weight bytes per chunk >> 4
+  alignas(16) uint32_t f_off[kMaxPhase][36];  // A offset (16 B units) | B offset inside the chunk's weights << 16
   int32_t dbg;       // diagnostics (STCD_DBG): bit0 skip MMAs
   long long* trace;  // diagnostics (STCD_TRACE=1): 16 clock stamps per CTA, else nullptr
 };
@@ -160,7 +171,9 @@ struct ChunkMma {    // MMA issuer
 
 #define STCD_HAS(flag, runtime_expr) ((EPI & E_GENERIC) ? (runtime_expr) : ((EPI & (flag)) != 0))
 
-template <int MT, uint32_t EPI>
+// MT = M tiles (images) per CTA pass sharing every weight block; MS = 2 when consecutive sub-tiles are
+// (T1, T2) Siamese pairs (the |f1 - f2| epilogue needs both), else 1.
+template <int MT, int MS, uint32_t EPI>
 __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_constant__ TmapPack tm,
                                                                   const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -174,7 +187,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  long long* tr = p.trace ? p.trace + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+  long long* tr = p.trace ? p.trace + ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
   const long long clk0 = clock64();
 #define STCD_STAMP(i) do { if (tr) tr[i] = clock64() - clk0; } while (0)
   if (tr && threadIdx.x == 0) {
@@ -183,8 +196,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     tr[0] = static_cast<long long>(gt);
   }
 
-  const int ph = blockIdx.y / p.n_ntiles;
-  const int nt = blockIdx.y - ph * p.n_ntiles;
+  const int ph = blockIdx.z;   // output phase
+  const int nt = blockIdx.y;   // N tile
   const int n0 = nt * p.n_tile;
   const PhaseInfo phase = p.phase[ph];
   const int my_tiles = (p.n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -299,11 +312,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
           const CUtensorMap* map = &tm.src[L.src_merged & 0xff];
           const int cx = x0 * L.xm + L.xa, cy = y0 * L.ym + L.ya, cn = img + L.n_off;
           if (L.src_merged >> 8) {
-            tma_load_4d(dst, map, &a_full[s], cx, cy, L.c8, cn);
-            if (MT == 2) tma_load_4d(dst + p.a_sub_bytes, map, &a_full[s], cx, cy, L.c8, cn + p.pair_off);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) tma_load_4d(dst + m * p.a_sub_bytes, map, &a_full[s], cx, cy, L.c8, cn + p.m_off[m]);
           } else {
-            tma_load_5d(dst, map, &a_full[s], 0, cx, cy, L.c8, cn);
-            if (MT == 2) tma_load_5d(dst + p.a_sub_bytes, map, &a_full[s], 0, cx, cy, L.c8, cn + p.pair_off);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) tma_load_5d(dst + m * p.a_sub_bytes, map, &a_full[s], 0, cx, cy, L.c8, cn + p.m_off[m]);
           }
         }
         if (++s == p.a_stages) {
@@ -359,6 +372,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     const uint32_t a_stage16 = p.a_stage_bytes >> 4;
     const uint32_t a_sub16 = p.a_sub_bytes >> 4;
     const bool resident = p.w_resident != 0;
+    const uint32_t n_tile_u = static_cast<uint32_t>(p.n_tile);
+    const bool fast = resident && p.f_regular[ph] != 0;
+    const int f_nmma = p.f_nmma[ph];
+    const uint32_t f_a_hi = p.f_a_hi[ph], f_a_lo_lbo = p.f_a_lo_lbo[ph], f_b_chunk16 = p.f_b_chunk16[ph];
+    const uint32_t b_lo_lbo = (n_tile_u & 0x3FFF) << 16;
     int s = 0, ws = 0;
     uint32_t a_par = 0, w_par = 0;
     uint32_t a_base16 = a_ring16;
@@ -376,7 +394,6 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d0 = tmem_base + acc * p.acc_cols;
-      const uint32_t d1 = d0 + p.n_tile;
       uint32_t accum = 0;
       int mma_off = 0;
       for (int c = 0; c < phase.chunk_count; ++c) {
@@ -385,7 +402,46 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
         mbar_wait(&a_full[s], a_par);
         tc_fence_after();
         if (t == 0 && c == 0 && leader) STCD_STAMP(2);
-        if (resident) {
+        if (fast) {
+          // regular phase: operand offsets come from the constant bank through uniform loads
+          const uint32_t a0 = f_a_lo_lbo + a_base16;
+          const uint32_t b0 = b_lo_lbo + w_base16 + static_cast<uint32_t>(c) * f_b_chunk16;
+          int i = 0;
+          for (; i + 4 <= f_nmma; i += 4) {
+            const uint4 e = *reinterpret_cast<const uint4*>(&p.f_off[ph][i]);   // one 16-byte constant load
+            if (leader) {  // ONE divergent region per 4 (x MT) MMAs: the four operand chains overlap
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.x & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (e.x >> 16), b_hi, idesc, accum);
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.y & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (e.y >> 16), b_hi, idesc, 1u);
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.z & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (e.z >> 16), b_hi, idesc, 1u);
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.w & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (e.w >> 16), b_hi, idesc, 1u);
+            }
+            accum = 1;
+          }
+          if (i < f_nmma) {
+            const uint4 e = *reinterpret_cast<const uint4*>(&p.f_off[ph][i]);   // entries past f_nmma are zero padding
+            const uint32_t ev[3] = {e.x, e.y, e.z};
+            if (leader) {
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                if (i + r < f_nmma) {
+#pragma unroll
+                  for (int m = 0; m < MT; ++m)
+                    umma_bf16_lohi(d0 + m * n_tile_u, a0 + (ev[r] & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (ev[r] >> 16), b_hi, idesc,
+                                   (r == 0) ? accum : 1u);
+                }
+              }
+            }
+            accum = 1;
+          }
+        } else if (resident) {
           // Lane i holds the descriptors of MMA i of this chunk; the issue loop only shuffles them
           // out, so its instructions are independent and pipeline instead of forming one chain.
           for (int base = 0; base < n_mma; base += 32) {
@@ -398,8 +454,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
               const uint32_t a_lo = __shfl_sync(0xffffffffu, my.x, j);
               const uint32_t b_lo = __shfl_sync(0xffffffffu, my.y, j);
               if (leader) {
-                umma_bf16_lohi(d0, a_lo, M.a_hi, b_lo, b_hi, idesc, accum);
-                if (MT == 2) umma_bf16_lohi(d1, a_lo + a_sub16, M.a_hi, b_lo, b_hi, idesc, accum);
+#pragma unroll
+                for (int m = 0; m < MT; ++m) umma_bf16_lohi(d0 + m * n_tile_u, a_lo + m * a_sub16, M.a_hi, b_lo, b_hi, idesc, accum);
               }
               accum = 1;
             }
@@ -412,8 +468,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint2 e = s_mma[mma_off + i + ks];
               if (leader) {
-                umma_bf16_lohi(d0, e.x + a_base16, M.a_hi, e.y + b_slot16, b_hi, idesc, accum);
-                if (MT == 2) umma_bf16_lohi(d1, e.x + a_base16 + a_sub16, M.a_hi, e.y + b_slot16, b_hi, idesc, accum);
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                  umma_bf16_lohi(d0 + m * n_tile_u, e.x + a_base16 + m * a_sub16, M.a_hi, e.y + b_slot16, b_hi, idesc, accum);
               }
               accum = 1;
             }
@@ -448,7 +505,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     const bool has_relu = STCD_HAS(E_RELU, p.relu != 0);
     const bool has_out0 = STCD_HAS(E_OUT0, p.out0 != nullptr);
     const bool has_pool = STCD_HAS(E_POOL, p.out_pool != nullptr);
-    const bool has_diff = (MT == 2) && STCD_HAS(E_DIFF, p.out_diff != nullptr);
+    const bool has_diff = (MS == 2) && STCD_HAS(E_DIFF, p.out_diff != nullptr);
     const bool has_f32 = STCD_HAS(E_F32, p.out_f32 != nullptr);
 
     // the residual is prefetched ahead of the accumulator wait, so this role reads global memory
@@ -460,7 +517,6 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     const uint32_t hw = static_cast<uint32_t>(p.ho) * p.wo;  // pixels per image plane
     const uint32_t hw_pool = hw >> 2;
     const int cg8 = n0 >> 3;  // first 8-channel group of this N tile
-    const size_t pair_imgs = static_cast<size_t>(p.pair_off);
     for (int t = 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
       const int tile_x = tile % p.tiles_x;
@@ -472,132 +528,138 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       const int oy = gy * p.osy + phase.oy, ox = gx * p.osx + phase.ox;
       const uint32_t pix = static_cast<uint32_t>(oy) * p.wo + ox;
       const uint32_t pix_pool = static_cast<uint32_t>(oy >> 1) * (p.wo >> 1) + (ox >> 1);
-      // element pointers of (img, first channel group, pixel); image m=1 is pair_imgs images further
+      // element pointers of (image 0, first channel group of this N tile, pixel)
       // out0 may be stored space-to-depth: plane of hw/4 pixels, parity class (oy&1, ox&1) selects the channel block
       const uint32_t hw0 = p.out0_s2d ? (hw >> 2) : hw;
       const uint32_t pix0 = p.out0_s2d ? pix_pool : pix;
       const uint32_t cg0 = p.out0_s2d ? static_cast<uint32_t>(((oy & 1) * 2 + (ox & 1)) * (p.cout >> 3)) : static_cast<uint32_t>(p.out0_coff >> 3);
-      __nv_bfloat16* q_out0 = has_out0 ? p.out0 + ((static_cast<size_t>(img) * p.out0_c8 + cg0 + cg8) * hw0 + pix0) * 8 : nullptr;
-      __nv_bfloat16* q_raw = has_raw ? p.out_raw + ((static_cast<size_t>(img) * p.out_raw_c8 + cg8) * hw + pix) * 8 : nullptr;
-      const __nv_bfloat16* q_res = has_res ? p.res + ((static_cast<size_t>(img) * p.res_c8 + cg8) * hw + pix) * 8 : nullptr;
-      __nv_bfloat16* q_pool = has_pool ? p.out_pool + ((static_cast<size_t>(img) * p.out_pool_c8 + cg8) * hw_pool + pix_pool) * 8 : nullptr;
-      __nv_bfloat16* q_diff = has_diff ? p.out_diff + ((static_cast<size_t>(img) * p.out_diff_c8 + cg8) * hw + pix) * 8 : nullptr;
-      // the residual does not depend on the accumulator: fetch the first 16 channels before waiting
-      // for the MMAs and the next 16 while the current ones are processed (global-load latency
-      // would otherwise be exposed once per 16-column step)
-      uint4 r_cur[MT][2], r_nxt[MT][2];
-      auto load_res = [&](int c0, uint4 (&dst)[MT][2]) {
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          const __nv_bfloat16* r = q_res + (m ? pair_imgs : 0) * p.res_c8 * hw * 8 + static_cast<size_t>(c0 >> 3) * hw * 8;
-          dst[m][0] = __ldg(reinterpret_cast<const uint4*>(r));
-          dst[m][1] = (p.cout - (n0 + c0) > 8) ? __ldg(reinterpret_cast<const uint4*>(r + static_cast<size_t>(hw) * 8))
-                                                : make_uint4(0u, 0u, 0u, 0u);
-        }
-      };
-      if (has_res && valid) load_res(0, r_cur);
+      __nv_bfloat16* q_out0 = has_out0 ? p.out0 + ((static_cast<size_t>(cg0) + cg8) * hw0 + pix0) * 8 : nullptr;
+      __nv_bfloat16* q_raw = has_raw ? p.out_raw + (static_cast<size_t>(cg8) * hw + pix) * 8 : nullptr;
+      const __nv_bfloat16* q_res = has_res ? p.res + (static_cast<size_t>(cg8) * hw + pix) * 8 : nullptr;
+      __nv_bfloat16* q_pool = has_pool ? p.out_pool + (static_cast<size_t>(cg8) * hw_pool + pix_pool) * 8 : nullptr;
+      __nv_bfloat16* q_diff = has_diff ? p.out_diff + (static_cast<size_t>(cg8) * hw + pix) * 8 : nullptr;
       const int acc = t & 1;
-      mbar_wait_relaxed(&acc_full[acc], (t >> 1) & 1);
-      tc_fence_after();
-      if (t == 0 && threadIdx.x == 96) STCD_STAMP(5);
       const uint32_t tlane = tmem_base + acc * p.acc_cols + (static_cast<uint32_t>(wq * 32) << 16);
+#pragma unroll
+      for (int mb = 0; mb < MT; mb += MS) {  // sub-tiles one at a time, Siamese pairs two at a time
+        size_t im[MS];                       // image index of each sub-tile of this group
+#pragma unroll
+        for (int m = 0; m < MS; ++m) im[m] = static_cast<size_t>(img + p.m_off[mb + m]);
+        // the residual does not depend on the accumulator: fetch the first 16 channels before waiting
+        // for the MMAs and the next 16 while the current ones are processed (global-load latency
+        // would otherwise be exposed once per 16-column step)
+        uint4 r_cur[MS][2], r_nxt[MS][2];
+        auto load_res = [&](int c0, uint4 (&dst)[MS][2]) {
+#pragma unroll
+          for (int m = 0; m < MS; ++m) {
+            const __nv_bfloat16* r = q_res + (im[m] * p.res_c8 + (c0 >> 3)) * hw * 8;
+            dst[m][0] = __ldg(reinterpret_cast<const uint4*>(r));
+            dst[m][1] = (p.cout - (n0 + c0) > 8) ? __ldg(reinterpret_cast<const uint4*>(r + static_cast<size_t>(hw) * 8))
+                                                  : make_uint4(0u, 0u, 0u, 0u);
+          }
+        };
+        if (has_res && valid) load_res(0, r_cur);
+        if (mb == 0) {
+          mbar_wait_relaxed(&acc_full[acc], (t >> 1) & 1);
+          tc_fence_after();
+          if (t == 0 && threadIdx.x == 96) STCD_STAMP(5);
+        }
+        const uint32_t tgrp = tlane + mb * p.n_tile;
 
-      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-        const int ch = n0 + c0;
-        if (ch >= p.cout) break;
-        const bool two = (p.cout - ch) > 8;  // both 8-channel groups of this 16-column step are real
-        if (has_res && valid && c0 + 16 < p.n_tile && ch + 16 < p.cout) load_res(c0 + 16, r_nxt);
-        uint32_t raw[MT][16];
-        tmem_ld16(tlane + c0, raw[0]);
-        if (MT == 2) tmem_ld16(tlane + p.n_tile + c0, raw[MT - 1]);
-        tmem_wait_ld();
-        float v[MT][16];
-        const size_t g_off = static_cast<size_t>(c0 >> 3) * hw * 8;            // channel-group offset (elements)
-        const size_t g_off_pool = static_cast<size_t>(c0 >> 3) * hw_pool * 8;
+        for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+          const int ch = n0 + c0;
+          if (ch >= p.cout) break;
+          const bool two = (p.cout - ch) > 8;  // both 8-channel groups of this 16-column step are real
+          if (has_res && valid && c0 + 16 < p.n_tile && ch + 16 < p.cout) load_res(c0 + 16, r_nxt);
+          uint32_t raw[MS][16];
 #pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          const size_t m_img = m ? pair_imgs : 0;
+          for (int m = 0; m < MS; ++m) tmem_ld16(tgrp + m * p.n_tile + c0, raw[m]);
+          tmem_wait_ld();
+          float v[MS][16];
+          const size_t g8 = static_cast<size_t>(c0 >> 3);  // channel-group offset inside the N tile
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 sc = *reinterpret_cast<const float4*>(&s_aff[0][c0 + j]);
-            const float4 sh = *reinterpret_cast<const float4*>(&s_aff[1][c0 + j]);
-            v[m][j + 0] = fmaf(__uint_as_float(raw[m][j + 0]), sc.x, sh.x);
-            v[m][j + 1] = fmaf(__uint_as_float(raw[m][j + 1]), sc.y, sh.y);
-            v[m][j + 2] = fmaf(__uint_as_float(raw[m][j + 2]), sc.z, sh.z);
-            v[m][j + 3] = fmaf(__uint_as_float(raw[m][j + 3]), sc.w, sh.w);
-          }
-          if (has_raw && valid) {
-            __nv_bfloat16* o = q_raw + m_img * p.out_raw_c8 * hw * 8 + g_off;
-            *reinterpret_cast<uint4*>(o) = pack8_bf16(v[m]);
-            if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(v[m] + 8);
-          }
-          if (has_aff2) {
+          for (int m = 0; m < MS; ++m) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[m][j] = fmaf(v[m][j], s_aff[2][c0 + j], s_aff[3][c0 + j]);
-          }
-          if (has_res && valid) {
-            float rv[16];
-            unpack8_bf16(r_cur[m][0], rv);
-            unpack8_bf16(r_cur[m][1], rv + 8);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[m][j] += rv[j];
-          }
-          if (has_relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[m][j] = fmaxf(v[m][j], 0.f);
-          }
-          if (has_f32) {
-            const int n = img + m * p.pair_off;
-            if (valid && n < p.n_valid) {
-              const int nv = min(16, p.cout - ch);
-              float* o = p.out_f32 + (static_cast<size_t>(n) * p.cout + ch) * hw + pix;
-              for (int j = 0; j < nv; ++j) o[static_cast<size_t>(j) * hw] = v[m][j];
+            for (int j = 0; j < 16; j += 4) {
+              const float4 sc = *reinterpret_cast<const float4*>(&s_aff[0][c0 + j]);
+              const float4 sh = *reinterpret_cast<const float4*>(&s_aff[1][c0 + j]);
+              v[m][j + 0] = fmaf(__uint_as_float(raw[m][j + 0]), sc.x, sh.x);
+              v[m][j + 1] = fmaf(__uint_as_float(raw[m][j + 1]), sc.y, sh.y);
+              v[m][j + 2] = fmaf(__uint_as_float(raw[m][j + 2]), sc.z, sh.z);
+              v[m][j + 3] = fmaf(__uint_as_float(raw[m][j + 3]), sc.w, sh.w);
             }
-          }
-          if (has_out0 || has_pool) {
-            const uint4 lo = pack8_bf16(v[m]), hi = pack8_bf16(v[m] + 8);
-            if (has_out0 && valid) {
-              if (p.fold_cs) {
-                // phases folded into N: this 16-column step belongs to phase fp, channels [chn, chn + 16)
-                const int fp = ch / p.fold_cs, chn = ch - fp * p.fold_cs;
-                if (chn < p.fold_cout) {
-                  const int fy = fp / p.osx;
-                  const uint32_t pixf = static_cast<uint32_t>(gy * p.osy + fy) * p.wo + (gx * p.osx + fp - fy * p.osx);
-                  __nv_bfloat16* o = p.out0 + (((static_cast<size_t>(img) + m_img) * p.out0_c8 + ((p.out0_coff + chn) >> 3)) * hw + pixf) * 8;
+            if (has_raw && valid) {
+              __nv_bfloat16* o = q_raw + (im[m] * p.out_raw_c8 + g8) * hw * 8;
+              *reinterpret_cast<uint4*>(o) = pack8_bf16(v[m]);
+              if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(v[m] + 8);
+            }
+            if (has_aff2) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[m][j] = fmaf(v[m][j], s_aff[2][c0 + j], s_aff[3][c0 + j]);
+            }
+            if (has_res && valid) {
+              float rv[16];
+              unpack8_bf16(r_cur[m][0], rv);
+              unpack8_bf16(r_cur[m][1], rv + 8);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[m][j] += rv[j];
+            }
+            if (has_relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[m][j] = fmaxf(v[m][j], 0.f);
+            }
+            if (has_f32) {
+              if (valid && im[m] < static_cast<size_t>(p.n_valid)) {
+                const int nv = min(16, p.cout - ch);
+                float* o = p.out_f32 + (im[m] * p.cout + ch) * hw + pix;
+                for (int j = 0; j < nv; ++j) o[static_cast<size_t>(j) * hw] = v[m][j];
+              }
+            }
+            if (has_out0 || has_pool) {
+              const uint4 lo = pack8_bf16(v[m]), hi = pack8_bf16(v[m] + 8);
+              if (has_out0 && valid) {
+                if (p.fold_cs) {
+                  // phases folded into N: this 16-column step belongs to phase fp, channels [chn, chn + 16)
+                  const int fp = ch / p.fold_cs, chn = ch - fp * p.fold_cs;
+                  if (chn < p.fold_cout) {
+                    const int fy = fp / p.osx;
+                    const uint32_t pixf = static_cast<uint32_t>(gy * p.osy + fy) * p.wo + (gx * p.osx + fp - fy * p.osx);
+                    __nv_bfloat16* o = p.out0 + ((im[m] * p.out0_c8 + ((p.out0_coff + chn) >> 3)) * hw + pixf) * 8;
+                    *reinterpret_cast<uint4*>(o) = lo;
+                    if (p.fold_cout - chn > 8) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = hi;
+                  }
+                } else {
+                  __nv_bfloat16* o = q_out0 + (im[m] * p.out0_c8 + g8) * hw0 * 8;
                   *reinterpret_cast<uint4*>(o) = lo;
-                  if (p.fold_cout - chn > 8) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = hi;
+                  if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw0) * 8) = hi;
                 }
-              } else {
-                __nv_bfloat16* o = q_out0 + (m_img * p.out0_c8 + (c0 >> 3)) * hw0 * 8;
-                *reinterpret_cast<uint4*>(o) = lo;
-                if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw0) * 8) = hi;
               }
-            }
-            if (has_pool) {
-              // max over the 2x2 window on the packed bf16 pairs (rounding is monotonic, so
-              // max(bf16(a), bf16(b)) == bf16(max(a, b))): lanes +1 (x) and +8 (y)
-              const uint4 plo = pool4_bf16x2(lo), phi = pool4_bf16x2(hi);
-              if (valid && ((lane & 9) == 0)) {
-                __nv_bfloat16* o = q_pool + m_img * p.out_pool_c8 * hw_pool * 8 + g_off_pool;
-                *reinterpret_cast<uint4*>(o) = plo;
-                if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw_pool) * 8) = phi;
+              if (has_pool) {
+                // max over the 2x2 window on the packed bf16 pairs (rounding is monotonic, so
+                // max(bf16(a), bf16(b)) == bf16(max(a, b))): lanes +1 (x) and +8 (y)
+                const uint4 plo = pool4_bf16x2(lo), phi = pool4_bf16x2(hi);
+                if (valid && ((lane & 9) == 0)) {
+                  __nv_bfloat16* o = q_pool + (im[m] * p.out_pool_c8 + g8) * hw_pool * 8;
+                  *reinterpret_cast<uint4*>(o) = plo;
+                  if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw_pool) * 8) = phi;
+                }
               }
             }
           }
-        }
-        if (has_diff && valid) {
-          float d[16];
+          if (has_diff && valid) {
+            float d[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) d[j] = fabsf(v[0][j] - v[MT - 1][j]);
-          __nv_bfloat16* o = q_diff + g_off;
-          *reinterpret_cast<uint4*>(o) = pack8_bf16(d);
-          if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(d + 8);
-        }
-        if (has_res) {
+            for (int j = 0; j < 16; ++j) d[j] = fabsf(v[0][j] - v[MS - 1][j]);
+            __nv_bfloat16* o = q_diff + (im[0] * p.out_diff_c8 + g8) * hw * 8;
+            *reinterpret_cast<uint4*>(o) = pack8_bf16(d);
+            if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(d + 8);
+          }
+          if (has_res) {
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            r_cur[m][0] = r_nxt[m][0];
-            r_cur[m][1] = r_nxt[m][1];
+            for (int m = 0; m < MS; ++m) {
+              r_cur[m][0] = r_nxt[m][0];
+              r_cur[m][1] = r_nxt[m][1];
+            }
           }
         }
       }
@@ -625,35 +687,57 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
 using ConvKernelFn = void (*)(const TmapPack, const ConvParams);
 
 struct ConvKernelEntry {
-  int mt;
+  int mt, ms;
   uint32_t epi;
   ConvKernelFn fn;
 };
 
-// Specialised instances for the epilogue combinations the lowered nets use; anything else runs the
-// generic instance (same code, epilogue features read from ConvParams at run time).
-#define STCD_CONV_INSTANCES(X)                      \
-  X(2, E_RELU | E_OUT0)                             \
-  X(2, E_RELU | E_POOL | E_DIFF)                    \
-  X(2, E_RELU | E_OUT0 | E_POOL)                    \
-  X(1, E_OUT0)                                      \
-  X(1, E_RELU | E_OUT0)                             \
-  X(1, E_F32)                                       \
-  X(2, E_RAW | E_AFF2 | E_RELU | E_OUT0)            \
-  X(1, E_RAW | E_AFF2 | E_RELU | E_OUT0)            \
-  X(2, E_RES | E_RELU | E_OUT0 | E_POOL)            \
-  X(1, E_RES | E_RELU | E_OUT0)                     \
+// Specialised instances for the (M tiles, pairing, epilogue) combinations the lowered nets use;
+// anything else runs the generic instance (same code, epilogue features read from ConvParams at
+// run time).  X(MT, MS, EPI)
+#define STCD_CONV_INSTANCES(X)                         \
+  /* FC-Siam encoder (Siamese pairs) */                \
+  X(2, 2, E_RELU | E_OUT0)                             \
+  X(2, 2, E_RELU | E_POOL | E_DIFF)                    \
+  X(2, 2, E_RELU | E_OUT0 | E_POOL)                    \
+  X(4, 2, E_RELU | E_OUT0)                             \
+  X(4, 2, E_RELU | E_POOL | E_DIFF)                    \
+  X(4, 2, E_RELU | E_OUT0 | E_POOL)                    \
+  /* decoders, up-convs, logits */                     \
+  X(1, 1, E_OUT0)                                      \
+  X(2, 1, E_OUT0)                                      \
+  X(1, 1, E_RELU | E_OUT0)                             \
+  X(2, 1, E_RELU | E_OUT0)                             \
+  X(4, 1, E_RELU | E_OUT0)                             \
+  X(1, 1, E_F32)                                       \
+  X(2, 1, E_F32)                                       \
+  /* SNUNet nested blocks */                           \
+  X(2, 2, E_RAW | E_AFF2 | E_RELU | E_OUT0)            \
+  X(4, 2, E_RAW | E_AFF2 | E_RELU | E_OUT0)            \
+  X(1, 1, E_RAW | E_AFF2 | E_RELU | E_OUT0)            \
+  X(2, 1, E_RAW | E_AFF2 | E_RELU | E_OUT0)            \
+  X(4, 1, E_RAW | E_AFF2 | E_RELU | E_OUT0)            \
+  X(2, 2, E_RES | E_RELU | E_OUT0 | E_POOL)            \
+  X(4, 2, E_RES | E_RELU | E_OUT0 | E_POOL)            \
+  X(1, 1, E_RES | E_RELU | E_OUT0)                     \
+  X(2, 1, E_RES | E_RELU | E_OUT0)                     \
+  X(4, 1, E_RES | E_RELU | E_OUT0)                     \
   /* SegCD: BasicBlock conv2 (+identity, ReLU) and the 1x1 downsample, Siamese pairs */ \
-  X(2, E_RES | E_RELU | E_OUT0)                     \
-  X(2, E_OUT0)
+  X(2, 2, E_RES | E_RELU | E_OUT0)                     \
+  X(4, 2, E_RES | E_RELU | E_OUT0)                     \
+  X(2, 2, E_OUT0)                                      \
+  X(4, 2, E_OUT0)
 
 inline const ConvKernelEntry* conv_kernel_table(int* n) {
   static const ConvKernelEntry table[] = {
-#define STCD_X(MT_, EPI_) {MT_, (EPI_), conv_ws_kernel<MT_, (EPI_)>},
+#define STCD_X(MT_, MS_, EPI_) {MT_, MS_, (EPI_), conv_ws_kernel<MT_, MS_, (EPI_)>},
       STCD_CONV_INSTANCES(STCD_X)
 #undef STCD_X
-      {1, E_GENERIC, conv_ws_kernel<1, E_GENERIC>},
-      {2, E_GENERIC, conv_ws_kernel<2, E_GENERIC>},
+      {1, 1, E_GENERIC, conv_ws_kernel<1, 1, E_GENERIC>},
+      {2, 1, E_GENERIC, conv_ws_kernel<2, 1, E_GENERIC>},
+      {2, 2, E_GENERIC, conv_ws_kernel<2, 2, E_GENERIC>},
+      {4, 1, E_GENERIC, conv_ws_kernel<4, 1, E_GENERIC>},
+      {4, 2, E_GENERIC, conv_ws_kernel<4, 2, E_GENERIC>},
   };
   *n = static_cast<int>(sizeof(table) / sizeof(table[0]));
   return table;

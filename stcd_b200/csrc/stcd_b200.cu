@@ -454,6 +454,7 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
   const int mt = d->pair ? 2 : 1;
   if (2 * mt * d->n_tile > 512)
     return -fail(STCD_ERR_INVALID, "double-buffered accumulators need %d TMEM columns (> 512)", 2 * mt * d->n_tile);
+  if (d->pair && (plan->chunk < 1)) return -fail(STCD_ERR_INVALID, "pair op on an empty chunk");
   if (d->hg < 1 || d->wg < 1 || d->osy < 1 || d->osx < 1) return -fail(STCD_ERR_INVALID, "bad grid/stride");
   for (int s = 0; s < d->n_src; ++s) {
     if (!valid_tensor(plan, d->src[s])) return -fail(STCD_ERR_INVALID, "bad src tensor %d", d->src[s]);
@@ -681,9 +682,6 @@ int stcd_plan_finalize(stcd_plan* plan) {
     p.wg = d.wg;
     p.tiles_x = (d.wg + stcd::kTileW - 1) / stcd::kTileW;
     p.tiles_y = (d.hg + stcd::kTileH - 1) / stcd::kTileH;
-    p.n_img = (d.pair ? 1 : d.img_mult) * plan->chunk;
-    p.n_tiles = p.tiles_x * p.tiles_y * p.n_img;
-    p.pair_off = d.pair ? plan->chunk : 0;
     p.n_ntiles = d.cout_pad / d.n_tile;
     p.osy = d.osy;
     p.osx = d.osx;
@@ -705,49 +703,128 @@ int stcd_plan_finalize(stcd_plan* plan) {
     p.kc = d.kc;
     p.n_tile = d.n_tile;
     p.cout = d.cout;
-    p.mt = op.mt;
     p.wblk_bytes = (uint32_t)d.n_tile * d.kc * 2;
     p.a_sub_bytes = (uint32_t)round_up(a_sub, 128);
-    p.a_stage_bytes = op.mt * p.a_sub_bytes;
-    p.acc_cols = op.mt * d.n_tile;
-    uint32_t cols = 32;
-    while (cols < 2 * p.acc_cols) cols <<= 1;
-    p.tmem_cols = cols;
-    // ---- shared-memory plan: weight-stationary when every block of a phase fits beside >= 2 A stages
     p.tab_bytes = (uint32_t)round_up((size_t)max_blocks * (d.kc / 16) * 8, 128);
     const size_t w_all = (size_t)max_blocks * p.wblk_bytes;
     const int groups = d.n_phase * p.n_ntiles;
+    // ---- M tiles per CTA pass (sub-tiles sharing every weight block) and the shared-memory plan.
+    // base: 1 image, or the (T1, T2) pair.  More sub-tiles = other images of the chunk: when the
+    // weights do not fit in shared memory they are re-streamed from L2 for every pass, so the widest
+    // pass that fits TMEM (2 accumulator sets) and shared memory wins; weight-stationary layers
+    // keep the base width (more, smaller tiles balance better over the SMs).
+    const int base_mt = d.pair ? 2 : 1;
+    const int base_imgs = (d.pair ? 1 : d.img_mult) * plan->chunk;
     int occ = 0;
-    for (int o = 2; o >= 1 && !occ; --o) {
-      if (force_occ && o != force_occ) continue;
-      if (cols * o > 512) continue;
-      const size_t budget = (o == 2 ? (kSmemMax - 2048) / 2 : kSmemMax) - 256 - p.tab_bytes;
-      const int min_stages = (o == 2) ? 3 : 2;
-      if (!force_stream && w_all + (size_t)min_stages * p.a_stage_bytes <= budget) {
-        occ = o;
-        p.w_resident = 1;
-        p.w_stages = 0;
-        p.a_stages = (int)std::min<size_t>(stcd::kMaxAStages, (budget - round_up(w_all, 128)) / p.a_stage_bytes);
-      } else if (o == 1) {
-        occ = 1;
-        p.w_resident = 0;
-        const size_t a_min = 3 * (size_t)p.a_stage_bytes;
-        if (a_min + 2 * (size_t)p.wblk_bytes > budget) return fail(STCD_ERR_INVALID, "conv op does not fit shared memory");
-        p.w_stages = (int)std::min<size_t>(std::min<size_t>(stcd::kMaxWStages, (size_t)max_blocks),
-                                           std::max<size_t>(2, (budget - a_min) / p.wblk_bytes));
-        p.a_stages = (int)std::min<size_t>(stcd::kMaxAStages,
-                                           (budget - round_up((size_t)p.w_stages * p.wblk_bytes, 128)) / p.a_stage_bytes);
+    auto try_plan = [&](int mt) -> bool {
+      const int g = mt / base_mt;
+      if (base_imgs % g) return false;
+      if (2 * mt * d.n_tile > 512) return false;
+      if (d.out_ext >= 0 && mt > 2) return false;
+      p.mt = mt;
+      p.a_stage_bytes = mt * p.a_sub_bytes;
+      p.acc_cols = mt * d.n_tile;
+      uint32_t cols = 32;
+      while (cols < 2 * p.acc_cols) cols <<= 1;
+      p.tmem_cols = cols;
+      occ = 0;
+      for (int o = 2; o >= 1 && !occ; --o) {
+        if (force_occ && o != force_occ) continue;
+        if (cols * o > 512) continue;
+        if ((o == 2 ? (kSmemMax - 2048) / 2 : kSmemMax) < 256 + p.tab_bytes + 2 * (size_t)p.a_stage_bytes) continue;
+        const size_t budget = (o == 2 ? (kSmemMax - 2048) / 2 : kSmemMax) - 256 - p.tab_bytes;
+        const int min_stages = (o == 2) ? 3 : 2;
+        if (!force_stream && w_all + (size_t)min_stages * p.a_stage_bytes <= budget) {
+          occ = o;
+          p.w_resident = 1;
+          p.w_stages = 0;
+          p.a_stages = (int)std::min<size_t>(stcd::kMaxAStages, (budget - round_up(w_all, 128)) / p.a_stage_bytes);
+        } else if (o == 1) {
+          const size_t a_min = 2 * (size_t)p.a_stage_bytes;
+          if (a_min + 2 * (size_t)p.wblk_bytes > budget) return false;
+          occ = 1;
+          p.w_resident = 0;
+          p.w_stages = (int)std::min<size_t>(std::min<size_t>(stcd::kMaxWStages, (size_t)max_blocks),
+                                             std::max<size_t>(2, (budget - a_min - (size_t)p.a_stage_bytes) / p.wblk_bytes));
+          p.a_stages = (int)std::min<size_t>(stcd::kMaxAStages,
+                                             (budget - round_up((size_t)p.w_stages * p.wblk_bytes, 128)) / p.a_stage_bytes);
+          if (p.a_stages < 2) return false;
+        }
       }
+      return occ != 0;
+    };
+    {
+      const int force_mt = env_int("STCD_FORCE_MT", 0);
+      bool ok = false;
+      if (force_mt && force_mt % base_mt == 0) ok = try_plan(force_mt);
+      if (!ok) {
+        ok = try_plan(base_mt);
+        if (ok && p.w_resident && !force_mt && d.n_phase == 1 && d.phase[0].chunk_count >= 3) {
+          // deep-K weight-stationary layers: wider passes amortise the per-chunk pipeline costs,
+          // as long as the weights stay resident
+          for (int mt = 4; mt > base_mt; mt >>= 1) {
+            const int passes = p.tiles_x * p.tiles_y * (base_imgs / (mt / base_mt));
+            if (passes < 2 * n_sm / groups) continue;
+            if (try_plan(mt) && p.w_resident) break;
+            ok = try_plan(base_mt);
+          }
+        } else if (ok && !p.w_resident && !force_mt) {
+          // weights streamed per pass: widen while it fits and every SM still gets >= 2 passes
+          for (int mt = 4; mt > base_mt; mt >>= 1) {
+            const int passes = p.tiles_x * p.tiles_y * (base_imgs / (mt / base_mt));
+            if (passes < 2 * n_sm / groups) continue;
+            if (try_plan(mt)) break;
+            ok = try_plan(base_mt);
+          }
+        }
+      }
+      if (!ok) occ = 0;
+    }
+    // ---- regular phases: per-MMA operand offsets into the constant bank (fast issue path)
+    for (int ph = 0; ph < d.n_phase; ++ph) {
+      const stcd_phase& f = d.phase[ph];
+      const stcd_chunk& c0 = op.chunks[f.chunk_begin];
+      const int ksteps = d.kc / 16;
+      bool regular = c0.n_taps * ksteps <= stcd::kFastMma && !env_int("STCD_NO_FAST", 0);
+      const int pw = p.src_pw[c0.src], phh = p.src_ph[c0.src];
+      for (int i = 0; i < f.chunk_count && regular; ++i) {
+        const stcd_chunk& c = op.chunks[f.chunk_begin + i];
+        if (c.n_taps != c0.n_taps || p.src_pw[c.src] != pw || p.src_ph[c.src] != phh) regular = false;
+        for (int k = 0; k < c.n_taps && regular; ++k)
+          if (op.taps[c.tap_begin + k].ty != op.taps[c0.tap_begin + k].ty || op.taps[c.tap_begin + k].tx != op.taps[c0.tap_begin + k].tx)
+            regular = false;
+      }
+      p.f_regular[ph] = regular ? 1 : 0;
+      if (!regular) continue;
+      p.f_nmma[ph] = c0.n_taps * ksteps;
+      p.f_a_hi[ph] = ((uint32_t)pw & 0x3FFF) | (1u << 14);
+      p.f_a_lo_lbo[ph] = ((uint32_t)(pw * phh) & 0x3FFF) << 16;
+      p.f_b_chunk16[ph] = (uint32_t)c0.n_taps * (p.wblk_bytes >> 4);
+      for (int k = 0; k < c0.n_taps; ++k)
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t a = (uint32_t)(op.taps[c0.tap_begin + k].ty * pw + op.taps[c0.tap_begin + k].tx) + (uint32_t)ks * 2u * pw * phh;
+          const uint32_t b = (uint32_t)k * (p.wblk_bytes >> 4) + (uint32_t)ks * 2u * d.n_tile;
+          if (a > 0xFFFFu || b > 0xFFFFu) return fail(STCD_ERR_INVALID, "fast-path offset overflow");
+          p.f_off[ph][k * ksteps + ks] = a | (b << 16);
+        }
+    }
+    op.mt = p.mt;
+    {
+      const int g = op.mt / base_mt;
+      p.n_img = base_imgs / g;
+      p.n_tiles = p.tiles_x * p.tiles_y * p.n_img;
+      for (int m = 0; m < op.mt; ++m)
+        p.m_off[m] = d.pair ? (m & 1) * plan->chunk + (m >> 1) * p.n_img : m * p.n_img;
     }
     if (!occ) return fail(STCD_ERR_INVALID, "conv op: no shared-memory plan (forced occupancy %d)", force_occ);
     const size_t w_region = round_up(p.w_resident ? w_all : (size_t)p.w_stages * p.wblk_bytes, 128);
     op.smem = p.tab_bytes + w_region + (size_t)p.a_stages * p.a_stage_bytes + 128;
     if (op.smem > kSmemMax) return fail(STCD_ERR_INVALID, "conv op needs %zu B of shared memory", op.smem);
     const int ctas = std::max(1, (n_sm * occ) / groups);
-    op.grid = dim3((unsigned)std::min(p.n_tiles, ctas), (unsigned)groups, 1);
+    op.grid = dim3((unsigned)std::min(p.n_tiles, ctas), (unsigned)p.n_ntiles, (unsigned)d.n_phase);
     p.dbg = env_int("STCD_DBG", 0);
     if (env_int("STCD_TRACE", 0)) {
-      const size_t nb = (size_t)op.grid.x * op.grid.y * 16 * sizeof(long long);
+      const size_t nb = (size_t)op.grid.x * op.grid.y * op.grid.z * 16 * sizeof(long long);
       CUDA_TRY(cudaMalloc(&op.trace, nb));
       CUDA_TRY(cudaMemset(op.trace, 0, nb));
       p.trace = op.trace;
@@ -766,9 +843,9 @@ int stcd_plan_finalize(stcd_plan* plan) {
              (d.out_diff >= 0 ? stcd::E_DIFF : 0u) | (d.out_ext >= 0 ? stcd::E_F32 : 0u);
     op.fn = nullptr;
     for (int i = 0; i < n_kernels && !force_generic; ++i)
-      if (kernels[i].mt == op.mt && kernels[i].epi == op.epi) op.fn = kernels[i].fn;
+      if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == op.epi) op.fn = kernels[i].fn;
     for (int i = 0; i < n_kernels && !op.fn; ++i)
-      if (kernels[i].mt == op.mt && kernels[i].epi == stcd::E_GENERIC) op.fn = kernels[i].fn;
+      if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == stcd::E_GENERIC) op.fn = kernels[i].fn;
     if (!op.fn) return fail(STCD_ERR_INVALID, "no conv kernel instance for mt=%d", op.mt);
     if (d.res >= 0) {
       p.res = (const __nv_bfloat16*)plan->tensors[d.res].ptr;
@@ -851,11 +928,11 @@ int64_t stcd_plan_read_trace(stcd_plan* plan, int op_index, int64_t* host, int64
   if (!plan || !plan->finalized || op_index < 0 || op_index >= (int)plan->ops.size() || plan->ops[op_index].kind != 0) return -1;
   const ConvOp& op = plan->convs[plan->ops[op_index].idx];
   if (info) {
-    info[0] = op.grid.x; info[1] = op.grid.y; info[2] = (int)op.smem; info[3] = op.p.a_stages; info[4] = op.p.w_stages;
+    info[0] = op.grid.x; info[1] = op.grid.y * op.grid.z; info[2] = (int)op.smem; info[3] = op.p.a_stages; info[4] = op.p.w_stages;
     info[5] = op.p.w_resident; info[6] = op.p.tmem_cols; info[7] = op.p.n_tiles; info[8] = op.p.a_stage_bytes; info[9] = op.p.wblk_bytes;
   }
   if (!op.trace || !host) return 0;
-  const int64_t n = std::min<int64_t>(max_words, (int64_t)op.grid.x * op.grid.y * 16);
+  const int64_t n = std::min<int64_t>(max_words, (int64_t)op.grid.x * op.grid.y * op.grid.z * 16);
   cudaDeviceSynchronize();
   if (cudaMemcpy(host, op.trace, n * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return n;

@@ -508,7 +508,9 @@ def add_conv(
                  and scale2 is None and not out0_s2d and out0 is not None)
     if fold is not False and osy * osx > 1 and len(phase_taps) == osy * osx and plain_out:
         f_taps, cs, cost_f, cost_unf = fold_phases(name, segs, phase_taps, cout, osy, osx, pair)
-        if fold or cost_f < cost_unf:
+        # measured (SNUNet Up1_x, C=64): a folded N=256 tile is slower than four N=64 phases (one accumulator set,
+        # occupancy 1); fold only while the whole op is one N <= 128 tile
+        if fold or (cost_f < cost_unf and osy * osx * cs <= 128):
             P = osy * osx
             fold_cs, fold_cout = cs, cout
             sc = np.ones(P * cs, np.float32)
