@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 5
+#define STCD_ABI_VERSION 6
 
 enum stcd_status {
   STCD_OK = 0,
@@ -257,6 +257,27 @@ enum stcd_label_kind { STCD_LABEL_I64 = 0, STCD_LABEL_U8 = 1, STCD_LABEL_I32 = 2
 int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const void* label,
                              int label_kind, int64_t n_img, int64_t pix_per_img, int num_class,
                              int64_t* cm_dev, uint8_t* pred_out_or_null, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* ViG Grapher graph ops (ChangeVIG path).  The reference imports them from `gcn_lib`              */
+/* (models/pyramid_vig.py:17; call sites models/ChangeVIG.py:61-63), a module that is not in its    */
+/* tree: semantics follow upstream vig_pytorch/gcn_lib.  Layouts are the         */
+/* reference's: node features fp32 [B][C][N] (= [B, C, N, 1]), neighbour tables int64.              */
+
+/* Replaces DenseDilatedKnnGraph(k, dilation)(x, y, relative_pos) (gcn_lib/torch_edge.py): L2-normalise the
+ * nodes over channels, dist = |x_i|^2 - 2 x_i.y_j + |y_j|^2 (+ relative_pos[i][j]), take the k*dilation nearest
+ * y-nodes of every x-node in ascending distance (ties: smaller index) and keep every dilation-th.
+ * x [B][C][N]; y [B][C][M] or NULL (y := x, M must equal N); relative_pos [N][M] or NULL; M <= 256, k*dilation <= M.
+ * nn_idx_out: int64 [B][N][k] = edge_index[0] (edge_index[1] is the centre index n).
+ * scratch: device fp32 [B * (N + M)] (the node norms). */
+int stcd_knn_graph(const float* x, const float* y_or_null, const float* relative_pos_or_null, int B, int C, int N,
+                   int M, int k, int dilation, int64_t* nn_idx_out, float* scratch, void* stream);
+
+/* Replaces the aggregation of MRConv2d.forward (gcn_lib/torch_vertex.py): m = max_k (y_j - x_i).
+ * interleave = 0: out fp32 [B][C][N] = m.  interleave = 1: out fp32 [B][2C][N], channel 2c = x_c, 2c + 1 = m_c
+ * (the channel-interleaved tensor MRConv2d feeds to its grouped 1x1 conv). */
+int stcd_max_relative(const float* x, const float* y_or_null, const int64_t* nn_idx, int B, int C, int N, int M,
+                      int k, int interleave, float* out, void* stream);
 
 #ifdef __cplusplus
 }

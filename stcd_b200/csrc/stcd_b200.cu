@@ -19,6 +19,7 @@
 #include "../../include/stcd_b200.h"
 #include "aux_kernels.cuh"
 #include "conv_ws.cuh"
+#include "graph_kernels.cuh"
 
 namespace {
 
@@ -1100,6 +1101,49 @@ int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const v
       default: STCD_DISPATCH_L(STCD_CMK, STCD_PRED_I64); break;
     }
   }
+  CUDA_TRY(cudaGetLastError());
+  return STCD_OK;
+}
+
+int stcd_knn_graph(const float* x, const float* y, const float* relpos, int B, int C, int N, int M, int k, int dilation,
+                   int64_t* nn_idx, float* scratch, void* stream) {
+  if (!x || !nn_idx || !scratch) return fail(STCD_ERR_INVALID, "NULL pointer");
+  if (B < 0 || C < 1 || N < 1 || M < 1 || k < 1 || dilation < 1) return fail(STCD_ERR_INVALID, "bad sizes B=%d C=%d N=%d M=%d k=%d d=%d", B, C, N, M, k, dilation);
+  if (!y && M != N) return fail(STCD_ERR_INVALID, "y is NULL (y := x) but M=%d != N=%d", M, N);
+  if (M > stcd::kKnnM) return fail(STCD_ERR_INVALID, "M=%d > %d keys (ViG stages have at most 256 after the reduce-ratio pooling)", M, stcd::kKnnM);
+  if (k * dilation > M) return fail(STCD_ERR_INVALID, "k*dilation=%d > M=%d", k * dilation, M);
+  if (B == 0) return STCD_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(STCD_ERR_NO_DEVICE, "no CUDA device visible: libstcd_b200 has no CPU fallback");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* xden = scratch;
+  float* yden = y ? scratch + (size_t)B * N : scratch;
+  stcd::node_norm_kernel<<<(unsigned)std::min<size_t>(((size_t)B * N + 255) / 256, 148 * 8), 256, 0, st>>>(x, xden, B, C, N);
+  if (y) stcd::node_norm_kernel<<<(unsigned)std::min<size_t>(((size_t)B * M + 255) / 256, 148 * 8), 256, 0, st>>>(y, yden, B, C, M);
+  stcd::knn_graph_kernel<<<dim3((N + stcd::kKnnQ - 1) / stcd::kKnnQ, B), 256, 0, st>>>(x, xden, y ? y : x, yden, relpos, C, N, M, k, dilation,
+                                                                                   reinterpret_cast<long long*>(nn_idx));
+  CUDA_TRY(cudaGetLastError());
+  return STCD_OK;
+}
+
+int stcd_max_relative(const float* x, const float* y, const int64_t* nn_idx, int B, int C, int N, int M, int k, int interleave,
+                      float* out, void* stream) {
+  if (!x || !nn_idx || !out) return fail(STCD_ERR_INVALID, "NULL pointer");
+  if (B < 0 || C < 1 || N < 1 || M < 1 || k < 1) return fail(STCD_ERR_INVALID, "bad sizes");
+  if (!y && M != N) return fail(STCD_ERR_INVALID, "y is NULL (y := x) but M=%d != N=%d", M, N);
+  if (B == 0) return STCD_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(STCD_ERR_NO_DEVICE, "no CUDA device visible: libstcd_b200 has no CPU fallback");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t total = (size_t)B * C * N;
+  stcd::max_relative_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(
+      x, y ? y : x, reinterpret_cast<const long long*>(nn_idx), B, C, N, M, k, interleave, out);
   CUDA_TRY(cudaGetLastError());
   return STCD_OK;
 }
