@@ -46,6 +46,10 @@ WORKLOADS = {
     "segcd_r34_1024_b16": dict(net="SegCD", n_class=1, h=1024, w=1024, batch=16, kind="sigmoid", chunk=8, input_sets=2,
                                desc="C3: smp SegCD (Unet, ResNet-34 Siamese encoder) 1024x1024 RGB pair tiles, batch 16 per GPU, "
                                     "bf16, + confusion-matrix F1/IoU on sigmoid(change) > 0.5"),
+    "segcd_r50_1024_b16": dict(net="SegCD", encoder="resnet50", n_class=1, h=1024, w=1024, batch=16, kind="sigmoid", chunk=8,
+                               input_sets=2,
+                               desc="smp SegCD with the ResNet-50 encoder train_stcd.py:638 selects, 1024x1024 RGB pair tiles, "
+                                    "batch 16 per GPU, bf16, + confusion matrix on sigmoid(change) > 0.5"),
     "segcd_r34_256_b64": dict(net="SegCD", n_class=1, h=256, w=256, batch=64, kind="sigmoid", chunk=16,
                               desc="smp SegCD (Unet, ResNet-34 Siamese encoder) 256x256 RGB pairs, batch 64 per GPU, bf16"),
 }
@@ -56,7 +60,7 @@ def build_net(wl):
     from stcd_b200 import synth
     from stcd_b200.networks import CLASSES
     if wl["net"] == "SegCD":
-        return synth.prepare_(CLASSES["SegCD"]("resnet34", classes=wl["n_class"]).eval(), "SegCD")
+        return synth.prepare_(CLASSES["SegCD"](wl.get("encoder", "resnet34"), classes=wl["n_class"]).eval(), "SegCD")
     return synth.prepare_(CLASSES[wl["net"]](3, wl["n_class"]).eval(), wl["net"])
 
 

@@ -25,6 +25,8 @@ CASES = {
     "snunet": ("models.SNUNet", "SNUNet_ECAM", (3, 2), 2, 32, 48),
     # smp.SegCD("resnet34", encoder_weights=None, classes=1): what train_stcd.py:637 instantiates (ResNet-34 row of C3)
     "segcd_r34": ("segmentation_models_pytorch", "SegCD", ("resnet34", 5, None), 2, 64, 96),
+    # smp.SegCD("resnet50"): the encoder train_stcd.py:638 selects (Bottleneck blocks)
+    "segcd_r50": ("segmentation_models_pytorch", "SegCD", ("resnet50", 5, None), 1, 64, 64),
 }
 
 

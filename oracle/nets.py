@@ -120,6 +120,16 @@ def _basic_block(sd: SD, pre: str, x: torch.Tensor, stride: int) -> torch.Tensor
     return F.relu(out + x)
 
 
+def _bottleneck(sd: SD, pre: str, x: torch.Tensor, stride: int) -> torch.Tensor:
+    """torchvision Bottleneck.forward (== models/resnet.py:104-124): the stride sits on the 3x3 conv2."""
+    out = F.relu(_bn(sd, f"{pre}.bn1", F.conv2d(x, sd[f"{pre}.conv1.weight"], None)))
+    out = F.relu(_bn(sd, f"{pre}.bn2", F.conv2d(out, sd[f"{pre}.conv2.weight"], None, stride=stride, padding=1)))
+    out = _bn(sd, f"{pre}.bn3", F.conv2d(out, sd[f"{pre}.conv3.weight"], None))
+    if f"{pre}.downsample.0.weight" in sd:
+        x = _bn(sd, f"{pre}.downsample.1", F.conv2d(x, sd[f"{pre}.downsample.0.weight"], None, stride=stride))
+    return F.relu(out + x)
+
+
 def _resnet_features(sd: SD, x: torch.Tensor, layers) -> List[torch.Tensor]:
     """ResNetEncoder.forward, segmentation_models_pytorch/encoders/resnet.py:47-65."""
     feats = [x]
@@ -128,7 +138,9 @@ def _resnet_features(sd: SD, x: torch.Tensor, layers) -> List[torch.Tensor]:
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
     for li, n in enumerate(layers):
         for b in range(n):
-            x = _basic_block(sd, f"encoder.layer{li + 1}.{b}", x, 2 if (b == 0 and li > 0) else 1)
+            pre = f"encoder.layer{li + 1}.{b}"
+            block = _bottleneck if f"{pre}.conv3.weight" in sd else _basic_block
+            x = block(sd, pre, x, 2 if (b == 0 and li > 0) else 1)
         feats.append(x)
     return feats
 

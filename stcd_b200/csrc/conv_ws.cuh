@@ -43,7 +43,7 @@ constexpr int kMaxSrc = 6;
 constexpr int kMaxPhase = 4;
 constexpr int kMaxAStages = 8;
 constexpr int kMaxWStages = 16;
-constexpr int kMaxChunks = 64;   // A-stage loads per phase
+constexpr int kMaxChunks = 128;  // A-stage loads per phase
 constexpr int kMaxTaps = 320;    // weight blocks per phase
 constexpr int kConvThreads = 224;
 constexpr int kFastMma = 36;     // per-chunk MMA offsets kept in the constant bank (9 taps x 4 K steps)

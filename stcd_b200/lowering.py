@@ -23,7 +23,7 @@ import torch
 
 TILE_H, TILE_W = 16, 8
 MAX_SRC = 6
-MAX_CHUNKS, MAX_TAPS = 64, 320
+MAX_CHUNKS, MAX_TAPS = 128, 320
 
 
 def _bf16_bits(x: torch.Tensor) -> np.ndarray:

@@ -4,7 +4,8 @@ Drop-in for ``segmentation_models_pytorch.SegCD`` (decoders/unet/model.py:267-33
 scripts instantiate (train_stcd.py:637-638): same constructor keywords, same parameter names
 (``encoder.layer1.0.conv1.weight`` ... ``decoder.blocks.0.conv1.0.weight`` ...
 ``segmentation_head.0.weight``: a reference ``state_dict`` loads), same return value
-``(mask_t1, mask_t2, change)``.  Eval-mode only; BasicBlock encoders (resnet18 / resnet34).
+``(mask_t1, mask_t2, change)``.  Eval-mode only; encoders resnet18 / resnet34 (BasicBlock) and resnet50
+(Bottleneck: the encoder train_stcd.py:638 actually selects).
 
 Lowering (both temporal images ride through every launch as Siamese pair tiles sharing the weights):
 
@@ -32,7 +33,8 @@ import torch.nn as nn
 from . import lowering as L
 from .module import PlannedModule
 
-_LAYERS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3)}
+_LAYERS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3), "resnet50": (3, 4, 6, 3)}
+_BOTTLENECK = {"resnet50"}           # torchvision Bottleneck (expansion 4); the others use BasicBlock
 _WIDTHS = (64, 128, 256, 512)
 
 
@@ -50,6 +52,24 @@ class _BasicBlock(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False), nn.BatchNorm2d(cout))
 
 
+class _Bottleneck(nn.Module):
+    """Parameter holder with torchvision Bottleneck's names (== models/resnet.py:78-124; stride on conv2)."""
+    expansion = 4
+
+    def __init__(self, cin: int, width: int, stride: int):
+        super().__init__()
+        cout = width * self.expansion
+        self.conv1 = nn.Conv2d(cin, width, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.conv2 = nn.Conv2d(width, width, 3, stride=stride, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.conv3 = nn.Conv2d(width, cout, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(cout)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride=stride, bias=False), nn.BatchNorm2d(cout))
+
+
 class _ResNetEncoder(nn.Module):
     """smp/encoders/resnet.py:37-65 (parameters only; fc / avgpool are deleted upstream too)."""
 
@@ -58,13 +78,16 @@ class _ResNetEncoder(nn.Module):
         self.conv1 = nn.Conv2d(in_channels, 64, 7, stride=2, padding=3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         cin = 64
-        for li, (n, cout) in enumerate(zip(_LAYERS[name], _WIDTHS)):
+        bott = name in _BOTTLENECK
+        for li, (n, width) in enumerate(zip(_LAYERS[name], _WIDTHS)):
             blocks = []
             for b in range(n):
-                blocks.append(_BasicBlock(cin, cout, 2 if (b == 0 and li > 0) else 1))
-                cin = cout
+                stride = 2 if (b == 0 and li > 0) else 1
+                blocks.append(_Bottleneck(cin, width, stride) if bott else _BasicBlock(cin, width, stride))
+                cin = width * 4 if bott else width
             setattr(self, f"layer{li + 1}", nn.Sequential(*blocks))
-        self.out_channels = (in_channels, 64, 64, 128, 256, 512)
+        e = 4 if bott else 1
+        self.out_channels = (in_channels, 64, 64 * e, 128 * e, 256 * e, 512 * e)
 
 
 def _conv_bn_relu(cin: int, cout: int) -> nn.Sequential:
@@ -100,7 +123,7 @@ class SegCD(PlannedModule):
                  activation=None, aux_params: Optional[dict] = None):
         super().__init__()
         if encoder_name not in _LAYERS:
-            raise NotImplementedError(f"stcd_b200.SegCD serves the BasicBlock ResNet encoders {sorted(_LAYERS)}; "
+            raise NotImplementedError(f"stcd_b200.SegCD serves the ResNet encoders {sorted(_LAYERS)}; "
                                       f"'{encoder_name}' stays with the reference")
         if encoder_weights is not None:
             raise NotImplementedError("pretrained encoder weights need the network; load a state_dict instead")
@@ -195,39 +218,75 @@ def lower_segcd(sd: Dict[str, torch.Tensor], encoder_name: str, in_channels: int
     cin = 64
 
     # ---------------- residual layers
-    for li, (n_blocks, cout) in enumerate(zip(_LAYERS[encoder_name], _WIDTHS)):
+    bott = encoder_name in _BOTTLENECK
+    for li, (n_blocks, width) in enumerate(zip(_LAYERS[encoder_name], _WIDTHS)):
+        cout = width * 4 if bott else width
         for b in range(n_blocks):
             pre = f"encoder.layer{li + 1}.{b}"
             stride = 2 if (b == 0 and li > 0) else 1
             last_of_layer = (b == n_blocks - 1) and li < 3
-            if stride == 2:
-                hh, ww = hh // 2, ww // 2
-            w1, w2 = sd[f"{pre}.conv1.weight"], sd[f"{pre}.conv2.weight"]
-            t = p.tensor(f"{pre}.t", 2, hh, ww, cout)
-            sc, sh = bn(f"{pre}.bn1", cout)
+            h_in, w_in = hh, ww
             if stride == 2:
                 assert x_s2d
-                segs = L.s2d_segments(x, cin)
-                L.add_conv(p, f"{pre}.conv1", segs, [(0, 0, L.s2d_conv_taps(w1, pad=1))], cout, hh, ww, 1, sc, sh,
-                           pair=True, relu=True, out0=t, macs_per_pair=2 * hh * ww * 9 * cin * cout)
-                ident = p.tensor(f"{pre}.ds", 2, hh, ww, cout)
-                sc, sh = bn(f"{pre}.downsample.1", cout)
-                L.add_conv(p, f"{pre}.downsample", segs, [(0, 0, L.s2d_conv_taps(sd[f"{pre}.downsample.0.weight"], pad=0))],
-                           cout, hh, ww, 1, sc, sh, pair=True, out0=ident, macs_per_pair=2 * hh * ww * cin * cout)
+                hh, ww = hh // 2, ww // 2
             else:
                 assert not x_s2d
-                L.add_conv(p, f"{pre}.conv1", [L.Segment(x, cin)], L.conv_taps(w1, pad=1), cout, hh, ww, 1, sc, sh,
-                           pair=True, relu=True, out0=t, macs_per_pair=2 * hh * ww * 9 * cin * cout)
+            if bott:
+                w1, w2, w3 = sd[f"{pre}.conv1.weight"], sd[f"{pre}.conv2.weight"], sd[f"{pre}.conv3.weight"]
+                sc, sh = bn(f"{pre}.bn1", width)
+                t2 = p.tensor(f"{pre}.t2", 2, hh, ww, width)
+                if stride == 2:
+                    # 1x1 conv at the input resolution on a space-to-depth input: one launch per parity class,
+                    # written to the same class of a space-to-depth output, which the stride-2 3x3 then reads
+                    t1 = p.tensor(f"{pre}.t1_s2d", 2, hh, ww, 4 * width)
+                    for cls, seg in enumerate(L.s2d_segments(x, cin)):
+                        L.add_conv(p, f"{pre}.conv1.{cls}", [seg], L.conv_taps(w1, pad=0), width, hh, ww, 1, sc, sh, pair=True,
+                                   relu=True, out0=t1, out0_coff=cls * width, macs_per_pair=2 * hh * ww * cin * width)
+                    sc, sh = bn(f"{pre}.bn2", width)
+                    L.add_conv(p, f"{pre}.conv2", L.s2d_segments(t1, width), [(0, 0, L.s2d_conv_taps(w2, pad=1))], width, hh, ww, 1,
+                               sc, sh, pair=True, relu=True, out0=t2, macs_per_pair=2 * hh * ww * 9 * width * width)
+                else:
+                    t1 = p.tensor(f"{pre}.t1", 2, hh, ww, width)
+                    L.add_conv(p, f"{pre}.conv1", [L.Segment(x, cin)], L.conv_taps(w1, pad=0), width, hh, ww, 1, sc, sh, pair=True,
+                               relu=True, out0=t1, macs_per_pair=2 * hh * ww * cin * width)
+                    sc, sh = bn(f"{pre}.bn2", width)
+                    L.add_conv(p, f"{pre}.conv2", [L.Segment(t1, width)], L.conv_taps(w2, pad=1), width, hh, ww, 1, sc, sh,
+                               pair=True, relu=True, out0=t2, macs_per_pair=2 * hh * ww * 9 * width * width)
+                last_w, last_in, last_c, last_bn, last_name = w3, t2, width, f"{pre}.bn3", f"{pre}.conv3"
+                last_taps, last_macs = L.conv_taps(w3, pad=0), 2 * hh * ww * width * cout
+            else:
+                w1, w2 = sd[f"{pre}.conv1.weight"], sd[f"{pre}.conv2.weight"]
+                t = p.tensor(f"{pre}.t", 2, hh, ww, cout)
+                sc, sh = bn(f"{pre}.bn1", cout)
+                if stride == 2:
+                    L.add_conv(p, f"{pre}.conv1", L.s2d_segments(x, cin), [(0, 0, L.s2d_conv_taps(w1, pad=1))], cout, hh, ww, 1,
+                               sc, sh, pair=True, relu=True, out0=t, macs_per_pair=2 * hh * ww * 9 * cin * cout)
+                else:
+                    L.add_conv(p, f"{pre}.conv1", [L.Segment(x, cin)], L.conv_taps(w1, pad=1), cout, hh, ww, 1, sc, sh,
+                               pair=True, relu=True, out0=t, macs_per_pair=2 * hh * ww * 9 * cin * cout)
+                last_in, last_c, last_bn, last_name = t, cout, f"{pre}.bn2", f"{pre}.conv2"
+                last_taps, last_macs = L.conv_taps(w2, pad=1), 2 * hh * ww * 9 * cout * cout
+            # identity path: the input, or a 1x1 (stride s) conv + BN of it
+            if f"{pre}.downsample.0.weight" in sd:
+                ident = p.tensor(f"{pre}.ds", 2, hh, ww, cout)
+                sc, sh = bn(f"{pre}.downsample.1", cout)
+                wd = sd[f"{pre}.downsample.0.weight"]
+                if stride == 2:
+                    L.add_conv(p, f"{pre}.downsample", L.s2d_segments(x, cin), [(0, 0, L.s2d_conv_taps(wd, pad=0))], cout, hh, ww,
+                               1, sc, sh, pair=True, out0=ident, macs_per_pair=2 * hh * ww * cin * cout)
+                else:
+                    L.add_conv(p, f"{pre}.downsample", [L.Segment(x, cin)], L.conv_taps(wd, pad=0), cout, hh, ww, 1, sc, sh,
+                               pair=True, out0=ident, macs_per_pair=2 * hh * ww * cin * cout)
+            else:
                 ident = x
-            sc, sh = bn(f"{pre}.bn2", cout)
+            sc, sh = bn(last_bn, cout)
             if last_of_layer:
                 o = p.tensor(f"{pre}.o_s2d", 2, hh // 2, ww // 2, 4 * cout)
                 skips.append((o, cout))
             else:
                 o = p.tensor(f"{pre}.o", 2, hh, ww, cout)
-            L.add_conv(p, f"{pre}.conv2", [L.Segment(t, cout)], L.conv_taps(w2, pad=1), cout, hh, ww, 1, sc, sh,
-                       pair=True, relu=True, res=ident, out0=o, out0_s2d=last_of_layer,
-                       macs_per_pair=2 * hh * ww * 9 * cout * cout)
+            L.add_conv(p, last_name, [L.Segment(last_in, last_c)], last_taps, cout, hh, ww, 1, sc, sh, pair=True, relu=True,
+                       res=ident, out0=o, out0_s2d=last_of_layer, macs_per_pair=last_macs)
             x, x_s2d, cin = o, last_of_layer, cout
 
     # ---------------- Unet decoder: (nearest x2, cat skip, conv-BN-ReLU, conv-BN-ReLU) x 5, per temporal image

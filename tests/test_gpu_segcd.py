@@ -30,7 +30,7 @@ def _check(ys, refs):
     assert agree.float().mean().item() >= 0.97
 
 
-@pytest.mark.parametrize("name", ["resnet34", "resnet18"])
+@pytest.mark.parametrize("name", ["resnet34", "resnet18", "resnet50"])
 def test_forward_matches_oracle_and_emulator(name):
     net = _net(name)
     x1, x2 = synth.image_pairs(3, 64, 96)
@@ -47,10 +47,11 @@ def test_forward_matches_oracle_and_emulator(name):
         assert (y.cpu() - e).abs().max().item() < 1.5e-2, "kernel vs emulator (same rounding points)"
 
 
-def test_forward_matches_golden(golden_dir):
-    g = np.load(os.path.join(golden_dir, "segcd_r34.npz"))
+@pytest.mark.parametrize("case,name", [("segcd_r34", "resnet34"), ("segcd_r50", "resnet50")])
+def test_forward_matches_golden(golden_dir, case, name):
+    g = np.load(os.path.join(golden_dir, f"{case}.npz"))
     assert float(g["gain"]) == synth.GAINS["SegCD"] and int(g["n_out"]) == 3
-    net = _net().cuda()
+    net = _net(name).cuda()
     x1, x2 = synth.image_pairs(int(g["batch"]), int(g["h"]), int(g["w"]), seed=int(g["data_seed"]))
     ys = net(x1.cuda(), x2.cuda())
     _check(ys, [torch.from_numpy(g[f"out{i}"]) for i in range(3)])

@@ -83,7 +83,25 @@ def test_segcd_program_matches_oracle():
     with pytest.raises(ValueError):
         net.lower(1000, 1024)
     with pytest.raises(NotImplementedError):
-        segcd.SegCD("resnet50")
+        segcd.SegCD("resnext50_32x4d")
+
+
+def test_segcd_resnet50_program_matches_oracle():
+    """The encoder the STCD script selects (train_stcd.py:638): Bottleneck blocks; the 1x1 conv ahead of a
+    stride-2 3x3 runs per parity class of its space-to-depth input."""
+    from stcd_b200 import segcd
+    net = synth.prepare_(segcd.SegCD("resnet50").eval(), "SegCD")
+    x1, x2 = synth.image_pairs(2, 64, 64)
+    with torch.no_grad():
+        y = nets.segcd_forward(net.state_dict(), x1, x2)
+    prog = net.lower(64, 64)
+    ye = emulate.run_program(prog, x1, x2, chunk=2)
+    for a, b in zip(ye, y):
+        assert (a - b).abs().max().item() < BF16_TOL
+    convs = [o for o in prog.ops if isinstance(o, L.ConvSpec)]
+    # stem + 16 blocks x 3 + 3 x 3 extra per-class conv1 launches + 4 downsamples + 10 decoder convs
+    assert len(convs) == 1 + 48 + 9 + 4 + 10
+    assert abs(2 * net.lower(1024, 1024).macs_per_pair() / 1e9 - 680.79) < 0.5
 
 
 def test_s2d_and_up2_tap_algebra():
