@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 6
+#define STCD_ABI_VERSION 7
 
 enum stcd_status {
   STCD_OK = 0,
@@ -166,6 +166,13 @@ int stcd_plan_add_input_pack(stcd_plan* plan, int dst_tensor, int cin);
  * x[c][2y + py][2x + px] (4*cin <= 16); the stem then runs as a 4x4 stride-1 conv. */
 int stcd_plan_add_input_pack_s2d(stcd_plan* plan, int dst_tensor, int cin);
 
+/* uint8 input pipeline (reference: data/dataset.py:196-203, ToTensor + Normalize on the host).
+ * Same as stcd_plan_add_input_pack / _s2d, but the plan's inputs become uint8 HWC images [n_pairs, H, W, cin] and
+ * the pack kernel evaluates ((u / 255) - mean[c]) / std[c] in fp32 (IEEE ops, the reference's expression) before
+ * the bf16 rounding: bit-identical to packing the host-normalised fp32 tensor, at a quarter of the PCIe bytes.
+ * A plan built with this op is run with stcd_forward_u8 / stcd_forward_host_u8.  mean, std: HOST float[cin]. */
+int stcd_plan_add_input_pack_u8(stcd_plan* plan, int dst_tensor, int cin, int s2d, const float* mean, const float* std_);
+
 /* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (smp/encoders/resnet.py:51) over a feature map stored
  * space-to-depth (src: [h][w] pixels x 4c channels = the (2h x 2w) map) -> dst [h][w] x c channels. */
 int stcd_plan_add_maxpool_s2d(stcd_plan* plan, int src_tensor, int dst_tensor, int c);
@@ -241,6 +248,13 @@ int stcd_forward_profile(stcd_plan* plan, const float* x1, const float* x2, int 
 int stcd_forward_host(stcd_plan* plan, const float* x1_host, const float* x2_host, int n_pairs,
                       float* const* outs_host, int n_outs);
 
+/* stcd_forward / stcd_forward_host for plans whose input op is stcd_plan_add_input_pack_u8:
+ * x1, x2 are uint8 HWC [n_pairs, H, W, cin] (device / host). */
+int stcd_forward_u8(stcd_plan* plan, const uint8_t* x1, const uint8_t* x2, int n_pairs, float* const* outs, int n_outs,
+                    void* stream);
+int stcd_forward_host_u8(stcd_plan* plan, const uint8_t* x1_host, const uint8_t* x2_host, int n_pairs,
+                         float* const* outs_host, int n_outs);
+
 /* Replaces `pred = argmax / sigmoid>thr / raw>=thr` + SegmentationMetric.addBatch
  * (train_stcd.py:477,483,572-588; models/evaluator.py:108-113). cm_dev: int64[num_class^2]
  * device accumulator, rows = ground truth, cols = prediction (train_stcd.py:576). */
@@ -252,7 +266,9 @@ enum stcd_pred_kind {
   STCD_PRED_I32 = 4,        /* class ids int32 (pred.int(), train_stcd.py:483) */
   STCD_PRED_I64 = 5         /* class ids int64 */
 };
-enum stcd_label_kind { STCD_LABEL_I64 = 0, STCD_LABEL_U8 = 1, STCD_LABEL_I32 = 2 };
+/* STCD_LABEL_U8_GE1: raw uint8 label image, binarised on the fly like the reference's loader (label[label >= 1] = 1,
+ * data/dataset.py:206-210): a {0, 255} PNG mask goes straight to the evaluator. */
+enum stcd_label_kind { STCD_LABEL_I64 = 0, STCD_LABEL_U8 = 1, STCD_LABEL_I32 = 2, STCD_LABEL_U8_GE1 = 3 };
 
 int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const void* label,
                              int label_kind, int64_t n_img, int64_t pix_per_img, int num_class,

@@ -104,9 +104,22 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
         T[op.out_diff][:n_img, :, :, : op.cout] = _bf16((vs[0] - vs[1]).abs()[..., : op.cout])
 
 
+def normalize_u8(img: torch.Tensor, mean, std) -> torch.Tensor:
+    """The reference loader on a decoded image batch: uint8 HWC [B, H, W, C] -> fp32 NCHW, torchvision's
+    ToTensor (x.div(255)) then Normalize (x.sub(mean).div(std)) in fp32 (data/dataset.py:196-203)."""
+    x = img.permute(0, 3, 1, 2).to(torch.float32).div(255)
+    m = torch.tensor(mean, dtype=torch.float32).view(1, -1, 1, 1)
+    s = torch.tensor(std, dtype=torch.float32).view(1, -1, 1, 1)
+    return x.sub(m).div(s)
+
+
 def run_program(prog: L.Program, x1: torch.Tensor, x2: torch.Tensor, chunk: int | None = None,
                 keep: Dict[str, torch.Tensor] | None = None) -> List[torch.Tensor]:
-    """x1, x2: fp32 NCHW [B, cin, H, W] -> list of fp32 NCHW external outputs."""
+    """x1, x2: fp32 NCHW [B, cin, H, W] (or uint8 HWC when the input op carries u8_norm) -> list of fp32 NCHW
+    external outputs."""
+    for op in prog.ops:
+        if isinstance(op, L.InputPackSpec) and op.u8_norm is not None:
+            x1, x2 = normalize_u8(x1, *op.u8_norm), normalize_u8(x2, *op.u8_norm)
     n = x1.shape[0]
     chunk = chunk or n
     outs = [torch.zeros(n, e.channels, e.h, e.w) for e in prog.ext]

@@ -125,7 +125,7 @@ class EcamDesc(C.Structure):
     ]
 
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -138,6 +138,7 @@ SYMBOLS = [
     ("stcd_plan_add_conv", C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
     ("stcd_plan_add_input_pack", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("stcd_plan_add_input_pack_s2d", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("stcd_plan_add_input_pack_u8", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("stcd_plan_add_maxpool_s2d", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("stcd_plan_add_seg_head", C.c_int, [C.c_void_p, C.c_void_p]),
     ("stcd_plan_add_ecam_head", C.c_int, [C.c_void_p, C.c_void_p]),
@@ -147,6 +148,8 @@ SYMBOLS = [
     ("stcd_plan_workspace_bytes", C.c_int64, [C.c_void_p]),
     ("stcd_plan_launches", C.c_int64, [C.c_void_p, C.c_int]),
     ("stcd_forward", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    ("stcd_forward_u8", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    ("stcd_forward_host_u8", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int]),
     ("stcd_forward_profile", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p,
                                        C.POINTER(C.c_float), C.c_int]),
     ("stcd_forward_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int]),

@@ -44,6 +44,89 @@ __global__ void __launch_bounds__(256) input_pack_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
+// uint8 input pipeline: the reference's CD_Dataset (data/dataset.py:196-203) turns uint8 HWC
+// RGB into normalised fp32 CHW on the host -- ToTensor (x / 255) then Normalize ((x - mean) / std) -- and ships
+// 12 B per pixel-image over PCIe.  These variants take the uint8 HWC images themselves (3 B per pixel-image) and
+// evaluate the reference's fp32 expression with IEEE ops before the bf16 rounding, so the packed tensor is
+// bit-identical to packing the host-normalised fp32 input.
+struct NormParams {
+  float mean[4], stdv[4];
+};
+
+__device__ __forceinline__ float norm_u8(uint8_t u, float mean, float stdv) {
+  return __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(u), 255.0f), mean), stdv);
+}
+
+// x1, x2: uint8 HWC [n_valid][h][w][CIN] -> dst bf16 [2*chunk][c8][h][w][8]
+template <int CIN>
+__global__ void __launch_bounds__(256) input_pack_u8_kernel(const uint8_t* __restrict__ x1, const uint8_t* __restrict__ x2,
+                                                            __nv_bfloat16* __restrict__ dst, int chunk, int n_valid, int c8,
+                                                            int hw, const NormParams np) {
+  const size_t total = static_cast<size_t>(2) * chunk * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / hw);
+    const int pix = static_cast<int>(i - static_cast<size_t>(n) * hw);
+    const int s = n / chunk, b = n - s * chunk;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.f;
+    if (b < n_valid) {
+      const uint8_t* src = (s ? x2 : x1) + (static_cast<size_t>(b) * hw + pix) * CIN;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) v[c] = norm_u8(__ldg(src + c), np.mean[c], np.stdv[c]);
+    }
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    __nv_bfloat16* o = dst + (static_cast<size_t>(n) * c8 * hw + pix) * 8;
+    *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (c8 > 1) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// space-to-depth variant: uint8 HWC [n_valid][2h][2w][CIN] -> dst bf16 [2*chunk][2][h][w][8], channel (py*2+px)*CIN + c
+template <int CIN>
+__global__ void __launch_bounds__(256) input_pack_s2d_u8_kernel(const uint8_t* __restrict__ x1, const uint8_t* __restrict__ x2,
+                                                                __nv_bfloat16* __restrict__ dst, int chunk, int n_valid, int h,
+                                                                int w, const NormParams np) {
+  const int hw = h * w;
+  const size_t total = static_cast<size_t>(2) * chunk * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / hw);
+    const int pix = static_cast<int>(i - static_cast<size_t>(n) * hw);
+    const int y = pix / w, x = pix - y * w;
+    const int s = n / chunk, b = n - s * chunk;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.f;
+    if (b < n_valid) {
+      const uint8_t* src = (s ? x2 : x1) + ((static_cast<size_t>(b) * 2 * h + 2 * y) * (2 * w) + 2 * x) * CIN;
+#pragma unroll
+      for (int py = 0; py < 2; ++py)
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+          for (int c = 0; c < CIN; ++c)
+            v[(py * 2 + px) * CIN + c] = norm_u8(__ldg(src + (static_cast<size_t>(py) * 2 * w + px) * CIN + c), np.mean[c], np.stdv[c]);
+    }
+    uint32_t wd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 hv = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      wd[j] = *reinterpret_cast<uint32_t*>(&hv);
+    }
+    __nv_bfloat16* o = dst + (static_cast<size_t>(n) * 2 * hw + pix) * 8;
+    *reinterpret_cast<uint4*>(o) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K9: pred/label -> confusion matrix.  cm[g*K + p] += #{label == g && pred == p}
 // (rows = ground truth, cols = prediction: train_stcd.py:576-578).
 // Thread-local counters -> warp REDUX -> one shared-memory row per warp -> 64-bit global
@@ -113,6 +196,7 @@ template <int LK>
 __device__ __forceinline__ long long label_at(const void* label, size_t idx) {
   if (LK == STCD_LABEL_I64) return __ldg(static_cast<const long long*>(label) + idx);
   if (LK == STCD_LABEL_U8) return __ldg(static_cast<const uint8_t*>(label) + idx);
+  if (LK == STCD_LABEL_U8_GE1) return __ldg(static_cast<const uint8_t*>(label) + idx) >= 1 ? 1 : 0;
   return __ldg(static_cast<const int32_t*>(label) + idx);
 }
 template <int LK>
@@ -124,10 +208,13 @@ __device__ __forceinline__ void label4_at(const void* label, size_t idx, long lo
     out[1] = a.y;
     out[2] = b.x;
     out[3] = b.y;
-  } else if (LK == STCD_LABEL_U8) {
+  } else if (LK == STCD_LABEL_U8 || LK == STCD_LABEL_U8_GE1) {
     const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(label) + idx));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = (w >> (8 * j)) & 0xff;
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t u = (w >> (8 * j)) & 0xff;
+      out[j] = (LK == STCD_LABEL_U8_GE1) ? (u >= 1 ? 1 : 0) : u;
+    }
   } else {
     const int4 a = __ldg(reinterpret_cast<const int4*>(static_cast<const int32_t*>(label) + idx));
     out[0] = a.x;

@@ -87,6 +87,8 @@ struct ConvOp {
 struct PackOp {
   int dst, cin;
   int s2d = 0;
+  int u8 = 0;                 // inputs are uint8 HWC, normalised in the pack kernel
+  stcd::NormParams norm;
 };
 
 struct PoolOp {
@@ -133,6 +135,7 @@ struct stcd_plan {
   size_t arena_bytes = 0;
   int n_ext = 0;
   int in_c = 0, in_h = 0, in_w = 0;
+  int in_u8 = 0;  // 1: the plan's inputs are uint8 HWC images (stcd_plan_add_input_pack_u8)
   int pdl = 1;  // programmatic dependent launch between the conv kernels (STCD_PDL=0 disables)
   std::vector<size_t> ext_elems;  // per external output: elements per image
   // host-buffer path
@@ -219,9 +222,11 @@ int launch_conv(const stcd_plan* plan, const ConvOp& op, int n_valid, float* con
   return STCD_OK;
 }
 
-int run_chunk(stcd_plan* plan, const float* x1, const float* x2, int n_valid, float* const* outs, cudaStream_t st,
+int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, float* const* outs, cudaStream_t st,
               cudaEvent_t* ev = nullptr) {
   int op_i = 0;
+  const float* x1 = static_cast<const float*>(x1v);
+  const float* x2 = static_cast<const float*>(x2v);
   if (ev) CUDA_TRY(cudaEventRecord(ev[0], st));
   for (const Op& o : plan->ops) {
     if (o.kind == 0) {
@@ -267,7 +272,23 @@ int run_chunk(stcd_plan* plan, const float* x1, const float* x2, int n_valid, fl
       const int hw = t.h * t.w;
       const size_t total = (size_t)2 * plan->chunk * hw;
       const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
-      if (k.s2d) {
+      if (k.u8) {
+        const uint8_t* u1 = static_cast<const uint8_t*>(x1v);
+        const uint8_t* u2 = static_cast<const uint8_t*>(x2v);
+        __nv_bfloat16* dp = (__nv_bfloat16*)t.ptr;
+#define STCD_PACK_U8(CIN)                                                                                                    \
+  if (k.s2d)                                                                                                                 \
+    stcd::input_pack_s2d_u8_kernel<CIN><<<blocks, 256, 0, st>>>(u1, u2, dp, plan->chunk, n_valid, t.h, t.w, k.norm);         \
+  else                                                                                                                       \
+    stcd::input_pack_u8_kernel<CIN><<<blocks, 256, 0, st>>>(u1, u2, dp, plan->chunk, n_valid, t.c / 8, hw, k.norm)
+        switch (k.cin) {
+          case 1: STCD_PACK_U8(1); break;
+          case 2: STCD_PACK_U8(2); break;
+          case 3: STCD_PACK_U8(3); break;
+          default: STCD_PACK_U8(4); break;
+        }
+#undef STCD_PACK_U8
+      } else if (k.s2d) {
         __nv_bfloat16* dp = (__nv_bfloat16*)t.ptr;
         switch (k.cin) {
           case 1: stcd::input_pack_s2d_kernel<1><<<blocks, 256, 0, st>>>(x1, x2, dp, plan->chunk, n_valid, t.h, t.w); break;
@@ -399,6 +420,24 @@ int stcd_plan_add_input_pack_s2d(stcd_plan* plan, int dst_tensor, int cin) {
   plan->in_h = 2 * t.h;
   plan->in_w = 2 * t.w;
   return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_input_pack_u8(stcd_plan* plan, int dst_tensor, int cin, int s2d, const float* mean, const float* std_) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (!mean || !std_) return -fail(STCD_ERR_INVALID, "mean/std are NULL");
+  if (cin < 1 || cin > 4) return -fail(STCD_ERR_INVALID, "uint8 input pack: cin %d not in [1, 4]", cin);
+  for (int c = 0; c < cin; ++c)
+    if (!(std_[c] > 0.f)) return -fail(STCD_ERR_INVALID, "std[%d] must be positive", c);
+  const int r = s2d ? stcd_plan_add_input_pack_s2d(plan, dst_tensor, cin) : stcd_plan_add_input_pack(plan, dst_tensor, cin);
+  if (r < 0) return r;
+  PackOp& k = plan->packs.back();
+  k.u8 = 1;
+  for (int c = 0; c < 4; ++c) {
+    k.norm.mean[c] = c < cin ? mean[c] : 0.f;
+    k.norm.stdv[c] = c < cin ? std_[c] : 1.f;
+  }
+  plan->in_u8 = 1;
+  return r;
 }
 
 int stcd_plan_add_maxpool_s2d(stcd_plan* plan, int src_tensor, int dst_tensor, int c) {
@@ -949,22 +988,34 @@ int64_t stcd_plan_launches(const stcd_plan* plan, int n_pairs) {
   return chunks * (int64_t)(plan->ops.size() + plan->ecams.size());  // an ECAM head op is two kernels
 }
 
-int stcd_forward(stcd_plan* plan, const float* x1, const float* x2, int n_pairs, float* const* outs, int n_outs,
-                 void* stream) {
+static int forward_any(stcd_plan* plan, const void* x1, const void* x2, int u8, int n_pairs, float* const* outs, int n_outs,
+                       void* stream) {
   if (!plan || !plan->finalized) return fail(STCD_ERR_STATE, "plan not finalized");
   if (!x1 || !x2 || n_pairs < 0) return fail(STCD_ERR_INVALID, "bad inputs");
+  if (plan->in_u8 != u8) return fail(STCD_ERR_INVALID, "plan takes %s inputs", plan->in_u8 ? "uint8 HWC (stcd_forward_u8)" : "fp32 NCHW (stcd_forward)");
   if (n_outs != plan->n_ext || (n_outs > 0 && !outs)) return fail(STCD_ERR_INVALID, "plan has %d external outputs, got %d", plan->n_ext, n_outs);
   CUDA_TRY(cudaSetDevice(plan->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t in_elems = (size_t)plan->in_c * plan->in_h * plan->in_w;
+  const size_t in_bytes = (size_t)plan->in_c * plan->in_h * plan->in_w * (u8 ? 1 : sizeof(float));
   std::vector<float*> o(n_outs);
   for (int start = 0; start < n_pairs; start += plan->chunk) {
     const int nv = std::min(plan->chunk, n_pairs - start);
     for (int k = 0; k < n_outs; ++k) o[k] = outs[k] ? outs[k] + (size_t)start * plan->ext_elems[k] : nullptr;
-    int r = run_chunk(plan, x1 + (size_t)start * in_elems, x2 + (size_t)start * in_elems, nv, o.data(), st);
+    int r = run_chunk(plan, static_cast<const uint8_t*>(x1) + (size_t)start * in_bytes,
+                      static_cast<const uint8_t*>(x2) + (size_t)start * in_bytes, nv, o.data(), st);
     if (r) return r;
   }
   return STCD_OK;
+}
+
+int stcd_forward(stcd_plan* plan, const float* x1, const float* x2, int n_pairs, float* const* outs, int n_outs,
+                 void* stream) {
+  return forward_any(plan, x1, x2, 0, n_pairs, outs, n_outs, stream);
+}
+
+int stcd_forward_u8(stcd_plan* plan, const uint8_t* x1, const uint8_t* x2, int n_pairs, float* const* outs, int n_outs,
+                    void* stream) {
+  return forward_any(plan, x1, x2, 1, n_pairs, outs, n_outs, stream);
 }
 
 int stcd_forward_profile(stcd_plan* plan, const float* x1, const float* x2, int n_pairs, float* const* outs, int n_outs,
@@ -975,7 +1026,9 @@ int stcd_forward_profile(stcd_plan* plan, const float* x1, const float* x2, int 
   if (n_outs != plan->n_ext || (n_outs > 0 && !outs)) return fail(STCD_ERR_INVALID, "plan has %d external outputs, got %d", plan->n_ext, n_outs);
   CUDA_TRY(cudaSetDevice(plan->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t in_elems = (size_t)plan->in_c * plan->in_h * plan->in_w;
+  const size_t in_bytes = (size_t)plan->in_c * plan->in_h * plan->in_w * (plan->in_u8 ? 1 : sizeof(float));
+  const uint8_t* b1 = reinterpret_cast<const uint8_t*>(x1);
+  const uint8_t* b2 = reinterpret_cast<const uint8_t*>(x2);
   std::vector<cudaEvent_t> ev(n_ops + 1);
   for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
   for (int i = 0; i < n_ops; ++i) op_ms[i] = 0.f;
@@ -984,7 +1037,7 @@ int stcd_forward_profile(stcd_plan* plan, const float* x1, const float* x2, int 
   for (int start = 0; start < n_pairs && rc == STCD_OK; start += plan->chunk) {
     const int nv = std::min(plan->chunk, n_pairs - start);
     for (int k = 0; k < n_outs; ++k) o[k] = outs[k] ? outs[k] + (size_t)start * plan->ext_elems[k] : nullptr;
-    rc = run_chunk(plan, x1 + (size_t)start * in_elems, x2 + (size_t)start * in_elems, nv, o.data(), st, ev.data());
+    rc = run_chunk(plan, b1 + (size_t)start * in_bytes, b2 + (size_t)start * in_bytes, nv, o.data(), st, ev.data());
     if (rc) break;
     if (cudaStreamSynchronize(st) != cudaSuccess) {
       rc = fail(STCD_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1000,14 +1053,17 @@ int stcd_forward_profile(stcd_plan* plan, const float* x1, const float* x2, int 
   return rc;
 }
 
-int stcd_forward_host(stcd_plan* plan, const float* x1h, const float* x2h, int n_pairs, float* const* outs_host,
-                      int n_outs) {
+static int forward_host_any(stcd_plan* plan, const void* x1v, const void* x2v, int u8, int n_pairs, float* const* outs_host,
+                            int n_outs) {
   if (!plan || !plan->finalized) return fail(STCD_ERR_STATE, "plan not finalized");
-  if (!x1h || !x2h || n_pairs < 0) return fail(STCD_ERR_INVALID, "bad inputs");
+  if (!x1v || !x2v || n_pairs < 0) return fail(STCD_ERR_INVALID, "bad inputs");
+  if (plan->in_u8 != u8) return fail(STCD_ERR_INVALID, "plan takes %s inputs", plan->in_u8 ? "uint8 HWC (stcd_forward_host_u8)" : "fp32 NCHW (stcd_forward_host)");
+  const uint8_t* x1h = static_cast<const uint8_t*>(x1v);
+  const uint8_t* x2h = static_cast<const uint8_t*>(x2v);
   if (n_outs != plan->n_ext || (n_outs > 0 && !outs_host)) return fail(STCD_ERR_INVALID, "plan has %d external outputs, got %d", plan->n_ext, n_outs);
   CUDA_TRY(cudaSetDevice(plan->device));
-  const size_t in_elems = (size_t)plan->in_c * plan->in_h * plan->in_w;
-  const size_t in_bytes = in_elems * plan->chunk * sizeof(float);
+  const size_t in_elems = (size_t)plan->in_c * plan->in_h * plan->in_w * (u8 ? 1 : sizeof(float));   // bytes per image
+  const size_t in_bytes = in_elems * plan->chunk;
   if (!plan->s_copy) {
     CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_copy, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_comp, cudaStreamNonBlocking));
@@ -1027,10 +1083,10 @@ int stcd_forward_host(stcd_plan* plan, const float* x1h, const float* x2h, int n
     const int b = it & 1;
     const int nv = std::min(plan->chunk, n_pairs - start);
     if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(plan->s_copy, plan->ev_comp[b], 0));  // staging buffer consumed
-    CUDA_TRY(cudaMemcpyAsync(plan->stage_in[b][0], x1h + (size_t)start * in_elems, in_elems * nv * sizeof(float),
-                             cudaMemcpyHostToDevice, plan->s_copy));
-    CUDA_TRY(cudaMemcpyAsync(plan->stage_in[b][1], x2h + (size_t)start * in_elems, in_elems * nv * sizeof(float),
-                             cudaMemcpyHostToDevice, plan->s_copy));
+    CUDA_TRY(cudaMemcpyAsync(plan->stage_in[b][0], x1h + (size_t)start * in_elems, in_elems * nv, cudaMemcpyHostToDevice,
+                             plan->s_copy));
+    CUDA_TRY(cudaMemcpyAsync(plan->stage_in[b][1], x2h + (size_t)start * in_elems, in_elems * nv, cudaMemcpyHostToDevice,
+                             plan->s_copy));
     CUDA_TRY(cudaEventRecord(plan->ev_h2d[b], plan->s_copy));
     CUDA_TRY(cudaStreamWaitEvent(plan->s_comp, plan->ev_h2d[b], 0));
     if (it >= 2) CUDA_TRY(cudaStreamWaitEvent(plan->s_comp, plan->ev_d2h[b], 0));  // output staging drained
@@ -1051,6 +1107,15 @@ int stcd_forward_host(stcd_plan* plan, const float* x1h, const float* x2h, int n
   return STCD_OK;
 }
 
+int stcd_forward_host(stcd_plan* plan, const float* x1h, const float* x2h, int n_pairs, float* const* outs_host, int n_outs) {
+  return forward_host_any(plan, x1h, x2h, 0, n_pairs, outs_host, n_outs);
+}
+
+int stcd_forward_host_u8(stcd_plan* plan, const uint8_t* x1h, const uint8_t* x2h, int n_pairs, float* const* outs_host,
+                         int n_outs) {
+  return forward_host_any(plan, x1h, x2h, 1, n_pairs, outs_host, n_outs);
+}
+
 int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const void* label, int label_kind,
                              int64_t n_img, int64_t pix, int num_class, int64_t* cm_dev, uint8_t* pred_out,
                              void* stream) {
@@ -1058,7 +1123,7 @@ int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const v
   if (n_img < 0 || pix < 0) return fail(STCD_ERR_INVALID, "negative size");
   if (num_class < 2 || num_class > 32) return fail(STCD_ERR_INVALID, "num_class %d not in [2, 32]", num_class);
   if (pred_kind < STCD_PRED_ARGMAX2 || pred_kind > STCD_PRED_I64) return fail(STCD_ERR_INVALID, "pred_kind %d", pred_kind);
-  if (label_kind < STCD_LABEL_I64 || label_kind > STCD_LABEL_I32) return fail(STCD_ERR_INVALID, "label_kind %d", label_kind);
+  if (label_kind < STCD_LABEL_I64 || label_kind > STCD_LABEL_U8_GE1) return fail(STCD_ERR_INVALID, "label_kind %d", label_kind);
   if (num_class != 2 && pred_kind <= STCD_PRED_RAW_GE) return fail(STCD_ERR_INVALID, "binarising kinds need num_class == 2");
   if (n_img == 0 || pix == 0) return STCD_OK;
   int ndev = 0;
@@ -1083,6 +1148,7 @@ int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const v
   switch (label_kind) {                                             \
     case STCD_LABEL_I64: M(PK, STCD_LABEL_I64); break;              \
     case STCD_LABEL_U8: M(PK, STCD_LABEL_U8); break;                \
+    case STCD_LABEL_U8_GE1: M(PK, STCD_LABEL_U8_GE1); break;        \
     default: M(PK, STCD_LABEL_I32); break;                          \
   }
   if (num_class == 2) {

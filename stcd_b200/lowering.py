@@ -119,6 +119,9 @@ class InputPackSpec:
     dst: str
     cin: int
     s2d: bool = False            # space-to-depth: dst is [h/2, w/2] with channel (py*2 + px)*cin + c
+    # (mean, std) per channel: the plan's inputs are uint8 HWC images and the pack kernel applies the reference
+    # loader's ToTensor + Normalize (data/dataset.py:196-203) before the bf16 rounding; None: fp32 NCHW inputs
+    u8_norm: Optional[Tuple[Tuple[float, ...], Tuple[float, ...]]] = None
 
 
 class SegTaps(list):

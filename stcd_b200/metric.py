@@ -25,7 +25,7 @@ import torch.nn as nn
 from . import _lib
 
 PRED_ARGMAX2, PRED_SIGMOID_GT, PRED_RAW_GE, PRED_U8, PRED_I32, PRED_I64 = range(6)
-LABEL_I64, LABEL_U8, LABEL_I32 = range(3)
+LABEL_I64, LABEL_U8, LABEL_I32, LABEL_U8_GE1 = range(4)
 
 _PRED_KINDS = {torch.uint8: PRED_U8, torch.bool: PRED_U8, torch.int32: PRED_I32, torch.int64: PRED_I64}
 _LABEL_KINDS = {torch.int64: LABEL_I64, torch.uint8: LABEL_U8, torch.bool: LABEL_U8, torch.int32: LABEL_I32}
@@ -92,9 +92,11 @@ class SegmentationMetric(nn.Module):
         self.count += 1
 
     def addLogits(self, logits: torch.Tensor, imgLabel: torch.Tensor, kind: str = "sigmoid", thr: float = 0.5,
-                  pred_out: Optional[torch.Tensor] = None):
+                  pred_out: Optional[torch.Tensor] = None, raw_mask_label: bool = False):
         """Fused binarise + histogram.  logits: fp32 [B,2,H,W] ('argmax') or [B,1,H,W] ('sigmoid',
-        'raw_ge'); imgLabel: [B,H,W] or [B,1,H,W] integer; pred_out: optional uint8 [B,H,W]."""
+        'raw_ge'); imgLabel: [B,H,W] or [B,1,H,W] integer; pred_out: optional uint8 [B,H,W].
+        raw_mask_label=True: imgLabel is the raw uint8 mask image ({0, 255}), binarised on the fly like the
+        reference's loader does (``label[label >= 1] = 1``, data/dataset.py:206-210)."""
         if self.numClass != 2:
             raise ValueError("addLogits binarises: numClass must be 2")
         if kind not in _LOGIT_KINDS:
@@ -111,13 +113,18 @@ class SegmentationMetric(nn.Module):
             label = label.view(torch.uint8)
         if label.dtype not in _LABEL_KINDS:
             raise TypeError(f"unsupported label dtype {label.dtype}")
+        label_kind = _LABEL_KINDS[label.dtype]
+        if raw_mask_label:
+            if label.dtype != torch.uint8:
+                raise TypeError("raw_mask_label needs the uint8 mask image")
+            label_kind = LABEL_U8_GE1
         po = None
         if pred_out is not None:
             assert pred_out.is_cuda and pred_out.dtype == torch.uint8 and pred_out.numel() == b * h * w
             po = C.c_void_p(pred_out.data_ptr())
         _lib.check(_lib.lib().stcd_confusion_add_batch(
             C.c_void_p(logits.data_ptr()), _LOGIT_KINDS[kind], float(thr), C.c_void_p(label.data_ptr()),
-            _LABEL_KINDS[label.dtype], b, h * w, 2, C.c_void_p(self._cm.data_ptr()), po, _stream_ptr(logits)),
+            label_kind, b, h * w, 2, C.c_void_p(self._cm.data_ptr()), po, _stream_ptr(logits)),
             "stcd_confusion_add_batch")
         self.count += 1
 

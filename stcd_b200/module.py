@@ -39,7 +39,24 @@ class PlannedModule(nn.Module):
     def lower(self, h: int, w: int) -> L.Program:  # pragma: no cover - abstract
         raise NotImplementedError
 
-    def plan_for(self, x: torch.Tensor):
+    #: the reference loader's normalisation (CD_Dataset.MEAN / STD, data/dataset.py:171-172)
+    IMAGENET_MEAN = (0.485, 0.456, 0.406)
+    IMAGENET_STD = (0.229, 0.224, 0.225)
+
+    @torch.no_grad()
+    def forward_uint8(self, a: torch.Tensor, b: torch.Tensor, mean=None, std=None):
+        """The same forward fed with the decoded uint8 HWC images ``[B, H, W, 3]`` the reference's loader starts
+        from (data/dataset.py:196-203): ToTensor + Normalize run inside the input-pack kernel, bit-identical to
+        ``self(normalize(a), normalize(b))`` at a quarter of the host-to-device bytes.  Returns what ``forward``
+        returns."""
+        norm = (tuple(mean or self.IMAGENET_MEAN), tuple(std or self.IMAGENET_STD))
+        outs = self.plan_for(a, u8_norm=norm).forward(a, b)
+        return self._wrap_outputs(outs)
+
+    def _wrap_outputs(self, outs):
+        return outs[0] if len(outs) == 1 else tuple(outs)
+
+    def plan_for(self, x: torch.Tensor, u8_norm=None):
         from .plan import Plan
         if self.training:
             raise RuntimeError("stcd_b200 implements the eval-mode inference path; call .eval() first "
@@ -47,9 +64,15 @@ class PlannedModule(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("stcd_b200 has no CPU path: move the module and its inputs to a B200 (cuda) device")
         chunk = max(1, min(int(self.chunk_pairs), int(x.shape[0])))
-        key = (x.device.index, int(x.shape[2]), int(x.shape[3]), chunk)
+        h, w = (int(x.shape[1]), int(x.shape[2])) if u8_norm is not None else (int(x.shape[2]), int(x.shape[3]))
+        key = (x.device.index, h, w, chunk, u8_norm)
         plan = self._plans.get(key)
         if plan is None:
-            plan = Plan(self.lower(key[1], key[2]), chunk, device=key[0])
+            prog = self.lower(h, w)
+            if u8_norm is not None:
+                for op in prog.ops:
+                    if isinstance(op, L.InputPackSpec):
+                        op.u8_norm = u8_norm
+            plan = Plan(prog, chunk, device=key[0])
             self._plans[key] = plan
         return plan

@@ -31,6 +31,7 @@ class Plan:
         self.prog = prog
         self.chunk = int(chunk_pairs)
         self.device = int(device)
+        self.u8 = False                      # set by _build when the input op takes uint8 HWC images
         self._h = C.c_void_p()
         _lib.check(self.lib.stcd_plan_create(self.device, self.chunk, C.byref(self._h)), "stcd_plan_create")
         try:
@@ -47,7 +48,13 @@ class Plan:
             ids[name] = _lib.check_id(lib.stcd_plan_add_tensor(h, t.mult, t.h, t.w, t.c, 0), f"tensor {name}")
         self.tensor_ids = ids
         for op in prog.ops:
-            if isinstance(op, InputPackSpec):
+            if isinstance(op, InputPackSpec) and op.u8_norm is not None:
+                mean = (C.c_float * op.cin)(*op.u8_norm[0][: op.cin])
+                std = (C.c_float * op.cin)(*op.u8_norm[1][: op.cin])
+                _lib.check_id(lib.stcd_plan_add_input_pack_u8(h, ids[op.dst], op.cin, 1 if op.s2d else 0, mean, std),
+                              f"uint8 input pack {op.name}")
+                self.u8 = True
+            elif isinstance(op, InputPackSpec):
                 add = lib.stcd_plan_add_input_pack_s2d if op.s2d else lib.stcd_plan_add_input_pack
                 _lib.check_id(add(h, ids[op.dst], op.cin), f"input pack {op.name}")
             elif isinstance(op, MaxPoolS2DSpec):
@@ -139,6 +146,12 @@ class Plan:
         p = self.prog
         if x1.shape != x2.shape:
             raise ValueError(f"x1 {tuple(x1.shape)} and x2 {tuple(x2.shape)} differ")
+        if self.u8:
+            if x1.dim() != 4 or tuple(x1.shape[1:]) != (p.h, p.w, p.in_channels):
+                raise ValueError(f"plan was built for uint8 [B,{p.h},{p.w},{p.in_channels}] (HWC) inputs, got {tuple(x1.shape)}")
+            if x1.dtype != torch.uint8 or x2.dtype != torch.uint8:
+                raise TypeError("this plan takes uint8 HWC images (the decoded RGB the reference's loader starts from)")
+            return int(x1.shape[0])
         if x1.dim() != 4 or tuple(x1.shape[1:]) != (p.in_channels, p.h, p.w):
             raise ValueError(f"plan was built for [B,{p.in_channels},{p.h},{p.w}] inputs, got {tuple(x1.shape)}")
         if x1.dtype != torch.float32 or x2.dtype != torch.float32:
@@ -157,8 +170,8 @@ class Plan:
             outs = [torch.empty(s, dtype=torch.float32, device=x1.device) for s in self.out_shapes(n)]
         ptrs = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
         stream = torch.cuda.current_stream(x1.device).cuda_stream
-        _lib.check(self.lib.stcd_forward(self._h, x1.data_ptr(), x2.data_ptr(), n, ptrs, len(outs),
-                                         C.c_void_p(stream)), "stcd_forward")
+        fwd = self.lib.stcd_forward_u8 if self.u8 else self.lib.stcd_forward
+        _lib.check(fwd(self._h, x1.data_ptr(), x2.data_ptr(), n, ptrs, len(outs), C.c_void_p(stream)), "stcd_forward")
         return list(outs)
 
     def forward_host(self, x1: torch.Tensor, x2: torch.Tensor, outs: Optional[Sequence[torch.Tensor]] = None
@@ -172,8 +185,8 @@ class Plan:
         if outs is None:
             outs = [torch.empty(s, dtype=torch.float32).pin_memory() for s in self.out_shapes(n)]
         ptrs = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
-        _lib.check(self.lib.stcd_forward_host(self._h, x1.data_ptr(), x2.data_ptr(), n, ptrs, len(outs)),
-                   "stcd_forward_host")
+        fwd = self.lib.stcd_forward_host_u8 if self.u8 else self.lib.stcd_forward_host
+        _lib.check(fwd(self._h, x1.data_ptr(), x2.data_ptr(), n, ptrs, len(outs)), "stcd_forward_host")
         return list(outs)
 
     def profile(self, x1: torch.Tensor, x2: torch.Tensor) -> List[tuple]:
