@@ -565,3 +565,44 @@ class EcamHeadSpec:
     b_final: np.ndarray          # float32 [n_class]
     out_ext: int = 0
     macs_per_pair: int = 0
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic HBM bytes (bench.py's roofline): every source read once + every output written once at its storage dtype
+
+
+def op_bytes_per_pair(prog: Program, op) -> int:
+    """Algorithmic bytes one image pair moves through op `op` (sources read once, outputs written once)."""
+    T = prog.tensors
+    if isinstance(op, InputPackSpec):
+        t = T[op.dst]
+        in_b = 1 if op.u8_norm is not None else 4
+        return 2 * (op.cin * prog.h * prog.w * in_b + t.h * t.w * t.c * 2)
+    if isinstance(op, MaxPoolS2DSpec):
+        t = T[op.dst]
+        return 2 * (4 * op.c + op.c) * t.h * t.w * 2
+    if isinstance(op, SegHeadSpec):
+        t = T[op.src]
+        return 2 * op.c * t.h * t.w * 2 + 3 * t.h * t.w * 4
+    if isinstance(op, EcamHeadSpec):
+        t = T[op.srcs[0]]
+        return 2 * 4 * op.c * t.h * t.w * 2 + op.n_class * t.h * t.w * 4
+    if isinstance(op, ConvSpec):
+        imgs = 2 if op.pair else op.img_mult
+        seen, byt = set(), 0
+        for ck in op.chunks:
+            key = (ck.src, ck.stream, ck.c0)
+            if key in seen:
+                continue
+            seen.add(key)
+            t = T[op.srcs[ck.src]]
+            byt += t.h * t.w * min(op.kc, t.c - ck.c0) * 2 * imgs
+        ho, wo = op.hg * op.osy, op.wg * op.osx
+        cout = op.fold_cout if op.fold_cs else op.cout
+        for o, f in ((op.out0, 1.0), (op.out_raw, 1.0), (op.res, 1.0), (op.out_pool, 0.25), (op.out_diff, 0.5 if op.pair else 1.0)):
+            if o:
+                byt += int(ho * wo * cout * 2 * imgs * f)
+        if op.out_ext >= 0:
+            byt += ho * wo * cout * 4 * imgs
+        return byt
+    return 0
