@@ -43,7 +43,7 @@ WORKLOADS = {
                                   desc="SiamUnet_diff 256x256 RGB pairs, batch 64 per GPU"),
     "siamunet_conc_256": dict(net="SiamUnet_conc", n_class=2, h=256, w=256, batch=8, kind="argmax",
                               desc="SiamUnet_conc 256x256 RGB pairs, batch 8 per GPU"),
-    "segcd_r34_1024_b16": dict(net="SegCD", n_class=1, h=1024, w=1024, batch=16, kind="sigmoid", chunk=8, input_sets=2,
+    "segcd_r34_1024_b16": dict(net="SegCD", n_class=1, h=1024, w=1024, batch=16, kind="sigmoid", chunk=16, input_sets=2,
                                desc="C3: smp SegCD (Unet, ResNet-34 Siamese encoder) 1024x1024 RGB pair tiles, batch 16 per GPU, "
                                     "bf16, + confusion-matrix F1/IoU on sigmoid(change) > 0.5"),
     "segcd_r50_1024_b16": dict(net="SegCD", encoder="resnet50", n_class=1, h=1024, w=1024, batch=16, kind="sigmoid", chunk=8,
@@ -92,17 +92,21 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  The sampler process is
+    started well before the region (nvidia-smi takes a few hundred ms to produce its first line); every row is
+    stamped on arrival and `summary()` keeps the rows that fall inside the region [t0, t1] (for a region shorter
+    than two sampling periods: the rows nearest to it, taken under the same load during warm-up / e2e)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -112,21 +116,35 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def __exit__(self, *a):
+    def __enter__(self):          # timed region begins
+        if self.proc is None:
+            self.start()
+        self.t0 = time.time()
+        return self
+
+    def __exit__(self, *a):       # timed region ends
+        self.t1 = time.time()
+
+    def stop(self):
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.12)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
+            self.proc = None
 
     def summary(self):
+        self.stop()
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.06]
+        near = inside or [r for (t, r) in self.rows if t0 - 1.0 <= t <= t1 + 1.0]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in near:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -138,7 +156,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "samples_inside_timed_region": len(inside)}
 
 
 def cpu_baseline(wl, seconds_target: float = 15.0, threads: int | None = None):
@@ -214,8 +233,6 @@ def run_reference(args, wl, rank, world):
 
 def run_ours(args, wl, rank, world, local_rank):
     import torch.distributed as dist
-    from stcd_b200 import synth
-    from stcd_b200.metric import SegmentationMetric
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — stcd_b200 has no CPU path (use --impl reference for the CPU arm)")
@@ -223,7 +240,35 @@ def run_ours(args, wl, rank, world, local_rank):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    out = measure(args, args.workload, wl, rank, world, local_rank, dev, full=True)
+    # BASELINE.json's metric names both sizes ("at 256^2 and 1024^2"): the other headline configuration rides
+    # along as a compact object (fewer steps, no CPU leg) so one default run reports both
+    other = {"snunet_256_b64": "segcd_r34_1024_b16", "segcd_r34_1024_b16": "snunet_256_b64"}.get(args.workload)
+    if other and not args.no_also:
+        import copy
+        a2 = copy.copy(args)
+        wl2 = WORKLOADS[other]
+        a2.workload, a2.chunk, a2.input_sets = other, wl2.get("chunk", 32), wl2.get("input_sets", 4)
+        a2.steps, a2.warmup, a2.no_cpu_baseline = min(args.steps, 5), 3, True
+        torch.cuda.empty_cache()
+        o2 = measure(a2, other, wl2, rank, world, local_rank, dev, full=False)
+        if out is not None and o2 is not None:
+            out["also"] = {k: o2[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "config",
+                                              "e2e", "gpu_launches", "roofline")}
+    if out is not None:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
+
+def measure(args, wl_name, wl, rank, world, local_rank, dev, full=True):
+    """One workload on this rank's GPU: returns the JSON object on rank 0, None elsewhere."""
+    import torch.distributed as dist
+    from stcd_b200 import synth
+    from stcd_b200.metric import SegmentationMetric
+
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
     B, H, W = wl["batch"], wl["h"], wl["w"]
     net = build_net(wl).to(dev)
     net.chunk_pairs = args.chunk
@@ -294,9 +339,10 @@ def run_ours(args, wl, rank, world, local_rank):
     # the same with the decoded uint8 HWC images the reference's loader starts from (data/dataset.py:196-203):
     # ToTensor + Normalize run in the input-pack kernel, a quarter of the PCIe bytes
     gu = torch.Generator().manual_seed(77 + rank)
-    hu1 = [torch.randint(0, 256, (B, H, W, 3), generator=gu, dtype=torch.uint8).pin_memory() for _ in range(n_sets)]
-    hu2 = [torch.randint(0, 256, (B, H, W, 3), generator=gu, dtype=torch.uint8).pin_memory() for _ in range(n_sets)]
-    step_e2e_u8 = make_e2e(hu1, hu2, net.forward_uint8)
+    if full:
+        hu1 = [torch.randint(0, 256, (B, H, W, 3), generator=gu, dtype=torch.uint8).pin_memory() for _ in range(n_sets)]
+        hu2 = [torch.randint(0, 256, (B, H, W, 3), generator=gu, dtype=torch.uint8).pin_memory() for _ in range(n_sets)]
+        step_e2e_u8 = make_e2e(hu1, hu2, net.forward_uint8)
 
     def timed(fn, steps, warmup, sampler=None):
         for i in range(warmup):
@@ -323,12 +369,11 @@ def run_ours(args, wl, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_total = timed(step, args.steps, args.warmup, sampler)
     metric.reset()
     ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
     metric.reset()
-    ms_e2e_u8 = timed(step_e2e_u8, args.steps, max(3, args.warmup // 2))
+    ms_e2e_u8 = timed(step_e2e_u8, args.steps, max(3, args.warmup // 2)) if full else float("nan")
     value = world * B * args.steps / (ms_total / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
     e2e_u8 = world * B * args.steps / (ms_e2e_u8 / 1e3)
@@ -357,7 +402,7 @@ def run_ours(args, wl, rank, world, local_rank):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tpath):
-            tr = json.load(open(tpath)).get(args.workload, {}).get(top[0])
+            tr = json.load(open(tpath)).get(wl_name, {}).get(top[0])
             if tr:                                   # ncu --set full: dram bytes read + written, per pair -> per launch
                 traffic = int(tr["dram_bytes_per_pair"] * min(args.chunk, B))
         launches = max(1, -(-B // args.chunk))        # the profile pass sums the op over its launches (chunks)
@@ -396,12 +441,13 @@ def run_ours(args, wl, rank, world, local_rank):
             "roofline": roof,
             "per_op_ms": [[n, round(ms, 4)] for n, ms, _ in prof],
         }
+        if not full:
+            out.pop("e2e_u8")
+            out.pop("per_op_ms")
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(wl)
-        print(json.dumps(out))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        return out
+    return None
 
 
 def main():
@@ -414,6 +460,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="image pairs per pass through the layer stack (0: the workload's default)")
     ap.add_argument("--input-sets", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the compact run of the other headline configuration")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

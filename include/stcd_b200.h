@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 7
+#define STCD_ABI_VERSION 8
 
 enum stcd_status {
   STCD_OK = 0,
@@ -264,7 +264,8 @@ enum stcd_pred_kind {
   STCD_PRED_RAW_GE = 2,     /* logits fp32 [n,1,h,w]  -> x >= thr           (evaluator.py:111) */
   STCD_PRED_U8 = 3,         /* class ids uint8 */
   STCD_PRED_I32 = 4,        /* class ids int32 (pred.int(), train_stcd.py:483) */
-  STCD_PRED_I64 = 5         /* class ids int64 */
+  STCD_PRED_I64 = 5,        /* class ids int64 */
+  STCD_PRED_U8_GE1 = 6      /* raw uint8 mask image ({0, 255} pseudo-label PNG): >= 1 -> class 1 */
 };
 /* STCD_LABEL_U8_GE1: raw uint8 label image, binarised on the fly like the reference's loader (label[label >= 1] = 1,
  * data/dataset.py:206-210): a {0, 255} PNG mask goes straight to the evaluator. */
@@ -294,6 +295,12 @@ int stcd_knn_graph(const float* x, const float* y_or_null, const float* relative
  * (the channel-interleaved tensor MRConv2d feeds to its grouped 1x1 conv). */
 int stcd_max_relative(const float* x, const float* y_or_null, const int64_t* nn_idx, int B, int C, int N, int M,
                       int k, int interleave, float* out, void* stream);
+
+/* Pseudo-label write path (train_stcd.py:155-196, train_pse_cd.py:145): binarise fp32 logits
+ * [n][1 or 2][pix] with `pred_kind` (ARGMAX2 / SIGMOID_GT / RAW_GE) and write the uint8 mask image the script saves
+ * as PNG: `on_value` (255, train_stcd.py:185) where the change class wins, else 0. */
+int stcd_binarise_mask(const float* logits, int pred_kind, float thr, int64_t n_img, int64_t pix_per_img,
+                       int on_value, uint8_t* mask_out, void* stream);
 
 #ifdef __cplusplus
 }

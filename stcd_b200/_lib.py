@@ -125,7 +125,7 @@ class EcamDesc(C.Structure):
     ]
 
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -155,6 +155,7 @@ SYMBOLS = [
     ("stcd_forward_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int]),
     ("stcd_confusion_add_batch", C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
                                            C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("stcd_binarise_mask", C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     ("stcd_knn_graph", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     ("stcd_max_relative", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

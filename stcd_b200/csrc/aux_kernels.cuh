@@ -149,6 +149,8 @@ __device__ __forceinline__ int pred_at(const void* pred, size_t n, size_t i, siz
     return (__ldg(static_cast<const float*>(pred) + n * pix + i) >= thr) ? 1 : 0;
   } else if (PK == STCD_PRED_U8) {
     return __ldg(static_cast<const uint8_t*>(pred) + n * pix + i);
+  } else if (PK == STCD_PRED_U8_GE1) {
+    return __ldg(static_cast<const uint8_t*>(pred) + n * pix + i) >= 1 ? 1 : 0;
   } else if (PK == STCD_PRED_I32) {
     return __ldg(static_cast<const int32_t*>(pred) + n * pix + i);
   } else {
@@ -172,10 +174,13 @@ __device__ __forceinline__ void pred4_at(const void* pred, size_t n, size_t i, s
     const float x[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) out[j] = (PK == STCD_PRED_SIGMOID_GT) ? binarise_sigmoid_gt(x[j], thr) : (x[j] >= thr);
-  } else if (PK == STCD_PRED_U8) {
+  } else if (PK == STCD_PRED_U8 || PK == STCD_PRED_U8_GE1) {
     const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(pred) + n * pix + i));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[j] = (w >> (8 * j)) & 0xff;
+    for (int j = 0; j < 4; ++j) {
+      const int u = (w >> (8 * j)) & 0xff;
+      out[j] = (PK == STCD_PRED_U8_GE1) ? (u >= 1 ? 1 : 0) : u;
+    }
   } else if (PK == STCD_PRED_I32) {
     const int4 a = __ldg(reinterpret_cast<const int4*>(static_cast<const int32_t*>(pred) + n * pix + i));
     out[0] = a.x;
@@ -278,6 +283,19 @@ __global__ void __launch_bounds__(256) confusion2_kernel(const void* __restrict_
     unsigned long long s = 0;
     for (int w = 0; w < (blockDim.x >> 5); ++w) s += wsum[w][threadIdx.x];
     if (s) atomicAdd(cm + threadIdx.x, s);
+  }
+}
+
+// Pseudo-label masks (train_stcd.py:176-196): mask = on_value where the binarised prediction is 1, else 0.
+// HBM-bound: 4 (or 8) B read + 1 B written per pixel.
+template <int PK>
+__global__ void __launch_bounds__(256) binarise_mask_kernel(const void* __restrict__ logits, size_t n_img, size_t pix, float thr,
+                                                            int on_value, uint8_t* __restrict__ mask) {
+  const size_t ne = n_img * pix;
+  for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < ne;
+       e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t n = e / pix, i = e - n * pix;
+    mask[e] = pred_at<PK>(logits, n, i, pix, thr) ? static_cast<uint8_t>(on_value) : static_cast<uint8_t>(0);
   }
 }
 

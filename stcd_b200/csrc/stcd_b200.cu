@@ -1122,7 +1122,8 @@ int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const v
   if (!pred || !label || !cm_dev) return fail(STCD_ERR_INVALID, "NULL pointer");
   if (n_img < 0 || pix < 0) return fail(STCD_ERR_INVALID, "negative size");
   if (num_class < 2 || num_class > 32) return fail(STCD_ERR_INVALID, "num_class %d not in [2, 32]", num_class);
-  if (pred_kind < STCD_PRED_ARGMAX2 || pred_kind > STCD_PRED_I64) return fail(STCD_ERR_INVALID, "pred_kind %d", pred_kind);
+  if (pred_kind < STCD_PRED_ARGMAX2 || pred_kind > STCD_PRED_U8_GE1) return fail(STCD_ERR_INVALID, "pred_kind %d", pred_kind);
+  if (pred_kind == STCD_PRED_U8_GE1 && num_class != 2) return fail(STCD_ERR_INVALID, "raw mask predictions need num_class == 2");
   if (label_kind < STCD_LABEL_I64 || label_kind > STCD_LABEL_U8_GE1) return fail(STCD_ERR_INVALID, "label_kind %d", label_kind);
   if (num_class != 2 && pred_kind <= STCD_PRED_RAW_GE) return fail(STCD_ERR_INVALID, "binarising kinds need num_class == 2");
   if (n_img == 0 || pix == 0) return STCD_OK;
@@ -1158,6 +1159,7 @@ int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const v
       case STCD_PRED_RAW_GE: STCD_DISPATCH_L(STCD_CM2, STCD_PRED_RAW_GE); break;
       case STCD_PRED_U8: STCD_DISPATCH_L(STCD_CM2, STCD_PRED_U8); break;
       case STCD_PRED_I32: STCD_DISPATCH_L(STCD_CM2, STCD_PRED_I32); break;
+      case STCD_PRED_U8_GE1: STCD_DISPATCH_L(STCD_CM2, STCD_PRED_U8_GE1); break;
       default: STCD_DISPATCH_L(STCD_CM2, STCD_PRED_I64); break;
     }
   } else {
@@ -1166,6 +1168,29 @@ int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const v
       case STCD_PRED_I32: STCD_DISPATCH_L(STCD_CMK, STCD_PRED_I32); break;
       default: STCD_DISPATCH_L(STCD_CMK, STCD_PRED_I64); break;
     }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return STCD_OK;
+}
+
+int stcd_binarise_mask(const float* logits, int pred_kind, float thr, int64_t n_img, int64_t pix, int on_value, uint8_t* mask,
+                       void* stream) {
+  if (!logits || !mask) return fail(STCD_ERR_INVALID, "NULL pointer");
+  if (pred_kind < STCD_PRED_ARGMAX2 || pred_kind > STCD_PRED_RAW_GE) return fail(STCD_ERR_INVALID, "pred_kind %d does not binarise logits", pred_kind);
+  if (n_img < 0 || pix < 0 || on_value < 1 || on_value > 255) return fail(STCD_ERR_INVALID, "bad sizes / on_value");
+  if (n_img == 0 || pix == 0) return STCD_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(STCD_ERR_NO_DEVICE, "no CUDA device visible: libstcd_b200 has no CPU fallback");
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t ne = (size_t)n_img * pix;
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((ne + 255) / 256, 148 * 16));
+  switch (pred_kind) {
+    case STCD_PRED_ARGMAX2: stcd::binarise_mask_kernel<STCD_PRED_ARGMAX2><<<blocks, 256, 0, st>>>(logits, n_img, pix, thr, on_value, mask); break;
+    case STCD_PRED_SIGMOID_GT: stcd::binarise_mask_kernel<STCD_PRED_SIGMOID_GT><<<blocks, 256, 0, st>>>(logits, n_img, pix, thr, on_value, mask); break;
+    default: stcd::binarise_mask_kernel<STCD_PRED_RAW_GE><<<blocks, 256, 0, st>>>(logits, n_img, pix, thr, on_value, mask); break;
   }
   CUDA_TRY(cudaGetLastError());
   return STCD_OK;

@@ -24,7 +24,7 @@ import torch.nn as nn
 
 from . import _lib
 
-PRED_ARGMAX2, PRED_SIGMOID_GT, PRED_RAW_GE, PRED_U8, PRED_I32, PRED_I64 = range(6)
+PRED_ARGMAX2, PRED_SIGMOID_GT, PRED_RAW_GE, PRED_U8, PRED_I32, PRED_I64, PRED_U8_GE1 = range(7)
 LABEL_I64, LABEL_U8, LABEL_I32, LABEL_U8_GE1 = range(4)
 
 _PRED_KINDS = {torch.uint8: PRED_U8, torch.bool: PRED_U8, torch.int32: PRED_I32, torch.int64: PRED_I64}
@@ -74,10 +74,20 @@ class SegmentationMetric(nn.Module):
             t = t.to(self._cm.device, non_blocking=True)
         return t.contiguous()
 
-    def addBatch(self, imgPredict: torch.Tensor, imgLabel: torch.Tensor):
+    def addBatch(self, imgPredict: torch.Tensor, imgLabel: torch.Tensor, raw_masks: bool = False):
+        """train_stcd.py:586-588.  raw_masks=True: both arguments are uint8 mask images ({0, 255}, the pseudo-label
+        PNGs of train_stcd.py:185-196), binarised on the fly (>= 1 -> class 1) -- numClass must be 2."""
         assert imgPredict.shape == imgLabel.shape
         pred = self._to_dev(imgPredict)
         label = self._to_dev(imgLabel)
+        if raw_masks:
+            if pred.dtype != torch.uint8 or label.dtype != torch.uint8 or self.numClass != 2:
+                raise TypeError("raw_masks needs two uint8 mask images and numClass == 2")
+            _lib.check(_lib.lib().stcd_confusion_add_batch(
+                C.c_void_p(pred.data_ptr()), PRED_U8_GE1, 0.0, C.c_void_p(label.data_ptr()), LABEL_U8_GE1, 1, pred.numel(), 2,
+                C.c_void_p(self._cm.data_ptr()), None, _stream_ptr(pred)), "stcd_confusion_add_batch")
+            self.count += 1
+            return
         if pred.dtype not in _PRED_KINDS or label.dtype not in _LABEL_KINDS:
             raise TypeError(f"unsupported dtypes pred={pred.dtype} label={label.dtype}")
         if pred.dtype == torch.bool:
