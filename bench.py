@@ -50,6 +50,9 @@ WORKLOADS = {
                                input_sets=2,
                                desc="smp SegCD with the ResNet-50 encoder train_stcd.py:638 selects, 1024x1024 RGB pair tiles, "
                                     "batch 16 per GPU, bf16, + confusion matrix on sigmoid(change) > 0.5"),
+    "changegnn_v1_256_b32": dict(net="ChangeGNNV1", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=16,
+                                 desc="C4: ChangeGNNV1 (pyramid ViG Grapher encoder: dense kNN k=9 + max-relative graph conv, "
+                                      "multi-scale difference decoder) 256x256 RGB pairs, batch 32 per GPU, bf16"),
     "segcd_r34_256_b64": dict(net="SegCD", n_class=1, h=256, w=256, batch=64, kind="sigmoid", chunk=16,
                               desc="smp SegCD (Unet, ResNet-34 Siamese encoder) 256x256 RGB pairs, batch 64 per GPU, bf16"),
 }
@@ -61,6 +64,8 @@ def build_net(wl):
     from stcd_b200.networks import CLASSES
     if wl["net"] == "SegCD":
         return synth.prepare_(CLASSES["SegCD"](wl.get("encoder", "resnet34"), classes=wl["n_class"]).eval(), "SegCD")
+    if wl["net"] == "ChangeGNNV1":
+        return synth.prepare_(CLASSES["ChangeGNNV1"](3, wl["n_class"], embed_dim=256).eval(), "ChangeGNNV1")
     return synth.prepare_(CLASSES[wl["net"]](3, wl["n_class"]).eval(), wl["net"])
 
 
@@ -74,6 +79,8 @@ def oracle_forward(wl, sd, x1, x2):
         return nets.snunet_forward(sd, x1, x2)
     if wl["net"] == "SegCD":
         return nets.segcd_forward(sd, x1, x2)
+    if wl["net"] == "ChangeGNNV1":
+        return nets.changegnn_forward(sd, x1, x2)
     raise KeyError(wl["net"])
 
 

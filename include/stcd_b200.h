@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 8
+#define STCD_ABI_VERSION 9
 
 enum stcd_status {
   STCD_OK = 0,
@@ -131,7 +131,7 @@ typedef struct stcd_conv_desc {
   const float* shift;             /* HOST, [cout_pad] */
   const float* scale2;            /* HOST or NULL */
   const float* shift2;            /* HOST or NULL */
-  int32_t relu;
+  int32_t relu;                   /* activation: 0 none, 1 ReLU, 2 GELU (erf form, nn.GELU()), 3 PReLU with one slope act_alpha */
   int32_t res;                    /* tensor id or -1 */
   int32_t out0, out0_coff;        /* tensor id or -1; channel offset inside out0 */
   int32_t out_raw;                /* tensor id or -1 */
@@ -151,6 +151,10 @@ typedef struct stcd_conv_desc {
    * cout to 4*cout, which is what Cout <= 32 layers need (an SS-mode MMA costs the same for any N <= 64).
    * Only the affine + ReLU + out0 epilogue is available in this mode.  fold_cs % 16 == 0. */
   int32_t fold_cs, fold_cout;
+  /* act_pre = 1: the activation is applied BEFORE the second affine (conv -> PReLU/ReLU -> BatchNorm, the order of
+   * ChangeFormer.py:1138-1157 conv_diff / make_prediction) instead of at the end of the epilogue; needs scale2/shift2. */
+  int32_t act_pre;
+  float act_alpha;
 } stcd_conv_desc;
 
 /* returns op index >= 0, or <0 */
@@ -190,6 +194,17 @@ typedef struct stcd_seghead_desc {
   int32_t out_ext;
 } stcd_seghead_desc;
 int stcd_plan_add_seg_head(stcd_plan* plan, const stcd_seghead_desc* desc);
+
+/* The graph half of a ViG Grapher block on a plan tensor (gcn_lib DyGraphConv2d up to MRConv2d's aggregation; see
+ * stcd_knn_graph / stcd_max_relative below for the semantics): y = avg_pool2d(x, r) if r > 1 else x, dense dilated kNN
+ * graph of x over y with the relative-position bias, dst = bf16(max_k (y_j - x_i)).  src, dst: bf16 [imgs][c/8][h][w][8]
+ * with the same image multiplicity; relative_pos: HOST fp32 [h*w][h*w/r^2] or NULL, copied at add time. */
+int stcd_plan_add_graph_conv(stcd_plan* plan, int src_tensor, int dst_tensor, int c, int k, int dilation, int r,
+                             const float* relative_pos);
+
+/* F.interpolate(x, scale_factor=scale, mode="bilinear", align_corners=False) between two plan tensors
+ * (ChangeVIG.py:246-262); dst is [scale*h][scale*w], first c channels. */
+int stcd_plan_add_bilinear_up(stcd_plan* plan, int src_tensor, int dst_tensor, int c, int scale);
 
 /* SNUNet's ECAM tail (models/SNUNet.py:144-149: two ChannelAttention blocks :46-59 + conv_final)
  * over four activation tensors of `c` channels each, as one fused op writing external output

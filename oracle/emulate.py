@@ -61,12 +61,19 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
                 full[m] = acc          # columns = (phase, channel): scattered to pixels by the store below
             else:
                 full[m][:, ph.oy::op.osy, ph.ox::op.osx] = acc
+    def act(v):
+        if op.act_kind == 1:
+            return torch.relu(v)
+        if op.act_kind == 2:
+            return torch.nn.functional.gelu(v)
+        if op.act_kind == 3:
+            return torch.where(v >= 0, v, v * op.act_alpha)
+        return v
+
     if op.fold_cs:
-        # phases folded into N: affine (+ReLU) per column, then column block p -> output pixel phase p
+        # phases folded into N: affine (+activation) per column, then column block p -> output pixel phase p
         for m in range(n_m):
-            v = full[m] * scale + shift
-            if op.relu:
-                v = torch.relu(v)
+            v = act(full[m] * scale + shift)
             sl = slice(m * chunk, m * chunk + n_img)
             for p_ in range(op.osy * op.osx):
                 q = _bf16(v[..., p_ * op.fold_cs: p_ * op.fold_cs + op.fold_cout])
@@ -79,11 +86,13 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
         if op.out_raw is not None:
             T[op.out_raw][sl, :, :, : op.cout] = _bf16(v[..., : op.cout])
         if op.scale2 is not None:
+            if op.act_pre:
+                v = act(v)
             v = v * torch.from_numpy(op.scale2) + torch.from_numpy(op.shift2)
         if op.res is not None:
             v[..., : op.cout] = v[..., : op.cout] + T[op.res][sl, :, :, : op.cout]
-        if op.relu:
-            v = torch.relu(v)
+        if not op.act_pre:
+            v = act(v)
         if op.out0 is not None and op.out0_s2d:
             # space-to-depth store: pixel (y, x), channel c -> pixel (y//2, x//2), channel ((y%2)*2 + x%2)*cout + c
             q = _bf16(v[..., : op.cout])
@@ -126,6 +135,8 @@ def run_program(prog: L.Program, x1: torch.Tensor, x2: torch.Tensor, chunk: int 
     for start in range(0, n, chunk):
         nv = min(chunk, n - start)
         T = {name: torch.zeros(t.mult * chunk, t.h, t.w, t.c) for name, t in prog.tensors.items()}
+        for name, val in prog.consts.items():
+            T[name][..., : val.shape[2]] = _bf16(val)[None]
         ext = [torch.zeros(chunk, e.channels, e.h, e.w) for e in prog.ext]
         for op in prog.ops:
             if isinstance(op, L.InputPackSpec) and op.s2d:
@@ -204,7 +215,30 @@ def run_seg_head(op: L.SegHeadSpec, T: Dict[str, torch.Tensor], chunk: int, ext:
     ext[op.out_ext + 2][:nv] = change[:nv]
 
 
+def run_graph_conv(op: L.GraphConvSpec, T: Dict[str, torch.Tensor]) -> None:
+    """csrc/graph_kernels.cuh on a bf16 tensor: fp32 kNN graph + max-relative, rounded to bf16 on store."""
+    from oracle import gcn
+    x = T[op.src][..., : op.c].permute(0, 3, 1, 2).contiguous()                  # [imgs, c, h, w]
+    b, c, h, w = x.shape
+    y = torch.nn.functional.avg_pool2d(x, op.r, op.r).reshape(b, c, -1, 1) if op.r > 1 else None
+    xn = x.reshape(b, c, -1, 1)
+    rp = None if op.relpos is None else torch.from_numpy(op.relpos)[None]
+    e = gcn.dense_dilated_knn_graph(xn, y, op.k, op.dilation, rp)
+    m = gcn.max_relative(xn, e, y).reshape(b, c, h, w)
+    T[op.dst][..., : op.c] = _bf16(m.permute(0, 2, 3, 1))
+
+
+def run_bilinear_up(op: L.BilinearUpSpec, T: Dict[str, torch.Tensor]) -> None:
+    x = T[op.src][..., : op.c].permute(0, 3, 1, 2)
+    y = torch.nn.functional.interpolate(x, scale_factor=op.scale, mode="bilinear", align_corners=False)
+    T[op.dst][..., : op.c] = _bf16(y.permute(0, 2, 3, 1))
+
+
 def run_aux(op, T, chunk, ext, nv):
+    if isinstance(op, L.GraphConvSpec):
+        return run_graph_conv(op, T)
+    if isinstance(op, L.BilinearUpSpec):
+        return run_bilinear_up(op, T)
     if isinstance(op, L.EcamHeadSpec):
         return run_ecam_head(op, T, chunk, ext, nv)
     if isinstance(op, L.MaxPoolS2DSpec):

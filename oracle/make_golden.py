@@ -27,6 +27,9 @@ CASES = {
     "segcd_r34": ("segmentation_models_pytorch", "SegCD", ("resnet34", 5, None), 2, 64, 96),
     # smp.SegCD("resnet50"): the encoder train_stcd.py:638 selects (Bottleneck blocks)
     "segcd_r50": ("segmentation_models_pytorch", "SegCD", ("resnet50", 5, None), 1, 64, 64),
+    # ChangeGNNV1 runs only at its img_size (pos_embed is not resized); gcn_lib comes from oracle/gcn_lib_restated.py
+    # (absent upstream dependency: this fixture pins everything EXCEPT the Grapher restatement itself)
+    "changegnn_v1": ("models.ChangeVIG", "ChangeGNNV1", (3, 2, False, 256), 1, 256, 256),
 }
 
 

@@ -168,3 +168,97 @@ def segcd_forward(sd: SD, A: torch.Tensor, B: torch.Tensor, layers=(3, 4, 6, 3))
     m1, m2 = head(d1), head(d2)
     change = torch.min(head(torch.abs(d1 - d2)), torch.abs(m1 - m2))
     return m1, m2, change
+
+
+# ------------------------------------------------------------------------------------------
+# ChangeGNNV1 (ViG pyramid encoder + multi-scale difference decoder)
+def _conv_bn(sd: SD, pre: str, x: torch.Tensor, stride: int = 1, padding: int = 0) -> torch.Tensor:
+    """nn.Sequential(Conv2d, BatchNorm2d) as registered under `pre`.0 / `pre`.1."""
+    return _bn(sd, f"{pre}.1", F.conv2d(x, sd[f"{pre}.0.weight"], sd.get(f"{pre}.0.bias"), stride=stride, padding=padding))
+
+
+def _grapher(sd: SD, pre: str, x: torch.Tensor, k: int, dilation: int, r: int) -> torch.Tensor:
+    """gcn_lib Grapher.forward (absent from the reference tree: SURVEY App. D, oracle/gcn_lib_restated.py)."""
+    from oracle import gcn
+    t = x
+    x = _conv_bn(sd, f"{pre}.fc1", x)
+    b, c, h, w = x.shape
+    y = F.avg_pool2d(x, r, r).reshape(b, c, -1, 1) if r > 1 else None
+    xn = x.reshape(b, c, -1, 1)
+    e = gcn.dense_dilated_knn_graph(xn, y, k, dilation, sd.get(f"{pre}.relative_pos"))
+    z = gcn.mr_features(xn, e, y)
+    g = f"{pre}.graph_conv.gconv.nn"
+    z = F.gelu(_bn(sd, f"{g}.1", F.conv2d(z, sd[f"{g}.0.weight"], sd.get(f"{g}.0.bias"), groups=4)))
+    x = _conv_bn(sd, f"{pre}.fc2", z.reshape(b, 2 * c, h, w))
+    return x + t
+
+
+def _ffn(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """models/pyramid_vig.py:41-63."""
+    return _conv_bn(sd, f"{pre}.fc2", F.gelu(_conv_bn(sd, f"{pre}.fc1", x))) + x
+
+
+def vig_encoder_features(sd: SD, x: torch.Tensor, blocks=(2, 2, 6, 2), k: int = 9, pre: str = "encoder") -> List[torch.Tensor]:
+    """EncoderV1.forward_features, models/ChangeVIG.py:85-94 (Stem / Downsample: pyramid_vig.py:66-100)."""
+    s = f"{pre}.stem.convs"
+    x = F.gelu(_bn(sd, f"{s}.1", F.conv2d(x, sd[f"{s}.0.weight"], sd[f"{s}.0.bias"], stride=2, padding=1)))
+    x = F.gelu(_bn(sd, f"{s}.4", F.conv2d(x, sd[f"{s}.3.weight"], sd[f"{s}.3.bias"], stride=2, padding=1)))
+    x = _bn(sd, f"{s}.7", F.conv2d(x, sd[f"{s}.6.weight"], sd[f"{s}.6.bias"], padding=1))
+    x = x + sd[f"{pre}.pos_embed"]
+    max_dilation = 49 // k
+    reduce_ratios = (4, 2, 1, 1)
+    outs, bi, idx = [], 0, 0
+    for i, n in enumerate(blocks):
+        if i > 0:
+            x = _conv_bn(sd, f"{pre}.backbone.{bi}.conv", x, stride=2, padding=1)
+            bi += 1
+        for _ in range(n):
+            x = _grapher(sd, f"{pre}.backbone.{bi}.0", x, k, min(idx // 4 + 1, max_dilation), reduce_ratios[i])
+            x = _ffn(sd, f"{pre}.backbone.{bi}.1", x)
+            bi += 1
+            idx += 1
+        outs.append(x)
+    return outs
+
+
+def changegnn_decoder(sd: SD, f1: List[torch.Tensor], f2: List[torch.Tensor], pre: str = "decoder") -> List[torch.Tensor]:
+    """DecoderV1.forward with decoder_heads="MLP", models/ChangeVIG.py:192-281."""
+    def mlp(k, t):          # MLP: per-pixel Linear (ChangeFormer.py:677-688)
+        return F.conv2d(t, sd[f"{pre}.decoder_heads_c{k}.proj.weight"][:, :, None, None], sd[f"{pre}.decoder_heads_c{k}.proj.bias"])
+
+    def diff(k, t):         # conv_diff: conv, PReLU, BN, (dropout,) conv, PReLU, BN (ChangeFormer.py:1138-1148)
+        d = f"{pre}.diff_c{k}"
+        t = _bn(sd, f"{d}.2", F.prelu(F.conv2d(t, sd[f"{d}.0.weight"], sd[f"{d}.0.bias"], padding=1), sd[f"{d}.1.weight"]))
+        return _bn(sd, f"{d}.6", F.prelu(F.conv2d(t, sd[f"{d}.4.weight"], sd[f"{d}.4.bias"], padding=1), sd[f"{d}.5.weight"]))
+
+    def pred(k, t):         # make_prediction: conv, ReLU, BN, conv (ChangeFormer.py:1151-1157)
+        m = f"{pre}.make_pred_c{k}"
+        t = _bn(sd, f"{m}.2", F.relu(F.conv2d(t, sd[f"{m}.0.weight"], sd[f"{m}.0.bias"], padding=1)))
+        return F.conv2d(t, sd[f"{m}.3.weight"], sd[f"{m}.3.bias"], padding=1)
+
+    def resblock(name, t):  # ResidualBlock (ChangeFormerBaseNetworks.py:108-120)
+        o = F.relu(F.conv2d(t, sd[f"{name}.conv1.conv2d.weight"], sd[f"{name}.conv1.conv2d.bias"], padding=1))
+        return F.conv2d(o, sd[f"{name}.conv2.conv2d.weight"], sd[f"{name}.conv2.conv2d.bias"], padding=1) * 0.1 + t
+
+    size = f1[0].shape[2:]
+    outs, ups, c_prev = [], [], None
+    for k in (4, 3, 2, 1):
+        a, b = f1[k - 1], f2[k - 1]
+        c = diff(k, torch.cat((mlp(k, a), mlp(k, b)), dim=1))
+        if c_prev is not None:
+            c = c + F.interpolate(c_prev, scale_factor=2, mode="bilinear")
+        outs.append(pred(k, c))
+        ups.append(c if k == 1 else F.interpolate(c, size=size, mode="bilinear", align_corners=False))
+        c_prev = c
+    x = _conv_bn(sd, f"{pre}.linear_fuse", torch.cat(ups, dim=1))
+    x = F.conv_transpose2d(x, sd[f"{pre}.convd2x.conv2d.weight"], sd[f"{pre}.convd2x.conv2d.bias"], stride=2, padding=1)
+    x = resblock(f"{pre}.dense_2x.0", x)
+    x = F.conv_transpose2d(x, sd[f"{pre}.convd1x.conv2d.weight"], sd[f"{pre}.convd1x.conv2d.bias"], stride=2, padding=1)
+    x = resblock(f"{pre}.dense_1x.0", x)
+    outs.append(F.conv2d(x, sd[f"{pre}.change_probability.conv2d.weight"], sd[f"{pre}.change_probability.conv2d.bias"], padding=1))
+    return outs
+
+
+def changegnn_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor) -> List[torch.Tensor]:
+    """ChangeGNNV1.forward, models/ChangeVIG.py:309-312: list of 5 tensors, full-resolution logits last."""
+    return changegnn_decoder(sd, vig_encoder_features(sd, x1), vig_encoder_features(sd, x2))

@@ -121,6 +121,9 @@ def install() -> None:
     finder = _StubFinder()
     finder.PREFIXES = tuple(p for p in _StubFinder.PREFIXES if p not in have_real)
     sys.meta_path.insert(0, finder)
+    if "gcn_lib" not in sys.modules:      # absent from the reference tree: the restated stand-in (parity unpinned)
+        from oracle import gcn_lib_restated
+        sys.modules["gcn_lib"] = gcn_lib_restated
     _installed = True
 
 

@@ -106,6 +106,7 @@ class ConvDesc(C.Structure):
         ("out_ext", C.c_int32),
         ("out0_s2d", C.c_int32),
         ("fold_cs", C.c_int32), ("fold_cout", C.c_int32),
+        ("act_pre", C.c_int32), ("act_alpha", C.c_float),
     ]
 
 
@@ -125,7 +126,7 @@ class EcamDesc(C.Structure):
     ]
 
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -141,6 +142,8 @@ SYMBOLS = [
     ("stcd_plan_add_input_pack_u8", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("stcd_plan_add_maxpool_s2d", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("stcd_plan_add_seg_head", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("stcd_plan_add_graph_conv", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    ("stcd_plan_add_bilinear_up", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("stcd_plan_add_ecam_head", C.c_int, [C.c_void_p, C.c_void_p]),
     ("stcd_plan_finalize", C.c_int, [C.c_void_p]),
     ("stcd_plan_tensor_copy", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int]),

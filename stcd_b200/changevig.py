@@ -1,0 +1,402 @@
+"""ChangeGNNV1 (ViG pyramid Siamese encoder + multi-scale difference decoder) behind ``net_G(x1, x2)``.
+
+Drop-in for ``models/ChangeVIG.py::ChangeGNNV1`` (registry key ``ChangeGNNV1``, models/networks.py:196-198): same
+constructor arguments, the reference's parameter names (a reference ``state_dict`` loads; the Grapher sub-module names
+follow upstream ``gcn_lib``, which the reference imports but does not ship -- SURVEY.md App. D), same return value: a
+list of five tensors ``[B,2,8,8] .. [B,2,64,64], [B,2,256,256]`` with the full-resolution logits last.
+
+Lowering (eval mode; both temporal images ride through every encoder launch as Siamese pair tiles):
+
+* Stem (pyramid_vig.py:66-83): 3x3 stride-2 convs read space-to-depth tensors (the image is packed space-to-depth, the
+  first conv stores its output space-to-depth); BN + GELU fold into the epilogue; ``+ pos_embed`` is a residual read.
+* Grapher (gcn_lib): fc1 (1x1 + BN) -> GRAPH OP (avg-pool by r, dense dilated kNN with the relative-position bias,
+  max-relative aggregation: csrc/graph_kernels.cuh) -> the grouped 1x1 conv over the interleaved (x, m) as a dense conv
+  over the virtual concat [x, m] with the group structure and the interleave folded into the packed weights, BN + GELU
+  in the epilogue -> fc2 (1x1 + BN) + residual.
+* FFN (pyramid_vig.py:41-63): two 1x1 convs, GELU and the residual in the epilogues.  The last block of stages 1-3 is
+  stored twice: plainly for the decoder and space-to-depth for the stride-2 Downsample conv.
+* DecoderV1 (ChangeVIG.py:192-281): per-pixel Linear heads as 1x1 convs; ``conv_diff`` reads ``cat(_c_1, _c_2)`` as two
+  stream segments (never materialised), conv -> PReLU -> BN runs as (bias, PReLU, second affine) in one epilogue, the
+  coarser scale's bilinear x2 is a residual read; bilinear resizes are one bandwidth kernel; ConvTranspose2d(k4, s2) runs
+  as 4 output phases; ResidualBlock's ``* 0.1 + x`` is an epilogue affine + residual.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import lowering as L
+from .module import PlannedModule
+
+_CHANNELS = (80, 160, 400, 640)
+_BLOCKS = (2, 2, 6, 2)
+_REDUCE = (4, 2, 1, 1)
+_K = 9
+
+
+def _relative_pos(c: int, n: int, r: int) -> torch.Tensor:
+    """gcn_lib Grapher's relative_pos parameter: -bicubic(2 E E^T / C) with E the 2-D sin-cos embedding (App. D)."""
+    g = int(n ** 0.5)
+
+    def sincos(d, pos):
+        omega = 1.0 / 10000 ** (np.arange(d // 2, dtype=np.float64) / (d / 2.0))
+        out = np.einsum("m,d->md", pos.reshape(-1), omega)
+        return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+
+    grid = np.stack(np.meshgrid(np.arange(g, dtype=np.float32), np.arange(g, dtype=np.float32)), axis=0).reshape(2, 1, g, g)
+    emb = np.concatenate([sincos(c // 2, grid[0]), sincos(c // 2, grid[1])], axis=1)
+    rel = torch.from_numpy(np.float32(2 * emb @ emb.T / emb.shape[1]))[None, None]
+    rel = torch.nn.functional.interpolate(rel, size=(n, n // (r * r)), mode="bicubic", align_corners=False)
+    return -rel.squeeze(1)
+
+
+class _MRConv(nn.Module):
+    def __init__(self, c: int):
+        super().__init__()
+        self.nn = nn.Sequential(nn.Conv2d(2 * c, 2 * c, 1, bias=True, groups=4), nn.BatchNorm2d(2 * c), nn.GELU())
+
+
+class _DyGraphConv(nn.Module):
+    def __init__(self, c: int):
+        super().__init__()
+        self.gconv = _MRConv(c)
+
+
+class _Grapher(nn.Module):
+    def __init__(self, c: int, k: int, dilation: int, r: int, n: int):
+        super().__init__()
+        self.k, self.dilation, self.r, self.n = k, dilation, r, n
+        self.fc1 = nn.Sequential(nn.Conv2d(c, c, 1), nn.BatchNorm2d(c))
+        self.graph_conv = _DyGraphConv(c)
+        self.fc2 = nn.Sequential(nn.Conv2d(2 * c, c, 1), nn.BatchNorm2d(c))
+        self.relative_pos = nn.Parameter(_relative_pos(c, n, r), requires_grad=False)
+
+
+class _FFN(nn.Module):
+    def __init__(self, c: int):
+        super().__init__()
+        self.fc1 = nn.Sequential(nn.Conv2d(c, 4 * c, 1), nn.BatchNorm2d(4 * c))
+        self.act = nn.GELU()
+        self.fc2 = nn.Sequential(nn.Conv2d(4 * c, c, 1), nn.BatchNorm2d(c))
+
+
+class _Stem(nn.Module):
+    def __init__(self, c: int):
+        super().__init__()
+        self.convs = nn.Sequential(nn.Conv2d(3, c // 2, 3, stride=2, padding=1), nn.BatchNorm2d(c // 2), nn.GELU(),
+                                   nn.Conv2d(c // 2, c, 3, stride=2, padding=1), nn.BatchNorm2d(c), nn.GELU(),
+                                   nn.Conv2d(c, c, 3, stride=1, padding=1), nn.BatchNorm2d(c))
+
+
+class _Downsample(nn.Module):
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.conv = nn.Sequential(nn.Conv2d(cin, cout, 3, stride=2, padding=1), nn.BatchNorm2d(cout))
+
+
+class _EncoderV1(nn.Module):
+    """models/ChangeVIG.py:26-97 (parameters only)."""
+
+    def __init__(self, img_size: int):
+        super().__init__()
+        self.stem = _Stem(_CHANNELS[0])
+        self.pos_embed = nn.Parameter(torch.zeros(1, _CHANNELS[0], img_size // 4, img_size // 4))
+        hw = (img_size // 4) ** 2
+        max_dilation = 49 // _K
+        mods: List[nn.Module] = []
+        idx = 0
+        for i, n_blocks in enumerate(_BLOCKS):
+            if i > 0:
+                mods.append(_Downsample(_CHANNELS[i - 1], _CHANNELS[i]))
+                hw //= 4
+            for _ in range(n_blocks):
+                mods.append(nn.Sequential(_Grapher(_CHANNELS[i], _K, min(idx // 4 + 1, max_dilation), _REDUCE[i], hw),
+                                          _FFN(_CHANNELS[i])))
+                idx += 1
+        self.backbone = nn.Sequential(*mods)
+
+
+class _MLP(nn.Module):
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.proj = nn.Linear(cin, cout)
+
+
+def _conv_diff(cin: int, cout: int) -> nn.Sequential:
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1), nn.PReLU(), nn.BatchNorm2d(cout), nn.Dropout(p=0.6),
+                         nn.Conv2d(cout, cout, 3, padding=1), nn.PReLU(), nn.BatchNorm2d(cout), nn.Dropout(p=0.6))
+
+
+def _make_prediction(cin: int, cout: int) -> nn.Sequential:
+    return nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1), nn.ReLU(), nn.BatchNorm2d(cout), nn.Conv2d(cout, cout, 3, padding=1))
+
+
+class _ConvLayer(nn.Module):
+    def __init__(self, cin, cout, k, stride, padding):
+        super().__init__()
+        self.conv2d = nn.Conv2d(cin, cout, k, stride, padding)
+
+
+class _UpsampleConvLayer(nn.Module):
+    def __init__(self, cin, cout, k, stride):
+        super().__init__()
+        self.conv2d = nn.ConvTranspose2d(cin, cout, k, stride=stride, padding=1)
+
+
+class _ResidualBlock(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = _ConvLayer(c, c, 3, 1, 1)
+        self.conv2 = _ConvLayer(c, c, 3, 1, 1)
+        self.relu = nn.ReLU()
+
+
+class _DecoderV1(nn.Module):
+    """models/ChangeVIG.py:100-165 with decoder_heads="MLP"."""
+
+    def __init__(self, in_channels, e: int, output_nc: int):
+        super().__init__()
+        c1, c2, c3, c4 = in_channels
+        self.decoder_heads_c4, self.decoder_heads_c3 = _MLP(c4, e), _MLP(c3, e)
+        self.decoder_heads_c2, self.decoder_heads_c1 = _MLP(c2, e), _MLP(c1, e)
+        for k in (4, 3, 2, 1):
+            setattr(self, f"diff_c{k}", _conv_diff(2 * e, e))
+        for k in (4, 3, 2, 1):
+            setattr(self, f"make_pred_c{k}", _make_prediction(e, output_nc))
+        self.linear_fuse = nn.Sequential(nn.Conv2d(e * 4, e, 1), nn.BatchNorm2d(e))
+        self.convd2x = _UpsampleConvLayer(e, e, 4, 2)
+        self.dense_2x = nn.Sequential(_ResidualBlock(e))
+        self.convd1x = _UpsampleConvLayer(e, e, 4, 2)
+        self.dense_1x = nn.Sequential(_ResidualBlock(e))
+        self.change_probability = _ConvLayer(e, output_nc, 3, 1, 1)
+        self.active = nn.Sigmoid()
+
+
+class ChangeGNNV1(PlannedModule):
+    """models/ChangeVIG.py:284-312."""
+    default_chunk_pairs = 16
+
+    def __init__(self, input_nc: int = 3, output_nc: int = 2, decoder_softmax: bool = False, embed_dim: int = 256,
+                 decoder_heads: str = "MLP", img_size: int = 256):
+        super().__init__()
+        if input_nc != 3:
+            raise NotImplementedError("ChangeGNNV1's Stem is hard-wired to 3 input channels (pyramid_vig.py:70)")
+        if decoder_softmax or decoder_heads != "MLP":
+            raise NotImplementedError("stcd_b200.ChangeGNNV1 serves decoder_heads='MLP', decoder_softmax=False (networks.py:197)")
+        if output_nc > 8 or embed_dim % 16:
+            raise NotImplementedError("output_nc <= 8, embed_dim a multiple of 16")
+        self.embed_dims = list(_CHANNELS)
+        self.embedding_dim = embed_dim
+        self.output_nc = output_nc
+        self.img_size = img_size
+        self.encoder = _EncoderV1(img_size)
+        self.decoder = _DecoderV1(_CHANNELS, embed_dim, output_nc)
+        for m in self.encoder.modules():            # EncoderV1.model_init, ChangeVIG.py:76-83
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight)
+                if m.bias is not None:
+                    m.bias.data.zero_()
+
+    def lower(self, h: int, w: int) -> L.Program:
+        return lower_changegnn(self.state_dict(), self.embedding_dim, self.output_nc, self.img_size, h, w)
+
+    @torch.no_grad()
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor):
+        return self.plan_for(x1).forward(x1, x2)        # list of 5, full-resolution logits last (evaluator.py:176 takes [-1])
+
+    def _wrap_outputs(self, outs):
+        return list(outs)
+
+
+# ------------------------------------------------------------------------------------------
+def _s2d_input_taps(weight: torch.Tensor, pad: int) -> List:
+    """A stride-2 conv over the image == a stride-1 conv over its space-to-depth packing (channel (py*2+px)*cin + c):
+    kernel row ky reads input row 2i + ky - pad = 2(i + dy) + py."""
+    cout, cin, k, _ = weight.shape
+    taps = {}
+    for ky in range(k):
+        dy, py = divmod(ky - pad, 2)
+        for kx in range(k):
+            dx, px = divmod(kx - pad, 2)
+            wt = taps.setdefault((dy, dx), torch.zeros(cout, 4 * cin, dtype=torch.float32))
+            wt[:, (py * 2 + px) * cin: (py * 2 + px + 1) * cin] = weight[:, :, ky, kx].to(torch.float32)
+    return [(0, 0, [(dy, dx, wt) for (dy, dx), wt in sorted(taps.items())])]
+
+
+def lower_changegnn(sd: Dict[str, torch.Tensor], e: int, n_class: int, img_size: int, h: int, w: int) -> L.Program:
+    """state_dict of the reference ChangeGNNV1 -> fused-op Program (eval mode)."""
+    if h != img_size or w != img_size:
+        # pos_embed is [1, C, img/4, img/4] and is added without resizing (ChangeVIG.py:87): the net only runs at img_size
+        raise ValueError(f"ChangeGNNV1 was built for {img_size}x{img_size} inputs (its pos_embed is not resized), got {h}x{w}")
+    if h % 32:
+        raise ValueError("img_size must be a multiple of 32")
+    sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
+    p = L.Program(model="ChangeGNNV1", in_channels=3, h=h, w=w)
+    ones = lambda c: np.ones(c, np.float32)  # noqa: E731
+    npf = lambda t: t.numpy().astype(np.float32)  # noqa: E731
+
+    def conv_bn(pre: str, cout: int):
+        return L.fold_bn(sd.get(f"{pre}.0.bias"), L.bn_params(sd, f"{pre}.1"), cout)
+
+    # ---------------- Stem
+    c0 = _CHANNELS[0]
+    hh, ww = h // 2, w // 2
+    p.tensor("in", 2, hh, ww, 16)
+    p.ops.append(L.InputPackSpec("pack", "in", 3, s2d=True))
+    s = "encoder.stem.convs"
+    t0 = p.tensor("stem.t0_s2d", 2, hh // 2, ww // 2, 4 * (c0 // 2))
+    sc, sh = L.fold_bn(sd[f"{s}.0.bias"], L.bn_params(sd, f"{s}.1"), c0 // 2)
+    L.add_conv(p, f"{s}.0", [L.Segment("in", 12)], _s2d_input_taps(sd[f"{s}.0.weight"], 1), c0 // 2, hh, ww, 1, sc, sh, pair=True,
+               act="gelu", out0=t0, out0_s2d=True, macs_per_pair=2 * hh * ww * 27 * (c0 // 2))
+    hh, ww = hh // 2, ww // 2
+    t1 = p.tensor("stem.t1", 2, hh, ww, c0)
+    sc, sh = L.fold_bn(sd[f"{s}.3.bias"], L.bn_params(sd, f"{s}.4"), c0)
+    L.add_conv(p, f"{s}.3", L.s2d_segments(t0, c0 // 2), [(0, 0, L.s2d_conv_taps(sd[f"{s}.3.weight"], pad=1))], c0, hh, ww, 1, sc, sh,
+               pair=True, act="gelu", out0=t1, macs_per_pair=2 * hh * ww * 9 * (c0 // 2) * c0)
+    pos = p.tensor("pos_embed", 2, hh, ww, c0)
+    p.consts[pos] = sd["encoder.pos_embed"][0].permute(1, 2, 0).contiguous()
+    x = p.tensor("stem.out", 2, hh, ww, c0)
+    sc, sh = L.fold_bn(sd[f"{s}.6.bias"], L.bn_params(sd, f"{s}.7"), c0)
+    L.add_conv(p, f"{s}.6", [L.Segment(t1, c0)], L.conv_taps(sd[f"{s}.6.weight"], pad=1), c0, hh, ww, 1, sc, sh, pair=True, res=pos,
+               out0=x, macs_per_pair=2 * hh * ww * 9 * c0 * c0)
+
+    # ---------------- ViG pyramid
+    feats = []                    # (tensor, channels, h, w) per stage, plain layout
+    max_dilation = 49 // _K
+    bi = idx = 0
+    x_s2d = None
+    for i, n_blocks in enumerate(_BLOCKS):
+        c = _CHANNELS[i]
+        if i > 0:
+            pre = f"encoder.backbone.{bi}.conv"
+            cprev = _CHANNELS[i - 1]
+            hh, ww = hh // 2, ww // 2
+            x = p.tensor(f"down{i}", 2, hh, ww, c)
+            sc, sh = conv_bn(pre, c)
+            L.add_conv(p, pre, L.s2d_segments(x_s2d, cprev), [(0, 0, L.s2d_conv_taps(sd[f"{pre}.0.weight"], pad=1))], c, hh, ww, 1,
+                       sc, sh, pair=True, out0=x, macs_per_pair=2 * hh * ww * 9 * cprev * c)
+            bi += 1
+        for b in range(n_blocks):
+            g, f = f"encoder.backbone.{bi}.0", f"encoder.backbone.{bi}.1"
+            dil = min(idx // 4 + 1, max_dilation)
+            r = _REDUCE[i]
+            # ---- Grapher
+            x1 = p.tensor(f"{g}.x1", 2, hh, ww, c)
+            sc, sh = conv_bn(f"{g}.fc1", c)
+            L.add_conv(p, f"{g}.fc1", [L.Segment(x, c)], L.conv_taps(sd[f"{g}.fc1.0.weight"], pad=0), c, hh, ww, 1, sc, sh, pair=True,
+                       out0=x1, macs_per_pair=2 * hh * ww * c * c)
+            m = p.tensor(f"{g}.m", 2, hh, ww, c)
+            rp = sd.get(f"{g}.relative_pos")
+            n, mk = hh * ww, hh * ww // (r * r)
+            if rp is not None and tuple(rp.shape[1:]) != (n, mk):
+                rp = torch.nn.functional.interpolate(rp.unsqueeze(0), size=(n, mk), mode="bicubic").squeeze(0)
+            p.ops.append(L.GraphConvSpec(f"{g}.graph", x1, m, c, _K, dil, r, None if rp is None else npf(rp[0]),
+                                         macs_per_pair=2 * n * mk * c))
+            # grouped 1x1 conv (groups=4) over the interleaved z = (x0, m0, x1, m1, ...): dense weights over [x, m]
+            wg = sd[f"{g}.graph_conv.gconv.nn.0.weight"][:, :, 0, 0]            # [2c, 2c/4]
+            dense = torch.zeros(2 * c, 2 * c)
+            per = 2 * c // 4
+            for grp in range(4):
+                dense[grp * per:(grp + 1) * per, grp * per:(grp + 1) * per] = wg[grp * per:(grp + 1) * per]
+            wx, wm = dense[:, 0::2], dense[:, 1::2]                                 # z[2j] = x[j], z[2j+1] = m[j]
+            gz = p.tensor(f"{g}.gz", 2, hh, ww, 2 * c)
+            sc, sh = L.fold_bn(sd.get(f"{g}.graph_conv.gconv.nn.0.bias"), L.bn_params(sd, f"{g}.graph_conv.gconv.nn.1"), 2 * c)
+            L.add_conv(p, f"{g}.graph_conv.nn", [L.Segment(x1, c), L.Segment(m, c)],
+                       [(0, 0, [(0, 0, torch.cat([wx, wm], 1))])], 2 * c, hh, ww, 1, sc, sh, pair=True, act="gelu", out0=gz,
+                       macs_per_pair=2 * hh * ww * 2 * c * (2 * c // 4))
+            xg = p.tensor(f"{g}.out", 2, hh, ww, c)
+            sc, sh = conv_bn(f"{g}.fc2", c)
+            L.add_conv(p, f"{g}.fc2", [L.Segment(gz, 2 * c)], L.conv_taps(sd[f"{g}.fc2.0.weight"], pad=0), c, hh, ww, 1, sc, sh,
+                       pair=True, res=x, out0=xg, macs_per_pair=2 * hh * ww * 2 * c * c)
+            # ---- FFN
+            hdn = p.tensor(f"{f}.h", 2, hh, ww, 4 * c)
+            sc, sh = conv_bn(f"{f}.fc1", 4 * c)
+            L.add_conv(p, f"{f}.fc1", [L.Segment(xg, c)], L.conv_taps(sd[f"{f}.fc1.0.weight"], pad=0), 4 * c, hh, ww, 1, sc, sh,
+                       pair=True, act="gelu", out0=hdn, macs_per_pair=2 * hh * ww * c * 4 * c)
+            x = p.tensor(f"{f}.out", 2, hh, ww, c)
+            sc, sh = conv_bn(f"{f}.fc2", c)
+            L.add_conv(p, f"{f}.fc2", [L.Segment(hdn, 4 * c)], L.conv_taps(sd[f"{f}.fc2.0.weight"], pad=0), c, hh, ww, 1, sc, sh,
+                       pair=True, res=xg, out0=x, macs_per_pair=2 * hh * ww * 4 * c * c)
+            if b == n_blocks - 1 and i < 3:
+                # the stage output also feeds the stride-2 Downsample: second, space-to-depth copy of the same conv
+                x_s2d = p.tensor(f"{f}.out_s2d", 2, hh // 2, ww // 2, 4 * c)
+                L.add_conv(p, f"{f}.fc2.s2d", [L.Segment(hdn, 4 * c)], L.conv_taps(sd[f"{f}.fc2.0.weight"], pad=0), c, hh, ww, 1,
+                           sc, sh, pair=True, res=xg, out0=x_s2d, out0_s2d=True, macs_per_pair=0)
+            bi += 1
+            idx += 1
+        feats.append((x, c, hh, ww))
+
+    # ---------------- DecoderV1
+    d = "decoder"
+    full_h, full_w = feats[0][2], feats[0][3]
+    c_prev = None
+    ups = []
+    for k in (4, 3, 2, 1):
+        ft, fc, fh, fw = feats[k - 1]
+        hd = p.tensor(f"{d}.c{k}", 2, fh, fw, e)
+        wl = sd[f"{d}.decoder_heads_c{k}.proj.weight"][:, :, None, None]
+        L.add_conv(p, f"{d}.decoder_heads_c{k}", [L.Segment(ft, fc)], L.conv_taps(wl, pad=0), e, fh, fw, 1, ones(e),
+                   npf(sd[f"{d}.decoder_heads_c{k}.proj.bias"]), pair=True, out0=hd, macs_per_pair=2 * fh * fw * fc * e)
+        dk = f"{d}.diff_c{k}"
+        ta = p.tensor(f"{dk}.a", 1, fh, fw, e)
+        s2, b2 = L.fold_bn(None, L.bn_params(sd, f"{dk}.2"), e)
+        L.add_conv(p, f"{dk}.0", [L.Segment(hd, e, stream=0), L.Segment(hd, e, stream=1)], L.conv_taps(sd[f"{dk}.0.weight"], pad=1), e,
+                   fh, fw, 1, ones(e), npf(sd[f"{dk}.0.bias"]), act="prelu", act_alpha=float(sd[f"{dk}.1.weight"][0]), act_pre=True,
+                   scale2=s2, shift2=b2, out0=ta, macs_per_pair=fh * fw * 9 * 2 * e * e)
+        res = None
+        if c_prev is not None:
+            res = p.tensor(f"{dk}.up_prev", 1, fh, fw, e)
+            p.ops.append(L.BilinearUpSpec(f"{dk}.up_prev", c_prev, res, e, 2))
+        ck = p.tensor(f"{dk}.out", 1, fh, fw, e)
+        s2, b2 = L.fold_bn(None, L.bn_params(sd, f"{dk}.6"), e)
+        L.add_conv(p, f"{dk}.4", [L.Segment(ta, e)], L.conv_taps(sd[f"{dk}.4.weight"], pad=1), e, fh, fw, 1, ones(e),
+                   npf(sd[f"{dk}.4.bias"]), act="prelu", act_alpha=float(sd[f"{dk}.5.weight"][0]), act_pre=True, scale2=s2, shift2=b2,
+                   res=res, out0=ck, macs_per_pair=fh * fw * 9 * e * e)
+        # intermediate prediction (outputs[0..3]): conv, ReLU, BN, conv -> fp32
+        mp = f"{d}.make_pred_c{k}"
+        tp = p.tensor(f"{mp}.t", 1, fh, fw, 8)
+        w0 = torch.zeros(8, e, 3, 3)
+        w0[:n_class] = sd[f"{mp}.0.weight"]
+        b0 = np.zeros(8, np.float32)
+        b0[:n_class] = npf(sd[f"{mp}.0.bias"])
+        s2, b2 = L.fold_bn(None, L.bn_params(sd, f"{mp}.2"), n_class)
+        s2p, b2p = np.zeros(8, np.float32), np.zeros(8, np.float32)
+        s2p[:n_class], b2p[:n_class] = s2, b2
+        L.add_conv(p, f"{mp}.0", [L.Segment(ck, e)], L.conv_taps(w0, pad=1), 8, fh, fw, 1, ones(8), b0, act="relu", act_pre=True,
+                   scale2=s2p, shift2=b2p, out0=tp, macs_per_pair=fh * fw * 9 * e * n_class)
+        L.add_conv(p, f"{mp}.3", [L.Segment(tp, n_class)], L.conv_taps(sd[f"{mp}.3.weight"], pad=1), n_class, fh, fw, 1, ones(n_class),
+                   npf(sd[f"{mp}.3.bias"]), out_ext=4 - k, macs_per_pair=fh * fw * 9 * n_class * n_class)
+        p.ext.append(L.ExtOutput(f"p_c{k}", n_class, fh, fw))
+        if k == 1:
+            ups.append(ck)
+        else:
+            up = p.tensor(f"{dk}.up_full", 1, full_h, full_w, e)
+            p.ops.append(L.BilinearUpSpec(f"{dk}.up_full", ck, up, e, full_h // fh))
+            ups.append(up)
+        c_prev = ck
+    fused = p.tensor(f"{d}.fused", 1, full_h, full_w, e)
+    sc, sh = conv_bn(f"{d}.linear_fuse", e)
+    L.add_conv(p, f"{d}.linear_fuse", [L.Segment(t, e) for t in ups], L.conv_taps(sd[f"{d}.linear_fuse.0.weight"], pad=0), e,
+               full_h, full_w, 1, sc, sh, out0=fused, macs_per_pair=full_h * full_w * 4 * e * e)
+    x, hh, ww = fused, full_h, full_w
+    for up_name, res_name in (("convd2x", "dense_2x.0"), ("convd1x", "dense_1x.0")):
+        wt = sd[f"{d}.{up_name}.conv2d.weight"]              # ConvTranspose2d [cin, cout, 4, 4], stride 2, padding 1
+        u = p.tensor(f"{d}.{up_name}.out", 1, 2 * hh, 2 * ww, e)
+        L.add_conv(p, f"{d}.{up_name}", [L.Segment(x, e)], L.convT_phase_taps(wt, stride=2, pad=1), e, hh, ww, 1, ones(e),
+                   npf(sd[f"{d}.{up_name}.conv2d.bias"]), osy=2, osx=2, out0=u, macs_per_pair=hh * ww * 16 * e * e)
+        hh, ww = 2 * hh, 2 * ww
+        r1 = p.tensor(f"{d}.{res_name}.t", 1, hh, ww, e)
+        L.add_conv(p, f"{d}.{res_name}.conv1", [L.Segment(u, e)], L.conv_taps(sd[f"{d}.{res_name}.conv1.conv2d.weight"], pad=1), e, hh,
+                   ww, 1, ones(e), npf(sd[f"{d}.{res_name}.conv1.conv2d.bias"]), relu=True, out0=r1, macs_per_pair=hh * ww * 9 * e * e)
+        x = p.tensor(f"{d}.{res_name}.out", 1, hh, ww, e)
+        L.add_conv(p, f"{d}.{res_name}.conv2", [L.Segment(r1, e)], L.conv_taps(sd[f"{d}.{res_name}.conv2.conv2d.weight"], pad=1), e, hh,
+                   ww, 1, 0.1 * ones(e), 0.1 * npf(sd[f"{d}.{res_name}.conv2.conv2d.bias"]), res=u, out0=x,
+                   macs_per_pair=hh * ww * 9 * e * e)
+    L.add_conv(p, f"{d}.change_probability", [L.Segment(x, e)], L.conv_taps(sd[f"{d}.change_probability.conv2d.weight"], pad=1),
+               n_class, hh, ww, 1, ones(n_class), npf(sd[f"{d}.change_probability.conv2d.bias"]), out_ext=4,
+               macs_per_pair=hh * ww * 9 * e * n_class)
+    p.ext.append(L.ExtOutput("cp", n_class, hh, ww))
+    return p

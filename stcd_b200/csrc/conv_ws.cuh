@@ -100,7 +100,9 @@ struct ConvParams {
   const float* shift;
   const float* scale2;
   const float* shift2;
-  int32_t relu;
+  int32_t relu;        // activation kind: 0 none, 1 ReLU, 2 GELU (erf), 3 PReLU (one slope act_alpha)
+  int32_t act_pre;     // 1: the activation sits before the second affine (conv -> act -> BN) instead of last
+  float act_alpha;
   const __nv_bfloat16* res;
   int32_t res_c8;
   __nv_bfloat16* out0;
@@ -507,6 +509,18 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     const bool has_pool = STCD_HAS(E_POOL, p.out_pool != nullptr);
     const bool has_diff = (MS == 2) && STCD_HAS(E_DIFF, p.out_diff != nullptr);
     const bool has_f32 = STCD_HAS(E_F32, p.out_f32 != nullptr);
+    auto apply_act = [&](float (&x)[16]) {   // p.relu is warp-uniform
+      if (p.relu == 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
+      } else if (p.relu == 2) {              // nn.GELU(): 0.5 x (1 + erf(x / sqrt 2))
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = 0.5f * x[j] * (1.f + erff(x[j] * 0.70710678118654752f));
+      } else if (p.relu == 3) {              // nn.PReLU() with one slope
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = x[j] >= 0.f ? x[j] : x[j] * p.act_alpha;
+      }
+    };
 
     // the residual is prefetched ahead of the accumulator wait, so this role reads global memory
     // written by the previous kernel without going through the A producer's dependency wait
@@ -594,6 +608,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
               if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(v[m] + 8);
             }
             if (has_aff2) {
+              if (p.act_pre) apply_act(v[m]);
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[m][j] = fmaf(v[m][j], s_aff[2][c0 + j], s_aff[3][c0 + j]);
             }
@@ -604,10 +619,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[m][j] += rv[j];
             }
-            if (has_relu) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[m][j] = fmaxf(v[m][j], 0.f);
-            }
+            if (has_relu && !p.act_pre) apply_act(v[m]);
             if (has_f32) {
               if (valid && im[m] < static_cast<size_t>(p.n_valid)) {
                 const int nv = min(16, p.cout - ch);

@@ -8,6 +8,7 @@
 // neighbours.  The work is small (N x M x C MACs with M <= 256) and the kernel keeps the whole [64 x M] distance
 // tile in registers -- the dense [B, N, M] tensor of the reference never exists.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -153,6 +154,125 @@ __global__ void __launch_bounds__(256) max_relative_kernel(const float* __restri
     } else {
       out[i] = m;
     }
+  }
+}
+
+// ---- plan-tensor variants (the Grapher inside a lowered net: activations are bf16 [img][c/8][hw][8]) ----
+
+// bf16 [B][c8][N][8] -> fp32 [B][C][N] (the layout the graph kernels read).  One thread per (b, group, n).
+__global__ void __launch_bounds__(256) unpack_nodes_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int B,
+                                                           int src_c8, int C, int N) {
+  const int g8 = C >> 3;
+  const size_t total = static_cast<size_t>(B) * g8 * N;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t n = i % N;
+    const size_t r = i / N;
+    const size_t g = r % g8, b = r / g8;
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + ((b * src_c8 + g) * N + n) * 8));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    float* o = dst + (b * C + g * 8) * N + n;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+      o[static_cast<size_t>(2 * j) * N] = __low2float(h);
+      o[static_cast<size_t>(2 * j + 1) * N] = __high2float(h);
+    }
+  }
+}
+
+// F.avg_pool2d(x, r, r) on fp32 [B*C][H][W] -> [B*C][H/r][W/r]; sums in row-major window order, then / r^2
+__global__ void __launch_bounds__(256) avgpool_nodes_kernel(const float* __restrict__ x, float* __restrict__ y, size_t planes, int H,
+                                                            int W, int r) {
+  const int ho = H / r, wo = W / r;
+  const size_t total = planes * ho * wo;
+  const float inv = 1.0f / static_cast<float>(r * r);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(i % wo);
+    const size_t t = i / wo;
+    const int oy = static_cast<int>(t % ho);
+    const size_t pl = t / ho;
+    const float* p = x + (pl * H + static_cast<size_t>(oy) * r) * W + static_cast<size_t>(ox) * r;
+    float s = 0.f;
+    for (int a = 0; a < r; ++a)
+      for (int b = 0; b < r; ++b) s += __ldg(p + static_cast<size_t>(a) * W + b);
+    y[i] = s * inv;
+  }
+}
+
+// max-relative with a bf16 [B][c8][N][8] destination: one thread per (b, 8-channel group, n)
+__global__ void __launch_bounds__(256) max_relative_nc8_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                               const long long* __restrict__ nn_idx, int B, int C, int N, int M,
+                                                               int k, __nv_bfloat16* __restrict__ dst, int dst_c8) {
+  const int g8 = C >> 3;
+  const size_t total = static_cast<size_t>(B) * g8 * N;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t n = i % N;
+    const size_t r = i / N;
+    const size_t g = r % g8, b = r / g8;
+    const long long* idx = nn_idx + (b * N + n) * k;
+    float xv[8], m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      xv[j] = __ldg(x + (b * C + g * 8 + j) * N + n);
+      m[j] = -CUDART_INF_F;
+    }
+    for (int t = 0; t < k; ++t) {
+      const long long jn = __ldg(idx + t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], __fsub_rn(__ldg(y + (b * C + g * 8 + j) * M + jn), xv[j]));
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(m[2 * j], m[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(dst + ((b * dst_c8 + g) * N + n) * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// Bilinear up-sampling by an integer factor, align_corners=False (PyTorch's area_pixel_compute_source_index:
+// src = (dst + 0.5) / scale - 0.5 clamped at 0), bf16 [B][c8][h][w][8] -> bf16 [B][c8][s*h][s*w][8], fp32 arithmetic.
+__global__ void __launch_bounds__(256) bilinear_up_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                          int B, int g8, int src_c8, int dst_c8, int h, int w, int scale) {
+  const int ho = h * scale, wo = w * scale;
+  const size_t total = static_cast<size_t>(B) * g8 * ho * wo;
+  const float rs = 1.0f / static_cast<float>(scale);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(i % wo);
+    size_t t = i / wo;
+    const int oy = static_cast<int>(t % ho);
+    t /= ho;
+    const size_t g = t % g8, b = t / g8;
+    const float sy = fmaxf(rs * (static_cast<float>(oy) + 0.5f) - 0.5f, 0.f);
+    const float sx = fmaxf(rs * (static_cast<float>(ox) + 0.5f) - 0.5f, 0.f);
+    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly = sy - static_cast<float>(y0), lx = sx - static_cast<float>(x0);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const __nv_bfloat16* base = src + (b * src_c8 + g) * static_cast<size_t>(h) * w * 8;
+    const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y0) * w + x0) * 8));
+    const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y0) * w + x1) * 8));
+    const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y1) * w + x0) * 8));
+    const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y1) * w + x1) * 8));
+    const uint32_t a[4] = {q00.x, q00.y, q00.z, q00.w}, bq[4] = {q01.x, q01.y, q01.z, q01.w};
+    const uint32_t c[4] = {q10.x, q10.y, q10.z, q10.w}, dq[4] = {q11.x, q11.y, q11.z, q11.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 v00 = *reinterpret_cast<const __nv_bfloat162*>(&a[j]), v01 = *reinterpret_cast<const __nv_bfloat162*>(&bq[j]);
+      const __nv_bfloat162 v10 = *reinterpret_cast<const __nv_bfloat162*>(&c[j]), v11 = *reinterpret_cast<const __nv_bfloat162*>(&dq[j]);
+      const float lo = hy * (hx * __low2float(v00) + lx * __low2float(v01)) + ly * (hx * __low2float(v10) + lx * __low2float(v11));
+      const float hi = hy * (hx * __high2float(v00) + lx * __high2float(v01)) + ly * (hx * __high2float(v10) + lx * __high2float(v11));
+      __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
+      o[j] = *reinterpret_cast<uint32_t*>(&r);
+    }
+    *reinterpret_cast<uint4*>(dst + ((b * dst_c8 + g) * static_cast<size_t>(ho) * wo + static_cast<size_t>(oy) * wo + ox) * 8) =
+        make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 

@@ -95,6 +95,20 @@ struct PoolOp {
   int src, dst, c;
 };
 
+struct GraphOp {
+  int src, dst, c, k, dilation, r;
+  std::vector<float> relpos;   // [N][M] or empty
+  float* relpos_dev = nullptr;
+  float* xf = nullptr;         // fp32 [imgs][C][N]
+  float* yf = nullptr;         // fp32 [imgs][C][M] (r > 1)
+  float* den = nullptr;        // [imgs * (N + M)]
+  long long* idx = nullptr;    // [imgs][N][k]
+};
+
+struct BilinearOp {
+  int src, dst, c, scale;
+};
+
 struct SegHeadOp {
   int src, c, out_ext;
   float bias;
@@ -112,7 +126,7 @@ struct EcamOp {
 };
 
 struct Op {
-  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head
+  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head, 5 graph conv, 6 bilinear up
   int idx;
 };
 
@@ -128,6 +142,8 @@ struct stcd_plan {
   std::vector<EcamOp> ecams;
   std::vector<PoolOp> pools;
   std::vector<SegHeadOp> heads;
+  std::vector<GraphOp> graphs;
+  std::vector<BilinearOp> bilinears;
   std::vector<Op> ops;
   uint8_t* workspace = nullptr;
   size_t workspace_bytes = 0;
@@ -251,6 +267,36 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
       stcd::maxpool3x3s2_s2d_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr,
                                                             td.mult * plan->chunk, k.c / 8, td.c / 8, td.h, td.w);
       CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 5) {
+      const GraphOp& k = plan->graphs[o.idx];
+      const Tensor& ts = plan->tensors[k.src];
+      const Tensor& td = plan->tensors[k.dst];
+      const int B = ts.mult * plan->chunk, N = ts.h * ts.w, M = N / (k.r * k.r);
+      auto nb = [](size_t total, int cap) { return (unsigned)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)148 * cap)); };
+      stcd::unpack_nodes_kernel<<<nb((size_t)B * (k.c / 8) * N, 8), 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, k.xf, B, ts.c / 8, k.c, N);
+      const float* y = k.xf;
+      if (k.r > 1) {
+        stcd::avgpool_nodes_kernel<<<nb((size_t)B * k.c * M, 8), 256, 0, st>>>(k.xf, k.yf, (size_t)B * k.c, ts.h, ts.w, k.r);
+        y = k.yf;
+      }
+      float* xden = k.den;
+      float* yden = k.r > 1 ? k.den + (size_t)B * N : k.den;
+      stcd::node_norm_kernel<<<nb((size_t)B * N, 8), 256, 0, st>>>(k.xf, xden, B, k.c, N);
+      if (k.r > 1) stcd::node_norm_kernel<<<nb((size_t)B * M, 8), 256, 0, st>>>(k.yf, yden, B, k.c, M);
+      stcd::knn_graph_kernel<<<dim3((N + stcd::kKnnQ - 1) / stcd::kKnnQ, B), 256, 0, st>>>(k.xf, xden, y, yden, k.relpos_dev, k.c, N, M, k.k,
+                                                                                       k.dilation, k.idx);
+      stcd::max_relative_nc8_kernel<<<nb((size_t)B * (k.c / 8) * N, 8), 256, 0, st>>>(k.xf, y, k.idx, B, k.c, N, M, k.k,
+                                                                                      (__nv_bfloat16*)td.ptr, td.c / 8);
+      CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 6) {
+      const BilinearOp& k = plan->bilinears[o.idx];
+      const Tensor& ts = plan->tensors[k.src];
+      const Tensor& td = plan->tensors[k.dst];
+      const int B = ts.mult * plan->chunk;
+      const size_t total = (size_t)B * (k.c / 8) * td.h * td.w;
+      stcd::bilinear_up_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, 148 * 16)), 256, 0, st>>>(
+          (const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, B, k.c / 8, ts.c / 8, td.c / 8, ts.h, ts.w, k.scale);
+      CUDA_TRY(cudaGetLastError());
     } else if (o.kind == 4) {
       const SegHeadOp& k = plan->heads[o.idx];
       const Tensor& t = plan->tensors[k.src];
@@ -352,6 +398,13 @@ void stcd_plan_destroy(stcd_plan* plan) {
   }
   for (SegHeadOp& e : plan->heads)
     if (e.w_dev) cudaFree(e.w_dev);
+  for (GraphOp& g : plan->graphs) {
+    if (g.relpos_dev) cudaFree(g.relpos_dev);
+    if (g.xf) cudaFree(g.xf);
+    if (g.yf) cudaFree(g.yf);
+    if (g.den) cudaFree(g.den);
+    if (g.idx) cudaFree(g.idx);
+  }
   if (plan->workspace) cudaFree(plan->workspace);
   if (plan->arena) cudaFree(plan->arena);
   for (int b = 0; b < 2; ++b) {
@@ -454,6 +507,45 @@ int stcd_plan_add_maxpool_s2d(stcd_plan* plan, int src_tensor, int dst_tensor, i
   return (int)plan->ops.size() - 1;
 }
 
+int stcd_plan_add_graph_conv(stcd_plan* plan, int src_tensor, int dst_tensor, int c, int k, int dilation, int r, const float* relpos) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, src_tensor) || !valid_tensor(plan, dst_tensor)) return -fail(STCD_ERR_INVALID, "bad tensor id");
+  const Tensor& ts = plan->tensors[src_tensor];
+  const Tensor& td = plan->tensors[dst_tensor];
+  if (c < 8 || (c % 8) || ts.c < c || td.c < c || ts.h != td.h || ts.w != td.w || ts.mult != td.mult)
+    return -fail(STCD_ERR_INVALID, "graph conv: src [%d*chunk,%d,%d,%d] / dst [%d*chunk,%d,%d,%d] must match and hold c=%d channels", ts.mult,
+                 ts.h, ts.w, ts.c, td.mult, td.h, td.w, td.c, c);
+  if (k < 1 || dilation < 1 || r < 1 || (ts.h % r) || (ts.w % r)) return -fail(STCD_ERR_INVALID, "graph conv: bad k/dilation/r");
+  const int N = ts.h * ts.w, M = N / (r * r);
+  if (M > stcd::kKnnM || k * dilation > M) return -fail(STCD_ERR_INVALID, "graph conv: M=%d keys (max %d), k*dilation=%d", M, stcd::kKnnM, k * dilation);
+  GraphOp g;
+  g.src = src_tensor;
+  g.dst = dst_tensor;
+  g.c = c;
+  g.k = k;
+  g.dilation = dilation;
+  g.r = r;
+  if (relpos) g.relpos.assign(relpos, relpos + (size_t)N * M);
+  plan->graphs.push_back(std::move(g));
+  plan->ops.push_back({5, (int)plan->graphs.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_bilinear_up(stcd_plan* plan, int src_tensor, int dst_tensor, int c, int scale) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, src_tensor) || !valid_tensor(plan, dst_tensor)) return -fail(STCD_ERR_INVALID, "bad tensor id");
+  const Tensor& ts = plan->tensors[src_tensor];
+  const Tensor& td = plan->tensors[dst_tensor];
+  if (c < 8 || (c % 8) || ts.c < c || td.c < c || scale < 1 || scale > 32 || td.h != ts.h * scale || td.w != ts.w * scale || ts.mult != td.mult)
+    return -fail(STCD_ERR_INVALID, "bilinear up: src [%d*chunk,%d,%d,%d] x%d does not give dst [%d*chunk,%d,%d,%d] (c=%d)", ts.mult, ts.h, ts.w,
+                 ts.c, scale, td.mult, td.h, td.w, td.c, c);
+  plan->bilinears.push_back({src_tensor, dst_tensor, c, scale});
+  plan->ops.push_back({6, (int)plan->bilinears.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
 int stcd_plan_add_seg_head(stcd_plan* plan, const stcd_seghead_desc* d) {
   if (!plan || !d) return -fail(STCD_ERR_STATE, "plan/desc is NULL");
   if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
@@ -488,6 +580,8 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
   if (!d->weights || !d->chunks || !d->taps || !d->scale || !d->shift)
     return -fail(STCD_ERR_INVALID, "NULL weights/chunks/taps/scale/shift");
   if ((d->scale2 == nullptr) != (d->shift2 == nullptr)) return -fail(STCD_ERR_INVALID, "scale2/shift2 must come together");
+  if (d->relu < 0 || d->relu > 3) return -fail(STCD_ERR_INVALID, "activation kind %d not in [0, 3]", d->relu);
+  if (d->act_pre && (!d->scale2 || !d->relu)) return -fail(STCD_ERR_INVALID, "act_pre needs an activation and the second affine");
   if (d->img_mult < 1 || d->img_mult > 2) return -fail(STCD_ERR_INVALID, "img_mult %d", d->img_mult);
   if (d->pair && d->img_mult != 1) return -fail(STCD_ERR_INVALID, "pair ops iterate over chunk_pairs images (img_mult=1)");
   if (d->out_diff >= 0 && !d->pair) return -fail(STCD_ERR_INVALID, "out_diff needs pair=1");
@@ -561,7 +655,9 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
       if (e.src < 0 || e.src >= d->n_src) return -fail(STCD_ERR_INVALID, "chunk %d: src %d", i, e.src);
       const Tensor& t = plan->tensors[d->src[e.src]];
       // a chunk may overhang the tensor's last 8-channel group: TMA zero-fills the missing group
-      if (e.c0 < 0 || (e.c0 % 8) || e.c0 >= t.c || e.c0 + d->kc > (t.c + 15) / 16 * 16)
+      // a chunk may overhang the tensor by one 8-channel group (TMA zero-fills it) or run into the next parity class
+      // of a space-to-depth tensor (those K rows carry zero weights)
+      if (e.c0 < 0 || (e.c0 % 8) || e.c0 >= t.c || e.c0 + d->kc > t.c + 8)
         return -fail(STCD_ERR_INVALID, "chunk %d: channels [%d,+%d) of %d", i, e.c0, d->kc, t.c);
       const int top = (d->pair ? 1 : d->img_mult - 1) * plan->chunk + plan->chunk - 1 + e.n_off;
       if (e.n_off < 0 || top >= t.mult * plan->chunk) return -fail(STCD_ERR_INVALID, "chunk %d: image offset %d overruns source", i, e.n_off);
@@ -877,6 +973,8 @@ int stcd_plan_finalize(stcd_plan* plan) {
       p.shift2 = sc + 3 * d.cout_pad;
     }
     p.relu = d.relu;
+    p.act_pre = d.act_pre;
+    p.act_alpha = d.act_alpha;
     // epilogue features -> kernel instance (specialised when one exists, else the generic one)
     op.epi = (d.out_raw >= 0 ? stcd::E_RAW : 0u) | (!op.scale2.empty() ? stcd::E_AFF2 : 0u) | (d.res >= 0 ? stcd::E_RES : 0u) |
              (d.relu ? stcd::E_RELU : 0u) | (d.out0 >= 0 ? stcd::E_OUT0 : 0u) | (d.out_pool >= 0 ? stcd::E_POOL : 0u) |
@@ -910,6 +1008,18 @@ int stcd_plan_finalize(stcd_plan* plan) {
     if (d.out_diff >= 0) {
       p.out_diff = (__nv_bfloat16*)plan->tensors[d.out_diff].ptr;
       p.out_diff_c8 = plan->tensors[d.out_diff].c / 8;
+    }
+  }
+  for (GraphOp& g : plan->graphs) {
+    const Tensor& ts = plan->tensors[g.src];
+    const size_t B = (size_t)ts.mult * plan->chunk, N = (size_t)ts.h * ts.w, M = N / (g.r * g.r);
+    CUDA_TRY(cudaMalloc(&g.xf, B * g.c * N * sizeof(float)));
+    if (g.r > 1) CUDA_TRY(cudaMalloc(&g.yf, B * g.c * M * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&g.den, B * (N + M) * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&g.idx, B * N * g.k * sizeof(long long)));
+    if (!g.relpos.empty()) {
+      CUDA_TRY(cudaMalloc(&g.relpos_dev, g.relpos.size() * sizeof(float)));
+      CUDA_TRY(cudaMemcpy(g.relpos_dev, g.relpos.data(), g.relpos.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
   }
   for (SegHeadOp& k : plan->heads) {
@@ -985,7 +1095,9 @@ int64_t stcd_plan_workspace_bytes(const stcd_plan* plan) {
 int64_t stcd_plan_launches(const stcd_plan* plan, int n_pairs) {
   if (!plan || n_pairs < 1) return 0;
   const int64_t chunks = (n_pairs + plan->chunk - 1) / plan->chunk;
-  return chunks * (int64_t)(plan->ops.size() + plan->ecams.size());  // an ECAM head op is two kernels
+  int64_t per_chunk = (int64_t)plan->ops.size() + (int64_t)plan->ecams.size();  // an ECAM head op is two kernels
+  for (const GraphOp& g : plan->graphs) per_chunk += 3 + (g.r > 1 ? 2 : 0);     // unpack, [pool], norm, [norm y], kNN, max-relative
+  return chunks * per_chunk;
 }
 
 static int forward_any(stcd_plan* plan, const void* x1, const void* x2, int u8, int n_pairs, float* const* outs, int n_outs,

@@ -106,6 +106,11 @@ class ConvSpec:
     #                              pixel (y//2, x//2), channel ((y%2)*2 + x%2) * cout + c
     fold_cs: int = 0             # > 0: the osy*osx output phases are folded into GEMM N: column p*fold_cs + c is
     fold_cout: int = 0           # channel c (< fold_cout) of output pixel (i*osy + p//osx, j*osx + p%osx)
+    # activation: 0 none, 1 ReLU, 2 GELU (erf), 3 PReLU with one slope `act_alpha`.  act_pre: the activation sits
+    # BEFORE the second affine (conv -> PReLU -> BN, ChangeFormer.py:1138-1148) instead of at the end of the epilogue
+    act_kind: int = 0
+    act_alpha: float = 0.0
+    act_pre: bool = False
 
     def weight_block(self, nt: int, block: int) -> torch.Tensor:
         """fp32 [n_tile, kc] view of one packed weight block (for the emulator)."""
@@ -141,6 +146,33 @@ class MaxPoolS2DSpec:
 
 
 @dataclass
+class GraphConvSpec:
+    """The graph half of a ViG Grapher block (gcn_lib DyGraphConv2d up to MRConv2d's aggregation):
+    y = avg_pool2d(x, r) if r > 1 else x; dense dilated kNN graph of x over y (k neighbours, every dilation-th of
+    the k*dilation nearest, + relative-position bias); dst = max_k (y_j - x_i), bf16.  src/dst: [imgs, h, w, c]."""
+    name: str
+    src: str
+    dst: str
+    c: int
+    k: int
+    dilation: int
+    r: int
+    relpos: Optional[np.ndarray]     # float32 [h*w, h*w / r^2] or None
+    macs_per_pair: int = 0
+
+
+@dataclass
+class BilinearUpSpec:
+    """F.interpolate(x, scale_factor=scale, mode="bilinear", align_corners=False) (ChangeVIG.py:246-262: `resize` and
+    `F.interpolate(_c4, scale_factor=2, mode="bilinear")`) on a bf16 tensor; dst is [imgs, scale*h, scale*w, c]."""
+    name: str
+    src: str
+    dst: str
+    c: int
+    scale: int
+
+
+@dataclass
 class SegHeadSpec:
     """SegCD's tail (segmentation_models_pytorch/decoders/unet/model.py:321-330) as ONE op over the
     decoder output d (both temporal streams, c channels): m1 = head(d1), m2 = head(d2),
@@ -172,6 +204,9 @@ class Program:
     tensors: Dict[str, TensorSpec] = field(default_factory=dict)
     ops: List[object] = field(default_factory=list)
     ext: List[ExtOutput] = field(default_factory=list)
+    # constant tensors (e.g. a positional embedding added as a residual): name -> fp32 [h, w, c], replicated over
+    # the images of the tensor when the plan is built
+    consts: Dict[str, torch.Tensor] = field(default_factory=dict)
 
     def tensor(self, name: str, mult: int, h: int, w: int, c: int) -> str:
         if name in self.tensors:
@@ -505,7 +540,16 @@ def add_conv(
     macs_per_pair: int = 0,
     out0_s2d: bool = False,
     fold: Optional[bool] = None,
+    act: Optional[str] = None,
+    act_alpha: float = 0.0,
+    act_pre: bool = False,
 ) -> ConvSpec:
+    if act is not None and relu:
+        raise ValueError(f"{name}: give either relu=True or act=...")
+    act_kind = 1 if relu else {None: 0, "relu": 1, "gelu": 2, "prelu": 3}[act]
+    relu = act_kind != 0          # the epilogue's "has activation" switch
+    if act_pre and scale2 is None:
+        raise ValueError(f"{name}: act_pre needs the second affine")
     fold_cs = fold_cout = 0
     plain_out = (res is None and out_raw is None and out_pool is None and out_diff is None and out_ext < 0
                  and scale2 is None and not out0_s2d and out0 is not None)
@@ -534,7 +578,7 @@ def add_conv(
         shift2=None if shift2 is None else _pad_vec(shift2, cout_pad, 0.0),
         relu=relu, res=res, out0=out0, out0_coff=out0_coff, out_raw=out_raw, out_pool=out_pool,
         out_diff=out_diff, out_ext=out_ext, macs_per_pair=macs_per_pair, out0_s2d=out0_s2d,
-        fold_cs=fold_cs, fold_cout=fold_cout,
+        fold_cs=fold_cs, fold_cout=fold_cout, act_kind=act_kind, act_alpha=float(act_alpha), act_pre=act_pre,
     )
     prog.ops.append(spec)
     return spec
@@ -587,6 +631,12 @@ def op_bytes_per_pair(prog: Program, op) -> int:
     if isinstance(op, EcamHeadSpec):
         t = T[op.srcs[0]]
         return 2 * 4 * op.c * t.h * t.w * 2 + op.n_class * t.h * t.w * 4
+    if isinstance(op, GraphConvSpec):
+        t = T[op.src]
+        return t.mult * (2 * op.c * t.h * t.w * 2 + (0 if op.relpos is None else op.relpos.size * 4))
+    if isinstance(op, BilinearUpSpec):
+        t = T[op.dst]
+        return t.mult * (op.c * t.h * t.w * 2 + op.c * t.h * t.w * 2 // (op.scale * op.scale))
     if isinstance(op, ConvSpec):
         imgs = 2 if op.pair else op.img_mult
         seen, byt = set(), 0

@@ -15,7 +15,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .lowering import ConvSpec, EcamHeadSpec, InputPackSpec, MaxPoolS2DSpec, Program, SegHeadSpec
+from .lowering import (BilinearUpSpec, ConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec, MaxPoolS2DSpec, Program,
+                       SegHeadSpec)
 
 
 def _fptr(a: Optional[np.ndarray]):
@@ -57,6 +58,12 @@ class Plan:
             elif isinstance(op, InputPackSpec):
                 add = lib.stcd_plan_add_input_pack_s2d if op.s2d else lib.stcd_plan_add_input_pack
                 _lib.check_id(add(h, ids[op.dst], op.cin), f"input pack {op.name}")
+            elif isinstance(op, GraphConvSpec):
+                rp = None if op.relpos is None else np.ascontiguousarray(op.relpos, np.float32)
+                _lib.check_id(lib.stcd_plan_add_graph_conv(h, ids[op.src], ids[op.dst], op.c, op.k, op.dilation, op.r, _fptr(rp)),
+                              f"graph conv {op.name}")
+            elif isinstance(op, BilinearUpSpec):
+                _lib.check_id(lib.stcd_plan_add_bilinear_up(h, ids[op.src], ids[op.dst], op.c, op.scale), f"bilinear {op.name}")
             elif isinstance(op, MaxPoolS2DSpec):
                 _lib.check_id(lib.stcd_plan_add_maxpool_s2d(h, ids[op.src], ids[op.dst], op.c), f"maxpool {op.name}")
             elif isinstance(op, SegHeadSpec):
@@ -72,6 +79,11 @@ class Plan:
             else:
                 raise TypeError(f"unknown op {op!r}")
         _lib.check(lib.stcd_plan_finalize(h), "stcd_plan_finalize")
+        for name, val in prog.consts.items():          # constant tensors: the same [h, w, c] block for every image
+            t = prog.tensors[name]
+            full = torch.zeros(t.mult * self.chunk, t.h, t.w, t.c)
+            full[..., : val.shape[2]] = val.to(torch.float32)[None]
+            self.write_tensor(name, full)
 
     def _add_conv(self, op: ConvSpec) -> None:
         ids = self.tensor_ids
@@ -108,7 +120,8 @@ class Plan:
                 None if op.scale2 is None else np.ascontiguousarray(op.scale2, np.float32),
                 None if op.shift2 is None else np.ascontiguousarray(op.shift2, np.float32)]
         d.scale, d.shift, d.scale2, d.shift2 = (_fptr(a) for a in keep)
-        d.relu = 1 if op.relu else 0
+        d.relu = op.act_kind if op.act_kind else (1 if op.relu else 0)
+        d.act_pre, d.act_alpha = (1 if op.act_pre else 0), float(op.act_alpha)
         tid = lambda n: -1 if n is None else ids[n]  # noqa: E731
         d.res = tid(op.res)
         d.out0, d.out0_coff = tid(op.out0), op.out0_coff

@@ -24,7 +24,7 @@ DATA_SEED = 1338
 # the logits) while the bf16 path's error is RELATIVE (~1 % of the activation scale after ~24 fused
 # layers, 5-sigma tail over 1e5 logits), so the harness keeps the logit standard deviation near 0.2-0.3:
 # non-degenerate change maps (tens of % "changed") with the tolerance still meaningful.
-GAINS = {"SiamUnet_diff": 0.72, "SiamUnet_conc": 0.70, "SNUNet_ECAM": 0.6, "SegCD": 0.70}
+GAINS = {"SiamUnet_diff": 0.72, "SiamUnet_conc": 0.70, "SNUNet_ECAM": 0.6, "SegCD": 0.70, "ChangeGNNV1": 0.5}
 # Head-bias offsets (parameter name, per-class values added after the random draw) that centre the
 # class margin of nets whose random-init margin is one-sided (SNUNet's post-ReLU features make class
 # 0 win everywhere): without it the change map is all-zero and pixel agreement says nothing.
@@ -56,6 +56,11 @@ def randomize_(net: nn.Module, seed: int = WEIGHT_SEED, gain: float = 1.0) -> nn
         elif isinstance(m, nn.LayerNorm):
             m.weight.copy_(0.8 + 0.4 * torch.rand(m.weight.shape, generator=g))
             m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+        elif isinstance(m, nn.PReLU):
+            m.weight.copy_(0.1 + 0.3 * torch.rand(m.weight.shape, generator=g))
+        pe = m._parameters.get("pos_embed") if hasattr(m, "_parameters") else None
+        if pe is not None:           # ViG / transformer positional embedding: zeros at construction (ChangeVIG.py:50)
+            pe.copy_(torch.randn(pe.shape, generator=g) * 0.1)
     return net
 
 

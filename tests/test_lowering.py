@@ -104,6 +104,30 @@ def test_segcd_resnet50_program_matches_oracle():
     assert abs(2 * net.lower(1024, 1024).macs_per_pair() / 1e9 - 680.79) < 0.5
 
 
+def test_changegnn_program_matches_oracle():
+    """Config C4's net: ViG Grapher blocks (graph op + grouped conv folded into a dense virtual-concat conv), GELU /
+    PReLU-before-BN epilogues, bilinear resizes, ConvTranspose2d(k4, s2) phases -- checked through the emulator."""
+    from stcd_b200 import changevig
+    net = synth.prepare_(changevig.ChangeGNNV1().eval(), "ChangeGNNV1")
+    x1, x2 = synth.image_pairs(1, 256, 256)
+    with torch.no_grad():
+        y = nets.changegnn_forward(net.state_dict(), x1, x2)
+    prog = net.lower(256, 256)
+    ye = emulate.run_program(prog, x1, x2, chunk=1)
+    assert len(ye) == 5
+    for a, b in zip(ye, y):
+        assert a.shape == b.shape and (a - b).abs().max().item() < BF16_TOL
+    margin = (y[-1][:, 1] - y[-1][:, 0]).abs()
+    agree = (ye[-1][:, 1] > ye[-1][:, 0]) == (y[-1][:, 1] > y[-1][:, 0])
+    assert agree[margin > BF16_TOL].float().mean().item() >= 0.999
+    assert 0.02 < (y[-1][:, 1] > y[-1][:, 0]).float().mean().item() < 0.98, "degenerate change map"
+    graphs = [o for o in prog.ops if isinstance(o, L.GraphConvSpec)]
+    assert [(g.k, g.dilation, g.r) for g in graphs] == [(9, 1, 4)] * 2 + [(9, 1, 2)] * 2 + [(9, 2, 1)] * 4 + [(9, 3, 1)] * 4
+    assert abs(2 * prog.macs_per_pair() / 1e9 - 283.07) < 0.5          # SURVEY §6: ~290 GFLOP per pair
+    with pytest.raises(ValueError):
+        net.lower(128, 128)            # pos_embed is not resized: the net only runs at img_size (ChangeVIG.py:87)
+
+
 def test_s2d_and_up2_tap_algebra():
     """The tap rewrites behind the SegCD lowering equal the reference ops they replace (fp32, no rounding)."""
     import torch.nn.functional as F
