@@ -53,6 +53,9 @@ WORKLOADS = {
     "changegnn_v1_256_b32": dict(net="ChangeGNNV1", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=16,
                                  desc="C4: ChangeGNNV1 (pyramid ViG Grapher encoder: dense kNN k=9 + max-relative graph conv, "
                                       "multi-scale difference decoder) 256x256 RGB pairs, batch 32 per GPU, bf16"),
+    "changeformer_v6_256_b32": dict(net="ChangeFormerV6", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=16,
+                                    desc="C5: ChangeFormerV6 (MiT transformer encoder + difference decoder) 256x256 RGB pairs, "
+                                         "batch 32 per GPU, bf16"),
     "segcd_r34_256_b64": dict(net="SegCD", n_class=1, h=256, w=256, batch=64, kind="sigmoid", chunk=16,
                               desc="smp SegCD (Unet, ResNet-34 Siamese encoder) 256x256 RGB pairs, batch 64 per GPU, bf16"),
 }
@@ -64,8 +67,8 @@ def build_net(wl):
     from stcd_b200.networks import CLASSES
     if wl["net"] == "SegCD":
         return synth.prepare_(CLASSES["SegCD"](wl.get("encoder", "resnet34"), classes=wl["n_class"]).eval(), "SegCD")
-    if wl["net"] == "ChangeGNNV1":
-        return synth.prepare_(CLASSES["ChangeGNNV1"](3, wl["n_class"], embed_dim=256).eval(), "ChangeGNNV1")
+    if wl["net"] in ("ChangeGNNV1", "ChangeFormerV6"):
+        return synth.prepare_(CLASSES[wl["net"]](3, wl["n_class"], embed_dim=256).eval(), wl["net"])
     return synth.prepare_(CLASSES[wl["net"]](3, wl["n_class"]).eval(), wl["net"])
 
 
@@ -81,6 +84,8 @@ def oracle_forward(wl, sd, x1, x2):
         return nets.segcd_forward(sd, x1, x2)
     if wl["net"] == "ChangeGNNV1":
         return nets.changegnn_forward(sd, x1, x2)
+    if wl["net"] == "ChangeFormerV6":
+        return nets.changeformer_forward(sd, x1, x2)
     raise KeyError(wl["net"])
 
 

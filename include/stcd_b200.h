@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 9
+#define STCD_ABI_VERSION 10
 
 enum stcd_status {
   STCD_OK = 0,
@@ -206,6 +206,19 @@ int stcd_plan_add_graph_conv(stcd_plan* plan, int src_tensor, int dst_tensor, in
  * (ChangeVIG.py:246-262); dst is [scale*h][scale*w], first c channels. */
 int stcd_plan_add_bilinear_up(stcd_plan* plan, int src_tensor, int dst_tensor, int c, int scale);
 
+/* MiT / ChangeFormer encoder ops between plan tensors (models/ChangeFormer.py).
+ * layernorm: nn.LayerNorm(c, eps) over the channels of every pixel / token (:226,475,480); dst_s2d_or_neg >= 0 also
+ *   writes the space-to-depth copy ([h/2][w/2], 4c channels) a following stride-2 patch-embedding conv reads.
+ *   gamma, beta: HOST fp32 [c].
+ * sr_attention: softmax(q k^T * scale) v per head (:338-358); q, dst [imgs][h][w][c], kv [imgs][hk][wk][2c] with
+ *   k = channels [0, c), v = [c, 2c); hk*wk <= 64 keys, c / heads in {64, 80}.
+ * dwconv3x3: depth-wise 3x3 (padding 1) + bias, then GELU if gelu != 0 (:283-289,512-523); weight HOST fp32 [c][9]. */
+int stcd_plan_add_layernorm(stcd_plan* plan, int src_tensor, int dst_tensor, int dst_s2d_or_neg, int c, const float* gamma,
+                            const float* beta, float eps);
+int stcd_plan_add_sr_attention(stcd_plan* plan, int q_tensor, int kv_tensor, int dst_tensor, int c, int heads, float scale);
+int stcd_plan_add_dwconv3x3(stcd_plan* plan, int src_tensor, int dst_tensor, int c, const float* weight, const float* bias,
+                            int gelu);
+
 /* SNUNet's ECAM tail (models/SNUNet.py:144-149: two ChannelAttention blocks :46-59 + conv_final)
  * over four activation tensors of `c` channels each, as one fused op writing external output
  * `out_ext` (fp32 NCHW [n, n_class, h, w]).  All weight pointers are HOST fp32, copied at add time:
@@ -301,7 +314,7 @@ int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const v
  * y-nodes of every x-node in ascending distance (ties: smaller index) and keep every dilation-th.
  * x [B][C][N]; y [B][C][M] or NULL (y := x, M must equal N); relative_pos [N][M] or NULL; M <= 256, k*dilation <= M.
  * nn_idx_out: int64 [B][N][k] = edge_index[0] (edge_index[1] is the centre index n).
- * scratch: device fp32 [B * (N + M)] (the node norms). */
+ * scratch: device fp32 [B * C * (N + M)] (the L2-normalised copies of x and y; B * C * N when y is NULL). */
 int stcd_knn_graph(const float* x, const float* y_or_null, const float* relative_pos_or_null, int B, int C, int N,
                    int M, int k, int dilation, int64_t* nn_idx_out, float* scratch, void* stream);
 

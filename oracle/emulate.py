@@ -234,7 +234,45 @@ def run_bilinear_up(op: L.BilinearUpSpec, T: Dict[str, torch.Tensor]) -> None:
     T[op.dst][..., : op.c] = _bf16(y.permute(0, 2, 3, 1))
 
 
+def run_layernorm(op: L.LayerNormSpec, T: Dict[str, torch.Tensor]) -> None:
+    x = T[op.src][..., : op.c]
+    y = _bf16(torch.nn.functional.layer_norm(x, (op.c,), torch.from_numpy(op.gamma), torch.from_numpy(op.beta), op.eps))
+    T[op.dst][..., : op.c] = y
+    if op.dst_s2d is not None:
+        for py in range(2):
+            for px in range(2):
+                k = (py * 2 + px) * op.c
+                T[op.dst_s2d][..., k: k + op.c] = y[:, py::2, px::2]
+
+
+def run_attention(op: L.AttentionSpec, T: Dict[str, torch.Tensor]) -> None:
+    q = T[op.q][..., : op.c]
+    kv = T[op.kv][..., : 2 * op.c]
+    b, h, w, c = q.shape
+    d = c // op.heads
+    qh = q.reshape(b, h * w, op.heads, d).permute(0, 2, 1, 3)
+    k = kv[..., :c].reshape(b, -1, op.heads, d).permute(0, 2, 1, 3)
+    v = kv[..., c:].reshape(b, -1, op.heads, d).permute(0, 2, 1, 3)
+    attn = ((qh @ k.transpose(-2, -1)) * op.scale).softmax(dim=-1)
+    T[op.dst][..., : c] = _bf16((attn @ v).transpose(1, 2).reshape(b, h, w, c))
+
+
+def run_dwconv(op: L.DWConvSpec, T: Dict[str, torch.Tensor]) -> None:
+    x = T[op.src][..., : op.c].permute(0, 3, 1, 2)
+    wt = torch.from_numpy(op.weight).reshape(op.c, 1, 3, 3)
+    y = torch.nn.functional.conv2d(x, wt, torch.from_numpy(op.bias), padding=1, groups=op.c)
+    if op.gelu:
+        y = torch.nn.functional.gelu(y)
+    T[op.dst][..., : op.c] = _bf16(y.permute(0, 2, 3, 1))
+
+
 def run_aux(op, T, chunk, ext, nv):
+    if isinstance(op, L.LayerNormSpec):
+        return run_layernorm(op, T)
+    if isinstance(op, L.AttentionSpec):
+        return run_attention(op, T)
+    if isinstance(op, L.DWConvSpec):
+        return run_dwconv(op, T)
     if isinstance(op, L.GraphConvSpec):
         return run_graph_conv(op, T)
     if isinstance(op, L.BilinearUpSpec):

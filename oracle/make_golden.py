@@ -30,6 +30,7 @@ CASES = {
     # ChangeGNNV1 runs only at its img_size (pos_embed is not resized); gcn_lib comes from oracle/gcn_lib_restated.py
     # (absent upstream dependency: this fixture pins everything EXCEPT the Grapher restatement itself)
     "changegnn_v1": ("models.ChangeVIG", "ChangeGNNV1", (3, 2, False, 256), 1, 256, 256),
+    "changeformer_v6": ("models.ChangeFormer", "ChangeFormerV6", (3, 2, False, 256), 1, 256, 256),
 }
 
 

@@ -262,3 +262,69 @@ def changegnn_decoder(sd: SD, f1: List[torch.Tensor], f2: List[torch.Tensor], pr
 def changegnn_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor) -> List[torch.Tensor]:
     """ChangeGNNV1.forward, models/ChangeVIG.py:309-312: list of 5 tensors, full-resolution logits last."""
     return changegnn_decoder(sd, vig_encoder_features(sd, x1), vig_encoder_features(sd, x2))
+
+
+# ------------------------------------------------------------------------------------------
+# ChangeFormerV6 (MiT-style Siamese transformer encoder + the same multi-scale difference decoder)
+def _ln(sd: SD, name: str, x: torch.Tensor, eps: float) -> torch.Tensor:
+    return F.layer_norm(x, (x.shape[-1],), sd[f"{name}.weight"], sd[f"{name}.bias"], eps)
+
+
+def _mit_attention(sd: SD, pre: str, x: torch.Tensor, h: int, w: int, heads: int, sr: int) -> torch.Tensor:
+    """Attention.forward, models/ChangeFormer.py:338-358 (attn_drop / proj_drop are identities in eval)."""
+    b, n, c = x.shape
+    d = c // heads
+    q = F.linear(x, sd[f"{pre}.q.weight"], sd[f"{pre}.q.bias"]).reshape(b, n, heads, d).permute(0, 2, 1, 3)
+    if sr > 1:
+        x_ = x.permute(0, 2, 1).reshape(b, c, h, w)
+        x_ = F.conv2d(x_, sd[f"{pre}.sr.weight"], sd[f"{pre}.sr.bias"], stride=sr).reshape(b, c, -1).permute(0, 2, 1)
+        x_ = _ln(sd, f"{pre}.norm", x_, 1e-5)              # nn.LayerNorm(dim): default eps (:316)
+    else:
+        x_ = x
+    kv = F.linear(x_, sd[f"{pre}.kv.weight"], sd[f"{pre}.kv.bias"]).reshape(b, -1, 2, heads, d).permute(2, 0, 3, 1, 4)
+    k, v = kv[0], kv[1]
+    attn = ((q @ k.transpose(-2, -1)) * (d ** -0.5)).softmax(dim=-1)
+    x = (attn @ v).transpose(1, 2).reshape(b, n, c)
+    return F.linear(x, sd[f"{pre}.proj.weight"], sd[f"{pre}.proj.bias"])
+
+
+def _mit_mlp(sd: SD, pre: str, x: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """Mlp.forward + DWConv, models/ChangeFormer.py:283-291,512-523."""
+    b, n, _ = x.shape
+    x = F.linear(x, sd[f"{pre}.fc1.weight"], sd[f"{pre}.fc1.bias"])
+    c = x.shape[2]
+    x = x.transpose(1, 2).reshape(b, c, h, w)
+    x = F.conv2d(x, sd[f"{pre}.dwconv.dwconv.weight"], sd[f"{pre}.dwconv.dwconv.bias"], padding=1, groups=c)
+    x = F.gelu(x.flatten(2).transpose(1, 2))
+    return F.linear(x, sd[f"{pre}.fc2.weight"], sd[f"{pre}.fc2.bias"])
+
+
+def mit_encoder_features(sd: SD, x: torch.Tensor, pre: str = "Tenc_x2", depths=(3, 3, 4, 3), heads=(1, 2, 4, 8),
+                         srs=(8, 4, 2, 1)) -> List[torch.Tensor]:
+    """EncoderTransformer_v3.forward_features, models/ChangeFormer.py:1434-1469 (ChangeFormerV6: patch 7 at every stage,
+    block LayerNorm eps 1e-6, :1681-1683; OverlapPatchEmbed's own LayerNorm keeps the default eps, :226)."""
+    outs = []
+    for s in range(4):
+        pe = f"{pre}.patch_embed{s + 1}"
+        x = F.conv2d(x, sd[f"{pe}.proj.weight"], sd[f"{pe}.proj.bias"], stride=4 if s == 0 else 2, padding=3)
+        b, c, h, w = x.shape
+        t = _ln(sd, f"{pe}.norm", x.flatten(2).transpose(1, 2), 1e-5)
+        for i in range(depths[s]):
+            blk = f"{pre}.block{s + 1}.{i}"
+            t = t + _mit_attention(sd, f"{blk}.attn", _ln(sd, f"{blk}.norm1", t, 1e-6), h, w, heads[s], srs[s])
+            t = t + _mit_mlp(sd, f"{blk}.mlp", _ln(sd, f"{blk}.norm2", t, 1e-6), h, w)
+        t = _ln(sd, f"{pre}.norm{s + 1}", t, 1e-6)
+        x = t.reshape(b, h, w, -1).permute(0, 3, 1, 2).contiguous()
+        outs.append(x)
+    return outs
+
+
+def changeformer_decoder(sd: SD, f1: List[torch.Tensor], f2: List[torch.Tensor], pre: str = "TDec_x2") -> List[torch.Tensor]:
+    """DecoderTransformer_v3.forward, models/ChangeFormer.py:1558-1631: DecoderV1's wiring with heads named linear_c{k}."""
+    renamed = {k.replace(f"{pre}.linear_c", f"{pre}.decoder_heads_c"): v for k, v in sd.items()}
+    return changegnn_decoder(renamed, f1, f2, pre)
+
+
+def changeformer_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor) -> List[torch.Tensor]:
+    """ChangeFormerV6.forward, models/ChangeFormer.py:1691-1701: list of 5 tensors, full-resolution logits last."""
+    return changeformer_decoder(sd, mit_encoder_features(sd, x1), mit_encoder_features(sd, x2))

@@ -126,7 +126,7 @@ class EcamDesc(C.Structure):
     ]
 
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -143,6 +143,10 @@ SYMBOLS = [
     ("stcd_plan_add_maxpool_s2d", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("stcd_plan_add_seg_head", C.c_int, [C.c_void_p, C.c_void_p]),
     ("stcd_plan_add_graph_conv", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    ("stcd_plan_add_layernorm", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                          C.c_float]),
+    ("stcd_plan_add_sr_attention", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
+    ("stcd_plan_add_dwconv3x3", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]),
     ("stcd_plan_add_bilinear_up", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("stcd_plan_add_ecam_head", C.c_int, [C.c_void_p, C.c_void_p]),
     ("stcd_plan_finalize", C.c_int, [C.c_void_p]),

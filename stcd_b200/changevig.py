@@ -157,11 +157,11 @@ class _ResidualBlock(nn.Module):
 class _DecoderV1(nn.Module):
     """models/ChangeVIG.py:100-165 with decoder_heads="MLP"."""
 
-    def __init__(self, in_channels, e: int, output_nc: int):
+    def __init__(self, in_channels, e: int, output_nc: int, head: str = "decoder_heads_c"):
         super().__init__()
         c1, c2, c3, c4 = in_channels
-        self.decoder_heads_c4, self.decoder_heads_c3 = _MLP(c4, e), _MLP(c3, e)
-        self.decoder_heads_c2, self.decoder_heads_c1 = _MLP(c2, e), _MLP(c1, e)
+        for k, c in ((4, c4), (3, c3), (2, c2), (1, c1)):      # DecoderTransformer_v3 calls them linear_c{k}
+            setattr(self, f"{head}{k}", _MLP(c, e))
         for k in (4, 3, 2, 1):
             setattr(self, f"diff_c{k}", _conv_diff(2 * e, e))
         for k in (4, 3, 2, 1):
@@ -329,17 +329,30 @@ def lower_changegnn(sd: Dict[str, torch.Tensor], e: int, n_class: int, img_size:
             idx += 1
         feats.append((x, c, hh, ww))
 
-    # ---------------- DecoderV1
-    d = "decoder"
+    lower_diff_decoder(p, sd, feats, e, n_class, "decoder", "decoder.decoder_heads_c{k}")
+    return p
+
+
+def lower_diff_decoder(p: L.Program, sd: Dict[str, torch.Tensor], feats, e: int, n_class: int, d: str, head_fmt: str) -> None:
+    """DecoderV1 (ChangeVIG.py:192-281) == DecoderTransformer_v3 (ChangeFormer.py:1558-1631): per-scale Linear heads on both
+    streams, conv_diff over cat(_c_1, _c_2) (+ the coarser scale's bilinear x2), intermediate predictions, bilinear
+    resize to the finest scale, 1x1 fuse + BN, two (ConvTranspose2d(k4, s2) + ResidualBlock), 3x3 head.
+    feats: [(tensor, channels, h, w)] fine -> coarse, both streams (mult 2); head_fmt: parameter prefix of the heads."""
+    ones = lambda c: np.ones(c, np.float32)  # noqa: E731
+    npf = lambda t: t.numpy().astype(np.float32)  # noqa: E731
+
+    def conv_bn(pre: str, cout: int):
+        return L.fold_bn(sd.get(f"{pre}.0.bias"), L.bn_params(sd, f"{pre}.1"), cout)
+
     full_h, full_w = feats[0][2], feats[0][3]
     c_prev = None
     ups = []
     for k in (4, 3, 2, 1):
         ft, fc, fh, fw = feats[k - 1]
         hd = p.tensor(f"{d}.c{k}", 2, fh, fw, e)
-        wl = sd[f"{d}.decoder_heads_c{k}.proj.weight"][:, :, None, None]
-        L.add_conv(p, f"{d}.decoder_heads_c{k}", [L.Segment(ft, fc)], L.conv_taps(wl, pad=0), e, fh, fw, 1, ones(e),
-                   npf(sd[f"{d}.decoder_heads_c{k}.proj.bias"]), pair=True, out0=hd, macs_per_pair=2 * fh * fw * fc * e)
+        wl = sd[head_fmt.format(k=k) + ".proj.weight"][:, :, None, None]
+        L.add_conv(p, head_fmt.format(k=k), [L.Segment(ft, fc)], L.conv_taps(wl, pad=0), e, fh, fw, 1, ones(e),
+                   npf(sd[head_fmt.format(k=k) + ".proj.bias"]), pair=True, out0=hd, macs_per_pair=2 * fh * fw * fc * e)
         dk = f"{d}.diff_c{k}"
         ta = p.tensor(f"{dk}.a", 1, fh, fw, e)
         s2, b2 = L.fold_bn(None, L.bn_params(sd, f"{dk}.2"), e)
@@ -399,4 +412,3 @@ def lower_changegnn(sd: Dict[str, torch.Tensor], e: int, n_class: int, img_size:
                n_class, hh, ww, 1, ones(n_class), npf(sd[f"{d}.change_probability.conv2d.bias"]), out_ext=4,
                macs_per_pair=hh * ww * 9 * e * n_class)
     p.ext.append(L.ExtOutput("cp", n_class, hh, ww))
-    return p

@@ -738,7 +738,20 @@ struct ConvKernelEntry {
   X(2, 2, E_RES | E_RELU | E_OUT0)                     \
   X(4, 2, E_RES | E_RELU | E_OUT0)                     \
   X(2, 2, E_OUT0)                                      \
-  X(4, 2, E_OUT0)
+  X(4, 2, E_OUT0)                                      \
+  /* ChangeGNN / ChangeFormer: 1x1 conv + residual without activation, conv -> act -> BN (+ residual) decoders */ \
+  X(2, 2, E_RES | E_OUT0)                              \
+  X(4, 2, E_RES | E_OUT0)                              \
+  X(1, 1, E_RES | E_OUT0)                              \
+  X(2, 1, E_RES | E_OUT0)                              \
+  X(4, 1, E_RES | E_OUT0)                              \
+  X(1, 1, E_AFF2 | E_RELU | E_OUT0)                    \
+  X(2, 1, E_AFF2 | E_RELU | E_OUT0)                    \
+  X(4, 1, E_AFF2 | E_RELU | E_OUT0)                    \
+  X(1, 1, E_AFF2 | E_RES | E_RELU | E_OUT0)            \
+  X(2, 1, E_AFF2 | E_RES | E_RELU | E_OUT0)            \
+  X(4, 1, E_AFF2 | E_RES | E_RELU | E_OUT0)            \
+  X(4, 1, E_OUT0)
 
 inline const ConvKernelEntry* conv_kernel_table(int* n) {
   static const ConvKernelEntry table[] = {

@@ -15,9 +15,10 @@
 
 namespace stcd {
 
-// denom[b][n] = max(||x[b, :, n]||_2, 1e-12)   (F.normalize(x, p=2, dim=1)).  One thread per node, coalesced over n.
-__global__ void __launch_bounds__(256) node_norm_kernel(const float* __restrict__ x, float* __restrict__ denom, int B, int C,
-                                                        int N) {
+// xn[b][:, n] = x[b][:, n] / max(||x[b, :, n]||_2, 1e-12)   (F.normalize(x, p=2, dim=1)).  One thread per node, coalesced
+// over n; the channel sum runs in index order, the division is IEEE.
+__global__ void __launch_bounds__(256) normalize_nodes_kernel(const float* __restrict__ x, float* __restrict__ xn, int B, int C,
+                                                             int N) {
   const size_t total = static_cast<size_t>(B) * N;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -28,7 +29,9 @@ __global__ void __launch_bounds__(256) node_norm_kernel(const float* __restrict_
       const float v = __ldg(p + static_cast<size_t>(c) * N);
       s = fmaf(v, v, s);
     }
-    denom[i] = fmaxf(sqrtf(s), 1e-12f);
+    const float den = fmaxf(sqrtf(s), 1e-12f);
+    float* o = xn + b * C * N + n;
+    for (int c = 0; c < C; ++c) o[static_cast<size_t>(c) * N] = __fdiv_rn(__ldg(p + static_cast<size_t>(c) * N), den);
   }
 }
 
@@ -36,17 +39,19 @@ constexpr int kKnnQ = 64;     // queries per CTA (8 per warp)
 constexpr int kKnnM = 256;    // max keys (8 per lane)
 constexpr int kKnnCC = 32;    // channels per shared-memory chunk
 
-// grid (ceil(N / 64), B), 256 threads.  nn_idx[b][n][t] = index of the (t*dilation)-th nearest key of query n.
-__global__ void __launch_bounds__(256) knn_graph_kernel(const float* __restrict__ x, const float* __restrict__ xden,
-                                                        const float* __restrict__ y, const float* __restrict__ yden,
+// grid (ceil(N / 64), B), 256 threads.  xn, yn: L2-normalised nodes.  nn_idx[b][n][t] = index of the (t*dilation)-th
+// nearest key of query n.  Warp w owns queries 8w..8w+7, lane l owns keys 8l..8l+7: per channel the 8 query values are
+// two broadcast LDS.128, the 8 key values two LDS.128, feeding 64 FMAs.  The k*dilation selection rounds run the eight
+// queries' warp arg-min chains interleaved (independent shuffle chains hide each other's latency).
+__global__ void __launch_bounds__(256) knn_graph_kernel(const float* __restrict__ xn, const float* __restrict__ yn,
                                                         const float* __restrict__ relpos, int C, int N, int M, int k,
                                                         int dilation, long long* __restrict__ nn_idx) {
-  __shared__ float xs[kKnnQ][kKnnCC + 1];
-  __shared__ float ys[kKnnM][kKnnCC + 1];
+  __shared__ __align__(16) float xs[kKnnCC][kKnnQ];
+  __shared__ __align__(16) float ys[kKnnCC][kKnnM];
   const int b = blockIdx.y, n0 = blockIdx.x * kKnnQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* xb = x + static_cast<size_t>(b) * C * N;
-  const float* yb = y + static_cast<size_t>(b) * C * M;
+  const float* xb = xn + static_cast<size_t>(b) * C * N;
+  const float* yb = yn + static_cast<size_t>(b) * C * M;
   float dot[8][8], xsq[8], ysq[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -60,21 +65,20 @@ __global__ void __launch_bounds__(256) knn_graph_kernel(const float* __restrict_
     for (int i = threadIdx.x; i < kKnnQ * kKnnCC; i += blockDim.x) {
       const int q = i % kKnnQ, cc = i / kKnnQ;
       const int n = n0 + q, c = c0 + cc;
-      xs[q][cc] = (n < N && c < C) ? __fdiv_rn(__ldg(xb + static_cast<size_t>(c) * N + n), __ldg(xden + static_cast<size_t>(b) * N + n)) : 0.f;
+      xs[cc][q] = (n < N && c < C) ? __ldg(xb + static_cast<size_t>(c) * N + n) : 0.f;
     }
     for (int i = threadIdx.x; i < kKnnM * kKnnCC; i += blockDim.x) {
       const int j = i % kKnnM, cc = i / kKnnM;
       const int c = c0 + cc;
-      ys[j][cc] = (j < M && c < C) ? __fdiv_rn(__ldg(yb + static_cast<size_t>(c) * M + j), __ldg(yden + static_cast<size_t>(b) * M + j)) : 0.f;
+      ys[cc][j] = (j < M && c < C) ? __ldg(yb + static_cast<size_t>(c) * M + j) : 0.f;
     }
     __syncthreads();
 #pragma unroll 4
     for (int cc = 0; cc < kKnnCC; ++cc) {
-      float xv[8], yv[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) xv[q] = xs[warp * 8 + q][cc];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) yv[j] = ys[lane + 32 * j][cc];
+      const float4 xa = *reinterpret_cast<const float4*>(&xs[cc][warp * 8]), xb4 = *reinterpret_cast<const float4*>(&xs[cc][warp * 8 + 4]);
+      const float4 ya = *reinterpret_cast<const float4*>(&ys[cc][lane * 8]), yb4 = *reinterpret_cast<const float4*>(&ys[cc][lane * 8 + 4]);
+      const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb4.x, xb4.y, xb4.z, xb4.w};
+      const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb4.x, yb4.y, yb4.z, yb4.w};
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         xsq[q] = fmaf(xv[q], xv[q], xsq[q]);
@@ -85,43 +89,57 @@ __global__ void __launch_bounds__(256) knn_graph_kernel(const float* __restrict_
       for (int j = 0; j < 8; ++j) ysq[j] = fmaf(yv[j], yv[j], ysq[j]);
     }
   }
-  const int kd = k * dilation;
+  // distances, in place: the reference's order of operations (x_sq + (-2 * inner)) + y_sq, then + relative_pos
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int n = n0 + warp * 8 + q;
-    if (n >= N) continue;      // warp-uniform
-    float dist[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int key = lane + 32 * j;
-      // the reference's order of operations: (x_sq + (-2 * inner)) + y_sq, then + relative_pos
+      const int key = lane * 8 + j;
       float dv = __fadd_rn(__fadd_rn(xsq[q], -2.f * dot[q][j]), ysq[j]);
-      if (relpos != nullptr && key < M) dv = __fadd_rn(dv, __ldg(relpos + static_cast<size_t>(n) * M + key));
-      dist[j] = key < M ? dv : CUDART_INF_F;
+      if (relpos != nullptr && key < M && n < N) dv = __fadd_rn(dv, __ldg(relpos + static_cast<size_t>(n) * M + key));
+      dot[q][j] = key < M ? dv : CUDART_INF_F;
     }
-    long long* out = nn_idx + (static_cast<size_t>(b) * N + n) * k;
-    for (int t = 0; t < kd; ++t) {
-      float best = dist[0];
-      int bi = lane;
+  }
+  const int kd = k * dilation;
+  for (int t = 0; t < kd; ++t) {
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      best[q] = dot[q][0];
+      bi[q] = lane * 8;
 #pragma unroll
       for (int j = 1; j < 8; ++j)
-        if (dist[j] < best) {
-          best = dist[j];
-          bi = lane + 32 * j;
+        if (dot[q][j] < best[q]) {
+          best[q] = dot[q][j];
+          bi[q] = lane * 8 + j;
         }
+    }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov < best || (ov == best && oi < bi)) {
-          best = ov;
-          bi = oi;
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best[q], o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi[q], o);
+        if (ov < best[q] || (ov == best[q] && oi < bi[q])) {   // ties: smaller index
+          best[q] = ov;
+          bi[q] = oi;
         }
       }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (lane + 32 * j == bi) dist[j] = CUDART_INF_F;
-      if (lane == 0 && (t % dilation) == 0) out[t / dilation] = bi;
+        if (lane * 8 + j == bi[q]) dot[q][j] = CUDART_INF_F;
+    }
+    if (lane == 0 && (t % dilation) == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int n = n0 + warp * 8 + q;
+        if (n < N) nn_idx[(static_cast<size_t>(b) * N + n) * k + t / dilation] = bi[q];
+      }
     }
   }
 }

@@ -20,6 +20,7 @@
 #include "aux_kernels.cuh"
 #include "conv_ws.cuh"
 #include "graph_kernels.cuh"
+#include "transformer_kernels.cuh"
 
 namespace {
 
@@ -101,12 +102,31 @@ struct GraphOp {
   float* relpos_dev = nullptr;
   float* xf = nullptr;         // fp32 [imgs][C][N]
   float* yf = nullptr;         // fp32 [imgs][C][M] (r > 1)
-  float* den = nullptr;        // [imgs * (N + M)]
+  float* xn = nullptr;         // fp32 [imgs][C][N], L2-normalised nodes
+  float* yn = nullptr;         // fp32 [imgs][C][M] (r > 1)
   long long* idx = nullptr;    // [imgs][N][k]
 };
 
 struct BilinearOp {
   int src, dst, c, scale;
+};
+
+struct LayerNormOp {
+  int src, dst, dst2, c;
+  float eps;
+  std::vector<float> gb;   // gamma | beta
+  float* gb_dev = nullptr;
+};
+
+struct AttentionOp {
+  int q, kv, dst, c, heads;
+  float scale;
+};
+
+struct DWConvOp {
+  int src, dst, c, gelu;
+  std::vector<float> wb;   // weight [c][9] | bias [c]
+  float* wb_dev = nullptr;
 };
 
 struct SegHeadOp {
@@ -126,7 +146,7 @@ struct EcamOp {
 };
 
 struct Op {
-  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head, 5 graph conv, 6 bilinear up
+  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head, 5 graph conv, 6 bilinear up, 7 layer norm, 8 attention, 9 dw conv
   int idx;
 };
 
@@ -144,6 +164,9 @@ struct stcd_plan {
   std::vector<SegHeadOp> heads;
   std::vector<GraphOp> graphs;
   std::vector<BilinearOp> bilinears;
+  std::vector<LayerNormOp> lns;
+  std::vector<AttentionOp> attns;
+  std::vector<DWConvOp> dws;
   std::vector<Op> ops;
   uint8_t* workspace = nullptr;
   size_t workspace_bytes = 0;
@@ -279,14 +302,47 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
         stcd::avgpool_nodes_kernel<<<nb((size_t)B * k.c * M, 8), 256, 0, st>>>(k.xf, k.yf, (size_t)B * k.c, ts.h, ts.w, k.r);
         y = k.yf;
       }
-      float* xden = k.den;
-      float* yden = k.r > 1 ? k.den + (size_t)B * N : k.den;
-      stcd::node_norm_kernel<<<nb((size_t)B * N, 8), 256, 0, st>>>(k.xf, xden, B, k.c, N);
-      if (k.r > 1) stcd::node_norm_kernel<<<nb((size_t)B * M, 8), 256, 0, st>>>(k.yf, yden, B, k.c, M);
-      stcd::knn_graph_kernel<<<dim3((N + stcd::kKnnQ - 1) / stcd::kKnnQ, B), 256, 0, st>>>(k.xf, xden, y, yden, k.relpos_dev, k.c, N, M, k.k,
-                                                                                       k.dilation, k.idx);
+      stcd::normalize_nodes_kernel<<<nb((size_t)B * N, 8), 256, 0, st>>>(k.xf, k.xn, B, k.c, N);
+      if (k.r > 1) stcd::normalize_nodes_kernel<<<nb((size_t)B * M, 8), 256, 0, st>>>(k.yf, k.yn, B, k.c, M);
+      stcd::knn_graph_kernel<<<dim3((N + stcd::kKnnQ - 1) / stcd::kKnnQ, B), 256, 0, st>>>(k.xn, k.r > 1 ? k.yn : k.xn, k.relpos_dev, k.c, N, M,
+                                                                                       k.k, k.dilation, k.idx);
       stcd::max_relative_nc8_kernel<<<nb((size_t)B * (k.c / 8) * N, 8), 256, 0, st>>>(k.xf, y, k.idx, B, k.c, N, M, k.k,
                                                                                       (__nv_bfloat16*)td.ptr, td.c / 8);
+      CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 7) {
+      const LayerNormOp& k = plan->lns[o.idx];
+      const Tensor& ts = plan->tensors[k.src];
+      const Tensor& td = plan->tensors[k.dst];
+      const int B = ts.mult * plan->chunk;
+      const size_t total = (size_t)B * ts.h * ts.w;
+      __nv_bfloat16* d2 = k.dst2 >= 0 ? (__nv_bfloat16*)plan->tensors[k.dst2].ptr : nullptr;
+      stcd::layernorm_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, 148 * 16)), 256, 0, st>>>(
+          (const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, d2, k.gb_dev, k.gb_dev + k.c, B, k.c, ts.c / 8, td.c / 8,
+          k.dst2 >= 0 ? plan->tensors[k.dst2].c / 8 : 0, ts.h, ts.w, k.eps);
+      CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 8) {
+      const AttentionOp& k = plan->attns[o.idx];
+      const Tensor& tq = plan->tensors[k.q];
+      const Tensor& tk = plan->tensors[k.kv];
+      const Tensor& td = plan->tensors[k.dst];
+      const int B = tq.mult * plan->chunk, N = tq.h * tq.w, NK = tk.h * tk.w, D = k.c / k.heads;
+      const dim3 grid((N + 127) / 128, k.heads, B);
+      if (D == 64)
+        stcd::sr_attention_kernel<64><<<grid, 128, 0, st>>>((const __nv_bfloat16*)tq.ptr, (const __nv_bfloat16*)tk.ptr, (__nv_bfloat16*)td.ptr,
+                                                           k.c, tq.c / 8, tk.c / 8, td.c / 8, N, NK, k.scale);
+      else
+        stcd::sr_attention_kernel<80><<<grid, 128, 0, st>>>((const __nv_bfloat16*)tq.ptr, (const __nv_bfloat16*)tk.ptr, (__nv_bfloat16*)td.ptr,
+                                                           k.c, tq.c / 8, tk.c / 8, td.c / 8, N, NK, k.scale);
+      CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 9) {
+      const DWConvOp& k = plan->dws[o.idx];
+      const Tensor& ts = plan->tensors[k.src];
+      const Tensor& td = plan->tensors[k.dst];
+      const int B = ts.mult * plan->chunk;
+      const size_t total = (size_t)B * (k.c / 8) * ts.h * ts.w;
+      stcd::dwconv3x3_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, 148 * 16)), 256, 0, st>>>(
+          (const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, k.wb_dev, k.wb_dev + (size_t)k.c * 9, B, k.c / 8, ts.c / 8, td.c / 8, ts.h,
+          ts.w, k.gelu);
       CUDA_TRY(cudaGetLastError());
     } else if (o.kind == 6) {
       const BilinearOp& k = plan->bilinears[o.idx];
@@ -398,11 +454,16 @@ void stcd_plan_destroy(stcd_plan* plan) {
   }
   for (SegHeadOp& e : plan->heads)
     if (e.w_dev) cudaFree(e.w_dev);
+  for (LayerNormOp& k : plan->lns)
+    if (k.gb_dev) cudaFree(k.gb_dev);
+  for (DWConvOp& k : plan->dws)
+    if (k.wb_dev) cudaFree(k.wb_dev);
   for (GraphOp& g : plan->graphs) {
     if (g.relpos_dev) cudaFree(g.relpos_dev);
     if (g.xf) cudaFree(g.xf);
     if (g.yf) cudaFree(g.yf);
-    if (g.den) cudaFree(g.den);
+    if (g.xn) cudaFree(g.xn);
+    if (g.yn) cudaFree(g.yn);
     if (g.idx) cudaFree(g.idx);
   }
   if (plan->workspace) cudaFree(plan->workspace);
@@ -529,6 +590,73 @@ int stcd_plan_add_graph_conv(stcd_plan* plan, int src_tensor, int dst_tensor, in
   if (relpos) g.relpos.assign(relpos, relpos + (size_t)N * M);
   plan->graphs.push_back(std::move(g));
   plan->ops.push_back({5, (int)plan->graphs.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_layernorm(stcd_plan* plan, int src_tensor, int dst_tensor, int dst_s2d, int c, const float* gamma, const float* beta,
+                            float eps) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, src_tensor) || !valid_tensor(plan, dst_tensor) || (dst_s2d >= 0 && !valid_tensor(plan, dst_s2d)) || !gamma || !beta)
+    return -fail(STCD_ERR_INVALID, "layer norm: bad tensor id / NULL gamma, beta");
+  const Tensor& ts = plan->tensors[src_tensor];
+  const Tensor& td = plan->tensors[dst_tensor];
+  if (c < 8 || (c % 8) || ts.c < c || td.c < c || ts.h != td.h || ts.w != td.w || ts.mult != td.mult || !(eps > 0.f))
+    return -fail(STCD_ERR_INVALID, "layer norm: src [%d*chunk,%d,%d,%d] / dst [%d*chunk,%d,%d,%d] must match and hold c=%d channels", ts.mult,
+                 ts.h, ts.w, ts.c, td.mult, td.h, td.w, td.c, c);
+  if (dst_s2d >= 0) {
+    const Tensor& t2 = plan->tensors[dst_s2d];
+    if ((ts.h % 2) || (ts.w % 2) || t2.h != ts.h / 2 || t2.w != ts.w / 2 || t2.c != 4 * c || t2.mult != ts.mult)
+      return -fail(STCD_ERR_INVALID, "layer norm: space-to-depth copy must be [%d*chunk,%d,%d,%d]", ts.mult, ts.h / 2, ts.w / 2, 4 * c);
+  }
+  LayerNormOp k;
+  k.src = src_tensor;
+  k.dst = dst_tensor;
+  k.dst2 = dst_s2d;
+  k.c = c;
+  k.eps = eps;
+  k.gb.assign(gamma, gamma + c);
+  k.gb.insert(k.gb.end(), beta, beta + c);
+  plan->lns.push_back(std::move(k));
+  plan->ops.push_back({7, (int)plan->lns.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_sr_attention(stcd_plan* plan, int q_tensor, int kv_tensor, int dst_tensor, int c, int heads, float scale) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, q_tensor) || !valid_tensor(plan, kv_tensor) || !valid_tensor(plan, dst_tensor)) return -fail(STCD_ERR_INVALID, "bad tensor id");
+  const Tensor& tq = plan->tensors[q_tensor];
+  const Tensor& tk = plan->tensors[kv_tensor];
+  const Tensor& td = plan->tensors[dst_tensor];
+  if (heads < 1 || c < 8 || (c % heads) || ((c / heads) != 64 && (c / heads) != 80))
+    return -fail(STCD_ERR_INVALID, "attention: c=%d heads=%d: head dim must be 64 or 80", c, heads);
+  if (tq.c != c || td.c != c || tk.c != 2 * c || tq.h != td.h || tq.w != td.w || tq.mult != td.mult || tq.mult != tk.mult)
+    return -fail(STCD_ERR_INVALID, "attention: q/dst must be [m*chunk,h,w,%d] and kv [m*chunk,hk,wk,%d]", c, 2 * c);
+  if (tk.h * tk.w > stcd::kAttnMaxKeys) return -fail(STCD_ERR_INVALID, "attention: %d keys (max %d)", tk.h * tk.w, stcd::kAttnMaxKeys);
+  plan->attns.push_back({q_tensor, kv_tensor, dst_tensor, c, heads, scale});
+  plan->ops.push_back({8, (int)plan->attns.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_dwconv3x3(stcd_plan* plan, int src_tensor, int dst_tensor, int c, const float* weight, const float* bias, int gelu) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, src_tensor) || !valid_tensor(plan, dst_tensor) || !weight || !bias) return -fail(STCD_ERR_INVALID, "dw conv: bad tensor id / NULL weights");
+  const Tensor& ts = plan->tensors[src_tensor];
+  const Tensor& td = plan->tensors[dst_tensor];
+  if (c < 8 || (c % 8) || ts.c < c || td.c < c || ts.h != td.h || ts.w != td.w || ts.mult != td.mult)
+    return -fail(STCD_ERR_INVALID, "dw conv: src [%d*chunk,%d,%d,%d] / dst [%d*chunk,%d,%d,%d] must match and hold c=%d channels", ts.mult, ts.h,
+                 ts.w, ts.c, td.mult, td.h, td.w, td.c, c);
+  DWConvOp k;
+  k.src = src_tensor;
+  k.dst = dst_tensor;
+  k.c = c;
+  k.gelu = gelu ? 1 : 0;
+  k.wb.assign(weight, weight + (size_t)c * 9);
+  k.wb.insert(k.wb.end(), bias, bias + c);
+  plan->dws.push_back(std::move(k));
+  plan->ops.push_back({9, (int)plan->dws.size() - 1});
   return (int)plan->ops.size() - 1;
 }
 
@@ -1015,12 +1143,21 @@ int stcd_plan_finalize(stcd_plan* plan) {
     const size_t B = (size_t)ts.mult * plan->chunk, N = (size_t)ts.h * ts.w, M = N / (g.r * g.r);
     CUDA_TRY(cudaMalloc(&g.xf, B * g.c * N * sizeof(float)));
     if (g.r > 1) CUDA_TRY(cudaMalloc(&g.yf, B * g.c * M * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&g.den, B * (N + M) * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&g.xn, B * g.c * N * sizeof(float)));
+    if (g.r > 1) CUDA_TRY(cudaMalloc(&g.yn, B * g.c * M * sizeof(float)));
     CUDA_TRY(cudaMalloc(&g.idx, B * N * g.k * sizeof(long long)));
     if (!g.relpos.empty()) {
       CUDA_TRY(cudaMalloc(&g.relpos_dev, g.relpos.size() * sizeof(float)));
       CUDA_TRY(cudaMemcpy(g.relpos_dev, g.relpos.data(), g.relpos.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
+  }
+  for (LayerNormOp& k : plan->lns) {
+    CUDA_TRY(cudaMalloc(&k.gb_dev, k.gb.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(k.gb_dev, k.gb.data(), k.gb.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  for (DWConvOp& k : plan->dws) {
+    CUDA_TRY(cudaMalloc(&k.wb_dev, k.wb.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(k.wb_dev, k.wb.data(), k.wb.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   for (SegHeadOp& k : plan->heads) {
     CUDA_TRY(cudaMalloc(&k.w_dev, k.w.size() * sizeof(float)));
@@ -1322,11 +1459,11 @@ int stcd_knn_graph(const float* x, const float* y, const float* relpos, int B, i
     return fail(STCD_ERR_NO_DEVICE, "no CUDA device visible: libstcd_b200 has no CPU fallback");
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float* xden = scratch;
-  float* yden = y ? scratch + (size_t)B * N : scratch;
-  stcd::node_norm_kernel<<<(unsigned)std::min<size_t>(((size_t)B * N + 255) / 256, 148 * 8), 256, 0, st>>>(x, xden, B, C, N);
-  if (y) stcd::node_norm_kernel<<<(unsigned)std::min<size_t>(((size_t)B * M + 255) / 256, 148 * 8), 256, 0, st>>>(y, yden, B, C, M);
-  stcd::knn_graph_kernel<<<dim3((N + stcd::kKnnQ - 1) / stcd::kKnnQ, B), 256, 0, st>>>(x, xden, y ? y : x, yden, relpos, C, N, M, k, dilation,
+  float* xn = scratch;
+  float* yn = y ? scratch + (size_t)B * C * N : scratch;
+  stcd::normalize_nodes_kernel<<<(unsigned)std::min<size_t>(((size_t)B * N + 255) / 256, 148 * 8), 256, 0, st>>>(x, xn, B, C, N);
+  if (y) stcd::normalize_nodes_kernel<<<(unsigned)std::min<size_t>(((size_t)B * M + 255) / 256, 148 * 8), 256, 0, st>>>(y, yn, B, C, M);
+  stcd::knn_graph_kernel<<<dim3((N + stcd::kKnnQ - 1) / stcd::kKnnQ, B), 256, 0, st>>>(xn, yn, relpos, C, N, M, k, dilation,
                                                                                    reinterpret_cast<long long*>(nn_idx));
   CUDA_TRY(cudaGetLastError());
   return STCD_OK;

@@ -1,0 +1,212 @@
+// MiT / ChangeFormer encoder ops that are not convolutions (models/ChangeFormer.py): LayerNorm over channels,
+// spatial-reduction attention, depth-wise 3x3 + GELU.  All on bf16 [img][c/8][h*w][8] plan tensors, fp32 arithmetic.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace stcd {
+
+__device__ __forceinline__ void unpack8(uint4 q, float* v) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+    v[2 * j] = __low2float(h);
+    v[2 * j + 1] = __high2float(h);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// nn.LayerNorm(C, eps) per pixel: y = (x - mean) / sqrt(var + eps) * gamma + beta, biased variance, fp32 statistics
+// (two passes over the pixel's C channels: mean, then centred sum of squares; the second and third reads hit L1/L2).
+// One thread per pixel, coalesced over pixels for every channel group.  Optionally also writes the space-to-depth copy
+// dst2 ([h/2][w/2] pixels, channel block (y%2)*2 + x%2).  HBM-bound: 2 B read + 2 (or 4) B written per element.
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                        __nv_bfloat16* __restrict__ dst2, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int B, int C, int src_c8, int dst_c8,
+                                                        int dst2_c8, int h, int w, float eps) {
+  const int hw = h * w, g8 = C >> 3;
+  const size_t total = static_cast<size_t>(B) * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / hw;
+    const int pix = static_cast<int>(i - b * hw);
+    const __nv_bfloat16* s = src + (b * src_c8 * hw + pix) * 8;
+    float sum = 0.f;
+    for (int g = 0; g < g8; ++g) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(s + static_cast<size_t>(g) * hw * 8)), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[j];
+    }
+    const float mean = sum / static_cast<float>(C);
+    float sq = 0.f;
+    for (int g = 0; g < g8; ++g) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(s + static_cast<size_t>(g) * hw * 8)), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[j] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+    const float rstd = rsqrtf(sq / static_cast<float>(C) + eps);
+    __nv_bfloat16* o = dst + (b * dst_c8 * hw + pix) * 8;
+    __nv_bfloat16* o2 = nullptr;
+    size_t hw2 = 0;
+    if (dst2 != nullptr) {
+      const int y = pix / w, x = pix - y * w;
+      hw2 = static_cast<size_t>(hw >> 2);
+      o2 = dst2 + ((b * dst2_c8 + static_cast<size_t>(((y & 1) * 2 + (x & 1)) * g8)) * hw2 + static_cast<size_t>(y >> 1) * (w >> 1) + (x >> 1)) * 8;
+    }
+    for (int g = 0; g < g8; ++g) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(s + static_cast<size_t>(g) * hw * 8)), v);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + g * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + g * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + g * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + g * 8 + 4));
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf((v[j] - mean) * rstd, gm[j], bt[j]);
+      const uint4 q = pack8(v);
+      *reinterpret_cast<uint4*>(o + static_cast<size_t>(g) * hw * 8) = q;
+      if (o2 != nullptr) *reinterpret_cast<uint4*>(o2 + static_cast<size_t>(g) * hw2 * 8) = q;
+    }
+  }
+}
+
+// Spatial-reduction attention (ChangeFormer.py:338-358): out[n] = softmax_j(q[n].k[j] * scale) v[j] per head, NK <= 64
+// keys.  grid (ceil(N / 128), heads, B), 128 threads = 128 queries; the head's K and V (fp32, [NK][D]) sit in shared
+// memory and every lane reads the same address (broadcast).  q streams through registers 8 channels at a time, the 64
+// scores stay in registers; the [N, NK] score matrix never exists in memory.
+constexpr int kAttnMaxKeys = 64;
+template <int D>   // head dim: 64 or 80
+__global__ void __launch_bounds__(128) sr_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
+                                                           __nv_bfloat16* __restrict__ out, int C, int q_c8, int kv_c8,
+                                                           int out_c8, int N, int NK, float scale) {
+  __shared__ __align__(16) float sk[kAttnMaxKeys][D];
+  __shared__ __align__(16) float sv[kAttnMaxKeys][D];
+  const int b = blockIdx.z, hd = blockIdx.y;
+  const int g0 = hd * (D / 8);                 // first channel group of this head inside q / k; v sits C/8 groups later
+  for (int i = threadIdx.x; i < NK * (D / 8); i += blockDim.x) {
+    const int j = i % NK, g = i / NK;
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(kv + ((static_cast<size_t>(b) * kv_c8 + g0 + g) * NK + j) * 8)), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sk[j][g * 8 + e] = v[e];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(kv + ((static_cast<size_t>(b) * kv_c8 + (C >> 3) + g0 + g) * NK + j) * 8)), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sv[j][g * 8 + e] = v[e];
+  }
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s[kAttnMaxKeys];
+#pragma unroll
+  for (int j = 0; j < kAttnMaxKeys; ++j) s[j] = 0.f;
+  for (int g = 0; g < D / 8; ++g) {
+    float qv[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(q + ((static_cast<size_t>(b) * q_c8 + g0 + g) * N + n) * 8)), qv);
+#pragma unroll
+    for (int j = 0; j < kAttnMaxKeys; ++j) {
+      if (j < NK) {
+        const float4 k0 = *reinterpret_cast<const float4*>(&sk[j][g * 8]), k1 = *reinterpret_cast<const float4*>(&sk[j][g * 8 + 4]);
+        s[j] = fmaf(qv[0], k0.x, s[j]);
+        s[j] = fmaf(qv[1], k0.y, s[j]);
+        s[j] = fmaf(qv[2], k0.z, s[j]);
+        s[j] = fmaf(qv[3], k0.w, s[j]);
+        s[j] = fmaf(qv[4], k1.x, s[j]);
+        s[j] = fmaf(qv[5], k1.y, s[j]);
+        s[j] = fmaf(qv[6], k1.z, s[j]);
+        s[j] = fmaf(qv[7], k1.w, s[j]);
+      }
+    }
+  }
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int j = 0; j < kAttnMaxKeys; ++j)
+    if (j < NK) {
+      s[j] *= scale;
+      mx = fmaxf(mx, s[j]);
+    }
+  float den = 0.f;
+#pragma unroll
+  for (int j = 0; j < kAttnMaxKeys; ++j) {
+    s[j] = (j < NK) ? expf(s[j] - mx) : 0.f;
+    den += s[j];
+  }
+  const float inv = 1.f / den;
+  for (int g = 0; g < D / 8; ++g) {
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < kAttnMaxKeys; ++j) {
+      if (j < NK) {
+        const float4 v0 = *reinterpret_cast<const float4*>(&sv[j][g * 8]), v1 = *reinterpret_cast<const float4*>(&sv[j][g * 8 + 4]);
+        o[0] = fmaf(s[j], v0.x, o[0]);
+        o[1] = fmaf(s[j], v0.y, o[1]);
+        o[2] = fmaf(s[j], v0.z, o[2]);
+        o[3] = fmaf(s[j], v0.w, o[3]);
+        o[4] = fmaf(s[j], v1.x, o[4]);
+        o[5] = fmaf(s[j], v1.y, o[5]);
+        o[6] = fmaf(s[j], v1.z, o[6]);
+        o[7] = fmaf(s[j], v1.w, o[7]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] *= inv;
+    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * out_c8 + g0 + g) * N + n) * 8) = pack8(o);
+  }
+}
+
+// Depth-wise 3x3 conv (padding 1) + bias [+ GELU]: Mlp.dwconv + act (ChangeFormer.py:283-289,512-523).
+// One thread per (pixel, 8-channel group): 9 neighbour loads of 16 B, weights [c][9] from L1.  HBM-bound: 2 B read +
+// 2 B written per element.
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                        const float* __restrict__ wgt, const float* __restrict__ bias, int B, int g8,
+                                                        int src_c8, int dst_c8, int h, int w, int gelu) {
+  const int hw = h * w;
+  const size_t total = static_cast<size_t>(B) * g8 * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int pix = static_cast<int>(i % hw);
+    const size_t r = i / hw;
+    const int g = static_cast<int>(r % g8);
+    const size_t b = r / g8;
+    const int y = pix / w, x = pix - y * w;
+    const __nv_bfloat16* base = src + (b * src_c8 + g) * static_cast<size_t>(hw) * 8;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = __ldg(bias + g * 8 + e);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= w) continue;
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(yy) * w + xx) * 8)), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], __ldg(wgt + (g * 8 + e) * 9 + ky * 3 + kx), acc[e]);
+      }
+    }
+    if (gelu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.5f * acc[e] * (1.f + erff(acc[e] * 0.70710678118654752f));
+    }
+    *reinterpret_cast<uint4*>(dst + ((b * dst_c8 + g) * static_cast<size_t>(hw) + pix) * 8) = pack8(acc);
+  }
+}
+
+}  // namespace stcd

@@ -50,7 +50,7 @@ class DenseDilatedKnnGraph(torch.nn.Module):
             if rp.numel() != n * m:
                 raise ValueError(f"relative_pos has {rp.numel()} elements, expected [1, {n}, {m}]")
         nn_idx = torch.empty(b, n, self.k, dtype=torch.int64, device=x.device)
-        scratch = torch.empty(b * (n + m), dtype=torch.float32, device=x.device)
+        scratch = torch.empty(b * c * (n + (m if y is not None else 0)), dtype=torch.float32, device=x.device)
         lib = _lib.lib()
         _lib.check(lib.stcd_knn_graph(x.data_ptr(), y.data_ptr() if y is not None else None,
                                       rp.data_ptr() if rp is not None else None, b, c, n, m, self.k, self.dilation,

@@ -162,6 +162,49 @@ class GraphConvSpec:
 
 
 @dataclass
+class LayerNormSpec:
+    """nn.LayerNorm(c, eps) over the channels of every pixel / token (ChangeFormer.py:226,475,480; biased variance,
+    fp32 statistics), bf16 in -> bf16 out.  dst_s2d: optional second copy stored space-to-depth ([h/2, w/2, 4c]) for a
+    following stride-2 patch-embedding conv."""
+    name: str
+    src: str
+    dst: str
+    c: int
+    gamma: np.ndarray
+    beta: np.ndarray
+    eps: float
+    dst_s2d: Optional[str] = None
+
+
+@dataclass
+class AttentionSpec:
+    """Spatial-reduction attention of a MiT block (ChangeFormer.py:338-358): softmax(q k^T * scale) v per head.
+    q: [imgs, h, w, c] (head hd = channels [hd*d, (hd+1)*d)); kv: [imgs, hk, wk, 2c] (k = channels [0, c), v = [c, 2c));
+    dst: [imgs, h, w, c].  fp32 scores / softmax on bf16 operands."""
+    name: str
+    q: str
+    kv: str
+    dst: str
+    c: int
+    heads: int
+    scale: float
+    macs_per_pair: int = 0
+
+
+@dataclass
+class DWConvSpec:
+    """Depth-wise 3x3 conv (padding 1) + bias, then an optional GELU: Mlp.dwconv + act (ChangeFormer.py:283-289,512-523)."""
+    name: str
+    src: str
+    dst: str
+    c: int
+    weight: np.ndarray           # float32 [c][9]
+    bias: np.ndarray             # float32 [c]
+    gelu: bool = True
+    macs_per_pair: int = 0
+
+
+@dataclass
 class BilinearUpSpec:
     """F.interpolate(x, scale_factor=scale, mode="bilinear", align_corners=False) (ChangeVIG.py:246-262: `resize` and
     `F.interpolate(_c4, scale_factor=2, mode="bilinear")`) on a bf16 tensor; dst is [imgs, scale*h, scale*w, c]."""
@@ -634,6 +677,15 @@ def op_bytes_per_pair(prog: Program, op) -> int:
     if isinstance(op, GraphConvSpec):
         t = T[op.src]
         return t.mult * (2 * op.c * t.h * t.w * 2 + (0 if op.relpos is None else op.relpos.size * 4))
+    if isinstance(op, LayerNormSpec):
+        t = T[op.src]
+        return t.mult * op.c * t.h * t.w * 2 * (2 if op.dst_s2d is None else 3)
+    if isinstance(op, DWConvSpec):
+        t = T[op.src]
+        return t.mult * op.c * t.h * t.w * 2 * 2
+    if isinstance(op, AttentionSpec):
+        tq, tk = T[op.q], T[op.kv]
+        return tq.mult * (2 * op.c * tq.h * tq.w * 2 + 2 * op.c * tk.h * tk.w * 2)
     if isinstance(op, BilinearUpSpec):
         t = T[op.dst]
         return t.mult * (op.c * t.h * t.w * 2 + op.c * t.h * t.w * 2 // (op.scale * op.scale))

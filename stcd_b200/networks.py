@@ -14,6 +14,7 @@ import torch
 from torch.nn import init
 
 from .siamunet import SiamUnet_conc, SiamUnet_diff
+from .changeformer import ChangeFormerV6
 from .changevig import ChangeGNNV1
 from .segcd import SegCD
 from .snunet import SNUNet_ECAM
@@ -23,7 +24,7 @@ from .snunet import SNUNet_ECAM
 _REFERENCE_ONLY = (
     "Unet", "SiamUnet_sub", "SiamUnet_cross_conc", "DTCDSCN", "IFNet", "base_resnet18", "base_transformer_pos_s4",
     "base_transformer_pos_s4_dd8", "base_transformer_pos_s4_dd8_dedim8", "ChangeFormerV1", "ChangeFormerV2",
-    "ChangeFormerV3", "ChangeFormerV4", "ChangeFormerV5", "ChangeFormerV6", "ChangeGNNV2",
+    "ChangeFormerV3", "ChangeFormerV4", "ChangeFormerV5", "ChangeGNNV2",
     "ChangeGNNV2_sub", "ChangeGNNV2_abs", "ChangeGNNV2_conc", "GNN",
 )
 
@@ -32,12 +33,13 @@ _REGISTRY = {
     "SiamUnet_conc": lambda a: SiamUnet_conc(input_nbr=3, label_nbr=a.n_class),    # networks.py:151-152
     "SNUNet": lambda a: SNUNet_ECAM(in_ch=3, out_ch=a.n_class),                    # networks.py:168-169
     "ChangeGNNV1": lambda a: ChangeGNNV1(embed_dim=a.embed_dim),                   # networks.py:199-200
+    "ChangeFormerV6": lambda a: ChangeFormerV6(embed_dim=a.embed_dim),             # networks.py:190-191
 }
 
 
 # class name (= the reference's) -> drop-in wrapper; synth.GAINS / bench.py / the tests key on these names
 CLASSES = {"SiamUnet_diff": SiamUnet_diff, "SiamUnet_conc": SiamUnet_conc, "SNUNet_ECAM": SNUNet_ECAM, "SegCD": SegCD,
-           "ChangeGNNV1": ChangeGNNV1}
+           "ChangeGNNV1": ChangeGNNV1, "ChangeFormerV6": ChangeFormerV6}
 
 
 def register(name: str, ctor) -> None:

@@ -15,8 +15,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .lowering import (BilinearUpSpec, ConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec, MaxPoolS2DSpec, Program,
-                       SegHeadSpec)
+from .lowering import (AttentionSpec, BilinearUpSpec, ConvSpec, DWConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec,
+                       LayerNormSpec, MaxPoolS2DSpec, Program, SegHeadSpec)
 
 
 def _fptr(a: Optional[np.ndarray]):
@@ -62,6 +62,17 @@ class Plan:
                 rp = None if op.relpos is None else np.ascontiguousarray(op.relpos, np.float32)
                 _lib.check_id(lib.stcd_plan_add_graph_conv(h, ids[op.src], ids[op.dst], op.c, op.k, op.dilation, op.r, _fptr(rp)),
                               f"graph conv {op.name}")
+            elif isinstance(op, LayerNormSpec):
+                g, b = np.ascontiguousarray(op.gamma, np.float32), np.ascontiguousarray(op.beta, np.float32)
+                _lib.check_id(lib.stcd_plan_add_layernorm(h, ids[op.src], ids[op.dst], -1 if op.dst_s2d is None else ids[op.dst_s2d],
+                                                          op.c, _fptr(g), _fptr(b), float(op.eps)), f"layer norm {op.name}")
+            elif isinstance(op, AttentionSpec):
+                _lib.check_id(lib.stcd_plan_add_sr_attention(h, ids[op.q], ids[op.kv], ids[op.dst], op.c, op.heads, float(op.scale)),
+                              f"attention {op.name}")
+            elif isinstance(op, DWConvSpec):
+                wt, b = np.ascontiguousarray(op.weight, np.float32), np.ascontiguousarray(op.bias, np.float32)
+                _lib.check_id(lib.stcd_plan_add_dwconv3x3(h, ids[op.src], ids[op.dst], op.c, _fptr(wt), _fptr(b), 1 if op.gelu else 0),
+                              f"dw conv {op.name}")
             elif isinstance(op, BilinearUpSpec):
                 _lib.check_id(lib.stcd_plan_add_bilinear_up(h, ids[op.src], ids[op.dst], op.c, op.scale), f"bilinear {op.name}")
             elif isinstance(op, MaxPoolS2DSpec):

@@ -128,6 +128,29 @@ def test_changegnn_program_matches_oracle():
         net.lower(128, 128)            # pos_embed is not resized: the net only runs at img_size (ChangeVIG.py:87)
 
 
+def test_changeformer_program_matches_oracle():
+    """Config C5's net: Linear layers as 1x1 convs, strided patch-embedding / spatial-reduction convs, LayerNorm,
+    64-key attention and depth-wise conv ops -- checked through the emulator."""
+    from stcd_b200 import changeformer
+    net = synth.prepare_(changeformer.ChangeFormerV6().eval(), "ChangeFormerV6")
+    x1, x2 = synth.image_pairs(1, 256, 256)
+    with torch.no_grad():
+        y = nets.changeformer_forward(net.state_dict(), x1, x2)
+    prog = net.lower(256, 256)
+    ye = emulate.run_program(prog, x1, x2, chunk=1)
+    assert len(ye) == 5
+    for a, b in zip(ye, y):
+        assert a.shape == b.shape and (a - b).abs().max().item() < BF16_TOL
+    margin = (y[-1][:, 1] - y[-1][:, 0]).abs()
+    agree = (ye[-1][:, 1] > ye[-1][:, 0]) == (y[-1][:, 1] > y[-1][:, 0])
+    assert agree[margin > BF16_TOL].float().mean().item() >= 0.999
+    assert 0.02 < (y[-1][:, 1] > y[-1][:, 0]).float().mean().item() < 0.98, "degenerate change map"
+    assert abs(2 * prog.macs_per_pair() / 1e9 - 277.459) < 0.01           # SURVEY §6: 277.459 GFLOP per pair
+    assert sum(isinstance(o, L.AttentionSpec) for o in prog.ops) == 13 and sum(isinstance(o, L.LayerNormSpec) for o in prog.ops) == 44
+    with pytest.raises(ValueError):
+        net.lower(128, 128)
+
+
 def test_s2d_and_up2_tap_algebra():
     """The tap rewrites behind the SegCD lowering equal the reference ops they replace (fp32, no rounding)."""
     import torch.nn.functional as F
