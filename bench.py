@@ -50,10 +50,10 @@ WORKLOADS = {
                                input_sets=2,
                                desc="smp SegCD with the ResNet-50 encoder train_stcd.py:638 selects, 1024x1024 RGB pair tiles, "
                                     "batch 16 per GPU, bf16, + confusion matrix on sigmoid(change) > 0.5"),
-    "changegnn_v1_256_b32": dict(net="ChangeGNNV1", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=16,
+    "changegnn_v1_256_b32": dict(net="ChangeGNNV1", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=32,
                                  desc="C4: ChangeGNNV1 (pyramid ViG Grapher encoder: dense kNN k=9 + max-relative graph conv, "
                                       "multi-scale difference decoder) 256x256 RGB pairs, batch 32 per GPU, bf16"),
-    "changeformer_v6_256_b32": dict(net="ChangeFormerV6", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=16,
+    "changeformer_v6_256_b32": dict(net="ChangeFormerV6", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=32,
                                     desc="C5: ChangeFormerV6 (MiT transformer encoder + difference decoder) 256x256 RGB pairs, "
                                          "batch 32 per GPU, bf16"),
     "segcd_r34_256_b64": dict(net="SegCD", n_class=1, h=256, w=256, batch=64, kind="sigmoid", chunk=16,

@@ -93,7 +93,7 @@ class _EncoderTransformerV3(nn.Module):
 
 class ChangeFormerV6(PlannedModule):
     """models/ChangeFormer.py:1669-1701."""
-    default_chunk_pairs = 16
+    default_chunk_pairs = 32
 
     def __init__(self, input_nc: int = 3, output_nc: int = 2, decoder_softmax: bool = False, embed_dim: int = 256):
         super().__init__()

@@ -177,7 +177,7 @@ class _DecoderV1(nn.Module):
 
 class ChangeGNNV1(PlannedModule):
     """models/ChangeVIG.py:284-312."""
-    default_chunk_pairs = 16
+    default_chunk_pairs = 32
 
     def __init__(self, input_nc: int = 3, output_nc: int = 2, decoder_softmax: bool = False, embed_dim: int = 256,
                  decoder_heads: str = "MLP", img_size: int = 256):

@@ -482,17 +482,32 @@ __global__ void __launch_bounds__(256) segcd_head_kernel(const __nv_bfloat16* __
   const int x0 = blockIdx.x * kHeadTW, y0 = blockIdx.y * kHeadTH;
   const size_t hw = static_cast<size_t>(h) * w;
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = wgt[i];
-  for (int i = threadIdx.x; i < 2 * C8 * PH * PW; i += blockDim.x) {
-    const int px = i % PW;
-    int r = i / PW;
-    const int py = r % PH;
-    r /= PH;
-    const int g = r % C8, s = r / C8;
-    const int yy = y0 + py - 1, xx = x0 + px - 1;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (yy >= 0 && yy < h && xx >= 0 && xx < w)
-      v = __ldg(reinterpret_cast<const uint4*>(d + ((static_cast<size_t>(s * chunk + n) * C8 + g) * hw + static_cast<size_t>(yy) * w + xx) * 8));
-    s_d[s][g][py][px] = v;
+  // Staging: one warp per (stream, channel group, tile row) -- 2 * C8 * 18 rows of 34 pixels, 16 B each -- with
+  // cp.async (zero-fill outside the image): no index divisions, every load of the tile in flight at once.
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int row = warp; row < 2 * C8 * PH; row += 8) {
+      const int py = row % PH;                 // PH = 18: one division per row, warp-uniform
+      const int sg = row / PH;
+      const int g = sg % C8, sidx = sg / C8;
+      const int yy = y0 + py - 1;
+      const bool row_ok = (yy >= 0) && (yy < h);
+      const __nv_bfloat16* src_row = d + ((static_cast<size_t>(sidx * chunk + n) * C8 + g) * hw + static_cast<size_t>(row_ok ? yy : 0) * w) * 8;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int px = lane + 32 * pass;
+        if (px < PW) {
+          const int xx = x0 + px - 1;
+          const bool ok = row_ok && xx >= 0 && xx < w;
+          const void* gp = src_row + static_cast<size_t>(ok ? xx : 0) * 8;
+          const uint32_t sp = static_cast<uint32_t>(__cvta_generic_to_shared(&s_d[sidx][g][py][px]));
+          const int nbytes = ok ? 16 : 0;      // src-size 0: the 16 destination bytes are zero-filled
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sp), "l"(gp), "r"(nbytes) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   // each thread: 2 vertically adjacent pixels (rows ty0, ty0 + 1).  Per filter column kx the 3 x C weights
