@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 10
+#define STCD_ABI_VERSION 11
 
 enum stcd_status {
   STCD_OK = 0,
@@ -181,6 +181,10 @@ int stcd_plan_add_input_pack_u8(stcd_plan* plan, int dst_tensor, int cin, int s2
  * space-to-depth (src: [h][w] pixels x 4c channels = the (2h x 2w) map) -> dst [h][w] x c channels. */
 int stcd_plan_add_maxpool_s2d(stcd_plan* plan, int src_tensor, int dst_tensor, int c);
 
+/* dst = |src[T1 images] - src[T2 images]| (torch.abs(f1 - f2), FFCTLCD.forward, decoders/unet/model.py:412): src holds
+ * both temporal streams (mult 2), dst one stream with the same [h][w][c] (any layout: elementwise). */
+int stcd_plan_add_absdiff(stcd_plan* plan, int src_tensor, int dst_tensor);
+
 /* SegCD's tail (segmentation_models_pytorch/decoders/unet/model.py:321-330) as one op over the decoder
  * output `src` (bf16, both temporal streams: mult = 2, c channels): with head = Conv2d(c, 1, 3, padding=1)
  * (base/heads.py:5-10), m1 = head(d1), m2 = head(d2), change = min(head(|d1 - d2|), |m1 - m2|).
@@ -192,6 +196,9 @@ typedef struct stcd_seghead_desc {
   const float* weight;
   float bias;
   int32_t out_ext;
+  /* FFCTLCD (decoders/unet/model.py:407-423): >= 0 names a single-stream tensor [chunk][c/8][h][w][8] holding
+   * decoder(|f1 - f2|); the feature-level branch is then head(that) instead of head(|d1 - d2|).  -1: SegCD. */
+  int32_t diff_src;
 } stcd_seghead_desc;
 int stcd_plan_add_seg_head(stcd_plan* plan, const stcd_seghead_desc* desc);
 

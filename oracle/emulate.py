@@ -209,7 +209,8 @@ def run_seg_head(op: L.SegHeadSpec, T: Dict[str, torch.Tensor], chunk: int, ext:
     b = torch.tensor([op.bias])
     head = lambda t: torch.nn.functional.conv2d(t, w, b, padding=1)  # noqa: E731
     m1, m2 = head(d1), head(d2)
-    change = torch.minimum(head((d1 - d2).abs()), (m1 - m2).abs())
+    dd = (d1 - d2).abs() if op.diff_src is None else T[op.diff_src][:chunk, :, :, : op.c].permute(0, 3, 1, 2)
+    change = torch.minimum(head(dd), (m1 - m2).abs())
     ext[op.out_ext][:nv] = m1[:nv]
     ext[op.out_ext + 1][:nv] = m2[:nv]
     ext[op.out_ext + 2][:nv] = change[:nv]
@@ -267,6 +268,9 @@ def run_dwconv(op: L.DWConvSpec, T: Dict[str, torch.Tensor]) -> None:
 
 
 def run_aux(op, T, chunk, ext, nv):
+    if isinstance(op, L.AbsDiffSpec):
+        T[op.dst][..., : op.c] = _bf16((T[op.src][:chunk, :, :, : op.c] - T[op.src][chunk: 2 * chunk, :, :, : op.c]).abs())
+        return None
     if isinstance(op, L.LayerNormSpec):
         return run_layernorm(op, T)
     if isinstance(op, L.AttentionSpec):

@@ -159,6 +159,16 @@ def _unet_decoder(sd: SD, feats: List[torch.Tensor], n_blocks: int) -> torch.Ten
     return x
 
 
+def ffctlcd_forward(sd: SD, A: torch.Tensor, B: torch.Tensor, layers=(3, 4, 6, 3)):
+    """FFCTLCD.forward, segmentation_models_pytorch/decoders/unet/model.py:407-423."""
+    n_blocks = sum(1 for k in sd if k.startswith("decoder.blocks.") and k.endswith(".conv1.0.weight"))
+    f1, f2 = _resnet_features(sd, A, layers), _resnet_features(sd, B, layers)
+    head = lambda t: F.conv2d(t, sd["segmentation_head.0.weight"], sd["segmentation_head.0.bias"], padding=1)  # noqa: E731
+    diffea = head(_unet_decoder(sd, [torch.abs(a - b) for a, b in zip(f1, f2)], n_blocks))
+    m1, m2 = head(_unet_decoder(sd, f1, n_blocks)), head(_unet_decoder(sd, f2, n_blocks))
+    return m1, m2, torch.min(diffea, torch.abs(m1 - m2))
+
+
 def segcd_forward(sd: SD, A: torch.Tensor, B: torch.Tensor, layers=(3, 4, 6, 3)):
     """SegCD.forward, segmentation_models_pytorch/decoders/unet/model.py:316-332 -> (mask_t1, mask_t2, change)."""
     n_blocks = sum(1 for k in sd if k.startswith("decoder.blocks.") and k.endswith(".conv1.0.weight"))

@@ -112,7 +112,7 @@ class ConvDesc(C.Structure):
 
 class SegHeadDesc(C.Structure):
     _fields_ = [("src", C.c_int32), ("c", C.c_int32), ("weight", C.POINTER(C.c_float)), ("bias", C.c_float),
-                ("out_ext", C.c_int32)]
+                ("out_ext", C.c_int32), ("diff_src", C.c_int32)]
 
 
 class EcamDesc(C.Structure):
@@ -126,7 +126,7 @@ class EcamDesc(C.Structure):
     ]
 
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -142,6 +142,7 @@ SYMBOLS = [
     ("stcd_plan_add_input_pack_u8", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("stcd_plan_add_maxpool_s2d", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("stcd_plan_add_seg_head", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("stcd_plan_add_absdiff", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("stcd_plan_add_graph_conv", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     ("stcd_plan_add_layernorm", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                           C.c_float]),

@@ -471,12 +471,35 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_s2d_kernel(const __nv_bfloat
 // algorithmic level: 2 * C * 2 B read + 12 B written per pixel.
 constexpr int kHeadTW = 32, kHeadTH = 16;
 
-template <int C8>
-__global__ void __launch_bounds__(256) segcd_head_kernel(const __nv_bfloat16* __restrict__ d, const float* __restrict__ wgt,
-                                                         float bias, int chunk, int h, int w, float* __restrict__ m1,
-                                                         float* __restrict__ m2, float* __restrict__ change) {
+// dst[b] = |src[b] - src[chunk + b]| on packed bf16 (fp32 subtract, one rounding): torch.abs(f1 - f2) of FFCTLCD
+// (decoders/unet/model.py:412).  Elementwise over 16-byte vectors: layout-agnostic.  HBM-bound: 4 B read + 2 B written.
+__global__ void __launch_bounds__(256) absdiff_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                      size_t vec_per_stream) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < vec_per_stream;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float a[8], b[8];
+    unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(src) + i), a);
+    unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(src) + vec_per_stream + i), b);
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 hv = __floats2bfloat162_rn(fabsf(a[2 * j] - b[2 * j]), fabsf(a[2 * j + 1] - b[2 * j + 1]));
+      w[j] = *reinterpret_cast<uint32_t*>(&hv);
+    }
+    reinterpret_cast<uint4*>(dst)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// DIFF = false: the third stream is |d1 - d2| (SegCD); DIFF = true: it is read from `dd`, the decoder output of the
+// |f1 - f2| features (FFCTLCD, decoders/unet/model.py:411-413), staged as a third tile.
+template <int C8, bool DIFF>
+__global__ void __launch_bounds__(256) segcd_head_kernel(const __nv_bfloat16* __restrict__ d, const __nv_bfloat16* __restrict__ dd,
+                                                         const float* __restrict__ wgt, float bias, int chunk, int h, int w,
+                                                         float* __restrict__ m1, float* __restrict__ m2, float* __restrict__ change) {
   constexpr int PW = kHeadTW + 2, PH = kHeadTH + 2, C = 8 * C8;
-  __shared__ uint4 s_d[2][C8][PH][PW];
+  constexpr int NS = DIFF ? 3 : 2;
+  extern __shared__ uint4 s_head_dyn[];         // [NS][C8][PH][PW] (58 KB for the 3-stream C=16 instance: dynamic, opt-in)
+  uint4 (*s_d)[C8][PH][PW] = reinterpret_cast<uint4 (*)[C8][PH][PW]>(s_head_dyn);
   __shared__ __align__(16) float s_w[9 * C];
   const int n = blockIdx.z;
   const int x0 = blockIdx.x * kHeadTW, y0 = blockIdx.y * kHeadTH;
@@ -486,13 +509,15 @@ __global__ void __launch_bounds__(256) segcd_head_kernel(const __nv_bfloat16* __
   // cp.async (zero-fill outside the image): no index divisions, every load of the tile in flight at once.
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int row = warp; row < 2 * C8 * PH; row += 8) {
+    for (int row = warp; row < NS * C8 * PH; row += 8) {
       const int py = row % PH;                 // PH = 18: one division per row, warp-uniform
       const int sg = row / PH;
       const int g = sg % C8, sidx = sg / C8;
       const int yy = y0 + py - 1;
       const bool row_ok = (yy >= 0) && (yy < h);
-      const __nv_bfloat16* src_row = d + ((static_cast<size_t>(sidx * chunk + n) * C8 + g) * hw + static_cast<size_t>(row_ok ? yy : 0) * w) * 8;
+      const __nv_bfloat16* src_row = (sidx < 2 ? d + (static_cast<size_t>(sidx * chunk + n) * C8 + g) * hw * 8
+                                               : dd + (static_cast<size_t>(n) * C8 + g) * hw * 8) +
+                                     static_cast<size_t>(row_ok ? yy : 0) * w * 8;
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
         const int px = lane + 32 * pass;
@@ -529,11 +554,12 @@ __global__ void __launch_bounds__(256) segcd_head_kernel(const __nv_bfloat16* __
       }
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
-      float v1[C], v2[C];
+      float v1[C], v2[C], v3[DIFF ? C : 1];
 #pragma unroll
       for (int g = 0; g < C8; ++g) {
         unpack8_bf16_f(s_d[0][g][ty0 + rr][tx + kx], v1 + 8 * g);
         unpack8_bf16_f(s_d[1][g][ty0 + rr][tx + kx], v2 + 8 * g);
+        if (DIFF) unpack8_bf16_f(s_d[NS - 1][g][ty0 + rr][tx + kx], v3 + 8 * g);
       }
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
@@ -543,7 +569,7 @@ __global__ void __launch_bounds__(256) segcd_head_kernel(const __nv_bfloat16* __
           for (int j = 0; j < C; ++j) {
             a1[r] = fmaf(v1[j], wk[ky][j], a1[r]);
             a2[r] = fmaf(v2[j], wk[ky][j], a2[r]);
-            ad[r] = fmaf(fabsf(v1[j] - v2[j]), wk[ky][j], ad[r]);
+            ad[r] = fmaf(DIFF ? v3[j] : fabsf(v1[j] - v2[j]), wk[ky][j], ad[r]);
           }
         }
       }

@@ -62,16 +62,25 @@ __global__ void __launch_bounds__(256) knn_graph_kernel(const float* __restrict_
   }
   for (int c0 = 0; c0 < C; c0 += kKnnCC) {
     __syncthreads();
+    // cp.async (4 B, zero-fill out of range): all 40 copies of a thread are in flight at once
     for (int i = threadIdx.x; i < kKnnQ * kKnnCC; i += blockDim.x) {
       const int q = i % kKnnQ, cc = i / kKnnQ;
       const int n = n0 + q, c = c0 + cc;
-      xs[cc][q] = (n < N && c < C) ? __ldg(xb + static_cast<size_t>(c) * N + n) : 0.f;
+      const bool ok = (n < N) && (c < C);
+      const float* gp = xb + (ok ? static_cast<size_t>(c) * N + n : 0);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&xs[cc][q]))),
+                   "l"(gp), "r"(ok ? 4 : 0) : "memory");
     }
     for (int i = threadIdx.x; i < kKnnM * kKnnCC; i += blockDim.x) {
       const int j = i % kKnnM, cc = i / kKnnM;
       const int c = c0 + cc;
-      ys[cc][j] = (j < M && c < C) ? __ldg(yb + static_cast<size_t>(c) * M + j) : 0.f;
+      const bool ok = (j < M) && (c < C);
+      const float* gp = yb + (ok ? static_cast<size_t>(c) * M + j : 0);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&ys[cc][j]))),
+                   "l"(gp), "r"(ok ? 4 : 0) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 #pragma unroll 4
     for (int cc = 0; cc < kKnnCC; ++cc) {
@@ -102,6 +111,7 @@ __global__ void __launch_bounds__(256) knn_graph_kernel(const float* __restrict_
     }
   }
   const int kd = k * dilation;
+  int phase = 0, slot = 0;      // every dilation-th winner is kept: counters instead of t % dilation, t / dilation
   for (int t = 0; t < kd; ++t) {
     float best[8];
     int bi[8];
@@ -134,13 +144,17 @@ __global__ void __launch_bounds__(256) knn_graph_kernel(const float* __restrict_
       for (int j = 0; j < 8; ++j)
         if (lane * 8 + j == bi[q]) dot[q][j] = CUDART_INF_F;
     }
-    if (lane == 0 && (t % dilation) == 0) {
+    if (phase == 0) {
+      if (lane == 0) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int n = n0 + warp * 8 + q;
-        if (n < N) nn_idx[(static_cast<size_t>(b) * N + n) * k + t / dilation] = bi[q];
+        for (int q = 0; q < 8; ++q) {
+          const int n = n0 + warp * 8 + q;
+          if (n < N) nn_idx[(static_cast<size_t>(b) * N + n) * k + slot] = bi[q];
+        }
       }
+      ++slot;
     }
+    if (++phase == dilation) phase = 0;
   }
 }
 

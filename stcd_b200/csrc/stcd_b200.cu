@@ -129,8 +129,13 @@ struct DWConvOp {
   float* wb_dev = nullptr;
 };
 
+struct AbsDiffOp {
+  int src, dst, c;
+};
+
 struct SegHeadOp {
   int src, c, out_ext;
+  int diff_src = -1;
   float bias;
   std::vector<float> w;  // [9][c]
   float* w_dev = nullptr;
@@ -146,7 +151,7 @@ struct EcamOp {
 };
 
 struct Op {
-  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head, 5 graph conv, 6 bilinear up, 7 layer norm, 8 attention, 9 dw conv
+  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head, 5 graph conv, 6 bilinear up, 7 layer norm, 8 attention, 9 dw conv, 10 |T1 - T2|
   int idx;
 };
 
@@ -167,6 +172,7 @@ struct stcd_plan {
   std::vector<LayerNormOp> lns;
   std::vector<AttentionOp> attns;
   std::vector<DWConvOp> dws;
+  std::vector<AbsDiffOp> absdiffs;
   std::vector<Op> ops;
   uint8_t* workspace = nullptr;
   size_t workspace_bytes = 0;
@@ -309,6 +315,13 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
       stcd::max_relative_nc8_kernel<<<nb((size_t)B * (k.c / 8) * N, 8), 256, 0, st>>>(k.xf, y, k.idx, B, k.c, N, M, k.k,
                                                                                       (__nv_bfloat16*)td.ptr, td.c / 8);
       CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 10) {
+      const AbsDiffOp& k = plan->absdiffs[o.idx];
+      const Tensor& td = plan->tensors[k.dst];
+      const size_t vecs = td.bytes / 16;           // 16-byte vectors per stream (dst holds one stream)
+      stcd::absdiff_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((vecs + 255) / 256, 148 * 16)), 256, 0, st>>>(
+          (const __nv_bfloat16*)plan->tensors[k.src].ptr, (__nv_bfloat16*)td.ptr, vecs);
+      CUDA_TRY(cudaGetLastError());
     } else if (o.kind == 7) {
       const LayerNormOp& k = plan->lns[o.idx];
       const Tensor& ts = plan->tensors[k.src];
@@ -339,10 +352,10 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
       const Tensor& ts = plan->tensors[k.src];
       const Tensor& td = plan->tensors[k.dst];
       const int B = ts.mult * plan->chunk;
-      const size_t total = (size_t)B * (k.c / 8) * ts.h * ts.w;
-      stcd::dwconv3x3_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, 148 * 16)), 256, 0, st>>>(
-          (const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, k.wb_dev, k.wb_dev + (size_t)k.c * 9, B, k.c / 8, ts.c / 8, td.c / 8, ts.h,
-          ts.w, k.gelu);
+      const int hwp = ts.h * ts.w;
+      const dim3 grid((unsigned)std::max(1, (hwp + 511) / 512), (unsigned)(k.c / 8), (unsigned)B);   // <= 4 pixels per thread
+      stcd::dwconv3x3_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, k.wb_dev, k.wb_dev + (size_t)k.c * 9, B,
+                                                   k.c / 8, ts.c / 8, td.c / 8, ts.h, ts.w, k.gelu);
       CUDA_TRY(cudaGetLastError());
     } else if (o.kind == 6) {
       const BilinearOp& k = plan->bilinears[o.idx];
@@ -362,10 +375,20 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
       if (!m1 || !m2 || !ch) return fail(STCD_ERR_INVALID, "external outputs %d..%d must not be NULL", k.out_ext, k.out_ext + 2);
       if (n_valid > 0) {
         const dim3 grid((t.w + stcd::kHeadTW - 1) / stcd::kHeadTW, (t.h + stcd::kHeadTH - 1) / stcd::kHeadTH, n_valid);
-        if (k.c == 8)
-          stcd::segcd_head_kernel<1><<<grid, 256, 0, st>>>((const __nv_bfloat16*)t.ptr, k.w_dev, k.bias, plan->chunk, t.h, t.w, m1, m2, ch);
-        else
-          stcd::segcd_head_kernel<2><<<grid, 256, 0, st>>>((const __nv_bfloat16*)t.ptr, k.w_dev, k.bias, plan->chunk, t.h, t.w, m1, m2, ch);
+        const __nv_bfloat16* dp = (const __nv_bfloat16*)t.ptr;
+        const __nv_bfloat16* ddp = k.diff_src >= 0 ? (const __nv_bfloat16*)plan->tensors[k.diff_src].ptr : nullptr;
+        const size_t tile = (size_t)(stcd::kHeadTH + 2) * (stcd::kHeadTW + 2) * 16 * (k.c / 8);
+        if (k.diff_src < 0) {
+          if (k.c == 8)
+            stcd::segcd_head_kernel<1, false><<<grid, 256, 2 * tile, st>>>(dp, ddp, k.w_dev, k.bias, plan->chunk, t.h, t.w, m1, m2, ch);
+          else
+            stcd::segcd_head_kernel<2, false><<<grid, 256, 2 * tile, st>>>(dp, ddp, k.w_dev, k.bias, plan->chunk, t.h, t.w, m1, m2, ch);
+        } else {
+          if (k.c == 8)
+            stcd::segcd_head_kernel<1, true><<<grid, 256, 3 * tile, st>>>(dp, ddp, k.w_dev, k.bias, plan->chunk, t.h, t.w, m1, m2, ch);
+          else
+            stcd::segcd_head_kernel<2, true><<<grid, 256, 3 * tile, st>>>(dp, ddp, k.w_dev, k.bias, plan->chunk, t.h, t.w, m1, m2, ch);
+        }
         CUDA_TRY(cudaGetLastError());
       }
     } else {
@@ -674,6 +697,19 @@ int stcd_plan_add_bilinear_up(stcd_plan* plan, int src_tensor, int dst_tensor, i
   return (int)plan->ops.size() - 1;
 }
 
+int stcd_plan_add_absdiff(stcd_plan* plan, int src_tensor, int dst_tensor) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, src_tensor) || !valid_tensor(plan, dst_tensor)) return -fail(STCD_ERR_INVALID, "bad tensor id");
+  const Tensor& ts = plan->tensors[src_tensor];
+  const Tensor& td = plan->tensors[dst_tensor];
+  if (ts.mult != 2 || td.mult != 1 || ts.h != td.h || ts.w != td.w || ts.c != td.c)
+    return -fail(STCD_ERR_INVALID, "abs-diff: src must be [2*chunk,%d,%d,%d] (both streams) and dst the same with one stream", td.h, td.w, td.c);
+  plan->absdiffs.push_back({src_tensor, dst_tensor, td.c});
+  plan->ops.push_back({10, (int)plan->absdiffs.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
 int stcd_plan_add_seg_head(stcd_plan* plan, const stcd_seghead_desc* d) {
   if (!plan || !d) return -fail(STCD_ERR_STATE, "plan/desc is NULL");
   if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
@@ -687,6 +723,13 @@ int stcd_plan_add_seg_head(stcd_plan* plan, const stcd_seghead_desc* d) {
   k.c = d->c;
   k.out_ext = d->out_ext;
   k.bias = d->bias;
+  k.diff_src = d->diff_src;
+  if (d->diff_src >= 0) {
+    if (!valid_tensor(plan, d->diff_src)) return -fail(STCD_ERR_INVALID, "seg head: bad diff_src tensor %d", d->diff_src);
+    const Tensor& tdiff = plan->tensors[d->diff_src];
+    if (tdiff.mult != 1 || tdiff.c != d->c || tdiff.h != t.h || tdiff.w != t.w)
+      return -fail(STCD_ERR_INVALID, "seg head: diff_src must be [chunk,%d,%d,%d]", t.h, t.w, d->c);
+  }
   k.w.assign(d->weight, d->weight + 9 * d->c);
   plan->n_ext = std::max(plan->n_ext, d->out_ext + 3);
   if ((int)plan->ext_elems.size() < plan->n_ext) plan->ext_elems.resize(plan->n_ext, 0);
@@ -1151,6 +1194,8 @@ int stcd_plan_finalize(stcd_plan* plan) {
       CUDA_TRY(cudaMemcpy(g.relpos_dev, g.relpos.data(), g.relpos.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
   }
+  // the 3-stream head instances stage 58 KB: dynamic shared memory above the 48 KB default
+  CUDA_TRY(cudaFuncSetAttribute(stcd::segcd_head_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   for (LayerNormOp& k : plan->lns) {
     CUDA_TRY(cudaMalloc(&k.gb_dev, k.gb.size() * sizeof(float)));
     CUDA_TRY(cudaMemcpy(k.gb_dev, k.gb.data(), k.gb.size() * sizeof(float), cudaMemcpyHostToDevice));

@@ -171,41 +171,54 @@ __global__ void __launch_bounds__(128) sr_attention_kernel(const __nv_bfloat16* 
 // Depth-wise 3x3 conv (padding 1) + bias [+ GELU]: Mlp.dwconv + act (ChangeFormer.py:283-289,512-523).
 // One thread per (pixel, 8-channel group): 9 neighbour loads of 16 B, weights [c][9] from L1.  HBM-bound: 2 B read +
 // 2 B written per element.
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+__global__ void __launch_bounds__(128) dwconv3x3_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                         const float* __restrict__ wgt, const float* __restrict__ bias, int B, int g8,
                                                         int src_c8, int dst_c8, int h, int w, int gelu) {
+  // grid (pixel blocks, g8, B): a CTA works on ONE channel group; its 9 x 8 weights and 8 biases sit in shared memory
+  // (broadcast float4 reads), which keeps the register count low enough for full occupancy: the kernel is latency-bound.
+  __shared__ __align__(16) float s_w[9][8];
+  __shared__ __align__(16) float s_b[8];
   const int hw = h * w;
-  const size_t total = static_cast<size_t>(B) * g8 * hw;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int pix = static_cast<int>(i % hw);
-    const size_t r = i / hw;
-    const int g = static_cast<int>(r % g8);
-    const size_t b = r / g8;
+  const int g = blockIdx.y;
+  const size_t b = blockIdx.z;
+  if (threadIdx.x < 72) s_w[threadIdx.x % 9][threadIdx.x / 9] = __ldg(wgt + (g * 8 + threadIdx.x / 9) * 9 + threadIdx.x % 9);
+  if (threadIdx.x < 8) s_b[threadIdx.x] = __ldg(bias + g * 8 + threadIdx.x);
+  __syncthreads();
+  const __nv_bfloat16* base = src + (b * src_c8 + g) * static_cast<size_t>(hw) * 8;
+  __nv_bfloat16* obase = dst + (b * dst_c8 + g) * static_cast<size_t>(hw) * 8;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += gridDim.x * blockDim.x) {
     const int y = pix / w, x = pix - y * w;
-    const __nv_bfloat16* base = src + (b * src_c8 + g) * static_cast<size_t>(hw) * 8;
+    uint4 q[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {              // all nine loads first: independent, in flight together
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      const bool ok = yy >= 0 && yy < h && xx >= 0 && xx < w;
+      q[t] = ok ? __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(yy) * w + xx) * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    }
     float acc[8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(&s_b[0]), b1 = *reinterpret_cast<const float4*>(&s_b[4]);
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = __ldg(bias + g * 8 + e);
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + ky - 1;
-      if (yy < 0 || yy >= h) continue;
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x + kx - 1;
-        if (xx < 0 || xx >= w) continue;
-        float v[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(yy) * w + xx) * 8)), v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(v[e], __ldg(wgt + (g * 8 + e) * 9 + ky * 3 + kx), acc[e]);
-      }
+    for (int t = 0; t < 9; ++t) {
+      float v[8];
+      unpack8(q[t], v);
+      const float4 w0 = *reinterpret_cast<const float4*>(&s_w[t][0]), w1 = *reinterpret_cast<const float4*>(&s_w[t][4]);
+      acc[0] = fmaf(v[0], w0.x, acc[0]);
+      acc[1] = fmaf(v[1], w0.y, acc[1]);
+      acc[2] = fmaf(v[2], w0.z, acc[2]);
+      acc[3] = fmaf(v[3], w0.w, acc[3]);
+      acc[4] = fmaf(v[4], w1.x, acc[4]);
+      acc[5] = fmaf(v[5], w1.y, acc[5]);
+      acc[6] = fmaf(v[6], w1.z, acc[6]);
+      acc[7] = fmaf(v[7], w1.w, acc[7]);
     }
     if (gelu) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = 0.5f * acc[e] * (1.f + erff(acc[e] * 0.70710678118654752f));
     }
-    *reinterpret_cast<uint4*>(dst + ((b * dst_c8 + g) * static_cast<size_t>(hw) + pix) * 8) = pack8(acc);
+    *reinterpret_cast<uint4*>(obase + static_cast<size_t>(pix) * 8) = pack8(acc);
   }
 }
 

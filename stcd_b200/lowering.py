@@ -216,6 +216,16 @@ class BilinearUpSpec:
 
 
 @dataclass
+class AbsDiffSpec:
+    """dst = |src[T1 images] - src[T2 images]| (torch.abs(f1 - f2), smp FFCTLCD.forward, decoders/unet/model.py:412):
+    src holds both streams (mult 2), dst one (mult 1); any layout (elementwise), first c channels."""
+    name: str
+    src: str
+    dst: str
+    c: int
+
+
+@dataclass
 class SegHeadSpec:
     """SegCD's tail (segmentation_models_pytorch/decoders/unet/model.py:321-330) as ONE op over the
     decoder output d (both temporal streams, c channels): m1 = head(d1), m2 = head(d2),
@@ -228,6 +238,9 @@ class SegHeadSpec:
     bias: float
     out_ext: int = 0
     macs_per_pair: int = 0
+    # FFCTLCD (model.py:407-423): the feature-level branch is head(decoder(|f1 - f2|)): its decoder output arrives as
+    # a separate single-stream tensor instead of |d1 - d2| computed from `src`
+    diff_src: Optional[str] = None
 
 
 @dataclass
@@ -670,7 +683,10 @@ def op_bytes_per_pair(prog: Program, op) -> int:
         return 2 * (4 * op.c + op.c) * t.h * t.w * 2
     if isinstance(op, SegHeadSpec):
         t = T[op.src]
-        return 2 * op.c * t.h * t.w * 2 + 3 * t.h * t.w * 4
+        return (2 + (op.diff_src is not None)) * op.c * t.h * t.w * 2 + 3 * t.h * t.w * 4
+    if isinstance(op, AbsDiffSpec):
+        t = T[op.dst]
+        return 3 * op.c * t.h * t.w * 2
     if isinstance(op, EcamHeadSpec):
         t = T[op.srcs[0]]
         return 2 * 4 * op.c * t.h * t.w * 2 + op.n_class * t.h * t.w * 4

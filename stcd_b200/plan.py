@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .lowering import (AttentionSpec, BilinearUpSpec, ConvSpec, DWConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec,
+from .lowering import (AbsDiffSpec, AttentionSpec, BilinearUpSpec, ConvSpec, DWConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec,
                        LayerNormSpec, MaxPoolS2DSpec, Program, SegHeadSpec)
 
 
@@ -62,6 +62,8 @@ class Plan:
                 rp = None if op.relpos is None else np.ascontiguousarray(op.relpos, np.float32)
                 _lib.check_id(lib.stcd_plan_add_graph_conv(h, ids[op.src], ids[op.dst], op.c, op.k, op.dilation, op.r, _fptr(rp)),
                               f"graph conv {op.name}")
+            elif isinstance(op, AbsDiffSpec):
+                _lib.check_id(lib.stcd_plan_add_absdiff(h, ids[op.src], ids[op.dst]), f"abs-diff {op.name}")
             elif isinstance(op, LayerNormSpec):
                 g, b = np.ascontiguousarray(op.gamma, np.float32), np.ascontiguousarray(op.beta, np.float32)
                 _lib.check_id(lib.stcd_plan_add_layernorm(h, ids[op.src], ids[op.dst], -1 if op.dst_s2d is None else ids[op.dst_s2d],
@@ -80,6 +82,7 @@ class Plan:
             elif isinstance(op, SegHeadSpec):
                 d = _lib.SegHeadDesc()
                 d.src, d.c, d.bias, d.out_ext = ids[op.src], op.c, float(op.bias), op.out_ext
+                d.diff_src = -1 if op.diff_src is None else ids[op.diff_src]
                 wkeep = np.ascontiguousarray(op.weight, np.float32)
                 d.weight = _fptr(wkeep)
                 _lib.check_id(lib.stcd_plan_add_seg_head(h, C.byref(d)), f"seg head {op.name}")

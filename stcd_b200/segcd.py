@@ -162,13 +162,22 @@ class SegCD(PlannedModule):
                 nn.init.xavier_uniform_(m.weight)
                 nn.init.constant_(m.bias, 0)
 
+    ffctl = False        # FFCTLCD: feature-level branch = head(decoder(|f1 - f2|)) instead of head(|d1 - d2|)
+
     def lower(self, h: int, w: int) -> L.Program:
-        return lower_segcd(self.state_dict(), self.encoder_name, self.inchannels, self.decoder_channels, h, w)
+        return lower_segcd(self.state_dict(), self.encoder_name, self.inchannels, self.decoder_channels, h, w, ffctl=self.ffctl)
 
     @torch.no_grad()
     def forward(self, A: torch.Tensor, B: torch.Tensor):
         m1, m2, change = self.plan_for(A).forward(A, B)
         return m1, m2, change
+
+
+class FFCTLCD(SegCD):
+    """segmentation_models_pytorch.FFCTLCD, decoders/unet/model.py:335-423 (the alternative train_stcd.py:636 keeps
+    commented out): same parameters as SegCD; the feature-level change branch runs the decoder on |f1 - f2| of every
+    encoder feature, the decision-level branch is |mask_t1 - mask_t2|, change = min of the two."""
+    ffctl = True
 
 
 # ------------------------------------------------------------------------------------------
@@ -189,7 +198,7 @@ def stem_s2d_taps(weight: torch.Tensor) -> List:
 
 
 def lower_segcd(sd: Dict[str, torch.Tensor], encoder_name: str, in_channels: int, decoder_channels: Sequence[int],
-                h: int, w: int) -> L.Program:
+                h: int, w: int, ffctl: bool = False) -> L.Program:
     """state_dict of the reference SegCD -> fused-op Program (eval mode)."""
     if h % 32 or w % 32:
         raise ValueError(f"SegCD lowering needs H and W divisible by 32 (got {h}x{w}): the reference's decoder "
@@ -289,41 +298,60 @@ def lower_segcd(sd: Dict[str, torch.Tensor], encoder_name: str, in_channels: int
                        res=ident, out0=o, out0_s2d=last_of_layer, macs_per_pair=last_macs)
             x, x_s2d, cin = o, last_of_layer, cout
 
-    # ---------------- Unet decoder: (nearest x2, cat skip, conv-BN-ReLU, conv-BN-ReLU) x 5, per temporal image
-    for bi, cout in enumerate(decoder_channels):
-        pre = f"decoder.blocks.{bi}"
-        skip = skips[len(skips) - 1 - bi] if bi < len(skips) else None
-        w1 = sd[f"{pre}.conv1.0.weight"]
-        cskip = skip[1] if skip else 0
-        if w1.shape[1] != cin + cskip:
-            raise ValueError(f"{pre}.conv1 expects {w1.shape[1]} input channels, lowering has {cin}+{cskip}")
-        segs = [L.Segment(x, cin)] + (L.s2d_segments(skip[0], cskip) if skip else [])
-        phases = []
-        for a in range(2):
-            for b in range(2):
-                st = L.SegTaps([L.up2_conv_taps(w1[:, :cin], 1, a, b)])
-                if skip:
-                    st.extend(L.s2d_conv_taps(w1[:, cin:], 1, a, b))
-                phases.append((a, b, st))
-        sc, sh = bn(f"{pre}.conv1.1", cout)
-        cpad = (cout + 7) // 8 * 8
-        t = p.tensor(f"{pre}.t", 2, 2 * hh, 2 * ww, cpad)
-        L.add_conv(p, f"{pre}.conv1", segs, phases, cout, hh, ww, 1, sc, sh, pair=True, relu=True, osy=2, osx=2, out0=t,
-                   macs_per_pair=2 * 4 * hh * ww * 9 * (cin + cskip) * cout)
-        hh, ww = 2 * hh, 2 * ww
-        sc, sh = bn(f"{pre}.conv2.1", cout)
-        o = p.tensor(f"{pre}.o", 2, hh, ww, cpad)
-        L.add_conv(p, f"{pre}.conv2", [L.Segment(t, cout)], L.conv_taps(sd[f"{pre}.conv2.0.weight"], pad=1), cout, hh, ww, 1,
-                   sc, sh, pair=True, relu=True, out0=o, macs_per_pair=2 * hh * ww * 9 * cout * cout)
-        x, cin = o, cout
+    # ---------------- Unet decoder: (nearest x2, cat skip, conv-BN-ReLU, conv-BN-ReLU) x 5
+    def decode(x, cin, hh, ww, skips, pair: bool, tag: str):
+        """One pass of the decoder over (x, skips): both temporal streams as pair tiles, or one single-stream tensor set."""
+        mult = 2 if pair else 1
+        for bi, cout in enumerate(decoder_channels):
+            pre = f"decoder.blocks.{bi}"
+            skip = skips[len(skips) - 1 - bi] if bi < len(skips) else None
+            w1 = sd[f"{pre}.conv1.0.weight"]
+            cskip = skip[1] if skip else 0
+            if w1.shape[1] != cin + cskip:
+                raise ValueError(f"{pre}.conv1 expects {w1.shape[1]} input channels, lowering has {cin}+{cskip}")
+            segs = [L.Segment(x, cin)] + (L.s2d_segments(skip[0], cskip) if skip else [])
+            phases = []
+            for a in range(2):
+                for b in range(2):
+                    st = L.SegTaps([L.up2_conv_taps(w1[:, :cin], 1, a, b)])
+                    if skip:
+                        st.extend(L.s2d_conv_taps(w1[:, cin:], 1, a, b))
+                    phases.append((a, b, st))
+            sc, sh = bn(f"{pre}.conv1.1", cout)
+            cpad = (cout + 7) // 8 * 8
+            t = p.tensor(f"{pre}.t{tag}", mult, 2 * hh, 2 * ww, cpad)
+            L.add_conv(p, f"{pre}.conv1{tag}", segs, phases, cout, hh, ww, 1, sc, sh, pair=pair, relu=True, osy=2, osx=2, out0=t,
+                       macs_per_pair=mult * 4 * hh * ww * 9 * (cin + cskip) * cout)
+            hh, ww = 2 * hh, 2 * ww
+            sc, sh = bn(f"{pre}.conv2.1", cout)
+            o = p.tensor(f"{pre}.o{tag}", mult, hh, ww, cpad)
+            L.add_conv(p, f"{pre}.conv2{tag}", [L.Segment(t, cout)], L.conv_taps(sd[f"{pre}.conv2.0.weight"], pad=1), cout, hh, ww, 1,
+                       sc, sh, pair=pair, relu=True, out0=o, macs_per_pair=mult * hh * ww * 9 * cout * cout)
+            x, cin = o, cout
+        return x, cin, hh, ww
+
+    diff_out = None
+    if ffctl:
+        # FFCTLCD (model.py:407-423): a third decoder pass over |f1 - f2| of every encoder feature
+        dskips = []
+        for (t_, c_) in skips:
+            ts = p.tensors[t_]
+            dt = p.tensor(f"{t_}.absdiff", 1, ts.h, ts.w, ts.c)
+            p.ops.append(L.AbsDiffSpec(f"{t_}.absdiff", t_, dt, ts.c))
+            dskips.append((dt, c_))
+        xd = p.tensor(f"{x}.absdiff", 1, hh, ww, cin)
+        p.ops.append(L.AbsDiffSpec(f"{x}.absdiff", x, xd, cin))
+        diff_out, _, _, _ = decode(xd, cin, hh, ww, dskips, False, ".diff")
+    x, cin, hh, ww = decode(x, cin, hh, ww, skips, True, "")
 
     # ---------------- heads + decision-level fusion
     wh = sd["segmentation_head.0.weight"]                      # [1, c, 3, 3]
-    if cin % 8 or cin > 32:
-        raise NotImplementedError(f"head kernel serves 8/16/24/32 decoder channels (got {cin})")
+    if cin not in (8, 16):
+        raise NotImplementedError(f"head kernel serves 8 or 16 decoder channels (got {cin})")
     p.ops.append(L.SegHeadSpec("segmentation_head", x, cin,
                                wh[0].permute(1, 2, 0).reshape(9, cin).contiguous().numpy().astype(np.float32),
-                               float(sd["segmentation_head.0.bias"][0]), out_ext=0, macs_per_pair=3 * hh * ww * 9 * cin))
+                               float(sd["segmentation_head.0.bias"][0]), out_ext=0, macs_per_pair=3 * hh * ww * 9 * cin,
+                               diff_src=diff_out))
     for nm in ("mask_t1", "mask_t2", "change"):
         p.ext.append(L.ExtOutput(nm, 1, hh, ww))
     return p

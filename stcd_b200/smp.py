@@ -6,11 +6,11 @@ train_stcd.py:637-638 does with the vendored package.
 """
 from __future__ import annotations
 
-from .segcd import SegCD
+from .segcd import FFCTLCD, SegCD
 
-__all__ = ["SegCD", "create_model"]
+__all__ = ["SegCD", "FFCTLCD", "create_model"]
 
-_ARCHS = {"segcd": SegCD}
+_ARCHS = {"segcd": SegCD, "ffctlcd": FFCTLCD}
 
 
 def create_model(arch: str, encoder_name: str = "resnet34", encoder_weights=None, in_channels: int = 3, classes: int = 1,

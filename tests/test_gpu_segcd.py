@@ -57,6 +57,23 @@ def test_forward_matches_golden(golden_dir, case, name):
     _check(ys, [torch.from_numpy(g[f"out{i}"]) for i in range(3)])
 
 
+def test_ffctlcd_matches_oracle_and_emulator():
+    """smp.FFCTLCD (decoders/unet/model.py:335-423): third decoder pass over |f1 - f2| of every encoder feature."""
+    net = synth.prepare_(segcd.FFCTLCD("resnet34").eval(), "SegCD")
+    x1, x2 = synth.image_pairs(3, 64, 96)
+    with torch.no_grad():
+        ref = nets.ffctlcd_forward(net.state_dict(), x1, x2)
+    emu = emulate.run_program(net.lower(64, 96), x1, x2, chunk=2)
+    net = net.cuda()
+    net.chunk_pairs = 2
+    ys = net(x1.cuda(), x2.cuda())
+    _check(ys, ref)
+    for y, e in zip(ys, emu):
+        assert (y.cpu() - e).abs().max().item() < 1.5e-2
+    import stcd_b200.smp as smp
+    assert isinstance(smp.create_model("FFCTLCD", "resnet18"), segcd.FFCTLCD)
+
+
 def test_layerwise_against_emulator():
     """Every intermediate tensor of the plan against the emulator: localises a wrong layer."""
     net = _net()

@@ -86,6 +86,19 @@ def test_segcd_program_matches_oracle():
         segcd.SegCD("resnext50_32x4d")
 
 
+def test_ffctlcd_program_matches_oracle():
+    from stcd_b200 import segcd
+    net = synth.prepare_(segcd.FFCTLCD("resnet18").eval(), "SegCD")
+    x1, x2 = synth.image_pairs(2, 64, 64)
+    with torch.no_grad():
+        y = nets.ffctlcd_forward(net.state_dict(), x1, x2, layers=(2, 2, 2, 2))
+    prog = net.lower(64, 64)
+    ye = emulate.run_program(prog, x1, x2, chunk=2)
+    for a, b in zip(ye, y):
+        assert (a - b).abs().max().item() < BF16_TOL
+    assert sum(isinstance(o, L.AbsDiffSpec) for o in prog.ops) == 5       # 4 skips + the bottleneck
+
+
 def test_segcd_resnet50_program_matches_oracle():
     """The encoder the STCD script selects (train_stcd.py:638): Bottleneck blocks; the 1x1 conv ahead of a
     stride-2 3x3 runs per parity class of its space-to-depth input."""

@@ -75,6 +75,18 @@ def test_oracle_matches_live_reference(case):
         assert (a - b).abs().max().item() < 1e-5
 
 
+@pytest.mark.skipif(not refimport.available(), reason="reference tree not present on this box")
+def test_ffctlcd_oracle_matches_live_reference():
+    smp = refimport.ref_module("segmentation_models_pytorch")
+    ref = synth.prepare_(smp.FFCTLCD("resnet18", encoder_weights=None, classes=1).eval(), "SegCD")
+    x1, x2 = synth.image_pairs(1, 64, 64, seed=6)
+    with torch.no_grad():
+        y_ref = ref(x1, x2)
+        y = nets.ffctlcd_forward(ref.state_dict(), x1, x2, layers=(2, 2, 2, 2))
+    for a, b in zip(y, y_ref):
+        assert (a - b).abs().max().item() < 1e-5
+
+
 def test_metric_oracle_matches_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "segmentation_metric.npz"))
     cm = ometric.confusion_matrix(g["pred"], g["label"]) + ometric.confusion_matrix(g["pred2"], g["label"])

@@ -31,6 +31,24 @@ def main():
                     if h == w or h.endswith("." + w):
                         rec[w] = f"{v} {u}".strip()
             rows_out.append(rec)
+    # labels of the form workload:op:pairs_per_launch also feed profiles/r1_traffic.json (bench.py's roofline.traffic)
+    import json, os
+    traffic = {}
+    def num(v):
+        x, unit = v.split()[0], (v.split() + [""])[1]
+        return float(x) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+    for r in rows_out:
+        parts = r["label"].split(":")
+        if len(parts) == 3 and "dram__bytes_read.sum" in r:
+            tot = num(r["dram__bytes_read.sum"]) + num(r["dram__bytes_write.sum"])
+            traffic.setdefault(parts[0], {})[parts[1]] = {
+                "dram_bytes_per_pair": int(tot / int(parts[2])),
+                "capture": f"{parts[2]} pairs per launch, {r['dram__bytes_read.sum']} read + {r['dram__bytes_write.sum']} written, {r.get('gpu__time_duration.sum')}"}
+    if traffic:
+        with open(os.path.join(os.path.dirname(out), "r1_traffic.json"), "w") as f:
+            json.dump({"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per image pair from the ncu --set full captures in "
+                                   "r1_ncu_full_summary.csv (bytes per launch / pairs per launch); bench.py scales it to its launch size",
+                       **traffic}, f, indent=1)
     cols = ["label", "kernel"] + WANT
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
