@@ -59,6 +59,7 @@ enum : uint32_t {
   E_POOL = 32u,   // out_pool <- maxpool2x2(v)
   E_DIFF = 64u,   // out_diff <- |v(T1) - v(T2)|
   E_F32 = 128u,   // out_f32 (NCHW fp32, external) <- v
+  E_ACTX = 256u,  // extended activation: GELU / PReLU and/or activation before the second affine (read at run time)
   E_GENERIC = 1u << 31
 };
 
@@ -509,8 +510,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     const bool has_pool = STCD_HAS(E_POOL, p.out_pool != nullptr);
     const bool has_diff = (MS == 2) && STCD_HAS(E_DIFF, p.out_diff != nullptr);
     const bool has_f32 = STCD_HAS(E_F32, p.out_f32 != nullptr);
+    // ReLU-only instances keep the lean path; GELU / PReLU / act-before-BN live behind E_ACTX so that their code
+    // (erff, the extra selects) costs the ReLU nets neither registers nor instructions
+    const bool has_actx = STCD_HAS(E_ACTX, p.relu >= 2 || p.act_pre != 0);
+    const bool act_pre = has_actx && p.act_pre != 0;
     auto apply_act = [&](float (&x)[16]) {   // p.relu is warp-uniform
-      if (p.relu == 1) {
+      if (!has_actx || p.relu == 1) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
       } else if (p.relu == 2) {              // nn.GELU(): 0.5 x (1 + erf(x / sqrt 2))
@@ -608,7 +613,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
               if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(v[m] + 8);
             }
             if (has_aff2) {
-              if (p.act_pre) apply_act(v[m]);
+              if (act_pre) apply_act(v[m]);
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[m][j] = fmaf(v[m][j], s_aff[2][c0 + j], s_aff[3][c0 + j]);
             }
@@ -619,7 +624,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[m][j] += rv[j];
             }
-            if (has_relu && !p.act_pre) apply_act(v[m]);
+            if (has_relu && !act_pre) apply_act(v[m]);
             if (has_f32) {
               if (valid && im[m] < static_cast<size_t>(p.n_valid)) {
                 const int nv = min(16, p.cout - ch);
@@ -739,19 +744,21 @@ struct ConvKernelEntry {
   X(4, 2, E_RES | E_RELU | E_OUT0)                     \
   X(2, 2, E_OUT0)                                      \
   X(4, 2, E_OUT0)                                      \
-  /* ChangeGNN / ChangeFormer: 1x1 conv + residual without activation, conv -> act -> BN (+ residual) decoders */ \
+  /* ChangeGNN / ChangeFormer: 1x1 conv + residual without activation; GELU convs; conv -> act -> BN (+ residual) decoders */ \
   X(2, 2, E_RES | E_OUT0)                              \
   X(4, 2, E_RES | E_OUT0)                              \
   X(1, 1, E_RES | E_OUT0)                              \
   X(2, 1, E_RES | E_OUT0)                              \
   X(4, 1, E_RES | E_OUT0)                              \
-  X(1, 1, E_AFF2 | E_RELU | E_OUT0)                    \
-  X(2, 1, E_AFF2 | E_RELU | E_OUT0)                    \
-  X(4, 1, E_AFF2 | E_RELU | E_OUT0)                    \
-  X(1, 1, E_AFF2 | E_RES | E_RELU | E_OUT0)            \
-  X(2, 1, E_AFF2 | E_RES | E_RELU | E_OUT0)            \
-  X(4, 1, E_AFF2 | E_RES | E_RELU | E_OUT0)            \
-  X(4, 1, E_OUT0)
+  X(4, 1, E_OUT0)                                      \
+  X(2, 2, E_RELU | E_ACTX | E_OUT0)                    \
+  X(4, 2, E_RELU | E_ACTX | E_OUT0)                    \
+  X(1, 1, E_AFF2 | E_RELU | E_ACTX | E_OUT0)           \
+  X(2, 1, E_AFF2 | E_RELU | E_ACTX | E_OUT0)           \
+  X(4, 1, E_AFF2 | E_RELU | E_ACTX | E_OUT0)           \
+  X(1, 1, E_AFF2 | E_RES | E_RELU | E_ACTX | E_OUT0)   \
+  X(2, 1, E_AFF2 | E_RES | E_RELU | E_ACTX | E_OUT0)   \
+  X(4, 1, E_AFF2 | E_RES | E_RELU | E_ACTX | E_OUT0)
 
 inline const ConvKernelEntry* conv_kernel_table(int* n) {
   static const ConvKernelEntry table[] = {

@@ -960,6 +960,22 @@ int stcd_plan_finalize(stcd_plan* plan) {
     // one shared-memory carve-out for every instance: consecutive launches never reconfigure the SM
     CUDA_TRY(cudaFuncSetAttribute(kernels[i].fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
+  // Per-CTA dynamic shared-memory budget for `o` resident CTAs per SM: the SM's capacity split o ways, minus the
+  // kernel's STATIC shared memory (tables, barriers, affine vectors) and the 1 KB the driver reserves per CTA.  Sizing
+  // against a fixed constant instead let occupancy-2 plans ask for a few KB too much and silently run one CTA per SM.
+  size_t static_smem = 0;
+  for (int i = 0; i < n_kernels; ++i) {
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, kernels[i].fn));
+    static_smem = std::max(static_smem, fa.sharedSizeBytes);
+  }
+  int smem_per_sm = 233472;
+  CUDA_TRY(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, plan->device));
+  auto cta_budget = [&](int o) -> size_t {
+    const size_t share = (size_t)smem_per_sm / o;
+    const size_t fixed = static_smem + 1024 + 256;
+    return std::min(kSmemMax, share > fixed ? share - fixed : 0);
+  };
   plan->pdl = env_int("STCD_PDL", 1);
   const int force_generic = env_int("STCD_FORCE_GENERIC", 0);
   int n_sm = 148;
@@ -1038,8 +1054,8 @@ int stcd_plan_finalize(stcd_plan* plan) {
       for (int o = 2; o >= 1 && !occ; --o) {
         if (force_occ && o != force_occ) continue;
         if (cols * o > 512) continue;
-        if ((o == 2 ? (kSmemMax - 2048) / 2 : kSmemMax) < 256 + p.tab_bytes + 2 * (size_t)p.a_stage_bytes) continue;
-        const size_t budget = (o == 2 ? (kSmemMax - 2048) / 2 : kSmemMax) - 256 - p.tab_bytes;
+        if (cta_budget(o) < 256 + p.tab_bytes + 2 * (size_t)p.a_stage_bytes) continue;
+        const size_t budget = cta_budget(o) - 256 - p.tab_bytes;
         const int min_stages = (o == 2) ? 3 : 2;
         if (!force_stream && w_all + (size_t)min_stages * p.a_stage_bytes <= budget) {
           occ = o;
@@ -1149,7 +1165,8 @@ int stcd_plan_finalize(stcd_plan* plan) {
     // epilogue features -> kernel instance (specialised when one exists, else the generic one)
     op.epi = (d.out_raw >= 0 ? stcd::E_RAW : 0u) | (!op.scale2.empty() ? stcd::E_AFF2 : 0u) | (d.res >= 0 ? stcd::E_RES : 0u) |
              (d.relu ? stcd::E_RELU : 0u) | (d.out0 >= 0 ? stcd::E_OUT0 : 0u) | (d.out_pool >= 0 ? stcd::E_POOL : 0u) |
-             (d.out_diff >= 0 ? stcd::E_DIFF : 0u) | (d.out_ext >= 0 ? stcd::E_F32 : 0u);
+             (d.out_diff >= 0 ? stcd::E_DIFF : 0u) | (d.out_ext >= 0 ? stcd::E_F32 : 0u) |
+             ((d.relu >= 2 || d.act_pre) ? stcd::E_ACTX : 0u);
     op.fn = nullptr;
     for (int i = 0; i < n_kernels && !force_generic; ++i)
       if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == op.epi) op.fn = kernels[i].fn;
