@@ -22,6 +22,9 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 CASES = {
     "siamunet_diff": ("models.SiamUnet_diff", "SiamUnet_diff", (3, 2), 2, 48, 32),
     "siamunet_conc": ("models.SiamUnet_conc", "SiamUnet_conc", (3, 2), 2, 32, 48),
+    "siamunet_sub": ("models.SiamUnet_sub", "SiamUnet_sub", (3, 2), 2, 32, 48),
+    "siamunet_crossconc": ("models.SiamUnet_crossconc", "SiamUnet_cross_conc", (3, 2), 2, 48, 32),
+    "unet_ef": ("models.Unet", "Unet", (3, 2), 2, 32, 32),
     "snunet": ("models.SNUNet", "SNUNet_ECAM", (3, 2), 2, 32, 48),
     # smp.SegCD("resnet34", encoder_weights=None, classes=1): what train_stcd.py:637 instantiates (ResNet-34 row of C3)
     "segcd_r34": ("segmentation_models_pytorch", "SegCD", ("resnet34", 5, None), 2, 64, 96),

@@ -36,10 +36,25 @@ def _siam_encoder(sd: SD, x: torch.Tensor) -> List[torch.Tensor]:
     return feats
 
 
+def _cross_conc(sd: SD, name: str, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """cross_conc.forward, models/SiamUnet_crossconc.py:27-33."""
+    n, c, h, w = a.shape
+    z = torch.ones(n, 2 * c, h, w)
+    z[:, 0::2] = a
+    z[:, 1::2] = b
+    z = F.relu(_bn(sd, f"{name}.diff.1", F.conv2d(z, sd[f"{name}.diff.0.weight"], sd[f"{name}.diff.0.bias"], padding=1, groups=c)))
+    return F.relu(_bn(sd, f"{name}.conv_res.1", F.conv2d(z, sd[f"{name}.conv_res.0.weight"], sd[f"{name}.conv_res.0.bias"], padding=1)))
+
+
 def siamunet_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor, fusion: str) -> torch.Tensor:
-    """models/SiamUnet_diff.py:94-181 (fusion='diff') / models/SiamUnet_conc.py:94-183 ('conc')."""
-    f1 = _siam_encoder(sd, x1)
-    f2 = _siam_encoder(sd, x2)
+    """models/SiamUnet_diff.py:94-181 ('diff'), SiamUnet_conc.py:94-183 ('conc'), SiamUnet_sub.py:94-180 ('sub'),
+    SiamUnet_crossconc.py:124-212 ('cross'), Unet.py:92-158 ('ef': one encoder over cat(x1, x2))."""
+    if fusion == "ef":
+        f2 = _siam_encoder(sd, torch.cat((x1, x2), 1))
+        f1 = f2
+    else:
+        f1 = _siam_encoder(sd, x1)
+        f2 = _siam_encoder(sd, x2)
     x = f2[4]                      # the decoder's bottleneck comes from image 2 only (:143,148)
 
     def dcbr(name, t):
@@ -50,7 +65,9 @@ def siamunet_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor, fusion: str) ->
         x = F.conv_transpose2d(x, sd[f"upconv{lvl}.weight"], sd[f"upconv{lvl}.bias"], stride=2, padding=1,
                                output_padding=1)
         x = F.pad(x, (0, a.size(3) - x.size(3), 0, a.size(2) - x.size(2)), mode="replicate")
-        x = torch.cat((x, torch.abs(a - b)), 1) if fusion == "diff" else torch.cat((x, a, b), 1)
+        skip = {"diff": lambda: (torch.abs(a - b),), "conc": lambda: (a, b), "sub": lambda: (torch.sub(b, a),),
+                "cross": lambda: (_cross_conc(sd, f"cross_conc{lvl}", a, b),), "ef": lambda: (a,)}[fusion]()
+        x = torch.cat((x,) + skip, 1)
         for n in names:
             x = dcbr(n, x)
     return F.conv_transpose2d(x, sd["conv11d.weight"], sd["conv11d.bias"], padding=1)

@@ -982,6 +982,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
   CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, plan->device));
 
   const int force_occ = env_int("STCD_FORCE_OCC", 0);
+  const int min_stages_occ2 = std::max(2, env_int("STCD_MIN_STAGES_OCC2", 2));  // two CTAs per SM with 2 A stages each beat one CTA with 8
   const int force_stream = env_int("STCD_FORCE_WSTREAM", 0);
   for (ConvOp& op : plan->convs) {
     const stcd_conv_desc& d = op.d;
@@ -1056,7 +1057,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
         if (cols * o > 512) continue;
         if (cta_budget(o) < 256 + p.tab_bytes + 2 * (size_t)p.a_stage_bytes) continue;
         const size_t budget = cta_budget(o) - 256 - p.tab_bytes;
-        const int min_stages = (o == 2) ? 3 : 2;
+        const int min_stages = (o == 2) ? min_stages_occ2 : 2;
         if (!force_stream && w_all + (size_t)min_stages * p.a_stage_bytes <= budget) {
           occ = o;
           p.w_resident = 1;

@@ -13,7 +13,9 @@ from stcd_b200 import siamunet, synth
 
 pytestmark = pytest.mark.gpu
 BF16_TOL = 2e-2
-NETS = {"diff": (siamunet.SiamUnet_diff, synth.GAINS["SiamUnet_diff"]), "conc": (siamunet.SiamUnet_conc, synth.GAINS["SiamUnet_conc"])}
+NETS = {"diff": (siamunet.SiamUnet_diff, synth.GAINS["SiamUnet_diff"]), "conc": (siamunet.SiamUnet_conc, synth.GAINS["SiamUnet_conc"]),
+        "sub": (siamunet.SiamUnet_sub, synth.GAINS["SiamUnet_sub"]), "cross": (siamunet.SiamUnet_cross_conc, synth.GAINS["SiamUnet_cross_conc"]),
+        "ef": (siamunet.Unet, synth.GAINS["Unet"])}
 
 
 def _net(fusion):
@@ -27,7 +29,7 @@ def _agreement(y, ref):
     return agree.float().mean().item(), agree[margin > BF16_TOL].float().mean().item()
 
 
-@pytest.mark.parametrize("fusion", ["diff", "conc"])
+@pytest.mark.parametrize("fusion", ["diff", "conc", "sub", "cross", "ef"])
 def test_forward_matches_oracle_and_emulator(fusion):
     net = _net(fusion)
     x1, x2 = synth.image_pairs(5, 64, 96)
@@ -37,6 +39,9 @@ def test_forward_matches_oracle_and_emulator(fusion):
     net = net.cuda()
     net.chunk_pairs = 4                      # 5 pairs -> one full chunk + a ragged one
     y = net(x1.cuda(), x2.cuda())
+    if fusion in ("sub", "cross"):          # these two return [x11d] (SiamUnet_sub.py:177-180)
+        assert isinstance(y, list) and len(y) == 1
+        y = y[0]
     assert isinstance(y, torch.Tensor) and y.shape == ref.shape and y.dtype == torch.float32
     y = y.cpu()
     assert (y - emu).abs().max().item() < 1.5e-2, "kernel vs emulator (same rounding points; bf16 flips cascade)"
@@ -45,14 +50,18 @@ def test_forward_matches_oracle_and_emulator(fusion):
     assert decided >= 0.999 and all_px >= 0.99
 
 
-@pytest.mark.parametrize("case", sorted(c for c in CASES if c.startswith("siamunet")))
+_FUSION = {"siamunet_diff": "diff", "siamunet_conc": "conc", "siamunet_sub": "sub", "siamunet_crossconc": "cross", "unet_ef": "ef"}
+
+
+@pytest.mark.parametrize("case", sorted(_FUSION))
 def test_forward_matches_golden(case, golden_dir):
     g = np.load(os.path.join(golden_dir, f"{case}.npz"))
-    fusion = case.split("_")[1]
+    fusion = _FUSION[case]
     net = synth.randomize_(NETS[fusion][0](3, 2).eval(), seed=int(g["weight_seed"]), gain=float(g["gain"])).cuda()
     assert float(g["gain"]) == NETS[fusion][1]
     x1, x2 = synth.image_pairs(int(g["batch"]), int(g["h"]), int(g["w"]), seed=int(g["data_seed"]))
-    y = net(x1.cuda(), x2.cuda()).cpu()
+    y = net(x1.cuda(), x2.cuda())
+    y = (y[-1] if isinstance(y, list) else y).cpu()
     ref = torch.from_numpy(g["out0"])
     assert (y - ref).abs().max().item() < BF16_TOL
     assert _agreement(y, ref)[1] >= 0.999

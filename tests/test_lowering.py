@@ -12,7 +12,10 @@ from stcd_b200 import siamunet, synth
 BF16_TOL = 2e-2
 
 
-@pytest.mark.parametrize("fusion,cls,gain", [("diff", siamunet.SiamUnet_diff, synth.GAINS["SiamUnet_diff"]), ("conc", siamunet.SiamUnet_conc, synth.GAINS["SiamUnet_conc"])])
+@pytest.mark.parametrize("fusion,cls,gain", [("diff", siamunet.SiamUnet_diff, synth.GAINS["SiamUnet_diff"]), ("conc", siamunet.SiamUnet_conc, synth.GAINS["SiamUnet_conc"]),
+                                             ("sub", siamunet.SiamUnet_sub, synth.GAINS["SiamUnet_sub"]),
+                                             ("cross", siamunet.SiamUnet_cross_conc, synth.GAINS["SiamUnet_cross_conc"]),
+                                             ("ef", siamunet.Unet, synth.GAINS["Unet"])])
 def test_siamunet_program_matches_oracle(fusion, cls, gain):
     net = synth.randomize_(cls(3, 2).eval(), gain=gain)
     x1, x2 = synth.image_pairs(3, 32, 48)

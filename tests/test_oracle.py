@@ -28,6 +28,8 @@ def _oracle_forward(case, sd, x1, x2):
         return [nets.siamunet_forward(sd, x1, x2, "diff")]
     if cls == "SiamUnet_conc":
         return [nets.siamunet_forward(sd, x1, x2, "conc")]
+    if cls in ("SiamUnet_sub", "SiamUnet_cross_conc", "Unet"):
+        return [nets.siamunet_forward(sd, x1, x2, {"SiamUnet_sub": "sub", "SiamUnet_cross_conc": "cross", "Unet": "ef"}[cls])]
     if cls == "SNUNet_ECAM":
         return [nets.snunet_forward(sd, x1, x2)]
     if cls == "SegCD":
