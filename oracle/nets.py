@@ -355,3 +355,64 @@ def changeformer_decoder(sd: SD, f1: List[torch.Tensor], f2: List[torch.Tensor],
 def changeformer_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor) -> List[torch.Tensor]:
     """ChangeFormerV6.forward, models/ChangeFormer.py:1691-1701: list of 5 tensors, full-resolution logits last."""
     return changeformer_decoder(sd, mit_encoder_features(sd, x1), mit_encoder_features(sd, x2))
+
+
+# ------------------------------------------------------------------------------------------
+# DTCDSCN (CDNet34: SE-ResNet-34 Siamese encoder, dilated centre block, SCSE decoder on the feature differences)
+def _se_block(sd: SD, pre: str, x: torch.Tensor, stride: int) -> torch.Tensor:
+    """SEBasicBlock.forward, models/DTCDSCN.py:93-109 (SELayer :22-26)."""
+    out = F.relu(_bn(sd, f"{pre}.bn1", F.conv2d(x, sd[f"{pre}.conv1.weight"], None, stride=stride, padding=1)))
+    out = _bn(sd, f"{pre}.bn2", F.conv2d(out, sd[f"{pre}.conv2.weight"], None, padding=1))
+    y = out.mean(dim=(2, 3))
+    y = torch.sigmoid(F.linear(F.relu(F.linear(y, sd[f"{pre}.se.fc.0.weight"])), sd[f"{pre}.se.fc.2.weight"]))
+    out = out * y[:, :, None, None]
+    if f"{pre}.downsample.0.weight" in sd:
+        x = _bn(sd, f"{pre}.downsample.1", F.conv2d(x, sd[f"{pre}.downsample.0.weight"], None, stride=stride))
+    return F.relu(out + x)
+
+
+def _dtcdscn_encoder(sd: SD, x: torch.Tensor, layers=(3, 4, 6, 3)) -> List[torch.Tensor]:
+    """CDNet_model.forward, encoder half (models/DTCDSCN.py:246-254)."""
+    x = F.relu(_bn(sd, "firstbn", F.conv2d(x, sd["firstconv.weight"], None, stride=2, padding=3)))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    feats = []
+    for li, n in enumerate(layers):
+        for b in range(n):
+            x = _se_block(sd, f"encoder{li + 1}.{b}", x, 2 if (b == 0 and li > 0) else 1)
+        feats.append(x)
+    return feats
+
+
+def _scse(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """SCSEBlock.forward, models/DTCDSCN.py:164-173."""
+    c = F.adaptive_avg_pool2d(x, 1)
+    c = torch.sigmoid(F.conv2d(F.relu(F.conv2d(c, sd[f"{pre}.channel_excitation.0.weight"])), sd[f"{pre}.channel_excitation.2.weight"]))
+    s = torch.sigmoid(F.conv2d(x, sd[f"{pre}.spatial_se.0.weight"]))
+    return x * c + x * s
+
+
+def _dtcdscn_decoder_block(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """DecoderBlock.forward, models/DTCDSCN.py:129-141."""
+    x = F.relu(_bn(sd, f"{pre}.norm1", F.conv2d(x, sd[f"{pre}.conv1.weight"], sd[f"{pre}.conv1.bias"])))
+    x = x + _scse(sd, f"{pre}.scse", x)
+    x = F.relu(_bn(sd, f"{pre}.norm2", F.conv_transpose2d(x, sd[f"{pre}.deconv2.weight"], sd[f"{pre}.deconv2.bias"], stride=2, padding=1,
+                                                          output_padding=1)))
+    return F.relu(_bn(sd, f"{pre}.norm3", F.conv2d(x, sd[f"{pre}.conv3.weight"], sd[f"{pre}.conv3.bias"])))
+
+
+def dtcdscn_forward(sd: SD, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """CDNet_model.forward, models/DTCDSCN.py:244-313 (the change branch: `*_master` modules on feature differences)."""
+    ex, ey = _dtcdscn_encoder(sd, x), _dtcdscn_encoder(sd, y)
+    t = ex[3] - ey[3]
+    d = t                                              # Dblock.forward (:65-71): x + sum of the dilated chain
+    acc = t
+    for i, dil in enumerate((1, 2, 4, 8)):
+        d = F.relu(F.conv2d(d, sd[f"dblock_master.dilate{i + 1}.weight"], sd[f"dblock_master.dilate{i + 1}.bias"], padding=dil, dilation=dil))
+        acc = acc + d
+    d4 = _dtcdscn_decoder_block(sd, "decoder4_master", acc) + ex[2] - ey[2]
+    d3 = _dtcdscn_decoder_block(sd, "decoder3_master", d4) + ex[1] - ey[1]
+    d2 = _dtcdscn_decoder_block(sd, "decoder2_master", d3) + ex[0] - ey[0]
+    d1 = _dtcdscn_decoder_block(sd, "decoder1_master", d2)
+    out = F.relu(F.conv_transpose2d(d1, sd["finaldeconv1_master.weight"], sd["finaldeconv1_master.bias"], stride=2, padding=1))
+    out = F.relu(F.conv2d(out, sd["finalconv2_master.weight"], sd["finalconv2_master.bias"], padding=1))
+    return F.conv2d(out, sd["finalconv3_master.weight"], sd["finalconv3_master.bias"], padding=1)

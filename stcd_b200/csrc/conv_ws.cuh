@@ -536,6 +536,37 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     const uint32_t hw = static_cast<uint32_t>(p.ho) * p.wo;  // pixels per image plane
     const uint32_t hw_pool = hw >> 2;
     const int cg8 = n0 >> 3;  // first 8-channel group of this N tile
+    // The residual does not depend on the accumulator.  With short K the epilogue is the pacing role (ncu: tensor pipe 50 %
+    // busy, epilogue warps on the long scoreboard), so its global-load latency must never be exposed: the first PF
+    // 16-channel steps of every (tile, sub-tile group) are fetched ONE WHOLE GROUP ahead -- issued before the wait for the
+    // previous group's accumulator -- and the later steps one step ahead.
+    constexpr int PF = (MS == 1) ? 2 : 1;
+    uint4 r_pre[PF][MS][2];
+    auto prefetch_unit = [&](int t2, int mb2) {
+      int tile2 = blockIdx.x + t2 * gridDim.x;
+      const int tile_x2 = tile2 % p.tiles_x;
+      tile2 /= p.tiles_x;
+      const int tile_y2 = tile2 % p.tiles_y;
+      const int img2 = tile2 / p.tiles_y;
+      const int gy2 = tile_y2 * kTileH + ty, gx2 = tile_x2 * kTileW + tx;
+      if (gy2 < p.hg && gx2 < p.wg) {
+        const uint32_t pix2 = static_cast<uint32_t>(gy2 * p.osy + phase.oy) * p.wo + (gx2 * p.osx + phase.ox);
+#pragma unroll
+        for (int sidx = 0; sidx < PF; ++sidx) {
+          const int c0 = 16 * sidx;
+          if (c0 < p.n_tile && n0 + c0 < p.cout) {
+#pragma unroll
+            for (int m = 0; m < MS; ++m) {
+              const __nv_bfloat16* r = p.res + ((static_cast<size_t>(img2 + p.m_off[mb2 + m]) * p.res_c8 + cg8 + 2 * sidx) * hw + pix2) * 8;
+              r_pre[sidx][m][0] = __ldg(reinterpret_cast<const uint4*>(r));
+              r_pre[sidx][m][1] = (p.cout - (n0 + c0) > 8) ? __ldg(reinterpret_cast<const uint4*>(r + static_cast<size_t>(hw) * 8))
+                                                          : make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+        }
+      }
+    };
+    if (has_res && my_tiles > 0) prefetch_unit(0, 0);
     for (int t = 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
       const int tile_x = tile % p.tiles_x;
@@ -564,10 +595,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
         size_t im[MS];                       // image index of each sub-tile of this group
 #pragma unroll
         for (int m = 0; m < MS; ++m) im[m] = static_cast<size_t>(img + p.m_off[mb + m]);
-        // the residual does not depend on the accumulator: fetch the first 16 channels before waiting
-        // for the MMAs and the next 16 while the current ones are processed (global-load latency
-        // would otherwise be exposed once per 16-column step)
-        uint4 r_cur[MS][2], r_nxt[MS][2];
+        uint4 r_cur[MS][2], r_nxt[MS][2], r_b[MS][2];
         auto load_res = [&](int c0, uint4 (&dst)[MS][2]) {
 #pragma unroll
           for (int m = 0; m < MS; ++m) {
@@ -577,7 +605,19 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
                                                   : make_uint4(0u, 0u, 0u, 0u);
           }
         };
-        if (has_res && valid) load_res(0, r_cur);
+        if (has_res) {
+#pragma unroll
+          for (int m = 0; m < MS; ++m) {
+            r_cur[m][0] = r_pre[0][m][0];
+            r_cur[m][1] = r_pre[0][m][1];
+            r_b[m][0] = r_pre[PF - 1][m][0];
+            r_b[m][1] = r_pre[PF - 1][m][1];
+          }
+          if (mb + MS < MT)                 // the next group's first steps, in flight while this group is processed
+            prefetch_unit(t, mb + MS);
+          else if (t + 1 < my_tiles)
+            prefetch_unit(t + 1, 0);
+        }
         if (mb == 0) {
           mbar_wait_relaxed(&acc_full[acc], (t >> 1) & 1);
           tc_fence_after();
@@ -589,7 +629,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
           const int ch = n0 + c0;
           if (ch >= p.cout) break;
           const bool two = (p.cout - ch) > 8;  // both 8-channel groups of this 16-column step are real
-          if (has_res && valid && c0 + 16 < p.n_tile && ch + 16 < p.cout) load_res(c0 + 16, r_nxt);
+          if (has_res && valid && c0 + 16 >= 16 * PF && c0 + 16 < p.n_tile && ch + 16 < p.cout) load_res(c0 + 16, r_nxt);
           uint32_t raw[MS][16];
 #pragma unroll
           for (int m = 0; m < MS; ++m) tmem_ld16(tgrp + m * p.n_tile + c0, raw[m]);
@@ -672,10 +712,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(d + 8);
           }
           if (has_res) {
+            const bool from_pre = (PF == 2) && (c0 == 0);   // step 1 was prefetched with step 0
 #pragma unroll
             for (int m = 0; m < MS; ++m) {
-              r_cur[m][0] = r_nxt[m][0];
-              r_cur[m][1] = r_nxt[m][1];
+              r_cur[m][0] = from_pre ? r_b[m][0] : r_nxt[m][0];
+              r_cur[m][1] = from_pre ? r_b[m][1] : r_nxt[m][1];
             }
           }
         }
