@@ -474,7 +474,7 @@ constexpr int kHeadTW = 32, kHeadTH = 16;
 // dst[b] = |src[b] - src[chunk + b]| on packed bf16 (fp32 subtract, one rounding): torch.abs(f1 - f2) of FFCTLCD
 // (decoders/unet/model.py:412).  Elementwise over 16-byte vectors: layout-agnostic.  HBM-bound: 4 B read + 2 B written.
 __global__ void __launch_bounds__(256) absdiff_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                      size_t vec_per_stream) {
+                                                      size_t vec_per_stream, int signed_diff) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < vec_per_stream;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float a[8], b[8];
@@ -483,7 +483,8 @@ __global__ void __launch_bounds__(256) absdiff_kernel(const __nv_bfloat16* __res
     uint32_t w[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      __nv_bfloat162 hv = __floats2bfloat162_rn(fabsf(a[2 * j] - b[2 * j]), fabsf(a[2 * j + 1] - b[2 * j + 1]));
+      const float d0 = a[2 * j] - b[2 * j], d1 = a[2 * j + 1] - b[2 * j + 1];     // signed: x - y (DTCDSCN.py:296-300)
+      __nv_bfloat162 hv = signed_diff ? __floats2bfloat162_rn(d0, d1) : __floats2bfloat162_rn(fabsf(d0), fabsf(d1));
       w[j] = *reinterpret_cast<uint32_t*>(&hv);
     }
     reinterpret_cast<uint4*>(dst)[i] = make_uint4(w[0], w[1], w[2], w[3]);

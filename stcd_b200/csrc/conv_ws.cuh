@@ -108,6 +108,7 @@ struct ConvParams {
   int32_t res_c8;
   __nv_bfloat16* out0;
   int32_t out0_c8, out0_coff;
+  int32_t reverse;   // 1: walk the tiles last-to-first (consecutive layers alternate, so a layer starts on the lines its producer wrote last: L2 hits)
   int32_t out0_s2d;  // 1: out0 is stored space-to-depth ([ho/2][wo/2] pixels, 4*cout channels)
   int32_t fold_cs, fold_cout;  // > 0: output phases folded into N (column p*fold_cs + c -> phase p, channel c)
   __nv_bfloat16* out_raw;
@@ -300,6 +301,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     pdl_wait();        // activations are written by the previous kernel(s)
     for (int t = 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
+      if (p.reverse) tile = p.n_tiles - 1 - tile;
       const int tile_x = tile % p.tiles_x;
       tile /= p.tiles_x;
       const int tile_y = tile % p.tiles_y;
@@ -540,10 +542,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     // busy, epilogue warps on the long scoreboard), so its global-load latency must never be exposed: the first PF
     // 16-channel steps of every (tile, sub-tile group) are fetched ONE WHOLE GROUP ahead -- issued before the wait for the
     // previous group's accumulator -- and the later steps one step ahead.
-    constexpr int PF = (MS == 1) ? 2 : 1;
+    constexpr int PF = (MS == 1) ? 2 : 1;   // deeper prefetch spills: the kernel sits at its 128-register budget
     uint4 r_pre[PF][MS][2];
     auto prefetch_unit = [&](int t2, int mb2) {
       int tile2 = blockIdx.x + t2 * gridDim.x;
+      if (p.reverse) tile2 = p.n_tiles - 1 - tile2;
       const int tile_x2 = tile2 % p.tiles_x;
       tile2 /= p.tiles_x;
       const int tile_y2 = tile2 % p.tiles_y;
@@ -569,6 +572,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     if (has_res && my_tiles > 0) prefetch_unit(0, 0);
     for (int t = 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
+      if (p.reverse) tile = p.n_tiles - 1 - tile;
       const int tile_x = tile % p.tiles_x;
       tile /= p.tiles_x;
       const int tile_y = tile % p.tiles_y;
@@ -595,7 +599,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
         size_t im[MS];                       // image index of each sub-tile of this group
 #pragma unroll
         for (int m = 0; m < MS; ++m) im[m] = static_cast<size_t>(img + p.m_off[mb + m]);
-        uint4 r_cur[MS][2], r_nxt[MS][2], r_b[MS][2];
+        uint4 r_cur[MS][2], r_nxt[MS][2], r_pf[PF > 1 ? PF - 1 : 1][MS][2];
         auto load_res = [&](int c0, uint4 (&dst)[MS][2]) {
 #pragma unroll
           for (int m = 0; m < MS; ++m) {
@@ -610,8 +614,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
           for (int m = 0; m < MS; ++m) {
             r_cur[m][0] = r_pre[0][m][0];
             r_cur[m][1] = r_pre[0][m][1];
-            r_b[m][0] = r_pre[PF - 1][m][0];
-            r_b[m][1] = r_pre[PF - 1][m][1];
+#pragma unroll
+            for (int q = 1; q < PF; ++q) {
+              r_pf[q - 1][m][0] = r_pre[q][m][0];
+              r_pf[q - 1][m][1] = r_pre[q][m][1];
+            }
           }
           if (mb + MS < MT)                 // the next group's first steps, in flight while this group is processed
             prefetch_unit(t, mb + MS);
@@ -712,11 +719,18 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(d + 8);
           }
           if (has_res) {
-            const bool from_pre = (PF == 2) && (c0 == 0);   // step 1 was prefetched with step 0
+            const int nstep = (c0 >> 4) + 1;               // steps 1 .. PF-1 were prefetched with step 0
 #pragma unroll
             for (int m = 0; m < MS; ++m) {
-              r_cur[m][0] = from_pre ? r_b[m][0] : r_nxt[m][0];
-              r_cur[m][1] = from_pre ? r_b[m][1] : r_nxt[m][1];
+              uint4 a = r_nxt[m][0], b = r_nxt[m][1];
+#pragma unroll
+              for (int q = 1; q < PF; ++q)
+                if (nstep == q) {
+                  a = r_pf[q - 1][m][0];
+                  b = r_pf[q - 1][m][1];
+                }
+              r_cur[m][0] = a;
+              r_cur[m][1] = b;
             }
           }
         }

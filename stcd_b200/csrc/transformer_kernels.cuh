@@ -222,4 +222,133 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const __nv_bfloat16* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Squeeze-and-excitation gates (DTCDSCN: SELayer, models/DTCDSCN.py:11-26; SCSEBlock :144-173).
+//   pass 1  chan_sum_kernel: per (image, channel) sums over a pixel range -> partial[b][range][C]  (fixed order: deterministic)
+//   pass 2  gate_apply_kernel: every CTA finishes the mean, runs the two tiny FC layers for its image in shared memory
+//           (g = sigmoid(W2 relu(W1 mean))), then applies its pixel range:
+//             mode 0 (SE block tail):  out = relu(x * g + res)                      (SEBasicBlock.forward :93-109)
+//             mode 1 (SCSE + skip):    out = x * (1 + g + sigmoid(ws . x_pixel))     (DecoderBlock: x + scse(x), :129-135,164-173)
+//           optionally also writing the space-to-depth copy a following stride-2 conv reads.
+// HBM-bound: x is read twice (three times in mode 1), written once (twice with the copy).
+constexpr int kGateMaxC = 512;
+constexpr int kGateMaxH = 32;
+
+__global__ void __launch_bounds__(256) chan_sum_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ partial, int C,
+                                                       int src_c8, int hw, int ranges) {
+  const int r = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+  const int per = (hw + ranges - 1) / ranges;
+  const int p0 = r * per, p1 = min(hw, p0 + per);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const __nv_bfloat16* base = src + (static_cast<size_t>(b) * src_c8 + g) * static_cast<size_t>(hw) * 8;
+  for (int px = p0 + threadIdx.x; px < p1; px += blockDim.x) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(px) * 8)), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += v[j];
+  }
+  __shared__ float sh[8][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float a = s[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) sh[warp][j] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += sh[w][threadIdx.x];
+    partial[(static_cast<size_t>(b) * ranges + r) * C + g * 8 + threadIdx.x] = a;
+  }
+}
+
+// grid (pixel blocks, B), 256 threads
+__global__ void __launch_bounds__(256) gate_apply_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ res,
+                                                         __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst2,
+                                                         const float* __restrict__ partial, const float* __restrict__ w1,
+                                                         const float* __restrict__ w2, const float* __restrict__ ws, int C, int hid,
+                                                         int src_c8, int res_c8, int dst_c8, int dst2_c8, int h, int w, int ranges,
+                                                         int mode, int pix_per_block) {
+  __shared__ float s_mean[kGateMaxC], s_gate[kGateMaxC], s_hid[kGateMaxH], s_ws[kGateMaxC];
+  const int b = blockIdx.y, hw = h * w, g8 = C >> 3;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int r = 0; r < ranges; ++r) a += partial[(static_cast<size_t>(b) * ranges + r) * C + c];
+    s_mean[c] = a / static_cast<float>(hw);
+    if (mode == 1) s_ws[c] = ws[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < hid) {
+    float a = 0.f;
+    for (int c = 0; c < C; ++c) a = fmaf(w1[threadIdx.x * C + c], s_mean[c], a);
+    s_hid[threadIdx.x] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int u = 0; u < hid; ++u) a = fmaf(w2[c * hid + u], s_hid[u], a);
+    s_gate[c] = 1.f / (1.f + expf(-a));
+  }
+  __syncthreads();
+  const int p_end = min(hw, (static_cast<int>(blockIdx.x) + 1) * pix_per_block);
+  for (int pix = blockIdx.x * pix_per_block + threadIdx.x; pix < p_end; pix += blockDim.x) {
+    const __nv_bfloat16* s = src + (static_cast<size_t>(b) * src_c8 * hw + pix) * 8;
+    float gs = 0.f;
+    if (mode == 1) {
+      float a = 0.f;
+      for (int g = 0; g < g8; ++g) {
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(s + static_cast<size_t>(g) * hw * 8)), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = fmaf(v[j], s_ws[g * 8 + j], a);
+      }
+      gs = 1.f / (1.f + expf(-a));
+    }
+    __nv_bfloat16* o = dst + (static_cast<size_t>(b) * dst_c8 * hw + pix) * 8;
+    __nv_bfloat16* o2 = nullptr;
+    size_t hw2 = 0;
+    if (dst2 != nullptr) {
+      const int y = pix / w, x = pix - y * w;
+      hw2 = static_cast<size_t>(hw >> 2);
+      o2 = dst2 + ((static_cast<size_t>(b) * dst2_c8 + static_cast<size_t>(((y & 1) * 2 + (x & 1)) * g8)) * hw2 + static_cast<size_t>(y >> 1) * (w >> 1) + (x >> 1)) * 8;
+    }
+    for (int g = 0; g < g8; ++g) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(s + static_cast<size_t>(g) * hw * 8)), v);
+      if (mode == 0) {
+        float rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (res != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(res + ((static_cast<size_t>(b) * res_c8 + g) * hw + pix) * 8)), rv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], s_gate[g * 8 + j], rv[j]), 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = v[j] * (1.f + s_gate[g * 8 + j] + gs);
+      }
+      const uint4 q = pack8(v);
+      *reinterpret_cast<uint4*>(o + static_cast<size_t>(g) * hw * 8) = q;
+      if (o2 != nullptr) *reinterpret_cast<uint4*>(o2 + static_cast<size_t>(g) * hw2 * 8) = q;
+    }
+  }
+}
+
+// dst = sum of up to 5 tensors (Dblock: x + d1 + d2 + d3 + d4, models/DTCDSCN.py:65-71), elementwise over 16-byte vectors
+struct AddNParams {
+  const __nv_bfloat16* src[5];
+  int n;
+};
+__global__ void __launch_bounds__(256) add_n_kernel(const AddNParams p, __nv_bfloat16* __restrict__ dst, size_t vecs) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < vecs; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < p.n; ++k) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.src[k]) + i), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += v[j];
+    }
+    reinterpret_cast<uint4*>(dst)[i] = pack8(a);
+  }
+}
+
 }  // namespace stcd
