@@ -56,6 +56,9 @@ WORKLOADS = {
     "changeformer_v6_256_b32": dict(net="ChangeFormerV6", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=32,
                                     desc="C5: ChangeFormerV6 (MiT transformer encoder + difference decoder) 256x256 RGB pairs, "
                                          "batch 32 per GPU, bf16"),
+    "dtcdscn_256_b32": dict(net="CDNet_model", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=32,
+                            desc="DTCDSCN (CDNet34: Siamese SE-ResNet-34, dilated centre block, SCSE decoder on feature differences) "
+                                 "256x256 RGB pairs, batch 32 per GPU, bf16"),
     "segcd_r34_256_b64": dict(net="SegCD", n_class=1, h=256, w=256, batch=64, kind="sigmoid", chunk=16,
                               desc="smp SegCD (Unet, ResNet-34 Siamese encoder) 256x256 RGB pairs, batch 64 per GPU, bf16"),
 }
@@ -86,6 +89,8 @@ def oracle_forward(wl, sd, x1, x2):
         return nets.changegnn_forward(sd, x1, x2)
     if wl["net"] == "ChangeFormerV6":
         return nets.changeformer_forward(sd, x1, x2)
+    if wl["net"] == "CDNet_model":
+        return nets.dtcdscn_forward(sd, x1, x2)
     raise KeyError(wl["net"])
 
 

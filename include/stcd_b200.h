@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 11
+#define STCD_ABI_VERSION 12
 
 enum stcd_status {
   STCD_OK = 0,
@@ -184,6 +184,20 @@ int stcd_plan_add_maxpool_s2d(stcd_plan* plan, int src_tensor, int dst_tensor, i
 /* dst = |src[T1 images] - src[T2 images]| (torch.abs(f1 - f2), FFCTLCD.forward, decoders/unet/model.py:412): src holds
  * both temporal streams (mult 2), dst one stream with the same [h][w][c] (any layout: elementwise). */
 int stcd_plan_add_absdiff(stcd_plan* plan, int src_tensor, int dst_tensor);
+/* the signed variant dst = (add) + src[T1] - src[T2] (DTCDSCN: decoder(...) + e_x - e_y, models/DTCDSCN.py:294-300);
+ * add_or_neg: a one-stream tensor of dst's shape, or -1 */
+int stcd_plan_add_subdiff(stcd_plan* plan, int src_tensor, int add_or_neg, int dst_tensor);
+
+/* Squeeze-and-excitation gates of DTCDSCN on plan tensors (models/DTCDSCN.py): g = sigmoid(w2 relu(w1 mean_hw(src))),
+ * w1 HOST fp32 [hid][c], w2 HOST fp32 [c][hid] (bias-free: SELayer :14-19, SCSEBlock.channel_excitation :153-158).
+ *   mode 0 (SEBasicBlock tail, :93-109):  dst = relu(src * g + res)        res_or_neg: tensor id or -1
+ *   mode 1 (DecoderBlock, :129-135):       dst = src * (1 + g + sigmoid(ws . src_pixel))   ws HOST fp32 [c] (spatial_se :160-162)
+ * dst_s2d_or_neg >= 0 also writes the space-to-depth copy.  c <= 512, hid <= 32. */
+int stcd_plan_add_channel_gate(stcd_plan* plan, int src_tensor, int res_or_neg, int dst_tensor, int dst_s2d_or_neg, int c, int hid,
+                               const float* w1, const float* w2, const float* ws_or_null, int mode);
+
+/* dst = sum of n <= 5 plan tensors of identical shape (Dblock.forward: x + d1 + d2 + d3 + d4, models/DTCDSCN.py:65-71) */
+int stcd_plan_add_sum(stcd_plan* plan, const int* src_tensors, int n, int dst_tensor);
 
 /* SegCD's tail (segmentation_models_pytorch/decoders/unet/model.py:321-330) as one op over the decoder
  * output `src` (bf16, both temporal streams: mult = 2, c channels): with head = Conv2d(c, 1, 3, padding=1)

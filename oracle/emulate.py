@@ -269,7 +269,30 @@ def run_dwconv(op: L.DWConvSpec, T: Dict[str, torch.Tensor]) -> None:
 
 def run_aux(op, T, chunk, ext, nv):
     if isinstance(op, L.AbsDiffSpec):
-        T[op.dst][..., : op.c] = _bf16((T[op.src][:chunk, :, :, : op.c] - T[op.src][chunk: 2 * chunk, :, :, : op.c]).abs())
+        d = T[op.src][:chunk, :, :, : op.c] - T[op.src][chunk: 2 * chunk, :, :, : op.c]
+        if op.signed and op.add is not None:
+            d = (T[op.add][..., : op.c] + T[op.src][:chunk, :, :, : op.c]) - T[op.src][chunk: 2 * chunk, :, :, : op.c]
+        T[op.dst][..., : op.c] = _bf16(d if op.signed else d.abs())
+        return None
+    if isinstance(op, L.SumSpec):
+        T[op.dst][...] = _bf16(sum(T[s_] for s_ in op.srcs))
+        return None
+    if isinstance(op, L.ChannelGateSpec):
+        x = T[op.src][..., : op.c]
+        g = torch.sigmoid(torch.relu(x.mean(dim=(1, 2)) @ torch.from_numpy(op.w1).T) @ torch.from_numpy(op.w2).T)[:, None, None, :]
+        if op.mode == 0:
+            y = x * g + (T[op.res][..., : op.c] if op.res is not None else 0.0)
+            y = torch.relu(y)
+        else:
+            gs = torch.sigmoid((x * torch.from_numpy(op.ws)).sum(-1, keepdim=True))
+            y = x * (1.0 + g + gs)
+        y = _bf16(y)
+        T[op.dst][..., : op.c] = y
+        if op.dst_s2d is not None:
+            for py in range(2):
+                for px in range(2):
+                    k = (py * 2 + px) * op.c
+                    T[op.dst_s2d][..., k: k + op.c] = y[:, py::2, px::2]
         return None
     if isinstance(op, L.LayerNormSpec):
         return run_layernorm(op, T)

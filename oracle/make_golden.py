@@ -9,6 +9,7 @@ TEST INFRASTRUCTURE.
 from __future__ import annotations
 
 import os
+import sys
 
 import numpy as np
 import torch
@@ -34,6 +35,8 @@ CASES = {
     # (absent upstream dependency: this fixture pins everything EXCEPT the Grapher restatement itself)
     "changegnn_v1": ("models.ChangeVIG", "ChangeGNNV1", (3, 2, False, 256), 1, 256, 256),
     "changeformer_v6": ("models.ChangeFormer", "ChangeFormerV6", (3, 2, False, 256), 1, 256, 256),
+    # CDNet34 = CDNet_model(in_channels, SEBasicBlock, [3, 4, 6, 3], num_classes) (models/DTCDSCN.py:316-320): the defaults
+    "dtcdscn": ("models.DTCDSCN", "CDNet_model", (3,), 2, 64, 96),
 }
 
 
@@ -45,7 +48,10 @@ def reference_net(case: str):
 
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])            # optional: regenerate the named cases only
     for case, (mod, cls, args, b, h, w) in CASES.items():
+        if only and case not in only:
+            continue
         net = reference_net(case)
         x1, x2 = synth.image_pairs(b, h, w)
         with torch.no_grad():
@@ -56,6 +62,8 @@ def main() -> None:
                             weight_seed=synth.WEIGHT_SEED, data_seed=synth.DATA_SEED,
                             x1_sum=float(x1.double().sum()), n_out=len(ys), **arrays)
         print(case, [tuple(t.shape) for t in ys], "std", float(ys[-1].std()))
+    if only and "segmentation_metric" not in only:
+        return
     # evaluator: the reference's SegmentationMetric on seeded predictions/labels
     SM = refimport.segmentation_metric_class()
     g = torch.Generator().manual_seed(7)

@@ -126,7 +126,7 @@ class EcamDesc(C.Structure):
     ]
 
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -143,6 +143,10 @@ SYMBOLS = [
     ("stcd_plan_add_maxpool_s2d", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("stcd_plan_add_seg_head", C.c_int, [C.c_void_p, C.c_void_p]),
     ("stcd_plan_add_absdiff", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("stcd_plan_add_subdiff", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    ("stcd_plan_add_channel_gate", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                             C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]),
+    ("stcd_plan_add_sum", C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int]),
     ("stcd_plan_add_graph_conv", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     ("stcd_plan_add_layernorm", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                           C.c_float]),

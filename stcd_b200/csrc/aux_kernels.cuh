@@ -473,17 +473,24 @@ constexpr int kHeadTW = 32, kHeadTH = 16;
 
 // dst[b] = |src[b] - src[chunk + b]| on packed bf16 (fp32 subtract, one rounding): torch.abs(f1 - f2) of FFCTLCD
 // (decoders/unet/model.py:412).  Elementwise over 16-byte vectors: layout-agnostic.  HBM-bound: 4 B read + 2 B written.
+// signed_diff: dst = (add ? add : 0) + src[T1] - src[T2]  (DTCDSCN's skip terms "decoder(...) + e_x - e_y", models/DTCDSCN.py:296-300)
 __global__ void __launch_bounds__(256) absdiff_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                      size_t vec_per_stream, int signed_diff) {
+                                                      size_t vec_per_stream, int signed_diff, const __nv_bfloat16* __restrict__ add) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < vec_per_stream;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float a[8], b[8];
     unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(src) + i), a);
     unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(src) + vec_per_stream + i), b);
+    if (add != nullptr) {
+      float c[8];
+      unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(add) + i), c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = (c[j] + a[j]);     // reference order: (d + e_x) - e_y
+    }
     uint32_t w[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float d0 = a[2 * j] - b[2 * j], d1 = a[2 * j + 1] - b[2 * j + 1];     // signed: x - y (DTCDSCN.py:296-300)
+      const float d0 = a[2 * j] - b[2 * j], d1 = a[2 * j + 1] - b[2 * j + 1];
       __nv_bfloat162 hv = signed_diff ? __floats2bfloat162_rn(d0, d1) : __floats2bfloat162_rn(fabsf(d0), fabsf(d1));
       w[j] = *reinterpret_cast<uint32_t*>(&hv);
     }

@@ -131,6 +131,19 @@ struct DWConvOp {
 
 struct AbsDiffOp {
   int src, dst, c;
+  int signed_diff = 0;
+  int add = -1;
+};
+
+struct GateOp {
+  int src, res, dst, dst2, c, hid, mode, ranges;
+  std::vector<float> w;      // w1 [hid][c] | w2 [c][hid] | ws [c] (mode 1)
+  float* w_dev = nullptr;
+  float* partial = nullptr;  // [imgs][ranges][c]
+};
+
+struct SumOp {
+  int src[5], n, dst;
 };
 
 struct SegHeadOp {
@@ -151,7 +164,7 @@ struct EcamOp {
 };
 
 struct Op {
-  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head, 5 graph conv, 6 bilinear up, 7 layer norm, 8 attention, 9 dw conv, 10 |T1 - T2|
+  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head, 5 graph conv, 6 bilinear up, 7 layer norm, 8 attention, 9 dw conv, 10 T1 - T2 (abs or signed), 11 channel gate, 12 sum
   int idx;
 };
 
@@ -173,6 +186,8 @@ struct stcd_plan {
   std::vector<AttentionOp> attns;
   std::vector<DWConvOp> dws;
   std::vector<AbsDiffOp> absdiffs;
+  std::vector<GateOp> gates;
+  std::vector<SumOp> sums;
   std::vector<Op> ops;
   uint8_t* workspace = nullptr;
   size_t workspace_bytes = 0;
@@ -320,7 +335,33 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
       const Tensor& td = plan->tensors[k.dst];
       const size_t vecs = td.bytes / 16;           // 16-byte vectors per stream (dst holds one stream)
       stcd::absdiff_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((vecs + 255) / 256, 148 * 16)), 256, 0, st>>>(
-          (const __nv_bfloat16*)plan->tensors[k.src].ptr, (__nv_bfloat16*)td.ptr, vecs);
+          (const __nv_bfloat16*)plan->tensors[k.src].ptr, (__nv_bfloat16*)td.ptr, vecs, k.signed_diff,
+          k.add >= 0 ? (const __nv_bfloat16*)plan->tensors[k.add].ptr : nullptr);
+      CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 11) {
+      const GateOp& k = plan->gates[o.idx];
+      const Tensor& ts = plan->tensors[k.src];
+      const Tensor& td = plan->tensors[k.dst];
+      const int B = ts.mult * plan->chunk, hw = ts.h * ts.w;
+      stcd::chan_sum_kernel<<<dim3(k.ranges, k.c / 8, B), 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, k.partial, k.c, ts.c / 8, hw, k.ranges);
+      const int ppb = 1024;
+      const float* w1 = k.w_dev;
+      const float* w2 = w1 + (size_t)k.hid * k.c;
+      const float* ws = k.mode == 1 ? w2 + (size_t)k.c * k.hid : nullptr;
+      stcd::gate_apply_kernel<<<dim3((hw + ppb - 1) / ppb, B), 256, 0, st>>>(
+          (const __nv_bfloat16*)ts.ptr, k.res >= 0 ? (const __nv_bfloat16*)plan->tensors[k.res].ptr : nullptr, (__nv_bfloat16*)td.ptr,
+          k.dst2 >= 0 ? (__nv_bfloat16*)plan->tensors[k.dst2].ptr : nullptr, k.partial, w1, w2, ws, k.c, k.hid, ts.c / 8,
+          k.res >= 0 ? plan->tensors[k.res].c / 8 : 0, td.c / 8, k.dst2 >= 0 ? plan->tensors[k.dst2].c / 8 : 0, ts.h, ts.w, k.ranges, k.mode,
+          ppb);
+      CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 12) {
+      const SumOp& k = plan->sums[o.idx];
+      const Tensor& td = plan->tensors[k.dst];
+      stcd::AddNParams ap;
+      ap.n = k.n;
+      for (int i = 0; i < 5; ++i) ap.src[i] = i < k.n ? (const __nv_bfloat16*)plan->tensors[k.src[i]].ptr : nullptr;
+      const size_t vecs = td.bytes / 16;
+      stcd::add_n_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((vecs + 255) / 256, 148 * 16)), 256, 0, st>>>(ap, (__nv_bfloat16*)td.ptr, vecs);
       CUDA_TRY(cudaGetLastError());
     } else if (o.kind == 7) {
       const LayerNormOp& k = plan->lns[o.idx];
@@ -479,6 +520,10 @@ void stcd_plan_destroy(stcd_plan* plan) {
     if (e.w_dev) cudaFree(e.w_dev);
   for (LayerNormOp& k : plan->lns)
     if (k.gb_dev) cudaFree(k.gb_dev);
+  for (GateOp& k : plan->gates) {
+    if (k.w_dev) cudaFree(k.w_dev);
+    if (k.partial) cudaFree(k.partial);
+  }
   for (DWConvOp& k : plan->dws)
     if (k.wb_dev) cudaFree(k.wb_dev);
   for (GraphOp& g : plan->graphs) {
@@ -707,6 +752,79 @@ int stcd_plan_add_absdiff(stcd_plan* plan, int src_tensor, int dst_tensor) {
     return -fail(STCD_ERR_INVALID, "abs-diff: src must be [2*chunk,%d,%d,%d] (both streams) and dst the same with one stream", td.h, td.w, td.c);
   plan->absdiffs.push_back({src_tensor, dst_tensor, td.c});
   plan->ops.push_back({10, (int)plan->absdiffs.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_subdiff(stcd_plan* plan, int src_tensor, int add, int dst_tensor) {
+  if (plan && add >= 0) {
+    if (!valid_tensor(plan, add) || !valid_tensor(plan, dst_tensor)) return -fail(STCD_ERR_INVALID, "bad tensor id");
+    const Tensor& ta = plan->tensors[add];
+    const Tensor& td = plan->tensors[dst_tensor];
+    if (ta.mult != 1 || ta.h != td.h || ta.w != td.w || ta.c != td.c) return -fail(STCD_ERR_INVALID, "signed diff: addend shape");
+  }
+  const int r = stcd_plan_add_absdiff(plan, src_tensor, dst_tensor);
+  if (r >= 0) {
+    plan->absdiffs.back().signed_diff = 1;
+    plan->absdiffs.back().add = add;
+  }
+  return r;
+}
+
+int stcd_plan_add_channel_gate(stcd_plan* plan, int src_tensor, int res, int dst_tensor, int dst_s2d, int c, int hid, const float* w1,
+                               const float* w2, const float* ws, int mode) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, src_tensor) || !valid_tensor(plan, dst_tensor) || (res >= 0 && !valid_tensor(plan, res)) ||
+      (dst_s2d >= 0 && !valid_tensor(plan, dst_s2d)) || !w1 || !w2 || (mode == 1 && !ws) || mode < 0 || mode > 1)
+    return -fail(STCD_ERR_INVALID, "channel gate: bad tensor id / NULL weights / mode");
+  const Tensor& ts = plan->tensors[src_tensor];
+  const Tensor& td = plan->tensors[dst_tensor];
+  if (c < 8 || (c % 8) || c > stcd::kGateMaxC || hid < 1 || hid > stcd::kGateMaxH || ts.c < c || td.c < c || ts.h != td.h || ts.w != td.w ||
+      ts.mult != td.mult)
+    return -fail(STCD_ERR_INVALID, "channel gate: c=%d (<= %d) hid=%d (<= %d); src/dst must match", c, stcd::kGateMaxC, hid, stcd::kGateMaxH);
+  if (res >= 0) {
+    const Tensor& tr = plan->tensors[res];
+    if (tr.h != ts.h || tr.w != ts.w || tr.c < c || tr.mult != ts.mult) return -fail(STCD_ERR_INVALID, "channel gate: residual shape");
+  }
+  if (dst_s2d >= 0) {
+    const Tensor& t2 = plan->tensors[dst_s2d];
+    if ((ts.h % 2) || (ts.w % 2) || t2.h != ts.h / 2 || t2.w != ts.w / 2 || t2.c != 4 * c || t2.mult != ts.mult)
+      return -fail(STCD_ERR_INVALID, "channel gate: space-to-depth copy must be [%d*chunk,%d,%d,%d]", ts.mult, ts.h / 2, ts.w / 2, 4 * c);
+  }
+  GateOp k;
+  k.src = src_tensor;
+  k.res = res;
+  k.dst = dst_tensor;
+  k.dst2 = dst_s2d;
+  k.c = c;
+  k.hid = hid;
+  k.mode = mode;
+  k.ranges = std::max(1, std::min(16, ts.h * ts.w / 4096));
+  k.w.assign(w1, w1 + (size_t)hid * c);
+  k.w.insert(k.w.end(), w2, w2 + (size_t)c * hid);
+  if (mode == 1) k.w.insert(k.w.end(), ws, ws + c);
+  plan->gates.push_back(std::move(k));
+  plan->ops.push_back({11, (int)plan->gates.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_sum(stcd_plan* plan, const int* src_tensors, int n, int dst_tensor) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!src_tensors || n < 1 || n > 5 || !valid_tensor(plan, dst_tensor)) return -fail(STCD_ERR_INVALID, "sum: 1..5 sources");
+  const Tensor& td = plan->tensors[dst_tensor];
+  SumOp k;
+  k.n = n;
+  k.dst = dst_tensor;
+  for (int i = 0; i < 5; ++i) k.src[i] = -1;
+  for (int i = 0; i < n; ++i) {
+    if (!valid_tensor(plan, src_tensors[i])) return -fail(STCD_ERR_INVALID, "sum: bad tensor id");
+    const Tensor& t = plan->tensors[src_tensors[i]];
+    if (t.h != td.h || t.w != td.w || t.c != td.c || t.mult != td.mult) return -fail(STCD_ERR_INVALID, "sum: shapes differ");
+    k.src[i] = src_tensors[i];
+  }
+  plan->sums.push_back(k);
+  plan->ops.push_back({12, (int)plan->sums.size() - 1});
   return (int)plan->ops.size() - 1;
 }
 
@@ -1215,6 +1333,12 @@ int stcd_plan_finalize(stcd_plan* plan) {
   }
   // the 3-stream head instances stage 58 KB: dynamic shared memory above the 48 KB default
   CUDA_TRY(cudaFuncSetAttribute(stcd::segcd_head_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  for (GateOp& k : plan->gates) {
+    const Tensor& ts = plan->tensors[k.src];
+    CUDA_TRY(cudaMalloc(&k.w_dev, k.w.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(k.w_dev, k.w.data(), k.w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&k.partial, (size_t)ts.mult * plan->chunk * k.ranges * k.c * sizeof(float)));
+  }
   for (LayerNormOp& k : plan->lns) {
     CUDA_TRY(cudaMalloc(&k.gb_dev, k.gb.size() * sizeof(float)));
     CUDA_TRY(cudaMemcpy(k.gb_dev, k.gb.data(), k.gb.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1297,6 +1421,7 @@ int64_t stcd_plan_launches(const stcd_plan* plan, int n_pairs) {
   if (!plan || n_pairs < 1) return 0;
   const int64_t chunks = (n_pairs + plan->chunk - 1) / plan->chunk;
   int64_t per_chunk = (int64_t)plan->ops.size() + (int64_t)plan->ecams.size();  // an ECAM head op is two kernels
+  per_chunk += (int64_t)plan->gates.size();                                    // a channel gate is two kernels
   for (const GraphOp& g : plan->graphs) per_chunk += 3 + (g.r > 1 ? 2 : 0);     // unpack, [pool], norm, [norm y], kNN, max-relative
   return chunks * per_chunk;
 }

@@ -223,6 +223,33 @@ class AbsDiffSpec:
     src: str
     dst: str
     c: int
+    signed: bool = False         # True: (add +) src[T1] - src[T2], no abs (DTCDSCN: decoder(..) + e_x - e_y, models/DTCDSCN.py:294-300)
+    add: Optional[str] = None
+
+
+@dataclass
+class ChannelGateSpec:
+    """Squeeze-and-excitation gates of DTCDSCN (models/DTCDSCN.py): g = sigmoid(w2 relu(w1 mean_hw(src))).
+    mode 0 (SEBasicBlock tail :93-109): dst = relu(src * g + res); mode 1 (DecoderBlock :129-135 with SCSEBlock :144-173):
+    dst = src * (1 + g + sigmoid(ws . src_pixel)).  dst_s2d: optional space-to-depth copy."""
+    name: str
+    src: str
+    dst: str
+    c: int
+    w1: np.ndarray               # float32 [hid][c]
+    w2: np.ndarray               # float32 [c][hid]
+    mode: int = 0
+    res: Optional[str] = None
+    ws: Optional[np.ndarray] = None   # float32 [c]
+    dst_s2d: Optional[str] = None
+
+
+@dataclass
+class SumSpec:
+    """dst = sum of up to five tensors (Dblock.forward, models/DTCDSCN.py:65-71)."""
+    name: str
+    srcs: List[str]
+    dst: str
 
 
 @dataclass
@@ -352,6 +379,7 @@ def _taps_to_gemm(
     phase_taps: Sequence[Tuple[int, int, List[Tuple[int, int, torch.Tensor]]]],
     cout: int,
     pair: bool,
+    max_kc: int = 64,
 ):
     """Build the K-program and the packed weights.
 
@@ -372,7 +400,7 @@ def _taps_to_gemm(
     for s in segs:
         if s.c_off % 8:
             raise ValueError(f"{name}: segment channel offset {s.c_off} is not a multiple of 8")
-    kc = choose_kc(stored_c)
+    kc = min(choose_kc(stored_c), max_kc)      # wide halos (dilated convs) take thinner chunks: the A stage is (tile + halo) * kc
     n_tile, cout_pad = choose_n_tile(cout, pair)
     n_nt = cout_pad // n_tile
     sy = [1] * len(srcs)
@@ -599,6 +627,7 @@ def add_conv(
     act: Optional[str] = None,
     act_alpha: float = 0.0,
     act_pre: bool = False,
+    max_kc: int = 64,
 ) -> ConvSpec:
     if act is not None and relu:
         raise ValueError(f"{name}: give either relu=True or act=...")
@@ -625,7 +654,7 @@ def add_conv(
     elif fold:
         raise ValueError(f"{name}: phase folding needs an up-sampling op whose only output is out0")
     wbits, kc, n_tile, cout_pad, phases, chunks, taps, srcs, sy, sx, ey, ex = _taps_to_gemm(
-        prog, name, segs, phase_taps, cout, pair)
+        prog, name, segs, phase_taps, cout, pair, max_kc)
     spec = ConvSpec(
         name=name, srcs=srcs, src_sy=sy, src_sx=sx, src_ey=ey, src_ex=ex, hg=hg, wg=wg, img_mult=img_mult, pair=pair,
         weights=wbits, kc=kc, n_tile=n_tile, cout=cout, cout_pad=cout_pad, phases=phases, chunks=chunks, taps=taps,
@@ -686,7 +715,13 @@ def op_bytes_per_pair(prog: Program, op) -> int:
         return (2 + (op.diff_src is not None)) * op.c * t.h * t.w * 2 + 3 * t.h * t.w * 4
     if isinstance(op, AbsDiffSpec):
         t = T[op.dst]
-        return 3 * op.c * t.h * t.w * 2
+        return (3 + (op.add is not None)) * op.c * t.h * t.w * 2
+    if isinstance(op, ChannelGateSpec):
+        t = T[op.src]
+        return t.mult * op.c * t.h * t.w * 2 * (3 + (op.mode == 1) + (op.res is not None) + (op.dst_s2d is not None))
+    if isinstance(op, SumSpec):
+        t = T[op.dst]
+        return t.mult * t.c * t.h * t.w * 2 * (len(op.srcs) + 1)
     if isinstance(op, EcamHeadSpec):
         t = T[op.srcs[0]]
         return 2 * 4 * op.c * t.h * t.w * 2 + op.n_class * t.h * t.w * 4

@@ -16,13 +16,14 @@ from torch.nn import init
 from .siamunet import SiamUnet_conc, SiamUnet_cross_conc, SiamUnet_diff, SiamUnet_sub, Unet
 from .changeformer import ChangeFormerV6
 from .changevig import ChangeGNNV1
+from .dtcdscn import CDNet34, CDNet_model
 from .segcd import SegCD
 from .snunet import SNUNet_ECAM
 
 # registry keys of models/networks.py:144-214 that this library does NOT implement (yet): asking for one
 # raises NotImplementedError like an unknown key does upstream, with the reason.
 _REFERENCE_ONLY = (
-    "DTCDSCN", "IFNet", "base_resnet18", "base_transformer_pos_s4",
+    "IFNet", "base_resnet18", "base_transformer_pos_s4",
     "base_transformer_pos_s4_dd8", "base_transformer_pos_s4_dd8_dedim8", "ChangeFormerV1", "ChangeFormerV2",
     "ChangeFormerV3", "ChangeFormerV4", "ChangeFormerV5", "ChangeGNNV2",
     "ChangeGNNV2_sub", "ChangeGNNV2_abs", "ChangeGNNV2_conc", "GNN",
@@ -34,6 +35,7 @@ _REGISTRY = {
     "SiamUnet_cross_conc": lambda a: SiamUnet_cross_conc(input_nbr=3, label_nbr=a.n_class),   # networks.py:152-153
     "SiamUnet_abs": lambda a: SiamUnet_diff(input_nbr=3, label_nbr=a.n_class),     # networks.py:148-149
     "SiamUnet_conc": lambda a: SiamUnet_conc(input_nbr=3, label_nbr=a.n_class),    # networks.py:151-152
+    "DTCDSCN": lambda a: CDNet34(in_channels=3, num_classes=a.n_class),            # networks.py:159-160
     "SNUNet": lambda a: SNUNet_ECAM(in_ch=3, out_ch=a.n_class),                    # networks.py:168-169
     "ChangeGNNV1": lambda a: ChangeGNNV1(embed_dim=a.embed_dim),                   # networks.py:199-200
     "ChangeFormerV6": lambda a: ChangeFormerV6(embed_dim=a.embed_dim),             # networks.py:190-191
@@ -43,7 +45,8 @@ _REGISTRY = {
 # class name (= the reference's) -> drop-in wrapper; synth.GAINS / bench.py / the tests key on these names
 CLASSES = {"SiamUnet_diff": SiamUnet_diff, "SiamUnet_conc": SiamUnet_conc, "SiamUnet_sub": SiamUnet_sub,
            "SiamUnet_cross_conc": SiamUnet_cross_conc, "Unet": Unet, "SNUNet_ECAM": SNUNet_ECAM, "SegCD": SegCD,
-           "ChangeGNNV1": ChangeGNNV1, "ChangeFormerV6": ChangeFormerV6}
+           "ChangeGNNV1": ChangeGNNV1, "ChangeFormerV6": ChangeFormerV6,
+           "CDNet_model": lambda in_channels=3, num_classes=2: CDNet34(in_channels, num_classes)}
 
 
 def register(name: str, ctor) -> None:

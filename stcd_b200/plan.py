@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .lowering import (AbsDiffSpec, AttentionSpec, BilinearUpSpec, ConvSpec, DWConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec,
+from .lowering import (AbsDiffSpec, AttentionSpec, ChannelGateSpec, SumSpec, BilinearUpSpec, ConvSpec, DWConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec,
                        LayerNormSpec, MaxPoolS2DSpec, Program, SegHeadSpec)
 
 
@@ -63,7 +63,20 @@ class Plan:
                 _lib.check_id(lib.stcd_plan_add_graph_conv(h, ids[op.src], ids[op.dst], op.c, op.k, op.dilation, op.r, _fptr(rp)),
                               f"graph conv {op.name}")
             elif isinstance(op, AbsDiffSpec):
-                _lib.check_id(lib.stcd_plan_add_absdiff(h, ids[op.src], ids[op.dst]), f"abs-diff {op.name}")
+                if op.signed:
+                    r = lib.stcd_plan_add_subdiff(h, ids[op.src], -1 if op.add is None else ids[op.add], ids[op.dst])
+                else:
+                    r = lib.stcd_plan_add_absdiff(h, ids[op.src], ids[op.dst])
+                _lib.check_id(r, f"diff {op.name}")
+            elif isinstance(op, ChannelGateSpec):
+                w1, w2 = np.ascontiguousarray(op.w1, np.float32), np.ascontiguousarray(op.w2, np.float32)
+                ws = None if op.ws is None else np.ascontiguousarray(op.ws, np.float32)
+                _lib.check_id(lib.stcd_plan_add_channel_gate(h, ids[op.src], -1 if op.res is None else ids[op.res], ids[op.dst],
+                                                             -1 if op.dst_s2d is None else ids[op.dst_s2d], op.c, w1.shape[0],
+                                                             _fptr(w1), _fptr(w2), _fptr(ws), op.mode), f"channel gate {op.name}")
+            elif isinstance(op, SumSpec):
+                arr = (C.c_int * len(op.srcs))(*[ids[s_] for s_ in op.srcs])
+                _lib.check_id(lib.stcd_plan_add_sum(h, arr, len(op.srcs), ids[op.dst]), f"sum {op.name}")
             elif isinstance(op, LayerNormSpec):
                 g, b = np.ascontiguousarray(op.gamma, np.float32), np.ascontiguousarray(op.beta, np.float32)
                 _lib.check_id(lib.stcd_plan_add_layernorm(h, ids[op.src], ids[op.dst], -1 if op.dst_s2d is None else ids[op.dst_s2d],

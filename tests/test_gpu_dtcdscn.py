@@ -1,0 +1,101 @@
+"""DTCDSCN (CDNet34) on the GPU against the oracle, the emulator and the golden fixture generated from the
+unmodified reference (models/DTCDSCN.py): logits within 2e-2 absolute (bf16 path), change maps agreeing on
+>= 99.9 % of decided pixels."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import emulate, nets
+from stcd_b200 import dtcdscn, synth
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 2e-2
+
+
+def _net():
+    return synth.prepare_(dtcdscn.CDNet34(3, 2).eval(), "CDNet_model")
+
+
+def _agreement(y, ref):
+    margin = (ref[:, 1] - ref[:, 0]).abs()
+    agree = (y[:, 1] > y[:, 0]) == (ref[:, 1] > ref[:, 0])
+    return agree.float().mean().item(), agree[margin > BF16_TOL].float().mean().item()
+
+
+def test_forward_matches_oracle_and_emulator():
+    net = _net()
+    x1, x2 = synth.image_pairs(3, 64, 96)
+    with torch.no_grad():
+        ref = nets.dtcdscn_forward(net.state_dict(), x1, x2)
+    keep = {}
+    emu = emulate.run_program(net.lower(64, 96), x1[:2], x2[:2], chunk=2, keep=keep)[0]
+    net = net.cuda()
+    net.chunk_pairs = 2                      # 3 pairs -> one full chunk + a ragged one
+    y = net(x1.cuda(), x2.cuda())
+    assert isinstance(y, torch.Tensor) and y.shape == ref.shape and y.dtype == torch.float32
+    y = y.cpu()
+    assert (y[:2] - emu).abs().max().item() < 1.5e-2, "kernel vs emulator (same rounding points; bf16 flips cascade)"
+    assert (y - ref).abs().max().item() < BF16_TOL, "kernel vs fp32 oracle"
+    all_px, decided = _agreement(y, ref)
+    assert decided >= 0.999 and all_px >= 0.97
+    assert 0.02 < (ref[:, 1] > ref[:, 0]).float().mean().item() < 0.98
+
+
+def test_intermediate_tensors_match_emulator():
+    """Every plan tensor of the first chunk against the emulator's (same rounding points): localises a wrong op."""
+    net = _net()
+    x1, x2 = synth.image_pairs(2, 64, 64)
+    keep = {}
+    emulate.run_program(net.lower(64, 64), x1, x2, chunk=2, keep=keep)
+    net = net.cuda()
+    net.chunk_pairs = 2
+    net(x1.cuda(), x2.cuda())
+    plan = net.plan_for(x1.cuda())
+    bad = []
+    torch.cuda.synchronize()
+    for name in plan.prog.tensors:
+        got, want = plan.read_tensor(name), keep[name]
+        # same rounding points, different fp32 accumulation order: isolated bf16-ulp flips cascade; a wrong op is O(1) off
+        err = ((got - want).abs().mean() / (want.abs().mean() + 1e-3)).item()
+        if err > 0.02:
+            bad.append((name, err))
+    assert not bad, bad[:8]
+
+
+def test_forward_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "dtcdscn.npz"))
+    net = synth.prepare_(dtcdscn.CDNet34(3, 2).eval(), "CDNet_model", seed=int(g["weight_seed"])).cuda()
+    x1, x2 = synth.image_pairs(int(g["batch"]), int(g["h"]), int(g["w"]), seed=int(g["data_seed"]))
+    y = net(x1.cuda(), x2.cuda()).cpu()
+    ref = torch.from_numpy(g["out0"])
+    assert (y - ref).abs().max().item() < BF16_TOL
+    assert _agreement(y, ref)[1] >= 0.999
+
+
+def test_256_shape_and_properties():
+    """256x256 (the reference's default img_size) at a batch the oracle finishes in seconds, plus determinism,
+    batch-order equivariance and host-buffer path == device path."""
+    net = _net()
+    x1, x2 = synth.image_pairs(5, 256, 256)
+    with torch.no_grad():
+        ref = nets.dtcdscn_forward(net.state_dict(), x1[:1], x2[:1])
+    net = net.cuda()
+    net.chunk_pairs = 4
+    y = net(x1.cuda(), x2.cuda())
+    assert (y[:1].cpu() - ref).abs().max().item() < BF16_TOL
+    assert torch.equal(y, net(x1.cuda(), x2.cuda())), "forward must be deterministic"
+    perm = torch.tensor([3, 1, 4, 0, 2])
+    yp = net(x1[perm].cuda(), x2[perm].cuda())
+    assert torch.equal(yp, y[perm.cuda()]), "pairs are independent: permuting the batch permutes the logits"
+    plan = net.plan_for(x1.cuda())
+    outs = plan.forward_host(x1.pin_memory(), x2.pin_memory())
+    assert torch.equal(outs[0], y.cpu()), "host-buffer path must equal the device path bit for bit"
+
+
+def test_define_G_returns_dtcdscn():
+    from types import SimpleNamespace
+    from stcd_b200 import networks
+    net = networks.define_G(SimpleNamespace(net_G="DTCDSCN", n_class=2), gpu_ids=[0])
+    assert isinstance(net, dtcdscn.CDNet_model) and next(net.parameters()).is_cuda

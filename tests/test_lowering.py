@@ -120,6 +120,37 @@ def test_segcd_resnet50_program_matches_oracle():
     assert abs(2 * net.lower(1024, 1024).macs_per_pair() / 1e9 - 680.79) < 0.5
 
 
+def test_dtcdscn_program_matches_oracle():
+    """DTCDSCN (CDNet34): SE gates (two-pass), signed feature differences fused with the decoder addends, dilated centre block
+    with statically dropped out-of-range taps, SCSE decoder, ConvTranspose2d phases -- checked through the emulator."""
+    from stcd_b200 import dtcdscn
+    net = synth.prepare_(dtcdscn.CDNet34(3, 2).eval(), "CDNet_model")
+    x1, x2 = synth.image_pairs(3, 64, 96)
+    with torch.no_grad():
+        y = nets.dtcdscn_forward(net.state_dict(), x1, x2)
+    prog = net.lower(64, 96)
+    ye = emulate.run_program(prog, x1, x2, chunk=2)[0]
+    assert ye.shape == y.shape == (3, 2, 64, 96) and (ye - y).abs().max().item() < BF16_TOL
+    margin = (y[:, 1] - y[:, 0]).abs()
+    agree = (ye[:, 1] > ye[:, 0]) == (y[:, 1] > y[:, 0])
+    assert agree[margin > BF16_TOL].float().mean().item() >= 0.999
+    assert 0.02 < (y[:, 1] > y[:, 0]).float().mean().item() < 0.98, "degenerate change map"
+    convs = [o for o in prog.ops if isinstance(o, L.ConvSpec)]
+    gates = [o for o in prog.ops if isinstance(o, L.ChannelGateSpec)]
+    # stem + 16 blocks x 2 + 3 downsamples + 4 dilated + 4 decoder blocks x 3 + 3 head convs
+    assert len(convs) == 1 + 32 + 3 + 4 + 12 + 3 and len(gates) == 16 + 4
+    # e4 is 2x3 here: dilations 2, 4, 8 reach past it on one or both axes, only in-range taps stay
+    dil = [o for o in convs if o.name.startswith("dblock_master")]
+    assert [len(o.taps) // len(o.chunks) for o in dil] == [9, 3, 1, 1]
+    big = net.lower(1024, 1024)
+    dil = [o for o in big.ops if isinstance(o, L.ConvSpec) and o.name.startswith("dblock_master")]
+    assert [o.kc for o in dil] == [64, 64, 32, 16] and [max(o.src_ey) for o in dil] == [2, 4, 8, 16]
+    # the single-image branch is held as parameters only, like upstream (its forward is commented out, DTCDSCN.py:256-292)
+    assert "decoder4.conv1.weight" in net.state_dict() and not any(o.name.startswith("decoder4.") for o in prog.ops)
+    with pytest.raises(ValueError):
+        net.lower(100, 96)
+
+
 def test_changegnn_program_matches_oracle():
     """Config C4's net: ViG Grapher blocks (graph op + grouped conv folded into a dense virtual-concat conv), GELU /
     PReLU-before-BN epilogues, bilinear resizes, ConvTranspose2d(k4, s2) phases -- checked through the emulator."""

@@ -38,6 +38,8 @@ def _oracle_forward(case, sd, x1, x2):
         return nets.changegnn_forward(sd, x1, x2)
     if cls == "ChangeFormerV6":
         return nets.changeformer_forward(sd, x1, x2)
+    if cls == "CDNet_model":
+        return [nets.dtcdscn_forward(sd, x1, x2)]
     raise KeyError(cls)
 
 
