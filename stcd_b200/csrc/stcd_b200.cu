@@ -343,8 +343,10 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
       const Tensor& ts = plan->tensors[k.src];
       const Tensor& td = plan->tensors[k.dst];
       const int B = ts.mult * plan->chunk, hw = ts.h * ts.w;
-      stcd::chan_sum_kernel<<<dim3(k.ranges, k.c / 8, B), 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, k.partial, k.c, ts.c / 8, hw, k.ranges);
-      const int ppb = 1024;
+      const int n_items = B * (k.c / 8) * k.ranges;   // one warp each
+      stcd::chan_sum_kernel<<<(n_items + 7) / 8, 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, k.partial, k.c, ts.c / 8, hw, k.ranges, n_items);
+      // ~2048 (pixel, channel group) items per CTA: enough CTAs to fill the machine on every level of the pyramid
+      const int ppb = std::max(32, std::min(stcd::kGateMaxPix, 2048 / (k.c / 8)));
       const float* w1 = k.w_dev;
       const float* w2 = w1 + (size_t)k.hid * k.c;
       const float* ws = k.mode == 1 ? w2 + (size_t)k.c * k.hid : nullptr;
@@ -799,7 +801,7 @@ int stcd_plan_add_channel_gate(stcd_plan* plan, int src_tensor, int res, int dst
   k.c = c;
   k.hid = hid;
   k.mode = mode;
-  k.ranges = std::max(1, std::min(16, ts.h * ts.w / 4096));
+  k.ranges = std::max(1, std::min(16, ts.h * ts.w / stcd::kGateRangePix));
   k.w.assign(w1, w1 + (size_t)hid * c);
   k.w.insert(k.w.end(), w2, w2 + (size_t)c * hid);
   if (mode == 1) k.w.insert(k.w.end(), ws, ws + c);

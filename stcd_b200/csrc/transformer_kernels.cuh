@@ -234,101 +234,106 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const __nv_bfloat16* __r
 constexpr int kGateMaxC = 512;
 constexpr int kGateMaxH = 32;
 
+// one warp per (pixel range, 8-channel group, image): lanes stride over the range's pixels, butterfly reduce (fixed order)
+constexpr int kGateRangePix = 512;
 __global__ void __launch_bounds__(256) chan_sum_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ partial, int C,
-                                                       int src_c8, int hw, int ranges) {
-  const int r = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+                                                       int src_c8, int hw, int ranges, int n_items) {
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (item >= n_items) return;
+  const int g8 = C >> 3;
+  const int r = item % ranges, g = (item / ranges) % g8, b = item / (ranges * g8);
   const int per = (hw + ranges - 1) / ranges;
   const int p0 = r * per, p1 = min(hw, p0 + per);
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const __nv_bfloat16* base = src + (static_cast<size_t>(b) * src_c8 + g) * static_cast<size_t>(hw) * 8;
-  for (int px = p0 + threadIdx.x; px < p1; px += blockDim.x) {
+#pragma unroll 4
+  for (int px = p0 + lane; px < p1; px += 32) {
     float v[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(px) * 8)), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] += v[j];
   }
-  __shared__ float sh[8][8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float a = s[j];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) sh[warp][j] = a;
+    for (int o = 16; o > 0; o >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
   }
-  __syncthreads();
-  if (threadIdx.x < 8) {
-    float a = 0.f;
-    for (int w = 0; w < 8; ++w) a += sh[w][threadIdx.x];
-    partial[(static_cast<size_t>(b) * ranges + r) * C + g * 8 + threadIdx.x] = a;
+  if (lane < 8) {
+    float a = s[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) a = lane == j ? s[j] : a;
+    partial[(static_cast<size_t>(b) * ranges + r) * C + g * 8 + lane] = a;
   }
 }
 
-// grid (pixel blocks, B), 256 threads
+// grid (pixel blocks, B), 256 threads.  Every CTA redoes the two tiny FC layers of its image (C x hid MACs, warp-cooperative),
+// then applies its pixels: work items are (channel group, pixel) so small maps with many channels still fill the CTA.
+constexpr int kGateMaxPix = 1024;
 __global__ void __launch_bounds__(256) gate_apply_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ res,
                                                          __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst2,
                                                          const float* __restrict__ partial, const float* __restrict__ w1,
                                                          const float* __restrict__ w2, const float* __restrict__ ws, int C, int hid,
                                                          int src_c8, int res_c8, int dst_c8, int dst2_c8, int h, int w, int ranges,
                                                          int mode, int pix_per_block) {
-  __shared__ float s_mean[kGateMaxC], s_gate[kGateMaxC], s_hid[kGateMaxH], s_ws[kGateMaxC];
+  __shared__ float s_mean[kGateMaxC], s_gate[kGateMaxC], s_hid[kGateMaxH], s_gs[kGateMaxPix];
   const int b = blockIdx.y, hw = h * w, g8 = C >> 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f;
     for (int r = 0; r < ranges; ++r) a += partial[(static_cast<size_t>(b) * ranges + r) * C + c];
     s_mean[c] = a / static_cast<float>(hw);
-    if (mode == 1) s_ws[c] = ws[c];
   }
   __syncthreads();
-  if (threadIdx.x < hid) {
+  for (int u = warp; u < hid; u += 8) {                 // lanes stride over c: coalesced w1 rows, fixed-order butterfly
     float a = 0.f;
-    for (int c = 0; c < C; ++c) a = fmaf(w1[threadIdx.x * C + c], s_mean[c], a);
-    s_hid[threadIdx.x] = fmaxf(a, 0.f);
+    for (int c = lane; c < C; c += 32) a = fmaf(__ldg(w1 + u * C + c), s_mean[c], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) s_hid[u] = fmaxf(a, 0.f);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f;
-    for (int u = 0; u < hid; ++u) a = fmaf(w2[c * hid + u], s_hid[u], a);
+    for (int u = 0; u < hid; ++u) a = fmaf(__ldg(w2 + c * hid + u), s_hid[u], a);
     s_gate[c] = 1.f / (1.f + expf(-a));
   }
-  __syncthreads();
-  const int p_end = min(hw, (static_cast<int>(blockIdx.x) + 1) * pix_per_block);
-  for (int pix = blockIdx.x * pix_per_block + threadIdx.x; pix < p_end; pix += blockDim.x) {
-    const __nv_bfloat16* s = src + (static_cast<size_t>(b) * src_c8 * hw + pix) * 8;
-    float gs = 0.f;
-    if (mode == 1) {
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int n_pix = min(hw, p_begin + pix_per_block) - p_begin;
+  const __nv_bfloat16* sb = src + static_cast<size_t>(b) * src_c8 * hw * 8;
+  if (mode == 1) {                                       // spatial gate per pixel: sigmoid(ws . x_pixel)
+    for (int i = threadIdx.x; i < n_pix; i += blockDim.x) {
       float a = 0.f;
       for (int g = 0; g < g8; ++g) {
         float v[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(s + static_cast<size_t>(g) * hw * 8)), v);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(sb + (static_cast<size_t>(g) * hw + p_begin + i) * 8)), v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a = fmaf(v[j], s_ws[g * 8 + j], a);
+        for (int j = 0; j < 8; ++j) a = fmaf(v[j], __ldg(ws + g * 8 + j), a);
       }
-      gs = 1.f / (1.f + expf(-a));
+      s_gs[i] = 1.f / (1.f + expf(-a));
     }
-    __nv_bfloat16* o = dst + (static_cast<size_t>(b) * dst_c8 * hw + pix) * 8;
-    __nv_bfloat16* o2 = nullptr;
-    size_t hw2 = 0;
+  }
+  __syncthreads();
+  const int hw2 = hw >> 2, w2h = w >> 1;
+  for (int it = threadIdx.x; it < n_pix * g8; it += blockDim.x) {
+    const int g = it / n_pix, i = it - g * n_pix, pix = p_begin + i;
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(sb + (static_cast<size_t>(g) * hw + pix) * 8)), v);
+    if (mode == 0) {
+      float rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (res != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(res + ((static_cast<size_t>(b) * res_c8 + g) * hw + pix) * 8)), rv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], s_gate[g * 8 + j], rv[j]), 0.f);
+    } else {
+      const float gs = s_gs[i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] * (1.f + s_gate[g * 8 + j] + gs);
+    }
+    const uint4 q = pack8(v);
+    *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(b) * dst_c8 + g) * hw + pix) * 8) = q;
     if (dst2 != nullptr) {
       const int y = pix / w, x = pix - y * w;
-      hw2 = static_cast<size_t>(hw >> 2);
-      o2 = dst2 + ((static_cast<size_t>(b) * dst2_c8 + static_cast<size_t>(((y & 1) * 2 + (x & 1)) * g8)) * hw2 + static_cast<size_t>(y >> 1) * (w >> 1) + (x >> 1)) * 8;
-    }
-    for (int g = 0; g < g8; ++g) {
-      float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(s + static_cast<size_t>(g) * hw * 8)), v);
-      if (mode == 0) {
-        float rv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (res != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(res + ((static_cast<size_t>(b) * res_c8 + g) * hw + pix) * 8)), rv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], s_gate[g * 8 + j], rv[j]), 0.f);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = v[j] * (1.f + s_gate[g * 8 + j] + gs);
-      }
-      const uint4 q = pack8(v);
-      *reinterpret_cast<uint4*>(o + static_cast<size_t>(g) * hw * 8) = q;
-      if (o2 != nullptr) *reinterpret_cast<uint4*>(o2 + static_cast<size_t>(g) * hw2 * 8) = q;
+      *reinterpret_cast<uint4*>(dst2 + ((static_cast<size_t>(b) * dst2_c8 + ((y & 1) * 2 + (x & 1)) * g8 + g) * hw2 +
+                                        static_cast<size_t>(y >> 1) * w2h + (x >> 1)) * 8) = q;
     }
   }
 }

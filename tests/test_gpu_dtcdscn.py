@@ -59,7 +59,8 @@ def test_intermediate_tensors_match_emulator():
         got, want = plan.read_tensor(name), keep[name]
         # same rounding points, different fp32 accumulation order: isolated bf16-ulp flips cascade; a wrong op is O(1) off
         err = ((got - want).abs().mean() / (want.abs().mean() + 1e-3)).item()
-        if err > 0.02:
+        # differences of two correlated streams carry the operands' rounding noise at a fraction of their magnitude
+        if err > (0.08 if name.endswith((".diff", ".d")) else 0.02):
             bad.append((name, err))
     assert not bad, bad[:8]
 
