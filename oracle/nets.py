@@ -416,3 +416,82 @@ def dtcdscn_forward(sd: SD, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     out = F.relu(F.conv_transpose2d(d1, sd["finaldeconv1_master.weight"], sd["finaldeconv1_master.bias"], stride=2, padding=1))
     out = F.relu(F.conv2d(out, sd["finalconv2_master.weight"], sd["finalconv2_master.bias"], padding=1))
     return F.conv2d(out, sd["finalconv3_master.weight"], sd["finalconv3_master.bias"], padding=1)
+
+
+# ------------------------------------------------------------------------------------------
+# BIT (models/networks.py: ResNet :223-305, BASE_Transformer :308-441; blocks in models/help_funcs.py)
+def _bit_backbone(sd: SD, x: torch.Tensor, stages: int) -> torch.Tensor:
+    """ResNet.forward_single, models/networks.py:277-305.  The backbone is models/resnet.py's resnet18 with
+    replace_stride_with_dilation=[False, True, True]: layer3 / layer4 keep stride 1, and BasicBlock silently resets the
+    requested dilation to 1 (models/resnet.py:47-49), so they are plain stride-1 3x3 blocks."""
+    x = F.relu(_bn(sd, "resnet.bn1", F.conv2d(x, sd["resnet.conv1.weight"], None, stride=2, padding=3)))
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    for li in range(min(stages, 5) - 1):
+        for b in range(2):
+            x = _basic_block(sd, f"resnet.layer{li + 1}.{b}", x, 2 if (li == 1 and b == 0) else 1)
+    x = F.interpolate(x, scale_factor=2, mode="nearest")               # self.upsamplex2 (if_upsample_2x=True)
+    return F.conv2d(x, sd["conv_pred.weight"], sd["conv_pred.bias"], padding=1)
+
+
+def _bit_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float, softmax: bool = True) -> torch.Tensor:
+    """help_funcs.py Attention / Cross_Attention core (:87-110, :122-146): q [b, n, inner], k / v [b, m, inner]."""
+    b, n, inner = q.shape
+    d = inner // heads
+    qh, kh, vh = (t.reshape(b, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    dots = torch.einsum("bhid,bhjd->bhij", qh, kh) * scale
+    attn = dots.softmax(dim=-1) if softmax else dots
+    return torch.einsum("bhij,bhjd->bhid", attn, vh).transpose(1, 2).reshape(b, n, inner)
+
+
+def _bit_ff(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """Residual(PreNorm(FeedForward)), help_funcs.py:21-26,37-43,56-68."""
+    y = F.layer_norm(x, (x.shape[-1],), sd[f"{pre}.fn.norm.weight"], sd[f"{pre}.fn.norm.bias"])
+    y = F.gelu(F.linear(y, sd[f"{pre}.fn.fn.net.0.weight"], sd[f"{pre}.fn.fn.net.0.bias"]))
+    return F.linear(y, sd[f"{pre}.fn.fn.net.3.weight"], sd[f"{pre}.fn.fn.net.3.bias"]) + x
+
+
+def bit_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor, stages: int = 4, heads: int = 8, decoder_softmax: bool = True) -> torch.Tensor:
+    """BASE_Transformer.forward, models/networks.py:405-441 (tokenizer=True, token_trans=True, with_pos='learned',
+    with_decoder=True, with_decoder_pos=None: the registry's three BIT keys, :174-182); without the transformer
+    parameters in `sd` it is ResNet.forward (:263-275, key 'base_resnet18').  Returns the logits (the reference wraps
+    them in a one-element list for BASE_Transformer)."""
+    f1, f2 = _bit_backbone(sd, x1, stages), _bit_backbone(sd, x2, stages)
+    if "conv_a.weight" in sd:
+        b, c, h, w = f1.shape
+        dim = c
+
+        def tokens(f):                                               # _forward_semantic_tokens, :359-367
+            a = F.conv2d(f, sd["conv_a.weight"]).reshape(b, -1, h * w).softmax(dim=-1)
+            return torch.einsum("bln,bcn->blc", a, f.reshape(b, c, h * w))
+
+        t = torch.cat([tokens(f1), tokens(f2)], dim=1) + sd["pos_embedding"]          # :419-420, 380-384
+        n_enc = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.layers."))
+        for l in range(n_enc):                                       # Transformer.forward, help_funcs.py:159-163
+            pre = f"transformer.layers.{l}"
+            y = F.layer_norm(t, (dim,), sd[f"{pre}.0.fn.norm.weight"], sd[f"{pre}.0.fn.norm.bias"])
+            q, k, v = F.linear(y, sd[f"{pre}.0.fn.fn.to_qkv.weight"]).chunk(3, dim=-1)
+            o = _bit_attention(q, k, v, heads, dim ** -0.5)
+            t = F.linear(o, sd[f"{pre}.0.fn.fn.to_out.0.weight"], sd[f"{pre}.0.fn.fn.to_out.0.bias"]) + t
+            t = _bit_ff(sd, f"{pre}.1", t)
+        t1, t2 = t.chunk(2, dim=1)
+        n_dec = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer_decoder.layers."))
+
+        def decode(f, m):                                            # _forward_transformer_decoder, :386-394
+            x = f.reshape(b, c, h * w).transpose(1, 2)
+            for l in range(n_dec):                                   # TransformerDecoder.forward, help_funcs.py:177-182
+                pre = f"transformer_decoder.layers.{l}"
+                nw, nb = sd[f"{pre}.0.fn.norm.weight"], sd[f"{pre}.0.fn.norm.bias"]
+                xn, mn = F.layer_norm(x, (dim,), nw, nb), F.layer_norm(m, (dim,), nw, nb)        # PreNorm2: one norm for both
+                q = F.linear(xn, sd[f"{pre}.0.fn.fn.to_q.weight"])
+                k = F.linear(mn, sd[f"{pre}.0.fn.fn.to_k.weight"])
+                v = F.linear(mn, sd[f"{pre}.0.fn.fn.to_v.weight"])
+                o = _bit_attention(q, k, v, heads, dim ** -0.5, decoder_softmax)
+                x = F.linear(o, sd[f"{pre}.0.fn.fn.to_out.0.weight"], sd[f"{pre}.0.fn.fn.to_out.0.bias"]) + x
+                x = _bit_ff(sd, f"{pre}.1", x)
+            return x.transpose(1, 2).reshape(b, c, h, w)
+
+        f1, f2 = decode(f1, t1), decode(f2, t2)
+    x = torch.abs(f1 - f2)
+    x = F.interpolate(x, scale_factor=4, mode="bilinear")           # self.upsamplex4 (align_corners unset -> False)
+    x = F.relu(_bn(sd, "classifier.1", F.conv2d(x, sd["classifier.0.weight"], None, padding=1)))
+    return F.conv2d(x, sd["classifier.3.weight"], sd["classifier.3.bias"], padding=1)

@@ -133,6 +133,18 @@ def ref_module(path: str):
     return importlib.import_module(path)
 
 
+def disable_pretrained_download() -> None:
+    """BIT builds its backbone with ``models.resnet18(pretrained=True, ...)`` (models/networks.py:234-235): a checkpoint
+    download.  There is no network here and the harness re-draws every weight anyway (stcd_b200/synth.py), so the one
+    line that fetches and loads the checkpoint is skipped; the module tree, names and forward are untouched."""
+    r = ref_module("models.resnet")
+    if getattr(r, "_stcd_patched", False):
+        return
+    orig = r._resnet
+    r._resnet = lambda arch, block, layers, pretrained, progress, **kw: orig(arch, block, layers, False, progress, **kw)
+    r._stcd_patched = True
+
+
 def segmentation_metric_class():
     """exec the source span of SegmentationMetric (train_stcd.py:515-593) without running the script."""
     import torch
