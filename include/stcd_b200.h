@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 12
+#define STCD_ABI_VERSION 13
 
 enum stcd_status {
   STCD_OK = 0,
@@ -195,6 +195,25 @@ int stcd_plan_add_subdiff(stcd_plan* plan, int src_tensor, int add_or_neg, int d
  * dst_s2d_or_neg >= 0 also writes the space-to-depth copy.  c <= 512, hid <= 32. */
 int stcd_plan_add_channel_gate(stcd_plan* plan, int src_tensor, int res_or_neg, int dst_tensor, int dst_s2d_or_neg, int c, int hid,
                                const float* w1, const float* w2, const float* ws_or_null, int mode);
+
+/* BIT's token path on a 32-channel plan tensor holding both streams (models/networks.py:359-394,414-428; blocks in
+ * models/help_funcs.py): semantic tokens -> + learned positions -> transformer encoder over the pair's 2L tokens -> transformer
+ * decoder (every pixel queries its image's L tokens).  c = 32, token_len = 4, heads = 8, mlp = 64 (the registered BIT keys).
+ * enc / dec: HOST fp32, one packed row per layer:
+ *   enc row: ln1_g[c] ln1_b[c] Wqkv[3*inner_enc][c] Wout[c][inner_enc] bout[c] ln2_g[c] ln2_b[c] W1[mlp][c] b1[mlp] W2[c][mlp] b2[c]
+ *   dec row: ln1_g[c] ln1_b[c] Wq[inner_dec][c] Wk[..][c] Wv[..][c] Wout[c][inner_dec] bout[c] ln2_g[c] ln2_b[c]
+ *            W1^T[c][mlp] b1[mlp] W2^T[mlp][c] b2[c]
+ * (torch Linear layouts [out][in]; the decoder's feed-forward weights transposed). */
+typedef struct {
+  int32_t c, token_len, heads, mlp;
+  int32_t n_enc, n_dec, inner_enc, inner_dec;
+  int32_t softmax;                 /* Cross_Attention(softmax=...) of the decoder, help_funcs.py:101-104 */
+  const float* conv_a;             /* [token_len][c]      conv_a.weight, networks.py:324 */
+  const float* pos;                /* [2*token_len][c]    pos_embedding, :337 */
+  const float* enc;
+  const float* dec;
+} stcd_bit_desc;
+int stcd_plan_add_bit_transformer(stcd_plan* plan, int src_tensor, int dst_tensor, const stcd_bit_desc* desc);
 
 /* dst = sum of n <= 5 plan tensors of identical shape (Dblock.forward: x + d1 + d2 + d3 + d4, models/DTCDSCN.py:65-71) */
 int stcd_plan_add_sum(stcd_plan* plan, const int* src_tensors, int n, int dst_tensor);

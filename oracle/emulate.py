@@ -274,6 +274,9 @@ def run_aux(op, T, chunk, ext, nv):
             d = (T[op.add][..., : op.c] + T[op.src][:chunk, :, :, : op.c]) - T[op.src][chunk: 2 * chunk, :, :, : op.c]
         T[op.dst][..., : op.c] = _bf16(d if op.signed else d.abs())
         return None
+    if isinstance(op, L.BitTransformerSpec):
+        run_bit_transformer(op, T, chunk)
+        return None
     if isinstance(op, L.SumSpec):
         T[op.dst][...] = _bf16(sum(T[s_] for s_ in op.srcs))
         return None
@@ -311,3 +314,41 @@ def run_aux(op, T, chunk, ext, nv):
     if isinstance(op, L.SegHeadSpec):
         return run_seg_head(op, T, chunk, ext, nv)
     raise TypeError(f"emulator: unknown op {op!r}")
+
+
+def run_bit_transformer(op: L.BitTransformerSpec, T: Dict[str, torch.Tensor], chunk: int) -> None:
+    """models/networks.py:359-394,414-428 on the bf16 feature map, fp32 arithmetic, one rounding at the output."""
+    import torch.nn.functional as F
+    x = T[op.src][..., : op.c]                                   # [2*chunk, h, w, c]
+    n2, h, w, c = x.shape
+    xf = x.reshape(n2, h * w, c)
+    a = torch.softmax(xf @ torch.from_numpy(op.conv_a).T, dim=1)  # softmax over pixels, [2*chunk, hw, L]
+    tok = torch.einsum("bnl,bnc->blc", a, xf)                    # [2*chunk, L, c]
+    t = torch.cat([tok[:chunk], tok[chunk:]], dim=1) + torch.from_numpy(op.pos)[None]      # [chunk, 2L, c]
+    scale = c ** -0.5
+
+    def attend(q, k, v, softmax=True):
+        b, n, inner = q.shape
+        d = inner // op.heads
+        qh, kh, vh = (z.reshape(b, -1, op.heads, d).transpose(1, 2) for z in (q, k, v))
+        dots = torch.einsum("bhid,bhjd->bhij", qh, kh) * scale
+        at = dots.softmax(-1) if softmax else dots
+        return torch.einsum("bhij,bhjd->bhid", at, vh).transpose(1, 2).reshape(b, n, inner)
+
+    for row in op.enc:
+        P = L.bit_unpack(L.bit_enc_fields(c, op.inner_enc, op.mlp), row)
+        y = F.layer_norm(t, (c,), P["ln1_g"], P["ln1_b"])
+        q, k, v = (y @ P["wqkv"].T).chunk(3, dim=-1)
+        t = attend(q, k, v) @ P["wout"].T + P["bout"] + t
+        y = F.layer_norm(t, (c,), P["ln2_g"], P["ln2_b"])
+        t = F.gelu(y @ P["w1"].T + P["b1"]) @ P["w2"].T + P["b2"] + t
+    m = torch.cat([t[:, : op.token_len], t[:, op.token_len:]], dim=0)                     # [2*chunk, L, c]: per image
+    z = xf
+    for row in op.dec:
+        P = L.bit_unpack(L.bit_dec_fields(c, op.inner_dec, op.mlp), row)
+        zn, mn = F.layer_norm(z, (c,), P["ln1_g"], P["ln1_b"]), F.layer_norm(m, (c,), P["ln1_g"], P["ln1_b"])
+        o = attend(zn @ P["wq"].T, mn @ P["wk"].T, mn @ P["wv"].T, op.softmax)
+        z = o @ P["wout"].T + P["bout"] + z
+        y = F.layer_norm(z, (c,), P["ln2_g"], P["ln2_b"])
+        z = F.gelu(y @ P["w1t"] + P["b1"]) @ P["w2t"] + P["b2"] + z
+    T[op.dst][..., : c] = _bf16(z.reshape(n2, h, w, c))

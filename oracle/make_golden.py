@@ -37,11 +37,18 @@ CASES = {
     "changeformer_v6": ("models.ChangeFormer", "ChangeFormerV6", (3, 2, False, 256), 1, 256, 256),
     # CDNet34 = CDNet_model(in_channels, SEBasicBlock, [3, 4, 6, 3], num_classes) (models/DTCDSCN.py:316-320): the defaults
     "dtcdscn": ("models.DTCDSCN", "CDNet_model", (3,), 2, 64, 96),
+    # BIT: BASE_Transformer(input_nc, output_nc, with_pos, resnet_stages_num, token_len, token_trans, enc_depth, dec_depth) =
+    # registry key base_transformer_pos_s4_dd8 (models/networks.py:177-179); ResNet(3, 2) = base_resnet18 (:170-171).
+    # The backbone's checkpoint download is skipped (refimport.disable_pretrained_download); weights are the harness' draw.
+    "bit_dd8": ("models.networks", "BASE_Transformer", (3, 2, "learned", 4, 4, True, 1, 8), 2, 64, 96),
+    "bit_resnet18": ("models.networks", "ResNet", (3, 2), 2, 64, 96),
 }
 
 
 def reference_net(case: str):
     mod, cls, args, *_ = CASES[case]
+    if mod == "models.networks":
+        refimport.disable_pretrained_download()
     net = getattr(refimport.ref_module(mod), cls)(*args).eval()
     return synth.prepare_(net, cls)
 

@@ -115,6 +115,14 @@ class SegHeadDesc(C.Structure):
                 ("out_ext", C.c_int32), ("diff_src", C.c_int32)]
 
 
+class BitDesc(C.Structure):
+    _fields_ = [("c", C.c_int32), ("token_len", C.c_int32), ("heads", C.c_int32), ("mlp", C.c_int32),
+                ("n_enc", C.c_int32), ("n_dec", C.c_int32), ("inner_enc", C.c_int32), ("inner_dec", C.c_int32),
+                ("softmax", C.c_int32),
+                ("conv_a", C.POINTER(C.c_float)), ("pos", C.POINTER(C.c_float)), ("enc", C.POINTER(C.c_float)),
+                ("dec", C.POINTER(C.c_float))]
+
+
 class EcamDesc(C.Structure):
     _fields_ = [
         ("src", C.c_int32 * 4),
@@ -126,7 +134,7 @@ class EcamDesc(C.Structure):
     ]
 
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -146,6 +154,7 @@ SYMBOLS = [
     ("stcd_plan_add_subdiff", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("stcd_plan_add_channel_gate", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                              C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]),
+    ("stcd_plan_add_bit_transformer", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("stcd_plan_add_sum", C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int]),
     ("stcd_plan_add_graph_conv", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     ("stcd_plan_add_layernorm", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),

@@ -21,6 +21,7 @@
 #include "conv_ws.cuh"
 #include "graph_kernels.cuh"
 #include "transformer_kernels.cuh"
+#include "bit_kernels.cuh"
 
 namespace {
 
@@ -142,6 +143,16 @@ struct GateOp {
   float* partial = nullptr;  // [imgs][ranges][c]
 };
 
+struct BitOp {
+  int src, dst;
+  stcd_bit_desc d;
+  std::vector<float> w;        // conv_a | pos | enc | dec
+  float* w_dev = nullptr;
+  float* tokens = nullptr;     // [2*chunk][L][c]
+  float* coef = nullptr;       // [2*chunk][n_dec][A | Bm]
+  size_t mixer_smem = 0;
+};
+
 struct SumOp {
   int src[5], n, dst;
 };
@@ -164,7 +175,7 @@ struct EcamOp {
 };
 
 struct Op {
-  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head, 5 graph conv, 6 bilinear up, 7 layer norm, 8 attention, 9 dw conv, 10 T1 - T2 (abs or signed), 11 channel gate, 12 sum
+  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head, 5 graph conv, 6 bilinear up, 7 layer norm, 8 attention, 9 dw conv, 10 T1 - T2 (abs or signed), 11 channel gate, 12 sum, 13 BIT token path
   int idx;
 };
 
@@ -188,6 +199,7 @@ struct stcd_plan {
   std::vector<AbsDiffOp> absdiffs;
   std::vector<GateOp> gates;
   std::vector<SumOp> sums;
+  std::vector<BitOp> bits;
   std::vector<Op> ops;
   uint8_t* workspace = nullptr;
   size_t workspace_bytes = 0;
@@ -356,6 +368,21 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
           k.res >= 0 ? plan->tensors[k.res].c / 8 : 0, td.c / 8, k.dst2 >= 0 ? plan->tensors[k.dst2].c / 8 : 0, ts.h, ts.w, k.ranges, k.mode,
           ppb);
       CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 13) {
+      const BitOp& k = plan->bits[o.idx];
+      const Tensor& ts = plan->tensors[k.src];
+      const Tensor& td = plan->tensors[k.dst];
+      const int imgs = 2 * plan->chunk, hw = ts.h * ts.w;
+      const float* conv_a = k.w_dev;
+      const float* pos = conv_a + stcd::kBitL * stcd::kBitC;
+      const float* enc = pos + 2 * stcd::kBitL * stcd::kBitC;
+      const float* dec = enc + (size_t)k.d.n_enc * stcd::bit_enc_size(k.d.inner_enc);
+      stcd::bit_tokenizer_kernel<<<imgs, 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, conv_a, k.tokens, ts.c / 8, hw);
+      stcd::bit_token_mixer_kernel<<<plan->chunk, 256, k.mixer_smem, st>>>(k.tokens, pos, enc, dec, k.coef, plan->chunk, k.d.n_enc, k.d.n_dec,
+                                                                          k.d.inner_enc, k.d.inner_dec, 1.f / sqrtf((float)stcd::kBitC));
+      stcd::bit_decoder_kernel<<<dim3((hw + 255) / 256, imgs), 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, dec, k.coef,
+                                                                            ts.c / 8, td.c / 8, hw, k.d.n_dec, k.d.inner_dec, k.d.softmax);
+      CUDA_TRY(cudaGetLastError());
     } else if (o.kind == 12) {
       const SumOp& k = plan->sums[o.idx];
       const Tensor& td = plan->tensors[k.dst];
@@ -522,6 +549,11 @@ void stcd_plan_destroy(stcd_plan* plan) {
     if (e.w_dev) cudaFree(e.w_dev);
   for (LayerNormOp& k : plan->lns)
     if (k.gb_dev) cudaFree(k.gb_dev);
+  for (BitOp& k : plan->bits) {
+    if (k.w_dev) cudaFree(k.w_dev);
+    if (k.tokens) cudaFree(k.tokens);
+    if (k.coef) cudaFree(k.coef);
+  }
   for (GateOp& k : plan->gates) {
     if (k.w_dev) cudaFree(k.w_dev);
     if (k.partial) cudaFree(k.partial);
@@ -807,6 +839,36 @@ int stcd_plan_add_channel_gate(stcd_plan* plan, int src_tensor, int res, int dst
   if (mode == 1) k.w.insert(k.w.end(), ws, ws + c);
   plan->gates.push_back(std::move(k));
   plan->ops.push_back({11, (int)plan->gates.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_bit_transformer(stcd_plan* plan, int src_tensor, int dst_tensor, const stcd_bit_desc* d) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!d || !valid_tensor(plan, src_tensor) || !valid_tensor(plan, dst_tensor) || !d->conv_a || !d->pos || !d->enc || !d->dec)
+    return -fail(STCD_ERR_INVALID, "BIT transformer: bad tensor id / NULL descriptor or weights");
+  if (d->c != stcd::kBitC || d->token_len != stcd::kBitL || d->heads != stcd::kBitHeads || d->mlp != stcd::kBitMlp)
+    return -fail(STCD_ERR_INVALID, "BIT transformer: c=%d token_len=%d heads=%d mlp=%d; the kernels serve 32 / 4 / 8 / 64", d->c, d->token_len,
+                 d->heads, d->mlp);
+  if (d->n_enc < 0 || d->n_enc > 16 || d->n_dec < 1 || d->n_dec > 32 || d->inner_enc < 8 || d->inner_enc > 1024 || (d->inner_enc % 8) ||
+      d->inner_dec < 8 || d->inner_dec > 1024 || (d->inner_dec % 8))
+    return -fail(STCD_ERR_INVALID, "BIT transformer: depths %d/%d, inner dims %d/%d out of range", d->n_enc, d->n_dec, d->inner_enc, d->inner_dec);
+  const Tensor& ts = plan->tensors[src_tensor];
+  const Tensor& td = plan->tensors[dst_tensor];
+  if (ts.mult != 2 || td.mult != 2 || ts.c != stcd::kBitC || td.c != stcd::kBitC || ts.h != td.h || ts.w != td.w)
+    return -fail(STCD_ERR_INVALID, "BIT transformer: src and dst must be [2*chunk,h,w,32] (both streams)");
+  BitOp k;
+  k.src = src_tensor;
+  k.dst = dst_tensor;
+  k.d = *d;
+  k.w.assign(d->conv_a, d->conv_a + stcd::kBitL * stcd::kBitC);
+  k.w.insert(k.w.end(), d->pos, d->pos + 2 * stcd::kBitL * stcd::kBitC);
+  k.w.insert(k.w.end(), d->enc, d->enc + (size_t)d->n_enc * stcd::bit_enc_size(d->inner_enc));
+  k.w.insert(k.w.end(), d->dec, d->dec + (size_t)d->n_dec * stcd::bit_dec_size(d->inner_dec));
+  k.d.conv_a = k.d.pos = k.d.enc = k.d.dec = nullptr;
+  k.mixer_smem = sizeof(float) * (size_t)std::max(8 * 3 * d->inner_enc, 2 * 8 * d->inner_dec);
+  plan->bits.push_back(std::move(k));
+  plan->ops.push_back({13, (int)plan->bits.size() - 1});
   return (int)plan->ops.size() - 1;
 }
 
@@ -1335,6 +1397,13 @@ int stcd_plan_finalize(stcd_plan* plan) {
   }
   // the 3-stream head instances stage 58 KB: dynamic shared memory above the 48 KB default
   CUDA_TRY(cudaFuncSetAttribute(stcd::segcd_head_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  for (BitOp& k : plan->bits) {
+    CUDA_TRY(cudaMalloc(&k.w_dev, k.w.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(k.w_dev, k.w.data(), k.w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&k.tokens, (size_t)2 * plan->chunk * stcd::kBitL * stcd::kBitC * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&k.coef, (size_t)2 * plan->chunk * k.d.n_dec * stcd::kBitCoef * sizeof(float)));
+    CUDA_TRY(cudaFuncSetAttribute(stcd::bit_token_mixer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.mixer_smem));
+  }
   for (GateOp& k : plan->gates) {
     const Tensor& ts = plan->tensors[k.src];
     CUDA_TRY(cudaMalloc(&k.w_dev, k.w.size() * sizeof(float)));
@@ -1424,6 +1493,7 @@ int64_t stcd_plan_launches(const stcd_plan* plan, int n_pairs) {
   const int64_t chunks = (n_pairs + plan->chunk - 1) / plan->chunk;
   int64_t per_chunk = (int64_t)plan->ops.size() + (int64_t)plan->ecams.size();  // an ECAM head op is two kernels
   per_chunk += (int64_t)plan->gates.size();                                    // a channel gate is two kernels
+  per_chunk += 2 * (int64_t)plan->bits.size();                                 // tokenizer + mixer + decoder
   for (const GraphOp& g : plan->graphs) per_chunk += 3 + (g.r > 1 ? 2 : 0);     // unpack, [pool], norm, [norm y], kNN, max-relative
   return chunks * per_chunk;
 }

@@ -245,6 +245,62 @@ class ChannelGateSpec:
 
 
 @dataclass
+class BitTransformerSpec:
+    """BIT's token path on a 32-channel feature map (models/networks.py:359-394,405-428; blocks in models/help_funcs.py):
+    semantic tokens (softmax over pixels of a 1x1 conv, :359-367), + learned positions, transformer encoder over the 2L
+    tokens of the pair, transformer decoder where every pixel queries its image's L tokens; src and dst hold both streams.
+
+    enc / dec are flat fp32 arrays, one row per layer (``bit_pack_enc`` / ``bit_pack_dec`` give the layouts)."""
+    name: str
+    src: str
+    dst: str
+    c: int                       # 32
+    token_len: int               # 4
+    heads: int                   # 8
+    inner_enc: int               # heads * dim_head
+    inner_dec: int               # heads * decoder_dim_head
+    mlp: int                     # 64
+    conv_a: np.ndarray           # float32 [token_len, c]
+    pos: np.ndarray              # float32 [2 * token_len, c]
+    enc: np.ndarray              # float32 [n_enc, bit_enc_size]
+    dec: np.ndarray              # float32 [n_dec, bit_dec_size]
+    softmax: bool = True
+    macs_per_pair: int = 0
+
+
+def bit_enc_fields(c: int, inner: int, mlp: int):
+    """(name, shape) of one encoder layer's packed parameters, in order (torch layouts: Linear weight = [out, in])."""
+    return [("ln1_g", (c,)), ("ln1_b", (c,)), ("wqkv", (3 * inner, c)), ("wout", (c, inner)), ("bout", (c,)),
+            ("ln2_g", (c,)), ("ln2_b", (c,)), ("w1", (mlp, c)), ("b1", (mlp,)), ("w2", (c, mlp)), ("b2", (c,))]
+
+
+def bit_dec_fields(c: int, inner: int, mlp: int):
+    """One decoder layer; the feed-forward weights are stored TRANSPOSED ([in, out]) so the per-pixel kernel reads rows."""
+    return [("ln1_g", (c,)), ("ln1_b", (c,)), ("wq", (inner, c)), ("wk", (inner, c)), ("wv", (inner, c)), ("wout", (c, inner)),
+            ("bout", (c,)), ("ln2_g", (c,)), ("ln2_b", (c,)), ("w1t", (c, mlp)), ("b1", (mlp,)), ("w2t", (mlp, c)), ("b2", (c,))]
+
+
+def bit_pack(fields, values: Dict[str, torch.Tensor]) -> np.ndarray:
+    out = []
+    for name, shape in fields:
+        v = values[name].detach().to(torch.float32).reshape(-1).numpy()
+        if v.size != int(np.prod(shape)):
+            raise ValueError(f"BIT packing: {name} has {v.size} elements, layout wants {shape}")
+        out.append(v)
+    return np.concatenate(out).astype(np.float32)
+
+
+def bit_unpack(fields, row: np.ndarray) -> Dict[str, torch.Tensor]:
+    out, o = {}, 0
+    for name, shape in fields:
+        n = int(np.prod(shape))
+        out[name] = torch.from_numpy(np.ascontiguousarray(row[o: o + n])).reshape(shape)
+        o += n
+    assert o == row.size
+    return out
+
+
+@dataclass
 class SumSpec:
     """dst = sum of up to five tensors (Dblock.forward, models/DTCDSCN.py:65-71)."""
     name: str
@@ -722,6 +778,9 @@ def op_bytes_per_pair(prog: Program, op) -> int:
     if isinstance(op, SumSpec):
         t = T[op.dst]
         return t.mult * t.c * t.h * t.w * 2 * (len(op.srcs) + 1)
+    if isinstance(op, BitTransformerSpec):
+        t = T[op.src]
+        return t.mult * op.c * t.h * t.w * 2 * 3            # tokenizer read + decoder read + write
     if isinstance(op, EcamHeadSpec):
         t = T[op.srcs[0]]
         return 2 * 4 * op.c * t.h * t.w * 2 + op.n_class * t.h * t.w * 4

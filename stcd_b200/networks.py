@@ -15,6 +15,7 @@ from torch.nn import init
 
 from .siamunet import SiamUnet_conc, SiamUnet_cross_conc, SiamUnet_diff, SiamUnet_sub, Unet
 from .changeformer import ChangeFormerV6
+from .bit import BASE_Transformer, ResNet
 from .changevig import ChangeGNNV1
 from .dtcdscn import CDNet34, CDNet_model
 from .segcd import SegCD
@@ -23,8 +24,7 @@ from .snunet import SNUNet_ECAM
 # registry keys of models/networks.py:144-214 that this library does NOT implement (yet): asking for one
 # raises NotImplementedError like an unknown key does upstream, with the reason.
 _REFERENCE_ONLY = (
-    "IFNet", "base_resnet18", "base_transformer_pos_s4",
-    "base_transformer_pos_s4_dd8", "base_transformer_pos_s4_dd8_dedim8", "ChangeFormerV1", "ChangeFormerV2",
+    "IFNet", "ChangeFormerV1", "ChangeFormerV2",
     "ChangeFormerV3", "ChangeFormerV4", "ChangeFormerV5", "ChangeGNNV2",
     "ChangeGNNV2_sub", "ChangeGNNV2_abs", "ChangeGNNV2_conc", "GNN",
 )
@@ -36,6 +36,13 @@ _REGISTRY = {
     "SiamUnet_abs": lambda a: SiamUnet_diff(input_nbr=3, label_nbr=a.n_class),     # networks.py:148-149
     "SiamUnet_conc": lambda a: SiamUnet_conc(input_nbr=3, label_nbr=a.n_class),    # networks.py:151-152
     "DTCDSCN": lambda a: CDNet34(in_channels=3, num_classes=a.n_class),            # networks.py:159-160
+    # BIT, networks.py:170-182
+    "base_resnet18": lambda a: ResNet(input_nc=3, output_nc=2, output_sigmoid=False),
+    "base_transformer_pos_s4": lambda a: BASE_Transformer(input_nc=3, output_nc=2, token_len=4, resnet_stages_num=4, with_pos="learned"),
+    "base_transformer_pos_s4_dd8": lambda a: BASE_Transformer(input_nc=3, output_nc=2, token_len=4, resnet_stages_num=4,
+                                                              with_pos="learned", enc_depth=1, dec_depth=8),
+    "base_transformer_pos_s4_dd8_dedim8": lambda a: BASE_Transformer(input_nc=3, output_nc=2, token_len=4, resnet_stages_num=4,
+                                                                     with_pos="learned", enc_depth=1, dec_depth=8, decoder_dim_head=8),
     "SNUNet": lambda a: SNUNet_ECAM(in_ch=3, out_ch=a.n_class),                    # networks.py:168-169
     "ChangeGNNV1": lambda a: ChangeGNNV1(embed_dim=a.embed_dim),                   # networks.py:199-200
     "ChangeFormerV6": lambda a: ChangeFormerV6(embed_dim=a.embed_dim),             # networks.py:190-191
@@ -46,6 +53,7 @@ _REGISTRY = {
 CLASSES = {"SiamUnet_diff": SiamUnet_diff, "SiamUnet_conc": SiamUnet_conc, "SiamUnet_sub": SiamUnet_sub,
            "SiamUnet_cross_conc": SiamUnet_cross_conc, "Unet": Unet, "SNUNet_ECAM": SNUNet_ECAM, "SegCD": SegCD,
            "ChangeGNNV1": ChangeGNNV1, "ChangeFormerV6": ChangeFormerV6,
+           "BASE_Transformer": BASE_Transformer, "ResNet": ResNet,
            "CDNet_model": lambda in_channels=3, num_classes=2: CDNet34(in_channels, num_classes)}
 
 

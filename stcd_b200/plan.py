@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .lowering import (AbsDiffSpec, AttentionSpec, ChannelGateSpec, SumSpec, BilinearUpSpec, ConvSpec, DWConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec,
+from .lowering import (AbsDiffSpec, AttentionSpec, BitTransformerSpec, ChannelGateSpec, SumSpec, BilinearUpSpec, ConvSpec, DWConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec,
                        LayerNormSpec, MaxPoolS2DSpec, Program, SegHeadSpec)
 
 
@@ -74,6 +74,15 @@ class Plan:
                 _lib.check_id(lib.stcd_plan_add_channel_gate(h, ids[op.src], -1 if op.res is None else ids[op.res], ids[op.dst],
                                                              -1 if op.dst_s2d is None else ids[op.dst_s2d], op.c, w1.shape[0],
                                                              _fptr(w1), _fptr(w2), _fptr(ws), op.mode), f"channel gate {op.name}")
+            elif isinstance(op, BitTransformerSpec):
+                d = _lib.BitDesc()
+                d.c, d.token_len, d.heads, d.mlp = op.c, op.token_len, op.heads, op.mlp
+                d.n_enc, d.n_dec, d.inner_enc, d.inner_dec, d.softmax = len(op.enc), len(op.dec), op.inner_enc, op.inner_dec, int(op.softmax)
+                keep = [np.ascontiguousarray(a, np.float32) for a in (op.conv_a, op.pos, op.enc, op.dec)]
+                if len(op.enc) == 0:
+                    keep[2] = np.zeros(1, np.float32)
+                d.conv_a, d.pos, d.enc, d.dec = (_fptr(a) for a in keep)
+                _lib.check_id(lib.stcd_plan_add_bit_transformer(h, ids[op.src], ids[op.dst], C.byref(d)), f"BIT transformer {op.name}")
             elif isinstance(op, SumSpec):
                 arr = (C.c_int * len(op.srcs))(*[ids[s_] for s_ in op.srcs])
                 _lib.check_id(lib.stcd_plan_add_sum(h, arr, len(op.srcs), ids[op.dst]), f"sum {op.name}")

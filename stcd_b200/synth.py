@@ -25,11 +25,12 @@ DATA_SEED = 1338
 # layers, 5-sigma tail over 1e5 logits), so the harness keeps the logit standard deviation near 0.2-0.3:
 # non-degenerate change maps (tens of % "changed") with the tolerance still meaningful.
 GAINS = {"SiamUnet_diff": 0.72, "SiamUnet_conc": 0.70, "SiamUnet_sub": 0.72, "SiamUnet_cross_conc": 0.72, "Unet": 0.64, "SNUNet_ECAM": 0.6, "SegCD": 0.70, "ChangeGNNV1": 0.5, "ChangeFormerV6": 0.5,
-         "CDNet_model": 0.6}
+         "CDNet_model": 0.6, "BASE_Transformer": 0.47, "ResNet": 0.6}
 # Head-bias offsets (parameter name, per-class values added after the random draw) that centre the
 # class margin of nets whose random-init margin is one-sided (SNUNet's post-ReLU features make class
 # 0 win everywhere): without it the change map is all-zero and pixel agreement says nothing.
-HEAD_BIAS = {"SNUNet_ECAM": ("conv_final.bias", [0.0, 0.95]), "CDNet_model": ("finalconv3_master.bias", [0.245, 0.0])}
+HEAD_BIAS = {"SNUNet_ECAM": ("conv_final.bias", [0.0, 0.95]), "CDNet_model": ("finalconv3_master.bias", [0.245, 0.0]),
+             "BASE_Transformer": ("classifier.3.bias", [0.19, 0.0])}
 
 
 @torch.no_grad()
@@ -62,6 +63,9 @@ def randomize_(net: nn.Module, seed: int = WEIGHT_SEED, gain: float = 1.0) -> nn
         pe = m._parameters.get("pos_embed") if hasattr(m, "_parameters") else None
         if pe is not None:           # ViG / transformer positional embedding: zeros at construction (ChangeVIG.py:50)
             pe.copy_(torch.randn(pe.shape, generator=g) * 0.1)
+        pe = m._parameters.get("pos_embedding") if hasattr(m, "_parameters") else None
+        if pe is not None:           # BIT's learned token positions: global-RNG randn at construction (networks.py:337)
+            pe.copy_(torch.randn(pe.shape, generator=g))
     return net
 
 

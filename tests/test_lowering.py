@@ -151,6 +151,44 @@ def test_dtcdscn_program_matches_oracle():
         net.lower(100, 96)
 
 
+@pytest.mark.parametrize("variant", ["s4", "dd8", "dd8_dedim8", "resnet18"])
+def test_bit_program_matches_oracle(variant):
+    """BIT (BASE_Transformer) and its ResNet-18 baseline: backbone convs, nearest x2 + conv_pred as merged-tap phases, the token
+    path as one op (checked semantically by the emulator from the PACKED weights), |x1 - x2|, bilinear x4, classifier."""
+    from stcd_b200 import bit
+    if variant == "resnet18":
+        net, stages, cls = bit.ResNet(3, 2), 5, "ResNet"
+    else:
+        kw = {"s4": {}, "dd8": dict(enc_depth=1, dec_depth=8), "dd8_dedim8": dict(enc_depth=1, dec_depth=8, decoder_dim_head=8)}[variant]
+        net, stages, cls = bit.BASE_Transformer(3, 2, with_pos="learned", resnet_stages_num=4, token_len=4, **kw), 4, "BASE_Transformer"
+    net = synth.prepare_(net.eval(), cls)
+    x1, x2 = synth.image_pairs(3, 64, 96)
+    with torch.no_grad():
+        y = nets.bit_forward(net.state_dict(), x1, x2, stages=stages)
+    prog = net.lower(64, 96)
+    ye = emulate.run_program(prog, x1, x2, chunk=2)[0]
+    assert ye.shape == y.shape == (3, 2, 64, 96) and (ye - y).abs().max().item() < BF16_TOL
+    margin = (y[:, 1] - y[:, 0]).abs()
+    agree = (ye[:, 1] > ye[:, 0]) == (y[:, 1] > y[:, 0])
+    assert agree[margin > BF16_TOL].float().mean().item() >= 0.999
+    if variant in ("dd8", "resnet18"):          # the harness' head-bias offset is tuned for the dd8 key
+        assert 0.02 < (y[:, 1] > y[:, 0]).float().mean().item() < 0.98, "degenerate change map"
+    convs = [o for o in prog.ops if isinstance(o, L.ConvSpec)]
+    bits = [o for o in prog.ops if isinstance(o, L.BitTransformerSpec)]
+    # stem + 2 convs per BasicBlock + 1 downsample per strided/widening layer + conv_pred + 2 classifier convs
+    assert len(convs) == 1 + 4 * (stages - 1) + (stages - 2) + 1 + 2
+    if variant == "resnet18":
+        assert not bits
+    else:
+        (b,) = bits
+        assert (len(b.enc), len(b.dec), b.inner_dec) == {"s4": (1, 1, 512), "dd8": (1, 8, 512), "dd8_dedim8": (1, 8, 64)}[variant]
+        assert b.enc.shape[1] == 2 * 32 + 3 * 512 * 32 + 32 * 512 + 32 + 2 * 32 + 64 * 32 + 64 + 32 * 64 + 32
+    # the backbone's unused layer4 / fc are held as parameters, like upstream
+    assert "resnet.fc.weight" in net.state_dict() and "resnet.layer4.1.conv2.weight" in net.state_dict()
+    with pytest.raises(ValueError):
+        net.lower(100, 96)
+
+
 def test_changegnn_program_matches_oracle():
     """Config C4's net: ViG Grapher blocks (graph op + grouped conv folded into a dense virtual-concat conv), GELU /
     PReLU-before-BN epilogues, bilinear resizes, ConvTranspose2d(k4, s2) phases -- checked through the emulator."""

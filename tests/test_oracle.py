@@ -40,6 +40,10 @@ def _oracle_forward(case, sd, x1, x2):
         return nets.changeformer_forward(sd, x1, x2)
     if cls == "CDNet_model":
         return [nets.dtcdscn_forward(sd, x1, x2)]
+    if cls == "BASE_Transformer":
+        return [nets.bit_forward(sd, x1, x2, stages=4)]
+    if cls == "ResNet":
+        return [nets.bit_forward(sd, x1, x2, stages=5)]
     raise KeyError(cls)
 
 
