@@ -201,9 +201,9 @@ int stcd_plan_add_channel_gate(stcd_plan* plan, int src_tensor, int res_or_neg, 
  * decoder (every pixel queries its image's L tokens).  c = 32, token_len = 4, heads = 8, mlp = 64 (the registered BIT keys).
  * enc / dec: HOST fp32, one packed row per layer:
  *   enc row: ln1_g[c] ln1_b[c] Wqkv[3*inner_enc][c] Wout[c][inner_enc] bout[c] ln2_g[c] ln2_b[c] W1[mlp][c] b1[mlp] W2[c][mlp] b2[c]
- *   dec row: ln1_g[c] ln1_b[c] Wq[inner_dec][c] Wk[..][c] Wv[..][c] Wout[c][inner_dec] bout[c] ln2_g[c] ln2_b[c]
+ *   dec row: ln1_g[c] ln1_b[c] Wq[inner_dec][c] Wk[..][c] Wv[..][c] Wout^T[inner_dec][c] bout[c] ln2_g[c] ln2_b[c]
  *            W1^T[c][mlp] b1[mlp] W2^T[mlp][c] b2[c]
- * (torch Linear layouts [out][in]; the decoder's feed-forward weights transposed). */
+ * (torch Linear layouts [out][in]; the decoder's to_out and feed-forward weights transposed). */
 typedef struct {
   int32_t c, token_len, heads, mlp;
   int32_t n_enc, n_dec, inner_enc, inner_dec;

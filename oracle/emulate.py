@@ -348,7 +348,7 @@ def run_bit_transformer(op: L.BitTransformerSpec, T: Dict[str, torch.Tensor], ch
         P = L.bit_unpack(L.bit_dec_fields(c, op.inner_dec, op.mlp), row)
         zn, mn = F.layer_norm(z, (c,), P["ln1_g"], P["ln1_b"]), F.layer_norm(m, (c,), P["ln1_g"], P["ln1_b"])
         o = attend(zn @ P["wq"].T, mn @ P["wk"].T, mn @ P["wv"].T, op.softmax)
-        z = o @ P["wout"].T + P["bout"] + z
+        z = o @ P["woutt"] + P["bout"] + z
         y = F.layer_norm(z, (c,), P["ln2_g"], P["ln2_b"])
         z = F.gelu(y @ P["w1t"] + P["b1"]) @ P["w2t"] + P["b2"] + z
     T[op.dst][..., : c] = _bf16(z.reshape(n2, h, w, c))

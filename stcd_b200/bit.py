@@ -272,7 +272,7 @@ def lower_bit(sd: Dict[str, torch.Tensor], in_channels: int, n_class: int, stage
             a, ff = f"transformer_decoder.layers.{l}.0.fn", f"transformer_decoder.layers.{l}.1.fn"
             dec_rows.append(L.bit_pack(L.bit_dec_fields(c, idd, mlp), {
                 "ln1_g": sd[f"{a}.norm.weight"], "ln1_b": sd[f"{a}.norm.bias"], "wq": sd[f"{a}.fn.to_q.weight"],
-                "wk": sd[f"{a}.fn.to_k.weight"], "wv": sd[f"{a}.fn.to_v.weight"], "wout": sd[f"{a}.fn.to_out.0.weight"],
+                "wk": sd[f"{a}.fn.to_k.weight"], "wv": sd[f"{a}.fn.to_v.weight"], "woutt": sd[f"{a}.fn.to_out.0.weight"].t().contiguous(),
                 "bout": sd[f"{a}.fn.to_out.0.bias"], "ln2_g": sd[f"{ff}.norm.weight"], "ln2_b": sd[f"{ff}.norm.bias"],
                 "w1t": sd[f"{ff}.fn.net.0.weight"].t().contiguous(), "b1": sd[f"{ff}.fn.net.0.bias"],
                 "w2t": sd[f"{ff}.fn.net.3.weight"].t().contiguous(), "b2": sd[f"{ff}.fn.net.3.bias"]}))

@@ -2,10 +2,10 @@
 // map [img][4][h*w][8], fp32 arithmetic.
 //
 //   bit_tokenizer_kernel   one CTA per image: tokens[l] = sum_n softmax_n(conv_a(x))[l, n] x[n]  (online softmax, one read)
-//   bit_token_mixer_kernel one CTA per pair: + learned positions, the transformer encoder over the pair's 2L tokens, then per
-//                          decoder layer and stream the collapsed cross-attention matrices
+//   bit_token_mixer_kernel one CTA per pair: + learned positions, the transformer encoder over the pair's 2L tokens
+//   bit_coef_kernel        one CTA per (pair, decoder layer): the collapsed cross-attention matrices of both streams
 //                            A[c][(h, j)]  = scale * sum_d Wq[h*dh + d][c] * k[j][h*dh + d]       k = Wk LN(m)
-//                            Bm[(h, j)][c] =         sum_d Wout[c][h*dh + d] * v[j][h*dh + d]     v = Wv LN(m)
+//                            Bm[(h, j)][c] =         sum_d Wout[c][h*dh + d] * v[j][h*dh + d]     v = Wv LN(m)   (Wout packed transposed)
 //                          so that softmax_j(q_h . k_hj * scale) v_hj Wout^T == softmax_groups(LN(x) A) Bm.
 //   bit_decoder_kernel     one thread per pixel, its 32 channels in registers through every decoder layer:
 //                          x += softmax_groups(LN(x) A) Bm + bout;  x += W2 gelu(W1 LN(x) + b1) + b2
@@ -128,10 +128,9 @@ __device__ __forceinline__ void bit_ln_rows(const float* __restrict__ in, float*
 
 // grid = pairs (chunk), 256 threads; dynamic smem: big[8 * 3 * inner_max] floats
 __global__ void __launch_bounds__(256) bit_token_mixer_kernel(const float* __restrict__ tokens, const float* __restrict__ pos,
-                                                              const float* __restrict__ enc, const float* __restrict__ dec,
-                                                              float* __restrict__ coef, int chunk, int n_enc, int n_dec,
-                                                              int inner_e, int inner_d, float scale) {
-  extern __shared__ float s_big[];                 // encoder: qkv [8][3*inner_e]; decoder: k | v [2][4][inner_d]
+                                                              const float* __restrict__ enc, float* __restrict__ tok_out, int chunk,
+                                                              int n_enc, int inner_e, float scale) {
+  extern __shared__ float s_big[];                 // qkv [8][3*inner_e]
   __shared__ float s_t[2 * kBitL * kBitC], s_y[2 * kBitL * kBitC], s_attn[kBitHeads][2 * kBitL][2 * kBitL], s_h[2 * kBitL * kBitMlp];
   const int pair = blockIdx.x, tid = threadIdx.x;
   constexpr int R = 2 * kBitL;                      // 8 token rows per pair
@@ -197,11 +196,22 @@ __global__ void __launch_bounds__(256) bit_token_mixer_kernel(const float* __res
       s_big[i * 3 * inner_e + col] = a;
     }
     __syncthreads();
-    {
-      const int r = tid / kBitC, c = tid % kBitC;
-      float a = __ldg(bout + c);
-      for (int j = 0; j < inner_e; ++j) a = fmaf(s_big[r * 3 * inner_e + j], __ldg(wout + static_cast<size_t>(c) * inner_e + j), a);
-      s_t[tid] += a;
+    for (int c = tid >> 5; c < kBitC; c += 8) {                 // warp per output channel: lanes stride over inner (coalesced rows)
+      const int lane = tid & 31;
+      float a[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[r] = 0.f;
+      for (int j = lane; j < inner_e; j += 32) {
+        const float wv_ = __ldg(wout + static_cast<size_t>(c) * inner_e + j);
+#pragma unroll
+        for (int r = 0; r < R; ++r) a[r] = fmaf(s_big[r * 3 * inner_e + j], wv_, a[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
+        if (lane == 0) s_t[r * kBitC + c] += a[r] + __ldg(bout + c);
+      }
     }
     __syncthreads();
     bit_ln_rows(s_t, s_y, ln2_g, ln2_b, R);
@@ -223,100 +233,149 @@ __global__ void __launch_bounds__(256) bit_token_mixer_kernel(const float* __res
     }
     __syncthreads();
   }
-  // decoder: the tokens are the memory of every layer (they do not change); collapse each layer's cross-attention
+  tok_out[static_cast<size_t>(pair) * R * kBitC + tid] = s_t[tid];
+}
+
+// grid (pairs, decoder layers), 256 threads; dynamic smem: k | v [2][8][inner_d] floats.  The encoder's tokens are the memory
+// of every decoder layer (they never change), so the layers' collapsed matrices are independent of each other.
+__global__ void __launch_bounds__(256) bit_coef_kernel(const float* __restrict__ tok, const float* __restrict__ dec, float* __restrict__ coef,
+                                                       int chunk, int n_dec, int inner_d, float scale) {
+  extern __shared__ float s_kv[];
+  __shared__ float s_t[2 * kBitL * kBitC], s_y[2 * kBitL * kBitC];
+  constexpr int R = 2 * kBitL;
+  const int pair = blockIdx.x, l = blockIdx.y, tid = threadIdx.x;
   const int dh = inner_d / kBitHeads;
-  for (int l = 0; l < n_dec; ++l) {
-    const float* P = dec + static_cast<size_t>(l) * bit_dec_size(inner_d);
-    const float* ln1_g = P;
-    const float* ln1_b = ln1_g + kBitC;
-    const float* wq = ln1_b + kBitC;
-    const float* wk = wq + inner_d * kBitC;
-    const float* wv = wk + inner_d * kBitC;
-    const float* wout = wv + inner_d * kBitC;
-    bit_ln_rows(s_t, s_y, ln1_g, ln1_b, R);                     // PreNorm2: the layer's norm on the memory too
-    __syncthreads();
-    float* s_k = s_big;                                         // [R][inner_d]
-    float* s_v = s_big + R * inner_d;
-    for (int j = tid; j < 2 * inner_d; j += blockDim.x) {
-      const float* wrow = (j < inner_d ? wk + static_cast<size_t>(j) * kBitC : wv + static_cast<size_t>(j - inner_d) * kBitC);
-      float w[kBitC];
+  s_t[tid] = tok[static_cast<size_t>(pair) * R * kBitC + tid];
+  __syncthreads();
+  const float* P = dec + static_cast<size_t>(l) * bit_dec_size(inner_d);
+  const float* wq = P + 2 * kBitC;
+  const float* wk = wq + inner_d * kBitC;
+  const float* wv = wk + inner_d * kBitC;
+  const float* woutt = wv + inner_d * kBitC;                    // [inner][c]
+  bit_ln_rows(s_t, s_y, P, P + kBitC, R);                       // PreNorm2: the layer's norm on the memory too
+  __syncthreads();
+  float* s_k = s_kv;                                            // [R][inner_d]
+  float* s_v = s_kv + R * inner_d;
+  for (int j = tid; j < 2 * inner_d; j += blockDim.x) {
+    const float* wrow = (j < inner_d ? wk + static_cast<size_t>(j) * kBitC : wv + static_cast<size_t>(j - inner_d) * kBitC);
+    float w[kBitC];
 #pragma unroll
-      for (int q = 0; q < kBitC / 4; ++q) {
-        const float4 t4 = __ldg(reinterpret_cast<const float4*>(wrow) + q);
-        w[4 * q] = t4.x, w[4 * q + 1] = t4.y, w[4 * q + 2] = t4.z, w[4 * q + 3] = t4.w;
-      }
-      for (int r = 0; r < R; ++r) {
-        float a = 0.f;
+    for (int q = 0; q < kBitC / 4; ++q) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(wrow) + q);
+      w[4 * q] = t4.x, w[4 * q + 1] = t4.y, w[4 * q + 2] = t4.z, w[4 * q + 3] = t4.w;
+    }
+    for (int r = 0; r < R; ++r) {
+      float a = 0.f;
 #pragma unroll
-        for (int c = 0; c < kBitC; ++c) a = fmaf(s_y[r * kBitC + c], w[c], a);
-        (j < inner_d ? s_k[r * inner_d + j] : s_v[r * inner_d + j - inner_d]) = a;
-      }
+      for (int c = 0; c < kBitC; ++c) a = fmaf(s_y[r * kBitC + c], w[c], a);
+      (j < inner_d ? s_k[r * inner_d + j] : s_v[r * inner_d + j - inner_d]) = a;
     }
-    __syncthreads();
-    for (int it = tid; it < 2 * kBitC * kBitHJ; it += blockDim.x) {       // (stream, c, hj): A and Bm
-      const int s = it / (kBitC * kBitHJ), rem = it % (kBitC * kBitHJ);
-      const int hj = rem / kBitC, c = rem % kBitC;                       // lanes vary c: Wq reads coalesce
-      const int h = hj / kBitL, j = hj % kBitL, row = s * kBitL + j;
-      float a = 0.f, b = 0.f;
-      for (int e = 0; e < dh; ++e) {
-        a = fmaf(__ldg(wq + static_cast<size_t>(h * dh + e) * kBitC + c), s_k[row * inner_d + h * dh + e], a);
-        b = fmaf(__ldg(wout + static_cast<size_t>(c) * inner_d + h * dh + e), s_v[row * inner_d + h * dh + e], b);
-      }
-      float* o = coef + (static_cast<size_t>(s * chunk + pair) * n_dec + l) * kBitCoef;
-      o[c * kBitHJ + hj] = a * scale;
-      o[kBitC * kBitHJ + hj * kBitC + c] = b;
+  }
+  __syncthreads();
+  for (int it = tid; it < 2 * kBitC * kBitHJ; it += blockDim.x) {         // (stream, hj, c): lanes vary c, both weight reads coalesce
+    const int s = it / (kBitC * kBitHJ), rem = it % (kBitC * kBitHJ);
+    const int hj = rem / kBitC, c = rem % kBitC;
+    const int h = hj / kBitL, j = hj % kBitL, row = s * kBitL + j;
+    float a = 0.f, b = 0.f;
+    for (int e = 0; e < dh; ++e) {
+      a = fmaf(__ldg(wq + static_cast<size_t>(h * dh + e) * kBitC + c), s_k[row * inner_d + h * dh + e], a);
+      b = fmaf(__ldg(woutt + static_cast<size_t>(h * dh + e) * kBitC + c), s_v[row * inner_d + h * dh + e], b);
     }
-    __syncthreads();
+    float* o = coef + (static_cast<size_t>(s * chunk + pair) * n_dec + l) * kBitCoef;
+    o[c * kBitHJ + hj] = a * scale;
+    o[kBitC * kBitHJ + hj * kBitC + c] = b;
   }
 }
 
 // ------------------------------------------------------------------------------------------ decoder
-__device__ __forceinline__ void bit_ln32(const float (&x)[kBitC], float (&y)[kBitC], const float* __restrict__ g, const float* __restrict__ b) {
+// Two pixels per thread and packed fp32 FMAs (FFMA2): every broadcast LDS.128 of a weight row feeds 8 FMAs (4 FFMA2), which
+// keeps the kernel on the FMA pipe instead of the shared-memory port.
+struct BitPx {                     // one pixel's 32 channels as 16 packed pairs
+  float2 v[kBitC / 2];
+};
+
+__device__ __forceinline__ void bit_ln32(const BitPx& x, float (&y)[kBitC], const float* __restrict__ g, const float* __restrict__ b) {
   float mean = 0.f;
 #pragma unroll
-  for (int c = 0; c < kBitC; ++c) mean += x[c];
+  for (int c = 0; c < kBitC / 2; ++c) mean += x.v[c].x + x.v[c].y;
   mean *= (1.f / kBitC);
   float var = 0.f;
 #pragma unroll
-  for (int c = 0; c < kBitC; ++c) var = fmaf(x[c] - mean, x[c] - mean, var);
+  for (int c = 0; c < kBitC / 2; ++c) {
+    var = fmaf(x.v[c].x - mean, x.v[c].x - mean, var);
+    var = fmaf(x.v[c].y - mean, x.v[c].y - mean, var);
+  }
   const float rs = rsqrtf(var * (1.f / kBitC) + 1e-5f);
 #pragma unroll
-  for (int c = 0; c < kBitC; ++c) y[c] = (x[c] - mean) * rs * g[c] + b[c];
+  for (int c = 0; c < kBitC / 2; ++c) {
+    y[2 * c] = (x.v[c].x - mean) * rs * g[2 * c] + b[2 * c];
+    y[2 * c + 1] = (x.v[c].y - mean) * rs * g[2 * c + 1] + b[2 * c + 1];
+  }
 }
 
-// out[N] += in[K] . W[K][N] (row-major rows in shared memory, broadcast float4 reads)
-template <int K, int N>
-__device__ __forceinline__ void bit_matvec(const float (&in)[K], const float* __restrict__ W, float (&out)[N]) {
+// out{0,1}[32] += in{0,1}[K] . W[K][32 of a row of `stride` floats]  (rows in shared memory, broadcast float4 reads)
+template <int K>
+__device__ __forceinline__ void bit_matvec2(const float* __restrict__ in0, const float* __restrict__ in1, const float* __restrict__ W,
+                                            int stride, BitPx& out0, BitPx& out1) {
 #pragma unroll
   for (int k = 0; k < K; ++k) {
+    const float2 a0 = make_float2(in0[k], in0[k]), a1 = make_float2(in1[k], in1[k]);
 #pragma unroll
-    for (int n4 = 0; n4 < N / 4; ++n4) {
-      const float4 w = *reinterpret_cast<const float4*>(W + k * N + 4 * n4);
-      out[4 * n4] = fmaf(in[k], w.x, out[4 * n4]);
-      out[4 * n4 + 1] = fmaf(in[k], w.y, out[4 * n4 + 1]);
-      out[4 * n4 + 2] = fmaf(in[k], w.z, out[4 * n4 + 2]);
-      out[4 * n4 + 3] = fmaf(in[k], w.w, out[4 * n4 + 3]);
+    for (int n4 = 0; n4 < kBitC / 4; ++n4) {
+      const float4 w = *reinterpret_cast<const float4*>(W + k * stride + 4 * n4);
+      const float2 wlo = make_float2(w.x, w.y), whi = make_float2(w.z, w.w);
+      out0.v[2 * n4] = __ffma2_rn(a0, wlo, out0.v[2 * n4]);
+      out0.v[2 * n4 + 1] = __ffma2_rn(a0, whi, out0.v[2 * n4 + 1]);
+      out1.v[2 * n4] = __ffma2_rn(a1, wlo, out1.v[2 * n4]);
+      out1.v[2 * n4 + 1] = __ffma2_rn(a1, whi, out1.v[2 * n4 + 1]);
     }
   }
 }
 
-// grid (pixel blocks, images), 256 threads
-__global__ void __launch_bounds__(256) bit_decoder_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                          const float* __restrict__ dec, const float* __restrict__ coef, int src_c8,
-                                                          int dst_c8, int hw, int n_dec, int inner_d, int softmax) {
+__device__ __forceinline__ void bit_softmax_groups(BitPx& d) {       // 8 heads x 4 keys: groups of two packed pairs
+#pragma unroll
+  for (int h = 0; h < kBitHeads; ++h) {
+    float2& p = d.v[2 * h];
+    float2& q = d.v[2 * h + 1];
+    const float mx = fmaxf(fmaxf(p.x, p.y), fmaxf(q.x, q.y));
+    p.x = __expf(p.x - mx), p.y = __expf(p.y - mx), q.x = __expf(q.x - mx), q.y = __expf(q.y - mx);
+    const float inv = 1.f / (p.x + p.y + q.x + q.y);
+    p.x *= inv, p.y *= inv, q.x *= inv, q.y *= inv;
+  }
+}
+
+constexpr int kBitDecThreads = 128;
+
+// grid (pixel blocks of 2 * kBitDecThreads, images)
+__global__ void __launch_bounds__(kBitDecThreads) bit_decoder_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                     const float* __restrict__ dec, const float* __restrict__ coef,
+                                                                     int src_c8, int dst_c8, int hw, int n_dec, int inner_d, int softmax) {
   __shared__ __align__(16) float s_ln1[2 * kBitC];
   __shared__ __align__(16) float s_coef[kBitCoef];
   __shared__ __align__(16) float s_tail[kBitDecTail];
-  const int img = blockIdx.y, pix = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = pix < hw;
-  float x[kBitC];
-  if (live) {
+  const int img = blockIdx.y;
+  const int pix0 = blockIdx.x * (2 * kBitDecThreads) + threadIdx.x, pix1 = pix0 + kBitDecThreads;
+  BitPx x0, x1;
+  {
     const __nv_bfloat16* b = src + static_cast<size_t>(img) * src_c8 * hw * 8;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) unpack8(__ldg(reinterpret_cast<const uint4*>(b + (static_cast<size_t>(g) * hw + pix) * 8)), x + 8 * g);
-  } else {
+    for (int g = 0; g < 4; ++g) {
+      float t[8];
+      if (pix0 < hw) unpack8(__ldg(reinterpret_cast<const uint4*>(b + (static_cast<size_t>(g) * hw + pix0) * 8)), t);
+      else {
 #pragma unroll
-    for (int c = 0; c < kBitC; ++c) x[c] = 0.f;
+        for (int j = 0; j < 8; ++j) t[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x0.v[4 * g + j] = make_float2(t[2 * j], t[2 * j + 1]);
+      if (pix1 < hw) unpack8(__ldg(reinterpret_cast<const uint4*>(b + (static_cast<size_t>(g) * hw + pix1) * 8)), t);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x1.v[4 * g + j] = make_float2(t[2 * j], t[2 * j + 1]);
+    }
   }
   for (int l = 0; l < n_dec; ++l) {
     const float* P = dec + static_cast<size_t>(l) * bit_dec_size(inner_d);
@@ -325,7 +384,8 @@ __global__ void __launch_bounds__(256) bit_decoder_kernel(const __nv_bfloat16* _
     for (int i = threadIdx.x; i < 2 * kBitC; i += blockDim.x) s_ln1[i] = __ldg(P + i);
     for (int i = threadIdx.x; i < kBitCoef / 4; i += blockDim.x)
       reinterpret_cast<float4*>(s_coef)[i] = __ldg(reinterpret_cast<const float4*>(cf) + i);
-    for (int i = threadIdx.x; i < kBitDecTail; i += blockDim.x) s_tail[i] = __ldg(P + bit_dec_tail_off(inner_d) + i);
+    for (int i = threadIdx.x; i < kBitDecTail / 4; i += blockDim.x)
+      reinterpret_cast<float4*>(s_tail)[i] = __ldg(reinterpret_cast<const float4*>(P + bit_dec_tail_off(inner_d)) + i);
     __syncthreads();
     const float* bout = s_tail;
     const float* ln2_g = bout + kBitC;
@@ -334,49 +394,51 @@ __global__ void __launch_bounds__(256) bit_decoder_kernel(const __nv_bfloat16* _
     const float* b1 = w1t + kBitC * kBitMlp;
     const float* w2t = b1 + kBitMlp;
     const float* b2 = w2t + kBitMlp * kBitC;
-    float y[kBitC];
-    bit_ln32(x, y, s_ln1, s_ln1 + kBitC);
+    float y0[kBitC], y1[kBitC];
+    bit_ln32(x0, y0, s_ln1, s_ln1 + kBitC);
+    bit_ln32(x1, y1, s_ln1, s_ln1 + kBitC);
     {
-      float d[kBitHJ];
+      BitPx d0, d1;
 #pragma unroll
-      for (int i = 0; i < kBitHJ; ++i) d[i] = 0.f;
-      bit_matvec<kBitC, kBitHJ>(y, s_coef, d);
+      for (int i = 0; i < kBitC / 2; ++i) d0.v[i] = d1.v[i] = make_float2(0.f, 0.f);
+      bit_matvec2<kBitC>(y0, y1, s_coef, kBitHJ, d0, d1);
       if (softmax) {
-#pragma unroll
-        for (int h = 0; h < kBitHeads; ++h) {
-          const float mx = fmaxf(fmaxf(d[4 * h], d[4 * h + 1]), fmaxf(d[4 * h + 2], d[4 * h + 3]));
-          float sum = 0.f;
-#pragma unroll
-          for (int j = 0; j < kBitL; ++j) {
-            d[4 * h + j] = __expf(d[4 * h + j] - mx);
-            sum += d[4 * h + j];
-          }
-          const float inv = 1.f / sum;
-#pragma unroll
-          for (int j = 0; j < kBitL; ++j) d[4 * h + j] *= inv;
-        }
+        bit_softmax_groups(d0);
+        bit_softmax_groups(d1);
       }
 #pragma unroll
-      for (int c = 0; c < kBitC; ++c) x[c] += bout[c];
-      bit_matvec<kBitHJ, kBitC>(d, s_coef + kBitC * kBitHJ, x);
+      for (int c = 0; c < kBitC / 2; ++c) {
+        const float2 bb = make_float2(bout[2 * c], bout[2 * c + 1]);
+        x0.v[c].x += bb.x, x0.v[c].y += bb.y, x1.v[c].x += bb.x, x1.v[c].y += bb.y;
+      }
+      bit_matvec2<kBitHJ>(reinterpret_cast<const float*>(d0.v), reinterpret_cast<const float*>(d1.v), s_coef + kBitC * kBitHJ, kBitC, x0, x1);
     }
-    bit_ln32(x, y, ln2_g, ln2_b);
-    {
-      float hbuf[kBitMlp];
+    bit_ln32(x0, y0, ln2_g, ln2_b);
+    bit_ln32(x1, y1, ln2_g, ln2_b);
 #pragma unroll
-      for (int k = 0; k < kBitMlp; ++k) hbuf[k] = b1[k];
-      bit_matvec<kBitC, kBitMlp>(y, w1t, hbuf);
+    for (int c = 0; c < kBitC / 2; ++c) {
+      const float2 bb = make_float2(b2[2 * c], b2[2 * c + 1]);
+      x0.v[c].x += bb.x, x0.v[c].y += bb.y, x1.v[c].x += bb.x, x1.v[c].y += bb.y;
+    }
+#pragma unroll 1
+    for (int half = 0; half < kBitMlp / kBitC; ++half) {        // hidden units 32 at a time: bounds the live registers
+      BitPx h0, h1;
 #pragma unroll
-      for (int k = 0; k < kBitMlp; ++k) hbuf[k] = bit_gelu(hbuf[k]);
+      for (int k = 0; k < kBitC / 2; ++k) h0.v[k] = h1.v[k] = make_float2(b1[half * kBitC + 2 * k], b1[half * kBitC + 2 * k + 1]);
+      bit_matvec2<kBitC>(y0, y1, w1t + half * kBitC, kBitMlp, h0, h1);
 #pragma unroll
-      for (int c = 0; c < kBitC; ++c) x[c] += b2[c];
-      bit_matvec<kBitMlp, kBitC>(hbuf, w2t, x);
+      for (int k = 0; k < kBitC / 2; ++k) {
+        h0.v[k].x = bit_gelu(h0.v[k].x), h0.v[k].y = bit_gelu(h0.v[k].y);
+        h1.v[k].x = bit_gelu(h1.v[k].x), h1.v[k].y = bit_gelu(h1.v[k].y);
+      }
+      bit_matvec2<kBitC>(reinterpret_cast<const float*>(h0.v), reinterpret_cast<const float*>(h1.v), w2t + half * kBitC * kBitC, kBitC, x0, x1);
     }
   }
-  if (live) {
-    __nv_bfloat16* o = dst + static_cast<size_t>(img) * dst_c8 * hw * 8;
+  __nv_bfloat16* o = dst + static_cast<size_t>(img) * dst_c8 * hw * 8;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(o + (static_cast<size_t>(g) * hw + pix) * 8) = pack8(x + 8 * g);
+  for (int g = 0; g < 4; ++g) {
+    if (pix0 < hw) *reinterpret_cast<uint4*>(o + (static_cast<size_t>(g) * hw + pix0) * 8) = pack8(reinterpret_cast<const float*>(x0.v + 4 * g));
+    if (pix1 < hw) *reinterpret_cast<uint4*>(o + (static_cast<size_t>(g) * hw + pix1) * 8) = pack8(reinterpret_cast<const float*>(x1.v + 4 * g));
   }
 }
 

@@ -149,6 +149,8 @@ struct BitOp {
   std::vector<float> w;        // conv_a | pos | enc | dec
   float* w_dev = nullptr;
   float* tokens = nullptr;     // [2*chunk][L][c]
+  float* tok_mixed = nullptr;  // [chunk][2L][c] after the encoder
+  size_t coef_smem = 0;
   float* coef = nullptr;       // [2*chunk][n_dec][A | Bm]
   size_t mixer_smem = 0;
 };
@@ -378,9 +380,12 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
       const float* enc = pos + 2 * stcd::kBitL * stcd::kBitC;
       const float* dec = enc + (size_t)k.d.n_enc * stcd::bit_enc_size(k.d.inner_enc);
       stcd::bit_tokenizer_kernel<<<imgs, 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, conv_a, k.tokens, ts.c / 8, hw);
-      stcd::bit_token_mixer_kernel<<<plan->chunk, 256, k.mixer_smem, st>>>(k.tokens, pos, enc, dec, k.coef, plan->chunk, k.d.n_enc, k.d.n_dec,
-                                                                          k.d.inner_enc, k.d.inner_dec, 1.f / sqrtf((float)stcd::kBitC));
-      stcd::bit_decoder_kernel<<<dim3((hw + 255) / 256, imgs), 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, dec, k.coef,
+      const float scale = 1.f / sqrtf((float)stcd::kBitC);     // dim ** -0.5 with dim = 32 (help_funcs.py:74,118), not dim_head
+      stcd::bit_token_mixer_kernel<<<plan->chunk, 256, k.mixer_smem, st>>>(k.tokens, pos, enc, k.tok_mixed, plan->chunk, k.d.n_enc,
+                                                                          k.d.inner_enc, scale);
+      stcd::bit_coef_kernel<<<dim3(plan->chunk, k.d.n_dec), 256, k.coef_smem, st>>>(k.tok_mixed, dec, k.coef, plan->chunk, k.d.n_dec,
+                                                                                   k.d.inner_dec, scale);
+      stcd::bit_decoder_kernel<<<dim3((hw + 2 * stcd::kBitDecThreads - 1) / (2 * stcd::kBitDecThreads), imgs), stcd::kBitDecThreads, 0, st>>>((const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, dec, k.coef,
                                                                             ts.c / 8, td.c / 8, hw, k.d.n_dec, k.d.inner_dec, k.d.softmax);
       CUDA_TRY(cudaGetLastError());
     } else if (o.kind == 12) {
@@ -552,6 +557,7 @@ void stcd_plan_destroy(stcd_plan* plan) {
   for (BitOp& k : plan->bits) {
     if (k.w_dev) cudaFree(k.w_dev);
     if (k.tokens) cudaFree(k.tokens);
+    if (k.tok_mixed) cudaFree(k.tok_mixed);
     if (k.coef) cudaFree(k.coef);
   }
   for (GateOp& k : plan->gates) {
@@ -866,7 +872,8 @@ int stcd_plan_add_bit_transformer(stcd_plan* plan, int src_tensor, int dst_tenso
   k.w.insert(k.w.end(), d->enc, d->enc + (size_t)d->n_enc * stcd::bit_enc_size(d->inner_enc));
   k.w.insert(k.w.end(), d->dec, d->dec + (size_t)d->n_dec * stcd::bit_dec_size(d->inner_dec));
   k.d.conv_a = k.d.pos = k.d.enc = k.d.dec = nullptr;
-  k.mixer_smem = sizeof(float) * (size_t)std::max(8 * 3 * d->inner_enc, 2 * 8 * d->inner_dec);
+  k.mixer_smem = sizeof(float) * (size_t)(8 * 3 * d->inner_enc);
+  k.coef_smem = sizeof(float) * (size_t)(2 * 8 * d->inner_dec);
   plan->bits.push_back(std::move(k));
   plan->ops.push_back({13, (int)plan->bits.size() - 1});
   return (int)plan->ops.size() - 1;
@@ -1402,7 +1409,9 @@ int stcd_plan_finalize(stcd_plan* plan) {
     CUDA_TRY(cudaMemcpy(k.w_dev, k.w.data(), k.w.size() * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&k.tokens, (size_t)2 * plan->chunk * stcd::kBitL * stcd::kBitC * sizeof(float)));
     CUDA_TRY(cudaMalloc(&k.coef, (size_t)2 * plan->chunk * k.d.n_dec * stcd::kBitCoef * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&k.tok_mixed, (size_t)plan->chunk * 2 * stcd::kBitL * stcd::kBitC * sizeof(float)));
     CUDA_TRY(cudaFuncSetAttribute(stcd::bit_token_mixer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.mixer_smem));
+    CUDA_TRY(cudaFuncSetAttribute(stcd::bit_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.coef_smem));
   }
   for (GateOp& k : plan->gates) {
     const Tensor& ts = plan->tensors[k.src];
@@ -1493,7 +1502,7 @@ int64_t stcd_plan_launches(const stcd_plan* plan, int n_pairs) {
   const int64_t chunks = (n_pairs + plan->chunk - 1) / plan->chunk;
   int64_t per_chunk = (int64_t)plan->ops.size() + (int64_t)plan->ecams.size();  // an ECAM head op is two kernels
   per_chunk += (int64_t)plan->gates.size();                                    // a channel gate is two kernels
-  per_chunk += 2 * (int64_t)plan->bits.size();                                 // tokenizer + mixer + decoder
+  per_chunk += 3 * (int64_t)plan->bits.size();                                 // tokenizer + mixer + coefficients + decoder
   for (const GraphOp& g : plan->graphs) per_chunk += 3 + (g.r > 1 ? 2 : 0);     // unpack, [pool], norm, [norm y], kNN, max-relative
   return chunks * per_chunk;
 }

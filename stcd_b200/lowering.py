@@ -275,8 +275,8 @@ def bit_enc_fields(c: int, inner: int, mlp: int):
 
 
 def bit_dec_fields(c: int, inner: int, mlp: int):
-    """One decoder layer; the feed-forward weights are stored TRANSPOSED ([in, out]) so the per-pixel kernel reads rows."""
-    return [("ln1_g", (c,)), ("ln1_b", (c,)), ("wq", (inner, c)), ("wk", (inner, c)), ("wv", (inner, c)), ("wout", (c, inner)),
+    """One decoder layer; to_out and the feed-forward weights are stored TRANSPOSED ([in, out]): the kernels read rows."""
+    return [("ln1_g", (c,)), ("ln1_b", (c,)), ("wq", (inner, c)), ("wk", (inner, c)), ("wv", (inner, c)), ("woutt", (inner, c)),
             ("bout", (c,)), ("ln2_g", (c,)), ("ln2_b", (c,)), ("w1t", (c, mlp)), ("b1", (mlp,)), ("w2t", (mlp, c)), ("b2", (c,))]
 
 

@@ -11,7 +11,12 @@ pairs = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 H = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 chunk = int(sys.argv[4]) if len(sys.argv) > 4 else pairs
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 1
-net = CLASSES[name]("resnet34") if name == "SegCD" else CLASSES[name](3, 2)
+if name == "SegCD":
+    net = CLASSES[name]("resnet34")
+elif name == "BASE_Transformer":        # registry key base_transformer_pos_s4_dd8
+    net = CLASSES[name](3, 2, with_pos="learned", resnet_stages_num=4, token_len=4, enc_depth=1, dec_depth=8)
+else:
+    net = CLASSES[name](3, 2)
 net = synth.prepare_(net.eval(), name).cuda()
 net.chunk_pairs = chunk
 x1, x2 = synth.image_pairs(pairs, H, H)
