@@ -62,6 +62,9 @@ WORKLOADS = {
     "bit_dd8_256_b32": dict(net="BASE_Transformer", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=32,
                             desc="BIT base_transformer_pos_s4_dd8 (ResNet-18 stages 1-3, 4 semantic tokens, 1 encoder + 8 decoder layers) "
                                  "256x256 RGB pairs, batch 32 per GPU, bf16 convs + fp32 token path"),
+    "ifnet_256_b16": dict(net="DSIFN", n_class=1, h=256, w=256, batch=16, kind="sigmoid", chunk=16,
+                          desc="IFNet / DSIFN (shared VGG16 features, channel + spatial attention difference decoder) 256x256 RGB pairs, "
+                               "batch 16 per GPU, bf16, change = sigmoid(out) > 0.5"),
     "segcd_r34_256_b64": dict(net="SegCD", n_class=1, h=256, w=256, batch=64, kind="sigmoid", chunk=16,
                               desc="smp SegCD (Unet, ResNet-34 Siamese encoder) 256x256 RGB pairs, batch 64 per GPU, bf16"),
 }
@@ -73,6 +76,8 @@ def build_net(wl):
     from stcd_b200.networks import CLASSES
     if wl["net"] == "SegCD":
         return synth.prepare_(CLASSES["SegCD"](wl.get("encoder", "resnet34"), classes=wl["n_class"]).eval(), "SegCD")
+    if wl["net"] == "DSIFN":
+        return synth.prepare_(CLASSES["DSIFN"]().eval(), "DSIFN")
     if wl["net"] == "BASE_Transformer":
         net = CLASSES["BASE_Transformer"](3, wl["n_class"], with_pos="learned", resnet_stages_num=4, token_len=4, enc_depth=1, dec_depth=8)
         return synth.prepare_(net.eval(), "BASE_Transformer")
@@ -99,6 +104,8 @@ def oracle_forward(wl, sd, x1, x2):
         return nets.dtcdscn_forward(sd, x1, x2)
     if wl["net"] == "BASE_Transformer":
         return nets.bit_forward(sd, x1, x2, stages=4)
+    if wl["net"] == "DSIFN":
+        return nets.dsifn_forward(sd, x1, x2)
     raise KeyError(wl["net"])
 
 

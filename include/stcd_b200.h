@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 13
+#define STCD_ABI_VERSION 14
 
 enum stcd_status {
   STCD_OK = 0,
@@ -214,6 +214,18 @@ typedef struct {
   const float* dec;
 } stcd_bit_desc;
 int stcd_plan_add_bit_transformer(stcd_plan* plan, int src_tensor, int dst_tensor, const stcd_bit_desc* desc);
+
+/* DSIFN's channel attention over a virtual concat (models/DSIFN.py:24-36 and `x = self.caK(x) * x`, :140,154,166,178):
+ * dst[1*chunk, h, w, sum(src_c)] = cat(srcs) * sigmoid(fc2(relu(fc1(avgpool))) + fc2(relu(fc1(maxpool)))).
+ * src i = stream src_streams[i] (0 / 1) of plan tensor src_tensors[i], its first src_c[i] channels (multiples of 8); n_src <= 4.
+ * fc1 HOST fp32 [hid][C], fc2 HOST fp32 [C][hid] (bias-free 1x1 convs); C <= 2048, hid <= 256. */
+int stcd_plan_add_channel_attention(stcd_plan* plan, const int* src_tensors, const int* src_streams, const int* src_c, int n_src,
+                                    int dst_tensor, int hid, const float* fc1, const float* fc2);
+
+/* DSIFN's spatial attention followed by its BatchNorm (models/DSIFN.py:39-51 and `x = bn_saK(saK(x) * x)`, :131-132 ...):
+ * dst = (src * sigmoid(conv7x7([mean_c src, max_c src]))) * scale + shift.  w HOST fp32 [2][7][7], scale / shift HOST fp32 [c]. */
+int stcd_plan_add_spatial_gate(stcd_plan* plan, int src_tensor, int dst_tensor, int c, const float* w, const float* scale,
+                               const float* shift);
 
 /* dst = sum of n <= 5 plan tensors of identical shape (Dblock.forward: x + d1 + d2 + d3 + d4, models/DTCDSCN.py:65-71) */
 int stcd_plan_add_sum(stcd_plan* plan, const int* src_tensors, int n, int dst_tensor);

@@ -277,6 +277,19 @@ def run_aux(op, T, chunk, ext, nv):
     if isinstance(op, L.BitTransformerSpec):
         run_bit_transformer(op, T, chunk)
         return None
+    if isinstance(op, L.ChannelAttentionSpec):
+        x = torch.cat([T[t][s_ * chunk: (s_ + 1) * chunk, :, :, :c_] for (t, s_, c_) in op.srcs], dim=-1)      # [chunk, h, w, C]
+        fc1, fc2 = torch.from_numpy(op.fc1), torch.from_numpy(op.fc2)
+        hid = torch.relu(x.mean(dim=(1, 2)) @ fc1.T) + torch.relu(x.amax(dim=(1, 2)) @ fc1.T)
+        T[op.dst][...] = _bf16(x * torch.sigmoid(hid @ fc2.T)[:, None, None, :])
+        return None
+    if isinstance(op, L.SpatialGateSpec):
+        import torch.nn.functional as F
+        x = T[op.src][..., : op.c]
+        m = torch.stack([x.mean(dim=-1), x.amax(dim=-1)], dim=1)                                   # [n, 2, h, w]
+        g = torch.sigmoid(F.conv2d(m, torch.from_numpy(op.w)[None], None, padding=3))[:, 0, :, :, None]
+        T[op.dst][..., : op.c] = _bf16(x * g * torch.from_numpy(op.scale) + torch.from_numpy(op.shift))
+        return None
     if isinstance(op, L.SumSpec):
         T[op.dst][...] = _bf16(sum(T[s_] for s_ in op.srcs))
         return None

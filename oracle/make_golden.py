@@ -42,13 +42,19 @@ CASES = {
     # The backbone's checkpoint download is skipped (refimport.disable_pretrained_download); weights are the harness' draw.
     "bit_dd8": ("models.networks", "BASE_Transformer", (3, 2, "learned", 4, 4, True, 1, 8), 2, 64, 96),
     "bit_resnet18": ("models.networks", "ResNet", (3, 2), 2, 64, 96),
+    # IFNet = DSIFN(base, base) with ONE shared vgg16_base (models/networks.py:164-166); args = () -> built by _build_ifnet
+    "ifnet": ("models.DSIFN", "DSIFN", (), 2, 64, 96),
 }
 
 
 def reference_net(case: str):
     mod, cls, args, *_ = CASES[case]
-    if mod == "models.networks":
+    if mod in ("models.networks", "models.DSIFN"):
         refimport.disable_pretrained_download()
+    if cls == "DSIFN":
+        m = refimport.ref_module(mod)
+        base = m.vgg16_base()
+        return synth.prepare_(m.DSIFN(base, base).eval(), cls)
     net = getattr(refimport.ref_module(mod), cls)(*args).eval()
     return synth.prepare_(net, cls)
 

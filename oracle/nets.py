@@ -495,3 +495,59 @@ def bit_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor, stages: int = 4, hea
     x = F.interpolate(x, scale_factor=4, mode="bilinear")           # self.upsamplex4 (align_corners unset -> False)
     x = F.relu(_bn(sd, "classifier.1", F.conv2d(x, sd["classifier.0.weight"], None, padding=1)))
     return F.conv2d(x, sd["classifier.3.weight"], sd["classifier.3.bias"], padding=1)
+
+
+# ------------------------------------------------------------------------------------------
+# IFNet / DSIFN (models/DSIFN.py): shared VGG16 features, deeply supervised difference decoder with channel / spatial attention
+_VGG_CONVS = (0, 2, 5, 7, 10, 12, 14, 17, 19, 21, 24, 26, 28)        # torchvision vgg16().features[:30]: conv indices
+_VGG_POOLS = (4, 9, 16, 23)
+_VGG_TAPS = (3, 8, 15, 22, 29)
+
+
+def _vgg16_features(sd: SD, pre: str, x: torch.Tensor) -> List[torch.Tensor]:
+    """vgg16_base.forward, models/DSIFN.py:15-21: outputs of features[3, 8, 15, 22, 29] (the ReLUs closing each block)."""
+    outs = []
+    for i in range(30):
+        if i in _VGG_CONVS:
+            x = F.relu(F.conv2d(x, sd[f"{pre}.features.{i}.weight"], sd[f"{pre}.features.{i}.bias"], padding=1))
+        elif i in _VGG_POOLS:
+            x = F.max_pool2d(x, kernel_size=2, stride=2)
+        if i in _VGG_TAPS:
+            outs.append(x)
+    return outs
+
+
+def _dsifn_conv_bn(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """conv2d_bn, models/DSIFN.py:54-60: conv3x3 -> PReLU -> BatchNorm (-> Dropout: identity in eval mode)."""
+    x = F.prelu(F.conv2d(x, sd[f"{pre}.0.weight"], sd[f"{pre}.0.bias"], padding=1), sd[f"{pre}.1.weight"])
+    return _bn(sd, f"{pre}.2", x)
+
+
+def _dsifn_ca(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """ChannelAttention.forward, models/DSIFN.py:32-36."""
+    def fc(v):
+        return F.conv2d(F.relu(F.conv2d(v, sd[f"{pre}.fc1.weight"])), sd[f"{pre}.fc2.weight"])
+    return torch.sigmoid(fc(F.adaptive_avg_pool2d(x, 1)) + fc(F.adaptive_max_pool2d(x, 1)))
+
+
+def _dsifn_sa(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """SpatialAttention.forward, models/DSIFN.py:45-51."""
+    m = torch.cat([x.mean(dim=1, keepdim=True), x.max(dim=1, keepdim=True)[0]], dim=1)
+    return torch.sigmoid(F.conv2d(m, sd[f"{pre}.conv1.weight"], None, padding=3))
+
+
+def dsifn_forward(sd: SD, t1: torch.Tensor, t2: torch.Tensor) -> torch.Tensor:
+    """DSIFN.forward, models/DSIFN.py:119-188: returns `out` = o5_conv4(...) (the four deep-supervision sigmoids are appended
+    to a list the reference discards)."""
+    f1, f2 = _vgg16_features(sd, "t1_base", t1), _vgg16_features(sd, "t2_base", t2)
+    x = torch.cat((f1[4], f2[4]), dim=1)
+    x = _dsifn_conv_bn(sd, "o1_conv2", _dsifn_conv_bn(sd, "o1_conv1", x))
+    x = _bn(sd, "bn_sa1", _dsifn_sa(sd, "sa1", x) * x)
+    for b, n_convs in ((2, 3), (3, 3), (4, 3), (5, 3)):
+        x = F.conv_transpose2d(x, sd[f"trans_conv{b - 1}.weight"], sd[f"trans_conv{b - 1}.bias"], stride=2)
+        x = torch.cat((x, f1[5 - b], f2[5 - b]), dim=1)
+        x = _dsifn_ca(sd, f"ca{b}", x) * x
+        for i in range(n_convs):
+            x = _dsifn_conv_bn(sd, f"o{b}_conv{i + 1}", x)
+        x = _bn(sd, f"bn_sa{b}", _dsifn_sa(sd, f"sa{b}", x) * x)
+    return F.conv2d(x, sd["o5_conv4.weight"], sd["o5_conv4.bias"])

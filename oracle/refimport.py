@@ -143,6 +143,10 @@ def disable_pretrained_download() -> None:
     orig = r._resnet
     r._resnet = lambda arch, block, layers, pretrained, progress, **kw: orig(arch, block, layers, False, progress, **kw)
     r._stcd_patched = True
+    # IFNet: ``vgg16(pretrained=True)`` from torchvision (models/DSIFN.py:12): same treatment
+    d = ref_module("models.DSIFN")
+    import torchvision
+    d.vgg16 = lambda pretrained=True: torchvision.models.vgg16(weights=None)
 
 
 def segmentation_metric_class():

@@ -134,7 +134,7 @@ class EcamDesc(C.Structure):
     ]
 
 
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -155,6 +155,10 @@ SYMBOLS = [
     ("stcd_plan_add_channel_gate", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                              C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]),
     ("stcd_plan_add_bit_transformer", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    ("stcd_plan_add_channel_attention", C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int,
+                                                  C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    ("stcd_plan_add_spatial_gate", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                             C.POINTER(C.c_float)]),
     ("stcd_plan_add_sum", C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int]),
     ("stcd_plan_add_graph_conv", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     ("stcd_plan_add_layernorm", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),

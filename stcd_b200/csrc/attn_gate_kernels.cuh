@@ -1,0 +1,173 @@
+// K13: DSIFN's attention gates (models/DSIFN.py:24-51) as bandwidth kernels on bf16 plan tensors [img][c/8][h*w][8], fp32 arithmetic.
+//
+//   channel attention  `ca(x) * x` over a VIRTUAL concat x = cat(decoder map, T1 feature, T2 feature) (:138-140 ...): per segment
+//                      chan_stats_kernel (sum + max per image and channel, one warp per (image, 8 channels, pixel range)), once
+//                      ca_fc_kernel (sigmoid(fc2(relu(fc1 avg)) + fc2(relu(fc1 max))), one CTA per image), per segment
+//                      ca_apply_kernel, which writes the scaled segment into the materialised concat the next conv reads.
+//   spatial attention  `bn(sa(x) * x)` (:131-132 ...): sa_stats_kernel (mean and max over the channels of every pixel) and
+//                      sa_apply_kernel (7x7 conv over the 2-channel statistics map staged in shared memory, sigmoid, gate,
+//                      folded BatchNorm).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "transformer_kernels.cuh"
+
+namespace stcd {
+
+constexpr int kCaMaxC = 2048, kCaMaxH = 256;
+
+// one warp per (pixel range, 8-channel group, image) of ONE segment; partial_{sum,max}[(img * ranges + r) * c_tot + c_off + ...]
+__global__ void __launch_bounds__(256) chan_stats_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ psum,
+                                                         float* __restrict__ pmax, int c_seg, int src_c8, int hw, int ranges, int n_items,
+                                                         int c_tot, int c_off) {
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (item >= n_items) return;
+  const int g8 = c_seg >> 3;
+  const int r = item % ranges, g = (item / ranges) % g8, b = item / (ranges * g8);
+  const int per = (hw + ranges - 1) / ranges;
+  const int p0 = r * per, p1 = min(hw, p0 + per);
+  float s[8], m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f, m[j] = -3.0e38f;
+  const __nv_bfloat16* base = src + (static_cast<size_t>(b) * src_c8 + g) * static_cast<size_t>(hw) * 8;
+#pragma unroll 4
+  for (int px = p0 + lane; px < p1; px += 32) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(px) * 8)), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += v[j], m[j] = fmaxf(m[j], v[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+      m[j] = fmaxf(m[j], __shfl_xor_sync(0xffffffffu, m[j], o));
+    }
+  }
+  if (lane < 8) {
+    float a = s[0], mm = m[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) a = lane == j ? s[j] : a, mm = lane == j ? m[j] : mm;
+    const size_t o = (static_cast<size_t>(b) * ranges + r) * c_tot + c_off + g * 8 + lane;
+    psum[o] = a;
+    pmax[o] = mm;
+  }
+}
+
+// grid = images, 256 threads: gate[img][c] = sigmoid(fc2 (relu(fc1 avg) + relu(fc1 max)))   (fc2 is linear and bias-free)
+__global__ void __launch_bounds__(256) ca_fc_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, const float* __restrict__ fc1,
+                                                    const float* __restrict__ fc2, float* __restrict__ gate, int C, int hid, int hw, int ranges) {
+  __shared__ float s_avg[kCaMaxC], s_max[kCaMaxC], s_hid[kCaMaxH];
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, m = -3.0e38f;
+    for (int r = 0; r < ranges; ++r) {
+      a += psum[(static_cast<size_t>(b) * ranges + r) * C + c];
+      m = fmaxf(m, pmax[(static_cast<size_t>(b) * ranges + r) * C + c]);
+    }
+    s_avg[c] = a / static_cast<float>(hw);
+    s_max[c] = m;
+  }
+  __syncthreads();
+  for (int u = warp; u < hid; u += 8) {
+    float a = 0.f, m = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float w = __ldg(fc1 + static_cast<size_t>(u) * C + c);
+      a = fmaf(w, s_avg[c], a);
+      m = fmaf(w, s_max[c], m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      m += __shfl_xor_sync(0xffffffffu, m, o);
+    }
+    if (lane == 0) s_hid[u] = fmaxf(a, 0.f) + fmaxf(m, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int u = 0; u < hid; ++u) a = fmaf(__ldg(fc2 + static_cast<size_t>(c) * hid + u), s_hid[u], a);
+    gate[static_cast<size_t>(b) * C + c] = 1.f / (1.f + expf(-a));
+  }
+}
+
+// dst[img][c_off/8 + g][pix] = src[img][g][pix] * gate[img][c_off + 8 g ..]: one segment, grid-stride over 16-byte vectors
+__global__ void __launch_bounds__(256) ca_apply_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                       const float* __restrict__ gate, int imgs, int c_seg, int src_c8, int dst_c8, int hw,
+                                                       int c_tot, int c_off) {
+  const int g8 = c_seg >> 3;
+  const size_t total = static_cast<size_t>(imgs) * g8 * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int pix = static_cast<int>(i % hw);
+    const int g = static_cast<int>((i / hw) % g8), b = static_cast<int>(i / (static_cast<size_t>(hw) * g8));
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(src + ((static_cast<size_t>(b) * src_c8 + g) * hw + pix) * 8)), v);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(b) * c_tot + c_off + g * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<size_t>(b) * c_tot + c_off + g * 8) + 1);
+    v[0] *= g0.x, v[1] *= g0.y, v[2] *= g0.z, v[3] *= g0.w, v[4] *= g1.x, v[5] *= g1.y, v[6] *= g1.z, v[7] *= g1.w;
+    *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(b) * dst_c8 + (c_off >> 3) + g) * hw + pix) * 8) = pack8(v);
+  }
+}
+
+// stats[img][pix] = (mean_c x, max_c x); one thread per pixel
+__global__ void __launch_bounds__(256) sa_stats_kernel(const __nv_bfloat16* __restrict__ src, float2* __restrict__ stats, int C, int src_c8, int hw) {
+  const int b = blockIdx.y, pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= hw) return;
+  const __nv_bfloat16* s = src + (static_cast<size_t>(b) * src_c8 * hw + pix) * 8;
+  float sum = 0.f, mx = -3.0e38f;
+  for (int g = 0; g < (C >> 3); ++g) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(s + static_cast<size_t>(g) * hw * 8)), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += v[j], mx = fmaxf(mx, v[j]);
+  }
+  stats[static_cast<size_t>(b) * hw + pix] = make_float2(sum / static_cast<float>(C), mx);
+}
+
+// block (32, 8) pixels; grid (ceil(w/32), ceil(h/8), images).  wgt: [2][7][7] (mean plane, max plane), scale/shift: folded BN
+constexpr int kSaTW = 32, kSaTH = 8;
+__global__ void __launch_bounds__(kSaTW* kSaTH) sa_apply_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                const float2* __restrict__ stats, const float* __restrict__ wgt,
+                                                                const float* __restrict__ scale, const float* __restrict__ shift, int C,
+                                                                int src_c8, int dst_c8, int h, int w) {
+  __shared__ float2 s_t[kSaTH + 6][kSaTW + 6];
+  __shared__ float s_w[98];
+  const int b = blockIdx.z, x0 = blockIdx.x * kSaTW, y0 = blockIdx.y * kSaTH, hw = h * w;
+  const int tid = threadIdx.y * kSaTW + threadIdx.x;
+  if (tid < 98) s_w[tid] = wgt[tid];
+  for (int i = tid; i < (kSaTH + 6) * (kSaTW + 6); i += kSaTW * kSaTH) {
+    const int ty = i / (kSaTW + 6), tx = i % (kSaTW + 6);
+    const int gy = y0 + ty - 3, gx = x0 + tx - 3;
+    s_t[ty][tx] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? stats[static_cast<size_t>(b) * hw + gy * w + gx] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x >= w || y >= h) return;
+  float a = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const float2 t = s_t[threadIdx.y + ky][threadIdx.x + kx];
+      a = fmaf(t.x, s_w[ky * 7 + kx], a);
+      a = fmaf(t.y, s_w[49 + ky * 7 + kx], a);
+    }
+  }
+  const float gs = 1.f / (1.f + expf(-a));
+  const int pix = y * w + x;
+  const __nv_bfloat16* s = src + (static_cast<size_t>(b) * src_c8 * hw + pix) * 8;
+  __nv_bfloat16* o = dst + (static_cast<size_t>(b) * dst_c8 * hw + pix) * 8;
+  for (int g = 0; g < (C >> 3); ++g) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(s + static_cast<size_t>(g) * hw * 8)), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j] * gs, __ldg(scale + g * 8 + j), __ldg(shift + g * 8 + j));
+    *reinterpret_cast<uint4*>(o + static_cast<size_t>(g) * hw * 8) = pack8(v);
+  }
+}
+
+}  // namespace stcd

@@ -22,6 +22,7 @@
 #include "graph_kernels.cuh"
 #include "transformer_kernels.cuh"
 #include "bit_kernels.cuh"
+#include "attn_gate_kernels.cuh"
 
 namespace {
 
@@ -155,6 +156,22 @@ struct BitOp {
   size_t mixer_smem = 0;
 };
 
+struct ChanAttnOp {
+  int n_src, src[4], stream[4], c[4], dst, c_tot, hid, ranges;
+  std::vector<float> w;        // fc1 | fc2
+  float* w_dev = nullptr;
+  float* psum = nullptr;       // [chunk][ranges][c_tot]
+  float* pmax = nullptr;
+  float* gate = nullptr;       // [chunk][c_tot]
+};
+
+struct SpatialGateOp {
+  int src, dst, c;
+  std::vector<float> w;        // conv [98] | scale [c] | shift [c]
+  float* w_dev = nullptr;
+  float2* stats = nullptr;     // [mult*chunk][h*w]
+};
+
 struct SumOp {
   int src[5], n, dst;
 };
@@ -177,7 +194,7 @@ struct EcamOp {
 };
 
 struct Op {
-  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head, 5 graph conv, 6 bilinear up, 7 layer norm, 8 attention, 9 dw conv, 10 T1 - T2 (abs or signed), 11 channel gate, 12 sum, 13 BIT token path
+  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head, 5 graph conv, 6 bilinear up, 7 layer norm, 8 attention, 9 dw conv, 10 T1 - T2 (abs or signed), 11 channel gate, 12 sum, 13 BIT token path, 14 channel attention, 15 spatial gate
   int idx;
 };
 
@@ -202,6 +219,8 @@ struct stcd_plan {
   std::vector<GateOp> gates;
   std::vector<SumOp> sums;
   std::vector<BitOp> bits;
+  std::vector<ChanAttnOp> chan_attns;
+  std::vector<SpatialGateOp> spatial_gates;
   std::vector<Op> ops;
   uint8_t* workspace = nullptr;
   size_t workspace_bytes = 0;
@@ -369,6 +388,39 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
           k.dst2 >= 0 ? (__nv_bfloat16*)plan->tensors[k.dst2].ptr : nullptr, k.partial, w1, w2, ws, k.c, k.hid, ts.c / 8,
           k.res >= 0 ? plan->tensors[k.res].c / 8 : 0, td.c / 8, k.dst2 >= 0 ? plan->tensors[k.dst2].c / 8 : 0, ts.h, ts.w, k.ranges, k.mode,
           ppb);
+      CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 14) {
+      const ChanAttnOp& k = plan->chan_attns[o.idx];
+      const Tensor& td = plan->tensors[k.dst];
+      const int B = plan->chunk, hw = td.h * td.w;
+      int c_off = 0;
+      for (int i = 0; i < k.n_src; ++i) {
+        const Tensor& ts = plan->tensors[k.src[i]];
+        const __nv_bfloat16* sp = (const __nv_bfloat16*)ts.ptr + (size_t)k.stream[i] * B * ts.c * hw;
+        const int n_items = B * (k.c[i] / 8) * k.ranges;
+        stcd::chan_stats_kernel<<<(n_items + 7) / 8, 256, 0, st>>>(sp, k.psum, k.pmax, k.c[i], ts.c / 8, hw, k.ranges, n_items, k.c_tot, c_off);
+        c_off += k.c[i];
+      }
+      stcd::ca_fc_kernel<<<B, 256, 0, st>>>(k.psum, k.pmax, k.w_dev, k.w_dev + (size_t)k.hid * k.c_tot, k.gate, k.c_tot, k.hid, hw, k.ranges);
+      c_off = 0;
+      for (int i = 0; i < k.n_src; ++i) {
+        const Tensor& ts = plan->tensors[k.src[i]];
+        const __nv_bfloat16* sp = (const __nv_bfloat16*)ts.ptr + (size_t)k.stream[i] * B * ts.c * hw;
+        const size_t total = (size_t)B * (k.c[i] / 8) * hw;
+        stcd::ca_apply_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, 148 * 16)), 256, 0, st>>>(
+            sp, (__nv_bfloat16*)td.ptr, k.gate, B, k.c[i], ts.c / 8, td.c / 8, hw, k.c_tot, c_off);
+        c_off += k.c[i];
+      }
+      CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 15) {
+      const SpatialGateOp& k = plan->spatial_gates[o.idx];
+      const Tensor& ts = plan->tensors[k.src];
+      const Tensor& td = plan->tensors[k.dst];
+      const int B = ts.mult * plan->chunk, hw = ts.h * ts.w;
+      stcd::sa_stats_kernel<<<dim3((hw + 255) / 256, B), 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, k.stats, k.c, ts.c / 8, hw);
+      stcd::sa_apply_kernel<<<dim3((ts.w + stcd::kSaTW - 1) / stcd::kSaTW, (ts.h + stcd::kSaTH - 1) / stcd::kSaTH, B),
+                              dim3(stcd::kSaTW, stcd::kSaTH), 0, st>>>((const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, k.stats, k.w_dev,
+                                                                       k.w_dev + 98, k.w_dev + 98 + k.c, k.c, ts.c / 8, td.c / 8, ts.h, ts.w);
       CUDA_TRY(cudaGetLastError());
     } else if (o.kind == 13) {
       const BitOp& k = plan->bits[o.idx];
@@ -554,6 +606,16 @@ void stcd_plan_destroy(stcd_plan* plan) {
     if (e.w_dev) cudaFree(e.w_dev);
   for (LayerNormOp& k : plan->lns)
     if (k.gb_dev) cudaFree(k.gb_dev);
+  for (ChanAttnOp& k : plan->chan_attns) {
+    if (k.w_dev) cudaFree(k.w_dev);
+    if (k.psum) cudaFree(k.psum);
+    if (k.pmax) cudaFree(k.pmax);
+    if (k.gate) cudaFree(k.gate);
+  }
+  for (SpatialGateOp& k : plan->spatial_gates) {
+    if (k.w_dev) cudaFree(k.w_dev);
+    if (k.stats) cudaFree(k.stats);
+  }
   for (BitOp& k : plan->bits) {
     if (k.w_dev) cudaFree(k.w_dev);
     if (k.tokens) cudaFree(k.tokens);
@@ -876,6 +938,61 @@ int stcd_plan_add_bit_transformer(stcd_plan* plan, int src_tensor, int dst_tenso
   k.coef_smem = sizeof(float) * (size_t)(2 * 8 * d->inner_dec);
   plan->bits.push_back(std::move(k));
   plan->ops.push_back({13, (int)plan->bits.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_channel_attention(stcd_plan* plan, const int* src_tensors, const int* src_streams, const int* src_c, int n_src,
+                                    int dst_tensor, int hid, const float* fc1, const float* fc2) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!src_tensors || !src_streams || !src_c || n_src < 1 || n_src > 4 || !valid_tensor(plan, dst_tensor) || !fc1 || !fc2 || hid < 1 ||
+      hid > stcd::kCaMaxH)
+    return -fail(STCD_ERR_INVALID, "channel attention: 1..4 sources, hid <= %d, non-NULL weights", stcd::kCaMaxH);
+  const Tensor& td = plan->tensors[dst_tensor];
+  ChanAttnOp k;
+  k.n_src = n_src;
+  k.dst = dst_tensor;
+  k.hid = hid;
+  k.c_tot = 0;
+  for (int i = 0; i < n_src; ++i) {
+    if (!valid_tensor(plan, src_tensors[i])) return -fail(STCD_ERR_INVALID, "channel attention: bad tensor id");
+    const Tensor& ts = plan->tensors[src_tensors[i]];
+    if (src_streams[i] < 0 || src_streams[i] >= ts.mult || src_c[i] < 8 || (src_c[i] % 8) || src_c[i] > ts.c || ts.h != td.h || ts.w != td.w)
+      return -fail(STCD_ERR_INVALID, "channel attention: source %d (stream %d, %d channels) does not fit its tensor / the destination", i,
+                   src_streams[i], src_c[i]);
+    k.src[i] = src_tensors[i];
+    k.stream[i] = src_streams[i];
+    k.c[i] = src_c[i];
+    k.c_tot += src_c[i];
+  }
+  if (td.mult != 1 || td.c != k.c_tot || k.c_tot > stcd::kCaMaxC)
+    return -fail(STCD_ERR_INVALID, "channel attention: dst must be [chunk,h,w,%d] (<= %d channels)", k.c_tot, stcd::kCaMaxC);
+  k.ranges = std::max(1, std::min(16, td.h * td.w / stcd::kGateRangePix));
+  k.w.assign(fc1, fc1 + (size_t)hid * k.c_tot);
+  k.w.insert(k.w.end(), fc2, fc2 + (size_t)k.c_tot * hid);
+  plan->chan_attns.push_back(std::move(k));
+  plan->ops.push_back({14, (int)plan->chan_attns.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_spatial_gate(stcd_plan* plan, int src_tensor, int dst_tensor, int c, const float* w, const float* scale, const float* shift) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, src_tensor) || !valid_tensor(plan, dst_tensor) || !w || !scale || !shift)
+    return -fail(STCD_ERR_INVALID, "spatial gate: bad tensor id / NULL weights");
+  const Tensor& ts = plan->tensors[src_tensor];
+  const Tensor& td = plan->tensors[dst_tensor];
+  if (c < 8 || (c % 8) || ts.c < c || td.c < c || ts.h != td.h || ts.w != td.w || ts.mult != td.mult)
+    return -fail(STCD_ERR_INVALID, "spatial gate: c=%d; src and dst must have the same shape", c);
+  SpatialGateOp k;
+  k.src = src_tensor;
+  k.dst = dst_tensor;
+  k.c = c;
+  k.w.assign(w, w + 98);
+  k.w.insert(k.w.end(), scale, scale + c);
+  k.w.insert(k.w.end(), shift, shift + c);
+  plan->spatial_gates.push_back(std::move(k));
+  plan->ops.push_back({15, (int)plan->spatial_gates.size() - 1});
   return (int)plan->ops.size() - 1;
 }
 
@@ -1404,6 +1521,19 @@ int stcd_plan_finalize(stcd_plan* plan) {
   }
   // the 3-stream head instances stage 58 KB: dynamic shared memory above the 48 KB default
   CUDA_TRY(cudaFuncSetAttribute(stcd::segcd_head_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  for (ChanAttnOp& k : plan->chan_attns) {
+    CUDA_TRY(cudaMalloc(&k.w_dev, k.w.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(k.w_dev, k.w.data(), k.w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&k.psum, (size_t)plan->chunk * k.ranges * k.c_tot * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&k.pmax, (size_t)plan->chunk * k.ranges * k.c_tot * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&k.gate, (size_t)plan->chunk * k.c_tot * sizeof(float)));
+  }
+  for (SpatialGateOp& k : plan->spatial_gates) {
+    const Tensor& ts = plan->tensors[k.src];
+    CUDA_TRY(cudaMalloc(&k.w_dev, k.w.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(k.w_dev, k.w.data(), k.w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&k.stats, (size_t)ts.mult * plan->chunk * ts.h * ts.w * sizeof(float2)));
+  }
   for (BitOp& k : plan->bits) {
     CUDA_TRY(cudaMalloc(&k.w_dev, k.w.size() * sizeof(float)));
     CUDA_TRY(cudaMemcpy(k.w_dev, k.w.data(), k.w.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1502,6 +1632,8 @@ int64_t stcd_plan_launches(const stcd_plan* plan, int n_pairs) {
   const int64_t chunks = (n_pairs + plan->chunk - 1) / plan->chunk;
   int64_t per_chunk = (int64_t)plan->ops.size() + (int64_t)plan->ecams.size();  // an ECAM head op is two kernels
   per_chunk += (int64_t)plan->gates.size();                                    // a channel gate is two kernels
+  for (const ChanAttnOp& k : plan->chan_attns) per_chunk += 2 * k.n_src;      // stats + apply per segment, one FC kernel
+  per_chunk += (int64_t)plan->spatial_gates.size();                            // statistics + apply
   per_chunk += 3 * (int64_t)plan->bits.size();                                 // tokenizer + mixer + coefficients + decoder
   for (const GraphOp& g : plan->graphs) per_chunk += 3 + (g.r > 1 ? 2 : 0);     // unpack, [pool], norm, [norm y], kNN, max-relative
   return chunks * per_chunk;

@@ -301,6 +301,30 @@ def bit_unpack(fields, row: np.ndarray) -> Dict[str, torch.Tensor]:
 
 
 @dataclass
+class ChannelAttentionSpec:
+    """dst = cat(srcs) * ca(cat(srcs)), ca = sigmoid(fc2(relu(fc1(avgpool))) + fc2(relu(fc1(maxpool)))) (ChannelAttention,
+    models/DSIFN.py:24-36; `x = self.caK(x) * x`, :140,154,166,178).  The concat is virtual on the input side; dst is the
+    materialised, scaled concat [chunk, h, w, sum(c)] the next conv reads."""
+    name: str
+    srcs: List[Tuple[str, int, int]]     # (tensor, stream, channels)
+    dst: str
+    fc1: np.ndarray                      # float32 [hid][C]
+    fc2: np.ndarray                      # float32 [C][hid]
+
+
+@dataclass
+class SpatialGateSpec:
+    """dst = bn(sa(x) * x), sa = sigmoid(conv7x7([mean_c x, max_c x])) (SpatialAttention, models/DSIFN.py:39-51; :131-132 ...)."""
+    name: str
+    src: str
+    dst: str
+    c: int
+    w: np.ndarray                        # float32 [2][7][7]
+    scale: np.ndarray                    # float32 [c]  folded BatchNorm
+    shift: np.ndarray
+
+
+@dataclass
 class SumSpec:
     """dst = sum of up to five tensors (Dblock.forward, models/DTCDSCN.py:65-71)."""
     name: str
@@ -778,6 +802,12 @@ def op_bytes_per_pair(prog: Program, op) -> int:
     if isinstance(op, SumSpec):
         t = T[op.dst]
         return t.mult * t.c * t.h * t.w * 2 * (len(op.srcs) + 1)
+    if isinstance(op, ChannelAttentionSpec):
+        t = T[op.dst]
+        return t.c * t.h * t.w * 2 * 3                      # every segment read twice, the concat written once
+    if isinstance(op, SpatialGateSpec):
+        t = T[op.src]
+        return t.mult * (op.c * t.h * t.w * 2 * 3 + t.h * t.w * 8 * 2)
     if isinstance(op, BitTransformerSpec):
         t = T[op.src]
         return t.mult * op.c * t.h * t.w * 2 * 3            # tokenizer read + decoder read + write

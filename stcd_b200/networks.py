@@ -17,6 +17,7 @@ from .siamunet import SiamUnet_conc, SiamUnet_cross_conc, SiamUnet_diff, SiamUne
 from .changeformer import ChangeFormerV6
 from .bit import BASE_Transformer, ResNet
 from .changevig import ChangeGNNV1
+from .dsifn import DSIFN, vgg16_base
 from .dtcdscn import CDNet34, CDNet_model
 from .segcd import SegCD
 from .snunet import SNUNet_ECAM
@@ -24,7 +25,7 @@ from .snunet import SNUNet_ECAM
 # registry keys of models/networks.py:144-214 that this library does NOT implement (yet): asking for one
 # raises NotImplementedError like an unknown key does upstream, with the reason.
 _REFERENCE_ONLY = (
-    "IFNet", "ChangeFormerV1", "ChangeFormerV2",
+    "ChangeFormerV1", "ChangeFormerV2",
     "ChangeFormerV3", "ChangeFormerV4", "ChangeFormerV5", "ChangeGNNV2",
     "ChangeGNNV2_sub", "ChangeGNNV2_abs", "ChangeGNNV2_conc", "GNN",
 )
@@ -43,6 +44,7 @@ _REGISTRY = {
                                                               with_pos="learned", enc_depth=1, dec_depth=8),
     "base_transformer_pos_s4_dd8_dedim8": lambda a: BASE_Transformer(input_nc=3, output_nc=2, token_len=4, resnet_stages_num=4,
                                                                      with_pos="learned", enc_depth=1, dec_depth=8, decoder_dim_head=8),
+    "IFNet": lambda a: _ifnet(),                                                   # networks.py:164-166
     "SNUNet": lambda a: SNUNet_ECAM(in_ch=3, out_ch=a.n_class),                    # networks.py:168-169
     "ChangeGNNV1": lambda a: ChangeGNNV1(embed_dim=a.embed_dim),                   # networks.py:199-200
     "ChangeFormerV6": lambda a: ChangeFormerV6(embed_dim=a.embed_dim),             # networks.py:190-191
@@ -55,6 +57,14 @@ CLASSES = {"SiamUnet_diff": SiamUnet_diff, "SiamUnet_conc": SiamUnet_conc, "Siam
            "ChangeGNNV1": ChangeGNNV1, "ChangeFormerV6": ChangeFormerV6,
            "BASE_Transformer": BASE_Transformer, "ResNet": ResNet,
            "CDNet_model": lambda in_channels=3, num_classes=2: CDNet34(in_channels, num_classes)}
+
+
+def _ifnet() -> DSIFN:
+    base_model = vgg16_base()
+    return DSIFN(base_model, base_model)
+
+
+CLASSES["DSIFN"] = _ifnet
 
 
 def register(name: str, ctor) -> None:

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .lowering import (AbsDiffSpec, AttentionSpec, BitTransformerSpec, ChannelGateSpec, SumSpec, BilinearUpSpec, ConvSpec, DWConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec,
+from .lowering import (AbsDiffSpec, AttentionSpec, BitTransformerSpec, ChannelAttentionSpec, ChannelGateSpec, SpatialGateSpec, SumSpec, BilinearUpSpec, ConvSpec, DWConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec,
                        LayerNormSpec, MaxPoolS2DSpec, Program, SegHeadSpec)
 
 
@@ -83,6 +83,18 @@ class Plan:
                     keep[2] = np.zeros(1, np.float32)
                 d.conv_a, d.pos, d.enc, d.dec = (_fptr(a) for a in keep)
                 _lib.check_id(lib.stcd_plan_add_bit_transformer(h, ids[op.src], ids[op.dst], C.byref(d)), f"BIT transformer {op.name}")
+            elif isinstance(op, ChannelAttentionSpec):
+                n = len(op.srcs)
+                ts = (C.c_int * n)(*[ids[s_[0]] for s_ in op.srcs])
+                ss = (C.c_int * n)(*[s_[1] for s_ in op.srcs])
+                cs = (C.c_int * n)(*[s_[2] for s_ in op.srcs])
+                fc1, fc2 = np.ascontiguousarray(op.fc1, np.float32), np.ascontiguousarray(op.fc2, np.float32)
+                _lib.check_id(lib.stcd_plan_add_channel_attention(h, ts, ss, cs, n, ids[op.dst], fc1.shape[0], _fptr(fc1), _fptr(fc2)),
+                              f"channel attention {op.name}")
+            elif isinstance(op, SpatialGateSpec):
+                w_, sc_, sh_ = (np.ascontiguousarray(a, np.float32) for a in (op.w, op.scale, op.shift))
+                _lib.check_id(lib.stcd_plan_add_spatial_gate(h, ids[op.src], ids[op.dst], op.c, _fptr(w_), _fptr(sc_), _fptr(sh_)),
+                              f"spatial gate {op.name}")
             elif isinstance(op, SumSpec):
                 arr = (C.c_int * len(op.srcs))(*[ids[s_] for s_ in op.srcs])
                 _lib.check_id(lib.stcd_plan_add_sum(h, arr, len(op.srcs), ids[op.dst]), f"sum {op.name}")

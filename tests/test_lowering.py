@@ -189,6 +189,34 @@ def test_bit_program_matches_oracle(variant):
         net.lower(100, 96)
 
 
+def test_dsifn_program_matches_oracle():
+    """IFNet (DSIFN): shared VGG16 with max-pools fused into the conv epilogues, conv -> PReLU -> BN epilogues, channel attention
+    over a virtual concat, spatial attention + BN, k2 s2 transposed convs as single-tap phases -- through the emulator."""
+    from stcd_b200 import dsifn, networks
+    net = synth.prepare_(networks.CLASSES["DSIFN"]().eval(), "DSIFN")
+    x1, x2 = synth.image_pairs(3, 64, 96)
+    with torch.no_grad():
+        y = nets.dsifn_forward(net.state_dict(), x1, x2)
+    prog = net.lower(64, 96)
+    ye = emulate.run_program(prog, x1, x2, chunk=2)[0]
+    assert ye.shape == y.shape == (3, 1, 64, 96) and (ye - y).abs().max().item() < BF16_TOL
+    agree = (ye > 0) == (y > 0)                              # sigmoid(out) > 0.5
+    assert agree[y.abs() > BF16_TOL].float().mean().item() >= 0.999
+    assert 0.02 < (y > 0).float().mean().item() < 0.98, "degenerate change map"
+    convs = [o for o in prog.ops if isinstance(o, L.ConvSpec)]
+    # 13 VGG convs + 2 + 3 x 4 conv2d_bn + 4 transposed convs + the 1x1 head; 4 channel attentions, 5 spatial gates
+    assert len(convs) == 13 + 14 + 4 + 1
+    assert sum(isinstance(o, L.ChannelAttentionSpec) for o in prog.ops) == 4 and sum(isinstance(o, L.SpatialGateSpec) for o in prog.ops) == 5
+    assert sum(o.out_pool is not None for o in convs) == 4, "the four max-pools ride in the producing conv's epilogue"
+    # the deep-supervision side heads are parameters only (their outputs are discarded upstream, DSIFN.py:133,147,159,171)
+    assert "o1_conv3.weight" in net.state_dict() and not any(o.name == "o1_conv3" for o in prog.ops)
+    other = dsifn.DSIFN(dsifn.vgg16_base(), dsifn.vgg16_base())
+    with pytest.raises(NotImplementedError):
+        other.lower(64, 64)                                  # two different bases: not the registry's network
+    with pytest.raises(ValueError):
+        net.lower(72, 64)
+
+
 def test_changegnn_program_matches_oracle():
     """Config C4's net: ViG Grapher blocks (graph op + grouped conv folded into a dense virtual-concat conv), GELU /
     PReLU-before-BN epilogues, bilinear resizes, ConvTranspose2d(k4, s2) phases -- checked through the emulator."""

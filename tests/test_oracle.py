@@ -44,6 +44,8 @@ def _oracle_forward(case, sd, x1, x2):
         return [nets.bit_forward(sd, x1, x2, stages=4)]
     if cls == "ResNet":
         return [nets.bit_forward(sd, x1, x2, stages=5)]
+    if cls == "DSIFN":
+        return [nets.dsifn_forward(sd, x1, x2)]
     raise KeyError(cls)
 
 
