@@ -58,11 +58,13 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const __nv_bfloat16* __
   }
 }
 
-// grid = images, 256 threads: gate[img][c] = sigmoid(fc2 (relu(fc1 avg) + relu(fc1 max)))   (fc2 is linear and bias-free)
+// grid (ceil(C / 256), images), 256 threads: gate[img][c] = sigmoid(fc2 (relu(fc1 avg) + relu(fc1 max)))  (fc2 is linear and
+// bias-free).  Every CTA redoes the hidden layer (hid x C MACs, warp-cooperative, coalesced fc1 rows) and finishes 256 channels;
+// fc2t is fc2 transposed to [hid][C] so those reads coalesce too.
 __global__ void __launch_bounds__(256) ca_fc_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, const float* __restrict__ fc1,
-                                                    const float* __restrict__ fc2, float* __restrict__ gate, int C, int hid, int hw, int ranges) {
+                                                    const float* __restrict__ fc2t, float* __restrict__ gate, int C, int hid, int hw, int ranges) {
   __shared__ float s_avg[kCaMaxC], s_max[kCaMaxC], s_hid[kCaMaxH];
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f, m = -3.0e38f;
     for (int r = 0; r < ranges; ++r) {
@@ -88,9 +90,10 @@ __global__ void __launch_bounds__(256) ca_fc_kernel(const float* __restrict__ ps
     if (lane == 0) s_hid[u] = fmaxf(a, 0.f) + fmaxf(m, 0.f);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
     float a = 0.f;
-    for (int u = 0; u < hid; ++u) a = fmaf(__ldg(fc2 + static_cast<size_t>(c) * hid + u), s_hid[u], a);
+    for (int u = 0; u < hid; ++u) a = fmaf(__ldg(fc2t + static_cast<size_t>(u) * C + c), s_hid[u], a);
     gate[static_cast<size_t>(b) * C + c] = 1.f / (1.f + expf(-a));
   }
 }

@@ -158,7 +158,7 @@ struct BitOp {
 
 struct ChanAttnOp {
   int n_src, src[4], stream[4], c[4], dst, c_tot, hid, ranges;
-  std::vector<float> w;        // fc1 | fc2
+  std::vector<float> w;        // fc1 [hid][C] | fc2^T [hid][C]
   float* w_dev = nullptr;
   float* psum = nullptr;       // [chunk][ranges][c_tot]
   float* pmax = nullptr;
@@ -401,7 +401,7 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
         stcd::chan_stats_kernel<<<(n_items + 7) / 8, 256, 0, st>>>(sp, k.psum, k.pmax, k.c[i], ts.c / 8, hw, k.ranges, n_items, k.c_tot, c_off);
         c_off += k.c[i];
       }
-      stcd::ca_fc_kernel<<<B, 256, 0, st>>>(k.psum, k.pmax, k.w_dev, k.w_dev + (size_t)k.hid * k.c_tot, k.gate, k.c_tot, k.hid, hw, k.ranges);
+      stcd::ca_fc_kernel<<<dim3((k.c_tot + 255) / 256, B), 256, 0, st>>>(k.psum, k.pmax, k.w_dev, k.w_dev + (size_t)k.hid * k.c_tot, k.gate, k.c_tot, k.hid, hw, k.ranges);
       c_off = 0;
       for (int i = 0; i < k.n_src; ++i) {
         const Tensor& ts = plan->tensors[k.src[i]];
@@ -969,7 +969,9 @@ int stcd_plan_add_channel_attention(stcd_plan* plan, const int* src_tensors, con
     return -fail(STCD_ERR_INVALID, "channel attention: dst must be [chunk,h,w,%d] (<= %d channels)", k.c_tot, stcd::kCaMaxC);
   k.ranges = std::max(1, std::min(16, td.h * td.w / stcd::kGateRangePix));
   k.w.assign(fc1, fc1 + (size_t)hid * k.c_tot);
-  k.w.insert(k.w.end(), fc2, fc2 + (size_t)k.c_tot * hid);
+  k.w.resize((size_t)2 * hid * k.c_tot);                       // fc2 [C][hid] stored transposed: [hid][C]
+  for (int c = 0; c < k.c_tot; ++c)
+    for (int u = 0; u < hid; ++u) k.w[(size_t)hid * k.c_tot + (size_t)u * k.c_tot + c] = fc2[(size_t)c * hid + u];
   plan->chan_attns.push_back(std::move(k));
   plan->ops.push_back({14, (int)plan->chan_attns.size() - 1});
   return (int)plan->ops.size() - 1;
