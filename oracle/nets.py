@@ -551,3 +551,93 @@ def dsifn_forward(sd: SD, t1: torch.Tensor, t2: torch.Tensor) -> torch.Tensor:
             x = _dsifn_conv_bn(sd, f"o{b}_conv{i + 1}", x)
         x = _bn(sd, f"bn_sa{b}", _dsifn_sa(sd, f"sa{b}", x) * x)
     return F.conv2d(x, sd["o5_conv4.weight"], sd["o5_conv4.bias"])
+
+
+# ------------------------------------------------------------------------------------------
+# ChangeGNNV2 / ChangeGNNV2_Compare (models/ChangeVIG.py:315-460,537-918): EncoderV2 == EncoderV1; DecoderV2 = HFFM + VFFM
+def _seq_conv_bn(sd: SD, pre: str, i: int, x: torch.Tensor, padding: int = 0) -> torch.Tensor:
+    """nn.Sequential members i (Conv2d) and i + 1 (BatchNorm2d)."""
+    return _bn(sd, f"{pre}.{i + 1}", F.conv2d(x, sd[f"{pre}.{i}.weight"], sd.get(f"{pre}.{i}.bias"), padding=padding))
+
+
+def _res_bottleneck(sd: SD, pre: str, out: torch.Tensor) -> torch.Tensor:
+    """act(conv_res(out) + conv(out)) shared by Cross_ConCat / Sub / Abs / Conc (ChangeVIG.py:323-347,670-750)."""
+    r = _seq_conv_bn(sd, f"{pre}.conv_res", 0, out, padding=1)
+    c = F.relu(_seq_conv_bn(sd, f"{pre}.conv", 0, out))
+    c = F.relu(_seq_conv_bn(sd, f"{pre}.conv", 3, c, padding=1))
+    c = _seq_conv_bn(sd, f"{pre}.conv", 6, c)
+    return F.relu(r + c)
+
+
+def _cross_concat_v2(sd: SD, pre: str, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Cross_ConCat.forward, ChangeVIG.py:339-347: channels interleaved (a0, b0, a1, b1, ...), grouped 3x3 conv (one group per
+    channel pair), BN, ReLU, then the residual bottleneck."""
+    n, c, h, w = a.shape
+    z = torch.stack([a, b], dim=2).reshape(n, 2 * c, h, w)
+    out = F.relu(_bn(sd, f"{pre}.diff.1", F.conv2d(z, sd[f"{pre}.diff.0.weight"], sd[f"{pre}.diff.0.bias"], padding=1, groups=c)))
+    return _res_bottleneck(sd, pre, out)
+
+
+def _global_local(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """Global_Local.forward, ChangeVIG.py:377-391."""
+    c = x.shape[1]
+    pooled = torch.cat([F.adaptive_avg_pool2d(x, 1), F.adaptive_max_pool2d(x, 1)], dim=2)            # [n, c, 2, 1]
+    ch = F.relu(_bn(sd, f"{pre}.channel_bn", F.conv2d(pooled, sd[f"{pre}.channel_conv.weight"], sd[f"{pre}.channel_conv.bias"], groups=c)))
+    sp_in = torch.cat([x.mean(dim=1, keepdim=True), x.max(dim=1, keepdim=True)[0]], dim=1)
+    sp = F.relu(F.conv2d(sp_in, sd[f"{pre}.spatial_conv.weight"], sd[f"{pre}.spatial_conv.bias"], padding=2))
+    gated = torch.sigmoid(ch * sp) * x
+    loc = torch.cat([F.conv2d(x, sd[f"{pre}.local_conv1.weight"], sd[f"{pre}.local_conv1.bias"], groups=c),
+                     F.conv2d(x, sd[f"{pre}.local_conv2.weight"], sd[f"{pre}.local_conv2.bias"], padding=1, groups=c),
+                     F.conv2d(x, sd[f"{pre}.local_conv3.weight"], sd[f"{pre}.local_conv3.bias"], padding=3, groups=c)], dim=1)
+    loc = F.conv2d(loc, sd[f"{pre}.local_conv4.weight"], sd[f"{pre}.local_conv4.bias"])
+    loc = F.conv2d(F.relu(_bn(sd, f"{pre}.local_bn", loc)), sd[f"{pre}.local_conv5.weight"], sd[f"{pre}.local_conv5.bias"], padding=1)
+    return gated + loc
+
+
+def _vffm(sd: SD, pre: str, low: torch.Tensor, high: torch.Tensor) -> torch.Tensor:
+    """VFFM.forward, ChangeVIG.py:452-460."""
+    high = F.conv_transpose2d(high, sd[f"{pre}.up.up.weight"], sd[f"{pre}.up.up.bias"], stride=2)
+    mixed = low + high
+
+    def mlp(p, v):                                   # Sequential: [pool,] conv, BN, ReLU, conv, BN
+        o = 1 if p != "local_att" else 0
+        v = F.relu(_seq_conv_bn(sd, f"{pre}.{p}", o, v))
+        return _seq_conv_bn(sd, f"{pre}.{p}", o + 3, v)
+
+    wei = torch.sigmoid(mlp("global_avg", F.adaptive_avg_pool2d(mixed, 1)) + mlp("global_max", F.adaptive_max_pool2d(mixed, 1))
+                        + mlp("local_att", mixed))
+    return 2 * low * wei + 2 * high * (1 - wei)
+
+
+def changegnn_v2_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor, diff_mode: str = "cross") -> List[torch.Tensor]:
+    """ChangeGNNV2.forward (ChangeVIG.py:661-664) / ChangeGNNV2_Compare.forward (:915-918): [full-resolution logits].
+    diff_mode: 'cross' (HFFM: Cross_ConCat) or the Compare variants 'sub' / 'abs' / 'conc' (HFFM_Compare, :753-765)."""
+    f1, f2 = vig_encoder_features(sd, x1), vig_encoder_features(sd, x2)
+    pre = "decoder"
+
+    def hffm(k):
+        a, b = f1[k - 1], f2[k - 1]
+        if diff_mode == "cross":
+            d = _cross_concat_v2(sd, f"{pre}.hffm{k}.cross_conc", a, b)
+        elif diff_mode == "sub":
+            d = _res_bottleneck(sd, f"{pre}.hffm{k}.diff", a - b)
+        elif diff_mode == "abs":
+            d = _res_bottleneck(sd, f"{pre}.hffm{k}.diff", (a - b).abs())
+        else:
+            q = f"{pre}.hffm{k}.diff"
+            out = F.relu(_bn(sd, f"{q}.diff.1", F.conv2d(torch.cat([a, b], dim=1), sd[f"{q}.diff.0.weight"], sd[f"{q}.diff.0.bias"], padding=1)))
+            d = _res_bottleneck(sd, q, out)
+        return _global_local(sd, f"{pre}.hffm{k}.global_local", d)
+
+    c = _vffm(sd, f"{pre}.vffm1", hffm(1), _vffm(sd, f"{pre}.vffm2", hffm(2), _vffm(sd, f"{pre}.vffm3", hffm(3), hffm(4))))
+
+    def resblock(q, x):                              # ResidualBlock.forward, ChangeFormerBaseNetworks.py:113-120
+        r = x
+        o = F.relu(F.conv2d(x, sd[f"{q}.conv1.conv2d.weight"], sd[f"{q}.conv1.conv2d.bias"], padding=1))
+        return F.conv2d(o, sd[f"{q}.conv2.conv2d.weight"], sd[f"{q}.conv2.conv2d.bias"], padding=1) * 0.1 + r
+
+    x = F.conv_transpose2d(c, sd[f"{pre}.convd2x.conv2d.weight"], sd[f"{pre}.convd2x.conv2d.bias"], stride=2, padding=1)
+    x = resblock(f"{pre}.dense_2x.0", x)
+    x = F.conv_transpose2d(x, sd[f"{pre}.convd1x.conv2d.weight"], sd[f"{pre}.convd1x.conv2d.bias"], stride=2, padding=1)
+    x = resblock(f"{pre}.dense_1x.0", x)
+    return [F.conv2d(x, sd[f"{pre}.change_probability.conv2d.weight"], sd[f"{pre}.change_probability.conv2d.bias"], padding=1)]
