@@ -62,6 +62,8 @@ WORKLOADS = {
     "bit_dd8_256_b32": dict(net="BASE_Transformer", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=32,
                             desc="BIT base_transformer_pos_s4_dd8 (ResNet-18 stages 1-3, 4 semantic tokens, 1 encoder + 8 decoder layers) "
                                  "256x256 RGB pairs, batch 32 per GPU, bf16 convs + fp32 token path"),
+    "changegnn_v2_256_b32": dict(net="ChangeGNNV2", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=32,
+                                 desc="ChangeGNNV2 (pyramid ViG encoder, HFFM + VFFM decoder) 256x256 RGB pairs, batch 32 per GPU, bf16"),
     "ifnet_256_b16": dict(net="DSIFN", n_class=1, h=256, w=256, batch=16, kind="sigmoid", chunk=16,
                           desc="IFNet / DSIFN (shared VGG16 features, channel + spatial attention difference decoder) 256x256 RGB pairs, "
                                "batch 16 per GPU, bf16, change = sigmoid(out) > 0.5"),
@@ -81,7 +83,7 @@ def build_net(wl):
     if wl["net"] == "BASE_Transformer":
         net = CLASSES["BASE_Transformer"](3, wl["n_class"], with_pos="learned", resnet_stages_num=4, token_len=4, enc_depth=1, dec_depth=8)
         return synth.prepare_(net.eval(), "BASE_Transformer")
-    if wl["net"] in ("ChangeGNNV1", "ChangeFormerV6"):
+    if wl["net"] in ("ChangeGNNV1", "ChangeFormerV6", "ChangeGNNV2"):
         return synth.prepare_(CLASSES[wl["net"]](3, wl["n_class"], embed_dim=256).eval(), wl["net"])
     return synth.prepare_(CLASSES[wl["net"]](3, wl["n_class"]).eval(), wl["net"])
 
@@ -106,6 +108,8 @@ def oracle_forward(wl, sd, x1, x2):
         return nets.bit_forward(sd, x1, x2, stages=4)
     if wl["net"] == "DSIFN":
         return nets.dsifn_forward(sd, x1, x2)
+    if wl["net"] == "ChangeGNNV2":
+        return nets.changegnn_v2_forward(sd, x1, x2, "cross")
     raise KeyError(wl["net"])
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 14
+#define STCD_ABI_VERSION 15
 
 enum stcd_status {
   STCD_OK = 0,
@@ -226,6 +226,19 @@ int stcd_plan_add_channel_attention(stcd_plan* plan, const int* src_tensors, con
  * dst = (src * sigmoid(conv7x7([mean_c src, max_c src]))) * scale + shift.  w HOST fp32 [2][7][7], scale / shift HOST fp32 [c]. */
 int stcd_plan_add_spatial_gate(stcd_plan* plan, int src_tensor, int dst_tensor, int c, const float* w, const float* scale,
                                const float* shift);
+
+/* ChangeGNNV2's Global_Local, global branch (models/ChangeVIG.py:377-385): dst = sigmoid(ch[c] * sp[pixel]) * src,
+ * ch = relu(BN(grouped (2,1) conv over [avgpool; maxpool])), sp = relu(conv5x5([mean_c, max_c]) + b).
+ * prm HOST fp32: w_avg[c] | w_max[c] | scale[c] | shift[c] (conv bias and BatchNorm folded) | w_sp[2][5][5] | b_sp.  c <= 512. */
+int stcd_plan_add_global_local_gate(stcd_plan* plan, int src_tensor, int dst_tensor, int c, const float* prm);
+
+/* ChangeGNNV2's VFFM (models/ChangeVIG.py:452-460): dst = 2 low wei + 2 high (1 - wei),
+ * wei = sigmoid(MLP_avg(avgpool(mixed)) + MLP_max(maxpool(mixed)) + local), mixed = low + high (a plan tensor), local = the
+ * local_att branch (a plan tensor).  All tensors [chunk, h, w, c] with exactly c channels.  prm HOST fp32: avg branch then max
+ * branch, each  W1[inter][c] | s1[inter] | t1[inter] | W2^T[inter][c] | s2[c] | t2[c]  (conv biases and BatchNorms folded).
+ * c <= 512, inter <= 128. */
+int stcd_plan_add_vffm(stcd_plan* plan, int low_tensor, int high_tensor, int mixed_tensor, int local_tensor, int dst_tensor, int c,
+                       int inter, const float* prm);
 
 /* dst = sum of n <= 5 plan tensors of identical shape (Dblock.forward: x + d1 + d2 + d3 + d4, models/DTCDSCN.py:65-71) */
 int stcd_plan_add_sum(stcd_plan* plan, const int* src_tensors, int n, int dst_tensor);

@@ -290,6 +290,24 @@ def run_aux(op, T, chunk, ext, nv):
         g = torch.sigmoid(F.conv2d(m, torch.from_numpy(op.w)[None], None, padding=3))[:, 0, :, :, None]
         T[op.dst][..., : op.c] = _bf16(x * g * torch.from_numpy(op.scale) + torch.from_numpy(op.shift))
         return None
+    if isinstance(op, L.GlobalLocalGateSpec):
+        import torch.nn.functional as F
+        x = T[op.src][..., : op.c]
+        ch = torch.relu((x.mean(dim=(1, 2)) * torch.from_numpy(op.w_avg) + x.amax(dim=(1, 2)) * torch.from_numpy(op.w_max))
+                        * torch.from_numpy(op.scale) + torch.from_numpy(op.shift))                              # [n, c]
+        m = torch.stack([x.mean(dim=-1), x.amax(dim=-1)], dim=1)
+        sp = torch.relu(F.conv2d(m, torch.from_numpy(op.w_sp)[None], torch.tensor([op.b_sp]), padding=2))[:, 0]   # [n, h, w]
+        T[op.dst][..., : op.c] = _bf16(torch.sigmoid(ch[:, None, None, :] * sp[..., None]) * x)
+        return None
+    if isinstance(op, L.VffmSpec):
+        low, high, mixed, local = T[op.low], T[op.high], T[op.mixed], T[op.local]
+        g = 0.0
+        for v, b in zip((mixed.mean(dim=(1, 2)), mixed.amax(dim=(1, 2))), op.branches):
+            hid = torch.relu(v @ torch.from_numpy(b["w1"]).T * torch.from_numpy(b["s1"]) + torch.from_numpy(b["t1"]))
+            g = g + (hid @ torch.from_numpy(b["w2"]).T * torch.from_numpy(b["s2"]) + torch.from_numpy(b["t2"]))
+        wei = torch.sigmoid(g[:, None, None, :] + local)
+        T[op.dst][...] = _bf16(2 * low * wei + 2 * high * (1 - wei))
+        return None
     if isinstance(op, L.SumSpec):
         T[op.dst][...] = _bf16(sum(T[s_] for s_ in op.srcs))
         return None

@@ -44,6 +44,9 @@ CASES = {
     "bit_resnet18": ("models.networks", "ResNet", (3, 2), 2, 64, 96),
     # IFNet = DSIFN(base, base) with ONE shared vgg16_base (models/networks.py:164-166); args = () -> built by _build_ifnet
     "ifnet": ("models.DSIFN", "DSIFN", (), 2, 64, 96),
+    # ChangeGNNV2 (Cross_ConCat HFFM) and the "sub" Compare variant; gcn_lib from oracle/gcn_lib_restated.py as for changegnn_v1
+    "changegnn_v2": ("models.ChangeVIG", "ChangeGNNV2", (3, 2, False, 256), 1, 256, 256),
+    "changegnn_v2_sub": ("models.ChangeVIG", "ChangeGNNV2_Compare", (3, 2, False, 256, "MLP", 256, "sub"), 1, 256, 256),
 }
 
 

@@ -22,7 +22,7 @@ Lowering (eval mode; both temporal images ride through every encoder launch as S
 """
 from __future__ import annotations
 
-from typing import Dict, List
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch
@@ -235,7 +235,15 @@ def lower_changegnn(sd: Dict[str, torch.Tensor], e: int, n_class: int, img_size:
         raise ValueError("img_size must be a multiple of 32")
     sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
     p = L.Program(model="ChangeGNNV1", in_channels=3, h=h, w=w)
-    ones = lambda c: np.ones(c, np.float32)  # noqa: E731
+    feats = lower_vig_encoder(p, sd, h, w)
+    lower_diff_decoder(p, sd, feats, e, n_class, "decoder", "decoder.decoder_heads_c{k}")
+    return p
+
+
+def lower_vig_encoder(p: L.Program, sd: Dict[str, torch.Tensor], h: int, w: int):
+    """EncoderV1 == EncoderV2 (ChangeVIG.py:26-97, 463-534): Stem + pos_embed, 12 Grapher + FFN blocks, 3 Downsamples.
+    Returns [(tensor, channels, h, w)] per stage, both streams."""
+    ones = lambda c: np.ones(c, np.float32)  # noqa: E731,F841
     npf = lambda t: t.numpy().astype(np.float32)  # noqa: E731
 
     def conv_bn(pre: str, cout: int):
@@ -328,9 +336,7 @@ def lower_changegnn(sd: Dict[str, torch.Tensor], e: int, n_class: int, img_size:
             bi += 1
             idx += 1
         feats.append((x, c, hh, ww))
-
-    lower_diff_decoder(p, sd, feats, e, n_class, "decoder", "decoder.decoder_heads_c{k}")
-    return p
+    return feats
 
 
 def lower_diff_decoder(p: L.Program, sd: Dict[str, torch.Tensor], feats, e: int, n_class: int, d: str, head_fmt: str) -> None:
@@ -394,7 +400,14 @@ def lower_diff_decoder(p: L.Program, sd: Dict[str, torch.Tensor], feats, e: int,
     sc, sh = conv_bn(f"{d}.linear_fuse", e)
     L.add_conv(p, f"{d}.linear_fuse", [L.Segment(t, e) for t in ups], L.conv_taps(sd[f"{d}.linear_fuse.0.weight"], pad=0), e,
                full_h, full_w, 1, sc, sh, out0=fused, macs_per_pair=full_h * full_w * 4 * e * e)
-    x, hh, ww = fused, full_h, full_w
+    lower_decoder_tail(p, sd, fused, full_h, full_w, e, n_class, d, out_ext=4)
+
+
+def lower_decoder_tail(p: L.Program, sd: Dict[str, torch.Tensor], x: str, hh: int, ww: int, e: int, n_class: int, d: str, out_ext: int) -> None:
+    """convd2x -> dense_2x -> convd1x -> dense_1x -> change_probability (ChangeVIG.py:264-274, 612-624): two
+    (ConvTranspose2d(k4, s2, p1) as 4 phases + ResidualBlock with the 0.1 scale in the epilogue), 3x3 head -> fp32."""
+    ones = lambda c: np.ones(c, np.float32)  # noqa: E731
+    npf = lambda t: t.numpy().astype(np.float32)  # noqa: E731
     for up_name, res_name in (("convd2x", "dense_2x.0"), ("convd1x", "dense_1x.0")):
         wt = sd[f"{d}.{up_name}.conv2d.weight"]              # ConvTranspose2d [cin, cout, 4, 4], stride 2, padding 1
         u = p.tensor(f"{d}.{up_name}.out", 1, 2 * hh, 2 * ww, e)
@@ -409,6 +422,286 @@ def lower_diff_decoder(p: L.Program, sd: Dict[str, torch.Tensor], feats, e: int,
                    ww, 1, 0.1 * ones(e), 0.1 * npf(sd[f"{d}.{res_name}.conv2.conv2d.bias"]), res=u, out0=x,
                    macs_per_pair=hh * ww * 9 * e * e)
     L.add_conv(p, f"{d}.change_probability", [L.Segment(x, e)], L.conv_taps(sd[f"{d}.change_probability.conv2d.weight"], pad=1),
-               n_class, hh, ww, 1, ones(n_class), npf(sd[f"{d}.change_probability.conv2d.bias"]), out_ext=4,
+               n_class, hh, ww, 1, ones(n_class), npf(sd[f"{d}.change_probability.conv2d.bias"]), out_ext=out_ext,
                macs_per_pair=hh * ww * 9 * e * n_class)
     p.ext.append(L.ExtOutput("cp", n_class, hh, ww))
+
+
+# ==========================================================================================
+# ChangeGNNV2 / ChangeGNNV2_Compare (models/ChangeVIG.py:315-460, 537-918): the same ViG encoder, HFFM + VFFM decoder
+def _res_bottleneck_modules(holder: nn.Module, cin: int, cout: int) -> None:
+    """conv_res / conv of Cross_ConCat, Sub, Abs, Conc (ChangeVIG.py:323-337)."""
+    holder.conv_res = nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1), nn.BatchNorm2d(cout))
+    holder.conv = nn.Sequential(nn.Conv2d(cin, cout // 2, 1), nn.BatchNorm2d(cout // 2), nn.ReLU(),
+                                nn.Conv2d(cout // 2, cout // 2, 3, padding=1), nn.BatchNorm2d(cout // 2), nn.ReLU(),
+                                nn.Conv2d(cout // 2, cout, 1), nn.BatchNorm2d(cout))
+
+
+class _CrossConCat(nn.Module):
+    """models/ChangeVIG.py:315-337."""
+
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.diff = nn.Sequential(nn.Conv2d(cin * 2, cin, 3, padding=1, groups=cin), nn.BatchNorm2d(cin), nn.ReLU())
+        _res_bottleneck_modules(self, cin, cout)
+
+
+class _DiffOnly(nn.Module):
+    """Sub / Abs (models/ChangeVIG.py:667-718): no parameters besides the residual bottleneck."""
+
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        _res_bottleneck_modules(self, cin, cout)
+
+
+class _Conc(nn.Module):
+    """models/ChangeVIG.py:721-750."""
+
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.diff = nn.Sequential(nn.Conv2d(cin * 2, cin, 3, padding=1), nn.BatchNorm2d(cin), nn.ReLU())
+        _res_bottleneck_modules(self, cin, cout)
+
+
+class _GlobalLocal(nn.Module):
+    """models/ChangeVIG.py:350-375 (``bt`` is never used in forward; it is a parameter all the same)."""
+
+    def __init__(self, c: int):
+        super().__init__()
+        self.channel_conv = nn.Conv2d(c, c, kernel_size=(2, 1), groups=c)
+        self.channel_bn = nn.BatchNorm2d(c)
+        self.spatial_conv = nn.Conv2d(2, 1, 5, padding=2)
+        self.local_conv1 = nn.Conv2d(c, c, 1, groups=c)
+        self.local_conv2 = nn.Conv2d(c, c, 3, padding=1, groups=c)
+        self.local_conv3 = nn.Conv2d(c, c, 7, padding=3, groups=c)
+        self.local_conv4 = nn.Conv2d(c * 3, c, 1)
+        self.local_conv5 = nn.Conv2d(c, c, 3, padding=1)
+        self.local_bn = nn.BatchNorm2d(c)
+        self.bt = nn.BatchNorm2d(c)
+
+
+class _HFFM(nn.Module):
+    """HFFM (ChangeVIG.py:408-415) / HFFM_Compare (:753-765)."""
+
+    def __init__(self, cin: int, cout: int, diff_mode: str):
+        super().__init__()
+        if diff_mode == "cross":
+            self.cross_conc = _CrossConCat(cin, cout)
+        else:
+            self.diff = _Conc(cin, cout) if diff_mode == "conc" else _DiffOnly(cin, cout)
+        self.global_local = _GlobalLocal(cout)
+
+
+class _Upsampling(nn.Module):
+    def __init__(self, c: int):
+        super().__init__()
+        self.up = nn.ConvTranspose2d(c, c, kernel_size=2, stride=2)
+
+
+class _VFFM(nn.Module):
+    """models/ChangeVIG.py:418-450."""
+
+    def __init__(self, c: int, r: int = 4):
+        super().__init__()
+        i = c // r
+        self.up = _Upsampling(c)
+        self.global_avg = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(c, i, 1), nn.BatchNorm2d(i), nn.ReLU(inplace=True),
+                                        nn.Conv2d(i, c, 1), nn.BatchNorm2d(c))
+        self.global_max = nn.Sequential(nn.AdaptiveMaxPool2d(1), nn.Conv2d(c, i, 1), nn.BatchNorm2d(i), nn.ReLU(inplace=True),
+                                        nn.Conv2d(i, c, 1), nn.BatchNorm2d(c))
+        self.local_att = nn.Sequential(nn.Conv2d(c, i, 1), nn.BatchNorm2d(i), nn.ReLU(inplace=True), nn.Conv2d(i, c, 1), nn.BatchNorm2d(c))
+
+
+class _DecoderV2(nn.Module):
+    """DecoderV2 (ChangeVIG.py:537-595) / DecoderV2_Compare (:768-826)."""
+
+    def __init__(self, in_channels, e: int, output_nc: int, diff_mode: str):
+        super().__init__()
+        c1, c2, c3, c4 = in_channels
+        self.hffm4 = _HFFM(c4, e, diff_mode)
+        self.hffm3 = _HFFM(c3, e, diff_mode)
+        self.hffm2 = _HFFM(c2, e, diff_mode)
+        self.hffm1 = _HFFM(c1, e, diff_mode)
+        self.vffm3 = _VFFM(e)
+        self.vffm2 = _VFFM(e)
+        self.vffm1 = _VFFM(e)
+        self.convd2x = _UpsampleConvLayer(e, e, 4, 2)
+        self.dense_2x = nn.Sequential(_ResidualBlock(e))
+        self.convd1x = _UpsampleConvLayer(e, e, 4, 2)
+        self.dense_1x = nn.Sequential(_ResidualBlock(e))
+        self.change_probability = _ConvLayer(e, output_nc, 3, 1, 1)
+        self.active = nn.Sigmoid()
+
+
+class ChangeGNNV2(PlannedModule):
+    """models/ChangeVIG.py:634-664 (registry key ``ChangeGNNV2``, models/networks.py:201-202).  ``img_size`` is accepted and,
+    like upstream, NOT forwarded to the encoder: EncoderV2 is always built for 256x256 (:647-650)."""
+    default_chunk_pairs = 32
+    _diff_mode = "cross"
+
+    def __init__(self, input_nc: int = 3, output_nc: int = 2, decoder_softmax: bool = False, embed_dim: int = 256,
+                 decoder_heads: str = "MLP", img_size: int = 256, diff_mode: Optional[str] = None):
+        super().__init__()
+        mode = self._diff_mode if diff_mode is None else diff_mode
+        if input_nc != 3:
+            raise NotImplementedError("the ViG Stem is hard-wired to 3 input channels (pyramid_vig.py:70)")
+        if decoder_softmax:
+            raise NotImplementedError("stcd_b200 serves decoder_softmax=False (models/networks.py:201-208)")
+        if mode not in ("cross", "sub", "abs", "conc"):
+            raise NotImplementedError(f"diff_mode {mode!r}")
+        if output_nc > 8 or embed_dim % 64 or embed_dim > 512:
+            raise NotImplementedError("output_nc <= 8, embed_dim a multiple of 64 up to 512")
+        self.embed_dims = list(_CHANNELS)
+        self.embedding_dim = embed_dim
+        self.output_nc = output_nc
+        self.diff_mode = mode
+        self.encoder = _EncoderV1(256)
+        self.decoder = _DecoderV2(_CHANNELS, embed_dim, output_nc, mode)
+        for m in self.encoder.modules():            # EncoderV2.model_init, ChangeVIG.py:513-520
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight)
+                if m.bias is not None:
+                    m.bias.data.zero_()
+
+    def lower(self, h: int, w: int) -> L.Program:
+        return lower_changegnn_v2(self.state_dict(), self.embedding_dim, self.output_nc, self.diff_mode, h, w)
+
+    @torch.no_grad()
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor):
+        return self.plan_for(x1).forward(x1, x2)        # [cp]: a one-element list (ChangeVIG.py:626-631)
+
+    def _wrap_outputs(self, outs):
+        return list(outs)
+
+
+class ChangeGNNV2_Compare(ChangeGNNV2):
+    """models/ChangeVIG.py:865-918 (keys ``ChangeGNNV2_sub`` / ``_abs`` / ``_conc``, models/networks.py:203-208)."""
+    _diff_mode = "sub"
+
+    def __init__(self, input_nc: int = 3, output_nc: int = 2, decoder_softmax: bool = False, embed_dim: int = 256,
+                 decoder_heads: str = "MLP", img_size: int = 256, diff_mode: str = "sub"):
+        super().__init__(input_nc, output_nc, decoder_softmax, embed_dim, decoder_heads, img_size, diff_mode=diff_mode)
+
+
+def lower_changegnn_v2(sd: Dict[str, torch.Tensor], e: int, n_class: int, diff_mode: str, h: int, w: int) -> L.Program:
+    """state_dict of the reference ChangeGNNV2 / ChangeGNNV2_Compare -> fused-op Program (eval mode)."""
+    if h != 256 or w != 256:
+        raise ValueError(f"ChangeGNNV2's encoder is built for 256x256 inputs (its pos_embed is not resized), got {h}x{w}")
+    sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
+    p = L.Program(model=f"ChangeGNNV2-{diff_mode}", in_channels=3, h=h, w=w)
+    feats = lower_vig_encoder(p, sd, h, w)
+    ones = lambda c: np.ones(c, np.float32)  # noqa: E731
+    npf = lambda t: np.ascontiguousarray(t.numpy().astype(np.float32))  # noqa: E731
+
+    def cbn(pre: str, i: int, cout: int):
+        return L.fold_bn(sd.get(f"{pre}.{i}.bias"), L.bn_params(sd, f"{pre}.{i + 1}"), cout)
+
+    def hffm(k: int) -> str:
+        ft, cin, hh, ww = feats[k - 1]
+        q = f"decoder.hffm{k}." + ("cross_conc" if diff_mode == "cross" else "diff")
+        # ---- the difference feature `out` [cin]
+        if diff_mode in ("sub", "abs"):
+            out = p.tensor(f"{q}.out", 1, hh, ww, cin)
+            p.ops.append(L.AbsDiffSpec(f"{q}.sub", ft, out, cin, signed=(diff_mode == "sub")))
+        elif diff_mode == "cross":
+            # grouped conv over the interleaved (a0, b0, a1, b1, ...) == block-diagonal dense conv over [a | b]; channel blocks
+            # keep the K-program short and skip most of the structural zeros
+            wg = sd[f"{q}.diff.0.weight"]                                  # [cin, 2, 3, 3]
+            sc, sh = cbn(f"{q}.diff", 0, cin)
+            out = p.tensor(f"{q}.out", 1, hh, ww, cin)
+            nb = -(-cin // 320)
+            blk = -(-cin // nb // 8) * 8
+            for c0 in range(0, cin, blk):
+                cb = min(blk, cin - c0)
+                taps = []
+                for ky in range(3):
+                    for kx in range(3):
+                        wt = torch.zeros(cb, 2 * cb)
+                        idx = torch.arange(cb)
+                        wt[idx, idx] = wg[c0: c0 + cb, 0, ky, kx]
+                        wt[idx, cb + idx] = wg[c0: c0 + cb, 1, ky, kx]
+                        taps.append((ky - 1, kx - 1, wt))
+                L.add_conv(p, f"{q}.diff.{c0}", [L.Segment(ft, cb, stream=0, c_off=c0, c_store=cb), L.Segment(ft, cb, stream=1, c_off=c0, c_store=cb)],
+                           [(0, 0, taps)], cb, hh, ww, 1, sc[c0: c0 + cb], sh[c0: c0 + cb], relu=True, out0=out, out0_coff=c0,
+                           macs_per_pair=hh * ww * 9 * 2 * cb)
+        else:                                                              # conc: dense 3x3 over cat(a, b), split along K by stream
+            wd = sd[f"{q}.diff.0.weight"]                                  # [cin, 2 cin, 3, 3]
+            sc, sh = cbn(f"{q}.diff", 0, cin)
+            part = p.tensor(f"{q}.part", 1, hh, ww, cin)
+            L.add_conv(p, f"{q}.diff.a", [L.Segment(ft, cin, stream=0)], L.conv_taps(wd[:, :cin], pad=1), cin, hh, ww, 1, sc, 0 * sh, out0=part,
+                       macs_per_pair=hh * ww * 9 * cin * cin)
+            out = p.tensor(f"{q}.out", 1, hh, ww, cin)
+            L.add_conv(p, f"{q}.diff.b", [L.Segment(ft, cin, stream=1)], L.conv_taps(wd[:, cin:], pad=1), cin, hh, ww, 1, sc, sh, relu=True,
+                       res=part, out0=out, macs_per_pair=hh * ww * 9 * cin * cin)
+        # ---- act(conv_res(out) + conv(out))
+        r = p.tensor(f"{q}.res", 1, hh, ww, e)
+        sc, sh = cbn(f"{q}.conv_res", 0, e)
+        L.add_conv(p, f"{q}.conv_res", [L.Segment(out, cin)], L.conv_taps(sd[f"{q}.conv_res.0.weight"], pad=1), e, hh, ww, 1, sc, sh, out0=r,
+                   macs_per_pair=hh * ww * 9 * cin * e)
+        c1 = p.tensor(f"{q}.c1", 1, hh, ww, e // 2)
+        sc, sh = cbn(f"{q}.conv", 0, e // 2)
+        L.add_conv(p, f"{q}.conv.0", [L.Segment(out, cin)], L.conv_taps(sd[f"{q}.conv.0.weight"], pad=0), e // 2, hh, ww, 1, sc, sh, relu=True,
+                   out0=c1, macs_per_pair=hh * ww * cin * e // 2)
+        c2 = p.tensor(f"{q}.c2", 1, hh, ww, e // 2)
+        sc, sh = cbn(f"{q}.conv", 3, e // 2)
+        L.add_conv(p, f"{q}.conv.3", [L.Segment(c1, e // 2)], L.conv_taps(sd[f"{q}.conv.3.weight"], pad=1), e // 2, hh, ww, 1, sc, sh, relu=True,
+                   out0=c2, macs_per_pair=hh * ww * 9 * (e // 2) * (e // 2))
+        d = p.tensor(f"{q}.d", 1, hh, ww, e)
+        sc, sh = cbn(f"{q}.conv", 6, e)
+        L.add_conv(p, f"{q}.conv.6", [L.Segment(c2, e // 2)], L.conv_taps(sd[f"{q}.conv.6.weight"], pad=0), e, hh, ww, 1, sc, sh, relu=True, res=r,
+                   out0=d, macs_per_pair=hh * ww * (e // 2) * e)
+        # ---- Global_Local
+        g = f"decoder.hffm{k}.global_local"
+        cs, ct = L.fold_bn(sd[f"{g}.channel_conv.bias"], L.bn_params(sd, f"{g}.channel_bn"), e)
+        gated = p.tensor(f"{g}.gated", 1, hh, ww, e)
+        wc = sd[f"{g}.channel_conv.weight"]                                # [e, 1, 2, 1]: (avg, max)
+        p.ops.append(L.GlobalLocalGateSpec(f"{g}.gate", d, gated, e, npf(wc[:, 0, 0, 0]), npf(wc[:, 0, 1, 0]), cs, ct,
+                                           npf(sd[f"{g}.spatial_conv.weight"][0]), float(sd[f"{g}.spatial_conv.bias"][0])))
+        # local_conv4(cat(dw1x1, dw3x3, dw7x7)) is linear in x: ONE dense 7x7 conv whose weights are the composition
+        w4 = sd[f"{g}.local_conv4.weight"][:, :, 0, 0]                     # [e, 3e]
+        wl = w4[:, 2 * e:, None, None] * sd[f"{g}.local_conv3.weight"][:, 0][None]                   # [e, e, 7, 7]
+        wl[:, :, 2:5, 2:5] += w4[:, e: 2 * e, None, None] * sd[f"{g}.local_conv2.weight"][:, 0][None]
+        wl[:, :, 3, 3] += w4[:, :e] * sd[f"{g}.local_conv1.weight"][:, 0, 0, 0][None]
+        bl = (sd[f"{g}.local_conv4.bias"] + w4[:, :e] @ sd[f"{g}.local_conv1.bias"] + w4[:, e: 2 * e] @ sd[f"{g}.local_conv2.bias"]
+              + w4[:, 2 * e:] @ sd[f"{g}.local_conv3.bias"])
+        sc, sh = L.fold_bn(bl, L.bn_params(sd, f"{g}.local_bn"), e)
+        l1 = p.tensor(f"{g}.l1", 1, hh, ww, e)
+        L.add_conv(p, f"{g}.local_conv1-4", [L.Segment(d, e)], L.conv_taps(wl, pad=3), e, hh, ww, 1, sc, sh, relu=True, out0=l1,
+                   macs_per_pair=hh * ww * (59 * e + 3 * e * e))
+        o = p.tensor(f"{g}.out", 1, hh, ww, e)
+        L.add_conv(p, f"{g}.local_conv5", [L.Segment(l1, e)], L.conv_taps(sd[f"{g}.local_conv5.weight"], pad=1), e, hh, ww, 1, ones(e),
+                   npf(sd[f"{g}.local_conv5.bias"]), res=gated, out0=o, macs_per_pair=hh * ww * 9 * e * e)
+        return o
+
+    def vffm(k: int, low: str, high_lr: str) -> str:
+        _, _, hh, ww = feats[k - 1]
+        v = f"decoder.vffm{k}"
+        high = p.tensor(f"{v}.high", 1, hh, ww, e)
+        L.add_conv(p, f"{v}.up", [L.Segment(high_lr, e)], L.convT_phase_taps(sd[f"{v}.up.up.weight"], 2, 0), e, hh // 2, ww // 2, 1, ones(e),
+                   npf(sd[f"{v}.up.up.bias"]), osy=2, osx=2, out0=high, macs_per_pair=(hh // 2) * (ww // 2) * 4 * e * e)
+        mixed = p.tensor(f"{v}.mixed", 1, hh, ww, e)
+        p.ops.append(L.SumSpec(f"{v}.mixed", [low, high], mixed))
+        i = e // 4
+        la1 = p.tensor(f"{v}.la1", 1, hh, ww, i)
+        sc, sh = cbn(f"{v}.local_att", 0, i)
+        L.add_conv(p, f"{v}.local_att.0", [L.Segment(mixed, e)], L.conv_taps(sd[f"{v}.local_att.0.weight"], pad=0), i, hh, ww, 1, sc, sh,
+                   relu=True, out0=la1, macs_per_pair=hh * ww * e * i)
+        la2 = p.tensor(f"{v}.la2", 1, hh, ww, e)
+        sc, sh = cbn(f"{v}.local_att", 3, e)
+        L.add_conv(p, f"{v}.local_att.3", [L.Segment(la1, i)], L.conv_taps(sd[f"{v}.local_att.3.weight"], pad=0), e, hh, ww, 1, sc, sh, out0=la2,
+                   macs_per_pair=hh * ww * i * e)
+        branches = []
+        for nm in ("global_avg", "global_max"):
+            s1, t1 = cbn(f"{v}.{nm}", 1, i)
+            s2, t2 = cbn(f"{v}.{nm}", 4, e)
+            branches.append(dict(w1=npf(sd[f"{v}.{nm}.1.weight"][:, :, 0, 0]), s1=s1, t1=t1, w2=npf(sd[f"{v}.{nm}.4.weight"][:, :, 0, 0]), s2=s2, t2=t2))
+        xo = p.tensor(f"{v}.out", 1, hh, ww, e)
+        p.ops.append(L.VffmSpec(v, low, high, mixed, la2, xo, e, i, (branches[0], branches[1])))
+        return xo
+
+    c = hffm(4)
+    for k in (3, 2, 1):
+        c = vffm(k, hffm(k), c)
+    _, _, hh, ww = feats[0]
+    lower_decoder_tail(p, sd, c, hh, ww, e, n_class, "decoder", out_ext=0)
+    return p

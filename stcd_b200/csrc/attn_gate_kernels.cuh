@@ -173,4 +173,121 @@ __global__ void __launch_bounds__(kSaTW* kSaTH) sa_apply_kernel(const __nv_bfloa
   }
 }
 
+// ------------------------------------------------------------------------------------------ ChangeGNNV2 decoder gates
+// Global_Local's global branch (models/ChangeVIG.py:377-385): out = sigmoid(ch[c] * sp[pixel]) * x with
+//   ch[c] = relu((w0[c] avg_c + w1[c] max_c) * cs[c] + ct[c])      (grouped (2,1) conv over [avg; max], bias + BatchNorm folded)
+//   sp    = relu(conv5x5([mean_c x, max_c x]) + b)
+// prm: w0[C] | w1[C] | cs[C] | ct[C] | wsp[2][5][5] | b.  block (32, 8) pixels; grid (ceil(w/32), ceil(h/8), images).
+constexpr int kGlMaxC = 512;
+__global__ void __launch_bounds__(kSaTW* kSaTH) gl_apply_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                const float2* __restrict__ stats, const float* __restrict__ psum,
+                                                                const float* __restrict__ pmax, const float* __restrict__ prm, int C,
+                                                                int src_c8, int dst_c8, int h, int w, int ranges) {
+  __shared__ float2 s_t[kSaTH + 4][kSaTW + 4];
+  __shared__ float s_w[51];
+  __shared__ float s_ch[kGlMaxC];
+  const int b = blockIdx.z, x0 = blockIdx.x * kSaTW, y0 = blockIdx.y * kSaTH, hw = h * w;
+  const int tid = threadIdx.y * kSaTW + threadIdx.x;
+  if (tid < 51) s_w[tid] = prm[4 * C + tid];
+  for (int c = tid; c < C; c += kSaTW * kSaTH) {
+    float a = 0.f, m = -3.0e38f;
+    for (int r = 0; r < ranges; ++r) {
+      a += psum[(static_cast<size_t>(b) * ranges + r) * C + c];
+      m = fmaxf(m, pmax[(static_cast<size_t>(b) * ranges + r) * C + c]);
+    }
+    a /= static_cast<float>(hw);
+    s_ch[c] = fmaxf(fmaf(fmaf(prm[c], a, prm[C + c] * m), prm[2 * C + c], prm[3 * C + c]), 0.f);
+  }
+  for (int i = tid; i < (kSaTH + 4) * (kSaTW + 4); i += kSaTW * kSaTH) {
+    const int ty = i / (kSaTW + 4), tx = i % (kSaTW + 4);
+    const int gy = y0 + ty - 2, gx = x0 + tx - 2;
+    s_t[ty][tx] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? stats[static_cast<size_t>(b) * hw + gy * w + gx] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x >= w || y >= h) return;
+  float a = s_w[50];
+#pragma unroll
+  for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 5; ++kx) {
+      const float2 t = s_t[threadIdx.y + ky][threadIdx.x + kx];
+      a = fmaf(t.x, s_w[ky * 5 + kx], a);
+      a = fmaf(t.y, s_w[25 + ky * 5 + kx], a);
+    }
+  }
+  const float sp = fmaxf(a, 0.f);
+  const int pix = y * w + x;
+  const __nv_bfloat16* s = src + (static_cast<size_t>(b) * src_c8 * hw + pix) * 8;
+  __nv_bfloat16* o = dst + (static_cast<size_t>(b) * dst_c8 * hw + pix) * 8;
+  for (int g = 0; g < (C >> 3); ++g) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(s + static_cast<size_t>(g) * hw * 8)), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= 1.f / (1.f + expf(-s_ch[g * 8 + j] * sp));
+    *reinterpret_cast<uint4*>(o + static_cast<size_t>(g) * hw * 8) = pack8(v);
+  }
+}
+
+// VFFM (models/ChangeVIG.py:452-460): xo = 2 low wei + 2 high (1 - wei), wei = sigmoid(g_avg[c] + g_max[c] + local[pixel, c]);
+// g_* = conv-BN-ReLU-conv-BN (1x1, on the pooled vector of mixed = low + high), BatchNorm and biases folded to scale / shift.
+// prm: avg branch then max branch, each  w1[inter][C] | s1[inter] | t1[inter] | w2t[inter][C] | s2[C] | t2[C].
+// grid (pixel blocks, images), 256 threads; every CTA redoes the two small MLPs of its image.
+__global__ void __launch_bounds__(256) vffm_apply_kernel(const __nv_bfloat16* __restrict__ low, const __nv_bfloat16* __restrict__ high,
+                                                         const __nv_bfloat16* __restrict__ local, __nv_bfloat16* __restrict__ dst,
+                                                         const float* __restrict__ psum, const float* __restrict__ pmax,
+                                                         const float* __restrict__ prm, int C, int inter, int hw, int ranges,
+                                                         int pix_per_block) {
+  __shared__ float s_v[2][kGlMaxC], s_h[2][kGlMaxC / 4], s_g[kGlMaxC];
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g8 = C >> 3;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, m = -3.0e38f;
+    for (int r = 0; r < ranges; ++r) {
+      a += psum[(static_cast<size_t>(b) * ranges + r) * C + c];
+      m = fmaxf(m, pmax[(static_cast<size_t>(b) * ranges + r) * C + c]);
+    }
+    s_v[0][c] = a / static_cast<float>(hw);
+    s_v[1][c] = m;
+  }
+  __syncthreads();
+  const int bsz = 2 * inter * C + 2 * inter + 2 * C;            // floats per branch
+  for (int it = warp; it < 2 * inter; it += 8) {
+    const int br = it / inter, u = it % inter;
+    const float* P = prm + br * bsz;
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(__ldg(P + static_cast<size_t>(u) * C + c), s_v[br][c], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) s_h[br][u] = fmaxf(fmaf(a, P[inter * C + u], P[inter * C + inter + u]), 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float tot = 0.f;
+    for (int br = 0; br < 2; ++br) {
+      const float* P = prm + br * bsz + inter * C + 2 * inter;   // w2t | s2 | t2
+      float a = 0.f;
+      for (int u = 0; u < inter; ++u) a = fmaf(__ldg(P + static_cast<size_t>(u) * C + c), s_h[br][u], a);
+      tot += fmaf(a, P[inter * C + c], P[inter * C + C + c]);
+    }
+    s_g[c] = tot;
+  }
+  __syncthreads();
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int n_pix = min(hw, p_begin + pix_per_block) - p_begin;
+  for (int it = threadIdx.x; it < n_pix * g8; it += blockDim.x) {
+    const int g = it / n_pix, pix = p_begin + it - g * n_pix;
+    const size_t off = ((static_cast<size_t>(b) * g8 + g) * hw + pix) * 8;
+    float lo[8], hi[8], lc[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(low + off)), lo);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(high + off)), hi);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(local + off)), lc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float wei = 1.f / (1.f + expf(-(s_g[g * 8 + j] + lc[j])));
+      lo[j] = 2.f * lo[j] * wei + 2.f * hi[j] * (1.f - wei);
+    }
+    *reinterpret_cast<uint4*>(dst + off) = pack8(lo);
+  }
+}
+
 }  // namespace stcd

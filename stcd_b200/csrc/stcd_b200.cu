@@ -172,6 +172,23 @@ struct SpatialGateOp {
   float2* stats = nullptr;     // [mult*chunk][h*w]
 };
 
+struct GlGateOp {
+  int src, dst, c, ranges;
+  std::vector<float> w;
+  float* w_dev = nullptr;
+  float* psum = nullptr;
+  float* pmax = nullptr;
+  float2* stats = nullptr;
+};
+
+struct VffmOp {
+  int low, high, mixed, local, dst, c, inter, ranges;
+  std::vector<float> w;
+  float* w_dev = nullptr;
+  float* psum = nullptr;
+  float* pmax = nullptr;
+};
+
 struct SumOp {
   int src[5], n, dst;
 };
@@ -194,7 +211,7 @@ struct EcamOp {
 };
 
 struct Op {
-  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head, 5 graph conv, 6 bilinear up, 7 layer norm, 8 attention, 9 dw conv, 10 T1 - T2 (abs or signed), 11 channel gate, 12 sum, 13 BIT token path, 14 channel attention, 15 spatial gate
+  int kind;  // 0 conv, 1 input pack, 2 ECAM head, 3 max-pool (space-to-depth source), 4 SegCD head, 5 graph conv, 6 bilinear up, 7 layer norm, 8 attention, 9 dw conv, 10 T1 - T2 (abs or signed), 11 channel gate, 12 sum, 13 BIT token path, 14 channel attention, 15 spatial gate, 16 global-local gate, 17 VFFM
   int idx;
 };
 
@@ -221,6 +238,8 @@ struct stcd_plan {
   std::vector<BitOp> bits;
   std::vector<ChanAttnOp> chan_attns;
   std::vector<SpatialGateOp> spatial_gates;
+  std::vector<GlGateOp> gl_gates;
+  std::vector<VffmOp> vffms;
   std::vector<Op> ops;
   uint8_t* workspace = nullptr;
   size_t workspace_bytes = 0;
@@ -411,6 +430,32 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
             sp, (__nv_bfloat16*)td.ptr, k.gate, B, k.c[i], ts.c / 8, td.c / 8, hw, k.c_tot, c_off);
         c_off += k.c[i];
       }
+      CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 16) {
+      const GlGateOp& k = plan->gl_gates[o.idx];
+      const Tensor& ts = plan->tensors[k.src];
+      const Tensor& td = plan->tensors[k.dst];
+      const int B = ts.mult * plan->chunk, hw = ts.h * ts.w;
+      const int n_items = B * (k.c / 8) * k.ranges;
+      stcd::chan_stats_kernel<<<(n_items + 7) / 8, 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, k.psum, k.pmax, k.c, ts.c / 8, hw, k.ranges,
+                                                                 n_items, k.c, 0);
+      stcd::sa_stats_kernel<<<dim3((hw + 255) / 256, B), 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, k.stats, k.c, ts.c / 8, hw);
+      stcd::gl_apply_kernel<<<dim3((ts.w + stcd::kSaTW - 1) / stcd::kSaTW, (ts.h + stcd::kSaTH - 1) / stcd::kSaTH, B),
+                              dim3(stcd::kSaTW, stcd::kSaTH), 0, st>>>((const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, k.stats, k.psum,
+                                                                       k.pmax, k.w_dev, k.c, ts.c / 8, td.c / 8, ts.h, ts.w, k.ranges);
+      CUDA_TRY(cudaGetLastError());
+    } else if (o.kind == 17) {
+      const VffmOp& k = plan->vffms[o.idx];
+      const Tensor& tm = plan->tensors[k.mixed];
+      const int B = tm.mult * plan->chunk, hw = tm.h * tm.w;
+      const int n_items = B * (k.c / 8) * k.ranges;
+      stcd::chan_stats_kernel<<<(n_items + 7) / 8, 256, 0, st>>>((const __nv_bfloat16*)tm.ptr, k.psum, k.pmax, k.c, tm.c / 8, hw, k.ranges,
+                                                                 n_items, k.c, 0);
+      const int ppb = std::max(32, std::min(1024, 4096 / (k.c / 8)));
+      stcd::vffm_apply_kernel<<<dim3((hw + ppb - 1) / ppb, B), 256, 0, st>>>(
+          (const __nv_bfloat16*)plan->tensors[k.low].ptr, (const __nv_bfloat16*)plan->tensors[k.high].ptr,
+          (const __nv_bfloat16*)plan->tensors[k.local].ptr, (__nv_bfloat16*)plan->tensors[k.dst].ptr, k.psum, k.pmax, k.w_dev, k.c, k.inter,
+          hw, k.ranges, ppb);
       CUDA_TRY(cudaGetLastError());
     } else if (o.kind == 15) {
       const SpatialGateOp& k = plan->spatial_gates[o.idx];
@@ -615,6 +660,17 @@ void stcd_plan_destroy(stcd_plan* plan) {
   for (SpatialGateOp& k : plan->spatial_gates) {
     if (k.w_dev) cudaFree(k.w_dev);
     if (k.stats) cudaFree(k.stats);
+  }
+  for (GlGateOp& k : plan->gl_gates) {
+    if (k.w_dev) cudaFree(k.w_dev);
+    if (k.psum) cudaFree(k.psum);
+    if (k.pmax) cudaFree(k.pmax);
+    if (k.stats) cudaFree(k.stats);
+  }
+  for (VffmOp& k : plan->vffms) {
+    if (k.w_dev) cudaFree(k.w_dev);
+    if (k.psum) cudaFree(k.psum);
+    if (k.pmax) cudaFree(k.pmax);
   }
   for (BitOp& k : plan->bits) {
     if (k.w_dev) cudaFree(k.w_dev);
@@ -995,6 +1051,47 @@ int stcd_plan_add_spatial_gate(stcd_plan* plan, int src_tensor, int dst_tensor, 
   k.w.insert(k.w.end(), shift, shift + c);
   plan->spatial_gates.push_back(std::move(k));
   plan->ops.push_back({15, (int)plan->spatial_gates.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_global_local_gate(stcd_plan* plan, int src_tensor, int dst_tensor, int c, const float* prm) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, src_tensor) || !valid_tensor(plan, dst_tensor) || !prm) return -fail(STCD_ERR_INVALID, "global-local gate: bad tensor id / NULL weights");
+  const Tensor& ts = plan->tensors[src_tensor];
+  const Tensor& td = plan->tensors[dst_tensor];
+  if (c < 8 || (c % 8) || c > stcd::kGlMaxC || ts.c < c || td.c < c || ts.h != td.h || ts.w != td.w || ts.mult != td.mult)
+    return -fail(STCD_ERR_INVALID, "global-local gate: c=%d (<= %d); src and dst must have the same shape", c, stcd::kGlMaxC);
+  GlGateOp k;
+  k.src = src_tensor;
+  k.dst = dst_tensor;
+  k.c = c;
+  k.ranges = std::max(1, std::min(16, ts.h * ts.w / stcd::kGateRangePix));
+  k.w.assign(prm, prm + 4 * (size_t)c + 51);
+  plan->gl_gates.push_back(std::move(k));
+  plan->ops.push_back({16, (int)plan->gl_gates.size() - 1});
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_vffm(stcd_plan* plan, int low, int high, int mixed, int local, int dst, int c, int inter, const float* prm) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  const int ids[5] = {low, high, mixed, local, dst};
+  for (int id : ids)
+    if (!valid_tensor(plan, id)) return -fail(STCD_ERR_INVALID, "VFFM: bad tensor id");
+  if (!prm || c < 8 || (c % 8) || c > stcd::kGlMaxC || inter < 1 || inter > stcd::kGlMaxC / 4)
+    return -fail(STCD_ERR_INVALID, "VFFM: c=%d (<= %d), inter=%d (<= %d)", c, stcd::kGlMaxC, inter, stcd::kGlMaxC / 4);
+  const Tensor& t0 = plan->tensors[low];
+  for (int id : ids) {
+    const Tensor& t = plan->tensors[id];
+    if (t.c != c || t.h != t0.h || t.w != t0.w || t.mult != t0.mult) return -fail(STCD_ERR_INVALID, "VFFM: all five tensors must be [m*chunk,h,w,%d]", c);
+  }
+  VffmOp k;
+  k.low = low, k.high = high, k.mixed = mixed, k.local = local, k.dst = dst, k.c = c, k.inter = inter;
+  k.ranges = std::max(1, std::min(16, t0.h * t0.w / stcd::kGateRangePix));
+  k.w.assign(prm, prm + 2 * ((size_t)2 * inter * c + 2 * inter + 2 * c));
+  plan->vffms.push_back(std::move(k));
+  plan->ops.push_back({17, (int)plan->vffms.size() - 1});
   return (int)plan->ops.size() - 1;
 }
 
@@ -1530,6 +1627,23 @@ int stcd_plan_finalize(stcd_plan* plan) {
     CUDA_TRY(cudaMalloc(&k.pmax, (size_t)plan->chunk * k.ranges * k.c_tot * sizeof(float)));
     CUDA_TRY(cudaMalloc(&k.gate, (size_t)plan->chunk * k.c_tot * sizeof(float)));
   }
+  for (GlGateOp& k : plan->gl_gates) {
+    const Tensor& ts = plan->tensors[k.src];
+    const size_t B = (size_t)ts.mult * plan->chunk;
+    CUDA_TRY(cudaMalloc(&k.w_dev, k.w.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(k.w_dev, k.w.data(), k.w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&k.psum, B * k.ranges * k.c * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&k.pmax, B * k.ranges * k.c * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&k.stats, B * ts.h * ts.w * sizeof(float2)));
+  }
+  for (VffmOp& k : plan->vffms) {
+    const Tensor& ts = plan->tensors[k.mixed];
+    const size_t B = (size_t)ts.mult * plan->chunk;
+    CUDA_TRY(cudaMalloc(&k.w_dev, k.w.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(k.w_dev, k.w.data(), k.w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&k.psum, B * k.ranges * k.c * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&k.pmax, B * k.ranges * k.c * sizeof(float)));
+  }
   for (SpatialGateOp& k : plan->spatial_gates) {
     const Tensor& ts = plan->tensors[k.src];
     CUDA_TRY(cudaMalloc(&k.w_dev, k.w.size() * sizeof(float)));
@@ -1636,6 +1750,7 @@ int64_t stcd_plan_launches(const stcd_plan* plan, int n_pairs) {
   per_chunk += (int64_t)plan->gates.size();                                    // a channel gate is two kernels
   for (const ChanAttnOp& k : plan->chan_attns) per_chunk += 2 * k.n_src;      // stats + apply per segment, one FC kernel
   per_chunk += (int64_t)plan->spatial_gates.size();                            // statistics + apply
+  per_chunk += 2 * (int64_t)plan->gl_gates.size() + (int64_t)plan->vffms.size();  // 3 kernels / 2 kernels
   per_chunk += 3 * (int64_t)plan->bits.size();                                 // tokenizer + mixer + coefficients + decoder
   for (const GraphOp& g : plan->graphs) per_chunk += 3 + (g.r > 1 ? 2 : 0);     // unpack, [pool], norm, [norm y], kNN, max-relative
   return chunks * per_chunk;

@@ -325,6 +325,47 @@ class SpatialGateSpec:
 
 
 @dataclass
+class GlobalLocalGateSpec:
+    """Global branch of ChangeGNNV2's Global_Local (models/ChangeVIG.py:377-385): dst = sigmoid(ch[c] * sp[pixel]) * src,
+    ch = relu((w_avg avg + w_max max) * scale + shift) (grouped (2,1) conv, bias + BN folded), sp = relu(conv5x5([mean, max]) + b)."""
+    name: str
+    src: str
+    dst: str
+    c: int
+    w_avg: np.ndarray            # float32 [c]
+    w_max: np.ndarray
+    scale: np.ndarray
+    shift: np.ndarray
+    w_sp: np.ndarray             # float32 [2][5][5]
+    b_sp: float
+
+    def packed(self) -> np.ndarray:
+        return np.concatenate([self.w_avg, self.w_max, self.scale, self.shift, self.w_sp.reshape(-1), [self.b_sp]]).astype(np.float32)
+
+
+@dataclass
+class VffmSpec:
+    """VFFM (models/ChangeVIG.py:452-460): dst = 2 low wei + 2 high (1 - wei), wei = sigmoid(MLP_avg(avgpool(mixed)) +
+    MLP_max(maxpool(mixed)) + local).  branches: (avg, max), each dict(w1 [inter][c], s1, t1, w2 [c][inter], s2, t2) with the
+    conv biases and BatchNorms folded into scale / shift."""
+    name: str
+    low: str
+    high: str
+    mixed: str
+    local: str
+    dst: str
+    c: int
+    inter: int
+    branches: Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray]]
+
+    def packed(self) -> np.ndarray:
+        out = []
+        for b in self.branches:
+            out += [b["w1"].reshape(-1), b["s1"], b["t1"], np.ascontiguousarray(b["w2"].T).reshape(-1), b["s2"], b["t2"]]
+        return np.concatenate(out).astype(np.float32)
+
+
+@dataclass
 class SumSpec:
     """dst = sum of up to five tensors (Dblock.forward, models/DTCDSCN.py:65-71)."""
     name: str
@@ -808,6 +849,12 @@ def op_bytes_per_pair(prog: Program, op) -> int:
     if isinstance(op, SpatialGateSpec):
         t = T[op.src]
         return t.mult * (op.c * t.h * t.w * 2 * 3 + t.h * t.w * 8 * 2)
+    if isinstance(op, GlobalLocalGateSpec):
+        t = T[op.src]
+        return t.mult * (op.c * t.h * t.w * 2 * 4 + t.h * t.w * 8 * 2)
+    if isinstance(op, VffmSpec):
+        t = T[op.low]
+        return t.mult * op.c * t.h * t.w * 2 * 5
     if isinstance(op, BitTransformerSpec):
         t = T[op.src]
         return t.mult * op.c * t.h * t.w * 2 * 3            # tokenizer read + decoder read + write

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .lowering import (AbsDiffSpec, AttentionSpec, BitTransformerSpec, ChannelAttentionSpec, ChannelGateSpec, SpatialGateSpec, SumSpec, BilinearUpSpec, ConvSpec, DWConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec,
+from .lowering import (AbsDiffSpec, AttentionSpec, BitTransformerSpec, ChannelAttentionSpec, ChannelGateSpec, GlobalLocalGateSpec, SpatialGateSpec, SumSpec, VffmSpec, BilinearUpSpec, ConvSpec, DWConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec,
                        LayerNormSpec, MaxPoolS2DSpec, Program, SegHeadSpec)
 
 
@@ -95,6 +95,13 @@ class Plan:
                 w_, sc_, sh_ = (np.ascontiguousarray(a, np.float32) for a in (op.w, op.scale, op.shift))
                 _lib.check_id(lib.stcd_plan_add_spatial_gate(h, ids[op.src], ids[op.dst], op.c, _fptr(w_), _fptr(sc_), _fptr(sh_)),
                               f"spatial gate {op.name}")
+            elif isinstance(op, GlobalLocalGateSpec):
+                prm = op.packed()
+                _lib.check_id(lib.stcd_plan_add_global_local_gate(h, ids[op.src], ids[op.dst], op.c, _fptr(prm)), f"global-local gate {op.name}")
+            elif isinstance(op, VffmSpec):
+                prm = op.packed()
+                _lib.check_id(lib.stcd_plan_add_vffm(h, ids[op.low], ids[op.high], ids[op.mixed], ids[op.local], ids[op.dst], op.c, op.inter,
+                                                     _fptr(prm)), f"VFFM {op.name}")
             elif isinstance(op, SumSpec):
                 arr = (C.c_int * len(op.srcs))(*[ids[s_] for s_ in op.srcs])
                 _lib.check_id(lib.stcd_plan_add_sum(h, arr, len(op.srcs), ids[op.dst]), f"sum {op.name}")

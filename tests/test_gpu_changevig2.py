@@ -1,0 +1,95 @@
+"""ChangeGNNV2 and the three ChangeGNNV2_Compare variants on the GPU against the oracle, the emulator and the golden fixtures
+generated from the unmodified reference (models/ChangeVIG.py:315-460,537-918; gcn_lib restated, see oracle/gcn.py): logits within
+2e-2 absolute (bf16 path), change maps agreeing on >= 99.9 % of decided pixels."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import emulate, nets
+from stcd_b200 import changevig, synth
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 2e-2
+
+
+def _net(mode):
+    cls = "ChangeGNNV2" if mode == "cross" else "ChangeGNNV2_Compare"
+    net = changevig.ChangeGNNV2() if mode == "cross" else changevig.ChangeGNNV2_Compare(diff_mode=mode)
+    return synth.prepare_(net.eval(), cls)
+
+
+def _agreement(y, ref):
+    margin = (ref[:, 1] - ref[:, 0]).abs()
+    agree = (y[:, 1] > y[:, 0]) == (ref[:, 1] > ref[:, 0])
+    return agree[margin > BF16_TOL].float().mean().item()
+
+
+@pytest.mark.parametrize("mode", ["cross", "sub", "abs", "conc"])
+def test_forward_matches_oracle(mode):
+    net = _net(mode)
+    x1, x2 = synth.image_pairs(3, 256, 256)
+    with torch.no_grad():
+        ref = nets.changegnn_v2_forward(net.state_dict(), x1, x2, mode)[-1]
+    net = net.cuda()
+    net.chunk_pairs = 2                      # 3 pairs -> one full chunk + a ragged one
+    y = net(x1.cuda(), x2.cuda())
+    assert isinstance(y, list) and len(y) == 1 and y[0].shape == ref.shape and y[0].dtype == torch.float32
+    y = y[-1].cpu()
+    assert (y - ref).abs().max().item() < BF16_TOL, "kernel vs fp32 oracle"
+    assert _agreement(y, ref) >= 0.999
+    assert 0.02 < (ref[:, 1] > ref[:, 0]).float().mean().item() < 0.98
+
+
+def test_decoder_tensors_match_emulator():
+    """Every DecoderV2 tensor of one chunk against the emulator's: localises a wrong op (block-diagonal convs, gates, VFFM)."""
+    net = _net("cross")
+    x1, x2 = synth.image_pairs(1, 256, 256)
+    keep = {}
+    emu = emulate.run_program(net.lower(256, 256), x1, x2, chunk=1, keep=keep)[0]
+    net = net.cuda()
+    net.chunk_pairs = 1
+    y = net(x1.cuda(), x2.cuda())[-1].cpu()
+    assert (y - emu).abs().max().item() < 1.5e-2
+    torch.cuda.synchronize()
+    plan = net.plan_for(x1.cuda())
+    bad = []
+    for name in plan.prog.tensors:
+        if not name.startswith("decoder."):
+            continue
+        got, want = plan.read_tensor(name), keep[name]
+        err = ((got - want).abs().mean() / (want.abs().mean() + 1e-3)).item()
+        if err > 0.03:
+            bad.append((name, err))
+    assert not bad, bad[:8]
+
+
+@pytest.mark.parametrize("case,mode", [("changegnn_v2", "cross"), ("changegnn_v2_sub", "sub")])
+def test_forward_matches_golden(case, mode, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"{case}.npz"))
+    net = _net(mode).cuda()
+    x1, x2 = synth.image_pairs(int(g["batch"]), int(g["h"]), int(g["w"]), seed=int(g["data_seed"]))
+    y = net(x1.cuda(), x2.cuda())[-1].cpu()
+    ref = torch.from_numpy(g["out0"])
+    assert (y - ref).abs().max().item() < BF16_TOL
+    assert _agreement(y, ref) >= 0.999
+
+
+def test_properties_and_define_G():
+    from types import SimpleNamespace
+    from stcd_b200 import networks
+    net = _net("cross").cuda()
+    x1, x2 = synth.image_pairs(5, 256, 256)
+    net.chunk_pairs = 4
+    y = net(x1.cuda(), x2.cuda())[-1]
+    assert torch.equal(y, net(x1.cuda(), x2.cuda())[-1]), "forward must be deterministic"
+    perm = torch.tensor([3, 1, 4, 0, 2])
+    yp = net(x1[perm].cuda(), x2[perm].cuda())[-1]
+    assert torch.equal(yp, y[perm.cuda()]), "pairs are independent: permuting the batch permutes the logits"
+    plan = net.plan_for(x1.cuda())
+    outs = plan.forward_host(x1.pin_memory(), x2.pin_memory())
+    assert torch.equal(outs[-1], y.cpu()), "host-buffer path must equal the device path bit for bit"
+    for key, mode in (("ChangeGNNV2", "cross"), ("ChangeGNNV2_sub", "sub"), ("ChangeGNNV2_abs", "abs"), ("ChangeGNNV2_conc", "conc")):
+        n2 = networks.define_G(SimpleNamespace(net_G=key, n_class=2, embed_dim=256, img_size=256), gpu_ids=[0])
+        assert isinstance(n2, changevig.ChangeGNNV2) and n2.diff_mode == mode and next(n2.parameters()).is_cuda

@@ -241,6 +241,34 @@ def test_changegnn_program_matches_oracle():
         net.lower(128, 128)            # pos_embed is not resized: the net only runs at img_size (ChangeVIG.py:87)
 
 
+@pytest.mark.parametrize("mode", ["cross", "sub", "abs", "conc"])
+def test_changegnn_v2_program_matches_oracle(mode):
+    """ChangeGNNV2 / ChangeGNNV2_Compare: the V1 ViG encoder + HFFM (Cross_ConCat as block-diagonal convs | Sub | Abs | Conc split
+    along K, residual bottleneck, Global_Local with its 1x1 / 3x3 / 7x7 depth-wise convs + 1x1 mix composed into one 7x7 conv)
+    + VFFM, through the emulator."""
+    from stcd_b200 import changevig
+    cls = "ChangeGNNV2" if mode == "cross" else "ChangeGNNV2_Compare"
+    net = changevig.ChangeGNNV2() if mode == "cross" else changevig.ChangeGNNV2_Compare(diff_mode=mode)
+    net = synth.prepare_(net.eval(), cls)
+    x1, x2 = synth.image_pairs(1, 256, 256)
+    with torch.no_grad():
+        y = nets.changegnn_v2_forward(net.state_dict(), x1, x2, mode)
+    prog = net.lower(256, 256)
+    ye = emulate.run_program(prog, x1, x2, chunk=1)
+    assert len(ye) == len(y) == 1 and ye[0].shape == y[0].shape == (1, 2, 256, 256)
+    assert (ye[0] - y[0]).abs().max().item() < BF16_TOL
+    margin = (y[0][:, 1] - y[0][:, 0]).abs()
+    agree = (ye[0][:, 1] > ye[0][:, 0]) == (y[0][:, 1] > y[0][:, 0])
+    assert agree[margin > BF16_TOL].float().mean().item() >= 0.999
+    assert 0.02 < (y[0][:, 1] > y[0][:, 0]).float().mean().item() < 0.98, "degenerate change map"
+    assert sum(isinstance(o, L.GlobalLocalGateSpec) for o in prog.ops) == 4 and sum(isinstance(o, L.VffmSpec) for o in prog.ops) == 3
+    if mode == "cross":
+        # block-diagonal grouped conv: 1 / 1 / 2 / 2 channel blocks for 80 / 160 / 400 / 640 channels
+        assert sum(".cross_conc.diff." in o.name for o in prog.ops if isinstance(o, L.ConvSpec)) == 6
+    with pytest.raises(ValueError):
+        net.lower(512, 512)
+
+
 def test_changeformer_program_matches_oracle():
     """Config C5's net: Linear layers as 1x1 convs, strided patch-embedding / spatial-reduction convs, LayerNorm,
     64-key attention and depth-wise conv ops -- checked through the emulator."""
