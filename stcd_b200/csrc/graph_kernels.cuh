@@ -17,21 +17,33 @@ namespace stcd {
 
 // xn[b][:, n] = x[b][:, n] / max(||x[b, :, n]||_2, 1e-12)   (F.normalize(x, p=2, dim=1)).  One thread per node, coalesced
 // over n; the channel sum runs in index order, the division is IEEE.
+// Block = 32 nodes x 8 channel slices (grid: node groups x images): slice s sums channels s, s + 8, ... in index order, the 8
+// partial sums are added in slice order (fixed order -> deterministic), then every slice writes its channels.
 __global__ void __launch_bounds__(256) normalize_nodes_kernel(const float* __restrict__ x, float* __restrict__ xn, int B, int C,
                                                              int N) {
-  const size_t total = static_cast<size_t>(B) * N;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t b = i / N, n = i - b * N;
-    const float* p = x + b * C * N + n;
+  __shared__ float part[8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int groups = (N + 31) / 32;
+  for (int item = blockIdx.x; item < B * groups; item += gridDim.x) {
+    const int b = item / groups, n = (item - b * groups) * 32 + lane;
+    const bool ok = n < N;
+    const float* p = x + static_cast<size_t>(b) * C * N + n;
     float s = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float v = __ldg(p + static_cast<size_t>(c) * N);
-      s = fmaf(v, v, s);
-    }
-    const float den = fmaxf(sqrtf(s), 1e-12f);
-    float* o = xn + b * C * N + n;
-    for (int c = 0; c < C; ++c) o[static_cast<size_t>(c) * N] = __fdiv_rn(__ldg(p + static_cast<size_t>(c) * N), den);
+    if (ok)
+      for (int c = slice; c < C; c += 8) {
+        const float v = __ldg(p + static_cast<size_t>(c) * N);
+        s = fmaf(v, v, s);
+      }
+    __syncthreads();
+    part[slice][lane] = s;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += part[k][lane];
+    const float den = fmaxf(sqrtf(tot), 1e-12f);
+    float* o = xn + static_cast<size_t>(b) * C * N + n;
+    if (ok)
+      for (int c = slice; c < C; c += 8) o[static_cast<size_t>(c) * N] = __fdiv_rn(__ldg(p + static_cast<size_t>(c) * N), den);
   }
 }
 
@@ -52,32 +64,55 @@ __global__ void __launch_bounds__(256) knn_graph_kernel(const float* __restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* xb = xn + static_cast<size_t>(b) * C * N;
   const float* yb = yn + static_cast<size_t>(b) * C * M;
-  float dot[8][8], xsq[8], ysq[8];
+  // packed fp32 accumulators (FFMA2): key pairs (2j, 2j + 1) of one query share an instruction.  Each lane of an FFMA2 is an IEEE
+  // fma and the channel order is unchanged, so every dot product is bit-identical to the scalar loop.
+  float2 dot2[8][4], xsq2[4], ysq2[4];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    xsq[q] = 0.f;
-    ysq[q] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dot[q][j] = 0.f;
+    for (int j = 0; j < 4; ++j) dot2[q][j] = make_float2(0.f, 0.f);
   }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) xsq2[j] = ysq2[j] = make_float2(0.f, 0.f);
+  // 16-byte staging copies need 16-byte aligned rows
+  const bool vec_ok = ((N & 3) == 0) && ((M & 3) == 0) && (((reinterpret_cast<uintptr_t>(xn) | reinterpret_cast<uintptr_t>(yn)) & 15) == 0);
   for (int c0 = 0; c0 < C; c0 += kKnnCC) {
     __syncthreads();
-    // cp.async (4 B, zero-fill out of range): all 40 copies of a thread are in flight at once
-    for (int i = threadIdx.x; i < kKnnQ * kKnnCC; i += blockDim.x) {
-      const int q = i % kKnnQ, cc = i / kKnnQ;
-      const int n = n0 + q, c = c0 + cc;
-      const bool ok = (n < N) && (c < C);
-      const float* gp = xb + (ok ? static_cast<size_t>(c) * N + n : 0);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&xs[cc][q]))),
-                   "l"(gp), "r"(ok ? 4 : 0) : "memory");
-    }
-    for (int i = threadIdx.x; i < kKnnM * kKnnCC; i += blockDim.x) {
-      const int j = i % kKnnM, cc = i / kKnnM;
-      const int c = c0 + cc;
-      const bool ok = (j < M) && (c < C);
-      const float* gp = yb + (ok ? static_cast<size_t>(c) * M + j : 0);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&ys[cc][j]))),
-                   "l"(gp), "r"(ok ? 4 : 0) : "memory");
+    // cp.async with zero-fill out of range; all copies of a thread are in flight at once
+    if (vec_ok) {
+      for (int i = threadIdx.x; i < (kKnnQ / 4) * kKnnCC; i += blockDim.x) {
+        const int q = (i % (kKnnQ / 4)) * 4, cc = i / (kKnnQ / 4);
+        const int n = n0 + q, c = c0 + cc;
+        const bool ok = (n < N) && (c < C);
+        const float* gp = xb + (ok ? static_cast<size_t>(c) * N + n : 0);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&xs[cc][q]))),
+                     "l"(gp), "r"(ok ? 16 : 0) : "memory");
+      }
+      for (int i = threadIdx.x; i < (kKnnM / 4) * kKnnCC; i += blockDim.x) {
+        const int j = (i % (kKnnM / 4)) * 4, cc = i / (kKnnM / 4);
+        const int c = c0 + cc;
+        const bool ok = (j < M) && (c < C);
+        const float* gp = yb + (ok ? static_cast<size_t>(c) * M + j : 0);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&ys[cc][j]))),
+                     "l"(gp), "r"(ok ? 16 : 0) : "memory");
+      }
+    } else {
+      for (int i = threadIdx.x; i < kKnnQ * kKnnCC; i += blockDim.x) {
+        const int q = i % kKnnQ, cc = i / kKnnQ;
+        const int n = n0 + q, c = c0 + cc;
+        const bool ok = (n < N) && (c < C);
+        const float* gp = xb + (ok ? static_cast<size_t>(c) * N + n : 0);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&xs[cc][q]))),
+                     "l"(gp), "r"(ok ? 4 : 0) : "memory");
+      }
+      for (int i = threadIdx.x; i < kKnnM * kKnnCC; i += blockDim.x) {
+        const int j = i % kKnnM, cc = i / kKnnM;
+        const int c = c0 + cc;
+        const bool ok = (j < M) && (c < C);
+        const float* gp = yb + (ok ? static_cast<size_t>(c) * M + j : 0);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&ys[cc][j]))),
+                     "l"(gp), "r"(ok ? 4 : 0) : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -87,16 +122,28 @@ __global__ void __launch_bounds__(256) knn_graph_kernel(const float* __restrict_
       const float4 xa = *reinterpret_cast<const float4*>(&xs[cc][warp * 8]), xb4 = *reinterpret_cast<const float4*>(&xs[cc][warp * 8 + 4]);
       const float4 ya = *reinterpret_cast<const float4*>(&ys[cc][lane * 8]), yb4 = *reinterpret_cast<const float4*>(&ys[cc][lane * 8 + 4]);
       const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb4.x, xb4.y, xb4.z, xb4.w};
-      const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb4.x, yb4.y, yb4.z, yb4.w};
+      const float2 yp[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb4.x, yb4.y), make_float2(yb4.z, yb4.w)};
+      const float2 xp[4] = {make_float2(xa.x, xa.y), make_float2(xa.z, xa.w), make_float2(xb4.x, xb4.y), make_float2(xb4.z, xb4.w)};
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        xsq[q] = fmaf(xv[q], xv[q], xsq[q]);
+        const float2 xx = make_float2(xv[q], xv[q]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dot[q][j] = fmaf(xv[q], yv[j], dot[q][j]);
+        for (int j = 0; j < 4; ++j) dot2[q][j] = __ffma2_rn(xx, yp[j], dot2[q][j]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ysq[j] = fmaf(yv[j], yv[j], ysq[j]);
+      for (int j = 0; j < 4; ++j) {
+        xsq2[j] = __ffma2_rn(xp[j], xp[j], xsq2[j]);
+        ysq2[j] = __ffma2_rn(yp[j], yp[j], ysq2[j]);
+      }
     }
+  }
+  float dot[8][8], xsq[8], ysq[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    xsq[2 * j] = xsq2[j].x, xsq[2 * j + 1] = xsq2[j].y;
+    ysq[2 * j] = ysq2[j].x, ysq[2 * j + 1] = ysq2[j].y;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dot[q][2 * j] = dot2[q][j].x, dot[q][2 * j + 1] = dot2[q][j].y;
   }
   // distances, in place: the reference's order of operations (x_sq + (-2 * inner)) + y_sq, then + relative_pos
 #pragma unroll

@@ -375,8 +375,9 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
         stcd::avgpool_nodes_kernel<<<nb((size_t)B * k.c * M, 8), 256, 0, st>>>(k.xf, k.yf, (size_t)B * k.c, ts.h, ts.w, k.r);
         y = k.yf;
       }
-      stcd::normalize_nodes_kernel<<<nb((size_t)B * N, 8), 256, 0, st>>>(k.xf, k.xn, B, k.c, N);
-      if (k.r > 1) stcd::normalize_nodes_kernel<<<nb((size_t)B * M, 8), 256, 0, st>>>(k.yf, k.yn, B, k.c, M);
+      auto ng = [](int B_, int n_) { return (unsigned)std::max(1, std::min(B_ * ((n_ + 31) / 32), 148 * 16)); };
+      stcd::normalize_nodes_kernel<<<ng(B, N), 256, 0, st>>>(k.xf, k.xn, B, k.c, N);
+      if (k.r > 1) stcd::normalize_nodes_kernel<<<ng(B, M), 256, 0, st>>>(k.yf, k.yn, B, k.c, M);
       stcd::knn_graph_kernel<<<dim3((N + stcd::kKnnQ - 1) / stcd::kKnnQ, B), 256, 0, st>>>(k.xn, k.r > 1 ? k.yn : k.xn, k.relpos_dev, k.c, N, M,
                                                                                        k.k, k.dilation, k.idx);
       stcd::max_relative_nc8_kernel<<<nb((size_t)B * (k.c / 8) * N, 8), 256, 0, st>>>(k.xf, y, k.idx, B, k.c, N, M, k.k,
@@ -1980,8 +1981,9 @@ int stcd_knn_graph(const float* x, const float* y, const float* relpos, int B, i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* xn = scratch;
   float* yn = y ? scratch + (size_t)B * C * N : scratch;
-  stcd::normalize_nodes_kernel<<<(unsigned)std::min<size_t>(((size_t)B * N + 255) / 256, 148 * 8), 256, 0, st>>>(x, xn, B, C, N);
-  if (y) stcd::normalize_nodes_kernel<<<(unsigned)std::min<size_t>(((size_t)B * M + 255) / 256, 148 * 8), 256, 0, st>>>(y, yn, B, C, M);
+  auto ng = [](int B_, int n_) { return (unsigned)std::max(1, std::min(B_ * ((n_ + 31) / 32), 148 * 16)); };
+  stcd::normalize_nodes_kernel<<<ng(B, N), 256, 0, st>>>(x, xn, B, C, N);
+  if (y) stcd::normalize_nodes_kernel<<<ng(B, M), 256, 0, st>>>(y, yn, B, C, M);
   stcd::knn_graph_kernel<<<dim3((N + stcd::kKnnQ - 1) / stcd::kKnnQ, B), 256, 0, st>>>(xn, yn, relpos, C, N, M, k, dilation,
                                                                                    reinterpret_cast<long long*>(nn_idx));
   CUDA_TRY(cudaGetLastError());
