@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
 }
 
 // Spatial-reduction attention (ChangeFormer.py:338-358): out[n] = softmax_j(q[n].k[j] * scale) v[j] per head, NK <= 64
-// keys.  grid (ceil(N / 128), heads, B), 128 threads = 128 queries; the head's K and V (fp32, [NK][D]) sit in shared
+// keys.  grid (ceil(N / 256), heads, B), 128 threads = 256 queries; the head's K and V (fp32, [NK][D]) sit in shared
 // memory and every lane reads the same address (broadcast).  q streams through registers 8 channels at a time, the 64
 // scores stay in registers; the [N, NK] score matrix never exists in memory.
 constexpr int kAttnMaxKeys = 64;
@@ -98,73 +98,87 @@ __global__ void __launch_bounds__(128) sr_attention_kernel(const __nv_bfloat16* 
   __shared__ __align__(16) float sv[kAttnMaxKeys][D];
   const int b = blockIdx.z, hd = blockIdx.y;
   const int g0 = hd * (D / 8);                 // first channel group of this head inside q / k; v sits C/8 groups later
+  // consecutive lanes take consecutive channel groups of one key: the two STS.128 per operand are bank-conflict free (the
+  // transposed order -- consecutive keys, 256-byte stride -- serialised every store 32 ways and cost as much as the math)
   for (int i = threadIdx.x; i < NK * (D / 8); i += blockDim.x) {
-    const int j = i % NK, g = i / NK;
+    const int g = i % (D / 8), j = i / (D / 8);
     float v[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(kv + ((static_cast<size_t>(b) * kv_c8 + g0 + g) * NK + j) * 8)), v);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) sk[j][g * 8 + e] = v[e];
+    *reinterpret_cast<float4*>(&sk[j][g * 8]) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(&sk[j][g * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
     unpack8(__ldg(reinterpret_cast<const uint4*>(kv + ((static_cast<size_t>(b) * kv_c8 + (C >> 3) + g0 + g) * NK + j) * 8)), v);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) sv[j][g * 8 + e] = v[e];
+    *reinterpret_cast<float4*>(&sv[j][g * 8]) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(&sv[j][g * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
   }
   __syncthreads();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float s[kAttnMaxKeys];
+  // two queries per thread (n0, n0 + 128), scores packed as (query 0, query 1) pairs: every broadcast LDS.128 of K / V feeds
+  // 8 FMAs as 4 FFMA2.  Each FFMA2 lane is an IEEE fma and the summation orders (channels, then keys) are the scalar ones.
+  const int n0 = blockIdx.x * (2 * blockDim.x) + threadIdx.x, n1 = n0 + blockDim.x;
+  if (n0 >= N) return;
+  const bool two = n1 < N;
+  float2 s[kAttnMaxKeys];
 #pragma unroll
-  for (int j = 0; j < kAttnMaxKeys; ++j) s[j] = 0.f;
+  for (int j = 0; j < kAttnMaxKeys; ++j) s[j] = make_float2(0.f, 0.f);
   for (int g = 0; g < D / 8; ++g) {
-    float qv[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(q + ((static_cast<size_t>(b) * q_c8 + g0 + g) * N + n) * 8)), qv);
+    float qa[8], qb[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(q + ((static_cast<size_t>(b) * q_c8 + g0 + g) * N + n0) * 8)), qa);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(q + ((static_cast<size_t>(b) * q_c8 + g0 + g) * N + (two ? n1 : n0)) * 8)), qb);
+    float2 qq[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qq[e] = make_float2(qa[e], qb[e]);
 #pragma unroll
     for (int j = 0; j < kAttnMaxKeys; ++j) {
       if (j < NK) {
         const float4 k0 = *reinterpret_cast<const float4*>(&sk[j][g * 8]), k1 = *reinterpret_cast<const float4*>(&sk[j][g * 8 + 4]);
-        s[j] = fmaf(qv[0], k0.x, s[j]);
-        s[j] = fmaf(qv[1], k0.y, s[j]);
-        s[j] = fmaf(qv[2], k0.z, s[j]);
-        s[j] = fmaf(qv[3], k0.w, s[j]);
-        s[j] = fmaf(qv[4], k1.x, s[j]);
-        s[j] = fmaf(qv[5], k1.y, s[j]);
-        s[j] = fmaf(qv[6], k1.z, s[j]);
-        s[j] = fmaf(qv[7], k1.w, s[j]);
+        s[j] = __ffma2_rn(qq[0], make_float2(k0.x, k0.x), s[j]);
+        s[j] = __ffma2_rn(qq[1], make_float2(k0.y, k0.y), s[j]);
+        s[j] = __ffma2_rn(qq[2], make_float2(k0.z, k0.z), s[j]);
+        s[j] = __ffma2_rn(qq[3], make_float2(k0.w, k0.w), s[j]);
+        s[j] = __ffma2_rn(qq[4], make_float2(k1.x, k1.x), s[j]);
+        s[j] = __ffma2_rn(qq[5], make_float2(k1.y, k1.y), s[j]);
+        s[j] = __ffma2_rn(qq[6], make_float2(k1.z, k1.z), s[j]);
+        s[j] = __ffma2_rn(qq[7], make_float2(k1.w, k1.w), s[j]);
       }
     }
   }
-  float mx = -CUDART_INF_F;
+  float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
 #pragma unroll
   for (int j = 0; j < kAttnMaxKeys; ++j)
     if (j < NK) {
-      s[j] *= scale;
-      mx = fmaxf(mx, s[j]);
+      s[j].x *= scale, s[j].y *= scale;
+      mx0 = fmaxf(mx0, s[j].x), mx1 = fmaxf(mx1, s[j].y);
     }
-  float den = 0.f;
+  float den0 = 0.f, den1 = 0.f;
 #pragma unroll
   for (int j = 0; j < kAttnMaxKeys; ++j) {
-    s[j] = (j < NK) ? expf(s[j] - mx) : 0.f;
-    den += s[j];
+    s[j].x = (j < NK) ? expf(s[j].x - mx0) : 0.f;
+    s[j].y = (j < NK) ? expf(s[j].y - mx1) : 0.f;
+    den0 += s[j].x, den1 += s[j].y;
   }
-  const float inv = 1.f / den;
+  const float inv0 = 1.f / den0, inv1 = 1.f / den1;
   for (int g = 0; g < D / 8; ++g) {
-    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float2 oa[4], ob[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oa[e] = ob[e] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < kAttnMaxKeys; ++j) {
       if (j < NK) {
         const float4 v0 = *reinterpret_cast<const float4*>(&sv[j][g * 8]), v1 = *reinterpret_cast<const float4*>(&sv[j][g * 8 + 4]);
-        o[0] = fmaf(s[j], v0.x, o[0]);
-        o[1] = fmaf(s[j], v0.y, o[1]);
-        o[2] = fmaf(s[j], v0.z, o[2]);
-        o[3] = fmaf(s[j], v0.w, o[3]);
-        o[4] = fmaf(s[j], v1.x, o[4]);
-        o[5] = fmaf(s[j], v1.y, o[5]);
-        o[6] = fmaf(s[j], v1.z, o[6]);
-        o[7] = fmaf(s[j], v1.w, o[7]);
+        const float2 p0 = make_float2(s[j].x, s[j].x), p1 = make_float2(s[j].y, s[j].y);
+        const float2 va = make_float2(v0.x, v0.y), vb = make_float2(v0.z, v0.w), vc = make_float2(v1.x, v1.y), vd = make_float2(v1.z, v1.w);
+        oa[0] = __ffma2_rn(p0, va, oa[0]), oa[1] = __ffma2_rn(p0, vb, oa[1]), oa[2] = __ffma2_rn(p0, vc, oa[2]), oa[3] = __ffma2_rn(p0, vd, oa[3]);
+        ob[0] = __ffma2_rn(p1, va, ob[0]), ob[1] = __ffma2_rn(p1, vb, ob[1]), ob[2] = __ffma2_rn(p1, vc, ob[2]), ob[3] = __ffma2_rn(p1, vd, ob[3]);
       }
     }
+    float o[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] *= inv;
-    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * out_c8 + g0 + g) * N + n) * 8) = pack8(o);
+    for (int e = 0; e < 4; ++e) o[2 * e] = oa[e].x * inv0, o[2 * e + 1] = oa[e].y * inv0;
+    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * out_c8 + g0 + g) * N + n0) * 8) = pack8(o);
+    if (two) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[2 * e] = ob[e].x * inv1, o[2 * e + 1] = ob[e].y * inv1;
+      *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * out_c8 + g0 + g) * N + n1) * 8) = pack8(o);
+    }
   }
 }
 
