@@ -641,3 +641,53 @@ def changegnn_v2_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor, diff_mode: 
     x = F.conv_transpose2d(x, sd[f"{pre}.convd1x.conv2d.weight"], sd[f"{pre}.convd1x.conv2d.bias"], stride=2, padding=1)
     x = resblock(f"{pre}.dense_1x.0", x)
     return [F.conv2d(x, sd[f"{pre}.change_probability.conv2d.weight"], sd[f"{pre}.change_probability.conv2d.bias"], padding=1)]
+
+
+# ------------------------------------------------------------------------------------------
+# VIG_V20_2 (registry key "GNN", models/ChangeVIG.py:921-1289): the same ViG encoder (prefix VIG_x2), conv_diff_V20 + csam_V20 + AFF
+def _csam_v20(sd: SD, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """csam_V20.forward, ChangeVIG.py:982-994."""
+    c = x.shape[1]
+    pooled = torch.cat([F.adaptive_avg_pool2d(x, 1), F.adaptive_max_pool2d(x, 1)], dim=2)
+    ch = F.gelu(_bn(sd, f"{pre}.batch_normal1", F.conv2d(pooled, sd[f"{pre}.conv1_1.weight"], sd[f"{pre}.conv1_1.bias"], groups=c)))
+    ch = F.linear(F.relu(F.linear(ch.permute(0, 2, 3, 1), sd[f"{pre}.liner1.weight"])), sd[f"{pre}.liner2.weight"], sd[f"{pre}.liner2.bias"])
+    ch = ch.permute(0, 3, 1, 2)
+    sp = torch.cat([x.mean(dim=1, keepdim=True), x.max(dim=1, keepdim=True)[0]], dim=1)
+    sp = F.conv2d(F.relu(F.conv2d(sp, sd[f"{pre}.conv2_1.weight"], None, padding=1)), sd[f"{pre}.conv2_2.weight"], None, padding=1)
+    return _bn(sd, f"{pre}.bt", (torch.sigmoid(ch) + torch.sigmoid(sp)) * x)
+
+
+def _aff(sd: SD, pre: str, x: torch.Tensor, residual: torch.Tensor) -> torch.Tensor:
+    """AFF.forward, ChangeVIG.py:1019-1028."""
+    xa = x + residual
+    xl = _seq_conv_bn(sd, f"{pre}.local_att", 3, F.relu(_seq_conv_bn(sd, f"{pre}.local_att", 0, xa)))
+    xg = _seq_conv_bn(sd, f"{pre}.global_att", 4, F.relu(_seq_conv_bn(sd, f"{pre}.global_att", 1, F.adaptive_avg_pool2d(xa, 1))))
+    wei = torch.sigmoid(xl + xg)
+    return 2 * x * wei + 2 * residual * (1 - wei)
+
+
+def vig_v20_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor) -> List[torch.Tensor]:
+    """VIG_V20_2.forward, ChangeVIG.py:1283-1289 with DecoderVIG_V20_2.forward (:1186-1239): [full-resolution logits]."""
+    f1, f2 = vig_encoder_features(sd, x1, pre="VIG_x2"), vig_encoder_features(sd, x2, pre="VIG_x2")
+    d = "TDec_x2"
+
+    def scale(k):
+        return _csam_v20(sd, f"{d}.csam{k}", _cross_concat_v2(sd, f"{d}.diff_c{k}", f1[k - 1], f2[k - 1]))
+
+    def up(k, t):
+        return F.conv_transpose2d(t, sd[f"{d}.trans_conv{k}.weight"], sd[f"{d}.trans_conv{k}.bias"], stride=2)
+
+    c = up(4, scale(4))
+    c = up(3, _aff(sd, f"{d}.aff3", scale(3), c))
+    c = up(2, _aff(sd, f"{d}.aff2", scale(2), c))
+    c = _aff(sd, f"{d}.aff1", scale(1), c)
+
+    def resblock(q, x):
+        o = F.relu(F.conv2d(x, sd[f"{q}.conv1.conv2d.weight"], sd[f"{q}.conv1.conv2d.bias"], padding=1))
+        return F.conv2d(o, sd[f"{q}.conv2.conv2d.weight"], sd[f"{q}.conv2.conv2d.bias"], padding=1) * 0.1 + x
+
+    x = F.conv_transpose2d(c, sd[f"{d}.convd2x.conv2d.weight"], sd[f"{d}.convd2x.conv2d.bias"], stride=2, padding=1)
+    x = resblock(f"{d}.dense_2x.0", x)
+    x = F.conv_transpose2d(x, sd[f"{d}.convd1x.conv2d.weight"], sd[f"{d}.convd1x.conv2d.bias"], stride=2, padding=1)
+    x = resblock(f"{d}.dense_1x.0", x)
+    return [F.conv2d(x, sd[f"{d}.change_probability.conv2d.weight"], sd[f"{d}.change_probability.conv2d.bias"], padding=1)]
