@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 15
+#define STCD_ABI_VERSION 16
 
 enum stcd_status {
   STCD_OK = 0,
@@ -231,6 +231,12 @@ int stcd_plan_add_spatial_gate(stcd_plan* plan, int src_tensor, int dst_tensor, 
  * ch = relu(BN(grouped (2,1) conv over [avgpool; maxpool])), sp = relu(conv5x5([mean_c, max_c]) + b).
  * prm HOST fp32: w_avg[c] | w_max[c] | scale[c] | shift[c] (conv bias and BatchNorm folded) | w_sp[2][5][5] | b_sp.  c <= 512. */
 int stcd_plan_add_global_local_gate(stcd_plan* plan, int src_tensor, int dst_tensor, int c, const float* prm);
+
+/* VIG_V20_2's csam_V20 (models/ChangeVIG.py:956-994): dst = bt((sigmoid(ch[c]) + sigmoid(sp[pixel])) * src),
+ * ch = liner2(relu(liner1(gelu(BN(grouped (2,1) conv over [avgpool; maxpool]))))), sp = conv3x3(relu(conv3x3([mean_c, max_c]))).
+ * prm HOST fp32: w_avg[c] | w_max[c] | scale[c] | shift[c] | liner1[hid][c] | liner2^T[hid][c] | liner2 bias[c] | bt scale[c] |
+ * bt shift[c] | conv2_1[2][3][3] | conv2_2[3][3].  c <= 512, hid <= 128. */
+int stcd_plan_add_csam_gate(stcd_plan* plan, int src_tensor, int dst_tensor, int c, int hid, const float* prm);
 
 /* ChangeGNNV2's VFFM (models/ChangeVIG.py:452-460): dst = 2 low wei + 2 high (1 - wei),
  * wei = sigmoid(MLP_avg(avgpool(mixed)) + MLP_max(maxpool(mixed)) + local), mixed = low + high (a plan tensor), local = the

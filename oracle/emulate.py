@@ -299,6 +299,18 @@ def run_aux(op, T, chunk, ext, nv):
         sp = torch.relu(F.conv2d(m, torch.from_numpy(op.w_sp)[None], torch.tensor([op.b_sp]), padding=2))[:, 0]   # [n, h, w]
         T[op.dst][..., : op.c] = _bf16(torch.sigmoid(ch[:, None, None, :] * sp[..., None]) * x)
         return None
+    if isinstance(op, L.CsamGateSpec):
+        import torch.nn.functional as F
+        x = T[op.src][..., : op.c]
+        z = (x.mean(dim=(1, 2)) * torch.from_numpy(op.w_avg) + x.amax(dim=(1, 2)) * torch.from_numpy(op.w_max)) * torch.from_numpy(op.scale) \
+            + torch.from_numpy(op.shift)
+        ch = torch.relu(F.gelu(z) @ torch.from_numpy(op.l1).T) @ torch.from_numpy(op.l2).T + torch.from_numpy(op.b2)        # [n, c]
+        m = torch.stack([x.mean(dim=-1), x.amax(dim=-1)], dim=1)
+        sp = F.conv2d(torch.relu(F.conv2d(m, torch.from_numpy(op.w21)[None], None, padding=1)), torch.from_numpy(op.w22)[None, None], None,
+                      padding=1)[:, 0]
+        g = torch.sigmoid(ch)[:, None, None, :] + torch.sigmoid(sp)[..., None]
+        T[op.dst][..., : op.c] = _bf16(g * x * torch.from_numpy(op.bt_scale) + torch.from_numpy(op.bt_shift))
+        return None
     if isinstance(op, L.VffmSpec):
         low, high, mixed, local = T[op.low], T[op.high], T[op.mixed], T[op.local]
         g = 0.0

@@ -134,7 +134,7 @@ class EcamDesc(C.Structure):
     ]
 
 
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -160,6 +160,7 @@ SYMBOLS = [
     ("stcd_plan_add_spatial_gate", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                              C.POINTER(C.c_float)]),
     ("stcd_plan_add_global_local_gate", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    ("stcd_plan_add_csam_gate", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     ("stcd_plan_add_vffm", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     ("stcd_plan_add_sum", C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int]),
     ("stcd_plan_add_graph_conv", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),

@@ -599,31 +599,12 @@ def lower_changegnn_v2(sd: Dict[str, torch.Tensor], e: int, n_class: int, diff_m
     def hffm(k: int) -> str:
         ft, cin, hh, ww = feats[k - 1]
         q = f"decoder.hffm{k}." + ("cross_conc" if diff_mode == "cross" else "diff")
+        if diff_mode == "cross":
+            return global_local(k, _lower_cross_concat(p, sd, q, ft, cin, hh, ww, e), hh, ww)
         # ---- the difference feature `out` [cin]
         if diff_mode in ("sub", "abs"):
             out = p.tensor(f"{q}.out", 1, hh, ww, cin)
             p.ops.append(L.AbsDiffSpec(f"{q}.sub", ft, out, cin, signed=(diff_mode == "sub")))
-        elif diff_mode == "cross":
-            # grouped conv over the interleaved (a0, b0, a1, b1, ...) == block-diagonal dense conv over [a | b]; channel blocks
-            # keep the K-program short and skip most of the structural zeros
-            wg = sd[f"{q}.diff.0.weight"]                                  # [cin, 2, 3, 3]
-            sc, sh = cbn(f"{q}.diff", 0, cin)
-            out = p.tensor(f"{q}.out", 1, hh, ww, cin)
-            nb = -(-cin // 320)
-            blk = -(-cin // nb // 8) * 8
-            for c0 in range(0, cin, blk):
-                cb = min(blk, cin - c0)
-                taps = []
-                for ky in range(3):
-                    for kx in range(3):
-                        wt = torch.zeros(cb, 2 * cb)
-                        idx = torch.arange(cb)
-                        wt[idx, idx] = wg[c0: c0 + cb, 0, ky, kx]
-                        wt[idx, cb + idx] = wg[c0: c0 + cb, 1, ky, kx]
-                        taps.append((ky - 1, kx - 1, wt))
-                L.add_conv(p, f"{q}.diff.{c0}", [L.Segment(ft, cb, stream=0, c_off=c0, c_store=cb), L.Segment(ft, cb, stream=1, c_off=c0, c_store=cb)],
-                           [(0, 0, taps)], cb, hh, ww, 1, sc[c0: c0 + cb], sh[c0: c0 + cb], relu=True, out0=out, out0_coff=c0,
-                           macs_per_pair=hh * ww * 9 * 2 * cb)
         else:                                                              # conc: dense 3x3 over cat(a, b), split along K by stream
             wd = sd[f"{q}.diff.0.weight"]                                  # [cin, 2 cin, 3, 3]
             sc, sh = cbn(f"{q}.diff", 0, cin)
@@ -650,7 +631,9 @@ def lower_changegnn_v2(sd: Dict[str, torch.Tensor], e: int, n_class: int, diff_m
         sc, sh = cbn(f"{q}.conv", 6, e)
         L.add_conv(p, f"{q}.conv.6", [L.Segment(c2, e // 2)], L.conv_taps(sd[f"{q}.conv.6.weight"], pad=0), e, hh, ww, 1, sc, sh, relu=True, res=r,
                    out0=d, macs_per_pair=hh * ww * (e // 2) * e)
-        # ---- Global_Local
+        return global_local(k, d, hh, ww)
+
+    def global_local(k: int, d: str, hh: int, ww: int) -> str:
         g = f"decoder.hffm{k}.global_local"
         cs, ct = L.fold_bn(sd[f"{g}.channel_conv.bias"], L.bn_params(sd, f"{g}.channel_bn"), e)
         gated = p.tensor(f"{g}.gated", 1, hh, ww, e)
@@ -704,4 +687,208 @@ def lower_changegnn_v2(sd: Dict[str, torch.Tensor], e: int, n_class: int, diff_m
         c = vffm(k, hffm(k), c)
     _, _, hh, ww = feats[0]
     lower_decoder_tail(p, sd, c, hh, ww, e, n_class, "decoder", out_ext=0)
+    return p
+
+
+# ==========================================================================================
+# VIG_V20_2 (registry key "GNN", models/ChangeVIG.py:921-1289): the ViG encoder under the prefix VIG_x2, conv_diff_V20 + csam_V20 + AFF
+class _ConvDiffV20(_CrossConCat):
+    """models/ChangeVIG.py:921-944: Cross_ConCat with in_channels given as 2 * C."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__(in_channels // 2, out_channels)
+
+
+class _CsamV20(nn.Module):
+    """models/ChangeVIG.py:956-980."""
+
+    def __init__(self, c: int, ratio: int = 8):
+        super().__init__()
+        self.conv1_1 = nn.Conv2d(c, c, kernel_size=(2, 1), groups=c)
+        self.batch_normal1 = nn.BatchNorm2d(c)
+        self.liner1 = nn.Linear(c, c // ratio, bias=False)
+        self.liner2 = nn.Linear(c // ratio, c)
+        self.conv2_1 = nn.Conv2d(2, 1, 3, padding=1, bias=False)
+        self.conv2_2 = nn.Conv2d(1, 1, 3, padding=1, bias=False)
+        self.bt = nn.BatchNorm2d(c)
+
+
+class _AFF(nn.Module):
+    """models/ChangeVIG.py:996-1017."""
+
+    def __init__(self, c: int, r: int = 4):
+        super().__init__()
+        i = c // r
+        self.local_att = nn.Sequential(nn.Conv2d(c, i, 1), nn.BatchNorm2d(i), nn.ReLU(inplace=True), nn.Conv2d(i, c, 1), nn.BatchNorm2d(c))
+        self.global_att = nn.Sequential(nn.AdaptiveAvgPool2d(1), nn.Conv2d(c, i, 1), nn.BatchNorm2d(i), nn.ReLU(inplace=True),
+                                        nn.Conv2d(i, c, 1), nn.BatchNorm2d(c))
+
+
+class _DecoderVIGV20(nn.Module):
+    """models/ChangeVIG.py:1105-1184."""
+
+    def __init__(self, in_channels, e: int, output_nc: int):
+        super().__init__()
+        c1, c2, c3, c4 = in_channels
+        self.diff_c4 = _ConvDiffV20(2 * c4, e)
+        self.diff_c3 = _ConvDiffV20(2 * c3, e)
+        self.diff_c2 = _ConvDiffV20(2 * c2, e)
+        self.diff_c1 = _ConvDiffV20(2 * c1, e)
+        self.trans_conv4 = nn.ConvTranspose2d(e, e, kernel_size=2, stride=2)
+        self.trans_conv3 = nn.ConvTranspose2d(e, e, kernel_size=2, stride=2)
+        self.trans_conv2 = nn.ConvTranspose2d(e, e, kernel_size=2, stride=2)
+        for k in (4, 3, 2, 1):
+            setattr(self, f"csam{k}", _CsamV20(e))
+        for k in (3, 2, 1):
+            setattr(self, f"aff{k}", _AFF(e))
+        self.convd2x = _UpsampleConvLayer(e, e, 4, 2)
+        self.dense_2x = nn.Sequential(_ResidualBlock(e))
+        self.convd1x = _UpsampleConvLayer(e, e, 4, 2)
+        self.dense_1x = nn.Sequential(_ResidualBlock(e))
+        self.change_probability = _ConvLayer(e, output_nc, 3, 1, 1)
+        self.active = nn.Sigmoid()
+
+
+class VIG_V20_2(PlannedModule):
+    """models/ChangeVIG.py:1242-1289 (registry key ``GNN``, models/networks.py:210-211)."""
+    default_chunk_pairs = 32
+
+    def __init__(self, input_nc: int = 3, output_nc: int = 2, decoder_softmax: bool = False, embed_dim: int = 256,
+                 decoder_heads: str = "MLP"):
+        super().__init__()
+        if input_nc != 3:
+            raise NotImplementedError("the ViG Stem is hard-wired to 3 input channels (pyramid_vig.py:70)")
+        if decoder_softmax:
+            raise NotImplementedError("stcd_b200 serves decoder_softmax=False (models/networks.py:211)")
+        if output_nc > 8 or embed_dim % 64 or embed_dim > 512:
+            raise NotImplementedError("output_nc <= 8, embed_dim a multiple of 64 up to 512")
+        self.embed_dims = list(_CHANNELS)
+        self.embedding_dim = embed_dim
+        self.output_nc = output_nc
+        self.VIG_x2 = _EncoderV1(256)
+        self.TDec_x2 = _DecoderVIGV20(_CHANNELS, embed_dim, output_nc)
+        for m in self.VIG_x2.modules():             # EncoderVIG_V20_2.model_init, ChangeVIG.py:1078-1085
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight)
+                if m.bias is not None:
+                    m.bias.data.zero_()
+
+    def lower(self, h: int, w: int) -> L.Program:
+        return lower_vig_v20(self.state_dict(), self.embedding_dim, self.output_nc, h, w)
+
+    @torch.no_grad()
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor):
+        return self.plan_for(x1).forward(x1, x2)        # [cp]
+
+    def _wrap_outputs(self, outs):
+        return list(outs)
+
+
+def _lower_cross_concat(p: L.Program, sd, q: str, ft: str, cin: int, hh: int, ww: int, e: int) -> str:
+    """Cross_ConCat / conv_diff_V20 (ChangeVIG.py:315-347, 921-953) on the pair tensor ft -> [chunk, hh, ww, e]."""
+    def cbn(pre: str, i: int, cout: int):
+        return L.fold_bn(sd.get(f"{pre}.{i}.bias"), L.bn_params(sd, f"{pre}.{i + 1}"), cout)
+
+    wg = sd[f"{q}.diff.0.weight"]                                  # [cin, 2, 3, 3]
+    sc, sh = cbn(f"{q}.diff", 0, cin)
+    out = p.tensor(f"{q}.out", 1, hh, ww, cin)
+    nb = -(-cin // 320)
+    blk = -(-cin // nb // 8) * 8
+    for c0 in range(0, cin, blk):
+        cb = min(blk, cin - c0)
+        taps = []
+        for ky in range(3):
+            for kx in range(3):
+                wt = torch.zeros(cb, 2 * cb)
+                idx = torch.arange(cb)
+                wt[idx, idx] = wg[c0: c0 + cb, 0, ky, kx]
+                wt[idx, cb + idx] = wg[c0: c0 + cb, 1, ky, kx]
+                taps.append((ky - 1, kx - 1, wt))
+        L.add_conv(p, f"{q}.diff.{c0}", [L.Segment(ft, cb, stream=0, c_off=c0, c_store=cb), L.Segment(ft, cb, stream=1, c_off=c0, c_store=cb)],
+                   [(0, 0, taps)], cb, hh, ww, 1, sc[c0: c0 + cb], sh[c0: c0 + cb], relu=True, out0=out, out0_coff=c0,
+                   macs_per_pair=hh * ww * 9 * 2 * cb)
+    r = p.tensor(f"{q}.res", 1, hh, ww, e)
+    sc, sh = cbn(f"{q}.conv_res", 0, e)
+    L.add_conv(p, f"{q}.conv_res", [L.Segment(out, cin)], L.conv_taps(sd[f"{q}.conv_res.0.weight"], pad=1), e, hh, ww, 1, sc, sh, out0=r,
+               macs_per_pair=hh * ww * 9 * cin * e)
+    c1 = p.tensor(f"{q}.c1", 1, hh, ww, e // 2)
+    sc, sh = cbn(f"{q}.conv", 0, e // 2)
+    L.add_conv(p, f"{q}.conv.0", [L.Segment(out, cin)], L.conv_taps(sd[f"{q}.conv.0.weight"], pad=0), e // 2, hh, ww, 1, sc, sh, relu=True,
+               out0=c1, macs_per_pair=hh * ww * cin * e // 2)
+    c2 = p.tensor(f"{q}.c2", 1, hh, ww, e // 2)
+    sc, sh = cbn(f"{q}.conv", 3, e // 2)
+    L.add_conv(p, f"{q}.conv.3", [L.Segment(c1, e // 2)], L.conv_taps(sd[f"{q}.conv.3.weight"], pad=1), e // 2, hh, ww, 1, sc, sh, relu=True,
+               out0=c2, macs_per_pair=hh * ww * 9 * (e // 2) * (e // 2))
+    d = p.tensor(f"{q}.d", 1, hh, ww, e)
+    sc, sh = cbn(f"{q}.conv", 6, e)
+    L.add_conv(p, f"{q}.conv.6", [L.Segment(c2, e // 2)], L.conv_taps(sd[f"{q}.conv.6.weight"], pad=0), e, hh, ww, 1, sc, sh, relu=True, res=r,
+               out0=d, macs_per_pair=hh * ww * (e // 2) * e)
+    return d
+
+
+def lower_vig_v20(sd: Dict[str, torch.Tensor], e: int, n_class: int, h: int, w: int) -> L.Program:
+    """state_dict of the reference VIG_V20_2 -> fused-op Program (eval mode)."""
+    if h != 256 or w != 256:
+        raise ValueError(f"VIG_V20_2's encoder is built for 256x256 inputs (its pos_embed is not resized), got {h}x{w}")
+    sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
+    p = L.Program(model="VIG_V20_2", in_channels=3, h=h, w=w)
+    # the shared encoder lowering reads the prefix "encoder."
+    enc_sd = {("encoder." + k[len("VIG_x2."):]): v for k, v in sd.items() if k.startswith("VIG_x2.")}
+    feats = lower_vig_encoder(p, enc_sd, h, w)
+    ones = lambda c: np.ones(c, np.float32)  # noqa: E731
+    npf = lambda t: np.ascontiguousarray(t.numpy().astype(np.float32))  # noqa: E731
+    d = "TDec_x2"
+
+    def cbn(pre: str, i: int, cout: int):
+        return L.fold_bn(sd.get(f"{pre}.{i}.bias"), L.bn_params(sd, f"{pre}.{i + 1}"), cout)
+
+    def scale(k: int) -> str:
+        ft, cin, hh, ww = feats[k - 1]
+        x = _lower_cross_concat(p, sd, f"{d}.diff_c{k}", ft, cin, hh, ww, e)
+        g = f"{d}.csam{k}"
+        cs, ct = L.fold_bn(sd[f"{g}.conv1_1.bias"], L.bn_params(sd, f"{g}.batch_normal1"), e)
+        bs, bt = L.fold_bn(None, L.bn_params(sd, f"{g}.bt"), e)
+        wc = sd[f"{g}.conv1_1.weight"]
+        o = p.tensor(f"{g}.o", 1, hh, ww, e)
+        p.ops.append(L.CsamGateSpec(g, x, o, e, npf(wc[:, 0, 0, 0]), npf(wc[:, 0, 1, 0]), cs, ct, npf(sd[f"{g}.liner1.weight"]),
+                                    npf(sd[f"{g}.liner2.weight"]), npf(sd[f"{g}.liner2.bias"]), bs, bt, npf(sd[f"{g}.conv2_1.weight"][0]),
+                                    npf(sd[f"{g}.conv2_2.weight"][0, 0])))
+        return o
+
+    def up(k: int, x: str) -> str:
+        _, _, hh, ww = feats[k - 1]
+        o = p.tensor(f"{d}.trans_conv{k}.o", 1, 2 * hh, 2 * ww, e)
+        L.add_conv(p, f"{d}.trans_conv{k}", [L.Segment(x, e)], L.convT_phase_taps(sd[f"{d}.trans_conv{k}.weight"], 2, 0), e, hh, ww, 1, ones(e),
+                   npf(sd[f"{d}.trans_conv{k}.bias"]), osy=2, osx=2, out0=o, macs_per_pair=hh * ww * 4 * e * e)
+        return o
+
+    def aff(k: int, x: str, residual: str) -> str:
+        _, _, hh, ww = feats[k - 1]
+        a = f"{d}.aff{k}"
+        i = e // 4
+        xa = p.tensor(f"{a}.xa", 1, hh, ww, e)
+        p.ops.append(L.SumSpec(f"{a}.xa", [x, residual], xa))
+        l1 = p.tensor(f"{a}.l1", 1, hh, ww, i)
+        sc, sh = cbn(f"{a}.local_att", 0, i)
+        L.add_conv(p, f"{a}.local_att.0", [L.Segment(xa, e)], L.conv_taps(sd[f"{a}.local_att.0.weight"], pad=0), i, hh, ww, 1, sc, sh, relu=True,
+                   out0=l1, macs_per_pair=hh * ww * e * i)
+        l2 = p.tensor(f"{a}.l2", 1, hh, ww, e)
+        sc, sh = cbn(f"{a}.local_att", 3, e)
+        L.add_conv(p, f"{a}.local_att.3", [L.Segment(l1, i)], L.conv_taps(sd[f"{a}.local_att.3.weight"], pad=0), e, hh, ww, 1, sc, sh, out0=l2,
+                   macs_per_pair=hh * ww * i * e)
+        s1, t1 = cbn(f"{a}.global_att", 1, i)
+        s2, t2 = cbn(f"{a}.global_att", 4, e)
+        avg = dict(w1=npf(sd[f"{a}.global_att.1.weight"][:, :, 0, 0]), s1=s1, t1=t1, w2=npf(sd[f"{a}.global_att.4.weight"][:, :, 0, 0]), s2=s2, t2=t2)
+        zero = dict(w1=np.zeros((i, e), np.float32), s1=np.zeros(i, np.float32), t1=np.zeros(i, np.float32), w2=np.zeros((e, i), np.float32),
+                    s2=np.zeros(e, np.float32), t2=np.zeros(e, np.float32))     # AFF has no max branch
+        o = p.tensor(f"{a}.o", 1, hh, ww, e)
+        p.ops.append(L.VffmSpec(a, x, residual, xa, l2, o, e, i, (avg, zero)))
+        return o
+
+    c = up(4, scale(4))
+    c = up(3, aff(3, scale(3), c))
+    c = up(2, aff(2, scale(2), c))
+    c = aff(1, scale(1), c)
+    _, _, hh, ww = feats[0]
+    lower_decoder_tail(p, sd, c, hh, ww, e, n_class, d, out_ext=0)
     return p

@@ -290,4 +290,95 @@ __global__ void __launch_bounds__(256) vffm_apply_kernel(const __nv_bfloat16* __
   }
 }
 
+// csam_V20 (models/ChangeVIG.py:956-994): out = bt((sigmoid(ch[c]) + sigmoid(sp[pixel])) * x),
+//   ch = liner2(relu(liner1(gelu(BN(grouped (2,1) conv over [avg; max])))))        per image
+//   sp = conv3x3(relu(conv3x3([mean_c x, max_c x])))                                both bias-free, zero padding between them
+// prm: w_avg[C] | w_max[C] | cs[C] | ct[C] | l1[hid][C] | l2t[hid][C] | b2[C] | bt_s[C] | bt_t[C] | w21[2][3][3] | w22[3][3].
+// block (32, 8) pixels; grid (ceil(w/32), ceil(h/8), images); every CTA redoes the C x hid channel MLP of its image.
+__global__ void __launch_bounds__(kSaTW* kSaTH) csam_apply_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                  const float2* __restrict__ stats, const float* __restrict__ psum,
+                                                                  const float* __restrict__ pmax, const float* __restrict__ prm, int C,
+                                                                  int hid, int src_c8, int dst_c8, int h, int w, int ranges) {
+  __shared__ float2 s_t[kSaTH + 4][kSaTW + 4];
+  __shared__ float s_m[kSaTH + 2][kSaTW + 2];
+  __shared__ float s_w[27];
+  __shared__ float s_v[kGlMaxC], s_ch[kGlMaxC], s_h[kGlMaxC / 4];
+  const int b = blockIdx.z, x0 = blockIdx.x * kSaTW, y0 = blockIdx.y * kSaTH, hw = h * w;
+  const int tid = threadIdx.y * kSaTW + threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* l1 = prm + 4 * C;
+  const float* l2t = l1 + static_cast<size_t>(hid) * C;
+  const float* b2 = l2t + static_cast<size_t>(hid) * C;
+  const float* bt_s = b2 + C;
+  const float* bt_t = bt_s + C;
+  if (tid < 27) s_w[tid] = bt_t[C + tid];
+  for (int c = tid; c < C; c += kSaTW * kSaTH) {
+    float a = 0.f, m = -3.0e38f;
+    for (int r = 0; r < ranges; ++r) {
+      a += psum[(static_cast<size_t>(b) * ranges + r) * C + c];
+      m = fmaxf(m, pmax[(static_cast<size_t>(b) * ranges + r) * C + c]);
+    }
+    a /= static_cast<float>(hw);
+    const float z = fmaf(fmaf(prm[c], a, prm[C + c] * m), prm[2 * C + c], prm[3 * C + c]);
+    s_v[c] = 0.5f * z * (1.f + erff(z * 0.70710678118654752f));
+  }
+  for (int i = tid; i < (kSaTH + 4) * (kSaTW + 4); i += kSaTW * kSaTH) {
+    const int ty = i / (kSaTW + 4), tx = i % (kSaTW + 4);
+    const int gy = y0 + ty - 2, gx = x0 + tx - 2;
+    s_t[ty][tx] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? stats[static_cast<size_t>(b) * hw + gy * w + gx] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  for (int u = warp; u < hid; u += 8) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a = fmaf(__ldg(l1 + static_cast<size_t>(u) * C + c), s_v[c], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) s_h[u] = fmaxf(a, 0.f);
+  }
+  // first 3x3 conv + ReLU on the tile + 1 halo; positions outside the image are the second conv's zero padding
+  for (int i = tid; i < (kSaTH + 2) * (kSaTW + 2); i += kSaTW * kSaTH) {
+    const int ty = i / (kSaTW + 2), tx = i % (kSaTW + 2);
+    const int gy = y0 + ty - 1, gx = x0 + tx - 1;
+    float a = 0.f;
+    if (gy >= 0 && gy < h && gx >= 0 && gx < w) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float2 t = s_t[ty + ky][tx + kx];
+          a = fmaf(t.x, s_w[ky * 3 + kx], a);
+          a = fmaf(t.y, s_w[9 + ky * 3 + kx], a);
+        }
+      }
+      a = fmaxf(a, 0.f);
+    }
+    s_m[ty][tx] = a;
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kSaTW * kSaTH) {
+    float a = b2[c];
+    for (int u = 0; u < hid; ++u) a = fmaf(__ldg(l2t + static_cast<size_t>(u) * C + c), s_h[u], a);
+    s_ch[c] = 1.f / (1.f + expf(-a));
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x >= w || y >= h) return;
+  float a = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) a = fmaf(s_m[threadIdx.y + ky][threadIdx.x + kx], s_w[18 + ky * 3 + kx], a);
+  }
+  const float sp = 1.f / (1.f + expf(-a));
+  const int pix = y * w + x;
+  const __nv_bfloat16* s = src + (static_cast<size_t>(b) * src_c8 * hw + pix) * 8;
+  __nv_bfloat16* o = dst + (static_cast<size_t>(b) * dst_c8 * hw + pix) * 8;
+  for (int g = 0; g < (C >> 3); ++g) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(s + static_cast<size_t>(g) * hw * 8)), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf((s_ch[g * 8 + j] + sp) * v[j], __ldg(bt_s + g * 8 + j), __ldg(bt_t + g * 8 + j));
+    *reinterpret_cast<uint4*>(o + static_cast<size_t>(g) * hw * 8) = pack8(v);
+  }
+}
+
 }  // namespace stcd

@@ -174,6 +174,7 @@ struct SpatialGateOp {
 
 struct GlGateOp {
   int src, dst, c, ranges;
+  int hid = 0;                 // > 0: csam_V20 (channel MLP + two 3x3 spatial convs) instead of Global_Local's gate
   std::vector<float> w;
   float* w_dev = nullptr;
   float* psum = nullptr;
@@ -441,9 +442,13 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
       stcd::chan_stats_kernel<<<(n_items + 7) / 8, 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, k.psum, k.pmax, k.c, ts.c / 8, hw, k.ranges,
                                                                  n_items, k.c, 0);
       stcd::sa_stats_kernel<<<dim3((hw + 255) / 256, B), 256, 0, st>>>((const __nv_bfloat16*)ts.ptr, k.stats, k.c, ts.c / 8, hw);
-      stcd::gl_apply_kernel<<<dim3((ts.w + stcd::kSaTW - 1) / stcd::kSaTW, (ts.h + stcd::kSaTH - 1) / stcd::kSaTH, B),
-                              dim3(stcd::kSaTW, stcd::kSaTH), 0, st>>>((const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, k.stats, k.psum,
-                                                                       k.pmax, k.w_dev, k.c, ts.c / 8, td.c / 8, ts.h, ts.w, k.ranges);
+      const dim3 tg((ts.w + stcd::kSaTW - 1) / stcd::kSaTW, (ts.h + stcd::kSaTH - 1) / stcd::kSaTH, B), tb(stcd::kSaTW, stcd::kSaTH);
+      if (k.hid > 0)
+        stcd::csam_apply_kernel<<<tg, tb, 0, st>>>((const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, k.stats, k.psum, k.pmax, k.w_dev, k.c,
+                                                   k.hid, ts.c / 8, td.c / 8, ts.h, ts.w, k.ranges);
+      else
+        stcd::gl_apply_kernel<<<tg, tb, 0, st>>>((const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, k.stats, k.psum, k.pmax, k.w_dev, k.c,
+                                                 ts.c / 8, td.c / 8, ts.h, ts.w, k.ranges);
       CUDA_TRY(cudaGetLastError());
     } else if (o.kind == 17) {
       const VffmOp& k = plan->vffms[o.idx];
@@ -1072,6 +1077,16 @@ int stcd_plan_add_global_local_gate(stcd_plan* plan, int src_tensor, int dst_ten
   plan->gl_gates.push_back(std::move(k));
   plan->ops.push_back({16, (int)plan->gl_gates.size() - 1});
   return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_csam_gate(stcd_plan* plan, int src_tensor, int dst_tensor, int c, int hid, const float* prm) {
+  if (hid < 1 || hid > stcd::kGlMaxC / 4) return -fail(STCD_ERR_INVALID, "csam gate: hid=%d (1..%d)", hid, stcd::kGlMaxC / 4);
+  const int r = stcd_plan_add_global_local_gate(plan, src_tensor, dst_tensor, c, prm);   // same tensors and checks; weights replaced below
+  if (r < 0) return r;
+  GlGateOp& k = plan->gl_gates.back();
+  k.hid = hid;
+  k.w.assign(prm, prm + 7 * (size_t)c + 2 * (size_t)hid * c + 27);
+  return r;
 }
 
 int stcd_plan_add_vffm(stcd_plan* plan, int low, int high, int mixed, int local, int dst, int c, int inter, const float* prm) {

@@ -344,6 +344,31 @@ class GlobalLocalGateSpec:
 
 
 @dataclass
+class CsamGateSpec:
+    """csam_V20 (models/ChangeVIG.py:956-994): dst = bt((sigmoid(ch[c]) + sigmoid(sp[pixel])) * src); ch = liner2(relu(liner1(gelu(
+    (w_avg avg + w_max max) * scale + shift)))), sp = conv3x3(relu(conv3x3([mean, max]))) (both bias-free)."""
+    name: str
+    src: str
+    dst: str
+    c: int
+    w_avg: np.ndarray            # float32 [c]
+    w_max: np.ndarray
+    scale: np.ndarray            # conv1_1 bias + batch_normal1 folded
+    shift: np.ndarray
+    l1: np.ndarray               # float32 [hid][c]
+    l2: np.ndarray               # float32 [c][hid]
+    b2: np.ndarray               # float32 [c]
+    bt_scale: np.ndarray
+    bt_shift: np.ndarray
+    w21: np.ndarray              # float32 [2][3][3]
+    w22: np.ndarray              # float32 [3][3]
+
+    def packed(self) -> np.ndarray:
+        return np.concatenate([self.w_avg, self.w_max, self.scale, self.shift, self.l1.reshape(-1), np.ascontiguousarray(self.l2.T).reshape(-1),
+                               self.b2, self.bt_scale, self.bt_shift, self.w21.reshape(-1), self.w22.reshape(-1)]).astype(np.float32)
+
+
+@dataclass
 class VffmSpec:
     """VFFM (models/ChangeVIG.py:452-460): dst = 2 low wei + 2 high (1 - wei), wei = sigmoid(MLP_avg(avgpool(mixed)) +
     MLP_max(maxpool(mixed)) + local).  branches: (avg, max), each dict(w1 [inter][c], s1, t1, w2 [c][inter], s2, t2) with the
@@ -849,7 +874,7 @@ def op_bytes_per_pair(prog: Program, op) -> int:
     if isinstance(op, SpatialGateSpec):
         t = T[op.src]
         return t.mult * (op.c * t.h * t.w * 2 * 3 + t.h * t.w * 8 * 2)
-    if isinstance(op, GlobalLocalGateSpec):
+    if isinstance(op, (GlobalLocalGateSpec, CsamGateSpec)):
         t = T[op.src]
         return t.mult * (op.c * t.h * t.w * 2 * 4 + t.h * t.w * 8 * 2)
     if isinstance(op, VffmSpec):

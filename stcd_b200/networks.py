@@ -16,7 +16,7 @@ from torch.nn import init
 from .siamunet import SiamUnet_conc, SiamUnet_cross_conc, SiamUnet_diff, SiamUnet_sub, Unet
 from .changeformer import ChangeFormerV6
 from .bit import BASE_Transformer, ResNet
-from .changevig import ChangeGNNV1, ChangeGNNV2, ChangeGNNV2_Compare
+from .changevig import ChangeGNNV1, ChangeGNNV2, ChangeGNNV2_Compare, VIG_V20_2
 from .dsifn import DSIFN, vgg16_base
 from .dtcdscn import CDNet34, CDNet_model
 from .segcd import SegCD
@@ -26,7 +26,7 @@ from .snunet import SNUNet_ECAM
 # raises NotImplementedError like an unknown key does upstream, with the reason.
 _REFERENCE_ONLY = (
     "ChangeFormerV1", "ChangeFormerV2",
-    "ChangeFormerV3", "ChangeFormerV4", "ChangeFormerV5", "GNN",
+    "ChangeFormerV3", "ChangeFormerV4", "ChangeFormerV5",
 )
 
 _REGISTRY = {
@@ -52,6 +52,7 @@ _REGISTRY = {
     "ChangeGNNV2_sub": lambda a: ChangeGNNV2_Compare(embed_dim=a.embed_dim, img_size=a.img_size, diff_mode="sub"),
     "ChangeGNNV2_abs": lambda a: ChangeGNNV2_Compare(embed_dim=a.embed_dim, img_size=a.img_size, diff_mode="abs"),
     "ChangeGNNV2_conc": lambda a: ChangeGNNV2_Compare(embed_dim=a.embed_dim, img_size=a.img_size, diff_mode="conc"),
+    "GNN": lambda a: VIG_V20_2(embed_dim=a.embed_dim),                             # networks.py:210-211
 }
 
 
@@ -59,7 +60,7 @@ _REGISTRY = {
 CLASSES = {"SiamUnet_diff": SiamUnet_diff, "SiamUnet_conc": SiamUnet_conc, "SiamUnet_sub": SiamUnet_sub,
            "SiamUnet_cross_conc": SiamUnet_cross_conc, "Unet": Unet, "SNUNet_ECAM": SNUNet_ECAM, "SegCD": SegCD,
            "ChangeGNNV1": ChangeGNNV1, "ChangeFormerV6": ChangeFormerV6,
-           "BASE_Transformer": BASE_Transformer, "ResNet": ResNet, "ChangeGNNV2": ChangeGNNV2, "ChangeGNNV2_Compare": ChangeGNNV2_Compare,
+           "BASE_Transformer": BASE_Transformer, "ResNet": ResNet, "ChangeGNNV2": ChangeGNNV2, "ChangeGNNV2_Compare": ChangeGNNV2_Compare, "VIG_V20_2": VIG_V20_2,
            "CDNet_model": lambda in_channels=3, num_classes=2: CDNet34(in_channels, num_classes)}
 
 

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .lowering import (AbsDiffSpec, AttentionSpec, BitTransformerSpec, ChannelAttentionSpec, ChannelGateSpec, GlobalLocalGateSpec, SpatialGateSpec, SumSpec, VffmSpec, BilinearUpSpec, ConvSpec, DWConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec,
+from .lowering import (AbsDiffSpec, AttentionSpec, BitTransformerSpec, ChannelAttentionSpec, ChannelGateSpec, CsamGateSpec, GlobalLocalGateSpec, SpatialGateSpec, SumSpec, VffmSpec, BilinearUpSpec, ConvSpec, DWConvSpec, EcamHeadSpec, GraphConvSpec, InputPackSpec,
                        LayerNormSpec, MaxPoolS2DSpec, Program, SegHeadSpec)
 
 
@@ -98,6 +98,9 @@ class Plan:
             elif isinstance(op, GlobalLocalGateSpec):
                 prm = op.packed()
                 _lib.check_id(lib.stcd_plan_add_global_local_gate(h, ids[op.src], ids[op.dst], op.c, _fptr(prm)), f"global-local gate {op.name}")
+            elif isinstance(op, CsamGateSpec):
+                prm = op.packed()
+                _lib.check_id(lib.stcd_plan_add_csam_gate(h, ids[op.src], ids[op.dst], op.c, op.l1.shape[0], _fptr(prm)), f"csam gate {op.name}")
             elif isinstance(op, VffmSpec):
                 prm = op.packed()
                 _lib.check_id(lib.stcd_plan_add_vffm(h, ids[op.low], ids[op.high], ids[op.mixed], ids[op.local], ids[op.dst], op.c, op.inter,

@@ -78,6 +78,30 @@ def test_forward_matches_golden(case, mode, golden_dir):
     assert _agreement(y, ref) >= 0.999
 
 
+def test_vig_v20_matches_oracle_and_golden(golden_dir):
+    """Registry key "GNN" (VIG_V20_2): csam_V20 gates + AFF."""
+    net = synth.prepare_(changevig.VIG_V20_2().eval(), "VIG_V20_2")
+    x1, x2 = synth.image_pairs(3, 256, 256)
+    with torch.no_grad():
+        ref = nets.vig_v20_forward(net.state_dict(), x1, x2)[-1]
+    net = net.cuda()
+    net.chunk_pairs = 2
+    y = net(x1.cuda(), x2.cuda())
+    assert isinstance(y, list) and len(y) == 1
+    y = y[-1].cpu()
+    assert (y - ref).abs().max().item() < BF16_TOL and _agreement(y, ref) >= 0.999
+    assert 0.02 < (ref[:, 1] > ref[:, 0]).float().mean().item() < 0.98
+    g = np.load(os.path.join(golden_dir, "vig_v20.npz"))
+    x1, x2 = synth.image_pairs(int(g["batch"]), int(g["h"]), int(g["w"]), seed=int(g["data_seed"]))
+    y = net(x1.cuda(), x2.cuda())[-1].cpu()
+    gref = torch.from_numpy(g["out0"])
+    assert (y - gref).abs().max().item() < BF16_TOL and _agreement(y, gref) >= 0.999
+    from types import SimpleNamespace
+    from stcd_b200 import networks
+    n2 = networks.define_G(SimpleNamespace(net_G="GNN", n_class=2, embed_dim=256, img_size=256), gpu_ids=[0])
+    assert isinstance(n2, changevig.VIG_V20_2)
+
+
 def test_properties_and_define_G():
     from types import SimpleNamespace
     from stcd_b200 import networks

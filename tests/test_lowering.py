@@ -269,6 +269,24 @@ def test_changegnn_v2_program_matches_oracle(mode):
         net.lower(512, 512)
 
 
+def test_vig_v20_program_matches_oracle():
+    """VIG_V20_2 (registry key "GNN"): the ViG encoder under the prefix VIG_x2, conv_diff_V20 (Cross_ConCat), csam_V20 gates, AFF as a
+    VFFM with an empty max branch, k2 s2 transposed convs -- through the emulator."""
+    from stcd_b200 import changevig
+    net = synth.prepare_(changevig.VIG_V20_2().eval(), "VIG_V20_2")
+    x1, x2 = synth.image_pairs(1, 256, 256)
+    with torch.no_grad():
+        y = nets.vig_v20_forward(net.state_dict(), x1, x2)
+    prog = net.lower(256, 256)
+    ye = emulate.run_program(prog, x1, x2, chunk=1)
+    assert len(ye) == len(y) == 1 and (ye[0] - y[0]).abs().max().item() < BF16_TOL
+    margin = (y[0][:, 1] - y[0][:, 0]).abs()
+    agree = (ye[0][:, 1] > ye[0][:, 0]) == (y[0][:, 1] > y[0][:, 0])
+    assert agree[margin > BF16_TOL].float().mean().item() >= 0.999
+    assert 0.02 < (y[0][:, 1] > y[0][:, 0]).float().mean().item() < 0.98, "degenerate change map"
+    assert sum(isinstance(o, L.CsamGateSpec) for o in prog.ops) == 4 and sum(isinstance(o, L.VffmSpec) for o in prog.ops) == 3
+
+
 def test_changeformer_program_matches_oracle():
     """Config C5's net: Linear layers as 1x1 convs, strided patch-embedding / spatial-reduction convs, LayerNorm,
     64-key attention and depth-wise conv ops -- checked through the emulator."""

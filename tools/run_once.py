@@ -15,7 +15,7 @@ if name == "SegCD":
     net = CLASSES[name]("resnet34")
 elif name == "BASE_Transformer":        # registry key base_transformer_pos_s4_dd8
     net = CLASSES[name](3, 2, with_pos="learned", resnet_stages_num=4, token_len=4, enc_depth=1, dec_depth=8)
-elif name in ("ChangeGNNV2", "ChangeGNNV2_Compare"):
+elif name in ("ChangeGNNV2", "ChangeGNNV2_Compare", "VIG_V20_2"):
     net = CLASSES[name]()
 elif name == "DSIFN":                   # registry key IFNet
     net = CLASSES[name]()
