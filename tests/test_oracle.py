@@ -82,7 +82,7 @@ def test_oracle_matches_live_reference(case):
     for k in sd:
         assert sd[k].shape == sd_ref[k].shape
         assert torch.equal(sd[k], sd_ref[k]), f"seeded weights differ at {k}"
-    x1, x2 = synth.image_pairs(1, 256, 256, seed=5) if case.startswith("change") else synth.image_pairs(1, 64, 32, seed=5)
+    x1, x2 = synth.image_pairs(1, 256, 256, seed=5) if case.startswith(("change", "vig")) else synth.image_pairs(1, 64, 32, seed=5)
     with torch.no_grad():
         y_ref = ref(x1, x2)
         y = _oracle_forward(case, sd, x1, x2)
