@@ -333,7 +333,7 @@ def mit_encoder_features(sd: SD, x: torch.Tensor, pre: str = "Tenc_x2", depths=(
     outs = []
     for s in range(4):
         pe = f"{pre}.patch_embed{s + 1}"
-        x = F.conv2d(x, sd[f"{pe}.proj.weight"], sd[f"{pe}.proj.bias"], stride=4 if s == 0 else 2, padding=3)
+        x = F.conv2d(x, sd[f"{pe}.proj.weight"], sd[f"{pe}.proj.bias"], stride=4 if s == 0 else 2, padding=sd[f"{pe}.proj.weight"].shape[2] // 2)
         b, c, h, w = x.shape
         t = _ln(sd, f"{pe}.norm", x.flatten(2).transpose(1, 2), 1e-5)
         for i in range(depths[s]):
@@ -691,3 +691,51 @@ def vig_v20_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor) -> List[torch.Te
     x = F.conv_transpose2d(x, sd[f"{d}.convd1x.conv2d.weight"], sd[f"{d}.convd1x.conv2d.bias"], stride=2, padding=1)
     x = resblock(f"{d}.dense_1x.0", x)
     return [F.conv2d(x, sd[f"{d}.change_probability.conv2d.weight"], sd[f"{d}.change_probability.conv2d.bias"], padding=1)]
+
+
+# ------------------------------------------------------------------------------------------
+# ChangeFormerV1 / V2 (models/ChangeFormer.py:644-674, 918-948): Tenc (EncoderTransformer, patch 7/s4 then 3/s2, depths 3-4-6-3) on both
+# dates, |fx1 - fx2| per scale, then convprojection_base (V1) or TDec (V2)
+def _cf_resblock(sd: SD, q: str, x: torch.Tensor) -> torch.Tensor:
+    """ResidualBlock.forward, ChangeFormerBaseNetworks.py:113-120."""
+    o = F.relu(F.conv2d(x, sd[f"{q}.conv1.conv2d.weight"], sd[f"{q}.conv1.conv2d.bias"], padding=1))
+    return F.conv2d(o, sd[f"{q}.conv2.conv2d.weight"], sd[f"{q}.conv2.conv2d.bias"], padding=1) * 0.1 + x
+
+
+def _cf_up(sd: SD, q: str, x: torch.Tensor) -> torch.Tensor:
+    """UpsampleConvLayer.forward (ConvTranspose2d k4 s2 p1), ChangeFormerBaseNetworks.py:96-105."""
+    return F.conv_transpose2d(x, sd[f"{q}.conv2d.weight"], sd[f"{q}.conv2d.bias"], stride=2, padding=1)
+
+
+def changeformer_v1_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """ChangeFormerV1.forward, ChangeFormer.py:657-674 with convprojection_base.forward (:605-641; the F.pad branches only
+    fire for sizes that are not multiples of 32)."""
+    f1 = mit_encoder_features(sd, x1, "Tenc", depths=(3, 4, 6, 3))
+    f2 = mit_encoder_features(sd, x2, "Tenc", depths=(3, 4, 6, 3))
+    di = [torch.abs(a - b) for a, b in zip(f1, f2)]
+    c = "convproj"
+    r = _cf_resblock(sd, f"{c}.dense_4.0", _cf_up(sd, f"{c}.convd16x", di[3])) + di[2]
+    r = _cf_resblock(sd, f"{c}.dense_3.0", _cf_up(sd, f"{c}.convd8x", r)) + di[1]
+    r = _cf_resblock(sd, f"{c}.dense_2.0", _cf_up(sd, f"{c}.convd4x", r)) + di[0]
+    r = _cf_up(sd, f"{c}.convd1x", _cf_resblock(sd, f"{c}.dense_1.0", _cf_up(sd, f"{c}.convd2x", r)))
+    return F.conv2d(r, sd["change_probability.conv2d.weight"], sd["change_probability.conv2d.bias"], padding=1)
+
+
+def changeformer_v2_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """ChangeFormerV2.forward, ChangeFormer.py:931-948 with TDec.forward (:762-790)."""
+    f1 = mit_encoder_features(sd, x1, "Tenc", depths=(3, 4, 6, 3))
+    f2 = mit_encoder_features(sd, x2, "Tenc", depths=(3, 4, 6, 3))
+    di = [torch.abs(a - b) for a, b in zip(f1, f2)]
+    d = "TDec"
+    size = di[0].shape[2:]
+    cs = []
+    for k in (4, 3, 2, 1):
+        t = di[k - 1]
+        n, _, hh, ww = t.shape
+        y = F.linear(t.flatten(2).transpose(1, 2), sd[f"{d}.linear_c{k}.proj.weight"], sd[f"{d}.linear_c{k}.proj.bias"])
+        y = y.permute(0, 2, 1).reshape(n, -1, hh, ww)
+        cs.append(y if k == 1 else F.interpolate(y, size=size, mode="bilinear", align_corners=False))
+    x = F.conv2d(torch.cat(cs, dim=1), sd[f"{d}.linear_fuse.weight"], sd[f"{d}.linear_fuse.bias"])
+    x = _cf_resblock(sd, f"{d}.dense_2x.0", _cf_up(sd, f"{d}.convd2x", x))
+    x = _cf_resblock(sd, f"{d}.dense_1x.0", _cf_up(sd, f"{d}.convd1x", x))
+    return F.conv2d(x, sd[f"{d}.change_probability.conv2d.weight"], sd[f"{d}.change_probability.conv2d.bias"], padding=1)

@@ -80,15 +80,20 @@ class _Block(nn.Module):
 class _EncoderTransformerV3(nn.Module):
     """models/ChangeFormer.py:1340-1432 (parameters only)."""
 
-    def __init__(self, in_chans: int):
+    def __init__(self, in_chans: int, depths=_DEPTHS, patch_k: int = 7, intra_patch: bool = False):
         super().__init__()
         self.patch_embed1 = _OverlapPatchEmbed(7, 4, in_chans, _DIMS[0])
-        self.patch_embed2 = _OverlapPatchEmbed(7, 2, _DIMS[0], _DIMS[1])
-        self.patch_embed3 = _OverlapPatchEmbed(7, 2, _DIMS[1], _DIMS[2])
-        self.patch_embed4 = _OverlapPatchEmbed(7, 2, _DIMS[2], _DIMS[3])
+        self.patch_embed2 = _OverlapPatchEmbed(patch_k, 2, _DIMS[0], _DIMS[1])
+        self.patch_embed3 = _OverlapPatchEmbed(patch_k, 2, _DIMS[1], _DIMS[2])
+        self.patch_embed4 = _OverlapPatchEmbed(patch_k, 2, _DIMS[2], _DIMS[3])
         for s in range(4):
-            setattr(self, f"block{s + 1}", nn.ModuleList([_Block(_DIMS[s], _SRS[s]) for _ in range(_DEPTHS[s])]))
+            setattr(self, f"block{s + 1}", nn.ModuleList([_Block(_DIMS[s], _SRS[s]) for _ in range(depths[s])]))
             setattr(self, f"norm{s + 1}", nn.LayerNorm(_DIMS[s], eps=1e-6))
+            if intra_patch and s < 3:
+                # EncoderTransformer's "intra-patch encoder" blocks (ChangeFormer.py:51-58, 66-73, 81-88): constructed, never
+                # called by forward_features (:141-185) -- parameters only
+                setattr(self, f"patch_block{s + 1}", nn.ModuleList([_Block(_DIMS[s + 1], _SRS[s])]))
+                setattr(self, f"pnorm{s + 1}", nn.LayerNorm(_DIMS[s + 1], eps=1e-6))
 
 
 class ChangeFormerV6(PlannedModule):
@@ -137,9 +142,16 @@ def lower_changeformer(sd: Dict[str, torch.Tensor], in_ch: int, e: int, n_class:
         raise ValueError("the attention kernel keeps at most 64 reduced tokens per image (256x256 inputs, the reference's img_size)")
     sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
     p = L.Program(model="ChangeFormerV6", in_channels=in_ch, h=h, w=w)
+    feats = lower_mit_encoder(p, sd, "Tenc_x2", in_ch, _DEPTHS, h, w)
+    lower_diff_decoder(p, sd, feats, e, n_class, "TDec_x2", "TDec_x2.linear_c{k}")
+    return p
+
+
+def lower_mit_encoder(p: L.Program, sd: Dict[str, torch.Tensor], enc: str, in_ch: int, depths, h: int, w: int):
+    """EncoderTransformer (ChangeFormer.py:23-193; patch embeds 7/s4 then 3/s2) == EncoderTransformer_v3 (:1342-1472; 7/s4 then 7/s2):
+    the patch size is read off the weights.  Returns [(tensor, channels, h, w)] per stage, both streams."""
     ones = lambda c: np.ones(c, np.float32)  # noqa: E731
     npf = lambda t: t.numpy().astype(np.float32)  # noqa: E731
-    enc = "Tenc_x2"
 
     def linear(name: str, pre: str, src: str, cin: int, cout: int, hh: int, ww: int, **kw) -> None:
         wt = sd[f"{pre}.weight"][:, :, None, None]
@@ -167,11 +179,12 @@ def lower_changeformer(sd: Dict[str, torch.Tensor], in_ch: int, e: int, n_class:
             cprev = _DIMS[s - 1]
             hh, ww = hh // 2, ww // 2
             t = p.tensor(f"{pe}.conv", 2, hh, ww, c)
-            L.add_conv(p, f"{pe}.proj", L.s2d_segments(x_s2d, cprev), [(0, 0, L.s2d_conv_taps(wt, pad=3))], c, hh, ww, 1, ones(c),
-                       npf(sd[f"{pe}.proj.bias"]), pair=True, out0=t, macs_per_pair=2 * hh * ww * 49 * cprev * c)
+            kk = wt.shape[2]
+            L.add_conv(p, f"{pe}.proj", L.s2d_segments(x_s2d, cprev), [(0, 0, L.s2d_conv_taps(wt, pad=kk // 2))], c, hh, ww, 1, ones(c),
+                       npf(sd[f"{pe}.proj.bias"]), pair=True, out0=t, macs_per_pair=2 * hh * ww * kk * kk * cprev * c)
         x = p.tensor(f"{pe}.out", 2, hh, ww, c)
         layernorm(f"{pe}.norm", f"{pe}.norm", t, x, c, 1e-5)
-        for i in range(_DEPTHS[s]):
+        for i in range(depths[s]):
             blk = f"{enc}.block{s + 1}.{i}"
             a = f"{blk}.attn"
             n1 = p.tensor(f"{blk}.n1", 2, hh, ww, c)
@@ -209,5 +222,4 @@ def lower_changeformer(sd: Dict[str, torch.Tensor], in_ch: int, e: int, n_class:
         x_s2d = p.tensor(f"{enc}.f{s + 1}_s2d", 2, hh // 2, ww // 2, 4 * c) if s < 3 else None
         layernorm(f"{enc}.norm{s + 1}", f"{enc}.norm{s + 1}", x, f, c, 1e-6, dst_s2d=x_s2d)
         feats.append((f, c, hh, ww))
-    lower_diff_decoder(p, sd, feats, e, n_class, "TDec_x2", "TDec_x2.linear_c{k}")
-    return p
+    return feats
