@@ -27,7 +27,8 @@ import torch
 import torch.nn as nn
 
 from . import lowering as L
-from .changevig import _DecoderV1, lower_diff_decoder
+from .changevig import (_ConvLayer, _DecoderV1, _MLP, _ResidualBlock, _UpsampleConvLayer, lower_decoder_tail,
+                        lower_diff_decoder)
 from .module import PlannedModule
 
 _DIMS = (64, 128, 320, 512)
@@ -223,3 +224,174 @@ def lower_mit_encoder(p: L.Program, sd: Dict[str, torch.Tensor], enc: str, in_ch
         layernorm(f"{enc}.norm{s + 1}", f"{enc}.norm{s + 1}", x, f, c, 1e-6, dst_s2d=x_s2d)
         feats.append((f, c, hh, ww))
     return feats
+
+
+# ==========================================================================================
+# ChangeFormerV1 / V2 (models/ChangeFormer.py:644-674, 918-948): Tenc = EncoderTransformer (patch 7/s4 then 3/s2, depths 3-4-6-3) on
+# both dates, |fx1 - fx2| per scale, convprojection_base (V1) or TDec (V2).  Both return ONE tensor.
+_DEPTHS_TENC = (3, 4, 6, 3)
+
+
+def _init_mit(enc: nn.Module) -> None:
+    """EncoderTransformer._init_weights, ChangeFormer.py:99-112."""
+    for m in enc.modules():
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.Conv2d):
+            fan_out = m.kernel_size[0] * m.kernel_size[1] * m.out_channels // m.groups
+            m.weight.data.normal_(0, (2.0 / fan_out) ** 0.5)
+            m.bias.data.zero_()
+
+
+class _ConvProjectionBase(nn.Module):
+    """models/ChangeFormer.py:591-603."""
+
+    def __init__(self):
+        super().__init__()
+        self.convd16x = _UpsampleConvLayer(512, 320, 4, 2)
+        self.dense_4 = nn.Sequential(_ResidualBlock(320))
+        self.convd8x = _UpsampleConvLayer(320, 128, 4, 2)
+        self.dense_3 = nn.Sequential(_ResidualBlock(128))
+        self.convd4x = _UpsampleConvLayer(128, 64, 4, 2)
+        self.dense_2 = nn.Sequential(_ResidualBlock(64))
+        self.convd2x = _UpsampleConvLayer(64, 16, 4, 2)
+        self.dense_1 = nn.Sequential(_ResidualBlock(16))
+        self.convd1x = _UpsampleConvLayer(16, 8, 4, 2)
+
+
+class _TDec(nn.Module):
+    """models/ChangeFormer.py:691-735."""
+
+    def __init__(self, in_channels, e: int, output_nc: int):
+        super().__init__()
+        c1, c2, c3, c4 = in_channels
+        self.linear_c4 = _MLP(c4, e)
+        self.linear_c3 = _MLP(c3, e)
+        self.linear_c2 = _MLP(c2, e)
+        self.linear_c1 = _MLP(c1, e)
+        self.linear_fuse = nn.Conv2d(e * 4, e, 1)
+        self.convd2x = _UpsampleConvLayer(e, e, 4, 2)
+        self.dense_2x = nn.Sequential(_ResidualBlock(e))
+        self.convd1x = _UpsampleConvLayer(e, e, 4, 2)
+        self.dense_1x = nn.Sequential(_ResidualBlock(e))
+        self.change_probability = _ConvLayer(e, output_nc, 3, 1, 1)
+        self.active = nn.Softmax(dim=1)
+
+
+class _ChangeFormerTenc(PlannedModule):
+    default_chunk_pairs = 32
+    _variant = ""
+
+    def __init__(self, input_nc: int = 3, output_nc: int = 2, decoder_softmax: bool = False):
+        super().__init__()
+        if decoder_softmax:
+            raise NotImplementedError("stcd_b200 serves decoder_softmax=False (models/networks.py:184-187)")
+        if input_nc != 3 or output_nc > 8:
+            raise NotImplementedError("Tenc is built for 3 input channels upstream (ChangeFormer.py:525-531); output_nc <= 8")
+        self.output_nc = output_nc
+        self.Tenc = _EncoderTransformerV3(3, depths=_DEPTHS_TENC, patch_k=3, intra_patch=True)
+        _init_mit(self.Tenc)
+
+    def lower(self, h: int, w: int) -> L.Program:
+        return lower_changeformer_tenc(self.state_dict(), self._variant, self.output_nc, h, w)
+
+    @torch.no_grad()
+    def forward(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+        return self.plan_for(x1).forward(x1, x2)[0]
+
+
+class ChangeFormerV1(_ChangeFormerTenc):
+    """models/ChangeFormer.py:644-674."""
+    _variant = "v1"
+
+    def __init__(self, input_nc: int = 3, output_nc: int = 2, decoder_softmax: bool = False):
+        super().__init__(input_nc, output_nc, decoder_softmax)
+        self.convproj = _ConvProjectionBase()
+        self.change_probability = _ConvLayer(8, output_nc, 3, 1, 1)
+        self.active = nn.Softmax(dim=1)
+
+
+class ChangeFormerV2(_ChangeFormerTenc):
+    """models/ChangeFormer.py:918-948."""
+    _variant = "v2"
+
+    def __init__(self, input_nc: int = 3, output_nc: int = 2, decoder_softmax: bool = False):
+        super().__init__(input_nc, output_nc, decoder_softmax)
+        self.TDec = _TDec(_DIMS, 32, output_nc)
+        self.output_activation = nn.Softmax(dim=1)
+
+
+def lower_changeformer_tenc(sd: Dict[str, torch.Tensor], variant: str, n_class: int, h: int, w: int) -> L.Program:
+    """state_dict of the reference ChangeFormerV1 / V2 -> fused-op Program (eval mode)."""
+    if h % 256 or w % 256 or (h // 32) * (w // 32) > 64:
+        raise ValueError(f"ChangeFormer{variant.upper()} lowering serves 256x256 inputs (the reference's img_size; 64 reduced tokens per image), got {h}x{w}")
+    sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
+    p = L.Program(model=f"ChangeFormer{variant.upper()}", in_channels=3, h=h, w=w)
+    ones = lambda c: np.ones(c, np.float32)  # noqa: E731
+    npf = lambda t: np.ascontiguousarray(t.numpy().astype(np.float32))  # noqa: E731
+    feats = lower_mit_encoder(p, sd, "Tenc", 3, _DEPTHS_TENC, h, w)
+    di = []                                                     # DI[i] = |fx1[i] - fx2[i]| (:664-666, 938-940)
+    for i, (ft, c, hh, ww) in enumerate(feats):
+        t = p.tensor(f"DI{i}", 1, hh, ww, c)
+        p.ops.append(L.AbsDiffSpec(f"DI{i}", ft, t, c))
+        di.append((t, c, hh, ww))
+
+    def up(q: str, x: str, cin: int, cout: int, hh: int, ww: int) -> str:
+        cp = (cout + 7) // 8 * 8
+        o = p.tensor(f"{q}.o", 1, 2 * hh, 2 * ww, cp)
+        L.add_conv(p, q, [L.Segment(x, cin)], L.convT_phase_taps(sd[f"{q}.conv2d.weight"], stride=2, pad=1), cout, hh, ww, 1, ones(cout),
+                   npf(sd[f"{q}.conv2d.bias"]), osy=2, osx=2, out0=o, macs_per_pair=hh * ww * 16 * cin * cout)
+        return o
+
+    def resblock(q: str, u: str, c: int, hh: int, ww: int, extra: str = None) -> str:
+        """ResidualBlock (conv, ReLU, conv * 0.1 + u) [+ extra]: the second residual is pre-added to u by one bandwidth op."""
+        cp = (c + 7) // 8 * 8
+        r1 = p.tensor(f"{q}.t", 1, hh, ww, cp)
+        L.add_conv(p, f"{q}.conv1", [L.Segment(u, c)], L.conv_taps(sd[f"{q}.conv1.conv2d.weight"], pad=1), c, hh, ww, 1, ones(c),
+                   npf(sd[f"{q}.conv1.conv2d.bias"]), relu=True, out0=r1, macs_per_pair=hh * ww * 9 * c * c)
+        res = u
+        if extra is not None:
+            res = p.tensor(f"{q}.res", 1, hh, ww, cp)
+            p.ops.append(L.SumSpec(f"{q}.res", [u, extra], res))
+        o = p.tensor(f"{q}.out", 1, hh, ww, cp)
+        L.add_conv(p, f"{q}.conv2", [L.Segment(r1, c)], L.conv_taps(sd[f"{q}.conv2.conv2d.weight"], pad=1), c, hh, ww, 1, 0.1 * ones(c),
+                   0.1 * npf(sd[f"{q}.conv2.conv2d.bias"]), res=res, out0=o, macs_per_pair=hh * ww * 9 * c * c)
+        return o
+
+    if variant == "v1":                                         # convprojection_base.forward, :605-641
+        c = "convproj"
+        t4, _, hh, ww = di[3]
+        x = up(f"{c}.convd16x", t4, 512, 320, hh, ww)
+        x = resblock(f"{c}.dense_4.0", x, 320, 2 * hh, 2 * ww, extra=di[2][0])
+        x = up(f"{c}.convd8x", x, 320, 128, 2 * hh, 2 * ww)
+        x = resblock(f"{c}.dense_3.0", x, 128, 4 * hh, 4 * ww, extra=di[1][0])
+        x = up(f"{c}.convd4x", x, 128, 64, 4 * hh, 4 * ww)
+        x = resblock(f"{c}.dense_2.0", x, 64, 8 * hh, 8 * ww, extra=di[0][0])
+        x = up(f"{c}.convd2x", x, 64, 16, 8 * hh, 8 * ww)
+        x = resblock(f"{c}.dense_1.0", x, 16, 16 * hh, 16 * ww)
+        x = up(f"{c}.convd1x", x, 16, 8, 16 * hh, 16 * ww)
+        hh, ww = 32 * hh, 32 * ww
+        L.add_conv(p, "change_probability", [L.Segment(x, 8)], L.conv_taps(sd["change_probability.conv2d.weight"], pad=1), n_class, hh, ww, 1,
+                   ones(n_class), npf(sd["change_probability.conv2d.bias"]), out_ext=0, macs_per_pair=hh * ww * 9 * 8 * n_class)
+        p.ext.append(L.ExtOutput("cp", n_class, hh, ww))
+        return p
+    # ---- V2: TDec.forward, :762-790
+    d, e = "TDec", 32
+    _, _, fh, fw = di[0]
+    ups = []
+    for k in (4, 3, 2, 1):
+        t, c, hh, ww = di[k - 1]
+        y = p.tensor(f"{d}.linear_c{k}.o", 1, hh, ww, e)
+        L.add_conv(p, f"{d}.linear_c{k}", [L.Segment(t, c)], L.conv_taps(sd[f"{d}.linear_c{k}.proj.weight"][:, :, None, None], pad=0), e, hh, ww, 1,
+                   ones(e), npf(sd[f"{d}.linear_c{k}.proj.bias"]), out0=y, macs_per_pair=hh * ww * c * e)
+        if k > 1:
+            u = p.tensor(f"{d}.linear_c{k}.up", 1, fh, fw, e)
+            p.ops.append(L.BilinearUpSpec(f"{d}.linear_c{k}.up", y, u, e, fh // hh))
+            y = u
+        ups.append(y)
+    fused = p.tensor(f"{d}.fused", 1, fh, fw, e)
+    L.add_conv(p, f"{d}.linear_fuse", [L.Segment(t, e) for t in ups], L.conv_taps(sd[f"{d}.linear_fuse.weight"], pad=0), e, fh, fw, 1, ones(e),
+               npf(sd[f"{d}.linear_fuse.bias"]), out0=fused, macs_per_pair=fh * fw * 4 * e * e)
+    lower_decoder_tail(p, sd, fused, fh, fw, e, n_class, d, out_ext=0)
+    return p

@@ -90,3 +90,38 @@ def test_properties_and_conventions():
     assert isinstance(g, changeformer.ChangeFormerV6)
     with pytest.raises(ValueError):
         net(torch.zeros(1, 3, 128, 128).cuda(), torch.zeros(1, 3, 128, 128).cuda())
+
+
+@pytest.mark.parametrize("version", ["1", "2"])
+def test_changeformer_v1_v2_match_oracle_and_golden(version, golden_dir):
+    """ChangeFormerV1 / V2 (Tenc encoder, |fx1 - fx2|, convprojection_base / TDec): ONE tensor out, like upstream."""
+    import os
+
+    import numpy as np
+    from types import SimpleNamespace
+
+    from stcd_b200 import changeformer as cf, networks
+    cls = f"ChangeFormerV{version}"
+    net = synth.prepare_(getattr(cf, cls)().eval(), cls)
+    x1, x2 = synth.image_pairs(3, 256, 256)
+    with torch.no_grad():
+        ref = getattr(nets, f"changeformer_v{version}_forward")(net.state_dict(), x1, x2)
+    net = net.cuda()
+    net.chunk_pairs = 2                      # 3 pairs -> one full chunk + a ragged one
+    y = net(x1.cuda(), x2.cuda())
+    assert isinstance(y, torch.Tensor) and y.shape == ref.shape and y.dtype == torch.float32
+    y = y.cpu()
+
+    def decided(a, b):
+        margin = (b[:, 1] - b[:, 0]).abs()
+        return ((a[:, 1] > a[:, 0]) == (b[:, 1] > b[:, 0]))[margin > 2e-2].float().mean().item()
+
+    assert (y - ref).abs().max().item() < 2e-2 and decided(y, ref) >= 0.999
+    assert 0.02 < (ref[:, 1] > ref[:, 0]).float().mean().item() < 0.98
+    g = np.load(os.path.join(golden_dir, f"changeformer_v{version}.npz"))
+    x1, x2 = synth.image_pairs(int(g["batch"]), int(g["h"]), int(g["w"]), seed=int(g["data_seed"]))
+    yg = net(x1.cuda(), x2.cuda()).cpu()
+    gref = torch.from_numpy(g["out0"])
+    assert (yg - gref).abs().max().item() < 2e-2 and decided(yg, gref) >= 0.999
+    n2 = networks.define_G(SimpleNamespace(net_G=cls, n_class=2, embed_dim=256, img_size=256), gpu_ids=[0])
+    assert isinstance(n2, getattr(cf, cls)) and next(n2.parameters()).is_cuda

@@ -310,6 +310,29 @@ def test_changeformer_program_matches_oracle():
         net.lower(128, 128)
 
 
+@pytest.mark.parametrize("version", ["1", "2"])
+def test_changeformer_v1_v2_program_matches_oracle(version):
+    """ChangeFormerV1 / V2: Tenc (EncoderTransformer: 3x3 stride-2 patch embeds, depths 3-4-6-3, the never-called intra-patch blocks
+    held as parameters), |fx1 - fx2| per scale, convprojection_base (V1) or TDec (V2) -- through the emulator."""
+    from stcd_b200 import changeformer
+    cls = f"ChangeFormerV{version}"
+    net = synth.prepare_(getattr(changeformer, cls)().eval(), cls)
+    x1, x2 = synth.image_pairs(1, 256, 256)
+    with torch.no_grad():
+        y = getattr(nets, f"changeformer_v{version}_forward")(net.state_dict(), x1, x2)
+    prog = net.lower(256, 256)
+    ye = emulate.run_program(prog, x1, x2, chunk=1)[0]
+    assert ye.shape == y.shape == (1, 2, 256, 256) and (ye - y).abs().max().item() < BF16_TOL
+    margin = (y[:, 1] - y[:, 0]).abs()
+    agree = (ye[:, 1] > ye[:, 0]) == (y[:, 1] > y[:, 0])
+    assert agree[margin > BF16_TOL].float().mean().item() >= 0.999
+    assert 0.02 < (y[:, 1] > y[:, 0]).float().mean().item() < 0.98, "degenerate change map"
+    assert "Tenc.patch_block2.0.attn.q.weight" in net.state_dict() and not any("patch_block" in o.name for o in prog.ops)
+    assert sum(isinstance(o, L.AttentionSpec) for o in prog.ops) == 16 and sum(isinstance(o, L.AbsDiffSpec) for o in prog.ops) == 4
+    with pytest.raises(ValueError):
+        net.lower(512, 512)
+
+
 def test_s2d_and_up2_tap_algebra():
     """The tap rewrites behind the SegCD lowering equal the reference ops they replace (fp32, no rounding)."""
     import torch.nn.functional as F
