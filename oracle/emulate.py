@@ -103,7 +103,12 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
         elif op.out0 is not None:
             T[op.out0][sl, :, :, op.out0_coff: op.out0_coff + op.cout] = _bf16(v[..., : op.cout])
         if op.out_ext >= 0:
-            ext[op.out_ext][:n_valid] = v[:n_valid, :, :, : op.cout].permute(0, 3, 1, 2)
+            o = v[:n_valid, :, :, : op.cout].permute(0, 3, 1, 2)
+            if len(op.phases) == op.osy * op.osx:
+                ext[op.out_ext][:n_valid] = o
+            else:                      # an op that owns only some output phases (PixelShuffle(4) as 4 ops x 4 phases) writes only those
+                for ph in op.phases:
+                    ext[op.out_ext][:n_valid, :, ph.oy::op.osy, ph.ox::op.osx] = o[:, :, ph.oy::op.osy, ph.ox::op.osx]
         if op.out_pool is not None:
             q = torch.maximum(torch.maximum(v[:, 0::2, 0::2], v[:, 0::2, 1::2]),
                               torch.maximum(v[:, 1::2, 0::2], v[:, 1::2, 1::2]))

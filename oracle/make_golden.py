@@ -48,6 +48,7 @@ CASES = {
     "changegnn_v2": ("models.ChangeVIG", "ChangeGNNV2", (3, 2, False, 256), 1, 256, 256),
     "changeformer_v1": ("models.ChangeFormer", "ChangeFormerV1", (), 1, 256, 256),
     "changeformer_v2": ("models.ChangeFormer", "ChangeFormerV2", (), 1, 256, 256),
+    "changeformer_v3": ("models.ChangeFormer", "ChangeFormerV3", (), 1, 256, 256),
     "vig_v20": ("models.ChangeVIG", "VIG_V20_2", (3, 2, False, 256), 1, 256, 256),          # registry key "GNN"
     "changegnn_v2_sub": ("models.ChangeVIG", "ChangeGNNV2_Compare", (3, 2, False, 256, "MLP", 256, "sub"), 1, 256, 256),
 }

@@ -739,3 +739,23 @@ def changeformer_v2_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor) -> torch
     x = _cf_resblock(sd, f"{d}.dense_2x.0", _cf_up(sd, f"{d}.convd2x", x))
     x = _cf_resblock(sd, f"{d}.dense_1x.0", _cf_up(sd, f"{d}.convd1x", x))
     return F.conv2d(x, sd[f"{d}.change_probability.conv2d.weight"], sd[f"{d}.change_probability.conv2d.bias"], padding=1)
+
+
+def changeformer_v3_forward(sd: SD, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """ChangeFormerV3.forward, ChangeFormer.py:966-973 with TDecV2.forward (:867-915): per-scale Linear heads on both dates, bilinear
+    resize to the 1/4 scale, |.-.| per scale, 1x1 fuse, 3x3 conv to 16 * n_class channels + ReLU, PixelShuffle(4)."""
+    f1 = mit_encoder_features(sd, x1, "Tenc", depths=(3, 4, 6, 3))
+    f2 = mit_encoder_features(sd, x2, "Tenc", depths=(3, 4, 6, 3))
+    d = "TDec"
+    size = f1[0].shape[2:]
+
+    def head(k, t):
+        n, _, hh, ww = t.shape
+        y = F.linear(t.flatten(2).transpose(1, 2), sd[f"{d}.linear_c{k}.proj.weight"], sd[f"{d}.linear_c{k}.proj.bias"])
+        y = y.permute(0, 2, 1).reshape(n, -1, hh, ww)
+        return y if k == 1 else F.interpolate(y, size=size, mode="bilinear", align_corners=False)
+
+    diffs = [torch.abs(head(k, f1[k - 1]) - head(k, f2[k - 1])) for k in (4, 3, 2, 1)]
+    c = F.conv2d(torch.cat(diffs, dim=1), sd[f"{d}.linear_fuse.weight"], sd[f"{d}.linear_fuse.bias"])
+    x = F.relu(F.conv2d(c, sd[f"{d}.pix_shuffle_conv.weight"], sd[f"{d}.pix_shuffle_conv.bias"], padding=1))
+    return F.pixel_shuffle(x, 4)

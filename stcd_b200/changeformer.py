@@ -322,6 +322,31 @@ class ChangeFormerV2(_ChangeFormerTenc):
         self.output_activation = nn.Softmax(dim=1)
 
 
+class _TDecV2(nn.Module):
+    """models/ChangeFormer.py:793-830."""
+
+    def __init__(self, in_channels, e: int, output_nc: int):
+        super().__init__()
+        c1, c2, c3, c4 = in_channels
+        self.linear_c4 = _MLP(c4, e)
+        self.linear_c3 = _MLP(c3, e)
+        self.linear_c2 = _MLP(c2, e)
+        self.linear_c1 = _MLP(c1, e)
+        self.linear_fuse = nn.Conv2d(e * 4, e, 1)
+        self.pix_shuffle_conv = nn.Conv2d(e, 16 * output_nc, 3, stride=1, padding=1)
+        self.pix_shuffle = nn.PixelShuffle(4)
+        self.active = nn.Softmax(dim=1)
+
+
+class ChangeFormerV3(_ChangeFormerTenc):
+    """models/ChangeFormer.py:951-973."""
+    _variant = "v3"
+
+    def __init__(self, input_nc: int = 3, output_nc: int = 2, decoder_softmax: bool = False):
+        super().__init__(input_nc, output_nc, decoder_softmax)
+        self.TDec = _TDecV2(_DIMS, 64, output_nc)
+
+
 def lower_changeformer_tenc(sd: Dict[str, torch.Tensor], variant: str, n_class: int, h: int, w: int) -> L.Program:
     """state_dict of the reference ChangeFormerV1 / V2 -> fused-op Program (eval mode)."""
     if h % 256 or w % 256 or (h // 32) * (w // 32) > 64:
@@ -331,6 +356,37 @@ def lower_changeformer_tenc(sd: Dict[str, torch.Tensor], variant: str, n_class: 
     ones = lambda c: np.ones(c, np.float32)  # noqa: E731
     npf = lambda t: np.ascontiguousarray(t.numpy().astype(np.float32))  # noqa: E731
     feats = lower_mit_encoder(p, sd, "Tenc", 3, _DEPTHS_TENC, h, w)
+    if variant == "v3":                                         # TDecV2.forward, :867-915
+        d, e = "TDec", 64
+        _, _, fh, fw = feats[0]
+        diffs = []
+        for k in (4, 3, 2, 1):
+            ft, c, hh, ww = feats[k - 1]
+            y = p.tensor(f"{d}.linear_c{k}.o", 2, hh, ww, e)
+            L.add_conv(p, f"{d}.linear_c{k}", [L.Segment(ft, c)], L.conv_taps(sd[f"{d}.linear_c{k}.proj.weight"][:, :, None, None], pad=0), e, hh,
+                       ww, 1, ones(e), npf(sd[f"{d}.linear_c{k}.proj.bias"]), pair=True, out0=y, macs_per_pair=2 * hh * ww * c * e)
+            if k > 1:
+                u = p.tensor(f"{d}.linear_c{k}.up", 2, fh, fw, e)
+                p.ops.append(L.BilinearUpSpec(f"{d}.linear_c{k}.up", y, u, e, fh // hh))
+                y = u
+            dk = p.tensor(f"{d}.diff{k}", 1, fh, fw, e)
+            p.ops.append(L.AbsDiffSpec(f"{d}.diff{k}", y, dk, e))
+            diffs.append(dk)
+        fused = p.tensor(f"{d}.fused", 1, fh, fw, e)
+        L.add_conv(p, f"{d}.linear_fuse", [L.Segment(t, e) for t in diffs], L.conv_taps(sd[f"{d}.linear_fuse.weight"], pad=0), e, fh, fw, 1,
+                   ones(e), npf(sd[f"{d}.linear_fuse.bias"]), out0=fused, macs_per_pair=fh * fw * 4 * e * e)
+        # relu(conv3x3 -> 16 * n_class) + PixelShuffle(4): output pixel (4y + i, 4x + j) of class c is conv channel c*16 + i*4 + j at
+        # (y, x) -- an up-sampling conv with 16 output phases.  The phases have different biases while a launch shares one
+        # per-channel affine, so every phase is its own (small) launch writing its pixels of the fp32 output.
+        wps, bps = sd[f"{d}.pix_shuffle_conv.weight"], sd[f"{d}.pix_shuffle_conv.bias"]
+        for i in range(4):
+            for j in range(4):
+                rows = [cc * 16 + i * 4 + j for cc in range(n_class)]
+                L.add_conv(p, f"{d}.pix_shuffle_conv.{i}{j}", [L.Segment(fused, e)], [(i, j, L.conv_taps(wps[rows], pad=1)[0][2])], n_class,
+                           fh, fw, 1, ones(n_class), npf(bps[rows]), relu=True, osy=4, osx=4, out_ext=0,
+                           macs_per_pair=fh * fw * 9 * e * n_class)
+        p.ext.append(L.ExtOutput("cp", n_class, 4 * fh, 4 * fw))
+        return p
     di = []                                                     # DI[i] = |fx1[i] - fx2[i]| (:664-666, 938-940)
     for i, (ft, c, hh, ww) in enumerate(feats):
         t = p.tensor(f"DI{i}", 1, hh, ww, c)

@@ -14,7 +14,7 @@ import torch
 from torch.nn import init
 
 from .siamunet import SiamUnet_conc, SiamUnet_cross_conc, SiamUnet_diff, SiamUnet_sub, Unet
-from .changeformer import ChangeFormerV1, ChangeFormerV2, ChangeFormerV6
+from .changeformer import ChangeFormerV1, ChangeFormerV2, ChangeFormerV3, ChangeFormerV6
 from .bit import BASE_Transformer, ResNet
 from .changevig import ChangeGNNV1, ChangeGNNV2, ChangeGNNV2_Compare, VIG_V20_2
 from .dsifn import DSIFN, vgg16_base
@@ -25,7 +25,7 @@ from .snunet import SNUNet_ECAM
 # registry keys of models/networks.py:144-214 that this library does NOT implement (yet): asking for one
 # raises NotImplementedError like an unknown key does upstream, with the reason.
 _REFERENCE_ONLY = (
-    "ChangeFormerV3", "ChangeFormerV4", "ChangeFormerV5",
+    "ChangeFormerV4", "ChangeFormerV5",
 )
 
 _REGISTRY = {
@@ -47,6 +47,7 @@ _REGISTRY = {
     "ChangeGNNV1": lambda a: ChangeGNNV1(embed_dim=a.embed_dim),                   # networks.py:199-200
     "ChangeFormerV1": lambda a: ChangeFormerV1(),                                  # networks.py:184-185
     "ChangeFormerV2": lambda a: ChangeFormerV2(),                                  # networks.py:186-187
+    "ChangeFormerV3": lambda a: ChangeFormerV3(),                                  # networks.py:188-189
     "ChangeFormerV6": lambda a: ChangeFormerV6(embed_dim=a.embed_dim),             # networks.py:190-191
     # networks.py:201-208
     "ChangeGNNV2": lambda a: ChangeGNNV2(embed_dim=a.embed_dim, img_size=a.img_size),
@@ -61,7 +62,7 @@ _REGISTRY = {
 CLASSES = {"SiamUnet_diff": SiamUnet_diff, "SiamUnet_conc": SiamUnet_conc, "SiamUnet_sub": SiamUnet_sub,
            "SiamUnet_cross_conc": SiamUnet_cross_conc, "Unet": Unet, "SNUNet_ECAM": SNUNet_ECAM, "SegCD": SegCD,
            "ChangeGNNV1": ChangeGNNV1, "ChangeFormerV6": ChangeFormerV6,
-           "BASE_Transformer": BASE_Transformer, "ResNet": ResNet, "ChangeGNNV2": ChangeGNNV2, "ChangeGNNV2_Compare": ChangeGNNV2_Compare, "VIG_V20_2": VIG_V20_2, "ChangeFormerV1": ChangeFormerV1, "ChangeFormerV2": ChangeFormerV2,
+           "BASE_Transformer": BASE_Transformer, "ResNet": ResNet, "ChangeGNNV2": ChangeGNNV2, "ChangeGNNV2_Compare": ChangeGNNV2_Compare, "VIG_V20_2": VIG_V20_2, "ChangeFormerV1": ChangeFormerV1, "ChangeFormerV2": ChangeFormerV2, "ChangeFormerV3": ChangeFormerV3,
            "CDNet_model": lambda in_channels=3, num_classes=2: CDNet34(in_channels, num_classes)}
 
 

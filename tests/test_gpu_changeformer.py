@@ -92,7 +92,7 @@ def test_properties_and_conventions():
         net(torch.zeros(1, 3, 128, 128).cuda(), torch.zeros(1, 3, 128, 128).cuda())
 
 
-@pytest.mark.parametrize("version", ["1", "2"])
+@pytest.mark.parametrize("version", ["1", "2", "3"])
 def test_changeformer_v1_v2_match_oracle_and_golden(version, golden_dir):
     """ChangeFormerV1 / V2 (Tenc encoder, |fx1 - fx2|, convprojection_base / TDec): ONE tensor out, like upstream."""
     import os

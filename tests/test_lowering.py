@@ -310,7 +310,7 @@ def test_changeformer_program_matches_oracle():
         net.lower(128, 128)
 
 
-@pytest.mark.parametrize("version", ["1", "2"])
+@pytest.mark.parametrize("version", ["1", "2", "3"])
 def test_changeformer_v1_v2_program_matches_oracle(version):
     """ChangeFormerV1 / V2: Tenc (EncoderTransformer: 3x3 stride-2 patch embeds, depths 3-4-6-3, the never-called intra-patch blocks
     held as parameters), |fx1 - fx2| per scale, convprojection_base (V1) or TDec (V2) -- through the emulator."""
@@ -329,6 +329,10 @@ def test_changeformer_v1_v2_program_matches_oracle(version):
     assert 0.02 < (y[:, 1] > y[:, 0]).float().mean().item() < 0.98, "degenerate change map"
     assert "Tenc.patch_block2.0.attn.q.weight" in net.state_dict() and not any("patch_block" in o.name for o in prog.ops)
     assert sum(isinstance(o, L.AttentionSpec) for o in prog.ops) == 16 and sum(isinstance(o, L.AbsDiffSpec) for o in prog.ops) == 4
+    if version == "3":             # PixelShuffle(4) head: one single-phase launch per output phase, all writing the fp32 output
+        ps = [o for o in prog.ops if isinstance(o, L.ConvSpec) and ".pix_shuffle_conv." in o.name]
+        assert len(ps) == 16 and all(o.osy == 4 and o.osx == 4 and len(o.phases) == 1 and o.out_ext == 0 for o in ps)
+        assert sorted((o.phases[0].oy, o.phases[0].ox) for o in ps) == [(i, j) for i in range(4) for j in range(4)]
     with pytest.raises(ValueError):
         net.lower(512, 512)
 

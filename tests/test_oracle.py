@@ -50,6 +50,8 @@ def _oracle_forward(case, sd, x1, x2):
         return [nets.changeformer_v1_forward(sd, x1, x2)]
     if cls == "ChangeFormerV2":
         return [nets.changeformer_v2_forward(sd, x1, x2)]
+    if cls == "ChangeFormerV3":
+        return [nets.changeformer_v3_forward(sd, x1, x2)]
     if cls == "VIG_V20_2":
         return nets.vig_v20_forward(sd, x1, x2)
     if cls == "ChangeGNNV2":
