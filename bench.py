@@ -64,6 +64,14 @@ WORKLOADS = {
                                  "256x256 RGB pairs, batch 32 per GPU, bf16 convs + fp32 token path"),
     "changegnn_v2_256_b32": dict(net="ChangeGNNV2", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=32,
                                  desc="ChangeGNNV2 (pyramid ViG encoder, HFFM + VFFM decoder) 256x256 RGB pairs, batch 32 per GPU, bf16"),
+    "gnn_256_b32": dict(net="VIG_V20_2", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=32,
+                        desc="VIG_V20_2 (registry key GNN: pyramid ViG encoder, conv_diff_V20 + csam_V20 + AFF decoder) 256x256 RGB pairs, batch 32 per GPU, bf16"),
+    "changeformer_v2_256_b32": dict(net="ChangeFormerV2", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=32,
+                                    desc="ChangeFormerV2 (Tenc MiT encoder depths 3-4-6-3, |fx1 - fx2|, TDec) 256x256 RGB pairs, batch 32 per GPU, bf16"),
+    "changeformer_v3_256_b32": dict(net="ChangeFormerV3", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=32,
+                                    desc="ChangeFormerV3 (Tenc MiT encoder, TDecV2 with a PixelShuffle(4) head) 256x256 RGB pairs, batch 32 per GPU, bf16"),
+    "changeformer_v1_256_b32": dict(net="ChangeFormerV1", n_class=2, h=256, w=256, batch=32, kind="argmax", chunk=32,
+                                    desc="ChangeFormerV1 (Tenc MiT encoder, |fx1 - fx2|, convprojection_base) 256x256 RGB pairs, batch 32 per GPU, bf16"),
     "ifnet_256_b16": dict(net="DSIFN", n_class=1, h=256, w=256, batch=16, kind="sigmoid", chunk=16,
                           desc="IFNet / DSIFN (shared VGG16 features, channel + spatial attention difference decoder) 256x256 RGB pairs, "
                                "batch 16 per GPU, bf16, change = sigmoid(out) > 0.5"),
@@ -83,6 +91,8 @@ def build_net(wl):
     if wl["net"] == "BASE_Transformer":
         net = CLASSES["BASE_Transformer"](3, wl["n_class"], with_pos="learned", resnet_stages_num=4, token_len=4, enc_depth=1, dec_depth=8)
         return synth.prepare_(net.eval(), "BASE_Transformer")
+    if wl["net"] in ("VIG_V20_2", "ChangeFormerV1", "ChangeFormerV2", "ChangeFormerV3"):
+        return synth.prepare_(CLASSES[wl["net"]]().eval(), wl["net"])
     if wl["net"] in ("ChangeGNNV1", "ChangeFormerV6", "ChangeGNNV2"):
         return synth.prepare_(CLASSES[wl["net"]](3, wl["n_class"], embed_dim=256).eval(), wl["net"])
     return synth.prepare_(CLASSES[wl["net"]](3, wl["n_class"]).eval(), wl["net"])
@@ -110,6 +120,10 @@ def oracle_forward(wl, sd, x1, x2):
         return nets.dsifn_forward(sd, x1, x2)
     if wl["net"] == "ChangeGNNV2":
         return nets.changegnn_v2_forward(sd, x1, x2, "cross")
+    if wl["net"] == "VIG_V20_2":
+        return nets.vig_v20_forward(sd, x1, x2)
+    if wl["net"] in ("ChangeFormerV1", "ChangeFormerV2", "ChangeFormerV3"):
+        return getattr(nets, "changeformer_v%s_forward" % wl["net"][-1])(sd, x1, x2)
     raise KeyError(wl["net"])
 
 
