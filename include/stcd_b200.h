@@ -114,7 +114,7 @@ typedef struct stcd_conv_desc {
    * bf16 [n_tiles][total blocks][kc/8][n_tile][8]  (block = one tap of one chunk) */
   const uint16_t* weights;        /* HOST pointer, copied at add time */
   int64_t w_elems;
-  int32_t kc;                     /* channels per chunk: 16, 32 or 64 */
+  int32_t kc;                     /* channels per chunk: a multiple of 16 in [16, 128] (64 / 32 / 16, or e.g. 80 for 80-, 160-, 400-channel maps) */
   int32_t n_tile;                 /* GEMM N per CTA (multiple of 16, <= 256) */
   int32_t cout;                   /* real output channels */
   int32_t cout_pad;               /* padded to a multiple of n_tile */

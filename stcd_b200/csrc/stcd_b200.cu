@@ -1164,7 +1164,7 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
   if (!plan || !d) return -fail(STCD_ERR_STATE, "plan/desc is NULL");
   if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
   if (d->n_src < 1 || d->n_src > STCD_MAX_SRC) return -fail(STCD_ERR_INVALID, "n_src %d", d->n_src);
-  if (d->kc != 16 && d->kc != 32 && d->kc != 64) return -fail(STCD_ERR_INVALID, "kc %d must be 16/32/64", d->kc);
+  if (d->kc < 16 || d->kc > 128 || (d->kc % 16)) return -fail(STCD_ERR_INVALID, "kc %d must be a multiple of 16 in [16, 128]", d->kc);
   if (d->n_tile < 16 || d->n_tile > 256 || d->n_tile % 16) return -fail(STCD_ERR_INVALID, "n_tile %d", d->n_tile);
   if (d->cout < 1 || d->cout_pad < d->cout || d->cout_pad % d->n_tile)
     return -fail(STCD_ERR_INVALID, "cout %d / cout_pad %d / n_tile %d", d->cout, d->cout_pad, d->n_tile);

@@ -499,13 +499,26 @@ class Segment:
     c_store: int = -1       # stored width of the segment (default: the rest of the tensor)
 
 
-def choose_kc(c_list: Sequence[int]) -> int:
+FAST_MMA = 36        # stcd::kFastMma: taps x K-steps of one chunk that fit the issue path's constant-bank table
+
+
+def choose_kc(c_list: Sequence[int], taps_per_chunk: int = 1, cap: int = 112) -> int:
     """Channels per A-stage chunk.  Stored channel counts are multiples of 8; a count that is an odd
-    multiple of 8 is covered by a 16-channel chunk whose missing half TMA zero-fills."""
-    for kc in (64, 32, 16):
-        if all(((c + 15) // 16 * 16) % kc == 0 for c in c_list):
-            return kc
-    raise ValueError(f"channel counts {list(c_list)} are not multiples of 8")
+    multiple of 8 is covered by a 16-channel chunk whose missing half TMA zero-fills.
+
+    Powers of two first (64, 32, 16).  Channel counts like 80 / 160 / 400 / 800 (the ViG pyramid) only divide by 16 or 32: a
+    400-channel 1x1 conv would run 25 one-MMA chunks and pay the per-chunk pipeline hand-off 25 times (measured 6-12x above
+    the layer's floor), so any multiple of 16 up to 112 that divides every segment is taken instead (80 -> 5 K-steps per chunk)
+    as long as the chunk's taps x K-steps still fit the fast issue path."""
+    stored = [(c + 15) // 16 * 16 for c in c_list]
+    best = next((kc for kc in (64, 32, 16) if kc <= max(cap, 16) and all(s % kc == 0 for s in stored)), None)
+    if best is None:
+        raise ValueError(f"channel counts {list(c_list)} are not multiples of 8")
+    if best < 64:
+        for kc in range(min(cap, 112) // 16 * 16, best, -16):
+            if all(s % kc == 0 for s in stored) and taps_per_chunk * (kc // 16) <= FAST_MMA:
+                return kc
+    return best
 
 
 def choose_n_tile(cout: int, pair: bool) -> Tuple[int, int]:
@@ -546,7 +559,6 @@ def _taps_to_gemm(
     for s in segs:
         if s.c_off % 8:
             raise ValueError(f"{name}: segment channel offset {s.c_off} is not a multiple of 8")
-    kc = min(choose_kc(stored_c), max_kc)      # wide halos (dilated convs) take thinner chunks: the A stage is (tile + halo) * kc
     n_tile, cout_pad = choose_n_tile(cout, pair)
     n_nt = cout_pad // n_tile
     sy = [1] * len(srcs)
@@ -557,6 +569,9 @@ def _taps_to_gemm(
 
     # per phase, per segment: [(dy, dx, W[cout, c_real])]
     seg_phase_taps = [(oy, ox, _split_taps(name, segs, taps)) for (oy, ox, taps) in phase_taps]
+    max_taps = max((len(t) for (_, _, staps) in seg_phase_taps for t in staps), default=1)
+    # wide halos (dilated convs) take thinner chunks: the A stage is (tile + halo) * kc
+    kc = choose_kc(stored_c, max(1, max_taps), cap=max_kc if max_kc < 64 else 112)
     # halo extents per source: max over phases and segments of the tap range (stride-1 sources only)
     ey = [0] * len(srcs)
     ex = [0] * len(srcs)
