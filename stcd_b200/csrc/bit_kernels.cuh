@@ -34,7 +34,7 @@ __host__ __device__ constexpr int bit_dec_size(int inner) {
 __host__ __device__ constexpr int bit_dec_tail_off(int inner) { return 2 * kBitC + 3 * inner * kBitC + kBitC * inner; }
 constexpr int kBitDecTail = kBitC + 2 * kBitC + kBitC * kBitMlp + kBitMlp + kBitMlp * kBitC + kBitC;
 
-__device__ __forceinline__ float bit_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float bit_gelu(float x) { return gelu_fast(x); }
 
 // ------------------------------------------------------------------------------------------ tokenizer
 // grid = images, 256 threads.  State per thread and token: running max m, sum s, weighted channel sums acc[32].

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const __nv_bfloat16* __r
     }
     if (gelu) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = 0.5f * acc[e] * (1.f + erff(acc[e] * 0.70710678118654752f));
+      for (int e = 0; e < 8; ++e) acc[e] = gelu_fast(acc[e]);
     }
     *reinterpret_cast<uint4*>(obase + static_cast<size_t>(pix) * 8) = pack8(acc);
   }
