@@ -15,6 +15,7 @@ C-ABI on the GPU box.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -521,10 +522,21 @@ def choose_kc(c_list: Sequence[int], taps_per_chunk: int = 1, cap: int = 112) ->
     return best
 
 
-def choose_n_tile(cout: int, pair: bool) -> Tuple[int, int]:
-    """N per CTA: accumulators are double-buffered in TMEM (512 columns): 2 * (2 if pair else 1) * n_tile <= 512."""
+NARROW_K_MMAS = int(os.environ.get("STCD_NARROW_K", "24"))       # measured: C4 +2.8 %, C5 +3 %, SegCD-R50 +3.5 % against 0
+
+
+def choose_n_tile(cout: int, pair: bool, k_mmas: int = 1 << 30) -> Tuple[int, int]:
+    """N per CTA: accumulators are double-buffered in TMEM (512 columns): 2 * (2 if pair else 1) * n_tile <= 512.
+
+    Narrow-K ops (k_mmas = MMAs per tile <= NARROW_K_MMAS, e.g. the 1x1 convs of the ViG / MiT blocks) are bound by their epilogue,
+    not by the tensor pipe: a pair op with N = 128 owns all 512 TMEM columns, i.e. ONE CTA and four epilogue warps per SM.  N = 64
+    halves the accumulator, so two CTAs share the SM and twice as many epilogue warps drain it (and 320 outputs are 5 x 64 instead
+    of 3 x 128 with 17 % padding)."""
     cp = (cout + 15) // 16 * 16
     limit = 128 if pair else 256
+    if k_mmas <= NARROW_K_MMAS and cp > 64:
+        cp = (cout + 63) // 64 * 64
+        return 64, cp
     if cp <= limit:
         return cp, cp
     cp = (cout + 127) // 128 * 128
@@ -559,8 +571,7 @@ def _taps_to_gemm(
     for s in segs:
         if s.c_off % 8:
             raise ValueError(f"{name}: segment channel offset {s.c_off} is not a multiple of 8")
-    n_tile, cout_pad = choose_n_tile(cout, pair)
-    n_nt = cout_pad // n_tile
+    n_nt = 0
     sy = [1] * len(srcs)
     sx = [1] * len(srcs)
     for s in segs:
@@ -572,6 +583,9 @@ def _taps_to_gemm(
     max_taps = max((len(t) for (_, _, staps) in seg_phase_taps for t in staps), default=1)
     # wide halos (dilated convs) take thinner chunks: the A stage is (tile + halo) * kc
     kc = choose_kc(stored_c, max(1, max_taps), cap=max_kc if max_kc < 64 else 112)
+    k_mmas = max((sum(len(t) * -(-sc_ // 16) for sc_, t in zip(stored_c, staps)) for (_, _, staps) in seg_phase_taps), default=1)
+    n_tile, cout_pad = choose_n_tile(cout, pair, k_mmas)
+    n_nt = cout_pad // n_tile
     # halo extents per source: max over phases and segments of the tap range (stride-1 sources only)
     ey = [0] * len(srcs)
     ex = [0] * len(srcs)
