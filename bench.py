@@ -35,7 +35,7 @@ import torch  # noqa: E402
 
 # workload -> (net kind, ctor args, synth gain, H, W, per-GPU batch, binarise kind, config string)
 WORKLOADS = {
-    "snunet_256_b64": dict(net="SNUNet_ECAM", n_class=2, h=256, w=256, batch=64, kind="argmax",
+    "snunet_256_b64": dict(net="SNUNet_ECAM", n_class=2, h=256, w=256, batch=64, kind="argmax", chunk=64,
                            desc="C2: SNUNet-CD (ECAM) 256x256 RGB pairs, batch 64 per GPU, bf16"),
     "siamunet_diff_256": dict(net="SiamUnet_diff", n_class=2, h=256, w=256, batch=8, kind="argmax",
                               desc="C1: SiamUnet_diff 256x256 RGB pairs, batch 8 per GPU"),
