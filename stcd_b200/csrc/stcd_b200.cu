@@ -518,7 +518,14 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
       const Tensor& td = plan->tensors[k.dst];
       const int B = tq.mult * plan->chunk, N = tq.h * tq.w, NK = tk.h * tk.w, D = k.c / k.heads;
       const dim3 grid((N + 255) / 256, k.heads, B);                       // two queries per thread
-      if (D == 64)
+      const bool use_mma = NK == 64 && env_int("STCD_ATTN_MMA", 1);        // every stage of the 256 x 256 configurations
+      if (use_mma && D == 64)
+        stcd::sr_attention_mma_kernel<64><<<dim3((N + 63) / 64, k.heads, B), 128, 0, st>>>(
+            (const __nv_bfloat16*)tq.ptr, (const __nv_bfloat16*)tk.ptr, (__nv_bfloat16*)td.ptr, k.c, tq.c / 8, tk.c / 8, td.c / 8, N, k.scale);
+      else if (use_mma && D == 80)
+        stcd::sr_attention_mma_kernel<80><<<dim3((N + 63) / 64, k.heads, B), 128, 0, st>>>(
+            (const __nv_bfloat16*)tq.ptr, (const __nv_bfloat16*)tk.ptr, (__nv_bfloat16*)td.ptr, k.c, tq.c / 8, tk.c / 8, td.c / 8, N, k.scale);
+      else if (D == 64)
         stcd::sr_attention_kernel<64><<<grid, 128, 0, st>>>((const __nv_bfloat16*)tq.ptr, (const __nv_bfloat16*)tk.ptr, (__nv_bfloat16*)td.ptr,
                                                            k.c, tq.c / 8, tk.c / 8, td.c / 8, N, NK, k.scale);
       else

@@ -237,6 +237,111 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const __nv_bfloat16* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// Tensor-core variant of the spatial-reduction attention for exactly 64 keys (every stage of the 256 x 256 configurations): a warp owns
+// 16 queries; S = Q K^T and O = P V are mma.sync m16n8k16 bf16 tiles (the whole problem is 64 MMAs per warp -- far too small for a
+// tcgen05 / TMEM pipeline, whose 128-row tiles and allocation hand-shake would dominate), the softmax runs on the accumulator
+// fragments (row max / sum over the quad that shares a row), and P is re-used as the A operand of the second product straight from
+// registers.  K ([key][d]) and V^T ([d][key]) of the (image, head) sit in shared memory as bf16 with padded rows (no bank conflicts
+// on the B-fragment loads).  Q, K, V are bf16 tensors already; P is rounded to bf16 for the second product (one more bf16 rounding
+// on a path that is bf16 end to end).  grid (N / 64, heads, images), 128 threads.
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+template <int D>   // head dim: 64 or 80 (multiples of 16)
+__global__ void __launch_bounds__(128) sr_attention_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
+                                                               __nv_bfloat16* __restrict__ out, int C, int q_c8, int kv_c8, int out_c8,
+                                                               int N, float scale) {
+  constexpr int NK = 64, KS = D + 8, VS = NK + 8;              // padded row strides (bf16 elements)
+  __shared__ __align__(16) __nv_bfloat16 sk[NK * KS];          // K [key][d]
+  __shared__ __align__(16) __nv_bfloat16 svt[D * VS];          // V^T [d][key]
+  const int b = blockIdx.z, hd = blockIdx.y;
+  const int g0 = hd * (D / 8);
+  for (int i = threadIdx.x; i < NK * (D / 8); i += blockDim.x) {
+    const int j = i % NK, g = i / NK;                          // consecutive lanes: consecutive keys (coalesced 16 B loads)
+    const uint4 kq = __ldg(reinterpret_cast<const uint4*>(kv + ((static_cast<size_t>(b) * kv_c8 + g0 + g) * NK + j) * 8));
+    *reinterpret_cast<uint4*>(&sk[j * KS + g * 8]) = kq;
+    const uint4 vq = __ldg(reinterpret_cast<const uint4*>(kv + ((static_cast<size_t>(b) * kv_c8 + (C >> 3) + g0 + g) * NK + j) * 8));
+    const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vq);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) svt[(g * 8 + e) * VS + j] = ve[e];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = lane >> 2, cq = (lane & 3) * 2;                // fragment row / column pair of this lane
+  const int n0 = blockIdx.x * 64 + warp * 16;
+  if (n0 >= N) return;
+  const int na = min(n0 + r, N - 1), nb = min(n0 + r + 8, N - 1);   // clamped: out-of-range rows are computed but never stored
+  // ---- S = Q K^T: 8 key tiles x (D / 16) k-steps
+  float sacc[8][4];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) sacc[t][0] = sacc[t][1] = sacc[t][2] = sacc[t][3] = 0.f;
+  const __nv_bfloat16* qb = q + (static_cast<size_t>(b) * q_c8 + g0) * static_cast<size_t>(N) * 8;
+#pragma unroll
+  for (int ks = 0; ks < D / 16; ++ks) {
+    uint32_t a[4];
+    const __nv_bfloat16* q0 = qb + static_cast<size_t>(2 * ks) * N * 8;
+    const __nv_bfloat16* q1 = q0 + static_cast<size_t>(N) * 8;
+    a[0] = __ldg(reinterpret_cast<const uint32_t*>(q0 + static_cast<size_t>(na) * 8 + cq));
+    a[1] = __ldg(reinterpret_cast<const uint32_t*>(q0 + static_cast<size_t>(nb) * 8 + cq));
+    a[2] = __ldg(reinterpret_cast<const uint32_t*>(q1 + static_cast<size_t>(na) * 8 + cq));
+    a[3] = __ldg(reinterpret_cast<const uint32_t*>(q1 + static_cast<size_t>(nb) * 8 + cq));
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const __nv_bfloat16* kr = &sk[(t * 8 + r) * KS + ks * 16 + cq];
+      mma_bf16_16816(sacc[t], a, *reinterpret_cast<const uint32_t*>(kr), *reinterpret_cast<const uint32_t*>(kr + 8));
+    }
+  }
+  // ---- softmax over the 64 keys of rows r (values [t][0..1]) and r + 8 (values [t][2..3]); a row lives in the 4 lanes of a quad
+  float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    mx0 = fmaxf(mx0, fmaxf(sacc[t][0], sacc[t][1]));
+    mx1 = fmaxf(mx1, fmaxf(sacc[t][2], sacc[t][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+  uint32_t pa[4][4];                                           // P as A fragments: k-step = 16 keys = two key tiles
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const float p0 = __expf((sacc[t][0] - mx0) * scale), p1 = __expf((sacc[t][1] - mx0) * scale);
+    const float p2 = __expf((sacc[t][2] - mx1) * scale), p3 = __expf((sacc[t][3] - mx1) * scale);
+    sum0 += p0 + p1;
+    sum1 += p2 + p3;
+    pa[t >> 1][(t & 1) * 2] = pack_bf16x2(p0, p1);
+    pa[t >> 1][(t & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+  // ---- O = P V: D / 8 channel tiles x 4 key steps
+  __nv_bfloat16* ob = out + (static_cast<size_t>(b) * out_c8 + g0) * static_cast<size_t>(N) * 8;
+#pragma unroll
+  for (int t = 0; t < D / 8; ++t) {
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const __nv_bfloat16* vr = &svt[(t * 8 + r) * VS + ks * 16 + cq];
+      mma_bf16_16816(o, pa[ks], *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+    }
+    if (n0 + r < N) *reinterpret_cast<uint32_t*>(ob + (static_cast<size_t>(t) * N + n0 + r) * 8 + cq) = pack_bf16x2(o[0] * inv0, o[1] * inv0);
+    if (n0 + r + 8 < N) *reinterpret_cast<uint32_t*>(ob + (static_cast<size_t>(t) * N + n0 + r + 8) * 8 + cq) = pack_bf16x2(o[2] * inv1, o[3] * inv1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Squeeze-and-excitation gates (DTCDSCN: SELayer, models/DTCDSCN.py:11-26; SCSEBlock :144-173).
 //   pass 1  chan_sum_kernel: per (image, channel) sums over a pixel range -> partial[b][range][C]  (fixed order: deterministic)
 //   pass 2  gate_apply_kernel: every CTA finishes the mean, runs the two tiny FC layers for its image in shared memory
