@@ -259,8 +259,14 @@ def run_attention(op: L.AttentionSpec, T: Dict[str, torch.Tensor]) -> None:
     qh = q.reshape(b, h * w, op.heads, d).permute(0, 2, 1, 3)
     k = kv[..., :c].reshape(b, -1, op.heads, d).permute(0, 2, 1, 3)
     v = kv[..., c:].reshape(b, -1, op.heads, d).permute(0, 2, 1, 3)
-    attn = ((qh @ k.transpose(-2, -1)) * op.scale).softmax(dim=-1)
-    T[op.dst][..., : c] = _bf16((attn @ v).transpose(1, 2).reshape(b, h, w, c))
+    s_ = (qh @ k.transpose(-2, -1)) * op.scale
+    if k.shape[2] == 64:
+        # the tensor-core kernel's rounding points: un-normalised probabilities exp(s - max) rounded to bf16 for P V, fp32 row sum
+        p_ = torch.exp(s_ - s_.amax(dim=-1, keepdim=True))
+        o = (_bf16(p_) @ v) / p_.sum(dim=-1, keepdim=True)
+    else:
+        o = s_.softmax(dim=-1) @ v
+    T[op.dst][..., : c] = _bf16(o.transpose(1, 2).reshape(b, h, w, c))
 
 
 def run_dwconv(op: L.DWConvSpec, T: Dict[str, torch.Tensor]) -> None:
