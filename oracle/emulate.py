@@ -211,10 +211,15 @@ def run_seg_head(op: L.SegHeadSpec, T: Dict[str, torch.Tensor], chunk: int, ext:
     d = T[op.src][..., : op.c].permute(0, 3, 1, 2)
     d1, d2 = d[:chunk], d[chunk: 2 * chunk]
     w = torch.from_numpy(op.weight).reshape(3, 3, op.c).permute(2, 0, 1)[None]      # [1, c, 3, 3]
+    mma = op.c == 16 and op.diff_src is None      # segcd_head_mma_kernel: bf16 weights, |d1 - d2| rounded to bf16
+    if mma:
+        w = _bf16(w)
     b = torch.tensor([op.bias])
     head = lambda t: torch.nn.functional.conv2d(t, w, b, padding=1)  # noqa: E731
     m1, m2 = head(d1), head(d2)
     dd = (d1 - d2).abs() if op.diff_src is None else T[op.diff_src][:chunk, :, :, : op.c].permute(0, 3, 1, 2)
+    if mma:
+        dd = _bf16(dd)
     change = torch.minimum(head(dd), (m1 - m2).abs())
     ext[op.out_ext][:nv] = m1[:nv]
     ext[op.out_ext + 1][:nv] = m2[:nv]

@@ -25,6 +25,19 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.f + copysignf(e, z));
 }
 
+// mma.sync m16n8k16 bf16 -> fp32 (the small tensor-core tiles of the attention and SegCD-head kernels)
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+
 
 // x1, x2: fp32 NCHW [n_valid, cin, h, w] -> dst bf16 [2*chunk][c8][h][w][8] (c8 = 1 or 2 channel
 // groups); channels >= cin are zero; T1 images occupy [0, chunk), T2 images [chunk, 2*chunk).
@@ -608,6 +621,96 @@ __global__ void __launch_bounds__(256) segcd_head_kernel(const __nv_bfloat16* __
       m1[o] = a1[r];
       m2[o] = a2[r];
       change[o] = fminf(ad[r], fabsf(a1[r] - a2[r]));
+    }
+  }
+}
+
+// Tensor-core variant of the SegCD head for C = 16 without a feature-level diff tensor (config C3): the three 3x3 convs 16 -> 1 over
+// d1, d2 and |d1 - d2| were 432 FMAs per pixel on the FP32 pipe (the kernel's bound).  A warp takes 16 consecutive pixels of a tile
+// row; one filter tap is one m16n8k16 step (K = its 16 channels), the A fragments come straight from the staged bf16 tile as 32-bit
+// LDS (a warp's loads cover 128 contiguous bytes), the weights sit in column 0 of the B fragment (rounded to bf16 like every conv
+// weight of the path), |d1 - d2| is formed on the packed pairs (HSUB2 + abs: the same single rounding as fp32 subtract -> bf16).
+// 27 MMAs per 16 pixels; 7 of the 8 output columns are padding, which is irrelevant at this size.
+__global__ void __launch_bounds__(256) segcd_head_mma_kernel(const __nv_bfloat16* __restrict__ d, const float* __restrict__ wgt, float bias,
+                                                             int chunk, int h, int w, float* __restrict__ m1, float* __restrict__ m2,
+                                                             float* __restrict__ change) {
+  constexpr int PW = kHeadTW + 2, PH = kHeadTH + 2, C8 = 2, C = 16;
+  extern __shared__ uint4 s_head_dyn[];         // [2][C8][PH][PW]
+  uint4 (*s_d)[C8][PH][PW] = reinterpret_cast<uint4 (*)[C8][PH][PW]>(s_head_dyn);
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.x * kHeadTW, y0 = blockIdx.y * kHeadTH;
+  const size_t hw = static_cast<size_t>(h) * w;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = warp; row < 2 * C8 * PH; row += 8) {
+    const int py = row % PH;
+    const int sg = row / PH;
+    const int g = sg % C8, sidx = sg / C8;
+    const int yy = y0 + py - 1;
+    const bool row_ok = (yy >= 0) && (yy < h);
+    const __nv_bfloat16* src_row = d + (static_cast<size_t>(sidx * chunk + n) * C8 + g) * hw * 8 + static_cast<size_t>(row_ok ? yy : 0) * w * 8;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int px = lane + 32 * pass;
+      if (px < PW) {
+        const int xx = x0 + px - 1;
+        const bool ok = row_ok && xx >= 0 && xx < w;
+        const void* gp = src_row + static_cast<size_t>(ok ? xx : 0) * 8;
+        const uint32_t sp = static_cast<uint32_t>(__cvta_generic_to_shared(&s_d[sidx][g][py][px]));
+        const int nbytes = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sp), "l"(gp), "r"(nbytes) : "memory");
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const int r = lane >> 2, cq = (lane & 3) * 2;
+  uint32_t b0[9], b1[9];                        // B fragments: column 0 (lanes with r == 0) holds the tap's 16 weights
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    b0[t] = r == 0 ? pack_bf16x2(__ldg(wgt + t * C + cq), __ldg(wgt + t * C + cq + 1)) : 0u;
+    b1[t] = r == 0 ? pack_bf16x2(__ldg(wgt + t * C + 8 + cq), __ldg(wgt + t * C + 8 + cq + 1)) : 0u;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const unsigned char* sb = reinterpret_cast<const unsigned char*>(s_head_dyn);
+  auto frag = [&](int s, int g, int py, int px) -> uint32_t {      // channels 8g + cq, +1 of pixel (py, px) of stream s
+    return *reinterpret_cast<const uint32_t*>(sb + ((static_cast<size_t>((s * C8 + g) * PH + py) * PW + px) * 16 + cq * 2));
+  };
+#pragma unroll 1
+  for (int i = 0; i < (kHeadTW / 16) * kHeadTH / 8; ++i) {         // 32 row segments of 16 pixels, 4 per warp
+    const int seg = warp * ((kHeadTW / 16) * kHeadTH / 8) + i;
+    const int ty = seg / (kHeadTW / 16), xw = (seg % (kHeadTW / 16)) * 16;
+    float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f}, cd[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int py = ty + ky, px = xw + r + kx;
+        uint32_t a1[4], a2[4], ad[4];
+        a1[0] = frag(0, 0, py, px), a1[1] = frag(0, 0, py, px + 8), a1[2] = frag(0, 1, py, px), a1[3] = frag(0, 1, py, px + 8);
+        a2[0] = frag(1, 0, py, px), a2[1] = frag(1, 0, py, px + 8), a2[2] = frag(1, 1, py, px), a2[3] = frag(1, 1, py, px + 8);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 df = __habs2(__hsub2(*reinterpret_cast<const __nv_bfloat162*>(&a1[e]), *reinterpret_cast<const __nv_bfloat162*>(&a2[e])));
+          ad[e] = *reinterpret_cast<const uint32_t*>(&df);
+        }
+        mma_bf16_16816(c1, a1, b0[ky * 3 + kx], b1[ky * 3 + kx]);
+        mma_bf16_16816(c2, a2, b0[ky * 3 + kx], b1[ky * 3 + kx]);
+        mma_bf16_16816(cd, ad, b0[ky * 3 + kx], b1[ky * 3 + kx]);
+      }
+    }
+    if (cq == 0) {                                                 // column 0 of the accumulator tile: rows r and r + 8
+      const int yy = y0 + ty;
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const int xx = x0 + xw + r + 8 * hrow;
+        if (yy < h && xx < w) {
+          const float v1 = c1[2 * hrow] + bias, v2 = c2[2 * hrow] + bias, vd = cd[2 * hrow] + bias;
+          const size_t o = static_cast<size_t>(n) * hw + static_cast<size_t>(yy) * w + xx;
+          m1[o] = v1;
+          m2[o] = v2;
+          change[o] = fminf(vd, fabsf(v1 - v2));
+        }
+      }
     }
   }
 }

@@ -566,6 +566,8 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
         if (k.diff_src < 0) {
           if (k.c == 8)
             stcd::segcd_head_kernel<1, false><<<grid, 256, 2 * tile, st>>>(dp, ddp, k.w_dev, k.bias, plan->chunk, t.h, t.w, m1, m2, ch);
+          else if (env_int("STCD_HEAD_MMA", 1))
+            stcd::segcd_head_mma_kernel<<<grid, 256, 2 * tile, st>>>(dp, k.w_dev, k.bias, plan->chunk, t.h, t.w, m1, m2, ch);
           else
             stcd::segcd_head_kernel<2, false><<<grid, 256, 2 * tile, st>>>(dp, ddp, k.w_dev, k.bias, plan->chunk, t.h, t.w, m1, m2, ch);
         } else {

@@ -244,17 +244,6 @@ __global__ void __launch_bounds__(128) dwconv3x3_kernel(const __nv_bfloat16* __r
 // registers.  K ([key][d]) and V^T ([d][key]) of the (image, head) sit in shared memory as bf16 with padded rows (no bank conflicts
 // on the B-fragment loads).  Q, K, V are bf16 tensors already; P is rounded to bf16 for the second product (one more bf16 rounding
 // on a path that is bf16 end to end).  grid (N / 64, heads, images), 128 threads.
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&v);
-}
-
 template <int D>   // head dim: 64 or 80 (multiples of 16)
 __global__ void __launch_bounds__(128) sr_attention_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
                                                                __nv_bfloat16* __restrict__ out, int C, int q_c8, int kv_c8, int out_c8,
