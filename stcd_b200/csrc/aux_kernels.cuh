@@ -25,6 +25,22 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.f + copysignf(e, z));
 }
 
+// gelu_fast on a packed pair: the polynomial and the products run as FFMA2 / FMUL2, the reciprocal and exponential stay scalar
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  const float2 z = __fmul2_rn(x, make_float2(0.70710678118654752f, 0.70710678118654752f));
+  const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+  const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), az, make_float2(1.f, 1.f));
+  const float2 t = make_float2(__fdividef(1.f, den.x), __fdividef(1.f, den.y));
+  float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
+  p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
+  p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
+  const float2 nz2 = __fmul2_rn(make_float2(-az.x, -az.y), az);
+  const float2 pe = __fmul2_rn(__fmul2_rn(p, t), make_float2(__expf(nz2.x), __expf(nz2.y)));
+  const float2 e = make_float2(copysignf(1.f - pe.x, z.x), copysignf(1.f - pe.y, z.y));      // erf(z)
+  return __fmul2_rn(__fmul2_rn(x, make_float2(0.5f, 0.5f)), make_float2(1.f + e.x, 1.f + e.y));
+}
+
 // mma.sync m16n8k16 bf16 -> fp32 (the small tensor-core tiles of the attention and SegCD-head kernels)
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"

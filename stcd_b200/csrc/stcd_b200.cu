@@ -538,7 +538,9 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
       const Tensor& td = plan->tensors[k.dst];
       const int B = ts.mult * plan->chunk;
       const int hwp = ts.h * ts.w;
-      const dim3 grid((unsigned)std::max(1, (hwp + 511) / 512), (unsigned)(k.c / 8), (unsigned)B);   // <= 4 pixels per thread
+      const int items = ((ts.w + 3) / 4) * ts.h;                        // one thread per 4 horizontally adjacent pixels
+      const dim3 grid((unsigned)std::max(1, (items + 127) / 128), (unsigned)(k.c / 8), (unsigned)B);
+      (void)hwp;
       stcd::dwconv3x3_kernel<<<grid, 128, 0, st>>>((const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, k.wb_dev, k.wb_dev + (size_t)k.c * 9, B,
                                                    k.c / 8, ts.c / 8, td.c / 8, ts.h, ts.w, k.gelu);
       CUDA_TRY(cudaGetLastError());
