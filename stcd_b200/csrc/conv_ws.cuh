@@ -522,7 +522,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
         for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
       } else if (p.relu == 2) {              // nn.GELU(): 0.5 x (1 + erf(x / sqrt 2))
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = gelu_fast(x[j]);
+        for (int j = 0; j < 16; j += 2) {
+          const float2 g2 = gelu_fast2(make_float2(x[j], x[j + 1]));
+          x[j] = g2.x, x[j + 1] = g2.y;
+        }
       } else if (p.relu == 3) {              // nn.PReLU() with one slope
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = x[j] >= 0.f ? x[j] : x[j] * p.act_alpha;
