@@ -428,8 +428,8 @@ __global__ void __launch_bounds__(kBitDecThreads) bit_decoder_kernel(const __nv_
       bit_matvec2<kBitC>(y0, y1, w1t + half * kBitC, kBitMlp, h0, h1);
 #pragma unroll
       for (int k = 0; k < kBitC / 2; ++k) {
-        h0.v[k].x = bit_gelu(h0.v[k].x), h0.v[k].y = bit_gelu(h0.v[k].y);
-        h1.v[k].x = bit_gelu(h1.v[k].x), h1.v[k].y = bit_gelu(h1.v[k].y);
+        h0.v[k] = gelu_fast2(h0.v[k]);
+        h1.v[k] = gelu_fast2(h1.v[k]);
       }
       bit_matvec2<kBitC>(reinterpret_cast<const float*>(h0.v), reinterpret_cast<const float*>(h1.v), w2t + half * kBitC * kBitC, kBitC, x0, x1);
     }
