@@ -507,7 +507,8 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
       const int B = ts.mult * plan->chunk;
       const size_t total = (size_t)B * ts.h * ts.w;
       __nv_bfloat16* d2 = k.dst2 >= 0 ? (__nv_bfloat16*)plan->tensors[k.dst2].ptr : nullptr;
-      stcd::layernorm_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, 148 * 16)), 256, 0, st>>>(
+      // 4 threads per pixel (a warp = 8 pixels x 4 channel slices)
+      stcd::layernorm_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((total * 4 + 255) / 256, 148 * 16)), 256, 0, st>>>(
           (const __nv_bfloat16*)ts.ptr, (__nv_bfloat16*)td.ptr, d2, k.gb_dev, k.gb_dev + k.c, B, k.c, ts.c / 8, td.c / 8,
           k.dst2 >= 0 ? plan->tensors[k.dst2].c / 8 : 0, ts.h, ts.w, k.eps);
       CUDA_TRY(cudaGetLastError());
