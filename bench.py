@@ -244,7 +244,31 @@ def cpu_baseline(wl, seconds_target: float = 15.0, threads: int | None = None):
 
 
 # ------------------------------------------------------------------------------------------ arms
+def reference_forward(wl, net):
+    """The UNMODIFIED reference module for this workload, fed with our net's state_dict (identical names), when
+    /root/reference is present (build container; oracle/refimport.py); else None -> the oracle port is timed."""
+    try:
+        from oracle import refimport
+        if not refimport.available():
+            return None
+        where = {"SNUNet_ECAM": ("models.SNUNet", "SNUNet_ECAM", (3, wl["n_class"])),
+                 "SiamUnet_diff": ("models.SiamUnet_diff", "SiamUnet_diff", (3, wl["n_class"])),
+                 "SiamUnet_conc": ("models.SiamUnet_conc", "SiamUnet_conc", (3, wl["n_class"])),
+                 "SegCD": ("segmentation_models_pytorch", "SegCD", (wl.get("encoder", "resnet34"), 5, None))}.get(wl["net"])
+        if where is None:
+            return None
+        ref = getattr(refimport.ref_module(where[0]), where[1])(*where[2]).eval()
+        ref.load_state_dict(net.state_dict())
+        return ref
+    except Exception as e:      # any import trouble: fall back to the port, say so
+        print(f"bench.py: reference import failed ({e!r}); timing the oracle port", file=sys.stderr)
+        return None
+
+
 def run_reference(args, wl, rank, world):
+    """The reference arm: the reference's own CPU forward + its bincount evaluator on this box's host cores, all
+    threads, on a BOUNDED sample of the workload per step (``config.pairs_per_step`` pairs of the workload's size --
+    the full batch of 64 would take minutes per step on a CPU)."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
@@ -253,13 +277,14 @@ def run_reference(args, wl, rank, world):
     from stcd_b200 import synth
     net = build_net(wl)
     sd = net.state_dict()
+    ref = reference_forward(wl, net)
     n = 2 if wl["h"] * wl["w"] < 512 * 512 else 1   # bounded sample per step
     x1, x2 = synth.image_pairs(n, wl["h"], wl["w"])
     lab = synth.labels(n, wl["h"], wl["w"]).numpy()
 
     def step():
         with torch.no_grad():
-            y = oracle_forward(wl, sd, x1, x2)
+            y = ref(x1, x2) if ref is not None else oracle_forward(wl, sd, x1, x2)
         y = y[-1] if isinstance(y, (list, tuple)) else y
         ometric.confusion_matrix(ometric.binarise(y.numpy(), wl["kind"]), lab)
 
@@ -270,15 +295,45 @@ def run_reference(args, wl, rank, world):
         step()
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
-    sample = f"{n} pairs per step, {args.steps} steps"
+    kind = "reference" if ref is not None else "port"
+    sample = (f"{n} pairs of {wl['h']}x{wl['w']} per step, {args.steps} steps; "
+              + ("unmodified reference module from /root/reference" if ref is not None else "oracle/nets.py port (no /root/reference on this box)")
+              + " + numpy bincount evaluator")
     print(json.dumps({
         "impl": "reference", "metric": "image-pairs/sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "batch_per_gpu": wl["batch"], "h": wl["h"], "w": wl["w"]},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": wl["desc"], "batch_per_gpu": wl["batch"], "h": wl["h"], "w": wl["w"],
+                   "pairs_per_step": n,
+                   "note": f"bounded sample: each timed step is {n} pair(s) of the workload's size, not the full batch"},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def pin_to_gpu_numa(local_rank: int):
+    """Bind this rank's threads (and, by first touch, the pinned host buffers it allocates afterwards) to the NUMA node
+    its GPU hangs off, so eight ranks' H2D copies do not all cross the same socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:              # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return {"numa_node": None}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:                           # no sysfs / nvml in this container: run unpinned
+        return {"numa_node": None, "why": repr(e)[:80]}
 
 
 def run_ours(args, wl, rank, world, local_rank):
@@ -288,6 +343,7 @@ def run_ours(args, wl, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device — stcd_b200 has no CPU path (use --impl reference for the CPU arm)")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = pin_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     out = measure(args, args.workload, wl, rank, world, local_rank, dev, full=True)
@@ -304,8 +360,9 @@ def run_ours(args, wl, rank, world, local_rank):
         o2 = measure(a2, other, wl2, rank, world, local_rank, dev, full=False)
         if out is not None and o2 is not None:
             out["also"] = {k: o2[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "config",
-                                              "e2e", "gpu_launches", "roofline")}
+                                              "e2e", "e2e_u8", "gpu_launches", "roofline")}
     if out is not None:
+        out["host"] = {"cores": os.cpu_count(), "rank0_affinity": numa}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -344,7 +401,10 @@ def measure(args, wl_name, wl, rank, world, local_rank, dev, full=True):
         s = i % n_sets
         plan.forward(dx1[s], dx2[s], outs=logits)
         metric.addLogits(logits[-1], dlab[s], kind=wl["kind"], pred_out=pred)
-        metric.allreduce()
+
+    # the path's only collective: the int64 matrix is summed over the ranks ONCE per evaluation, like the reference
+    # reads its matrix once after the loop (train_stcd.py:488-492) -- inside the timed region, after the last step
+    step.finish = metric.allreduce
 
     # End to end through the public API (net(x1, x2) + SegmentationMetric.addLogits) with HOST buffers.  Like a
     # DataLoader(pin_memory=True) + non_blocking prefetcher, the H2D copy of step i+1 rides a copy stream while
@@ -378,18 +438,22 @@ def measure(args, wl_name, wl, rank, world, local_rank, dev, full=True):
             y = y[-1] if isinstance(y, (list, tuple)) else y
             metric.addLogits(y, slot["lab"], kind=wl["kind"], pred_out=pred)
             slot["free"].record(cur)
-            metric.allreduce()
             hpred.copy_(pred, non_blocking=True)
             hcm.copy_(metric.confusion_counts().reshape(-1), non_blocking=True)
 
+        def finish():
+            metric.allreduce()
+            hcm.copy_(metric.confusion_counts().reshape(-1), non_blocking=True)
+
         step_fn.reset = lambda: state.update(next=None)   # the timed region starts with nothing prefetched
+        step_fn.finish = finish
         return step_fn
 
     step_e2e = make_e2e(hx1, hx2, net)
     # the same with the decoded uint8 HWC images the reference's loader starts from (data/dataset.py:196-203):
     # ToTensor + Normalize run in the input-pack kernel, a quarter of the PCIe bytes
     gu = torch.Generator().manual_seed(77 + rank)
-    if full:
+    if True:
         hu1 = [torch.randint(0, 256, (B, H, W, 3), generator=gu, dtype=torch.uint8).pin_memory() for _ in range(n_sets)]
         hu2 = [torch.randint(0, 256, (B, H, W, 3), generator=gu, dtype=torch.uint8).pin_memory() for _ in range(n_sets)]
         step_e2e_u8 = make_e2e(hu1, hu2, net.forward_uint8)
@@ -408,6 +472,8 @@ def measure(args, wl_name, wl, rank, world, local_rank, dev, full=True):
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        if hasattr(fn, "finish"):
+            fn.finish()
         e1.record()
         if world > 1:
             dist.barrier()
@@ -423,7 +489,7 @@ def measure(args, wl_name, wl, rank, world, local_rank, dev, full=True):
     metric.reset()
     ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
     metric.reset()
-    ms_e2e_u8 = timed(step_e2e_u8, args.steps, max(3, args.warmup // 2)) if full else float("nan")
+    ms_e2e_u8 = timed(step_e2e_u8, args.steps, max(3, args.warmup // 2))
     value = world * B * args.steps / (ms_total / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
     e2e_u8 = world * B * args.steps / (ms_e2e_u8 / 1e3)
@@ -492,7 +558,6 @@ def measure(args, wl_name, wl, rank, world, local_rank, dev, full=True):
             "per_op_ms": [[n, round(ms, 4)] for n, ms, _ in prof],
         }
         if not full:
-            out.pop("e2e_u8")
             out.pop("per_op_ms")
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(wl)

@@ -44,3 +44,26 @@ def scores(cm: np.ndarray) -> dict:
         iou = diag / (cm.sum(1) + cm.sum(0) - diag)
         oa = diag.sum() / cm.sum()
     return {"OA": oa, "Precision": precision, "Recall": recall, "F1": f1, "IoU": iou, "mIoU": iou.mean()}
+
+
+def confuse_matrix_meter_scores(pred: np.ndarray, label: np.ndarray, n_class: int = 2) -> dict:
+    """Independent numpy statement of what ``ConfuseMatrixMeter.update_cm`` + ``get_scores`` produce for one batch
+    (models/evaluator.py:115,150-167).  PARITY UNPINNED: ``misc/metric_tool.py`` is absent from the reference tree; this
+    follows upstream BIT_CD's ``get_confuse_matrix`` (labels outside [0, n_class) masked out) and ``cm2score`` (eps =
+    float32 machine epsilon in every quotient, nanmean over classes)."""
+    eps = np.finfo(np.float32).eps
+    gt, pr = label.ravel().astype(np.int64), pred.ravel().astype(np.int64)
+    keep = (gt >= 0) & (gt < n_class)
+    hist = np.zeros((n_class, n_class), np.float64)
+    for g in range(n_class):
+        for p in range(n_class):
+            hist[g, p] = np.count_nonzero(keep & (gt == g) & (pr == p))
+    tp = np.diag(hist)
+    rec = tp / (hist.sum(1) + eps)
+    pre = tp / (hist.sum(0) + eps)
+    f1 = 2 * rec * pre / (rec + pre + eps)
+    iou = tp / (hist.sum(1) + hist.sum(0) - tp + eps)
+    out = {"acc": tp.sum() / (hist.sum() + eps), "miou": np.nanmean(iou), "mf1": np.nanmean(f1)}
+    for i in range(n_class):
+        out.update({f"iou_{i}": iou[i], f"F1_{i}": f1[i], f"precision_{i}": pre[i], f"recall_{i}": rec[i]})
+    return out

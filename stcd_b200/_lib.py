@@ -34,25 +34,62 @@ def _sources():
     return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [HEADER]
 
 
+STAMP_PATH = PKG_DIR / "libstcd_b200.so.srchash"      # sha256 of the sources the .so was built from (travels with it)
+LOCK_PATH = PKG_DIR / ".build.lock"
+
+
+def _source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for src in _sources():
+        h.update(src.name.encode())
+        h.update(src.read_bytes())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
+    """Stale when the .so is missing or was built from other sources (content hash, not mtimes: a snapshot copied
+    to a GPU box does not keep them)."""
     if not LIB_PATH.exists():
         return True
-    t = LIB_PATH.stat().st_mtime
-    return any(s.stat().st_mtime > t for s in _sources())
+    try:
+        return STAMP_PATH.read_text().strip() != _source_hash()
+    except OSError:
+        t = LIB_PATH.stat().st_mtime          # no stamp (built by hand): fall back to mtimes
+        return any(s.stat().st_mtime > t for s in _sources())
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> stcd_b200/libstcd_b200.so"""
-    if not force and not needs_build():
-        return LIB_PATH
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", str(LIB_PATH), str(CSRC / "stcd_b200.cu")]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise StcdError(f"nvcc failed ({' '.join(cmd)}):\n{r.stdout}\n{r.stderr}")
-    if verbose:
-        print(r.stderr)
-    return LIB_PATH
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> stcd_b200/libstcd_b200.so
+
+    Safe under torchrun: ranks serialise on a file lock, the compiler writes a temporary file that is renamed
+    over the library (no rank can dlopen a half-written .so) and whoever gets the lock second finds it fresh."""
+    import fcntl
+    import tempfile
+    with open(LOCK_PATH, "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB_PATH
+            nvcc = os.environ.get("NVCC", "nvcc")
+            fd, tmp = tempfile.mkstemp(prefix=".libstcd_b200.", suffix=".so.tmp", dir=str(PKG_DIR))
+            os.close(fd)
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, str(CSRC / "stcd_b200.cu")]
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True)
+                if r.returncode != 0:
+                    raise StcdError(f"nvcc failed ({' '.join(cmd)}):\n{r.stdout}\n{r.stderr}")
+                os.chmod(tmp, 0o755)
+                os.replace(tmp, LIB_PATH)
+                STAMP_PATH.write_text(_source_hash() + "\n")
+            finally:
+                if os.path.exists(tmp):
+                    os.unlink(tmp)
+            if verbose:
+                print(r.stderr)
+            return LIB_PATH
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 class Chunk(C.Structure):
@@ -204,6 +241,12 @@ def lib() -> C.CDLL:
         except (StcdError, FileNotFoundError) as e:
             if not LIB_PATH.exists():
                 raise StcdError(f"libstcd_b200.so is missing and could not be built: {e}") from e
+            if os.environ.get("STCD_ALLOW_STALE", "0") != "1":
+                # never serve kernels older than the sources silently (ABI_VERSION only catches struct changes)
+                raise StcdError("libstcd_b200.so is older than stcd_b200/csrc and the rebuild failed "
+                                f"(set STCD_ALLOW_STALE=1 to load it anyway): {e}") from e
+            import warnings
+            warnings.warn(f"loading a STALE libstcd_b200.so (rebuild failed: {e})", RuntimeWarning)
     handle = C.CDLL(str(LIB_PATH))
     for name, restype, argtypes in SYMBOLS:
         fn = getattr(handle, name)

@@ -310,7 +310,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       for (int c = 0; c < phase.chunk_count; ++c) {
         const ChunkLoad L = s_cload[c];
         mbar_wait_relaxed(&a_empty[s], par);
-        if (leader) {
+        if (p.dbg & 8) {   // diagnostics: no activation loads
+          if (leader) mbar_arrive(&a_full[s]);
+        } else if (leader) {
           mbar_expect_tx(&a_full[s], L.tx_bytes);
           if (t == 0 && c == 0) STCD_STAMP(8);
           uint8_t* dst = smem_a + s * p.a_stage_bytes;
@@ -506,7 +508,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     // ============================== epilogue (warps 3..6) ==============================
     const bool has_raw = STCD_HAS(E_RAW, p.out_raw != nullptr);
     const bool has_aff2 = STCD_HAS(E_AFF2, p.scale2 != nullptr);
-    const bool has_res = STCD_HAS(E_RES, p.res != nullptr);
+    const bool has_res = STCD_HAS(E_RES, p.res != nullptr) && !(p.dbg & 4);   // dbg bit2: no residual
     const bool has_relu = STCD_HAS(E_RELU, p.relu != 0);
     const bool has_out0 = STCD_HAS(E_OUT0, p.out0 != nullptr);
     const bool has_pool = STCD_HAS(E_POOL, p.out_pool != nullptr);
@@ -581,7 +583,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       const int tile_y = tile % p.tiles_y;
       const int img = tile / p.tiles_y;
       const int gy = tile_y * kTileH + ty, gx = tile_x * kTileW + tx;
-      const bool valid = (gy < p.hg) && (gx < p.wg);
+      const bool valid = (gy < p.hg) && (gx < p.wg) && !(p.dbg & 2);   // dbg bit1: no global stores / residual loads
       const int oy = gy * p.osy + phase.oy, ox = gx * p.osx + phase.ox;
       const uint32_t pix = static_cast<uint32_t>(oy) * p.wo + ox;
       const uint32_t pix_pool = static_cast<uint32_t>(oy >> 1) * (p.wo >> 1) + (ox >> 1);

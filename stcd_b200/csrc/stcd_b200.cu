@@ -624,6 +624,29 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
 }  // namespace
 
 // ================================================================================ C-ABI
+// Entry points run on the plan's (or the buffers') device and leave the caller's current device as they found it:
+// a model on cuda:1 must not flip PyTorch's current device for the calling thread.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int dev) {
+    if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+// device that owns a device pointer (-1: not a device pointer / unknown, stay on the current device)
+static int device_of(const void* ptr) {
+  cudaPointerAttributes a;
+  if (ptr && cudaPointerGetAttributes(&a, ptr) == cudaSuccess && (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged))
+    return a.device;
+  cudaGetLastError();
+  return -1;
+}
+
 extern "C" {
 
 const char* stcd_last_error(void) { return g_err.c_str(); }
@@ -658,7 +681,7 @@ int stcd_plan_create(int device, int chunk_pairs, stcd_plan** out) {
 
 void stcd_plan_destroy(stcd_plan* plan) {
   if (!plan) return;
-  cudaSetDevice(plan->device);
+  DeviceGuard dev_guard(plan->device);
   for (ConvOp& op : plan->convs)
     if (op.trace) cudaFree(op.trace);
   for (EcamOp& e : plan->ecams) {
@@ -1342,7 +1365,7 @@ int stcd_plan_add_ecam_head(stcd_plan* plan, const stcd_ecam_desc* d) {
 int stcd_plan_finalize(stcd_plan* plan) {
   if (!plan) return fail(STCD_ERR_STATE, "plan is NULL");
   if (plan->finalized) return fail(STCD_ERR_STATE, "plan already finalized");
-  CUDA_TRY(cudaSetDevice(plan->device));
+  DeviceGuard dev_guard(plan->device);   // the caller's current device is restored on return
   // ---- activation workspace
   size_t off = 0;
   for (Tensor& t : plan->tensors) {
@@ -1744,7 +1767,7 @@ int stcd_plan_tensor_copy(stcd_plan* plan, int tensor_id, void* host, int64_t by
   if (!valid_tensor(plan, tensor_id) || !host) return fail(STCD_ERR_INVALID, "bad tensor id %d / NULL host buffer", tensor_id);
   const Tensor& t = plan->tensors[tensor_id];
   if (bytes != (int64_t)t.bytes) return fail(STCD_ERR_INVALID, "tensor %d has %zu bytes, got %lld", tensor_id, t.bytes, (long long)bytes);
-  CUDA_TRY(cudaSetDevice(plan->device));
+  DeviceGuard dev_guard(plan->device);   // the caller's current device is restored on return
   CUDA_TRY(cudaDeviceSynchronize());
   if (to_device)
     CUDA_TRY(cudaMemcpy(t.ptr, host, t.bytes, cudaMemcpyHostToDevice));
@@ -1790,7 +1813,7 @@ static int forward_any(stcd_plan* plan, const void* x1, const void* x2, int u8, 
   if (!x1 || !x2 || n_pairs < 0) return fail(STCD_ERR_INVALID, "bad inputs");
   if (plan->in_u8 != u8) return fail(STCD_ERR_INVALID, "plan takes %s inputs", plan->in_u8 ? "uint8 HWC (stcd_forward_u8)" : "fp32 NCHW (stcd_forward)");
   if (n_outs != plan->n_ext || (n_outs > 0 && !outs)) return fail(STCD_ERR_INVALID, "plan has %d external outputs, got %d", plan->n_ext, n_outs);
-  CUDA_TRY(cudaSetDevice(plan->device));
+  DeviceGuard dev_guard(plan->device);   // the caller's current device is restored on return
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t in_bytes = (size_t)plan->in_c * plan->in_h * plan->in_w * (u8 ? 1 : sizeof(float));
   std::vector<float*> o(n_outs);
@@ -1820,7 +1843,7 @@ int stcd_forward_profile(stcd_plan* plan, const float* x1, const float* x2, int 
   if (!x1 || !x2 || n_pairs < 0 || !op_ms) return fail(STCD_ERR_INVALID, "bad inputs");
   if (n_ops != (int)plan->ops.size()) return fail(STCD_ERR_INVALID, "plan has %zu ops, got %d", plan->ops.size(), n_ops);
   if (n_outs != plan->n_ext || (n_outs > 0 && !outs)) return fail(STCD_ERR_INVALID, "plan has %d external outputs, got %d", plan->n_ext, n_outs);
-  CUDA_TRY(cudaSetDevice(plan->device));
+  DeviceGuard dev_guard(plan->device);   // the caller's current device is restored on return
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t in_bytes = (size_t)plan->in_c * plan->in_h * plan->in_w * (plan->in_u8 ? 1 : sizeof(float));
   const uint8_t* b1 = reinterpret_cast<const uint8_t*>(x1);
@@ -1857,7 +1880,7 @@ static int forward_host_any(stcd_plan* plan, const void* x1v, const void* x2v, i
   const uint8_t* x1h = static_cast<const uint8_t*>(x1v);
   const uint8_t* x2h = static_cast<const uint8_t*>(x2v);
   if (n_outs != plan->n_ext || (n_outs > 0 && !outs_host)) return fail(STCD_ERR_INVALID, "plan has %d external outputs, got %d", plan->n_ext, n_outs);
-  CUDA_TRY(cudaSetDevice(plan->device));
+  DeviceGuard dev_guard(plan->device);   // the caller's current device is restored on return
   const size_t in_elems = (size_t)plan->in_c * plan->in_h * plan->in_w * (u8 ? 1 : sizeof(float));   // bytes per image
   const size_t in_bytes = in_elems * plan->chunk;
   if (!plan->s_copy) {
@@ -1928,6 +1951,7 @@ int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const v
     cudaGetLastError();
     return fail(STCD_ERR_NO_DEVICE, "no CUDA device visible: libstcd_b200 has no CPU fallback");
   }
+  DeviceGuard dev_guard(device_of(cm_dev));   // launch where the buffers live
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned long long* cm = reinterpret_cast<unsigned long long*>(cm_dev);
   const size_t ne = (size_t)n_img * pix;
@@ -1980,6 +2004,7 @@ int stcd_binarise_mask(const float* logits, int pred_kind, float thr, int64_t n_
     cudaGetLastError();
     return fail(STCD_ERR_NO_DEVICE, "no CUDA device visible: libstcd_b200 has no CPU fallback");
   }
+  DeviceGuard dev_guard(device_of(mask));   // launch where the buffers live
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t ne = (size_t)n_img * pix;
   const int blocks = (int)std::max<size_t>(1, std::min<size_t>((ne + 255) / 256, 148 * 16));
@@ -2005,6 +2030,7 @@ int stcd_knn_graph(const float* x, const float* y, const float* relpos, int B, i
     cudaGetLastError();
     return fail(STCD_ERR_NO_DEVICE, "no CUDA device visible: libstcd_b200 has no CPU fallback");
   }
+  DeviceGuard dev_guard(device_of(nn_idx));   // launch where the buffers live
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* xn = scratch;
   float* yn = y ? scratch + (size_t)B * C * N : scratch;
@@ -2028,6 +2054,7 @@ int stcd_max_relative(const float* x, const float* y, const int64_t* nn_idx, int
     cudaGetLastError();
     return fail(STCD_ERR_NO_DEVICE, "no CUDA device visible: libstcd_b200 has no CPU fallback");
   }
+  DeviceGuard dev_guard(device_of(out));   // launch where the buffers live
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t total = (size_t)B * C * N;
   stcd::max_relative_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(

@@ -2,8 +2,14 @@
 
 A wrapper keeps the reference module's parameter names (so a reference ``state_dict`` loads) and
 lowers itself to a libstcd_b200 plan per (device, H, W, chunk) on first use; anything that touches
-the weights (``load_state_dict``, ``.to``, ``.cuda``, re-initialisation through
-``networks.init_weights``) drops the packed copies.
+the weights drops the packed copies: ``load_state_dict`` / ``.to`` / ``.cuda`` / re-initialisation
+through ``networks.init_weights`` explicitly, and everything else (a child's ``load_state_dict``,
+``p.data.copy_``, an EMA update, fine-tuning the same parameters elsewhere) through a fingerprint of
+every parameter's and buffer's ``(data_ptr, _version)`` that is compared before each forward.
+
+Plans hold ctypes handles of device objects: they are never copied or pickled.  ``copy.deepcopy(net)``
+(train_stcd.py:81-87,326), ``torch.save(net)`` and ``pickle`` see a module without plans; the copy
+lowers itself again on its first forward.
 """
 from __future__ import annotations
 
@@ -22,19 +28,42 @@ class PlannedModule(nn.Module):
     def __init__(self):
         super().__init__()
         self._plans: Dict[tuple, object] = {}
+        self._fp_tensors = None      # parameters + buffers the cached plans were lowered from
+        self._fp = None              # their fingerprint at lowering time
         self.chunk_pairs = self.default_chunk_pairs
 
     # weights changed (load_state_dict / .to / re-init): packed copies are stale
     def _apply(self, fn, *a, **k):
-        self._plans = {}
+        self.invalidate_plans()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._plans = {}
+        self.invalidate_plans()
         return super().load_state_dict(*a, **k)
 
     def invalidate_plans(self) -> None:
         self._plans = {}
+        self._fp_tensors = None
+        self._fp = None
+
+    # plans own device objects through ctypes handles: a copy / pickle of the module starts without them
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_plans"] = {}
+        state["_fp_tensors"] = None
+        state["_fp"] = None
+        return state
+
+    def _weights_fingerprint(self):
+        """(data_ptr, _version) over every parameter and buffer: changes on any in-place write (``copy_``, optimiser
+        steps, a child's ``load_state_dict``) and on ``p.data = ...``.  The tensor list is cached with the plans."""
+        ts = self._fp_tensors
+        if ts is None:
+            ts = self._fp_tensors = [t for t in list(self.parameters()) + list(self.buffers()) if t is not None]
+        h = len(ts)
+        for t in ts:
+            h = (h * 1000003 + t._version * 31 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
+        return h
 
     def lower(self, h: int, w: int) -> L.Program:  # pragma: no cover - abstract
         raise NotImplementedError
@@ -66,6 +95,9 @@ class PlannedModule(nn.Module):
         chunk = max(1, min(int(self.chunk_pairs), int(x.shape[0])))
         h, w = (int(x.shape[1]), int(x.shape[2])) if u8_norm is not None else (int(x.shape[2]), int(x.shape[3]))
         key = (x.device.index, h, w, chunk, u8_norm)
+        if self._plans:
+            if self._weights_fingerprint() != self._fp:     # weights were written since the plans were lowered
+                self.invalidate_plans()
         plan = self._plans.get(key)
         if plan is None:
             prog = self.lower(h, w)
@@ -74,5 +106,7 @@ class PlannedModule(nn.Module):
                     if isinstance(op, L.InputPackSpec):
                         op.u8_norm = u8_norm
             plan = Plan(prog, chunk, device=key[0])
+            if not self._plans:
+                self._fp = self._weights_fingerprint()
             self._plans[key] = plan
         return plan

@@ -37,7 +37,9 @@ def _worker(rank, world, port, n_pairs, out_dir):
         cm = torch.zeros(4, dtype=torch.int64)
         if e > b:
             cm += torch.from_numpy(ometric.confusion_matrix(pred[b:e], label[b:e]).reshape(-1).astype(np.int64))
-        parallel.allreduce_confusion(cm)
+        total = parallel.allreduce_confusion(cm, pixels=(e - b) * pred[0].size)
+        assert int(total) == n_pairs * pred[0].size          # the pixel count rides in the same all-reduce
+        assert int(cm.sum()) == int(total)
         assert parallel.rank_world() == (rank, world)
         np.save(os.path.join(out_dir, f"cm{rank}.npy"), cm.numpy())
     finally:

@@ -104,3 +104,77 @@ def test_full_size_checksum_c3():
     assert np.array_equal(cm, ometric.confusion_matrix(ometric.binarise(logits.numpy(), "sigmoid"), label.numpy()))
     with pytest.raises(AssertionError):
         m.addBatch(torch.zeros(2, 3, dtype=torch.int32).cuda(), torch.zeros(3, 2, dtype=torch.int64).cuda())
+
+
+def test_out_of_range_classes_raise_like_the_reference_bincount():
+    """train_stcd.py:572-579: bincount(...).reshape(numClass, numClass) fails when a class index is outside [0, numClass);
+    the kernel skips such pixels, so every read of the matrix must raise instead of scoring a reduced pixel set."""
+    pred = torch.zeros(2, 1, 16, 16, dtype=torch.int32)
+    label = torch.zeros(2, 1, 16, 16, dtype=torch.int64)
+    label[0, 0, 3, 4] = 255                                       # a raw {0, 255} mask passed as class indices
+    with pytest.raises((RuntimeError, ValueError)):               # the reference itself
+        ometric.confusion_matrix(pred.numpy(), label.numpy())
+    m = SegmentationMetric(2)
+    m.addBatch(pred.cuda(), label.cuda())
+    with pytest.raises(ValueError, match="outside"):
+        m.confusionMatrix
+    with pytest.raises(ValueError):
+        m.F1score()
+    m.reset()
+    pred[1, 0, 0, 0] = 7                                          # an out-of-range prediction
+    label[0, 0, 3, 4] = 1
+    m.addBatch(pred.cuda(), label.cuda())
+    with pytest.raises(ValueError):
+        m.IntersectionOverUnion()
+    m.reset()
+    label[0, 0, 3, 4] = -1
+    m.addBatch(torch.zeros_like(pred).cuda(), label.cuda())
+    with pytest.raises(ValueError):
+        m.confusionMatrix
+    # the documented way to feed raw masks still works and counts every pixel
+    m.reset()
+    raw = torch.zeros(2, 16, 16, dtype=torch.uint8)
+    raw[0, 2, 2] = 255
+    m.addBatch(raw.cuda(), raw.cuda(), raw_masks=True)
+    assert m.confusionMatrix.sum() == raw.numel()
+
+
+def test_gen_confusion_matrix_is_side_effect_free():
+    g = torch.Generator().manual_seed(3)
+    pred = (torch.rand(2, 1, 20, 20, generator=g) < 0.4).int()
+    label = (torch.rand(2, 1, 20, 20, generator=g) < 0.3).long()
+    m = SegmentationMetric(2)
+    cm = m.genConfusionMatrix(pred.cuda(), label.cuda())
+    assert np.array_equal(cm.numpy(), ometric.confusion_matrix(pred.numpy(), label.numpy()))
+    assert int(m.confusion_counts().sum()) == 0
+
+
+def test_confuse_matrix_meter_matches_restatement():
+    """models/evaluator.py:99-122,150-167 (ConfuseMatrixMeter; parity unpinned: misc/metric_tool.py is absent upstream)."""
+    from stcd_b200.metric import ConfuseMatrixMeter
+    g = np.random.default_rng(9)
+    meter = ConfuseMatrixMeter(n_class=2)
+    tot_p, tot_l = [], []
+    for i in range(3):
+        pr = (g.random((2, 40, 56)) < 0.3).astype(np.int64)
+        gt = (g.random((2, 40, 56)) < 0.2).astype(np.int64)
+        if i == 1:
+            gt[0, :4] = 255                                       # ignore label: masked by upstream's helper
+        mf1 = meter.update_cm(pr=pr, gt=gt)                       # numpy in, as the reference calls it
+        want = ometric.confuse_matrix_meter_scores(pr, gt)
+        assert abs(mf1 - want["mf1"]) < 1e-12
+        tot_p.append(pr)
+        tot_l.append(gt)
+    got = meter.get_scores()
+    want = ometric.confuse_matrix_meter_scores(np.concatenate(tot_p), np.concatenate(tot_l))
+    assert set(got) == set(want) == {"acc", "miou", "mf1", "iou_0", "iou_1", "F1_0", "F1_1", "precision_0", "precision_1",
+                                     "recall_0", "recall_1"}
+    for k in want:
+        assert abs(got[k] - want[k]) < 1e-12, k
+    # device tensors in: same numbers, no host round trip for the inputs
+    meter.clear()
+    meter.update_cm(pr=torch.from_numpy(tot_p[0]).cuda(), gt=torch.from_numpy(tot_l[0]).cuda())
+    w0 = ometric.confuse_matrix_meter_scores(tot_p[0], tot_l[0])
+    assert abs(meter.get_scores()["miou"] - w0["miou"]) < 1e-12
+    with pytest.raises(ValueError):
+        meter.update_cm(pr=np.full((1, 4, 4), 3), gt=np.zeros((1, 4, 4), np.int64))

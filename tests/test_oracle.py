@@ -146,3 +146,20 @@ def test_binarise_semantics():
     assert ometric.binarise(x, "raw_ge", 0.5).ravel().tolist() == [0, 0, 0, 0, 1]
     two = np.stack([np.zeros((1, 1, 3)), np.array([[[0.0, 1.0, -1.0]]])], axis=1).astype(np.float32).reshape(1, 2, 1, 3)
     assert ometric.binarise(two, "argmax").ravel().tolist() == [0, 1, 0]     # ties -> class 0
+
+
+def test_cm2score_matches_independent_statement():
+    """ConfuseMatrixMeter's score dict (models/evaluator.py:150-167; misc/metric_tool.py absent upstream: parity unpinned)."""
+    import numpy as np
+    from oracle import metric as ometric
+    from stcd_b200.metric import cm2score
+    g = np.random.default_rng(4)
+    pr = (g.random((3, 32, 32)) < 0.4).astype(np.int64)
+    gt = (g.random((3, 32, 32)) < 0.25).astype(np.int64)
+    cm = ometric.confusion_matrix(pr, gt)
+    got, want = cm2score(cm), ometric.confuse_matrix_meter_scores(pr, gt)
+    assert set(got) == set(want)
+    for k in want:
+        assert abs(got[k] - want[k]) < 1e-12, k
+    absent = cm2score(np.array([[10.0, 0.0], [0.0, 0.0]]))      # class 1 absent: eps keeps every score finite (0, not NaN)
+    assert absent["F1_1"] == 0.0 and absent["iou_1"] == 0.0 and np.isfinite(absent["mf1"])

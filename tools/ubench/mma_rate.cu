@@ -34,11 +34,12 @@ __global__ void __launch_bounds__(128) k(int n_tile, int mode, int reps, int fen
     uint64_t ad, bd;
     if (mode == 0) { ad = desc_nosw(a, 2880, 160); bd = desc_nosw(b, n_tile * 16, 128); }
     else if (mode == 1) { ad = desc_nosw(a, 2048, 128); bd = desc_nosw(b, n_tile * 16, 128); }
+    else if (mode == 3) { ad = desc_nosw(a, 3072, 128); bd = desc_nosw(b, n_tile * 16, 128); }
     else { ad = make_kmajor_desc(a, 128, 1024); bd = make_kmajor_desc(b, 128, 1024); }
     long long t0 = clock64();
     for (int i = 0; i < reps; ++i) {
       if (fence_each) tc_fence_after();
-      umma_bf16(tb, ad + (mode == 0 ? (i % 9) : 0), bd, idesc, 1);
+      umma_bf16(tb, ad + (mode == 0 ? (i % 9) : (mode == 3 ? (i % 3) * 32 : 0)), bd, idesc, 1);
     }
     long long t1 = clock64();
     umma_commit(&bar);
@@ -55,9 +56,9 @@ int main() {
   long long* d; cudaMalloc(&d, 16);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int reps = 256;
-  for (int fence = 0; fence < 2; ++fence)
-    for (int mode = 0; mode < 3; ++mode)
-      for (int n : {16, 32, 64, 128, 256}) {
+  for (int fence = 0; fence < 1; ++fence)
+    for (int mode : {0, 1, 3, 2})
+      for (int n : {16, 32, 48, 64, 96, 128, 192, 256}) {
         for (int ctas : {1, 148}) {
           k<<<ctas, 128, 100 * 1024>>>(n, mode, reps, fence, d);
           cudaError_t e = cudaDeviceSynchronize();
