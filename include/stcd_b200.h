@@ -54,6 +54,8 @@ int stcd_device_count(void);
 /* The batch is processed in chunks of `chunk_pairs` image pairs so that inter-layer           */
 /* activations stay resident in the 126 MB L2.                                                 */
 
+/* device = -1 creates a VALIDATION plan: every stcd_plan_add_* call checks and records its descriptor exactly as on a
+ * device, stcd_plan_finalize returns STCD_ERR_NO_DEVICE (host-side tests of the lowering run without a GPU). */
 int stcd_plan_create(int device, int chunk_pairs, stcd_plan** out);
 void stcd_plan_destroy(stcd_plan* plan);
 

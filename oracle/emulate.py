@@ -58,7 +58,16 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
                     blk += 1
             assert blk == ph.w_block + ph.n_blocks
             if op.fold_cs:
-                full[m] = acc          # columns = (phase, channel): scattered to pixels by the store below
+                # columns = (folded phase, channel): affine (+ activation) per column, then column block p of GEMM phase
+                # (oy, ox) -> output pixel phase (oy + p // osx, ox + p % osx)
+                v = acc * scale + shift
+                v = torch.relu(v) if op.act_kind == 1 else (torch.nn.functional.gelu(v) if op.act_kind == 2 else
+                                                             (torch.where(v >= 0, v, v * op.act_alpha) if op.act_kind == 3 else v))
+                sl = slice(m * chunk, m * chunk + n_img)
+                for p_ in range(op.cout // op.fold_cs):
+                    q = _bf16(v[..., p_ * op.fold_cs: p_ * op.fold_cs + op.fold_cout])
+                    T[op.out0][sl, ph.oy + p_ // op.osx::op.osy, ph.ox + p_ % op.osx::op.osx,
+                               op.out0_coff: op.out0_coff + op.fold_cout] = q
             else:
                 full[m][:, ph.oy::op.osy, ph.ox::op.osx] = acc
     def act(v):
@@ -71,13 +80,6 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
         return v
 
     if op.fold_cs:
-        # phases folded into N: affine (+activation) per column, then column block p -> output pixel phase p
-        for m in range(n_m):
-            v = act(full[m] * scale + shift)
-            sl = slice(m * chunk, m * chunk + n_img)
-            for p_ in range(op.osy * op.osx):
-                q = _bf16(v[..., p_ * op.fold_cs: p_ * op.fold_cs + op.fold_cout])
-                T[op.out0][sl, p_ // op.osx::op.osy, p_ % op.osx::op.osx, op.out0_coff: op.out0_coff + op.fold_cout] = q
         return
     vs = []
     for m in range(n_m):

@@ -74,7 +74,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             nvcc = os.environ.get("NVCC", "nvcc")
             fd, tmp = tempfile.mkstemp(prefix=".libstcd_b200.", suffix=".so.tmp", dir=str(PKG_DIR))
             os.close(fd)
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, str(CSRC / "stcd_b200.cu")]
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["--threads", "0", "-o", tmp] + [str(f) for f in sorted(CSRC.glob("*.cu"))]
             try:
                 r = subprocess.run(cmd, capture_output=True, text=True)
                 if r.returncode != 0:

@@ -6,40 +6,9 @@
 #include <stdint.h>
 
 #include "../../include/stcd_b200.h"
+#include "ptx.cuh"
 
 namespace stcd {
-
-// nn.GELU() = 0.5 x (1 + erf(x / sqrt 2)) with erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 in exact arithmetic, 5e-7 measured
-// in fp32 with the fast exp / reciprocal): one MUFU.RCP, one MUFU.EX2 and 8 FMAs instead of erff's ~30 instructions and two
-// branches.  The GELU's absolute error stays below 2e-7, its relative error below 2e-4 -- 20x under the bf16 rounding that
-// follows every use.  It sits in conv epilogues where 4 warps finish 128 x 128 values per tile: with erff those layers ran
-// 6-8x above their HBM floor (ViG FFN fc1, Grapher nn, MiT dwconv).
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = x * 0.70710678118654752f, az = fabsf(z);
-  const float t = __fdividef(1.f, fmaf(0.3275911f, az, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.f - p * t * __expf(-az * az);      // erf(|z|)
-  return 0.5f * x * (1.f + copysignf(e, z));
-}
-
-// gelu_fast on a packed pair: the polynomial and the products run as FFMA2 / FMUL2, the reciprocal and exponential stay scalar
-__device__ __forceinline__ float2 gelu_fast2(float2 x) {
-  const float2 z = __fmul2_rn(x, make_float2(0.70710678118654752f, 0.70710678118654752f));
-  const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
-  const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), az, make_float2(1.f, 1.f));
-  const float2 t = make_float2(__fdividef(1.f, den.x), __fdividef(1.f, den.y));
-  float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
-  p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
-  p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
-  p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
-  const float2 nz2 = __fmul2_rn(make_float2(-az.x, -az.y), az);
-  const float2 pe = __fmul2_rn(__fmul2_rn(p, t), make_float2(__expf(nz2.x), __expf(nz2.y)));
-  const float2 e = make_float2(copysignf(1.f - pe.x, z.x), copysignf(1.f - pe.y, z.y));      // erf(z)
-  return __fmul2_rn(__fmul2_rn(x, make_float2(0.5f, 0.5f)), make_float2(1.f + e.x, 1.f + e.y));
-}
 
 // mma.sync m16n8k16 bf16 -> fp32 (the small tensor-core tiles of the attention and SegCD-head kernels)
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {

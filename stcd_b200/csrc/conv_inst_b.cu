@@ -1,0 +1,7 @@
+// conv_ws_kernel instances, part B (see STCD_CONV_INSTANCES_B in conv_ws.cuh): one of four translation units
+// compiled in parallel.
+#include "conv_ws.cuh"
+
+namespace stcd {
+STCD_DEFINE_CONV_TABLE(conv_kernel_table_b, STCD_CONV_INSTANCES_B)
+}  // namespace stcd

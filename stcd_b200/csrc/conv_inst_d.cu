@@ -1,0 +1,7 @@
+// conv_ws_kernel instances, part D (see STCD_CONV_INSTANCES_D in conv_ws.cuh): one of four translation units
+// compiled in parallel.
+#include "conv_ws.cuh"
+
+namespace stcd {
+STCD_DEFINE_CONV_TABLE(conv_kernel_table_d, STCD_CONV_INSTANCES_D)
+}  // namespace stcd

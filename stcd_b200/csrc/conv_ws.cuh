@@ -47,6 +47,7 @@ constexpr int kMaxChunks = 128;  // A-stage loads per phase
 constexpr int kMaxTaps = 320;    // weight blocks per phase
 constexpr int kConvThreads = 224;
 constexpr int kFastMma = 36;     // per-chunk MMA offsets kept in the constant bank (9 taps x 4 K steps)
+constexpr int kMaxRSlots = 4;    // residual tiles in flight (TMA -> shared-memory ring)
 
 // epilogue features; a kernel instance either fixes them at compile time or (E_GENERIC) reads
 // them from ConvParams at run time
@@ -60,6 +61,7 @@ enum : uint32_t {
   E_DIFF = 64u,   // out_diff <- |v(T1) - v(T2)|
   E_F32 = 128u,   // out_f32 (NCHW fp32, external) <- v
   E_ACTX = 256u,  // extended activation: GELU / PReLU and/or activation before the second affine (read at run time)
+  E_RSM = 512u,   // with E_RES: the residual tile arrives by TMA in a shared-memory ring (ConvParams::res_slots > 0)
   E_GENERIC = 1u << 31
 };
 
@@ -78,6 +80,7 @@ struct PhaseInfo {
 
 struct TmapPack {
   CUtensorMap src[kMaxSrc];
+  CUtensorMap res;   // residual tensor, box = one output tile x n_tile channels (E_RSM)
 };
 
 struct ConvParams {
@@ -106,11 +109,17 @@ struct ConvParams {
   float act_alpha;
   const __nv_bfloat16* res;
   int32_t res_c8;
+  // Residual ring (E_RSM).  Per-thread residual loads kept only ~2 KB per epilogue warp in flight: at DRAM latency that is
+  // 2.4 TB/s for the whole chip, and the short-K layers with a residual (conv*.conv2 of the nested blocks) ran at exactly
+  // that rate (262 us with the residual, 152 us without).  The A producer now fetches the residual tile of each pass with
+  // ONE TMA box per sub-tile, `res_slots` passes ahead; the epilogue reads it with conflict-free 16-byte LDS.
+  int32_t res_slots;                       // 0: per-thread global loads
+  uint32_t res_slot_bytes, res_sub_bytes;  // ring slot = MT sub-tiles of [n_tile/8][16][8][8] bf16
   __nv_bfloat16* out0;
   int32_t out0_c8, out0_coff;
   int32_t reverse;   // 1: walk the tiles last-to-first (consecutive layers alternate, so a layer starts on the lines its producer wrote last: L2 hits)
   int32_t out0_s2d;  // 1: out0 is stored space-to-depth ([ho/2][wo/2] pixels, 4*cout channels)
-  int32_t fold_cs, fold_cout;  // > 0: output phases folded into N (column p*fold_cs + c -> phase p, channel c)
+  int32_t fold_cs, fold_cout;  // > 0: output phases folded into N (column p*fold_cs + c -> phase (oy + p / osx, ox + p % osx), channel c)
   __nv_bfloat16* out_raw;
   int32_t out_raw_c8;
   __nv_bfloat16* out_pool;
@@ -184,6 +193,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
   __shared__ __align__(8) uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
   __shared__ __align__(8) uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t r_full[kMaxRSlots], r_empty[kMaxRSlots];
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) ChunkLoad s_cload[kMaxChunks];
   __shared__ __align__(8) ChunkMma s_cmma[kMaxChunks];
@@ -213,11 +223,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
   uint8_t* smem_w = smem + p.tab_bytes;
   const uint32_t w_region = (p.w_resident ? static_cast<uint32_t>(phase.n_blocks) : static_cast<uint32_t>(p.w_stages)) * p.wblk_bytes;
   uint8_t* smem_a = smem_w + ((w_region + 127u) & ~127u);
+  uint8_t* smem_r = smem_a + static_cast<size_t>(p.a_stages) * p.a_stage_bytes;   // residual ring (a_stage_bytes is a multiple of 128)
   const uint8_t* wsrc = p.wpack + (static_cast<size_t>(nt) * p.blocks_per_ntile + phase.w_block) * p.wblk_bytes;
   const int w_per = (phase.n_blocks + kMaxWStages - 1) / kMaxWStages;  // resident mode: blocks per barrier slot
 
   if (threadIdx.x == 32) {
     for (int i = 0; i < p.n_src; ++i) tma_prefetch_desc(&tm.src[i]);
+    if (p.res_slots) tma_prefetch_desc(&tm.res);
   }
   // ---- tile-invariant tables
   {
@@ -277,6 +289,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);
     }
+    for (int s = 0; s < kMaxRSlots; ++s) {
+      mbar_init(&r_full[s], 1);
+      mbar_init(&r_empty[s], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -298,6 +314,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     const bool leader = elect_one();
     int s = 0;
     uint32_t par = 1;  // parity to wait for on a_empty[s]: first pass through the ring never blocks
+    int rs = 0;
+    uint32_t rpar = 1;
+    const uint32_t res_tx = static_cast<uint32_t>(MT) * static_cast<uint32_t>(p.n_tile) * (kTileH * kTileW * 2u);
     pdl_wait();        // activations are written by the previous kernel(s)
     for (int t = 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
@@ -307,12 +326,24 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       const int tile_y = tile % p.tiles_y;
       const int img = tile / p.tiles_y;
       const int x0 = tile_x * kTileW, y0 = tile_y * kTileH;
+      if (p.res_slots) {
+        // the pass's residual tiles: one box {8 px x 8 ch, 16 rows, n_tile / 8 groups} per sub-tile
+        mbar_wait_relaxed(&r_empty[rs], rpar);
+        if (leader) {
+          mbar_expect_tx(&r_full[rs], res_tx);
+          uint8_t* dst = smem_r + static_cast<size_t>(rs) * p.res_slot_bytes;
+#pragma unroll
+          for (int m = 0; m < MT; ++m) tma_load_4d(dst + m * p.res_sub_bytes, &tm.res, &r_full[rs], x0 * 8, y0, n0 >> 3, img + p.m_off[m]);
+        }
+        if (++rs == p.res_slots) {
+          rs = 0;
+          rpar ^= 1;
+        }
+      }
       for (int c = 0; c < phase.chunk_count; ++c) {
         const ChunkLoad L = s_cload[c];
         mbar_wait_relaxed(&a_empty[s], par);
-        if (p.dbg & 8) {   // diagnostics: no activation loads
-          if (leader) mbar_arrive(&a_full[s]);
-        } else if (leader) {
+        if (leader) {
           mbar_expect_tx(&a_full[s], L.tx_bytes);
           if (t == 0 && c == 0) STCD_STAMP(8);
           uint8_t* dst = smem_a + s * p.a_stage_bytes;
@@ -508,7 +539,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     // ============================== epilogue (warps 3..6) ==============================
     const bool has_raw = STCD_HAS(E_RAW, p.out_raw != nullptr);
     const bool has_aff2 = STCD_HAS(E_AFF2, p.scale2 != nullptr);
-    const bool has_res = STCD_HAS(E_RES, p.res != nullptr) && !(p.dbg & 4);   // dbg bit2: no residual
+    const bool has_res = STCD_HAS(E_RES, p.res != nullptr);
+    const bool res_sm = has_res && STCD_HAS(E_RSM, p.res_slots > 0);   // residual tile in the shared-memory ring
+    const bool res_rg = has_res && !res_sm;                            // residual through per-thread global loads
     const bool has_relu = STCD_HAS(E_RELU, p.relu != 0);
     const bool has_out0 = STCD_HAS(E_OUT0, p.out0 != nullptr);
     const bool has_pool = STCD_HAS(E_POOL, p.out_pool != nullptr);
@@ -536,7 +569,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
 
     // the residual is prefetched ahead of the accumulator wait, so this role reads global memory
     // written by the previous kernel without going through the A producer's dependency wait
-    if (has_res) pdl_wait();
+    if (res_rg) pdl_wait();
     const int wq = warp & 3;  // TMEM lane quarter this warp may access
     const int ty = 4 * wq + (lane >> 3);
     const int tx = lane & 7;
@@ -574,7 +607,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
         }
       }
     };
-    if (has_res && my_tiles > 0) prefetch_unit(0, 0);
+    if (res_rg && my_tiles > 0) prefetch_unit(0, 0);
+    int ers = 0;
+    uint32_t erpar = 0;
     for (int t = 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
       if (p.reverse) tile = p.n_tiles - 1 - tile;
@@ -583,7 +618,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       const int tile_y = tile % p.tiles_y;
       const int img = tile / p.tiles_y;
       const int gy = tile_y * kTileH + ty, gx = tile_x * kTileW + tx;
-      const bool valid = (gy < p.hg) && (gx < p.wg) && !(p.dbg & 2);   // dbg bit1: no global stores / residual loads
+      const bool valid = (gy < p.hg) && (gx < p.wg);
       const int oy = gy * p.osy + phase.oy, ox = gx * p.osx + phase.ox;
       const uint32_t pix = static_cast<uint32_t>(oy) * p.wo + ox;
       const uint32_t pix_pool = static_cast<uint32_t>(oy >> 1) * (p.wo >> 1) + (ox >> 1);
@@ -594,7 +629,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       const uint32_t cg0 = p.out0_s2d ? static_cast<uint32_t>(((oy & 1) * 2 + (ox & 1)) * (p.cout >> 3)) : static_cast<uint32_t>(p.out0_coff >> 3);
       __nv_bfloat16* q_out0 = has_out0 ? p.out0 + ((static_cast<size_t>(cg0) + cg8) * hw0 + pix0) * 8 : nullptr;
       __nv_bfloat16* q_raw = has_raw ? p.out_raw + (static_cast<size_t>(cg8) * hw + pix) * 8 : nullptr;
-      const __nv_bfloat16* q_res = has_res ? p.res + (static_cast<size_t>(cg8) * hw + pix) * 8 : nullptr;
+      const __nv_bfloat16* q_res = res_rg ? p.res + (static_cast<size_t>(cg8) * hw + pix) * 8 : nullptr;
       __nv_bfloat16* q_pool = has_pool ? p.out_pool + (static_cast<size_t>(cg8) * hw_pool + pix_pool) * 8 : nullptr;
       __nv_bfloat16* q_diff = has_diff ? p.out_diff + (static_cast<size_t>(cg8) * hw + pix) * 8 : nullptr;
       const int acc = t & 1;
@@ -614,7 +649,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
                                                   : make_uint4(0u, 0u, 0u, 0u);
           }
         };
-        if (has_res) {
+        if (res_rg) {
 #pragma unroll
           for (int m = 0; m < MS; ++m) {
             r_cur[m][0] = r_pre[0][m][0];
@@ -631,6 +666,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             prefetch_unit(t + 1, 0);
         }
         if (mb == 0) {
+          if (res_sm) mbar_wait_relaxed(&r_full[ers], erpar);
           mbar_wait_relaxed(&acc_full[acc], (t >> 1) & 1);
           tc_fence_after();
           if (t == 0 && threadIdx.x == 96) STCD_STAMP(5);
@@ -641,7 +677,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
           const int ch = n0 + c0;
           if (ch >= p.cout) break;
           const bool two = (p.cout - ch) > 8;  // both 8-channel groups of this 16-column step are real
-          if (has_res && valid && c0 + 16 >= 16 * PF && c0 + 16 < p.n_tile && ch + 16 < p.cout) load_res(c0 + 16, r_nxt);
+          if (res_rg && valid && c0 + 16 >= 16 * PF && c0 + 16 < p.n_tile && ch + 16 < p.cout) load_res(c0 + 16, r_nxt);
           uint32_t raw[MS][16];
 #pragma unroll
           for (int m = 0; m < MS; ++m) tmem_ld16(tgrp + m * p.n_tile + c0, raw[m]);
@@ -669,6 +705,14 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[m][j] = fmaf(v[m][j], s_aff[2][c0 + j], s_aff[3][c0 + j]);
             }
+            if (res_sm) {
+              // tile in shared memory: [n_tile / 8][16 rows][8 px] x 16 B -- consecutive lanes, consecutive 16 B
+              const uint4* rt = reinterpret_cast<const uint4*>(smem_r + static_cast<size_t>(ers) * p.res_slot_bytes +
+                                                               static_cast<size_t>(mb + m) * p.res_sub_bytes) +
+                                (c0 >> 3) * (kTileH * kTileW) + ty * kTileW + tx;
+              r_cur[m][0] = rt[0];
+              r_cur[m][1] = rt[kTileH * kTileW];
+            }
             if (has_res && valid) {
               float rv[16];
               unpack8_bf16(r_cur[m][0], rv);
@@ -691,8 +735,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
                   // phases folded into N: this 16-column step belongs to phase fp, channels [chn, chn + 16)
                   const int fp = ch / p.fold_cs, chn = ch - fp * p.fold_cs;
                   if (chn < p.fold_cout) {
-                    const int fy = fp / p.osx;
-                    const uint32_t pixf = static_cast<uint32_t>(gy * p.osy + fy) * p.wo + (gx * p.osx + fp - fy * p.osx);
+                    const int fy = fp / p.osx;   // all phases folded: GEMM phase (0, 0); horizontal phases only: (oy, 0), fp < osx
+                    const uint32_t pixf = static_cast<uint32_t>(gy * p.osy + phase.oy + fy) * p.wo + (gx * p.osx + phase.ox + fp - fy * p.osx);
                     __nv_bfloat16* o = p.out0 + ((im[m] * p.out0_c8 + ((p.out0_coff + chn) >> 3)) * hw + pixf) * 8;
                     *reinterpret_cast<uint4*>(o) = lo;
                     if (p.fold_cout - chn > 8) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = hi;
@@ -723,7 +767,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             *reinterpret_cast<uint4*>(o) = pack8_bf16(d);
             if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(d + 8);
           }
-          if (has_res) {
+          if (res_rg) {
             const int nstep = (c0 >> 4) + 1;               // steps 1 .. PF-1 were prefetched with step 0
 #pragma unroll
             for (int m = 0; m < MS; ++m) {
@@ -743,6 +787,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (res_sm) {
+        if (lane == 0) mbar_arrive(&r_empty[ers]);
+        if (++ers == p.res_slots) {
+          ers = 0;
+          erpar ^= 1;
+        }
+      }
       if (threadIdx.x == 96) {
         if (t == 0) STCD_STAMP(6);
         if (t == my_tiles - 1) STCD_STAMP(10);
@@ -771,8 +822,9 @@ struct ConvKernelEntry {
 
 // Specialised instances for the (M tiles, pairing, epilogue) combinations the lowered nets use;
 // anything else runs the generic instance (same code, epilogue features read from ConvParams at
-// run time).  X(MT, MS, EPI)
-#define STCD_CONV_INSTANCES(X)                         \
+// run time).  The instances are compiled in four translation units (conv_inst_{a,b,c,d}.cu, built in
+// parallel); conv_kernel_table() in stcd_b200.cu concatenates their tables.  X(MT, MS, EPI)
+#define STCD_CONV_INSTANCES_A(X)                       \
   /* FC-Siam encoder (Siamese pairs) */                \
   X(2, 2, E_RELU | E_OUT0)                             \
   X(2, 2, E_RELU | E_POOL | E_DIFF)                    \
@@ -788,7 +840,12 @@ struct ConvKernelEntry {
   X(4, 1, E_RELU | E_OUT0)                             \
   X(1, 1, E_F32)                                       \
   X(2, 1, E_F32)                                       \
-  /* SNUNet nested blocks */                           \
+  X(2, 2, E_OUT0)                                      \
+  X(4, 2, E_OUT0)                                      \
+  X(4, 1, E_OUT0)
+
+#define STCD_CONV_INSTANCES_B(X)                       \
+  /* SNUNet nested blocks: conv1 (raw identity + BN/ReLU), conv2 (+ identity; residual from the smem ring or by loads) */ \
   X(2, 2, E_RAW | E_AFF2 | E_RELU | E_OUT0)            \
   X(4, 2, E_RAW | E_AFF2 | E_RELU | E_OUT0)            \
   X(1, 1, E_RAW | E_AFF2 | E_RELU | E_OUT0)            \
@@ -796,21 +853,35 @@ struct ConvKernelEntry {
   X(4, 1, E_RAW | E_AFF2 | E_RELU | E_OUT0)            \
   X(2, 2, E_RES | E_RELU | E_OUT0 | E_POOL)            \
   X(4, 2, E_RES | E_RELU | E_OUT0 | E_POOL)            \
+  X(2, 2, E_RES | E_RSM | E_RELU | E_OUT0 | E_POOL)    \
+  X(4, 2, E_RES | E_RSM | E_RELU | E_OUT0 | E_POOL)    \
   X(1, 1, E_RES | E_RELU | E_OUT0)                     \
   X(2, 1, E_RES | E_RELU | E_OUT0)                     \
   X(4, 1, E_RES | E_RELU | E_OUT0)                     \
-  /* SegCD: BasicBlock conv2 (+identity, ReLU) and the 1x1 downsample, Siamese pairs */ \
+  X(1, 1, E_RES | E_RSM | E_RELU | E_OUT0)             \
+  X(2, 1, E_RES | E_RSM | E_RELU | E_OUT0)             \
+  X(4, 1, E_RES | E_RSM | E_RELU | E_OUT0)
+
+#define STCD_CONV_INSTANCES_C(X)                       \
+  /* SegCD: BasicBlock conv2 (+identity, ReLU), Siamese pairs */ \
   X(2, 2, E_RES | E_RELU | E_OUT0)                     \
   X(4, 2, E_RES | E_RELU | E_OUT0)                     \
-  X(2, 2, E_OUT0)                                      \
-  X(4, 2, E_OUT0)                                      \
-  /* ChangeGNN / ChangeFormer: 1x1 conv + residual without activation; GELU convs; conv -> act -> BN (+ residual) decoders */ \
+  X(2, 2, E_RES | E_RSM | E_RELU | E_OUT0)             \
+  X(4, 2, E_RES | E_RSM | E_RELU | E_OUT0)             \
+  /* ChangeGNN / ChangeFormer: 1x1 conv + residual without activation */ \
   X(2, 2, E_RES | E_OUT0)                              \
   X(4, 2, E_RES | E_OUT0)                              \
   X(1, 1, E_RES | E_OUT0)                              \
   X(2, 1, E_RES | E_OUT0)                              \
   X(4, 1, E_RES | E_OUT0)                              \
-  X(4, 1, E_OUT0)                                      \
+  X(2, 2, E_RES | E_RSM | E_OUT0)                      \
+  X(4, 2, E_RES | E_RSM | E_OUT0)                      \
+  X(1, 1, E_RES | E_RSM | E_OUT0)                      \
+  X(2, 1, E_RES | E_RSM | E_OUT0)                      \
+  X(4, 1, E_RES | E_RSM | E_OUT0)
+
+#define STCD_CONV_INSTANCES_D(X)                       \
+  /* GELU convs; conv -> act -> BN (+ residual) decoders */ \
   X(2, 2, E_RELU | E_ACTX | E_OUT0)                    \
   X(4, 2, E_RELU | E_ACTX | E_OUT0)                    \
   X(1, 1, E_AFF2 | E_RELU | E_ACTX | E_OUT0)           \
@@ -818,21 +889,29 @@ struct ConvKernelEntry {
   X(4, 1, E_AFF2 | E_RELU | E_ACTX | E_OUT0)           \
   X(1, 1, E_AFF2 | E_RES | E_RELU | E_ACTX | E_OUT0)   \
   X(2, 1, E_AFF2 | E_RES | E_RELU | E_ACTX | E_OUT0)   \
-  X(4, 1, E_AFF2 | E_RES | E_RELU | E_ACTX | E_OUT0)
+  X(4, 1, E_AFF2 | E_RES | E_RELU | E_ACTX | E_OUT0)   \
+  X(1, 1, E_AFF2 | E_RES | E_RSM | E_RELU | E_ACTX | E_OUT0)   \
+  X(2, 1, E_AFF2 | E_RES | E_RSM | E_RELU | E_ACTX | E_OUT0)   \
+  X(4, 1, E_AFF2 | E_RES | E_RSM | E_RELU | E_ACTX | E_OUT0)   \
+  /* generic: epilogue features read from ConvParams at run time */ \
+  X(1, 1, E_GENERIC)                                   \
+  X(2, 1, E_GENERIC)                                   \
+  X(2, 2, E_GENERIC)                                   \
+  X(4, 1, E_GENERIC)                                   \
+  X(4, 2, E_GENERIC)
 
-inline const ConvKernelEntry* conv_kernel_table(int* n) {
-  static const ConvKernelEntry table[] = {
-#define STCD_X(MT_, MS_, EPI_) {MT_, MS_, (EPI_), conv_ws_kernel<MT_, MS_, (EPI_)>},
-      STCD_CONV_INSTANCES(STCD_X)
-#undef STCD_X
-      {1, 1, E_GENERIC, conv_ws_kernel<1, 1, E_GENERIC>},
-      {2, 1, E_GENERIC, conv_ws_kernel<2, 1, E_GENERIC>},
-      {2, 2, E_GENERIC, conv_ws_kernel<2, 2, E_GENERIC>},
-      {4, 1, E_GENERIC, conv_ws_kernel<4, 1, E_GENERIC>},
-      {4, 2, E_GENERIC, conv_ws_kernel<4, 2, E_GENERIC>},
-  };
-  *n = static_cast<int>(sizeof(table) / sizeof(table[0]));
-  return table;
-}
+// one table per translation unit
+const ConvKernelEntry* conv_kernel_table_a(int* n);
+const ConvKernelEntry* conv_kernel_table_b(int* n);
+const ConvKernelEntry* conv_kernel_table_c(int* n);
+const ConvKernelEntry* conv_kernel_table_d(int* n);
+
+#define STCD_DEFINE_CONV_TABLE(NAME, LIST)                                                   \
+  const ConvKernelEntry* NAME(int* n) {                                                      \
+    static const ConvKernelEntry table[] = {LIST(STCD_CONV_TABLE_ENTRY)};                    \
+    *n = static_cast<int>(sizeof(table) / sizeof(table[0]));                                 \
+    return table;                                                                            \
+  }
+#define STCD_CONV_TABLE_ENTRY(MT_, MS_, EPI_) {MT_, MS_, (EPI_), conv_ws_kernel<MT_, MS_, (EPI_)>},
 
 }  // namespace stcd

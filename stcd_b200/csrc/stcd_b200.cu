@@ -256,7 +256,24 @@ struct stcd_plan {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   float* stage_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   std::vector<float*> stage_out[2];
+  // CUDA graphs of one chunk's launch list, keyed by the caller's pointers (STCD_GRAPH=0 disables).  A small net at a small
+  // batch is launch-bound (SiamUnet_diff, 8 pairs: 25 launches of 12-30 us of device time each): replaying a captured graph
+  // removes the per-launch host cost and keeps the programmatic-dependent-launch edges between the kernels.
+  struct GraphEntry {
+    const void* x1 = nullptr;
+    const void* x2 = nullptr;
+    int n_valid = 0;
+    std::vector<float*> outs;
+    cudaGraphExec_t exec = nullptr;
+    int seen = 0;               // a key is captured the second time it shows up (pointers that never repeat stay on plain launches)
+    uint64_t last_use = 0;
+  };
+  std::vector<GraphEntry> graph_cache;
+  uint64_t graph_clock = 0;
+  int graph_mode = 1;           // 0: off; set to 0 for good when a capture or instantiation fails
+  cudaStream_t s_capture = nullptr;
 };
+constexpr size_t kGraphCacheSize = 16;
 
 namespace {
 
@@ -670,8 +687,10 @@ int stcd_plan_create(int device, int chunk_pairs, stcd_plan** out) {
   if (!out) return fail(STCD_ERR_INVALID, "out is NULL");
   *out = nullptr;
   if (chunk_pairs < 1 || chunk_pairs > 4096) return fail(STCD_ERR_INVALID, "chunk_pairs %d out of range", chunk_pairs);
-  int r = check_sm100(device);
-  if (r) return r;
+  if (device != -1) {          // device -1: a validation plan (descriptors are checked and recorded, finalize refuses)
+    int r = check_sm100(device);
+    if (r) return r;
+  }
   stcd_plan* p = new stcd_plan();
   p->device = device;
   p->chunk = chunk_pairs;
@@ -682,6 +701,9 @@ int stcd_plan_create(int device, int chunk_pairs, stcd_plan** out) {
 void stcd_plan_destroy(stcd_plan* plan) {
   if (!plan) return;
   DeviceGuard dev_guard(plan->device);
+  for (auto& g : plan->graph_cache)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (plan->s_capture) cudaStreamDestroy(plan->s_capture);
   for (ConvOp& op : plan->convs)
     if (op.trace) cudaFree(op.trace);
   for (EcamOp& e : plan->ecams) {
@@ -1229,10 +1251,14 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
   const int ho = d->hg * d->osy, wo = d->wg * d->osx;
   const int out_imgs = (d->pair ? 2 : d->img_mult);
   if (d->fold_cs) {
+    // all osy*osx phases in one GEMM phase, or the osx horizontal phases in each of osy GEMM phases (oy = 0 .. osy-1, ox = 0)
     const int P = d->osy * d->osx;
-    if (P < 2 || d->n_phase != 1 || d->fold_cs % 16 || d->cout != P * d->fold_cs || d->fold_cout < 8 || d->fold_cout > d->fold_cs ||
-        (d->fold_cout % 8))
-      return -fail(STCD_ERR_INVALID, "phase folding: need one phase entry, cout == osy*osx*fold_cs, fold_cs %% 16 == 0, fold_cout %% 8 == 0 "
+    const bool all_folded = d->n_phase == 1 && d->cout == P * d->fold_cs;
+    bool x_folded = d->osx > 1 && d->n_phase == d->osy && d->cout == d->osx * d->fold_cs;
+    for (int ph = 0; ph < d->n_phase && x_folded; ++ph) x_folded = (d->phase[ph].ox == 0 && d->phase[ph].oy >= 0 && d->phase[ph].oy < d->osy);
+    if (P < 2 || !(all_folded || x_folded) || d->fold_cs % 16 || d->fold_cout < 8 || d->fold_cout > d->fold_cs || (d->fold_cout % 8))
+      return -fail(STCD_ERR_INVALID, "phase folding: need one GEMM phase with cout == osy*osx*fold_cs, or osy GEMM phases (ox = 0) with "
+                   "cout == osx*fold_cs; fold_cs %% 16 == 0, fold_cout %% 8 == 0 "
                    "(got osy=%d osx=%d n_phase=%d cout=%d fold_cs=%d fold_cout=%d)", d->osy, d->osx, d->n_phase, d->cout, d->fold_cs, d->fold_cout);
     if (d->out0 < 0 || d->out0_s2d || d->out_raw >= 0 || d->res >= 0 || d->out_pool >= 0 || d->out_diff >= 0 || d->out_ext >= 0 || d->scale2)
       return -fail(STCD_ERR_INVALID, "phase folding supports the affine + ReLU + out0 epilogue only");
@@ -1363,6 +1389,8 @@ int stcd_plan_add_ecam_head(stcd_plan* plan, const stcd_ecam_desc* d) {
 }
 
 int stcd_plan_finalize(stcd_plan* plan) {
+  if (plan && plan->device < 0)
+    return fail(STCD_ERR_NO_DEVICE, "validation plan (device -1): descriptors were checked, nothing can run -- libstcd_b200 has no CPU fallback");
   if (!plan) return fail(STCD_ERR_STATE, "plan is NULL");
   if (plan->finalized) return fail(STCD_ERR_STATE, "plan already finalized");
   DeviceGuard dev_guard(plan->device);   // the caller's current device is restored on return
@@ -1409,7 +1437,17 @@ int stcd_plan_finalize(stcd_plan* plan) {
   static_assert(sizeof(stcd_tap) == sizeof(stcd::Tap), "tap layout");
   const size_t kSmemMax = 227 * 1024 - 12 * 1024;  // dynamic budget: static tables + barriers live beside it
   int n_kernels = 0;
-  const stcd::ConvKernelEntry* kernels = stcd::conv_kernel_table(&n_kernels);
+  static std::vector<stcd::ConvKernelEntry> all_kernels;     // the four translation units' tables, concatenated once
+  if (all_kernels.empty()) {
+    using TableFn = const stcd::ConvKernelEntry* (*)(int*);
+    for (TableFn fn : {stcd::conv_kernel_table_a, stcd::conv_kernel_table_b, stcd::conv_kernel_table_c, stcd::conv_kernel_table_d}) {
+      int n = 0;
+      const stcd::ConvKernelEntry* t = fn(&n);
+      all_kernels.insert(all_kernels.end(), t, t + n);
+    }
+  }
+  n_kernels = (int)all_kernels.size();
+  const stcd::ConvKernelEntry* kernels = all_kernels.data();
   for (int i = 0; i < n_kernels; ++i)
   {
     CUDA_TRY(cudaFuncSetAttribute(kernels[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
@@ -1433,6 +1471,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
     return std::min(kSmemMax, share > fixed ? share - fixed : 0);
   };
   plan->pdl = env_int("STCD_PDL", 1);
+  plan->graph_mode = env_int("STCD_GRAPH", 1);
   const int force_generic = env_int("STCD_FORCE_GENERIC", 0);
   int n_sm = 148;
   CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, plan->device));
@@ -1598,7 +1637,31 @@ int stcd_plan_finalize(stcd_plan* plan) {
     }
     if (!occ) return fail(STCD_ERR_INVALID, "conv op: no shared-memory plan (forced occupancy %d)", force_occ);
     const size_t w_region = round_up(p.w_resident ? w_all : (size_t)p.w_stages * p.wblk_bytes, 128);
-    op.smem = p.tab_bytes + w_region + (size_t)p.a_stages * p.a_stage_bytes + 128;
+    // ---- residual ring: the pass's residual tiles arrive by TMA, up to kMaxRSlots passes ahead, when the ring fits beside
+    // >= 2 (3 when there is room) A stages; else the epilogue loads the residual itself
+    p.res_slots = 0;
+    if (d.res >= 0 && d.n_phase == 1 && d.osy == 1 && d.osx == 1 && env_int("STCD_RES_SMEM", 1)) {
+      const Tensor& tr = plan->tensors[d.res];
+      const size_t sub = (size_t)d.n_tile * stcd::kTileH * stcd::kTileW * 2;       // [n_tile / 8][16][8][8] bf16
+      const size_t slot = sub * p.mt;
+      const size_t fixed = 256 + p.tab_bytes + w_region;
+      const size_t budget = cta_budget(occ);
+      if (tr.h == p.ho && tr.w == p.wo) {
+        for (int r = stcd::kMaxRSlots; r >= 2 && !p.res_slots; --r) {
+          const int a_min = std::min(p.a_stages, r >= 3 ? 3 : 2);
+          if (fixed + (size_t)a_min * p.a_stage_bytes + r * slot > budget) continue;
+          p.res_slots = r;
+          p.res_slot_bytes = (uint32_t)slot;
+          p.res_sub_bytes = (uint32_t)sub;
+          p.a_stages = (int)std::min<size_t>(p.a_stages, (budget - fixed - r * slot) / p.a_stage_bytes);
+        }
+      }
+      if (p.res_slots) {
+        int r = encode_act_map(&op.tm.res, tr.ptr, tr.mult * plan->chunk, tr.h, tr.w, tr.c, d.n_tile, 1, 1, 0, 0);
+        if (r) return r;
+      }
+    }
+    op.smem = p.tab_bytes + w_region + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.res_slots * p.res_slot_bytes + 128;
     if (op.smem > kSmemMax) return fail(STCD_ERR_INVALID, "conv op needs %zu B of shared memory", op.smem);
     const int ctas = std::max(1, (n_sm * occ) / groups);
     op.grid = dim3((unsigned)std::min(p.n_tiles, ctas), (unsigned)p.n_ntiles, (unsigned)d.n_phase);
@@ -1624,7 +1687,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
     op.epi = (d.out_raw >= 0 ? stcd::E_RAW : 0u) | (!op.scale2.empty() ? stcd::E_AFF2 : 0u) | (d.res >= 0 ? stcd::E_RES : 0u) |
              (d.relu ? stcd::E_RELU : 0u) | (d.out0 >= 0 ? stcd::E_OUT0 : 0u) | (d.out_pool >= 0 ? stcd::E_POOL : 0u) |
              (d.out_diff >= 0 ? stcd::E_DIFF : 0u) | (d.out_ext >= 0 ? stcd::E_F32 : 0u) |
-             ((d.relu >= 2 || d.act_pre) ? stcd::E_ACTX : 0u);
+             ((d.relu >= 2 || d.act_pre) ? stcd::E_ACTX : 0u) | (p.res_slots ? stcd::E_RSM : 0u);
     op.fn = nullptr;
     for (int i = 0; i < n_kernels && !force_generic; ++i)
       if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == op.epi) op.fn = kernels[i].fn;
@@ -1807,6 +1870,77 @@ int64_t stcd_plan_launches(const stcd_plan* plan, int n_pairs) {
   return chunks * per_chunk;
 }
 
+// One chunk through a cached CUDA graph when this exact (inputs, outputs, n_valid) has been seen before, else plain launches.
+static int run_chunk_graphed(stcd_plan* plan, const void* x1, const void* x2, int nv, float* const* outs, int n_outs, cudaStream_t st) {
+  if (!plan->graph_mode) return run_chunk(plan, x1, x2, nv, outs, st);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();                       // the caller is capturing its own graph: just record the launches into it
+    return run_chunk(plan, x1, x2, nv, outs, st);
+  }
+  stcd_plan::GraphEntry* e = nullptr;
+  for (auto& g : plan->graph_cache) {
+    if (g.x1 != x1 || g.x2 != x2 || g.n_valid != nv || (int)g.outs.size() != n_outs) continue;
+    bool same = true;
+    for (int k = 0; k < n_outs && same; ++k) same = (g.outs[k] == outs[k]);
+    if (same) {
+      e = &g;
+      break;
+    }
+  }
+  const uint64_t now = ++plan->graph_clock;
+  if (e && e->exec) {
+    e->last_use = now;
+    CUDA_TRY(cudaGraphLaunch(e->exec, st));
+    return STCD_OK;
+  }
+  if (!e) {                                   // first sighting: remember the key (evict the least recently used), launch plainly
+    if (plan->graph_cache.size() >= kGraphCacheSize) {
+      size_t lru = 0;
+      for (size_t i = 1; i < plan->graph_cache.size(); ++i)
+        if (plan->graph_cache[i].last_use < plan->graph_cache[lru].last_use) lru = i;
+      if (plan->graph_cache[lru].exec) cudaGraphExecDestroy(plan->graph_cache[lru].exec);
+      plan->graph_cache.erase(plan->graph_cache.begin() + lru);
+    }
+    stcd_plan::GraphEntry g;
+    g.x1 = x1;
+    g.x2 = x2;
+    g.n_valid = nv;
+    g.outs.assign(outs, outs + n_outs);
+    g.seen = 1;
+    g.last_use = now;
+    plan->graph_cache.push_back(g);
+    return run_chunk(plan, x1, x2, nv, outs, st);
+  }
+  // second sighting: capture the launch list on the plan's own stream, instantiate, replay on the caller's stream
+  e->last_use = now;
+  e->seen++;
+  if (!plan->s_capture && cudaStreamCreateWithFlags(&plan->s_capture, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    plan->graph_mode = 0;
+    return run_chunk(plan, x1, x2, nv, outs, st);
+  }
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  bool ok = cudaStreamBeginCapture(plan->s_capture, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+  if (ok) {
+    const int r = run_chunk(plan, x1, x2, nv, outs, plan->s_capture);
+    const cudaError_t ce = cudaStreamEndCapture(plan->s_capture, &graph);
+    ok = (r == STCD_OK) && ce == cudaSuccess && graph != nullptr;
+  }
+  if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) {                                  // never again for this plan; plain launches are always correct
+    cudaGetLastError();
+    if (exec) cudaGraphExecDestroy(exec);
+    plan->graph_mode = 0;
+    return run_chunk(plan, x1, x2, nv, outs, st);
+  }
+  e->exec = exec;
+  CUDA_TRY(cudaGraphLaunch(exec, st));
+  return STCD_OK;
+}
+
 static int forward_any(stcd_plan* plan, const void* x1, const void* x2, int u8, int n_pairs, float* const* outs, int n_outs,
                        void* stream) {
   if (!plan || !plan->finalized) return fail(STCD_ERR_STATE, "plan not finalized");
@@ -1820,8 +1954,8 @@ static int forward_any(stcd_plan* plan, const void* x1, const void* x2, int u8, 
   for (int start = 0; start < n_pairs; start += plan->chunk) {
     const int nv = std::min(plan->chunk, n_pairs - start);
     for (int k = 0; k < n_outs; ++k) o[k] = outs[k] ? outs[k] + (size_t)start * plan->ext_elems[k] : nullptr;
-    int r = run_chunk(plan, static_cast<const uint8_t*>(x1) + (size_t)start * in_bytes,
-                      static_cast<const uint8_t*>(x2) + (size_t)start * in_bytes, nv, o.data(), st);
+    int r = run_chunk_graphed(plan, static_cast<const uint8_t*>(x1) + (size_t)start * in_bytes,
+                              static_cast<const uint8_t*>(x2) + (size_t)start * in_bytes, nv, o.data(), n_outs, st);
     if (r) return r;
   }
   return STCD_OK;

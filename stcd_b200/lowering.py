@@ -105,8 +105,9 @@ class ConvSpec:
     macs_per_pair: int = 0       # reference-equivalent MACs (for the roofline), per image pair
     out0_s2d: bool = False       # out0 is stored space-to-depth: pixel (y, x), channel c ->
     #                              pixel (y//2, x//2), channel ((y%2)*2 + x%2) * cout + c
-    fold_cs: int = 0             # > 0: the osy*osx output phases are folded into GEMM N: column p*fold_cs + c is
-    fold_cout: int = 0           # channel c (< fold_cout) of output pixel (i*osy + p//osx, j*osx + p%osx)
+    fold_cs: int = 0             # > 0: output phases are folded into GEMM N: column p*fold_cs + c of GEMM phase (oy, ox) is
+    fold_cout: int = 0           # channel c (< fold_cout) of output pixel (i*osy + oy + p//osx, j*osx + ox + p%osx);
+    #                              all osy*osx phases in ONE GEMM phase (oy = ox = 0), or the osx horizontal ones per row parity
     # activation: 0 none, 1 ReLU, 2 GELU (erf), 3 PReLU with one slope `act_alpha`.  act_pre: the activation sits
     # BEFORE the second affine (conv -> PReLU -> BN, ChangeFormer.py:1138-1148) instead of at the end of the epilogue
     act_kind: int = 0
@@ -716,6 +717,9 @@ def up2_conv_taps(weight: torch.Tensor, pad: int, a: int, b: int) -> List[Tuple[
     return [(dy, dx, w) for (dy, dx), w in sorted(merged.items())]
 
 
+FOLD_X_MAX_N = int(os.environ.get("STCD_FOLD_X_MAX_N", "128"))   # widest GEMM N of a horizontally folded up-sampling op
+
+
 def mma_cycles(n: int) -> int:
     """Measured cost of one SS-mode tcgen05.mma M=128 K=16 on B200 (tools/ubench/mma_rate.cu): for N <= 64 the
     4 KB A-operand read from shared memory, not the math, sets the pace."""
@@ -736,6 +740,32 @@ def _split_taps(name: str, segs: Sequence[Segment], taps) -> List[list]:
         if ci != w.shape[1]:
             raise ValueError(f"{name}: weight has {w.shape[1]} input channels, segments give {ci}")
     return out
+
+
+def fold_phases_x(name: str, segs: Sequence[Segment], phase_taps, cout: int, osy: int, osx: int):
+    """Fold only the osx HORIZONTAL output phases into GEMM N (one GEMM phase per output row parity).
+
+    Column block px of row-parity phase oy owns output pixel (i*osy + oy, j*osx + px): a thread then holds the
+    horizontally adjacent output pixels of its input pixel, and both halves of every 32-byte sector leave the SM
+    together.  Per-phase launches wrote each sector half from different CTAs far apart in time: the up-sampling
+    ops of SNUNet ran at 3 TB/s of store traffic (Up1_x: 263 us with the stores, 85 us without).
+    Returns ([(oy, 0, SegTaps)] per row parity, cs)."""
+    cs = (cout + 15) // 16 * 16
+    per_phase = {(oy, ox): _split_taps(name, segs, taps) for (oy, ox, taps) in phase_taps}
+    if sorted(per_phase) != [(a, b) for a in range(osy) for b in range(osx)]:
+        raise ValueError(f"{name}: folding needs exactly one tap list per output phase")
+    out = []
+    for oy in range(osy):
+        folded = SegTaps([[] for _ in segs])
+        for si, s in enumerate(segs):
+            merged: Dict[Tuple[int, int], torch.Tensor] = {}
+            for ox in range(osx):
+                for (dy, dx, w) in per_phase[(oy, ox)][si]:
+                    blk = merged.setdefault((dy, dx), torch.zeros(osx * cs, s.c_real, dtype=torch.float32))
+                    blk[ox * cs: ox * cs + cout] += w
+            folded[si] = [(dy, dx, w) for (dy, dx), w in sorted(merged.items())]
+        out.append((oy, 0, folded))
+    return out, cs
 
 
 def fold_phases(name: str, segs: Sequence[Segment], phase_taps, cout: int, osy: int, osx: int, pair: bool):
@@ -826,6 +856,16 @@ def add_conv(
                 sc[p_ * cs: p_ * cs + cout] = scale[:cout]
                 sh[p_ * cs: p_ * cs + cout] = shift[:cout]
             phase_taps, cout, scale, shift = f_taps, P * cs, sc, sh
+        elif osx > 1 and osx * cs <= FOLD_X_MAX_N:
+            # not one tile: fold the horizontal phases only (stores of adjacent output pixels leave together)
+            f_taps, cs = fold_phases_x(name, segs, phase_taps, cout, osy, osx)
+            fold_cs, fold_cout = cs, cout
+            sc = np.ones(osx * cs, np.float32)
+            sh = np.zeros(osx * cs, np.float32)
+            for p_ in range(osx):
+                sc[p_ * cs: p_ * cs + cout] = scale[:cout]
+                sh[p_ * cs: p_ * cs + cout] = shift[:cout]
+            phase_taps, cout, scale, shift = f_taps, osx * cs, sc, sh
     elif fold:
         raise ValueError(f"{name}: phase folding needs an up-sampling op whose only output is out0")
     wbits, kc, n_tile, cout_pad, phases, chunks, taps, srcs, sy, sx, ey, ex = _taps_to_gemm(

@@ -28,6 +28,8 @@ def _fptr(a: Optional[np.ndarray]):
 
 class Plan:
     def __init__(self, prog: Program, chunk_pairs: int, device: int = 0):
+        """device = -1: a validation plan -- every op descriptor goes through the library's checks (as on a GPU box), nothing
+        is finalized and nothing can run (the host-side tests use it without a GPU)."""
         self.lib = _lib.lib()
         self.prog = prog
         self.chunk = int(chunk_pairs)
@@ -136,6 +138,8 @@ class Plan:
                 self._add_ecam(op)
             else:
                 raise TypeError(f"unknown op {op!r}")
+        if self.device < 0:
+            return
         _lib.check(lib.stcd_plan_finalize(h), "stcd_plan_finalize")
         for name, val in prog.consts.items():          # constant tensors: the same [h, w, c] block for every image
             t = prog.tensors[name]

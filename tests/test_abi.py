@@ -57,3 +57,29 @@ def test_argument_validation_without_gpu():
     assert lib.stcd_confusion_add_batch(buf, 9, 0.0, buf, 1, 1, 16, 2, cm, None, None) == 1
     assert lib.stcd_confusion_add_batch(buf, 0, 0.0, buf, 1, 1, 16, 3, cm, None, None) == 1
     assert lib.stcd_forward(None, None, None, 1, None, 0, None) == 4      # STCD_ERR_STATE
+
+
+# every registry family at a small legal size: the library's own descriptor checks run on the lowered programs without a
+# GPU (a validation plan, device -1), so a lowering change that the C side rejects fails HERE, not on the GPU box
+_VALIDATE = [
+    ("SiamUnet_diff", (3, 2), 64, 64), ("SiamUnet_conc", (3, 2), 64, 64), ("SiamUnet_sub", (3, 2), 32, 48),
+    ("SiamUnet_cross_conc", (3, 2), 48, 32), ("Unet", (3, 2), 32, 32), ("SNUNet_ECAM", (3, 2), 64, 96),
+    ("SegCD", ("resnet34",), 64, 96), ("CDNet_model", (3,), 64, 96), ("DSIFN", (), 64, 96),
+    ("ChangeFormerV6", (3, 2, False, 256), 256, 256), ("ChangeGNNV1", (3, 2, False, 256), 256, 256),
+    ("SiamUnet_diff", (3, 2), 256, 256), ("SNUNet_ECAM", (3, 2), 256, 256),
+]
+
+
+@pytest.mark.parametrize("name,args,h,w", _VALIDATE, ids=[f"{n}-{h}x{w}" for n, _, h, w in _VALIDATE])
+def test_lowered_programs_pass_the_library_checks(name, args, h, w):
+    from stcd_b200.networks import CLASSES
+    from stcd_b200.plan import Plan
+    net = CLASSES[name](*args).eval()
+    prog = net.lower(h, w)
+    for chunk in (1, 4):
+        plan = Plan(prog, chunk, device=-1)
+        assert plan.launches(chunk) == 0 or plan.launches(chunk) > 0      # recorded, never finalized
+        lib = _lib.lib()
+        assert lib.stcd_plan_finalize(plan._h) == 3                        # STCD_ERR_NO_DEVICE: nothing can run
+        assert b"no CPU fallback" in lib.stcd_last_error()
+        plan.close()

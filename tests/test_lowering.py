@@ -77,9 +77,11 @@ def test_segcd_program_matches_oracle():
     # 1 stem + 16 blocks x 2 + 3 downsamples + 5 decoder blocks x 2 = 46 convs; + pack, max-pool, head
     assert len(convs) == 46 and len(prog.ops) == 49
     dec1 = [o for o in convs if o.name.startswith("decoder") and o.name.endswith("conv1")]
-    # nearest-x2 + conv as 4 output phases; the narrow ones (Cout 32, 16) fold their phases into GEMM N
-    assert all((len(o.phases) == 4 and not o.fold_cs) or (len(o.phases) == 1 and o.fold_cs) for o in dec1)
-    assert [o.fold_cs for o in dec1] == [0, 0, 0, 32, 16] and [o.n_tile for o in dec1][3:] == [128, 64]
+    # nearest-x2 + conv as 4 output phases; the narrow ones (Cout 32, 16) fold all phases into GEMM N, Cout 64 folds the
+    # two horizontal phases of each output-row parity (2 GEMM phases, N = 128: adjacent output pixels leave together)
+    assert all((len(o.phases) == 4 and not o.fold_cs) or (len(o.phases) in (1, 2) and o.fold_cs) for o in dec1)
+    assert [o.fold_cs for o in dec1] == [0, 0, 64, 32, 16] and [o.n_tile for o in dec1][2:] == [128, 128, 64]
+    assert [len(o.phases) for o in dec1] == [4, 4, 2, 1, 1]
     big = net.lower(1024, 1024)
     # 500.397 GFLOP per pair at 1024x1024 (encoder 153.1 + decoder 96.6 + head 0.45 GMAC)
     assert abs(2 * big.macs_per_pair() / 1e9 - 500.397) < 0.5
@@ -394,7 +396,8 @@ def test_program_structure_and_macs():
     assert abs(prog.macs_per_pair() / 1e9 - 4.228) < 0.001
     up = [o for o in convs if o.name.startswith("upconv")]
     assert all((len(o.phases) == 4 or o.fold_cs) and o.osy == 2 and o.osx == 2 for o in up)
-    assert [o.fold_cs for o in up] == [0, 0, 32, 16]      # upconv2 / upconv1: phases folded into N (4*C <= 128)
+    # upconv2 / upconv1: all phases folded into N (4*C <= 128); upconv3: the horizontal phases per output-row parity (2*C = 128)
+    assert [o.fold_cs for o in up] == [0, 64, 32, 16] and [len(o.phases) for o in up] == [4, 2, 1, 1]
     taps = sorted(ph.n_blocks * o.kc // 128 for o in up[:1] for ph in o.phases)
     assert taps == [1, 2, 2, 4]          # stride-2 ConvTranspose2d(k3): taps per output phase
     assert abs(siamunet.SiamUnet_conc(3, 2).eval().lower(256, 256).macs_per_pair() / 1e9 - 4.832) < 0.001
