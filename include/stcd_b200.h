@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 16
+#define STCD_ABI_VERSION 17
 
 enum stcd_status {
   STCD_OK = 0,
@@ -151,12 +151,22 @@ typedef struct stcd_conv_desc {
    * has ONE phase entry, cout = osy*osx*fold_cs columns, and column p*fold_cs + c (c < fold_cout) is channel c of
    * output pixel (i*osy + p/osx, j*osx + p%osx): the A operand is fetched once for all phases and N grows from
    * cout to 4*cout, which is what Cout <= 32 layers need (an SS-mode MMA costs the same for any N <= 64).
-   * Only the affine + ReLU + out0 epilogue is available in this mode.  fold_cs % 16 == 0. */
+   * Only the affine + ReLU + out0 epilogue is available in this mode.  fold_cs % 16 == 0.
+   * Alternatively the op has osy phase entries (oy = 0 .. osy-1, ox = 0) of cout = osx*fold_cs columns each: only the
+   * horizontal phases are folded (column block p -> output pixel (i*osy + oy, j*osx + p)). */
   int32_t fold_cs, fold_cout;
   /* act_pre = 1: the activation is applied BEFORE the second affine (conv -> PReLU/ReLU -> BatchNorm, the order of
    * ChangeFormer.py:1138-1157 conv_diff / make_prediction) instead of at the end of the epilogue; needs scale2/shift2. */
   int32_t act_pre;
   float act_alpha;
+  /* Horizontal tap folding of a stride-1 3x3 conv with few output channels (nn.Conv2d(k=3, padding=1): SNUNet.py:17-26,
+   * SiamUnet_diff.py:18-48; ConvTranspose2d(k=3, s=1, p=1) decoder "convs": SiamUnet_diff.py:54-90).  xf_cs > 0: the K-program
+   * holds ONE tap per filter row (dy = -1, 0, +1; dx = 0; no horizontal halo) whose weight block stacks the row's three
+   * filter columns, n_tile = cout_pad = 3*xf_cs (xf_cs = cout rounded up to 16): column b*xf_cs + c of the accumulator at
+   * input position x is tap (dy, b - 1)'s contribution to channel c of output x - (b - 1); the epilogue sums the three
+   * blocks across neighbouring pixels.  Tiles are 8 x 16 input positions with 14 output columns (the library's choice;
+   * hg / wg stay the output dims).  Single phase, stride-1 sources, osy = osx = 1, no space-to-depth / folded store. */
+  int32_t xf_cs;
 } stcd_conv_desc;
 
 /* returns op index >= 0, or <0 */

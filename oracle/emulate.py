@@ -68,6 +68,15 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
                     q = _bf16(v[..., p_ * op.fold_cs: p_ * op.fold_cs + op.fold_cout])
                     T[op.out0][sl, ph.oy + p_ // op.osx::op.osy, ph.ox + p_ % op.osx::op.osx,
                                op.out0_coff: op.out0_coff + op.fold_cout] = q
+            elif op.xf_cs:
+                # horizontal tap folding: column block b at input position x is tap (dy, b - 1)'s contribution to output
+                # x - (b - 1);  out[x] = D_0[x - 1] + D_1[x] + D_2[x + 1]  (positions outside the image contribute zeros)
+                cs = op.xf_cs
+                d0, d1, d2 = acc[..., :cs], acc[..., cs: 2 * cs], acc[..., 2 * cs: 3 * cs]
+                out = d1.clone()
+                out[:, :, 1:] += d0[:, :, :-1]
+                out[:, :, :-1] += d2[:, :, 1:]
+                full[m][..., :cs] = out
             else:
                 full[m][:, ph.oy::op.osy, ph.ox::op.osx] = acc
     def act(v):

@@ -144,6 +144,7 @@ class ConvDesc(C.Structure):
         ("out0_s2d", C.c_int32),
         ("fold_cs", C.c_int32), ("fold_cout", C.c_int32),
         ("act_pre", C.c_int32), ("act_alpha", C.c_float),
+        ("xf_cs", C.c_int32),
     ]
 
 
@@ -171,7 +172,7 @@ class EcamDesc(C.Structure):
     ]
 
 
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [

@@ -48,6 +48,11 @@ constexpr int kMaxTaps = 320;    // weight blocks per phase
 constexpr int kConvThreads = 224;
 constexpr int kFastMma = 36;     // per-chunk MMA offsets kept in the constant bank (9 taps x 4 K steps)
 constexpr int kMaxRSlots = 4;    // residual tiles in flight (TMA -> shared-memory ring)
+// Horizontally folded 3x3 convs (E_XF): the tile is 8 rows x 16 columns of INPUT positions, of which the inner 14 columns
+// are outputs (tiles overlap by one column on each side).
+constexpr int kXfTileH = 8;
+constexpr int kXfTileW = 16;
+constexpr int kXfStep = 14;
 
 // epilogue features; a kernel instance either fixes them at compile time or (E_GENERIC) reads
 // them from ConvParams at run time
@@ -62,6 +67,16 @@ enum : uint32_t {
   E_F32 = 128u,   // out_f32 (NCHW fp32, external) <- v
   E_ACTX = 256u,  // extended activation: GELU / PReLU and/or activation before the second affine (read at run time)
   E_RSM = 512u,   // with E_RES: the residual tile arrives by TMA in a shared-memory ring (ConvParams::res_slots > 0)
+  // Horizontal tap folding of a stride-1 3x3 conv with few output channels.  An SS-mode tcgen05.mma M=128 K=16 costs ~45
+  // cycles for any N <= 64 (the 4 KB A operand read from shared memory): a Cout-32 layer run tap by tap is capped at 36 % of
+  // the tensor peak.  Folded, the three taps of one filter ROW share one MMA: A = the input tile shifted vertically only,
+  // B = [W(dy,-1); W(dy,0); W(dy,+1)] (N = 3 * cs, cs = Cout rounded up to 16), so column block b of the accumulator at input
+  // position x holds that tap's contribution to output x - (b - 1), and the epilogue forms
+  //     out[x] = D_0[x - 1] + D_1[x] + D_2[x + 1]
+  // with two warp shuffles per value (a warp owns two tile rows of 16 positions; the outer two columns of a tile only
+  // feed their neighbours).  3 MMAs of N = 96 (~56 cycles) replace 9 of N = 32 (45 cycles): 2.4x fewer tensor-pipe cycles
+  // for Cout 32, 3x for Cout 16, and the box has no horizontal halo (rows of 256 contiguous bytes).
+  E_XF = 1024u,
   E_GENERIC = 1u << 31
 };
 
@@ -114,7 +129,9 @@ struct ConvParams {
   // that rate (262 us with the residual, 152 us without).  The A producer now fetches the residual tile of each pass with
   // ONE TMA box per sub-tile, `res_slots` passes ahead; the epilogue reads it with conflict-free 16-byte LDS.
   int32_t res_slots;                       // 0: per-thread global loads
-  uint32_t res_slot_bytes, res_sub_bytes;  // ring slot = MT sub-tiles of [n_tile/8][16][8][8] bf16
+  uint32_t res_slot_bytes, res_sub_bytes;  // ring slot = MT sub-tiles of [res_ch/8][tile rows][tile px][8] bf16
+  int32_t res_ch;                          // channels per residual box (n_tile; cs for E_XF)
+  int32_t xf_cs;                           // E_XF: column-block stride cs (n_tile = 3 * cs); 0 otherwise
   __nv_bfloat16* out0;
   int32_t out0_c8, out0_coff;
   int32_t reverse;   // 1: walk the tiles last-to-first (consecutive layers alternate, so a layer starts on the lines its producer wrote last: L2 hits)
@@ -161,12 +178,15 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
   const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
   return *reinterpret_cast<const uint32_t*>(&r);
 }
+// 2x2 max over the window whose top-left pixel this lane holds: the right neighbour is DX lanes away, the lower one DY
+template <int DX, int DY>
 __device__ __forceinline__ uint32_t pool1_bf16x2(uint32_t a) {
-  a = max_bf16x2(a, __shfl_xor_sync(0xffffffffu, a, 1));
-  return max_bf16x2(a, __shfl_xor_sync(0xffffffffu, a, 8));
+  a = max_bf16x2(a, __shfl_down_sync(0xffffffffu, a, DX));
+  return max_bf16x2(a, __shfl_down_sync(0xffffffffu, a, DY));
 }
+template <int DX, int DY>
 __device__ __forceinline__ uint4 pool4_bf16x2(uint4 q) {
-  return make_uint4(pool1_bf16x2(q.x), pool1_bf16x2(q.y), pool1_bf16x2(q.z), pool1_bf16x2(q.w));
+  return make_uint4(pool1_bf16x2<DX, DY>(q.x), pool1_bf16x2<DX, DY>(q.y), pool1_bf16x2<DX, DY>(q.z), pool1_bf16x2<DX, DY>(q.w));
 }
 
 // per-chunk tables, built once per CTA
@@ -199,6 +219,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
   __shared__ __align__(8) ChunkMma s_cmma[kMaxChunks];
   __shared__ __align__(16) float s_aff[4][256];      // scale, shift, scale2, shift2 of this CTA's N tile
 
+  constexpr bool XF = (EPI & E_XF) != 0;
+  constexpr int TH = XF ? kXfTileH : kTileH;      // tile rows
+  constexpr int TW = XF ? kXfTileW : kTileW;      // tile columns (input positions for XF)
+  constexpr int XSTEP = XF ? kXfStep : kTileW;    // output columns per tile
+  constexpr int XOFF = XF ? 1 : 0;                // the tile starts one column left of its first output
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   long long* tr = p.trace ? p.trace + ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
@@ -251,7 +276,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       s_cload[c] = L;
       const int ksteps = p.kc >> 4;
       ChunkMma M;
-      M.a_hi = (static_cast<uint32_t>(pw) & 0x3FFF) | (1u << 14);            // SBO = pw * 16 B; descriptor version 1
+      // SBO (next 8 rows of M): the next tile line, pw * 16 B; XF tiles have no horizontal halo and 16-pixel lines, so the
+      // 8-pixel groups of a tile are 128 B apart throughout
+      M.a_hi = (XF ? 8u : (static_cast<uint32_t>(pw) & 0x3FFF)) | (1u << 14);   // descriptor version 1
       M.n_mma = static_cast<uint32_t>(ch.n_taps * ksteps);
       s_cmma[c] = M;
       const uint32_t a_lo_lbo = (static_cast<uint32_t>(pw * phh) & 0x3FFF) << 16;   // LBO = pw * ph * 16 B
@@ -316,7 +343,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     uint32_t par = 1;  // parity to wait for on a_empty[s]: first pass through the ring never blocks
     int rs = 0;
     uint32_t rpar = 1;
-    const uint32_t res_tx = static_cast<uint32_t>(MT) * static_cast<uint32_t>(p.n_tile) * (kTileH * kTileW * 2u);
+    const uint32_t res_tx = static_cast<uint32_t>(MT) * static_cast<uint32_t>(p.res_ch) * (TH * TW * 2u);
     pdl_wait();        // activations are written by the previous kernel(s)
     for (int t = 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
@@ -325,9 +352,9 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       tile /= p.tiles_x;
       const int tile_y = tile % p.tiles_y;
       const int img = tile / p.tiles_y;
-      const int x0 = tile_x * kTileW, y0 = tile_y * kTileH;
+      const int x0 = tile_x * XSTEP - XOFF, y0 = tile_y * TH;
       if (p.res_slots) {
-        // the pass's residual tiles: one box {8 px x 8 ch, 16 rows, n_tile / 8 groups} per sub-tile
+        // the pass's residual tiles: one box {tile px x 8 ch, tile rows, res_ch / 8 groups} per sub-tile
         mbar_wait_relaxed(&r_empty[rs], rpar);
         if (leader) {
           mbar_expect_tx(&r_full[rs], res_tx);
@@ -571,8 +598,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     // written by the previous kernel without going through the A producer's dependency wait
     if (res_rg) pdl_wait();
     const int wq = warp & 3;  // TMEM lane quarter this warp may access
-    const int ty = 4 * wq + (lane >> 3);
-    const int tx = lane & 7;
+    // pixel of the tile this thread (= TMEM lane 32 * wq + lane) owns: 4 lines of 8 per warp, or (XF) 2 lines of 16
+    const int ty = XF ? 2 * wq + (lane >> 4) : 4 * wq + (lane >> 3);
+    const int tx = XF ? (lane & 15) : (lane & 7);
+    const bool lane_out = !XF || (tx >= 1 && tx <= kXfStep);   // XF: the outer two columns only feed their neighbours
+    const int c_lim = XF ? p.xf_cs : p.n_tile;                 // output channels this CTA finishes
     const uint32_t hw = static_cast<uint32_t>(p.ho) * p.wo;  // pixels per image plane
     const uint32_t hw_pool = hw >> 2;
     const int cg8 = n0 >> 3;  // first 8-channel group of this N tile
@@ -589,13 +619,13 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       tile2 /= p.tiles_x;
       const int tile_y2 = tile2 % p.tiles_y;
       const int img2 = tile2 / p.tiles_y;
-      const int gy2 = tile_y2 * kTileH + ty, gx2 = tile_x2 * kTileW + tx;
-      if (gy2 < p.hg && gx2 < p.wg) {
+      const int gy2 = tile_y2 * TH + ty, gx2 = tile_x2 * XSTEP + tx - XOFF;
+      if (gy2 < p.hg && gx2 < p.wg && lane_out) {
         const uint32_t pix2 = static_cast<uint32_t>(gy2 * p.osy + phase.oy) * p.wo + (gx2 * p.osx + phase.ox);
 #pragma unroll
         for (int sidx = 0; sidx < PF; ++sidx) {
           const int c0 = 16 * sidx;
-          if (c0 < p.n_tile && n0 + c0 < p.cout) {
+          if (c0 < c_lim && n0 + c0 < p.cout) {
 #pragma unroll
             for (int m = 0; m < MS; ++m) {
               const __nv_bfloat16* r = p.res + ((static_cast<size_t>(img2 + p.m_off[mb2 + m]) * p.res_c8 + cg8 + 2 * sidx) * hw + pix2) * 8;
@@ -617,8 +647,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       tile /= p.tiles_x;
       const int tile_y = tile % p.tiles_y;
       const int img = tile / p.tiles_y;
-      const int gy = tile_y * kTileH + ty, gx = tile_x * kTileW + tx;
-      const bool valid = (gy < p.hg) && (gx < p.wg);
+      const int gy = tile_y * TH + ty, gx = tile_x * XSTEP + tx - XOFF;
+      const bool valid = (gy < p.hg) && (gx < p.wg) && lane_out;
       const int oy = gy * p.osy + phase.oy, ox = gx * p.osx + phase.ox;
       const uint32_t pix = static_cast<uint32_t>(oy) * p.wo + ox;
       const uint32_t pix_pool = static_cast<uint32_t>(oy >> 1) * (p.wo >> 1) + (ox >> 1);
@@ -673,15 +703,72 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
         }
         const uint32_t tgrp = tlane + mb * p.n_tile;
 
-        for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        // Up-sampling ops with the horizontal output phases folded into N (osx = 2): column blocks 2q and 2q + 1 are the
+        // two horizontally adjacent output pixels (row phase q) of this thread's input pixel -- 32 contiguous bytes per
+        // channel group, written with ONE 256-bit store.  Two 16-byte stores (or two phases in different CTAs) write each
+        // 32-byte sector in halves, and partially written sectors cost the memory system a fill: SNUNet's Up1_x ran at
+        // 263 us with its stores and 85 us without them.
+        constexpr bool kMayFold2 = ((EPI & E_GENERIC) != 0 || (EPI & (E_RAW | E_AFF2 | E_RES | E_POOL | E_DIFF | E_F32)) == 0) && !XF && MS == 1;
+        if (kMayFold2 && p.fold_cs && p.osx == 2) {
+          const int n_rows = (p.cout / p.fold_cs) >> 1;      // row phases in this GEMM phase: 2 (all phases folded) or 1
+          const size_t imf = static_cast<size_t>(img + p.m_off[mb]);
+          for (int q = 0; q < n_rows; ++q) {
+            const uint32_t pixf = static_cast<uint32_t>(gy * p.osy + phase.oy + q) * p.wo + (gx * 2 + phase.ox);
+            for (int c0 = 0; c0 < p.fold_cs; c0 += 16) {
+              if (c0 >= p.fold_cout) break;
+              const int col_a = 2 * q * p.fold_cs + c0, col_b = col_a + p.fold_cs;
+              uint32_t ra[16], rb[16];
+              tmem_ld16(tgrp + col_a, ra);
+              tmem_ld16(tgrp + col_b, rb);
+              tmem_wait_ld();
+              float va[16], vb[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                va[j] = fmaf(__uint_as_float(ra[j]), s_aff[0][col_a + j], s_aff[1][col_a + j]);
+                vb[j] = fmaf(__uint_as_float(rb[j]), s_aff[0][col_b + j], s_aff[1][col_b + j]);
+              }
+              if (has_relu) {
+                apply_act(va);
+                apply_act(vb);
+              }
+              if (valid) {
+                __nv_bfloat16* o = p.out0 + ((imf * p.out0_c8 + ((p.out0_coff + c0) >> 3)) * hw + pixf) * 8;
+                st_global_256(o, pack8_bf16(va), pack8_bf16(vb));
+                if (p.fold_cout - c0 > 8) st_global_256(o + static_cast<size_t>(hw) * 8, pack8_bf16(va + 8), pack8_bf16(vb + 8));
+              }
+            }
+          }
+          continue;
+        }
+
+        for (int c0 = 0; c0 < c_lim; c0 += 16) {
           const int ch = n0 + c0;
           if (ch >= p.cout) break;
           const bool two = (p.cout - ch) > 8;  // both 8-channel groups of this 16-column step are real
-          if (res_rg && valid && c0 + 16 >= 16 * PF && c0 + 16 < p.n_tile && ch + 16 < p.cout) load_res(c0 + 16, r_nxt);
+          if (res_rg && valid && c0 + 16 >= 16 * PF && c0 + 16 < c_lim && ch + 16 < p.cout) load_res(c0 + 16, r_nxt);
           uint32_t raw[MS][16];
+          if (!XF) {
 #pragma unroll
-          for (int m = 0; m < MS; ++m) tmem_ld16(tgrp + m * p.n_tile + c0, raw[m]);
-          tmem_wait_ld();
+            for (int m = 0; m < MS; ++m) tmem_ld16(tgrp + m * p.n_tile + c0, raw[m]);
+            tmem_wait_ld();
+          } else {
+            // out[x] = D_0[x - 1] + D_1[x] + D_2[x + 1]: column block b sits at column b * cs; the left / right neighbours
+            // are the adjacent lanes (a warp holds two tile lines of 16 positions; lanes 0 and 15 of a line never output)
+#pragma unroll
+            for (int m = 0; m < MS; ++m) {
+              uint32_t dl[16], dr[16];
+              tmem_ld16(tgrp + m * p.n_tile + c0, dl);
+              tmem_ld16(tgrp + m * p.n_tile + p.xf_cs + c0, raw[m]);
+              tmem_ld16(tgrp + m * p.n_tile + 2 * p.xf_cs + c0, dr);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float l = __shfl_up_sync(0xffffffffu, __uint_as_float(dl[j]), 1);
+                const float r = __shfl_down_sync(0xffffffffu, __uint_as_float(dr[j]), 1);
+                raw[m][j] = __float_as_uint((l + __uint_as_float(raw[m][j])) + r);
+              }
+            }
+          }
           float v[MS][16];
           const size_t g8 = static_cast<size_t>(c0 >> 3);  // channel-group offset inside the N tile
 #pragma unroll
@@ -706,12 +793,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
               for (int j = 0; j < 16; ++j) v[m][j] = fmaf(v[m][j], s_aff[2][c0 + j], s_aff[3][c0 + j]);
             }
             if (res_sm) {
-              // tile in shared memory: [n_tile / 8][16 rows][8 px] x 16 B -- consecutive lanes, consecutive 16 B
+              // tile in shared memory: [res_ch / 8][tile rows][tile px] x 16 B -- consecutive lanes, consecutive 16 B
               const uint4* rt = reinterpret_cast<const uint4*>(smem_r + static_cast<size_t>(ers) * p.res_slot_bytes +
                                                                static_cast<size_t>(mb + m) * p.res_sub_bytes) +
-                                (c0 >> 3) * (kTileH * kTileW) + ty * kTileW + tx;
+                                (c0 >> 3) * (TH * TW) + ty * TW + tx;
               r_cur[m][0] = rt[0];
-              r_cur[m][1] = rt[kTileH * kTileW];
+              r_cur[m][1] = rt[TH * TW];
             }
             if (has_res && valid) {
               float rv[16];
@@ -749,9 +836,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
               }
               if (has_pool) {
                 // max over the 2x2 window on the packed bf16 pairs (rounding is monotonic, so
-                // max(bf16(a), bf16(b)) == bf16(max(a, b))): lanes +1 (x) and +8 (y)
-                const uint4 plo = pool4_bf16x2(lo), phi = pool4_bf16x2(hi);
-                if (valid && ((lane & 9) == 0)) {
+                // max(bf16(a), bf16(b)) == bf16(max(a, b))): lanes +1 (x) and +8 (y); XF tiles: +1 and +16, and the first
+                // output column of a tile is lane 1 (tile origins are even, so even output columns sit on odd lanes)
+                const uint4 plo = pool4_bf16x2<1, XF ? 16 : 8>(lo), phi = pool4_bf16x2<1, XF ? 16 : 8>(hi);
+                if (valid && (XF ? ((lane & 17) == 1) : ((lane & 9) == 0))) {
                   __nv_bfloat16* o = q_pool + (im[m] * p.out_pool_c8 + g8) * hw_pool * 8;
                   *reinterpret_cast<uint4*>(o) = plo;
                   if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw_pool) * 8) = phi;
@@ -822,7 +910,7 @@ struct ConvKernelEntry {
 
 // Specialised instances for the (M tiles, pairing, epilogue) combinations the lowered nets use;
 // anything else runs the generic instance (same code, epilogue features read from ConvParams at
-// run time).  The instances are compiled in four translation units (conv_inst_{a,b,c,d}.cu, built in
+// run time).  The instances are compiled in six translation units (conv_inst_{a..f}.cu, built in
 // parallel); conv_kernel_table() in stcd_b200.cu concatenates their tables.  X(MT, MS, EPI)
 #define STCD_CONV_INSTANCES_A(X)                       \
   /* FC-Siam encoder (Siamese pairs) */                \
@@ -900,7 +988,41 @@ struct ConvKernelEntry {
   X(4, 1, E_GENERIC)                                   \
   X(4, 2, E_GENERIC)
 
+#define STCD_CONV_INSTANCES_E(X)                       \
+  /* horizontally folded 3x3 convs (E_XF), Siamese pairs: FC-Siam / SNUNet level-0 and level-1 encoder layers */ \
+  X(2, 2, E_XF | E_RELU | E_OUT0)                      \
+  X(4, 2, E_XF | E_RELU | E_OUT0)                      \
+  X(2, 2, E_XF | E_RELU | E_POOL | E_DIFF)             \
+  X(4, 2, E_XF | E_RELU | E_POOL | E_DIFF)             \
+  X(2, 2, E_XF | E_RELU | E_OUT0 | E_POOL)             \
+  X(4, 2, E_XF | E_RELU | E_OUT0 | E_POOL)             \
+  X(2, 2, E_XF | E_RAW | E_AFF2 | E_RELU | E_OUT0)     \
+  X(4, 2, E_XF | E_RAW | E_AFF2 | E_RELU | E_OUT0)     \
+  X(2, 2, E_XF | E_RES | E_RSM | E_RELU | E_OUT0 | E_POOL) \
+  X(4, 2, E_XF | E_RES | E_RSM | E_RELU | E_OUT0 | E_POOL) \
+  X(2, 2, E_XF | E_GENERIC)                            \
+  X(4, 2, E_XF | E_GENERIC)
+
+#define STCD_CONV_INSTANCES_F(X)                       \
+  /* horizontally folded 3x3 convs (E_XF), one stream: decoders, nested-block nodes, logits */ \
+  X(1, 1, E_XF | E_RELU | E_OUT0)                      \
+  X(2, 1, E_XF | E_RELU | E_OUT0)                      \
+  X(4, 1, E_XF | E_RELU | E_OUT0)                      \
+  X(1, 1, E_XF | E_RAW | E_AFF2 | E_RELU | E_OUT0)     \
+  X(2, 1, E_XF | E_RAW | E_AFF2 | E_RELU | E_OUT0)     \
+  X(4, 1, E_XF | E_RAW | E_AFF2 | E_RELU | E_OUT0)     \
+  X(1, 1, E_XF | E_RES | E_RSM | E_RELU | E_OUT0)      \
+  X(2, 1, E_XF | E_RES | E_RSM | E_RELU | E_OUT0)      \
+  X(4, 1, E_XF | E_RES | E_RSM | E_RELU | E_OUT0)      \
+  X(1, 1, E_XF | E_F32)                                \
+  X(2, 1, E_XF | E_F32)                                \
+  X(1, 1, E_XF | E_GENERIC)                            \
+  X(2, 1, E_XF | E_GENERIC)                            \
+  X(4, 1, E_XF | E_GENERIC)
+
 // one table per translation unit
+const ConvKernelEntry* conv_kernel_table_e(int* n);
+const ConvKernelEntry* conv_kernel_table_f(int* n);
 const ConvKernelEntry* conv_kernel_table_a(int* n);
 const ConvKernelEntry* conv_kernel_table_b(int* n);
 const ConvKernelEntry* conv_kernel_table_c(int* n);

@@ -190,6 +190,13 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// 32 contiguous bytes (32-byte aligned) in ONE store: both halves of a sector leave together (STG.E.256)
+__device__ __forceinline__ void st_global_256(void* ptr, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- shared epilogue math
 // nn.GELU() = 0.5 x (1 + erf(x / sqrt 2)) with erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7 in exact arithmetic, 5e-7 measured
 // in fp32 with the fast exp / reciprocal): one MUFU.RCP, one MUFU.EX2 and 8 FMAs instead of erff's ~30 instructions and two

@@ -292,7 +292,8 @@ int check_sm100(int device) {
   return STCD_OK;
 }
 
-int encode_act_map(CUtensorMap* m, void* base, int n, int h, int w, int c, int kc, int sx, int sy, int ex, int ey) {
+int encode_act_map(CUtensorMap* m, void* base, int n, int h, int w, int c, int kc, int sx, int sy, int ex, int ey,
+                   int tile_w = stcd::kTileW, int tile_h = stcd::kTileH) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(STCD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   if (sx == 1 && sy == 1) {
@@ -300,7 +301,7 @@ int encode_act_map(CUtensorMap* m, void* base, int n, int h, int w, int c, int k
     // one dimension so a box row is (8 + ex) * 16 bytes instead of 16 (TMA cost is per box row).
     cuuint64_t gdim[4] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)(c / 8), (cuuint64_t)n};
     cuuint64_t gstr[3] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)(c / 8) * h * w * 16};
-    cuuint32_t box[4] = {(cuuint32_t)((stcd::kTileW + ex) * 8), (cuuint32_t)(stcd::kTileH + ey), (cuuint32_t)(kc / 8), 1};
+    cuuint32_t box[4] = {(cuuint32_t)((tile_w + ex) * 8), (cuuint32_t)(tile_h + ey), (cuuint32_t)(kc / 8), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (box[0] > 256) return fail(STCD_ERR_INVALID, "halo %d too wide for one TMA box row", ex);
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -312,7 +313,7 @@ int encode_act_map(CUtensorMap* m, void* base, int n, int h, int w, int c, int k
   // [img][c/8][h][w][8] bf16: dims fastest-first {8, w, h, c/8, img}
   cuuint64_t gdim[5] = {8, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)(c / 8), (cuuint64_t)n};
   cuuint64_t gstr[4] = {16, (cuuint64_t)w * 16, (cuuint64_t)h * w * 16, (cuuint64_t)(c / 8) * h * w * 16};
-  cuuint32_t box[5] = {8, (cuuint32_t)((stcd::kTileW + ex) * sx), (cuuint32_t)((stcd::kTileH + ey) * sy), (cuuint32_t)(kc / 8), 1};
+  cuuint32_t box[5] = {8, (cuuint32_t)((tile_w + ex) * sx), (cuuint32_t)((tile_h + ey) * sy), (cuuint32_t)(kc / 8), 1};
   cuuint32_t estr[5] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1238,6 +1239,16 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
   if (2 * mt * d->n_tile > 512)
     return -fail(STCD_ERR_INVALID, "double-buffered accumulators need %d TMEM columns (> 512)", 2 * mt * d->n_tile);
   if (d->pair && (plan->chunk < 1)) return -fail(STCD_ERR_INVALID, "pair op on an empty chunk");
+  if (d->xf_cs) {
+    bool ok = d->xf_cs >= 16 && d->xf_cs % 16 == 0 && d->n_tile == 3 * d->xf_cs && d->cout_pad == d->n_tile && d->cout <= d->xf_cs &&
+              d->n_phase == 1 && d->osy == 1 && d->osx == 1 && !d->out0_s2d && !d->fold_cs;
+    for (int s = 0; s < d->n_src && ok; ++s) ok = d->src_sy[s] == 1 && d->src_sx[s] == 1 && d->src_ex[s] == 0 && d->src_ey[s] == 2;
+    for (int t = 0; t < d->n_taps && ok; ++t) ok = d->taps[t].tx == 0 && d->taps[t].ty >= 0 && d->taps[t].ty <= 2;
+    for (int c = 0; c < d->n_chunks && ok; ++c) ok = d->chunks[c].bx == 0 && d->chunks[c].by == -1 && d->chunks[c].n_taps == 3;
+    if (!ok)
+      return -fail(STCD_ERR_INVALID, "horizontal tap folding (xf_cs=%d) needs n_tile == cout_pad == 3*xf_cs, cout <= xf_cs, one phase, "
+                   "stride-1 sources with halo (2, 0), three taps (dy, 0) per chunk and a plain (not space-to-depth / folded) store", d->xf_cs);
+  }
   if (d->hg < 1 || d->wg < 1 || d->osy < 1 || d->osx < 1) return -fail(STCD_ERR_INVALID, "bad grid/stride");
   for (int s = 0; s < d->n_src; ++s) {
     if (!valid_tensor(plan, d->src[s])) return -fail(STCD_ERR_INVALID, "bad src tensor %d", d->src[s]);
@@ -1437,10 +1448,11 @@ int stcd_plan_finalize(stcd_plan* plan) {
   static_assert(sizeof(stcd_tap) == sizeof(stcd::Tap), "tap layout");
   const size_t kSmemMax = 227 * 1024 - 12 * 1024;  // dynamic budget: static tables + barriers live beside it
   int n_kernels = 0;
-  static std::vector<stcd::ConvKernelEntry> all_kernels;     // the four translation units' tables, concatenated once
+  static std::vector<stcd::ConvKernelEntry> all_kernels;     // the translation units' tables, concatenated once
   if (all_kernels.empty()) {
     using TableFn = const stcd::ConvKernelEntry* (*)(int*);
-    for (TableFn fn : {stcd::conv_kernel_table_a, stcd::conv_kernel_table_b, stcd::conv_kernel_table_c, stcd::conv_kernel_table_d}) {
+    for (TableFn fn : {stcd::conv_kernel_table_a, stcd::conv_kernel_table_b, stcd::conv_kernel_table_c, stcd::conv_kernel_table_d,
+                       stcd::conv_kernel_table_e, stcd::conv_kernel_table_f}) {
       int n = 0;
       const stcd::ConvKernelEntry* t = fn(&n);
       all_kernels.insert(all_kernels.end(), t, t + n);
@@ -1485,22 +1497,26 @@ int stcd_plan_finalize(stcd_plan* plan) {
     stcd::ConvParams& p = op.p;
     memset(&p, 0, sizeof(p));
     size_t a_sub = 0;
+    const bool xf = d.xf_cs > 0;
+    const int tile_w = xf ? stcd::kXfTileW : stcd::kTileW, tile_h = xf ? stcd::kXfTileH : stcd::kTileH;
+    const int tile_step_x = xf ? stcd::kXfStep : stcd::kTileW;      // output columns per tile
     for (int s = 0; s < d.n_src; ++s) {
       const Tensor& t = plan->tensors[d.src[s]];
       int r = encode_act_map(&op.tm.src[s], t.ptr, t.mult * plan->chunk, t.h, t.w, t.c, d.kc, d.src_sx[s], d.src_sy[s],
-                             d.src_ex[s], d.src_ey[s]);
+                             d.src_ex[s], d.src_ey[s], tile_w, tile_h);
       if (r) return r;
       p.src_sy[s] = d.src_sy[s];
       p.src_sx[s] = d.src_sx[s];
       p.src_merged[s] = (d.src_sx[s] == 1 && d.src_sy[s] == 1) ? 1 : 0;
-      p.src_pw[s] = stcd::kTileW + d.src_ex[s];
-      p.src_ph[s] = stcd::kTileH + d.src_ey[s];
+      p.src_pw[s] = tile_w + d.src_ex[s];
+      p.src_ph[s] = tile_h + d.src_ey[s];
       a_sub = std::max(a_sub, (size_t)(d.kc / 8) * p.src_pw[s] * p.src_ph[s] * 16);
     }
     p.hg = d.hg;
     p.wg = d.wg;
-    p.tiles_x = (d.wg + stcd::kTileW - 1) / stcd::kTileW;
-    p.tiles_y = (d.hg + stcd::kTileH - 1) / stcd::kTileH;
+    p.tiles_x = (d.wg + tile_step_x - 1) / tile_step_x;
+    p.tiles_y = (d.hg + tile_h - 1) / tile_h;
+    p.xf_cs = d.xf_cs;
     p.n_ntiles = d.cout_pad / d.n_tile;
     p.osy = d.osy;
     p.osx = d.osx;
@@ -1616,7 +1632,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
       p.f_regular[ph] = regular ? 1 : 0;
       if (!regular) continue;
       p.f_nmma[ph] = c0.n_taps * ksteps;
-      p.f_a_hi[ph] = ((uint32_t)pw & 0x3FFF) | (1u << 14);
+      p.f_a_hi[ph] = (xf ? 8u : ((uint32_t)pw & 0x3FFF)) | (1u << 14);     // SBO: the next 8 pixels of M (XF: 128 B throughout)
       p.f_a_lo_lbo[ph] = ((uint32_t)(pw * phh) & 0x3FFF) << 16;
       p.f_b_chunk16[ph] = (uint32_t)c0.n_taps * (p.wblk_bytes >> 4);
       for (int k = 0; k < c0.n_taps; ++k)
@@ -1642,7 +1658,8 @@ int stcd_plan_finalize(stcd_plan* plan) {
     p.res_slots = 0;
     if (d.res >= 0 && d.n_phase == 1 && d.osy == 1 && d.osx == 1 && env_int("STCD_RES_SMEM", 1)) {
       const Tensor& tr = plan->tensors[d.res];
-      const size_t sub = (size_t)d.n_tile * stcd::kTileH * stcd::kTileW * 2;       // [n_tile / 8][16][8][8] bf16
+      p.res_ch = xf ? d.xf_cs : d.n_tile;
+      const size_t sub = (size_t)p.res_ch * tile_h * tile_w * 2;                   // [res_ch / 8][tile rows][tile px][8] bf16
       const size_t slot = sub * p.mt;
       const size_t fixed = 256 + p.tab_bytes + w_region;
       const size_t budget = cta_budget(occ);
@@ -1657,7 +1674,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
         }
       }
       if (p.res_slots) {
-        int r = encode_act_map(&op.tm.res, tr.ptr, tr.mult * plan->chunk, tr.h, tr.w, tr.c, d.n_tile, 1, 1, 0, 0);
+        int r = encode_act_map(&op.tm.res, tr.ptr, tr.mult * plan->chunk, tr.h, tr.w, tr.c, p.res_ch, 1, 1, 0, 0, tile_w, tile_h);
         if (r) return r;
       }
     }
@@ -1687,12 +1704,12 @@ int stcd_plan_finalize(stcd_plan* plan) {
     op.epi = (d.out_raw >= 0 ? stcd::E_RAW : 0u) | (!op.scale2.empty() ? stcd::E_AFF2 : 0u) | (d.res >= 0 ? stcd::E_RES : 0u) |
              (d.relu ? stcd::E_RELU : 0u) | (d.out0 >= 0 ? stcd::E_OUT0 : 0u) | (d.out_pool >= 0 ? stcd::E_POOL : 0u) |
              (d.out_diff >= 0 ? stcd::E_DIFF : 0u) | (d.out_ext >= 0 ? stcd::E_F32 : 0u) |
-             ((d.relu >= 2 || d.act_pre) ? stcd::E_ACTX : 0u) | (p.res_slots ? stcd::E_RSM : 0u);
+             ((d.relu >= 2 || d.act_pre) ? stcd::E_ACTX : 0u) | (p.res_slots ? stcd::E_RSM : 0u) | (xf ? stcd::E_XF : 0u);
     op.fn = nullptr;
     for (int i = 0; i < n_kernels && !force_generic; ++i)
       if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == op.epi) op.fn = kernels[i].fn;
     for (int i = 0; i < n_kernels && !op.fn; ++i)
-      if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == stcd::E_GENERIC) op.fn = kernels[i].fn;
+      if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == (stcd::E_GENERIC | (xf ? stcd::E_XF : 0u))) op.fn = kernels[i].fn;
     if (!op.fn) return fail(STCD_ERR_INVALID, "no conv kernel instance for mt=%d", op.mt);
     if (d.res >= 0) {
       p.res = (const __nv_bfloat16*)plan->tensors[d.res].ptr;

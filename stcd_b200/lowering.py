@@ -113,6 +113,10 @@ class ConvSpec:
     act_kind: int = 0
     act_alpha: float = 0.0
     act_pre: bool = False
+    # > 0: horizontal tap folding of a stride-1 3x3 conv (csrc/conv_ws.cuh, E_XF): one tap per filter row whose weight block
+    # stacks the row's three filter columns, n_tile = cout_pad = 3 * xf_cs; the epilogue sums the column blocks across
+    # neighbouring pixels.  `cout` stays the real channel count.
+    xf_cs: int = 0
 
     def weight_block(self, nt: int, block: int) -> torch.Tensor:
         """fp32 [n_tile, kc] view of one packed weight block (for the emulator)."""
@@ -552,6 +556,7 @@ def _taps_to_gemm(
     cout: int,
     pair: bool,
     max_kc: int = 64,
+    force_n_tile: int = 0,
 ):
     """Build the K-program and the packed weights.
 
@@ -585,7 +590,7 @@ def _taps_to_gemm(
     # wide halos (dilated convs) take thinner chunks: the A stage is (tile + halo) * kc
     kc = choose_kc(stored_c, max(1, max_taps), cap=max_kc if max_kc < 64 else 112)
     k_mmas = max((sum(len(t) * -(-sc_ // 16) for sc_, t in zip(stored_c, staps)) for (_, _, staps) in seg_phase_taps), default=1)
-    n_tile, cout_pad = choose_n_tile(cout, pair, k_mmas)
+    n_tile, cout_pad = (force_n_tile, force_n_tile) if force_n_tile else choose_n_tile(cout, pair, k_mmas)
     n_nt = cout_pad // n_tile
     # halo extents per source: max over phases and segments of the tap range (stride-1 sources only)
     ey = [0] * len(srcs)
@@ -715,6 +720,40 @@ def up2_conv_taps(weight: torch.Tensor, pad: int, a: int, b: int) -> List[Tuple[
             w = weight[:, :, ky, kx].to(torch.float32)
             merged[(dy, dx)] = merged[(dy, dx)] + w if (dy, dx) in merged else w.clone()
     return [(dy, dx, w) for (dy, dx), w in sorted(merged.items())]
+
+
+XF_MAX_CS = int(os.environ.get("STCD_XF_MAX_CS", "32"))       # widest Cout (rounded up to 16) that takes horizontal tap folding; 0 disables
+XF_MIN_W = 28
+
+
+def xf_taps(name: str, segs: Sequence[Segment], phase_taps, cout: int, pair: bool, hg: int, wg: int):
+    """Horizontal tap folding (ConvSpec.xf_cs): returns (single-phase SegTaps with one tap per filter row and [3*cs, c]
+    weight blocks, cs) when the op is a stride-1 3x3 conv over stride-1 sources with Cout <= XF_MAX_CS, else None.
+
+    An SS-mode tcgen05.mma M=128 K=16 costs ~45 cycles for N <= 64 and ~56 for N = 96 (A + B operand bytes over the
+    128 B/clk shared-memory read): three taps per MMA instead of one cut the tensor-pipe cycles of a Cout-32 layer 2.4x
+    (Cout 16: 3x); 14 of a tile's 16 columns are outputs, so the net gain is 2.1x / 2.6x."""
+    cs = (cout + 15) // 16 * 16
+    if not XF_MAX_CS or cs > XF_MAX_CS or len(phase_taps) != 1 or wg < XF_MIN_W or hg < 8:
+        return None
+    if 2 * (2 if pair else 1) * 3 * cs > 512:           # double-buffered accumulators of N = 3 * cs columns per sub-tile
+        return None
+    if any(s.sy != 1 or s.sx != 1 for s in segs):
+        return None
+    oy, ox, taps = phase_taps[0]
+    per_seg = _split_taps(name, segs, taps)
+    want = sorted((dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1))
+    out = SegTaps([[] for _ in segs])
+    for si, (s, t) in enumerate(zip(segs, per_seg)):
+        if sorted((dy, dx) for (dy, dx, _) in t) != want:
+            return None
+        by_off = {(dy, dx): w for (dy, dx, w) in t}
+        for dy in (-1, 0, 1):
+            blk = torch.zeros(3 * cs, s.c_real, dtype=torch.float32)
+            for b, dx in enumerate((-1, 0, 1)):
+                blk[b * cs: b * cs + cout] = by_off[(dy, dx)]
+            out[si].append((dy, 0, blk))
+    return [(oy, ox, out)], cs
 
 
 FOLD_X_MAX_N = int(os.environ.get("STCD_FOLD_X_MAX_N", "128"))   # widest GEMM N of a horizontally folded up-sampling op
@@ -868,8 +907,18 @@ def add_conv(
             phase_taps, cout, scale, shift = f_taps, osx * cs, sc, sh
     elif fold:
         raise ValueError(f"{name}: phase folding needs an up-sampling op whose only output is out0")
-    wbits, kc, n_tile, cout_pad, phases, chunks, taps, srcs, sy, sx, ey, ex = _taps_to_gemm(
-        prog, name, segs, phase_taps, cout, pair, max_kc)
+    xf_cs = 0
+    if osy == 1 and osx == 1 and not out0_s2d and not fold_cs and act_kind in (0, 1) and not act_pre:
+        xf = xf_taps(name, segs, phase_taps, cout, pair, hg, wg)
+        if xf is not None:
+            xf_phase_taps, xf_cs = xf
+    if xf_cs:
+        wbits, kc, n_tile, cout_pad, phases, chunks, taps, srcs, sy, sx, ey, ex = _taps_to_gemm(
+            prog, name, segs, xf_phase_taps, 3 * xf_cs, pair, max_kc, force_n_tile=3 * xf_cs)
+    else:
+        # a folded op keeps its column blocks in ONE N tile (the store pairs blocks of the same CTA)
+        wbits, kc, n_tile, cout_pad, phases, chunks, taps, srcs, sy, sx, ey, ex = _taps_to_gemm(
+            prog, name, segs, phase_taps, cout, pair, max_kc, force_n_tile=cout if fold_cs else 0)
     spec = ConvSpec(
         name=name, srcs=srcs, src_sy=sy, src_sx=sx, src_ey=ey, src_ex=ex, hg=hg, wg=wg, img_mult=img_mult, pair=pair,
         weights=wbits, kc=kc, n_tile=n_tile, cout=cout, cout_pad=cout_pad, phases=phases, chunks=chunks, taps=taps,
@@ -879,6 +928,7 @@ def add_conv(
         relu=relu, res=res, out0=out0, out0_coff=out0_coff, out_raw=out_raw, out_pool=out_pool,
         out_diff=out_diff, out_ext=out_ext, macs_per_pair=macs_per_pair, out0_s2d=out0_s2d,
         fold_cs=fold_cs, fold_cout=fold_cout, act_kind=act_kind, act_alpha=float(act_alpha), act_pre=act_pre,
+        xf_cs=xf_cs,
     )
     prog.ops.append(spec)
     return spec

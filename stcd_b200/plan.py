@@ -191,6 +191,7 @@ class Plan:
         d.out_ext = op.out_ext
         d.out0_s2d = 1 if op.out0_s2d else 0
         d.fold_cs, d.fold_cout = op.fold_cs, op.fold_cout
+        d.xf_cs = op.xf_cs
         _lib.check_id(self.lib.stcd_plan_add_conv(self._h, C.byref(d)), f"conv {op.name}")
 
     def _add_ecam(self, op: EcamHeadSpec) -> None:
