@@ -910,7 +910,7 @@ struct ConvKernelEntry {
 
 // Specialised instances for the (M tiles, pairing, epilogue) combinations the lowered nets use;
 // anything else runs the generic instance (same code, epilogue features read from ConvParams at
-// run time).  The instances are compiled in six translation units (conv_inst_{a..f}.cu, built in
+// run time).  The instances are compiled in five translation units (conv_inst_{a..e}.cu, built in
 // parallel); conv_kernel_table() in stcd_b200.cu concatenates their tables.  X(MT, MS, EPI)
 #define STCD_CONV_INSTANCES_A(X)                       \
   /* FC-Siam encoder (Siamese pairs) */                \
@@ -989,22 +989,8 @@ struct ConvKernelEntry {
   X(4, 2, E_GENERIC)
 
 #define STCD_CONV_INSTANCES_E(X)                       \
-  /* horizontally folded 3x3 convs (E_XF), Siamese pairs: FC-Siam / SNUNet level-0 and level-1 encoder layers */ \
-  X(2, 2, E_XF | E_RELU | E_OUT0)                      \
-  X(4, 2, E_XF | E_RELU | E_OUT0)                      \
-  X(2, 2, E_XF | E_RELU | E_POOL | E_DIFF)             \
-  X(4, 2, E_XF | E_RELU | E_POOL | E_DIFF)             \
-  X(2, 2, E_XF | E_RELU | E_OUT0 | E_POOL)             \
-  X(4, 2, E_XF | E_RELU | E_OUT0 | E_POOL)             \
-  X(2, 2, E_XF | E_RAW | E_AFF2 | E_RELU | E_OUT0)     \
-  X(4, 2, E_XF | E_RAW | E_AFF2 | E_RELU | E_OUT0)     \
-  X(2, 2, E_XF | E_RES | E_RSM | E_RELU | E_OUT0 | E_POOL) \
-  X(4, 2, E_XF | E_RES | E_RSM | E_RELU | E_OUT0 | E_POOL) \
-  X(2, 2, E_XF | E_GENERIC)                            \
-  X(4, 2, E_XF | E_GENERIC)
-
-#define STCD_CONV_INSTANCES_F(X)                       \
-  /* horizontally folded 3x3 convs (E_XF), one stream: decoders, nested-block nodes, logits */ \
+  /* horizontally folded 3x3 convs (E_XF), one stream: decoders, nested-block nodes, logits.  The lowering never folds      \
+     Siamese-pair ops (twice the accumulator columns: one CTA per SM, measured 2x slower), so there are no MS = 2 instances */ \
   X(1, 1, E_XF | E_RELU | E_OUT0)                      \
   X(2, 1, E_XF | E_RELU | E_OUT0)                      \
   X(4, 1, E_XF | E_RELU | E_OUT0)                      \
@@ -1022,7 +1008,6 @@ struct ConvKernelEntry {
 
 // one table per translation unit
 const ConvKernelEntry* conv_kernel_table_e(int* n);
-const ConvKernelEntry* conv_kernel_table_f(int* n);
 const ConvKernelEntry* conv_kernel_table_a(int* n);
 const ConvKernelEntry* conv_kernel_table_b(int* n);
 const ConvKernelEntry* conv_kernel_table_c(int* n);

@@ -256,9 +256,8 @@ struct stcd_plan {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   float* stage_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   std::vector<float*> stage_out[2];
-  // CUDA graphs of one chunk's launch list, keyed by the caller's pointers (STCD_GRAPH=0 disables).  A small net at a small
-  // batch is launch-bound (SiamUnet_diff, 8 pairs: 25 launches of 12-30 us of device time each): replaying a captured graph
-  // removes the per-launch host cost and keeps the programmatic-dependent-launch edges between the kernels.
+  // CUDA graphs of one chunk's launch list, keyed by the caller's pointers (opt-in: STCD_GRAPH=1; see stcd_plan_finalize for
+  // the measurement that keeps it off by default).
   struct GraphEntry {
     const void* x1 = nullptr;
     const void* x2 = nullptr;
@@ -1452,7 +1451,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
   if (all_kernels.empty()) {
     using TableFn = const stcd::ConvKernelEntry* (*)(int*);
     for (TableFn fn : {stcd::conv_kernel_table_a, stcd::conv_kernel_table_b, stcd::conv_kernel_table_c, stcd::conv_kernel_table_d,
-                       stcd::conv_kernel_table_e, stcd::conv_kernel_table_f}) {
+                       stcd::conv_kernel_table_e}) {
       int n = 0;
       const stcd::ConvKernelEntry* t = fn(&n);
       all_kernels.insert(all_kernels.end(), t, t + n);
@@ -1483,7 +1482,11 @@ int stcd_plan_finalize(stcd_plan* plan) {
     return std::min(kSmemMax, share > fixed ? share - fixed : 0);
   };
   plan->pdl = env_int("STCD_PDL", 1);
-  plan->graph_mode = env_int("STCD_GRAPH", 1);
+  // Opt-in (STCD_GRAPH=1).  Measured on B200 (round 2, gpurun_out/gab_*): replaying the captured chunk is NOT faster than the
+  // programmatic-dependent-launch chain the plain path already issues -- SiamUnet_diff at 8 pairs: 26.7 k pairs/s plain vs
+  // 14.4 k through the graph, ChangeGNNV1: 2 239 vs 1 300, SNUNet / SegCD: equal.  The small nets are bound by the device-side
+  // fill / drain of each kernel (4-11 us from the end of one layer to the first MMA of the next), not by host launch cost.
+  plan->graph_mode = env_int("STCD_GRAPH", 0);
   const int force_generic = env_int("STCD_FORCE_GENERIC", 0);
   int n_sm = 148;
   CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, plan->device));

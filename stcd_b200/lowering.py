@@ -722,7 +722,7 @@ def up2_conv_taps(weight: torch.Tensor, pad: int, a: int, b: int) -> List[Tuple[
     return [(dy, dx, w) for (dy, dx), w in sorted(merged.items())]
 
 
-XF_MAX_CS = int(os.environ.get("STCD_XF_MAX_CS", "32"))       # widest Cout (rounded up to 16) that takes horizontal tap folding; 0 disables
+XF_MAX_CS = int(os.environ.get("STCD_XF_MAX_CS", "64"))       # widest Cout (rounded up to 16) that takes horizontal tap folding; 0 disables
 XF_MIN_W = 28
 
 
@@ -736,7 +736,19 @@ def xf_taps(name: str, segs: Sequence[Segment], phase_taps, cout: int, pair: boo
     cs = (cout + 15) // 16 * 16
     if not XF_MAX_CS or cs > XF_MAX_CS or len(phase_taps) != 1 or wg < XF_MIN_W or hg < 8:
         return None
-    if 2 * (2 if pair else 1) * 3 * cs > 512:           # double-buffered accumulators of N = 3 * cs columns per sub-tile
+    # Siamese-pair ops would need 2 x 2 x 3cs TMEM columns: one CTA per SM with four epilogue warps for twice the accumulator
+    # reads -- measured 2x SLOWER than the tap-by-tap form (SNUNet conv0_0: 262 -> 525 us), and the pair layers of the
+    # nets have too few input channels to profit anyway
+    if pair:
+        return None
+    # Cost model (cycles per output pixel, measured MMA costs: tools/ubench/mma_n.cu).  The folded form reads 3x the accumulator
+    # columns from TMEM (64 B/clk per SM: 24 * cs cycles per tile) and shuffles them, so it only pays once the tile's MMAs
+    # outlast that: e.g. Cout 32 from >= 48 input channels, Cout 16 from >= 32 (measured: SNUNet conv0_x.conv1, 128-224 input
+    # channels, 907 -> 622 us; conv0_x.conv2, 32 input channels, 166 -> 222 us).
+    k16 = sum((s.c_real + 15) // 16 for s in segs)
+    cost_std = k16 * 9 * mma_cycles(cs) / 128.0
+    cost_xf = max(k16 * 3 * mma_cycles(3 * cs), 24 * cs + 200) / 112.0
+    if cost_xf >= cost_std:
         return None
     if any(s.sy != 1 or s.sx != 1 for s in segs):
         return None
@@ -762,7 +774,7 @@ FOLD_X_MAX_N = int(os.environ.get("STCD_FOLD_X_MAX_N", "128"))   # widest GEMM N
 def mma_cycles(n: int) -> int:
     """Measured cost of one SS-mode tcgen05.mma M=128 K=16 on B200 (tools/ubench/mma_rate.cu): for N <= 64 the
     4 KB A-operand read from shared memory, not the math, sets the pace."""
-    return 45 if n <= 64 else (64 if n <= 128 else 128)
+    return max(45, 32 + n // 4, n // 2)        # 45 (N <= 48), 48 (64), 56 (96), 64 (128), 96 (192), 128 (256)
 
 
 def _split_taps(name: str, segs: Sequence[Segment], taps) -> List[list]:
