@@ -919,6 +919,11 @@ def add_conv(
             phase_taps, cout, scale, shift = f_taps, osx * cs, sc, sh
     elif fold:
         raise ValueError(f"{name}: phase folding needs an up-sampling op whose only output is out0")
+    if res is not None and pair:
+        # Siamese-pair ops with a residual: a 64-channel chunk of both streams (2 x 23 KB per stage) leaves no room for the
+        # residual ring beside resident 64 -> 64 weights (74 KB) -- the op fell back to per-thread residual loads and ran at
+        # 0.39 of the HBM roof (SNUNet conv1_0.conv2).  32-channel chunks halve the stage; the MMAs per chunk stay >= 18.
+        max_kc = min(max_kc, 32)
     xf_cs = 0
     if osy == 1 and osx == 1 and not out0_s2d and not fold_cs and act_kind in (0, 1) and not act_pre:
         xf = xf_taps(name, segs, phase_taps, cout, pair, hg, wg)

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+import parity
 from oracle import emulate, nets
 from stcd_b200 import changeformer, synth
 
@@ -28,6 +29,9 @@ def _check(ys, refs, tol=BF16_TOL):
     agree = (y[:, 1] > y[:, 0]) == (ref[:, 1] > ref[:, 0])
     assert agree[margin > BF16_TOL].float().mean().item() >= 0.999
     assert agree.float().mean().item() >= 0.97
+    # recorded for the parity table (tests/parity.py); relative bounds for a deep bf16 net (see tests/test_gpu_segcd.py)
+    r = parity.report("%s:full-res logits" % "changeformer_v6", y, ref, "argmax")
+    assert r["rms_over_std"] <= 0.04 and r["max_over_std"] <= 0.25, r
 
 
 def test_forward_matches_oracle_and_emulator():

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+import parity
 from oracle import emulate, nets
 from stcd_b200 import segcd, synth
 from stcd_b200.metric import SegmentationMetric
@@ -19,11 +20,20 @@ def _net(name="resnet34"):
     return synth.prepare_(segcd.SegCD(name).eval(), "SegCD")
 
 
-def _check(ys, refs):
+def _check(ys, refs, tag="segcd"):
+    """The masks m1 / m2 are held to the shared relative criteria (tests/parity.py); the logit spread is NOT raised to 0.25 for
+    this family: ~50 fused bf16 layers put the rms error at ~2 % of the spread (oracle/emulate.py reproduces it on the CPU),
+    so 2e-2 absolute only holds up to a spread of ~0.15, and `change` = min(head(|d1 - d2|), |m1 - m2|) is a DIFFERENCE of two
+    nearly equal Siamese outputs whose error is that of the masks against a spread half as wide.  Users who need more take
+    the split-precision path (precision="tf32")."""
     assert len(ys) == 3
-    for y, ref in zip(ys, refs):
+    for k, (y, ref) in enumerate(zip(ys, refs)):
         assert y.shape == ref.shape and y.dtype == torch.float32
         assert (y.cpu() - ref).abs().max().item() < BF16_TOL
+        r = parity.report(f"{tag}:{('m1', 'm2', 'change')[k]}", y, ref, "sigmoid")
+        if k < 2:
+            assert r["rms_over_std"] <= 0.03 and r["max_over_std"] <= 0.16, r
+            assert r["agree_decided"] >= 0.999 and r["agree_all"] >= 0.99, r
     change, ref = ys[2].cpu(), refs[2]
     agree = (change > 0) == (ref > 0)
     assert agree[ref.abs() > BF16_TOL].float().mean().item() >= 0.999
@@ -93,6 +103,24 @@ def test_layerwise_against_emulator():
         worst[name] = ((got - keep[name]).abs().mean() / (keep[name].abs().mean() + 1e-6)).item()
     bad = {k: v for k, v in worst.items() if v > 1e-2}
     assert not bad, bad
+
+
+def test_config_c3_full_batch_chunk16_vs_oracle():
+    """Config C3 exactly as bench.py runs it: 16 tiles of 1024x1024 in ONE chunk of 16, compared with the fp32 oracle on four
+    pairs drawn from different positions of the chunk."""
+    net = _net()
+    x1, x2 = synth.image_pairs(16, 1024, 1024)
+    idx = [0, 5, 10, 15]
+    with torch.no_grad():
+        ref = nets.segcd_forward(net.state_dict(), x1[idx], x2[idx])
+    net = net.cuda()
+    net.chunk_pairs = 16
+    ys = net(x1.cuda(), x2.cuda())
+    assert ys[2].shape == (16, 1, 1024, 1024)
+    _check([y[idx] for y in ys], ref, tag="segcd_r34:C3 16x1024x1024 chunk 16 (pairs 0,5,10,15 vs oracle)")
+    net.chunk_pairs = 4
+    ys4 = net(x1.cuda(), x2.cuda())
+    assert all(torch.equal(u, v) for u, v in zip(ys4, ys)), "outputs must not depend on the chunk size"
 
 
 def test_full_size_tile_and_properties():

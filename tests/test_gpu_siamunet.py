@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 
+import parity
 from oracle import emulate, nets
 from oracle.make_golden import CASES
 from stcd_b200 import siamunet, synth
@@ -46,8 +47,10 @@ def test_forward_matches_oracle_and_emulator(fusion):
     y = y.cpu()
     assert (y - emu).abs().max().item() < 1.5e-2, "kernel vs emulator (same rounding points; bf16 flips cascade)"
     assert (y - ref).abs().max().item() < BF16_TOL, "kernel vs fp32 oracle"
-    all_px, decided = _agreement(y, ref)
-    assert decided >= 0.999 and all_px >= 0.99
+    # absolute AND relative criteria, all-pixel and decided-pixel agreement (tests/parity.py); config C1's family additionally
+    # with a logit spread >= 0.25 so that the absolute bound cannot be met by small logits
+    r = parity.check(f"siamunet_{fusion}:5x64x96", y, ref, "argmax", min_std=0.25 if fusion == "diff" else 0.15)
+    assert r["agree_decided"] >= 0.999 and r["agree_all"] >= 0.995
 
 
 _FUSION = {"siamunet_diff": "diff", "siamunet_conc": "conc", "siamunet_sub": "sub", "siamunet_crossconc": "cross", "unet_ef": "ef"}
@@ -65,6 +68,7 @@ def test_forward_matches_golden(case, golden_dir):
     ref = torch.from_numpy(g["out0"])
     assert (y - ref).abs().max().item() < BF16_TOL
     assert _agreement(y, ref)[1] >= 0.999
+    parity.check(f"golden:{case}", y, ref, "argmax", min_std=0.15, all_px=0.99)
 
 
 def test_full_size_config_c1_and_host_path():
@@ -78,6 +82,7 @@ def test_full_size_config_c1_and_host_path():
     net = net.cuda()
     y = net(x1.cuda(), x2.cuda())
     assert (y[:2].cpu() - ref).abs().max().item() < BF16_TOL
+    parity.check("siamunet_diff:C1 8x256x256 (pairs 0-1 vs oracle)", y[:2], ref, "argmax")
     y2 = net(x1.cuda(), x2.cuda())
     assert torch.equal(y, y2), "forward must be deterministic"
     perm = torch.tensor([3, 1, 7, 0, 2, 6, 5, 4])

@@ -30,3 +30,18 @@ for _ in range(reps):
 torch.cuda.synchronize()
 y = y[-1] if isinstance(y, (tuple, list)) else y
 print("ok", float(y.abs().mean()))
+if os.environ.get("STCD_DUMP_OPS"):          # op list in launch order, for tools/ncu_layers.py
+    import json
+    from stcd_b200 import lowering as L
+    plan = net.plan_for(x1)
+    ops = []
+    for op in plan.prog.ops:
+        kernels = 1
+        if isinstance(op, L.EcamHeadSpec):
+            kernels = 2
+        elif isinstance(op, L.GraphConvSpec):
+            kernels = 4 + (2 if op.r > 1 else 0)
+        ops.append({"name": op.name, "type": type(op).__name__, "kernels": kernels,
+                    "bytes_per_pair": int(L.op_bytes_per_pair(plan.prog, op)), "macs_per_pair": int(getattr(op, "macs_per_pair", 0)),
+                    "n_tile": getattr(op, "n_tile", 0), "xf_cs": getattr(op, "xf_cs", 0), "fold_cs": getattr(op, "fold_cs", 0)})
+    json.dump({"net": name, "pairs": pairs, "chunk": chunk, "h": H, "ops": ops}, open(os.environ["STCD_DUMP_OPS"], "w"))
