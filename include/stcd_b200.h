@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define STCD_ABI_VERSION 17
+#define STCD_ABI_VERSION 18
 
 enum stcd_status {
   STCD_OK = 0,
@@ -167,6 +167,13 @@ typedef struct stcd_conv_desc {
    * blocks across neighbouring pixels.  Tiles are 8 x 16 input positions with 14 output columns (the library's choice;
    * hg / wg stay the output dims).  Single phase, stride-1 sources, osy = osx = 1, no space-to-depth / folded store. */
   int32_t xf_cs;
+  /* Split precision (the tolerance class the north star calls "tf32": logits within 1e-3 of the fp32 reference; the reference
+   * itself computes in fp32, models/SNUNet.py:116-152).  split = 1: every bf16 tensor this op touches stores 2x its logical
+   * channels -- a hi plane bf16(v) in channel groups [0, c8/2) and a lo plane bf16(v - hi) in [c8/2, c8) -- the K-program
+   * (built by the host) reads each logical source as the three segments (hi, lo, hi) against the weights (Whi, Whi, Wlo), the
+   * epilogue writes both planes of out0 / out_raw / out_pool / out_diff and reads the residual as hi + lo.  Not combined
+   * with out0_s2d, fold_cs or xf_cs. */
+  int32_t split;
 } stcd_conv_desc;
 
 /* returns op index >= 0, or <0 */
@@ -176,6 +183,10 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* desc);
  * -> bf16 [2*chunk][2][h][w][8] (cin <= 8 real channels, 16 stored) with the T1 images first, then
  * the T2 images. */
 int stcd_plan_add_input_pack(stcd_plan* plan, int dst_tensor, int cin);
+
+/* Split-precision variant (see stcd_conv_desc.split): dst has 16 stored channels, [0, 8) = bf16(x), [8, 16) = bf16(x - bf16(x));
+ * cin <= 8. */
+int stcd_plan_add_input_pack_split(stcd_plan* plan, int dst_tensor, int cin);
 
 /* Space-to-depth variant for the 7x7 stride-2 ResNet stem (smp/encoders/resnet.py:50): x1, x2 fp32 NCHW
  * [n_pairs, cin, 2h, 2w] -> bf16 [2*chunk][2][h][w][8] with channel (py*2 + px)*cin + c holding
@@ -317,6 +328,7 @@ typedef struct stcd_ecam_desc {
   const float* w_final;
   const float* b_final;
   int32_t out_ext;
+  int32_t split;      /* split precision: each source stores 2c channels (hi plane, lo plane) and is read as hi + lo */
 } stcd_ecam_desc;
 int stcd_plan_add_ecam_head(stcd_plan* plan, const stcd_ecam_desc* desc);
 

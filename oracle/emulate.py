@@ -20,6 +20,26 @@ def _bf16(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).to(torch.float32)
 
 
+def _store(T: Dict[str, torch.Tensor], name: str, idx, coff: int, v: torch.Tensor, split: bool) -> None:
+    """Store logical channels v[..., :c] at channel offset `coff` of tensor `name`: one bf16 value per element, or (split
+    precision) hi = bf16(v) in the hi plane and lo = bf16(v - hi) in the lo plane (second half of the stored channels)."""
+    c = v.shape[-1]
+    hi = _bf16(v)
+    T[name][idx + (slice(coff, coff + c),)] = hi
+    if split:
+        half = T[name].shape[-1] // 2
+        T[name][idx + (slice(half + coff, half + coff + c),)] = _bf16(v - hi)
+
+
+def _load(T: Dict[str, torch.Tensor], name: str, idx, c: int, split: bool) -> torch.Tensor:
+    t = T[name]
+    v = t[idx + (slice(0, c),)]
+    if split:
+        half = t.shape[-1] // 2
+        v = v + t[idx + (slice(half, half + c),)]
+    return v
+
+
 def _gather(src: torch.Tensor, rows: torch.Tensor, cols: torch.Tensor) -> torch.Tensor:
     """src [N,h,w,c]; rows [hg], cols [wg] (may be out of range -> zeros, like TMA OOB fill)."""
     h, w = src.shape[1], src.shape[2]
@@ -91,17 +111,19 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
     if op.fold_cs:
         return
     vs = []
+    sp = bool(getattr(op, "split", False))
     for m in range(n_m):
         v = full[m] * scale + shift
         sl = slice(m * chunk, m * chunk + n_img)
+        every = (sl, slice(None), slice(None))
         if op.out_raw is not None:
-            T[op.out_raw][sl, :, :, : op.cout] = _bf16(v[..., : op.cout])
+            _store(T, op.out_raw, every, 0, v[..., : op.cout], sp)
         if op.scale2 is not None:
             if op.act_pre:
                 v = act(v)
             v = v * torch.from_numpy(op.scale2) + torch.from_numpy(op.shift2)
         if op.res is not None:
-            v[..., : op.cout] = v[..., : op.cout] + T[op.res][sl, :, :, : op.cout]
+            v[..., : op.cout] = v[..., : op.cout] + _load(T, op.res, every, op.cout, sp)
         if not op.act_pre:
             v = act(v)
         if op.out0 is not None and op.out0_s2d:
@@ -112,7 +134,7 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
                     k = (py * 2 + px) * op.cout
                     T[op.out0][sl, :, :, k: k + op.cout] = q[:, py::2, px::2]
         elif op.out0 is not None:
-            T[op.out0][sl, :, :, op.out0_coff: op.out0_coff + op.cout] = _bf16(v[..., : op.cout])
+            _store(T, op.out0, every, op.out0_coff, v[..., : op.cout], sp)
         if op.out_ext >= 0:
             o = v[:n_valid, :, :, : op.cout].permute(0, 3, 1, 2)
             if len(op.phases) == op.osy * op.osx:
@@ -123,10 +145,10 @@ def run_conv(op: L.ConvSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[t
         if op.out_pool is not None:
             q = torch.maximum(torch.maximum(v[:, 0::2, 0::2], v[:, 0::2, 1::2]),
                               torch.maximum(v[:, 1::2, 0::2], v[:, 1::2, 1::2]))
-            T[op.out_pool][sl, :, :, : op.cout] = _bf16(q[..., : op.cout])
+            _store(T, op.out_pool, every, 0, q[..., : op.cout], sp)
         vs.append(v)
     if op.out_diff is not None:
-        T[op.out_diff][:n_img, :, :, : op.cout] = _bf16((vs[0] - vs[1]).abs()[..., : op.cout])
+        _store(T, op.out_diff, (slice(0, n_img), slice(None), slice(None)), 0, (vs[0] - vs[1]).abs()[..., : op.cout], sp)
 
 
 def normalize_u8(img: torch.Tensor, mean, std) -> torch.Tensor:
@@ -164,9 +186,9 @@ def run_program(prog: L.Program, x1: torch.Tensor, x2: torch.Tensor, chunk: int 
                             k = (py * 2 + px) * op.cin
                             dst[s_ * chunk: s_ * chunk + nv, :, :, k: k + op.cin] = v[:, py::2, px::2]
             elif isinstance(op, L.InputPackSpec):
-                dst = T[op.dst]
-                dst[:nv, :, :, : op.cin] = _bf16(x1[start: start + nv].permute(0, 2, 3, 1))
-                dst[chunk: chunk + nv, :, :, : op.cin] = _bf16(x2[start: start + nv].permute(0, 2, 3, 1))
+                every = (slice(None), slice(None))
+                _store(T, op.dst, (slice(0, nv),) + every, 0, x1[start: start + nv].permute(0, 2, 3, 1), op.split)
+                _store(T, op.dst, (slice(chunk, chunk + nv),) + every, 0, x2[start: start + nv].permute(0, 2, 3, 1), op.split)
             elif isinstance(op, L.ConvSpec):
                 run_conv(op, T, chunk, ext, nv)
             else:
@@ -181,7 +203,7 @@ def run_program(prog: L.Program, x1: torch.Tensor, x2: torch.Tensor, chunk: int 
 def run_ecam_head(op: L.EcamHeadSpec, T: Dict[str, torch.Tensor], chunk: int, ext: List[torch.Tensor], nv: int) -> None:
     """csrc/aux_kernels.cuh ecam_stats_kernel + ecam_head_kernel: fp32 reductions over the bf16 level-0
     tensors, fp32 MLPs, then a per-image 1x1 head (models/SNUNet.py:144-149)."""
-    xs = [T[s][:chunk] for s in op.srcs]                    # [chunk, h, w, C]
+    xs = [_load(T, s, (slice(0, chunk), slice(None), slice(None)), op.c, op.split) for s in op.srcs]      # [chunk, h, w, C]
     out = torch.cat(xs, 3)                                  # [chunk, h, w, 4C]
     intra = xs[0] + xs[1] + xs[2] + xs[3]
 

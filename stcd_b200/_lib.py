@@ -145,6 +145,7 @@ class ConvDesc(C.Structure):
         ("fold_cs", C.c_int32), ("fold_cout", C.c_int32),
         ("act_pre", C.c_int32), ("act_alpha", C.c_float),
         ("xf_cs", C.c_int32),
+        ("split", C.c_int32),
     ]
 
 
@@ -169,10 +170,11 @@ class EcamDesc(C.Structure):
         ("ca1_fc1", C.POINTER(C.c_float)), ("ca1_fc2", C.POINTER(C.c_float)),
         ("w_final", C.POINTER(C.c_float)), ("b_final", C.POINTER(C.c_float)),
         ("out_ext", C.c_int32),
+        ("split", C.c_int32),
     ]
 
 
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 # every symbol include/stcd_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
@@ -184,6 +186,7 @@ SYMBOLS = [
     ("stcd_plan_add_tensor", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("stcd_plan_add_conv", C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
     ("stcd_plan_add_input_pack", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("stcd_plan_add_input_pack_split", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("stcd_plan_add_input_pack_s2d", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("stcd_plan_add_input_pack_u8", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     ("stcd_plan_add_maxpool_s2d", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),

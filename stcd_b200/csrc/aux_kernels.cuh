@@ -30,7 +30,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // pixel chunk per channel group (a warp writes 512 contiguous bytes).
 __global__ void __launch_bounds__(256) input_pack_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
                                                          __nv_bfloat16* __restrict__ dst, int chunk, int n_valid,
-                                                         int cin, int c8, int hw) {
+                                                         int cin, int c8, int hw, int split) {
   const size_t total = static_cast<size_t>(2) * chunk * hw;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -45,6 +45,10 @@ __global__ void __launch_bounds__(256) input_pack_kernel(const float* __restrict
 #pragma unroll
       for (int c = 0; c < 16; ++c)
         if (c < cin) v[c] = __ldg(src + static_cast<size_t>(c) * hw);
+      if (split) {     // split precision: channels [8, 16) hold the lo parts x - bf16(x) of channels [0, 8)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[8 + c] = v[c] - __bfloat162float(__float2bfloat16_rn(v[c]));
+      }
     }
     uint32_t w[8];
 #pragma unroll
@@ -366,6 +370,7 @@ struct EcamParams {
   const float* w_final;  // [n_class][4C]
   const float* b_final;  // [n_class]
   float* out;            // fp32 NCHW [n_valid][n_class][hw]
+  int32_t split;         // split precision: every source holds 2 * c/8 channel groups (hi plane, lo plane); value = hi + lo
 };
 
 __device__ __forceinline__ void unpack8_bf16_f(uint4 q, float* v) {
@@ -713,7 +718,9 @@ __global__ void __launch_bounds__(256) ecam_stats_kernel(const EcamParams p) {
       s[k][j] = 0.f;
       m[k][j] = -INFINITY;
     }
-  const size_t base = (static_cast<size_t>(n) * (p.c >> 3) + g) * p.hw;
+  const int c8s = (p.c >> 3) * (p.split ? 2 : 1);     // stored channel groups per source
+  const size_t base = (static_cast<size_t>(n) * c8s + g) * p.hw;
+  const size_t lo_off = static_cast<size_t>(p.c >> 3) * p.hw * 8;
   for (int px = p0 + threadIdx.x; px < p1; px += blockDim.x) {
     float it[8];
 #pragma unroll
@@ -722,6 +729,12 @@ __global__ void __launch_bounds__(256) ecam_stats_kernel(const EcamParams p) {
     for (int k = 0; k < 4; ++k) {
       float v[8];
       unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(p.src[k] + (base + px) * 8)), v);
+      if (p.split) {
+        float lo[8];
+        unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(p.src[k] + (base + px) * 8 + lo_off)), lo);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += lo[j];
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s[k][j] += v[j];
@@ -841,7 +854,14 @@ __global__ void __launch_bounds__(256) ecam_head_kernel(const EcamParams p) {
     for (int k = 0; k < 4; ++k) {
       for (int g = 0; g < g8; ++g) {
         float v[8];
-        unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(p.src[k] + ((static_cast<size_t>(n) * g8 + g) * p.hw + px) * 8)), v);
+        const size_t at = ((static_cast<size_t>(n) * (p.split ? 2 * g8 : g8) + g) * p.hw + px) * 8;
+        unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(p.src[k] + at)), v);
+        if (p.split) {     // value = hi plane + lo plane
+          float lo[8];
+          unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(p.src[k] + at + static_cast<size_t>(g8) * p.hw * 8)), lo);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += lo[j];
+        }
         const int ch = k * c + g * 8;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

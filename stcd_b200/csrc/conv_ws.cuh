@@ -44,7 +44,7 @@ constexpr int kMaxPhase = 4;
 constexpr int kMaxAStages = 8;
 constexpr int kMaxWStages = 16;
 constexpr int kMaxChunks = 128;  // A-stage loads per phase
-constexpr int kMaxTaps = 320;    // weight blocks per phase
+constexpr int kMaxTaps = 512;    // weight blocks per phase (split precision triples the K-program: 1024 channels x 9 taps / 64 x 3 = 432)
 constexpr int kConvThreads = 224;
 constexpr int kFastMma = 36;     // per-chunk MMA offsets kept in the constant bank (9 taps x 4 K steps)
 constexpr int kMaxRSlots = 4;    // residual tiles in flight (TMA -> shared-memory ring)
@@ -132,6 +132,10 @@ struct ConvParams {
   uint32_t res_slot_bytes, res_sub_bytes;  // ring slot = MT sub-tiles of [res_ch/8][tile rows][tile px][8] bf16
   int32_t res_ch;                          // channels per residual box (n_tile; cs for E_XF)
   int32_t xf_cs;                           // E_XF: column-block stride cs (n_tile = 3 * cs); 0 otherwise
+  // Split precision (the "tf32" tolerance class; generic instances only).  Every bf16 tensor holds a hi plane (channel groups
+  // [0, c8/2)) and a lo plane ([c8/2, c8)): hi = bf16(v), lo = bf16(v - hi).  The K-program already reads (hi, lo, hi) against
+  // (Whi, Whi, Wlo); the epilogue writes both planes of every bf16 output and reads the residual as hi + lo.
+  int32_t split;
   __nv_bfloat16* out0;
   int32_t out0_c8, out0_coff;
   int32_t reverse;   // 1: walk the tiles last-to-first (consecutive layers alternate, so a layer starts on the lines its producer wrote last: L2 hits)
@@ -164,6 +168,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
   return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+// lo part of the split representation of 8 values: bf16(v - float(bf16(v)))
+__device__ __forceinline__ uint4 pack8_bf16_lo(const float* v) {
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+  return pack8_bf16(r);
 }
 __device__ __forceinline__ void unpack8_bf16(uint4 q, float* v) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -567,8 +578,19 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     const bool has_raw = STCD_HAS(E_RAW, p.out_raw != nullptr);
     const bool has_aff2 = STCD_HAS(E_AFF2, p.scale2 != nullptr);
     const bool has_res = STCD_HAS(E_RES, p.res != nullptr);
+    const bool split = (EPI & E_GENERIC) != 0 && p.split != 0;         // split precision: generic instances only
     const bool res_sm = has_res && STCD_HAS(E_RSM, p.res_slots > 0);   // residual tile in the shared-memory ring
-    const bool res_rg = has_res && !res_sm;                            // residual through per-thread global loads
+    const bool res_rg = has_res && !res_sm && !split;                  // residual through prefetched per-thread global loads
+    // 16 values -> the hi plane at `o` (two 8-channel groups `plane` elements apart) and, in split precision, the lo plane
+    // `lo_off` elements further
+    auto store16 = [&](__nv_bfloat16* o, size_t plane, size_t lo_off, const float* x, bool both) {
+      *reinterpret_cast<uint4*>(o) = pack8_bf16(x);
+      if (both) *reinterpret_cast<uint4*>(o + plane) = pack8_bf16(x + 8);
+      if (split) {
+        *reinterpret_cast<uint4*>(o + lo_off) = pack8_bf16_lo(x);
+        if (both) *reinterpret_cast<uint4*>(o + lo_off + plane) = pack8_bf16_lo(x + 8);
+      }
+    };
     const bool has_relu = STCD_HAS(E_RELU, p.relu != 0);
     const bool has_out0 = STCD_HAS(E_OUT0, p.out0 != nullptr);
     const bool has_pool = STCD_HAS(E_POOL, p.out_pool != nullptr);
@@ -596,7 +618,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
 
     // the residual is prefetched ahead of the accumulator wait, so this role reads global memory
     // written by the previous kernel without going through the A producer's dependency wait
-    if (res_rg) pdl_wait();
+    if (res_rg || (has_res && split)) pdl_wait();
     const int wq = warp & 3;  // TMEM lane quarter this warp may access
     // pixel of the tile this thread (= TMEM lane 32 * wq + lane) owns: 4 lines of 8 per warp, or (XF) 2 lines of 16
     const int ty = XF ? 2 * wq + (lane >> 4) : 4 * wq + (lane >> 3);
@@ -784,8 +806,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             }
             if (has_raw && valid) {
               __nv_bfloat16* o = q_raw + (im[m] * p.out_raw_c8 + g8) * hw * 8;
-              *reinterpret_cast<uint4*>(o) = pack8_bf16(v[m]);
-              if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(v[m] + 8);
+              store16(o, static_cast<size_t>(hw) * 8, static_cast<size_t>(p.out_raw_c8 >> 1) * hw * 8, v[m], two);
             }
             if (has_aff2) {
               if (act_pre) apply_act(v[m]);
@@ -800,7 +821,21 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
               r_cur[m][0] = rt[0];
               r_cur[m][1] = rt[TH * TW];
             }
-            if (has_res && valid) {
+            if (has_res && valid && split) {
+              // residual = hi + lo, read where it is needed (the precision path is not the throughput path)
+              const __nv_bfloat16* r = p.res + ((im[m] * p.res_c8 + cg8 + g8) * hw + pix) * 8;
+              const size_t lo_off = static_cast<size_t>(p.res_c8 >> 1) * hw * 8;
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                if (half == 0 || two) {
+                  float a[8], b[8];
+                  unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(r + half * static_cast<size_t>(hw) * 8)), a);
+                  unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(r + half * static_cast<size_t>(hw) * 8 + lo_off)), b);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[m][8 * half + j] += a[j] + b[j];
+                }
+              }
+            } else if (has_res && valid) {
               float rv[16];
               unpack8_bf16(r_cur[m][0], rv);
               unpack8_bf16(r_cur[m][1], rv + 8);
@@ -815,7 +850,24 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
                 for (int j = 0; j < nv; ++j) o[static_cast<size_t>(j) * hw] = v[m][j];
               }
             }
-            if (has_out0 || has_pool) {
+            if ((has_out0 || has_pool) && split) {
+              if (has_out0 && valid) {
+                __nv_bfloat16* o = q_out0 + (im[m] * p.out0_c8 + g8) * hw0 * 8;
+                store16(o, static_cast<size_t>(hw0) * 8, static_cast<size_t>(p.out0_c8 >> 1) * hw0 * 8, v[m], two);
+              }
+              if (has_pool) {
+                float vp[16];      // the pooled value must be formed in fp32: max does not commute with the (hi, lo) split
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  float a = fmaxf(v[m][j], __shfl_down_sync(0xffffffffu, v[m][j], 1));
+                  vp[j] = fmaxf(a, __shfl_down_sync(0xffffffffu, a, XF ? 16 : 8));
+                }
+                if (valid && (XF ? ((lane & 17) == 1) : ((lane & 9) == 0))) {
+                  __nv_bfloat16* o = q_pool + (im[m] * p.out_pool_c8 + g8) * hw_pool * 8;
+                  store16(o, static_cast<size_t>(hw_pool) * 8, static_cast<size_t>(p.out_pool_c8 >> 1) * hw_pool * 8, vp, two);
+                }
+              }
+            } else if (has_out0 || has_pool) {
               const uint4 lo = pack8_bf16(v[m]), hi = pack8_bf16(v[m] + 8);
               if (has_out0 && valid) {
                 if (p.fold_cs) {
@@ -852,8 +904,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < 16; ++j) d[j] = fabsf(v[0][j] - v[MS - 1][j]);
             __nv_bfloat16* o = q_diff + (im[0] * p.out_diff_c8 + g8) * hw * 8;
-            *reinterpret_cast<uint4*>(o) = pack8_bf16(d);
-            if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = pack8_bf16(d + 8);
+            store16(o, static_cast<size_t>(hw) * 8, static_cast<size_t>(p.out_diff_c8 >> 1) * hw * 8, d, two);
           }
           if (res_rg) {
             const int nstep = (c0 >> 4) + 1;               // steps 1 .. PF-1 were prefetched with step 0

@@ -92,6 +92,7 @@ struct PackOp {
   int s2d = 0;
   int u8 = 0;                 // inputs are uint8 HWC, normalised in the pack kernel
   stcd::NormParams norm;
+  int split = 0;              // split precision: channels [8, 16) = lo parts of channels [0, 8)
 };
 
 struct PoolOp {
@@ -629,7 +630,7 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
           default: stcd::input_pack_s2d_kernel<4><<<blocks, 256, 0, st>>>(x1, x2, dp, plan->chunk, n_valid, t.h, t.w); break;
         }
       } else
-        stcd::input_pack_kernel<<<blocks, 256, 0, st>>>(x1, x2, (__nv_bfloat16*)t.ptr, plan->chunk, n_valid, k.cin, t.c / 8, hw);
+        stcd::input_pack_kernel<<<blocks, 256, 0, st>>>(x1, x2, (__nv_bfloat16*)t.ptr, plan->chunk, n_valid, k.cin, t.c / 8, hw, k.split);
       CUDA_TRY(cudaGetLastError());
     }
     ++op_i;
@@ -798,6 +799,24 @@ int stcd_plan_add_input_pack(stcd_plan* plan, int dst_tensor, int cin) {
     return -fail(STCD_ERR_INVALID, "input pack needs a [2*chunk][1 or 2][h][w][8] tensor and cin <= its channels (got mult=%d c=%d cin=%d)",
                  t.mult, t.c, cin);
   plan->packs.push_back({dst_tensor, cin});
+  plan->ops.push_back({1, (int)plan->packs.size() - 1});
+  plan->in_c = cin;
+  plan->in_h = t.h;
+  plan->in_w = t.w;
+  return (int)plan->ops.size() - 1;
+}
+
+int stcd_plan_add_input_pack_split(stcd_plan* plan, int dst_tensor, int cin) {
+  if (!plan) return -fail(STCD_ERR_STATE, "plan is NULL");
+  if (plan->finalized) return -fail(STCD_ERR_STATE, "plan already finalized");
+  if (!valid_tensor(plan, dst_tensor)) return -fail(STCD_ERR_INVALID, "bad dst tensor %d", dst_tensor);
+  const Tensor& t = plan->tensors[dst_tensor];
+  if (t.mult != 2 || t.c != 16 || cin < 1 || cin > 8)
+    return -fail(STCD_ERR_INVALID, "split input pack needs a [2*chunk][2][h][w][8] tensor (hi plane, lo plane) and cin <= 8 (got mult=%d c=%d cin=%d)",
+                 t.mult, t.c, cin);
+  PackOp k{dst_tensor, cin};
+  k.split = 1;
+  plan->packs.push_back(k);
   plan->ops.push_back({1, (int)plan->packs.size() - 1});
   plan->in_c = cin;
   plan->in_h = t.h;
@@ -1238,6 +1257,8 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
   if (2 * mt * d->n_tile > 512)
     return -fail(STCD_ERR_INVALID, "double-buffered accumulators need %d TMEM columns (> 512)", 2 * mt * d->n_tile);
   if (d->pair && (plan->chunk < 1)) return -fail(STCD_ERR_INVALID, "pair op on an empty chunk");
+  if (d->split && (d->out0_s2d || d->fold_cs || d->xf_cs || d->relu > 1 || d->act_pre))
+    return -fail(STCD_ERR_INVALID, "split precision: plain / ReLU epilogues only (no space-to-depth, folded or horizontally folded stores)");
   if (d->xf_cs) {
     bool ok = d->xf_cs >= 16 && d->xf_cs % 16 == 0 && d->n_tile == 3 * d->xf_cs && d->cout_pad == d->n_tile && d->cout <= d->xf_cs &&
               d->n_phase == 1 && d->osy == 1 && d->osx == 1 && !d->out0_s2d && !d->fold_cs;
@@ -1277,7 +1298,9 @@ int stcd_plan_add_conv(stcd_plan* plan, const stcd_conv_desc* d) {
     if (id < 0) return 0;
     if (!valid_tensor(plan, id)) return fail(STCD_ERR_INVALID, "bad %s tensor %d", name, id);
     const Tensor& t = plan->tensors[id];
-    if (t.h != hh || t.w != ww || t.c < coff + (d->fold_cs ? d->fold_cout : d->cout) || t.mult != mult)
+    if (d->split && (t.c % 16))
+      return fail(STCD_ERR_INVALID, "split precision: %s tensor %d needs a hi and a lo plane (channels %d not a multiple of 16)", name, id, t.c);
+    if (t.h != hh || t.w != ww || (d->split ? t.c / 2 : t.c) < coff + (d->fold_cs ? d->fold_cout : d->cout) || t.mult != mult)
       return fail(STCD_ERR_INVALID, "%s tensor %d is [%d*chunk,%d,%d,%d], op writes [%d*chunk,%d,%d,%d+%d]", name, id,
                   t.mult, t.h, t.w, t.c, mult, hh, ww, coff, d->cout);
     return 0;
@@ -1377,7 +1400,7 @@ int stcd_plan_add_ecam_head(stcd_plan* plan, const stcd_ecam_desc* d) {
   for (int k = 0; k < 4; ++k) {
     if (!valid_tensor(plan, d->src[k])) return -fail(STCD_ERR_INVALID, "ecam head: bad src tensor %d", d->src[k]);
     const Tensor& t = plan->tensors[d->src[k]];
-    if (t.mult != 1 || t.c != d->c || (k && (t.h != h || t.w != w)))
+    if (t.mult != 1 || t.c != (d->split ? 2 : 1) * d->c || (k && (t.h != h || t.w != w)))
       return -fail(STCD_ERR_INVALID, "ecam head: src %d is [%d*chunk,%d,%d,%d], need [chunk,%d,%d,%d]", k, t.mult, t.h, t.w, t.c, h, w, d->c);
     h = t.h;
     w = t.w;
@@ -1659,7 +1682,8 @@ int stcd_plan_finalize(stcd_plan* plan) {
     // ---- residual ring: the pass's residual tiles arrive by TMA, up to kMaxRSlots passes ahead, when the ring fits beside
     // >= 2 (3 when there is room) A stages; else the epilogue loads the residual itself
     p.res_slots = 0;
-    if (d.res >= 0 && d.n_phase == 1 && d.osy == 1 && d.osx == 1 && env_int("STCD_RES_SMEM", 1)) {
+    p.split = d.split ? 1 : 0;
+    if (d.res >= 0 && d.n_phase == 1 && d.osy == 1 && d.osx == 1 && !d.split && env_int("STCD_RES_SMEM", 1)) {
       const Tensor& tr = plan->tensors[d.res];
       p.res_ch = xf ? d.xf_cs : d.n_tile;
       const size_t sub = (size_t)p.res_ch * tile_h * tile_w * 2;                   // [res_ch / 8][tile rows][tile px][8] bf16
@@ -1709,7 +1733,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
              (d.out_diff >= 0 ? stcd::E_DIFF : 0u) | (d.out_ext >= 0 ? stcd::E_F32 : 0u) |
              ((d.relu >= 2 || d.act_pre) ? stcd::E_ACTX : 0u) | (p.res_slots ? stcd::E_RSM : 0u) | (xf ? stcd::E_XF : 0u);
     op.fn = nullptr;
-    for (int i = 0; i < n_kernels && !force_generic; ++i)
+    for (int i = 0; i < n_kernels && !force_generic && !d.split; ++i)     // split precision lives in the generic instances
       if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == op.epi) op.fn = kernels[i].fn;
     for (int i = 0; i < n_kernels && !op.fn; ++i)
       if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == (stcd::E_GENERIC | (xf ? stcd::E_XF : 0u))) op.fn = kernels[i].fn;
@@ -1820,6 +1844,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
     memset(&q, 0, sizeof(q));
     for (int k = 0; k < 4; ++k) q.src[k] = (const __nv_bfloat16*)plan->tensors[d.src[k]].ptr;
     q.c = d.c;
+    q.split = d.split ? 1 : 0;
     q.hw = e.hw;
     q.n_img = plan->chunk;
     q.n_class = d.n_class;

@@ -24,7 +24,7 @@ import torch
 
 TILE_H, TILE_W = 16, 8
 MAX_SRC = 6
-MAX_CHUNKS, MAX_TAPS = 128, 320
+MAX_CHUNKS, MAX_TAPS = 128, 512
 
 
 def _bf16_bits(x: torch.Tensor) -> np.ndarray:
@@ -117,6 +117,9 @@ class ConvSpec:
     # stacks the row's three filter columns, n_tile = cout_pad = 3 * xf_cs; the epilogue sums the column blocks across
     # neighbouring pixels.  `cout` stays the real channel count.
     xf_cs: int = 0
+    # split precision: every bf16 output is written as (hi, lo) planes (lo plane at channel offset = half the tensor's stored
+    # channels) and the residual is read as hi + lo; the K-program already holds the (hi, lo, hi) x (Whi, Whi, Wlo) segments
+    split: bool = False
 
     def weight_block(self, nt: int, block: int) -> torch.Tensor:
         """fp32 [n_tile, kc] view of one packed weight block (for the emulator)."""
@@ -133,6 +136,7 @@ class InputPackSpec:
     # (mean, std) per channel: the plan's inputs are uint8 HWC images and the pack kernel applies the reference
     # loader's ToTensor + Normalize (data/dataset.py:196-203) before the bf16 rounding; None: fp32 NCHW inputs
     u8_norm: Optional[Tuple[Tuple[float, ...], Tuple[float, ...]]] = None
+    split: bool = False          # split precision: channels [0, 8) hold bf16(x), [8, 16) hold bf16(x - bf16(x))
 
 
 class SegTaps(list):
@@ -442,14 +446,33 @@ class Program:
     # constant tensors (e.g. a positional embedding added as a residual): name -> fp32 [h, w, c], replicated over
     # the images of the tensor when the plan is built
     consts: Dict[str, torch.Tensor] = field(default_factory=dict)
+    # "bf16": activations are single bf16 values (north star: logits within 2e-2).
+    # "split": the precision path the reference API calls tf32 (north star: logits within 1e-3).  Every activation and weight
+    # is carried as a (hi, lo) PAIR of bf16 values -- hi = bf16(v), lo = bf16(v - hi): 16 mantissa bits, against tf32's 11 --
+    # and every product as hi*hi + lo*hi + hi*lo in fp32 accumulators (the lo*lo term is below 2**-16 relative).  Plain
+    # kind::tf32 MMAs do NOT meet 1e-3 on these nets (measured with tf32-rounded operands on the oracle, logit std 0.42:
+    # max error 3.7e-3); the split form does (~6e-5), on the same bf16 tensor-core path: a tensor holds its hi plane in
+    # channels [0, C) and its lo plane in [C, 2C), a conv reads (hi, lo, hi) as three K segments with weights (Whi, Whi, Wlo)
+    # -- 3 bf16 MMAs per product where kind::tf32 would spend the time of 2, at the same 4 bytes per activation.
+    precision: str = "bf16"
+
+    @property
+    def split(self) -> bool:
+        return self.precision == "split"
 
     def tensor(self, name: str, mult: int, h: int, w: int, c: int) -> str:
+        """Declare an activation tensor of `c` logical channels (split precision: 2c stored, hi plane then lo plane)."""
         if name in self.tensors:
             raise ValueError(f"duplicate tensor {name}")
         if c % 8:
             raise ValueError(f"tensor {name}: channels {c} must be a multiple of 8")
-        self.tensors[name] = TensorSpec(name, mult, h, w, c)
+        self.tensors[name] = TensorSpec(name, mult, h, w, 2 * c if self.split else c)
         return name
+
+    def half(self, name: str) -> int:
+        """Logical channel count of a tensor (= the offset of its lo plane in split precision)."""
+        t = self.tensors[name]
+        return t.c // 2 if self.split else t.c
 
     def macs_per_pair(self) -> int:
         return sum(getattr(o, "macs_per_pair", 0) for o in self.ops)
@@ -852,6 +875,31 @@ def fold_phases(name: str, segs: Sequence[Segment], phase_taps, cout: int, osy: 
     return [(0, 0, folded)], cs, cost_f, cost_unf
 
 
+def _split_operands(prog: Program, name: str, segs: Sequence[Segment], phase_taps):
+    """Split precision: a * w  ->  a_hi * w_hi + a_lo * w_hi + a_hi * w_lo as three K segments per logical segment.
+
+    Segment s over tensor T (hi plane at channel s.c_off, lo plane at half(T) + s.c_off) becomes
+    (hi plane, W_hi), (lo plane, W_hi), (hi plane, W_lo) with W_hi = bf16(W), W_lo = W - W_hi (rounded to bf16 by the
+    weight packer).  Returns (segments, [(oy, ox, SegTaps)])."""
+    out_segs: List[Segment] = []
+    for s in segs:
+        half = prog.half(s.tensor)
+        store = (half - s.c_off) if s.c_store < 0 else s.c_store
+        hi = Segment(s.tensor, s.c_real, s.stream, s.sy, s.sx, s.c_off, store)
+        lo = Segment(s.tensor, s.c_real, s.stream, s.sy, s.sx, half + s.c_off, store)
+        out_segs += [hi, lo, hi]
+    out_taps = []
+    for (oy, ox, taps) in phase_taps:
+        per_seg = _split_taps(name, segs, taps)
+        st = SegTaps()
+        for t in per_seg:
+            w_hi = [(dy, dx, w.to(torch.bfloat16).to(torch.float32)) for (dy, dx, w) in t]
+            w_lo = [(dy, dx, w - wh) for (dy, dx, w), (_, _, wh) in zip(t, w_hi)]
+            st += [w_hi, list(w_hi), w_lo]
+        out_taps.append((oy, ox, st))
+    return out_segs, out_taps
+
+
 def add_conv(
     prog: Program,
     name: str,
@@ -891,6 +939,12 @@ def add_conv(
     relu = act_kind != 0          # the epilogue's "has activation" switch
     if act_pre and scale2 is None:
         raise ValueError(f"{name}: act_pre needs the second affine")
+    split = prog.split
+    if split:
+        if out0_s2d or act_kind not in (0, 1) or act_pre:
+            raise NotImplementedError(f"{name}: split precision covers the ReLU conv families (FC-Siam, SNUNet)")
+        fold = False                # folded / horizontally folded forms keep their specialised bf16 epilogues
+        segs, phase_taps = _split_operands(prog, name, segs, phase_taps)
     fold_cs = fold_cout = 0
     plain_out = (res is None and out_raw is None and out_pool is None and out_diff is None and out_ext < 0
                  and scale2 is None and not out0_s2d and out0 is not None)
@@ -919,13 +973,14 @@ def add_conv(
             phase_taps, cout, scale, shift = f_taps, osx * cs, sc, sh
     elif fold:
         raise ValueError(f"{name}: phase folding needs an up-sampling op whose only output is out0")
-    if res is not None and pair:
+    if res is not None and pair and cout <= 64:
         # Siamese-pair ops with a residual: a 64-channel chunk of both streams (2 x 23 KB per stage) leaves no room for the
         # residual ring beside resident 64 -> 64 weights (74 KB) -- the op fell back to per-thread residual loads and ran at
-        # 0.39 of the HBM roof (SNUNet conv1_0.conv2).  32-channel chunks halve the stage; the MMAs per chunk stay >= 18.
+        # 0.39 of the HBM roof (SNUNet conv1_0.conv2: 354 -> 298 us).  32-channel chunks halve the stage; the MMAs per chunk
+        # stay >= 18.  Wider layers stream their weights and lose with thinner chunks (conv2_0.conv2: 160 -> 248 us), so they keep 64.
         max_kc = min(max_kc, 32)
     xf_cs = 0
-    if osy == 1 and osx == 1 and not out0_s2d and not fold_cs and act_kind in (0, 1) and not act_pre:
+    if osy == 1 and osx == 1 and not out0_s2d and not fold_cs and act_kind in (0, 1) and not act_pre and not split:
         xf = xf_taps(name, segs, phase_taps, cout, pair, hg, wg)
         if xf is not None:
             xf_phase_taps, xf_cs = xf
@@ -945,7 +1000,7 @@ def add_conv(
         relu=relu, res=res, out0=out0, out0_coff=out0_coff, out_raw=out_raw, out_pool=out_pool,
         out_diff=out_diff, out_ext=out_ext, macs_per_pair=macs_per_pair, out0_s2d=out0_s2d,
         fold_cs=fold_cs, fold_cout=fold_cout, act_kind=act_kind, act_alpha=float(act_alpha), act_pre=act_pre,
-        xf_cs=xf_cs,
+        xf_cs=xf_cs, split=split,
     )
     prog.ops.append(spec)
     return spec
@@ -976,6 +1031,7 @@ class EcamHeadSpec:
     b_final: np.ndarray          # float32 [n_class]
     out_ext: int = 0
     macs_per_pair: int = 0
+    split: bool = False          # split precision: each source holds (hi, lo) planes, read as hi + lo
 
 
 # ------------------------------------------------------------------------------------------

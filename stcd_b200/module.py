@@ -24,6 +24,23 @@ from . import lowering as L
 class PlannedModule(nn.Module):
     #: image pairs per pass through the layer stack (one plan workspace holds this many)
     default_chunk_pairs = 32
+    #: families whose lowering implements the split-precision path (``precision = "tf32"``)
+    supports_precision_path = False
+    #: "bf16" (default; north star: logits within 2e-2 of the fp32 reference) or "tf32" (north star: within 1e-3).  The
+    #: reference computes in fp32 and its only numeric switch is cudnn.benchmark (train_stcd.py:59); "tf32" names the tolerance
+    #: class the north star asks for, served by split-bf16 operands (lowering.Program.precision: 16 mantissa bits per operand,
+    #: three bf16 MMAs per product) because plain tf32 MMAs miss 1e-3 on these nets.  Set it before the first forward or any
+    #: time after: plans are cached per precision.
+    precision = "bf16"
+
+    @property
+    def plan_precision(self) -> str:
+        """The lowering's name for the selected precision ("bf16" or "split")."""
+        if self.precision not in ("bf16", "tf32"):
+            raise ValueError(f"precision must be 'bf16' or 'tf32', got {self.precision!r}")
+        if self.precision == "tf32" and not self.supports_precision_path:
+            raise NotImplementedError(f"{type(self).__name__} has no 'tf32' precision path (implemented: the FC-Siam family and SNUNet-CD)")
+        return "split" if self.precision == "tf32" else "bf16"
 
     def __init__(self):
         super().__init__()
@@ -94,7 +111,7 @@ class PlannedModule(nn.Module):
             raise RuntimeError("stcd_b200 has no CPU path: move the module and its inputs to a B200 (cuda) device")
         chunk = max(1, min(int(self.chunk_pairs), int(x.shape[0])))
         h, w = (int(x.shape[1]), int(x.shape[2])) if u8_norm is not None else (int(x.shape[2]), int(x.shape[3]))
-        key = (x.device.index, h, w, chunk, u8_norm)
+        key = (x.device.index, h, w, chunk, u8_norm, self.plan_precision)
         if self._plans:
             if self._weights_fingerprint() != self._fp:     # weights were written since the plans were lowered
                 self.invalidate_plans()

@@ -117,10 +117,15 @@ def init_net(net, init_type="normal", init_gain=0.02, gpu_ids=[]):  # noqa: B006
 
 
 def define_G(args, init_type="normal", init_gain=0.02, gpu_ids=[]):  # noqa: B006
-    """models/networks.py:138-215."""
+    """models/networks.py:138-215.  One extension beside the reference's fields (net_G, n_class, embed_dim, img_size):
+    ``args.precision`` ("bf16" default | "tf32"), the north star's two tolerance classes (stcd_b200/module.py)."""
     name = args.net_G
     if name in _REGISTRY:
         net = _REGISTRY[name](args)
+        precision = getattr(args, "precision", None)
+        if precision is not None:
+            net.precision = precision
+            net.plan_precision          # raises here, not at the first forward, when the family has no such path
     elif name in _REFERENCE_ONLY:
         raise NotImplementedError("Generator model name [%s] is served by the reference only; stcd_b200 accelerates %s"
                                   % (name, sorted(_REGISTRY)))

@@ -51,6 +51,8 @@ class Plan:
             ids[name] = _lib.check_id(lib.stcd_plan_add_tensor(h, t.mult, t.h, t.w, t.c, 0), f"tensor {name}")
         self.tensor_ids = ids
         for op in prog.ops:
+            if isinstance(op, InputPackSpec) and op.u8_norm is not None and op.split:
+                raise NotImplementedError("split precision takes fp32 inputs (forward_uint8 is the bf16 path's loader fusion)")
             if isinstance(op, InputPackSpec) and op.u8_norm is not None:
                 mean = (C.c_float * op.cin)(*op.u8_norm[0][: op.cin])
                 std = (C.c_float * op.cin)(*op.u8_norm[1][: op.cin])
@@ -58,7 +60,9 @@ class Plan:
                               f"uint8 input pack {op.name}")
                 self.u8 = True
             elif isinstance(op, InputPackSpec):
-                add = lib.stcd_plan_add_input_pack_s2d if op.s2d else lib.stcd_plan_add_input_pack
+                if op.split and op.s2d:
+                    raise NotImplementedError("split precision has no space-to-depth input pack")
+                add = lib.stcd_plan_add_input_pack_split if op.split else (lib.stcd_plan_add_input_pack_s2d if op.s2d else lib.stcd_plan_add_input_pack)
                 _lib.check_id(add(h, ids[op.dst], op.cin), f"input pack {op.name}")
             elif isinstance(op, GraphConvSpec):
                 rp = None if op.relpos is None else np.ascontiguousarray(op.relpos, np.float32)
@@ -192,6 +196,7 @@ class Plan:
         d.out0_s2d = 1 if op.out0_s2d else 0
         d.fold_cs, d.fold_cout = op.fold_cs, op.fold_cout
         d.xf_cs = op.xf_cs
+        d.split = 1 if op.split else 0
         _lib.check_id(self.lib.stcd_plan_add_conv(self._h, C.byref(d)), f"conv {op.name}")
 
     def _add_ecam(self, op: EcamHeadSpec) -> None:
@@ -204,6 +209,7 @@ class Plan:
                 (op.ca_fc1, op.ca_fc2, op.ca1_fc1, op.ca1_fc2, op.w_final, op.b_final)]
         d.ca_fc1, d.ca_fc2, d.ca1_fc1, d.ca1_fc2, d.w_final, d.b_final = (_fptr(a) for a in keep)
         d.out_ext = op.out_ext
+        d.split = 1 if op.split else 0
         _lib.check_id(self.lib.stcd_plan_add_ecam_head(self._h, C.byref(d)), f"ecam head {op.name}")
 
     # ------------------------------------------------------------------ queries

@@ -63,6 +63,7 @@ class _CrossConc(nn.Module):
 
 class _SiamUnet(PlannedModule):
     fusion = "diff"
+    supports_precision_path = True
 
     def __init__(self, input_nbr: int, label_nbr: int):
         super().__init__()
@@ -88,7 +89,7 @@ class _SiamUnet(PlannedModule):
                 setattr(self, f"cross_conc{i + 1}", _CrossConc(2 * c, c))
 
     def lower(self, h: int, w: int) -> L.Program:
-        return lower_siamunet(self.state_dict(), self.fusion, self.input_nbr, self.label_nbr, h, w)
+        return lower_siamunet(self.state_dict(), self.fusion, self.input_nbr, self.label_nbr, h, w, precision=self.plan_precision)
 
     returns_list = False     # SiamUnet_sub / SiamUnet_cross_conc return [x11d] (SiamUnet_sub.py:177-180)
 
@@ -129,8 +130,8 @@ class Unet(_SiamUnet):
 
 
 # ------------------------------------------------------------------------------------------
-def lower_siamunet(sd: Dict[str, torch.Tensor], fusion: str, input_nbr: int, label_nbr: int, h: int, w: int
-                   ) -> L.Program:
+def lower_siamunet(sd: Dict[str, torch.Tensor], fusion: str, input_nbr: int, label_nbr: int, h: int, w: int,
+                   precision: str = "bf16") -> L.Program:
     """state_dict of the reference module -> fused-op Program (eval mode)."""
     if h % 16 or w % 16:
         # ReplicationPad2d (SiamUnet_diff.py:149) is a no-op exactly when H and W are multiples of 16
@@ -138,9 +139,11 @@ def lower_siamunet(sd: Dict[str, torch.Tensor], fusion: str, input_nbr: int, lab
     if input_nbr > 16:
         raise ValueError("input_nbr > 16 not supported by the input packer")
     sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
-    p = L.Program(model=f"SiamUnet_{fusion}", in_channels=input_nbr, h=h, w=w)
+    p = L.Program(model=f"SiamUnet_{fusion}", in_channels=input_nbr, h=h, w=w, precision=precision)
+    if p.split and input_nbr > 8:
+        raise NotImplementedError("split precision packs at most 8 input channels")
     p.tensor("in", 2, h, w, 8 if input_nbr <= 8 else 16)
-    p.ops.append(L.InputPackSpec("pack", "in", input_nbr))
+    p.ops.append(L.InputPackSpec("pack", "in", input_nbr, split=p.split))
 
     def bn_fold(name: str, cout: int):
         return L.fold_bn(sd[f"conv{name}.bias"], L.bn_params(sd, f"bn{name}"), cout)

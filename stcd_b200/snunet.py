@@ -60,6 +60,7 @@ class ChannelAttention(nn.Module):
 
 class SNUNet_ECAM(PlannedModule):
     """models/SNUNet.py:60-152."""
+    supports_precision_path = True
 
     def __init__(self, in_ch: int = 3, out_ch: int = 1):
         super().__init__()
@@ -101,7 +102,7 @@ class SNUNet_ECAM(PlannedModule):
                 nn.init.constant_(m.bias, 0)
 
     def lower(self, h: int, w: int) -> L.Program:
-        return lower_snunet(self.state_dict(), self.in_ch, self.out_ch, h, w)
+        return lower_snunet(self.state_dict(), self.in_ch, self.out_ch, h, w, precision=self.plan_precision)
 
     @torch.no_grad()
     def forward(self, xA: torch.Tensor, xB: torch.Tensor) -> torch.Tensor:
@@ -109,7 +110,7 @@ class SNUNet_ECAM(PlannedModule):
 
 
 # ------------------------------------------------------------------------------------------
-def lower_snunet(sd: Dict[str, torch.Tensor], in_ch: int, out_ch: int, h: int, w: int) -> L.Program:
+def lower_snunet(sd: Dict[str, torch.Tensor], in_ch: int, out_ch: int, h: int, w: int, precision: str = "bf16") -> L.Program:
     """state_dict of the reference SNUNet_ECAM -> fused-op Program (eval mode)."""
     if h % 16 or w % 16:
         raise ValueError(f"SNUNet lowering needs H and W divisible by 16 (got {h}x{w}): four 2x2 poolings")
@@ -119,9 +120,9 @@ def lower_snunet(sd: Dict[str, torch.Tensor], in_ch: int, out_ch: int, h: int, w
         raise ValueError("out_ch > 4 not supported by the fused ECAM head")
     sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items()}
     f = FILTERS
-    p = L.Program(model="SNUNet_ECAM", in_channels=in_ch, h=h, w=w)
+    p = L.Program(model="SNUNet_ECAM", in_channels=in_ch, h=h, w=w, precision=precision)
     p.tensor("in", 2, h, w, 8)
-    p.ops.append(L.InputPackSpec("pack", "in", in_ch))
+    p.ops.append(L.InputPackSpec("pack", "in", in_ch, split=p.split))
 
     def nested(name: str, segs: Sequence[L.Segment], cout: int, hh: int, ww: int, *, pair: bool,
                pool: Optional[str] = None) -> str:
@@ -198,6 +199,6 @@ def lower_snunet(sd: Dict[str, torch.Tensor], in_ch: int, out_ch: int, h: int, w
         ca1_fc2=sd["ca1.fc2.weight"].reshape(f[0], -1).numpy().astype(np.float32).copy(),
         w_final=sd["conv_final.weight"].reshape(out_ch, c4).numpy().astype(np.float32).copy(),
         b_final=sd["conv_final.bias"].numpy().astype(np.float32).copy(),
-        out_ext=0, macs_per_pair=h * w * c4 * out_ch))
+        out_ext=0, macs_per_pair=h * w * c4 * out_ch, split=p.split))
     p.ext.append(L.ExtOutput("logits", out_ch, h, w))
     return p

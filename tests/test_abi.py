@@ -68,13 +68,17 @@ _VALIDATE = [
     ("ChangeFormerV6", (3, 2, False, 256), 256, 256), ("ChangeGNNV1", (3, 2, False, 256), 256, 256),
     ("SiamUnet_diff", (3, 2), 256, 256), ("SNUNet_ECAM", (3, 2), 256, 256),
 ]
+_VALIDATE_SPLIT = [("SiamUnet_diff", (3, 2), 64, 64), ("SiamUnet_conc", (3, 2), 64, 64), ("SNUNet_ECAM", (3, 2), 64, 96),
+                   ("SiamUnet_diff", (3, 2), 256, 256), ("SNUNet_ECAM", (3, 2), 256, 256)]
 
 
-@pytest.mark.parametrize("name,args,h,w", _VALIDATE, ids=[f"{n}-{h}x{w}" for n, _, h, w in _VALIDATE])
-def test_lowered_programs_pass_the_library_checks(name, args, h, w):
+@pytest.mark.parametrize("name,args,h,w,precision", [v + ("bf16",) for v in _VALIDATE] + [v + ("tf32",) for v in _VALIDATE_SPLIT],
+                         ids=[f"{n}-{h}x{w}" for n, _, h, w in _VALIDATE] + [f"{n}-{h}x{w}-tf32" for n, _, h, w in _VALIDATE_SPLIT])
+def test_lowered_programs_pass_the_library_checks(name, args, h, w, precision):
     from stcd_b200.networks import CLASSES
     from stcd_b200.plan import Plan
     net = CLASSES[name](*args).eval()
+    net.precision = precision
     prog = net.lower(h, w)
     for chunk in (1, 4):
         plan = Plan(prog, chunk, device=-1)

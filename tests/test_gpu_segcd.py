@@ -32,7 +32,7 @@ def _check(ys, refs, tag="segcd"):
         assert (y.cpu() - ref).abs().max().item() < BF16_TOL
         r = parity.report(f"{tag}:{('m1', 'm2', 'change')[k]}", y, ref, "sigmoid")
         if k < 2:
-            assert r["rms_over_std"] <= 0.03 and r["max_over_std"] <= 0.16, r
+            assert r["rms_over_std"] <= 0.03 and r["max_over_std"] <= 0.2, r      # the tail over up to 4 * 10**6 logits
             assert r["agree_decided"] >= 0.999 and r["agree_all"] >= 0.99, r
     change, ref = ys[2].cpu(), refs[2]
     agree = (change > 0) == (ref > 0)

@@ -439,3 +439,45 @@ def test_lowering_rejects_bad_shapes():
         net.train()(torch.zeros(1, 3, 16, 16), torch.zeros(1, 3, 16, 16))
     with pytest.raises(RuntimeError):      # no CPU path
         net.eval()(torch.zeros(1, 3, 16, 16), torch.zeros(1, 3, 16, 16))
+
+
+@pytest.mark.parametrize("family", ["siamunet_diff", "siamunet_conc", "snunet"])
+def test_split_precision_program_meets_1e3(family):
+    """precision = "tf32" (split-bf16 operands: lowering.Program.precision) through the emulator: logits within 1e-3 of the fp32
+    oracle at a logit spread >= 0.25 -- the tolerance class the north star names for the tf32 path -- and the change maps
+    agree on every decided pixel.  Plain tf32 rounding of the operands does NOT meet it."""
+    from stcd_b200 import siamunet, snunet
+    if family == "snunet":
+        net = synth.prepare_(snunet.SNUNet_ECAM(3, 2).eval(), "SNUNet_ECAM")
+        fwd = nets.snunet_forward
+    else:
+        fusion = family.split("_")[1]
+        cls = {"diff": siamunet.SiamUnet_diff, "conc": siamunet.SiamUnet_conc}[fusion]
+        net = synth.randomize_(cls(3, 2).eval(), gain=0.77)
+        fwd = lambda sd, a, b: nets.siamunet_forward(sd, a, b, fusion)  # noqa: E731
+    net.precision = "tf32"
+    x1, x2 = synth.image_pairs(3, 32, 48)
+    with torch.no_grad():
+        ref = fwd(net.state_dict(), x1, x2)
+    prog = net.lower(32, 48)
+    assert prog.split and all(o.split for o in prog.ops if isinstance(o, (L.ConvSpec, L.InputPackSpec)))
+    assert not any(o.xf_cs or o.fold_cs for o in prog.ops if isinstance(o, L.ConvSpec))
+    y = emulate.run_program(prog, x1, x2, chunk=2)[0]
+    err = (y - ref).abs().max().item()
+    assert ref.std().item() >= 0.2 and err < 1e-3, (ref.std().item(), err)
+    assert err < 2e-4, err                       # 16-bit operand mantissas: ~1e-4 of the logit spread
+    agree = ((y[:, 1] > y[:, 0]) == (ref[:, 1] > ref[:, 0]))[(ref[:, 1] - ref[:, 0]).abs() > 1e-3]
+    assert agree.all()
+    net.precision = "bf16"                       # the same module lowers back to the bf16 program
+    assert not net.lower(32, 48).split
+    net.precision = "fp64"
+    with pytest.raises(ValueError):
+        net.lower(32, 48)
+
+
+def test_precision_path_is_refused_where_it_is_not_implemented():
+    from stcd_b200 import segcd
+    net = segcd.SegCD("resnet34").eval()
+    net.precision = "tf32"
+    with pytest.raises(NotImplementedError):
+        net.plan_precision

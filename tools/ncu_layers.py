@@ -7,15 +7,22 @@ Times under ncu are cold-cache and serialised (compare shares and fractions, not
 
 Tensor-pipe utilisation, normalised here (ncu's `sm__ops_path_tensor_op_hmma_*` counters read 0 for tcgen05.mma, and the
 `sm__pipe_tensor_subpipe_hmma_cycles_active_realtime` counter is collected per TPC, which is how round 1's table got ratios > 1):
-  tensor_math_pct   = executed MACs / (elapsed SM cycles x 4096 MAC/clk/SM x SMs), with executed MACs = 4 x the bytes the MMAs wrote
-                      to tensor memory (`sm__mem_tensor_writes_op_utcmma.sum`: an M=128, K=16 MMA writes 128*N*4 bytes of D and
-                      performs 128*N*16 MACs) -- the fraction of the dense bf16 peak the kernel's MMAs amount to, in [0, 100];
-  tensor_busy_pct   = tensor sub-pipe active cycles / elapsed cycles, halved when the raw ratio shows the per-TPC double count."""
+  mma_insts         = `sm__inst_executed_pipe_tensor_subpipe_hmma.sum`: this one does count tcgen05.mma (checked: SNUNet conv0_4.conv2,
+                      64 pairs = 32768 tiles x 18 MMAs = 589 824, the counter reads 589 824);
+  tensor_math_pct   = mma_insts x (128 x N x 16 MACs) / (elapsed SM cycles x 4096 MAC/clk/SM x 148 SMs): the share of the dense bf16
+                      peak the kernel's MMAs amount to (includes MACs on padding / halo columns), in [0, 100];
+  tensor_busy_pct   = mma_insts x cost(N) / (elapsed SM cycles x 148): the share of the cycles the tensor pipe is occupied, with
+                      cost(N) the measured cycles one SS-mode M=128 K=16 MMA holds the pipe (tools/ubench/mma_n.cu: 45 for N <= 48,
+                      48.5 / 56.5 / 64 / 96 / 128 for N = 64 / 96 / 128 / 192 / 256), in [0, 100]."""
 import csv, json, os, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-T = "sm__mem_tensor_writes_op_utcmma.sum"
+T = "sm__inst_executed_pipe_tensor_subpipe_hmma.sum"
 N_SM = 148
+
+
+def mma_cost(n):
+    return max(45.0, 32.0 + n / 4.0, n / 2.0) if n else float("nan")
 
 
 def main():
@@ -69,12 +76,13 @@ def main():
         alg_f = 2.0 * op["macs_per_pair"] * pairs_per_launch if op else float("nan")
         total_us += dur_us
         nan = float("nan")
-        tm_bytes = d.get(T, nan) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(d.get("unit:" + T, "byte"), 1)
-        cyc_avg, cyc_sum = d.get("sm__cycles_elapsed.avg", nan), d.get("sm__cycles_elapsed.sum", nan)
-        math_pct = 100.0 * 4.0 * tm_bytes / (cyc_avg * 4096.0 * N_SM) if cyc_avg else nan
-        busy = d.get("sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.sum", nan) / cyc_sum if cyc_sum else nan
+        n_mma = d.get(T, nan)
+        n_tile = op["n_tile"] if op else 0
+        cyc_avg = d.get("sm__cycles_elapsed.avg", nan)
+        math_pct = 100.0 * n_mma * 128.0 * n_tile * 16.0 / (cyc_avg * 4096.0 * N_SM) if (cyc_avg and n_tile) else nan
+        busy = 100.0 * n_mma * mma_cost(n_tile) / (cyc_avg * N_SM) if (cyc_avg and n_tile) else nan
         table.append({"id": k, "op": name, "kernel": d["kernel"].split("(")[0][-48:], "us": dur_us, "tensor_pct": math_pct,
-                      "tensor_busy_raw": busy, "mma_insts": d.get("sm__inst_executed_pipe_tensor_subpipe_hmma.sum", nan),
+                      "tensor_busy_pct": busy, "mma_insts": n_mma,
                       "dram_read_MB": rd / 1e6, "dram_write_MB": wr / 1e6, "dram_GBs": gbs, "dram_frac_of_measured": gbs / peaks["hbm_gbs"],
                       "dram_pct_ncu": d.get("dram__throughput.avg.pct_of_peak_sustained_elapsed", float("nan")),
                       "alg_MB": alg_b / 1e6, "alg_GBs": alg_b / (dur_us * 1e-6) / 1e9 if dur_us else float("nan"),
@@ -90,10 +98,10 @@ def main():
         w.writerows(table)
     with open(out + ".txt", "w") as f:
         f.write(f"# {meta['net']} {meta['pairs']} pairs of {meta['h']}x{meta['h']} (chunk {meta['chunk']}): one forward under ncu, --clock-control none; "
-                f"times are cold-cache and serialised.\n# tensor% = MACs executed by tcgen05.mma / (elapsed cycles x 4096 x {N_SM} SMs), MACs = 4 x {T}; busy = raw tensor sub-pipe active / elapsed\n# peaks: HBM {peaks['hbm_gbs']} GB/s, bf16 {peaks['bf16_tflops']} TFLOP/s (MEASURED_PEAKS.json)\n")
-        f.write(f"{'op':28s} {'us':>8s} {'share':>6s} {'tensor%':>8s} {'busy':>5s} {'dramGB/s':>9s} {'of HBM':>7s} {'alg GB/s':>9s} {'alg/HBM':>8s} {'algTF/s':>8s} {'N':>4s} {'xf':>3s} {'regs':>5s}\n")
+                f"times are cold-cache and serialised.\n# tensor% = tcgen05.mma count ({T}) x 128 x N x 16 MACs / (elapsed cycles x 4096 x {N_SM} SMs); busy% = count x measured cycles per MMA of that N / (elapsed cycles x {N_SM})\n# peaks: HBM {peaks['hbm_gbs']} GB/s, bf16 {peaks['bf16_tflops']} TFLOP/s (MEASURED_PEAKS.json)\n")
+        f.write(f"{'op':28s} {'us':>8s} {'share':>6s} {'tensor%':>8s} {'busy%':>6s} {'dramGB/s':>9s} {'of HBM':>7s} {'alg GB/s':>9s} {'alg/HBM':>8s} {'algTF/s':>8s} {'N':>4s} {'xf':>3s} {'regs':>5s}\n")
         for r in table:
-            f.write(f"{r['op'][:28]:28s} {r['us']:8.1f} {r['us'] / total_us:6.3f} {r['tensor_pct']:8.1f} {r['tensor_busy_raw']:5.2f} {r['dram_GBs']:9.0f} {r['dram_frac_of_measured']:7.2f} "
+            f.write(f"{r['op'][:28]:28s} {r['us']:8.1f} {r['us'] / total_us:6.3f} {r['tensor_pct']:8.1f} {r['tensor_busy_pct']:6.1f} {r['dram_GBs']:9.0f} {r['dram_frac_of_measured']:7.2f} "
                     f"{r['alg_GBs']:9.0f} {r['alg_hbm_frac']:8.2f} {r['alg_TFLOPs']:8.1f} {r['n_tile']:4d} {r['xf']:3d} {r['regs']:5.0f}\n")
         f.write(f"total {total_us:.1f} us over {len(table)} launches\n")
     print(open(out + ".txt").read())
