@@ -19,9 +19,9 @@
 // either ALL blocks once per CTA (weight-stationary: the CTA then streams pixel tiles past them)
 // or through a ring when they do not fit.
 //
-// Warp roles (7 warps): 0 = A producer (TMA), 1 = W producer (bulk copy), 2 = MMA issuer (also
+// Warp roles (8 warps): 0 = A producer (TMA), 1 = W producer (bulk copy), 2 = MMA issuer (also
 // owns TMEM alloc/dealloc), 3..6 = epilogue (TMEM -> registers -> folded BN / ReLU / residual /
-// |f1-f2| / 2x2 max-pool -> global).  Accumulators are double-buffered in TMEM so the epilogue
+// |f1-f2| / 2x2 max-pool -> global), 7 = residual producer (TMA into a small ring, when the op has one).  Accumulators are double-buffered in TMEM so the epilogue
 // of tile i overlaps the MMAs of tile i+1; CTAs are persistent over their tiles.
 //
 // Measured on B200 (tools/ubench, profiles/): a tcgen05.mma M=128 K=16 in SS mode costs ~45
@@ -45,9 +45,9 @@ constexpr int kMaxAStages = 8;
 constexpr int kMaxWStages = 16;
 constexpr int kMaxChunks = 128;  // A-stage loads per phase
 constexpr int kMaxTaps = 512;    // weight blocks per phase (split precision triples the K-program: 1024 channels x 9 taps / 64 x 3 = 432)
-constexpr int kConvThreads = 224;
+constexpr int kConvThreads = 256;   // 8 warps: A producer, W producer, MMA issuer, 4 epilogue warps, residual producer
 constexpr int kFastMma = 36;     // per-chunk MMA offsets kept in the constant bank (9 taps x 4 K steps)
-constexpr int kMaxRSlots = 4;    // residual tiles in flight (TMA -> shared-memory ring)
+constexpr int kMaxRSlots = 8;    // residual blocks in flight (TMA -> shared-memory ring)
 // Horizontally folded 3x3 convs (E_XF): the tile is 8 rows x 16 columns of INPUT positions, of which the inner 14 columns
 // are outputs (tiles overlap by one column on each side).
 constexpr int kXfTileH = 8;
@@ -126,11 +126,14 @@ struct ConvParams {
   int32_t res_c8;
   // Residual ring (E_RSM).  Per-thread residual loads kept only ~2 KB per epilogue warp in flight: at DRAM latency that is
   // 2.4 TB/s for the whole chip, and the short-K layers with a residual (conv*.conv2 of the nested blocks) ran at exactly
-  // that rate (262 us with the residual, 152 us without).  The A producer now fetches the residual tile of each pass with
-  // ONE TMA box per sub-tile, `res_slots` passes ahead; the epilogue reads it with conflict-free 16-byte LDS.
+  // that rate (262 us with the residual, 152 us without).  A dedicated warp now fetches the residual by TMA into a ring of
+  // small slots -- one slot = `res_rb` channels of the MS sub-tiles the epilogue finishes together (<= 16 KB, so the ring also
+  // fits beside 128-column Siamese-pair ops whose whole residual tile would take 64 KB) -- in the order the epilogue consumes
+  // them, up to `res_slots` blocks ahead; the epilogue reads it with conflict-free 16-byte LDS.
   int32_t res_slots;                       // 0: per-thread global loads
-  uint32_t res_slot_bytes, res_sub_bytes;  // ring slot = MT sub-tiles of [res_ch/8][tile rows][tile px][8] bf16
-  int32_t res_ch;                          // channels per residual box (n_tile; cs for E_XF)
+  uint32_t res_slot_bytes, res_sub_bytes;  // ring slot = MS sub-tiles of [res_rb/8][tile rows][tile px][8] bf16
+  int32_t res_ch;                          // residual channels this CTA needs per sub-tile (n_tile; cs for E_XF)
+  int32_t res_rb;                          // channels per slot (multiple of 16)
   int32_t xf_cs;                           // E_XF: column-block stride cs (n_tile = 3 * cs); 0 otherwise
   // Split precision (the "tf32" tolerance class; generic instances only).  Every bf16 tensor holds a hi plane (channel groups
   // [0, c8/2)) and a lo plane ([c8/2, c8)): hi = bf16(v), lo = bf16(v - hi).  The K-program already reads (hi, lo, hi) against
@@ -352,9 +355,6 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     const bool leader = elect_one();
     int s = 0;
     uint32_t par = 1;  // parity to wait for on a_empty[s]: first pass through the ring never blocks
-    int rs = 0;
-    uint32_t rpar = 1;
-    const uint32_t res_tx = static_cast<uint32_t>(MT) * static_cast<uint32_t>(p.res_ch) * (TH * TW * 2u);
     pdl_wait();        // activations are written by the previous kernel(s)
     for (int t = 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
@@ -364,20 +364,6 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       const int tile_y = tile % p.tiles_y;
       const int img = tile / p.tiles_y;
       const int x0 = tile_x * XSTEP - XOFF, y0 = tile_y * TH;
-      if (p.res_slots) {
-        // the pass's residual tiles: one box {tile px x 8 ch, tile rows, res_ch / 8 groups} per sub-tile
-        mbar_wait_relaxed(&r_empty[rs], rpar);
-        if (leader) {
-          mbar_expect_tx(&r_full[rs], res_tx);
-          uint8_t* dst = smem_r + static_cast<size_t>(rs) * p.res_slot_bytes;
-#pragma unroll
-          for (int m = 0; m < MT; ++m) tma_load_4d(dst + m * p.res_sub_bytes, &tm.res, &r_full[rs], x0 * 8, y0, n0 >> 3, img + p.m_off[m]);
-        }
-        if (++rs == p.res_slots) {
-          rs = 0;
-          rpar ^= 1;
-        }
-      }
       for (int c = 0; c < phase.chunk_count; ++c) {
         const ChunkLoad L = s_cload[c];
         mbar_wait_relaxed(&a_empty[s], par);
@@ -573,7 +559,44 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp == 7) {
+    // ============================== residual producer (TMA) ==============================
+    if (p.res_slots) {
+      const bool leader = elect_one();
+      int rs = 0;
+      uint32_t rpar = 1;     // first pass through the ring never blocks
+      const int n_ch = min(XF ? p.xf_cs : p.n_tile, p.cout - n0);          // channels the epilogue walks (in steps of 16)
+      const int n_blocks = (n_ch + p.res_rb - 1) / p.res_rb;
+      const uint32_t tx = static_cast<uint32_t>(MS) * static_cast<uint32_t>(p.res_rb) * (TH * TW * 2u);
+      pdl_wait();            // the residual is written by an earlier kernel
+      for (int t = 0; t < my_tiles; ++t) {
+        int tile = blockIdx.x + t * gridDim.x;
+        if (p.reverse) tile = p.n_tiles - 1 - tile;
+        const int tile_x = tile % p.tiles_x;
+        tile /= p.tiles_x;
+        const int tile_y = tile % p.tiles_y;
+        const int img = tile / p.tiles_y;
+        const int x0 = tile_x * XSTEP - XOFF, y0 = tile_y * TH;
+        for (int mb = 0; mb < MT; mb += MS) {
+          for (int cb = 0; cb < n_blocks; ++cb) {     // the order the epilogue consumes: (sub-tile group, channel block)
+            mbar_wait_relaxed(&r_empty[rs], rpar);
+            if (leader) {
+              mbar_expect_tx(&r_full[rs], tx);
+              uint8_t* dst = smem_r + static_cast<size_t>(rs) * p.res_slot_bytes;
+#pragma unroll
+              for (int m = 0; m < MS; ++m)
+                tma_load_4d(dst + m * p.res_sub_bytes, &tm.res, &r_full[rs], x0 * 8, y0, (n0 + cb * p.res_rb) >> 3, img + p.m_off[mb + m]);
+            }
+            if (++rs == p.res_slots) {
+              rs = 0;
+              rpar ^= 1;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp < 7) {
     // ============================== epilogue (warps 3..6) ==============================
     const bool has_raw = STCD_HAS(E_RAW, p.out_raw != nullptr);
     const bool has_aff2 = STCD_HAS(E_AFF2, p.scale2 != nullptr);
@@ -718,7 +741,6 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             prefetch_unit(t + 1, 0);
         }
         if (mb == 0) {
-          if (res_sm) mbar_wait_relaxed(&r_full[ers], erpar);
           mbar_wait_relaxed(&acc_full[acc], (t >> 1) & 1);
           tc_fence_after();
           if (t == 0 && threadIdx.x == 96) STCD_STAMP(5);
@@ -814,10 +836,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
               for (int j = 0; j < 16; ++j) v[m][j] = fmaf(v[m][j], s_aff[2][c0 + j], s_aff[3][c0 + j]);
             }
             if (res_sm) {
-              // tile in shared memory: [res_ch / 8][tile rows][tile px] x 16 B -- consecutive lanes, consecutive 16 B
+              // slot in shared memory: [MS sub-tiles][res_rb / 8][tile rows][tile px] x 16 B -- consecutive lanes, consecutive 16 B
+              if (m == 0 && (c0 % p.res_rb) == 0) mbar_wait_relaxed(&r_full[ers], erpar);     // a new block of this group
               const uint4* rt = reinterpret_cast<const uint4*>(smem_r + static_cast<size_t>(ers) * p.res_slot_bytes +
-                                                               static_cast<size_t>(mb + m) * p.res_sub_bytes) +
-                                (c0 >> 3) * (TH * TW) + ty * TW + tx;
+                                                               static_cast<size_t>(m) * p.res_sub_bytes) +
+                                ((c0 % p.res_rb) >> 3) * (TH * TW) + ty * TW + tx;
               r_cur[m][0] = rt[0];
               r_cur[m][1] = rt[TH * TW];
             }
@@ -919,6 +942,15 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
                 }
               r_cur[m][0] = a;
               r_cur[m][1] = b;
+            }
+          }
+          if (res_sm && (((c0 + 16) % p.res_rb) == 0 || c0 + 16 >= min(c_lim, p.cout - n0))) {
+            // the last step of this residual block: hand the slot back to the residual producer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&r_empty[ers]);
+            if (++ers == p.res_slots) {
+              ers = 0;
+              erpar ^= 1;
             }
           }
         }

@@ -1679,20 +1679,26 @@ int stcd_plan_finalize(stcd_plan* plan) {
     }
     if (!occ) return fail(STCD_ERR_INVALID, "conv op: no shared-memory plan (forced occupancy %d)", force_occ);
     const size_t w_region = round_up(p.w_resident ? w_all : (size_t)p.w_stages * p.wblk_bytes, 128);
-    // ---- residual ring: the pass's residual tiles arrive by TMA, up to kMaxRSlots passes ahead, when the ring fits beside
-    // >= 2 (3 when there is room) A stages; else the epilogue loads the residual itself
+    // ---- residual ring: a dedicated warp fetches the residual by TMA in blocks of `res_rb` channels of the MS sub-tiles the
+    // epilogue finishes together (slot <= 16 KB), up to kMaxRSlots blocks ahead, when >= 2 slots (32 KB when there is room)
+    // fit beside >= 2 A stages; else the epilogue loads the residual itself
     p.res_slots = 0;
     p.split = d.split ? 1 : 0;
     if (d.res >= 0 && d.n_phase == 1 && d.osy == 1 && d.osx == 1 && !d.split && env_int("STCD_RES_SMEM", 1)) {
       const Tensor& tr = plan->tensors[d.res];
+      const int ms = d.pair ? 2 : 1;
       p.res_ch = xf ? d.xf_cs : d.n_tile;
-      const size_t sub = (size_t)p.res_ch * tile_h * tile_w * 2;                   // [res_ch / 8][tile rows][tile px][8] bf16
-      const size_t slot = sub * p.mt;
+      int rb = 64 / ms;                                   // 16 KB slots: 64 channels of one stream, 32 of a Siamese pair
+      while (rb > 16 && rb > p.res_ch) rb >>= 1;
+      p.res_rb = rb;
+      const size_t sub = (size_t)rb * tile_h * tile_w * 2;                         // [res_rb / 8][tile rows][tile px][8] bf16
+      const size_t slot = sub * ms;
       const size_t fixed = 256 + p.tab_bytes + w_region;
       const size_t budget = cta_budget(occ);
       if (tr.h == p.ho && tr.w == p.wo) {
         for (int r = stcd::kMaxRSlots; r >= 2 && !p.res_slots; --r) {
-          const int a_min = std::min(p.a_stages, r >= 3 ? 3 : 2);
+          if (r * slot > 64 * 1024) continue;              // 64 KB in flight per CTA covers the DRAM latency
+          const int a_min = std::min(p.a_stages, r * slot >= 32 * 1024 ? 3 : 2);
           if (fixed + (size_t)a_min * p.a_stage_bytes + r * slot > budget) continue;
           p.res_slots = r;
           p.res_slot_bytes = (uint32_t)slot;
@@ -1701,7 +1707,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
         }
       }
       if (p.res_slots) {
-        int r = encode_act_map(&op.tm.res, tr.ptr, tr.mult * plan->chunk, tr.h, tr.w, tr.c, p.res_ch, 1, 1, 0, 0, tile_w, tile_h);
+        int r = encode_act_map(&op.tm.res, tr.ptr, tr.mult * plan->chunk, tr.h, tr.w, tr.c, p.res_rb, 1, 1, 0, 0, tile_w, tile_h);
         if (r) return r;
       }
     }
