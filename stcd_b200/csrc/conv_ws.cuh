@@ -958,13 +958,6 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (res_sm) {
-        if (lane == 0) mbar_arrive(&r_empty[ers]);
-        if (++ers == p.res_slots) {
-          ers = 0;
-          erpar ^= 1;
-        }
-      }
       if (threadIdx.x == 96) {
         if (t == 0) STCD_STAMP(6);
         if (t == my_tiles - 1) STCD_STAMP(10);
