@@ -518,7 +518,7 @@ def measure(args, wl_name, wl, rank, world, local_rank, dev, full=True):
         t_hbm = top_bytes / (peaks["hbm"] * 1e9)
         kname = ("conv_ws_kernel" if isinstance(top_op, L.ConvSpec) else type(top_op).__name__) + f"[{top[0]}]"
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")      # per-op DRAM bytes from the round's ncu tables
         if os.path.exists(tpath):
             tr = json.load(open(tpath)).get(wl_name, {}).get(top[0])
             if tr:                                   # ncu --set full: dram bytes read + written, per pair -> per launch

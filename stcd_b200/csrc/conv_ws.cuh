@@ -604,6 +604,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     const bool split = (EPI & E_GENERIC) != 0 && p.split != 0;         // split precision: generic instances only
     const bool res_sm = has_res && STCD_HAS(E_RSM, p.res_slots > 0);   // residual tile in the shared-memory ring
     const bool res_rg = has_res && !res_sm && !split;                  // residual through prefetched per-thread global loads
+    const int rb_mask = p.res_rb - 1;                                  // res_rb is a power of two (16 / 32 / 64)
     // 16 values -> the hi plane at `o` (two 8-channel groups `plane` elements apart) and, in split precision, the lo plane
     // `lo_off` elements further
     auto store16 = [&](__nv_bfloat16* o, size_t plane, size_t lo_off, const float* x, bool both) {
@@ -648,6 +649,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     const int tx = XF ? (lane & 15) : (lane & 7);
     const bool lane_out = !XF || (tx >= 1 && tx <= kXfStep);   // XF: the outer two columns only feed their neighbours
     const int c_lim = XF ? p.xf_cs : p.n_tile;                 // output channels this CTA finishes
+    const int n_ch_epi = min(c_lim, p.cout - n0);              // ... of which real ones
     const uint32_t hw = static_cast<uint32_t>(p.ho) * p.wo;  // pixels per image plane
     const uint32_t hw_pool = hw >> 2;
     const int cg8 = n0 >> 3;  // first 8-channel group of this N tile
@@ -837,10 +839,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             }
             if (res_sm) {
               // slot in shared memory: [MS sub-tiles][res_rb / 8][tile rows][tile px] x 16 B -- consecutive lanes, consecutive 16 B
-              if (m == 0 && (c0 % p.res_rb) == 0) mbar_wait_relaxed(&r_full[ers], erpar);     // a new block of this group
+              if (m == 0 && (c0 & rb_mask) == 0) mbar_wait_relaxed(&r_full[ers], erpar);     // a new block of this group
               const uint4* rt = reinterpret_cast<const uint4*>(smem_r + static_cast<size_t>(ers) * p.res_slot_bytes +
                                                                static_cast<size_t>(m) * p.res_sub_bytes) +
-                                ((c0 % p.res_rb) >> 3) * (TH * TW) + ty * TW + tx;
+                                ((c0 & rb_mask) >> 3) * (TH * TW) + ty * TW + tx;
               r_cur[m][0] = rt[0];
               r_cur[m][1] = rt[TH * TW];
             }
@@ -944,7 +946,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
               r_cur[m][1] = b;
             }
           }
-          if (res_sm && (((c0 + 16) % p.res_rb) == 0 || c0 + 16 >= min(c_lim, p.cout - n0))) {
+          if (res_sm && (((c0 + 16) & rb_mask) == 0 || c0 + 16 >= n_ch_epi)) {
             // the last step of this residual block: hand the slot back to the residual producer
             __syncwarp();
             if (lane == 0) mbar_arrive(&r_empty[ers]);

@@ -1696,9 +1696,10 @@ int stcd_plan_finalize(stcd_plan* plan) {
       const size_t fixed = 256 + p.tab_bytes + w_region;
       const size_t budget = cta_budget(occ);
       if (tr.h == p.ho && tr.w == p.wo) {
-        for (int r = stcd::kMaxRSlots; r >= 2 && !p.res_slots; --r) {
-          if (r * slot > 64 * 1024) continue;              // 64 KB in flight per CTA covers the DRAM latency
-          const int a_min = std::min(p.a_stages, r * slot >= 32 * 1024 ? 3 : 2);
+        // four blocks in flight (32-64 KB) cover the DRAM latency; more would take the room of the activation stages, which
+        // matter more (eight 8 KB slots instead of four cost SNUNet's conv0_x.conv2 three of its five A stages: 190 -> 237 us)
+        for (int r = 4; r >= 2 && !p.res_slots; --r) {
+          const int a_min = std::min(p.a_stages, r >= 3 ? 3 : 2);
           if (fixed + (size_t)a_min * p.a_stage_bytes + r * slot > budget) continue;
           p.res_slots = r;
           p.res_slot_bytes = (uint32_t)slot;
