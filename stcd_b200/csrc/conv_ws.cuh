@@ -793,9 +793,36 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
           const bool two = (p.cout - ch) > 8;  // both 8-channel groups of this 16-column step are real
           if (res_rg && valid && c0 + 16 >= 16 * PF && c0 + 16 < c_lim && ch + 16 < p.cout) load_res(c0 + 16, r_nxt);
           uint32_t raw[MS][16];
+          // Everything that comes from shared memory -- the column affines and, with the residual ring, the residual -- is
+          // requested while the accumulator load is in flight: one epilogue warp per scheduler has nothing else to hide their
+          // latency with (ncu source view, round 2: the step's FFMAs waited on the short scoreboard for the affine LDS, the
+          // unpack on the long one for the residual read through a generic pointer).
           if (!XF) {
 #pragma unroll
             for (int m = 0; m < MS; ++m) tmem_ld16(tgrp + m * p.n_tile + c0, raw[m]);
+          }
+          float4 a_sc[4], a_sh[4], a_sc2[4], a_sh2[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            a_sc[j] = *reinterpret_cast<const float4*>(&s_aff[0][c0 + 4 * j]);
+            a_sh[j] = *reinterpret_cast<const float4*>(&s_aff[1][c0 + 4 * j]);
+            if (has_aff2) {
+              a_sc2[j] = *reinterpret_cast<const float4*>(&s_aff[2][c0 + 4 * j]);
+              a_sh2[j] = *reinterpret_cast<const float4*>(&s_aff[3][c0 + 4 * j]);
+            }
+          }
+          if (res_sm) {
+            // slot in shared memory: [MS sub-tiles][res_rb / 8][tile rows][tile px] x 16 B -- consecutive lanes, consecutive 16 B
+            if ((c0 & rb_mask) == 0) mbar_wait_relaxed(&r_full[ers], erpar);     // a new block of this group
+            const uint32_t rt = smem_u32(smem_r) + static_cast<uint32_t>(ers) * p.res_slot_bytes +
+                                (static_cast<uint32_t>((c0 & rb_mask) >> 3) * (TH * TW) + ty * TW + tx) * 16u;
+#pragma unroll
+            for (int m = 0; m < MS; ++m) {
+              r_cur[m][0] = lds128(rt + m * p.res_sub_bytes);
+              r_cur[m][1] = lds128(rt + m * p.res_sub_bytes + TH * TW * 16);
+            }
+          }
+          if (!XF) {
             tmem_wait_ld();
           } else {
             // out[x] = D_0[x - 1] + D_1[x] + D_2[x + 1]: column block b sits at column b * cs; the left / right neighbours
@@ -820,13 +847,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
 #pragma unroll
           for (int m = 0; m < MS; ++m) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 sc = *reinterpret_cast<const float4*>(&s_aff[0][c0 + j]);
-              const float4 sh = *reinterpret_cast<const float4*>(&s_aff[1][c0 + j]);
-              v[m][j + 0] = fmaf(__uint_as_float(raw[m][j + 0]), sc.x, sh.x);
-              v[m][j + 1] = fmaf(__uint_as_float(raw[m][j + 1]), sc.y, sh.y);
-              v[m][j + 2] = fmaf(__uint_as_float(raw[m][j + 2]), sc.z, sh.z);
-              v[m][j + 3] = fmaf(__uint_as_float(raw[m][j + 3]), sc.w, sh.w);
+            for (int j = 0; j < 4; ++j) {
+              v[m][4 * j + 0] = fmaf(__uint_as_float(raw[m][4 * j + 0]), a_sc[j].x, a_sh[j].x);
+              v[m][4 * j + 1] = fmaf(__uint_as_float(raw[m][4 * j + 1]), a_sc[j].y, a_sh[j].y);
+              v[m][4 * j + 2] = fmaf(__uint_as_float(raw[m][4 * j + 2]), a_sc[j].z, a_sh[j].z);
+              v[m][4 * j + 3] = fmaf(__uint_as_float(raw[m][4 * j + 3]), a_sc[j].w, a_sh[j].w);
             }
             if (has_raw && valid) {
               __nv_bfloat16* o = q_raw + (im[m] * p.out_raw_c8 + g8) * hw * 8;
@@ -835,16 +860,12 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             if (has_aff2) {
               if (act_pre) apply_act(v[m]);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[m][j] = fmaf(v[m][j], s_aff[2][c0 + j], s_aff[3][c0 + j]);
-            }
-            if (res_sm) {
-              // slot in shared memory: [MS sub-tiles][res_rb / 8][tile rows][tile px] x 16 B -- consecutive lanes, consecutive 16 B
-              if (m == 0 && (c0 & rb_mask) == 0) mbar_wait_relaxed(&r_full[ers], erpar);     // a new block of this group
-              const uint4* rt = reinterpret_cast<const uint4*>(smem_r + static_cast<size_t>(ers) * p.res_slot_bytes +
-                                                               static_cast<size_t>(m) * p.res_sub_bytes) +
-                                ((c0 & rb_mask) >> 3) * (TH * TW) + ty * TW + tx;
-              r_cur[m][0] = rt[0];
-              r_cur[m][1] = rt[TH * TW];
+              for (int j = 0; j < 4; ++j) {
+                v[m][4 * j + 0] = fmaf(v[m][4 * j + 0], a_sc2[j].x, a_sh2[j].x);
+                v[m][4 * j + 1] = fmaf(v[m][4 * j + 1], a_sc2[j].y, a_sh2[j].y);
+                v[m][4 * j + 2] = fmaf(v[m][4 * j + 2], a_sc2[j].z, a_sh2[j].z);
+                v[m][4 * j + 3] = fmaf(v[m][4 * j + 3], a_sc2[j].w, a_sh2[j].w);
+              }
             }
             if (has_res && valid && split) {
               // residual = hi + lo, read where it is needed (the precision path is not the throughput path)

@@ -190,6 +190,14 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// 16-byte shared-memory load from a 32-bit shared address (an explicit LDS.128: a load through a generic pointer is tracked on the
+// long scoreboard)
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+
 // 32 contiguous bytes (32-byte aligned) in ONE store: both halves of a sector leave together (STG.E.256)
 __device__ __forceinline__ void st_global_256(void* ptr, uint4 a, uint4 b) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
