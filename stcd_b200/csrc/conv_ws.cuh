@@ -743,6 +743,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             prefetch_unit(t + 1, 0);
         }
         if (mb == 0) {
+          if (res_sm) mbar_wait_relaxed(&r_full[ers], erpar);   // the tile's first residual block: off the critical path here
           mbar_wait_relaxed(&acc_full[acc], (t >> 1) & 1);
           tc_fence_after();
           if (t == 0 && threadIdx.x == 96) STCD_STAMP(5);
