@@ -353,6 +353,36 @@ int launch_conv(const stcd_plan* plan, const ConvOp& op, int n_valid, float* con
   return STCD_OK;
 }
 
+// Dense dilated kNN: the tensor-core kernel (csrc/graph_kernels.cuh knn_mma_kernel) for k * dilation <= 27 (the Grapher's
+// 9 / 18 / 27), else -- or with STCD_KNN_MMA=0 -- the fp32 register-tile kernel.
+int launch_knn(const float* xn, const float* yn, const float* relpos, int B, int C, int N, int M, int k, int dilation, long long* idx,
+               cudaStream_t st) {
+  const int kd = k * dilation;
+  static const int use_mma = env_int("STCD_KNN_MMA", 1);
+  if (use_mma && kd <= 27 && M <= stcd::kKnnM) {
+    const int MP = (M + 15) & ~15;
+    const size_t smem = (size_t)3 * (stcd::kKnnKC / 8) * (stcd::kKnnTQ + MP) * 16 + 128;
+    const dim3 grid((N + stcd::kKnnTQ - 1) / stcd::kKnnTQ, B);
+#define STCD_KNN_LAUNCH(KD)                                                                                                   \
+    do {                                                                                                                       \
+      static bool attr_set = false;                                                                                            \
+      if (!attr_set) {                                                                                                         \
+        CUDA_TRY(cudaFuncSetAttribute(stcd::knn_mma_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));     \
+        attr_set = true;                                                                                                       \
+      }                                                                                                                        \
+      stcd::knn_mma_kernel<KD><<<grid, 256, smem, st>>>(xn, yn, relpos, C, N, M, k, dilation, idx);                            \
+    } while (0)
+    if (kd <= 9) STCD_KNN_LAUNCH(9);
+    else if (kd <= 18) STCD_KNN_LAUNCH(18);
+    else STCD_KNN_LAUNCH(27);
+#undef STCD_KNN_LAUNCH
+  } else {
+    stcd::knn_graph_kernel<<<dim3((N + stcd::kKnnQ - 1) / stcd::kKnnQ, B), 256, 0, st>>>(xn, yn, relpos, C, N, M, k, dilation, idx);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return STCD_OK;
+}
+
 int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, float* const* outs, cudaStream_t st,
               cudaEvent_t* ev = nullptr) {
   int op_i = 0;
@@ -397,8 +427,10 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
       auto ng = [](int B_, int n_) { return (unsigned)std::max(1, std::min(B_ * ((n_ + 31) / 32), 148 * 16)); };
       stcd::normalize_nodes_kernel<<<ng(B, N), 256, 0, st>>>(k.xf, k.xn, B, k.c, N);
       if (k.r > 1) stcd::normalize_nodes_kernel<<<ng(B, M), 256, 0, st>>>(k.yf, k.yn, B, k.c, M);
-      stcd::knn_graph_kernel<<<dim3((N + stcd::kKnnQ - 1) / stcd::kKnnQ, B), 256, 0, st>>>(k.xn, k.r > 1 ? k.yn : k.xn, k.relpos_dev, k.c, N, M,
-                                                                                       k.k, k.dilation, k.idx);
+      {
+        int r = launch_knn(k.xn, k.r > 1 ? k.yn : k.xn, k.relpos_dev, B, k.c, N, M, k.k, k.dilation, k.idx, st);
+        if (r) return r;
+      }
       stcd::max_relative_nc8_kernel<<<nb((size_t)B * (k.c / 8) * N, 8), 256, 0, st>>>(k.xf, y, k.idx, B, k.c, N, M, k.k,
                                                                                       (__nv_bfloat16*)td.ptr, td.c / 8);
       CUDA_TRY(cudaGetLastError());
@@ -1507,7 +1539,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
   plan->pdl = env_int("STCD_PDL", 1);
   // Opt-in (STCD_GRAPH=1).  Measured on B200 (round 2, gpurun_out/gab_*): replaying the captured chunk is NOT faster than the
   // programmatic-dependent-launch chain the plain path already issues -- SiamUnet_diff at 8 pairs: 26.7 k pairs/s plain vs
-  // 14.4 k through the graph, ChangeGNNV1: 2 239 vs 1 300, SNUNet / SegCD: equal.  The small nets are bound by the device-side
+  // 14.4 k through the graph, ChangeGNNV1: 2 239 vs 1 847 (1 300 in another run), SNUNet / SegCD: equal (profiles/r2_graph_ab.txt).  The small nets are bound by the device-side
   // fill / drain of each kernel (4-11 us from the end of one layer to the first MMA of the next), not by host launch cost.
   plan->graph_mode = env_int("STCD_GRAPH", 0);
   const int force_generic = env_int("STCD_FORCE_GENERIC", 0);
@@ -2223,10 +2255,7 @@ int stcd_knn_graph(const float* x, const float* y, const float* relpos, int B, i
   auto ng = [](int B_, int n_) { return (unsigned)std::max(1, std::min(B_ * ((n_ + 31) / 32), 148 * 16)); };
   stcd::normalize_nodes_kernel<<<ng(B, N), 256, 0, st>>>(x, xn, B, C, N);
   if (y) stcd::normalize_nodes_kernel<<<ng(B, M), 256, 0, st>>>(y, yn, B, C, M);
-  stcd::knn_graph_kernel<<<dim3((N + stcd::kKnnQ - 1) / stcd::kKnnQ, B), 256, 0, st>>>(xn, yn, relpos, C, N, M, k, dilation,
-                                                                                   reinterpret_cast<long long*>(nn_idx));
-  CUDA_TRY(cudaGetLastError());
-  return STCD_OK;
+  return launch_knn(xn, yn, relpos, B, C, N, M, k, dilation, reinterpret_cast<long long*>(nn_idx), st);
 }
 
 int stcd_max_relative(const float* x, const float* y, const int64_t* nn_idx, int B, int C, int N, int M, int k, int interleave,
