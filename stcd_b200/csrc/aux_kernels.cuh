@@ -706,6 +706,7 @@ __global__ void __launch_bounds__(256) segcd_head_mma_kernel(const __nv_bfloat16
 }
 
 // grid (ranges, C/8, n_img), 256 threads
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) ecam_stats_kernel(const EcamParams p) {
   const int r = blockIdx.x, g = blockIdx.y, n = blockIdx.z;
   const int per = (p.hw + p.ranges - 1) / p.ranges;
@@ -718,7 +719,7 @@ __global__ void __launch_bounds__(256) ecam_stats_kernel(const EcamParams p) {
       s[k][j] = 0.f;
       m[k][j] = -INFINITY;
     }
-  const int c8s = (p.c >> 3) * (p.split ? 2 : 1);     // stored channel groups per source
+  const int c8s = (p.c >> 3) * (SPLIT ? 2 : 1);     // stored channel groups per source
   const size_t base = (static_cast<size_t>(n) * c8s + g) * p.hw;
   const size_t lo_off = static_cast<size_t>(p.c >> 3) * p.hw * 8;
   for (int px = p0 + threadIdx.x; px < p1; px += blockDim.x) {
@@ -729,7 +730,7 @@ __global__ void __launch_bounds__(256) ecam_stats_kernel(const EcamParams p) {
     for (int k = 0; k < 4; ++k) {
       float v[8];
       unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(p.src[k] + (base + px) * 8)), v);
-      if (p.split) {
+      if (SPLIT) {
         float lo[8];
         unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(p.src[k] + (base + px) * 8 + lo_off)), lo);
 #pragma unroll
@@ -783,6 +784,7 @@ __global__ void __launch_bounds__(256) ecam_stats_kernel(const EcamParams p) {
 constexpr int kEcamPixPerBlock = 2048;
 
 // grid (ceil(hw / kEcamPixPerBlock), n_valid), 256 threads
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) ecam_head_kernel(const EcamParams p) {
   __shared__ float s_avg[320], s_max[320];        // 5C <= 320
   __shared__ float s_hid[4][16];                  // ca: avg, max; ca1: avg, max
@@ -854,9 +856,9 @@ __global__ void __launch_bounds__(256) ecam_head_kernel(const EcamParams p) {
     for (int k = 0; k < 4; ++k) {
       for (int g = 0; g < g8; ++g) {
         float v[8];
-        const size_t at = ((static_cast<size_t>(n) * (p.split ? 2 * g8 : g8) + g) * p.hw + px) * 8;
+        const size_t at = ((static_cast<size_t>(n) * (SPLIT ? 2 * g8 : g8) + g) * p.hw + px) * 8;
         unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(p.src[k] + at)), v);
-        if (p.split) {     // value = hi plane + lo plane
+        if (SPLIT) {     // value = hi plane + lo plane
           float lo[8];
           unpack8_bf16_f(__ldg(reinterpret_cast<const uint4*>(p.src[k] + at + static_cast<size_t>(g8) * p.hw * 8)), lo);
 #pragma unroll

@@ -399,9 +399,12 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
       q.n_valid = n_valid;
       q.out = outs[e.d.out_ext];
       if (!q.out) return fail(STCD_ERR_INVALID, "external output %d is NULL", e.d.out_ext);
-      stcd::ecam_stats_kernel<<<dim3(q.ranges, q.c / 8, n_valid), 256, 0, st>>>(q);
+      const dim3 g_stats(q.ranges, q.c / 8, n_valid), g_head((e.hw + stcd::kEcamPixPerBlock - 1) / stcd::kEcamPixPerBlock, n_valid);
+      if (q.split) stcd::ecam_stats_kernel<true><<<g_stats, 256, 0, st>>>(q);
+      else stcd::ecam_stats_kernel<false><<<g_stats, 256, 0, st>>>(q);
       CUDA_TRY(cudaGetLastError());
-      stcd::ecam_head_kernel<<<dim3((e.hw + stcd::kEcamPixPerBlock - 1) / stcd::kEcamPixPerBlock, n_valid), 256, 0, st>>>(q);
+      if (q.split) stcd::ecam_head_kernel<true><<<g_head, 256, 0, st>>>(q);
+      else stcd::ecam_head_kernel<false><<<g_head, 256, 0, st>>>(q);
       CUDA_TRY(cudaGetLastError());
     } else if (o.kind == 3) {
       const PoolOp& k = plan->pools[o.idx];
