@@ -409,7 +409,8 @@ int stcd_confusion_add_batch(const void* pred, int pred_kind, float thr, const v
  * y-nodes of every x-node in ascending distance (ties: smaller index) and keep every dilation-th.
  * x [B][C][N]; y [B][C][M] or NULL (y := x, M must equal N); relative_pos [N][M] or NULL; M <= 256, k*dilation <= M.
  * nn_idx_out: int64 [B][N][k] = edge_index[0] (edge_index[1] is the centre index n).
- * scratch: device fp32 [B * C * (N + M)] (the L2-normalised copies of x and y; B * C * N when y is NULL). */
+ * scratch: device fp32 [B * C * (N + M)] (the L2-normalised copies of x and y; B * C * N when y is NULL) -- used by the fp32
+ * kernel (k * dilation > 27); the tensor-core kernel takes its plane workspace from the stream-ordered memory pool. */
 int stcd_knn_graph(const float* x, const float* y_or_null, const float* relative_pos_or_null, int B, int C, int N,
                    int M, int k, int dilation, int64_t* nn_idx_out, float* scratch, void* stream);
 

@@ -108,6 +108,11 @@ struct GraphOp {
   float* xn = nullptr;         // fp32 [imgs][C][N], L2-normalised nodes
   float* yn = nullptr;         // fp32 [imgs][C][M] (r > 1)
   long long* idx = nullptr;    // [imgs][N][k]
+  // tensor-core path: L2-normalised nodes as three bf16 planes in the MMA operand layout + their squared norms
+  __nv_bfloat16* xp = nullptr;
+  __nv_bfloat16* yp = nullptr; // r > 1
+  float* xsq = nullptr;
+  float* ysq = nullptr;        // r > 1
 };
 
 struct BilinearOp {
@@ -383,6 +388,40 @@ int launch_knn(const float* xn, const float* yn, const float* relpos, int B, int
   return STCD_OK;
 }
 
+// bytes of the plane + squared-norm workspace of `rows` nodes x C channels for B images (rows padded to 128)
+size_t knn_planes_bytes(int B, int C, int rows) {
+  return (size_t)B * 3 * stcd::knn_gpad(C) * stcd::knn_rpad(rows, 128) * 16;
+}
+size_t knn_sq_bytes(int B, int rows) { return (size_t)B * stcd::knn_rpad(rows, 128) * sizeof(float); }
+
+// Tensor-core kNN on pre-split planes (knn_prep_kernel + knn_pipe_kernel).  xf / yf: fp32 [B][C][N] / [B][C][M] (yf NULL: y := x).
+// xp / xsq (and yp / ysq when yf is given): zero-initialised workspaces of knn_planes_bytes / knn_sq_bytes.
+int launch_knn_pipe(const float* xf, const float* yf, const float* relpos, int B, int C, int N, int M, int k, int dilation,
+                    __nv_bfloat16* xp, float* xsq, __nv_bfloat16* yp, float* ysq, long long* idx, cudaStream_t st) {
+  const int kd = k * dilation;
+  const int G_pad = stcd::knn_gpad(C), NR = stcd::knn_rpad(N, 128), MR = yf ? stcd::knn_rpad(M, 128) : NR, MP = (M + 15) & ~15;
+  auto ng = [](int B_, int n_) { return (unsigned)std::max(1, std::min(B_ * ((n_ + 31) / 32), 148 * 16)); };
+  stcd::knn_prep_kernel<<<ng(B, N), 256, 0, st>>>(xf, xp, xsq, B, C, N, G_pad, NR);
+  if (yf) stcd::knn_prep_kernel<<<ng(B, M), 256, 0, st>>>(yf, yp, ysq, B, C, M, G_pad, MR);
+  const size_t smem = (size_t)2 * 3 * 4 * (stcd::kKnnTQ + MP) * 16 + 128;
+  const dim3 grid((N + stcd::kKnnTQ - 1) / stcd::kKnnTQ, B);
+#define STCD_KNN_PIPE(KD)                                                                                                      \
+  do {                                                                                                                         \
+    static bool attr_set = false;                                                                                              \
+    if (!attr_set) {                                                                                                           \
+      CUDA_TRY(cudaFuncSetAttribute(stcd::knn_pipe_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));      \
+      attr_set = true;                                                                                                         \
+    }                                                                                                                          \
+    stcd::knn_pipe_kernel<KD><<<grid, 192, smem, st>>>(xp, xsq, NR, yf ? yp : xp, yf ? ysq : xsq, MR, MP, relpos, C, N, M, k, dilation, idx); \
+  } while (0)
+  if (kd <= 9) STCD_KNN_PIPE(9);
+  else if (kd <= 18) STCD_KNN_PIPE(18);
+  else STCD_KNN_PIPE(27);
+#undef STCD_KNN_PIPE
+  CUDA_TRY(cudaGetLastError());
+  return STCD_OK;
+}
+
 int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, float* const* outs, cudaStream_t st,
               cudaEvent_t* ev = nullptr) {
   int op_i = 0;
@@ -427,10 +466,13 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
         stcd::avgpool_nodes_kernel<<<nb((size_t)B * k.c * M, 8), 256, 0, st>>>(k.xf, k.yf, (size_t)B * k.c, ts.h, ts.w, k.r);
         y = k.yf;
       }
-      auto ng = [](int B_, int n_) { return (unsigned)std::max(1, std::min(B_ * ((n_ + 31) / 32), 148 * 16)); };
-      stcd::normalize_nodes_kernel<<<ng(B, N), 256, 0, st>>>(k.xf, k.xn, B, k.c, N);
-      if (k.r > 1) stcd::normalize_nodes_kernel<<<ng(B, M), 256, 0, st>>>(k.yf, k.yn, B, k.c, M);
-      {
+      if (k.xp) {      // tensor-core path: normalise + split once, then the pipelined kernel
+        int r = launch_knn_pipe(k.xf, k.r > 1 ? k.yf : nullptr, k.relpos_dev, B, k.c, N, M, k.k, k.dilation, k.xp, k.xsq, k.yp, k.ysq, k.idx, st);
+        if (r) return r;
+      } else {
+        auto ng = [](int B_, int n_) { return (unsigned)std::max(1, std::min(B_ * ((n_ + 31) / 32), 148 * 16)); };
+        stcd::normalize_nodes_kernel<<<ng(B, N), 256, 0, st>>>(k.xf, k.xn, B, k.c, N);
+        if (k.r > 1) stcd::normalize_nodes_kernel<<<ng(B, M), 256, 0, st>>>(k.yf, k.yn, B, k.c, M);
         int r = launch_knn(k.xn, k.r > 1 ? k.yn : k.xn, k.relpos_dev, B, k.c, N, M, k.k, k.dilation, k.idx, st);
         if (r) return r;
       }
@@ -789,6 +831,10 @@ void stcd_plan_destroy(stcd_plan* plan) {
     if (g.yf) cudaFree(g.yf);
     if (g.xn) cudaFree(g.xn);
     if (g.yn) cudaFree(g.yn);
+    if (g.xp) cudaFree(g.xp);
+    if (g.yp) cudaFree(g.yp);
+    if (g.xsq) cudaFree(g.xsq);
+    if (g.ysq) cudaFree(g.ysq);
     if (g.idx) cudaFree(g.idx);
   }
   if (plan->workspace) cudaFree(plan->workspace);
@@ -1810,8 +1856,22 @@ int stcd_plan_finalize(stcd_plan* plan) {
     const size_t B = (size_t)ts.mult * plan->chunk, N = (size_t)ts.h * ts.w, M = N / (g.r * g.r);
     CUDA_TRY(cudaMalloc(&g.xf, B * g.c * N * sizeof(float)));
     if (g.r > 1) CUDA_TRY(cudaMalloc(&g.yf, B * g.c * M * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&g.xn, B * g.c * N * sizeof(float)));
-    if (g.r > 1) CUDA_TRY(cudaMalloc(&g.yn, B * g.c * M * sizeof(float)));
+    const bool knn_pipe = env_int("STCD_KNN_MMA", 1) != 0 && g.k * g.dilation <= 27 && M <= (size_t)stcd::kKnnM;
+    if (knn_pipe) {
+      CUDA_TRY(cudaMalloc(&g.xp, knn_planes_bytes((int)B, g.c, (int)N)));
+      CUDA_TRY(cudaMemset(g.xp, 0, knn_planes_bytes((int)B, g.c, (int)N)));      // padding rows / groups stay zero for good
+      CUDA_TRY(cudaMalloc(&g.xsq, knn_sq_bytes((int)B, (int)N)));
+      CUDA_TRY(cudaMemset(g.xsq, 0, knn_sq_bytes((int)B, (int)N)));
+      if (g.r > 1) {
+        CUDA_TRY(cudaMalloc(&g.yp, knn_planes_bytes((int)B, g.c, (int)M)));
+        CUDA_TRY(cudaMemset(g.yp, 0, knn_planes_bytes((int)B, g.c, (int)M)));
+        CUDA_TRY(cudaMalloc(&g.ysq, knn_sq_bytes((int)B, (int)M)));
+        CUDA_TRY(cudaMemset(g.ysq, 0, knn_sq_bytes((int)B, (int)M)));
+      }
+    } else {
+      CUDA_TRY(cudaMalloc(&g.xn, B * g.c * N * sizeof(float)));
+      if (g.r > 1) CUDA_TRY(cudaMalloc(&g.yn, B * g.c * M * sizeof(float)));
+    }
     CUDA_TRY(cudaMalloc(&g.idx, B * N * g.k * sizeof(long long)));
     if (!g.relpos.empty()) {
       CUDA_TRY(cudaMalloc(&g.relpos_dev, g.relpos.size() * sizeof(float)));
@@ -2253,6 +2313,19 @@ int stcd_knn_graph(const float* x, const float* y, const float* relpos, int B, i
   }
   DeviceGuard dev_guard(device_of(nn_idx));   // launch where the buffers live
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (env_int("STCD_KNN_MMA", 1) != 0 && k * dilation <= 27) {
+    // tensor-core path: the plane workspace (6 bytes per value, more than `scratch` holds) is taken from and returned to the
+    // stream-ordered pool around the two kernels
+    const size_t xb = knn_planes_bytes(B, C, N), xs = knn_sq_bytes(B, N), yb = y ? knn_planes_bytes(B, C, M) : 0, ys = y ? knn_sq_bytes(B, M) : 0;
+    uint8_t* ws = nullptr;
+    CUDA_TRY(cudaMallocAsync(&ws, xb + xs + yb + ys, st));
+    CUDA_TRY(cudaMemsetAsync(ws, 0, xb + xs + yb + ys, st));
+    int r = launch_knn_pipe(x, y, relpos, B, C, N, M, k, dilation, reinterpret_cast<__nv_bfloat16*>(ws), reinterpret_cast<float*>(ws + xb),
+                            y ? reinterpret_cast<__nv_bfloat16*>(ws + xb + xs) : nullptr, y ? reinterpret_cast<float*>(ws + xb + xs + yb) : nullptr,
+                            reinterpret_cast<long long*>(nn_idx), st);
+    cudaFreeAsync(ws, st);
+    return r;
+  }
   float* xn = scratch;
   float* yn = y ? scratch + (size_t)B * C * N : scratch;
   auto ng = [](int B_, int n_) { return (unsigned)std::max(1, std::min(B_ * ((n_ + 31) / 32), 148 * 16)); };
