@@ -2,11 +2,12 @@
 // dense dilated kNN graph construction and the max-relative aggregation, on the reference's own layout
 // (fp32 node features [B][C][N], N = H*W nodes; int64 neighbour tables).
 //
-// The neighbour ORDER is what the downstream max-relative features depend on, so the distance is computed in
-// fp32 on the CUDA cores with the reference's expression (|x|^2 - 2 x.y + |y|^2 on L2-normalised nodes, plus the
-// relative-position bias) rather than in bf16 on the tensor pipe: a bf16 distance reorders near-equidistant
-// neighbours.  The work is small (N x M x C MACs with M <= 256) and the kernel keeps the whole [64 x M] distance
-// tile in registers -- the dense [B, N, M] tensor of the reference never exists.
+// The neighbour ORDER is what the downstream max-relative features depend on, so the distance keeps fp32 accuracy with
+// the reference's expression (|x|^2 - 2 x.y + |y|^2 on L2-normalised nodes, plus the relative-position bias): a bf16 or tf32
+// distance reorders near-equidistant neighbours.  Two implementations: knn_prep_kernel + knn_pipe_kernel (round 2; tcgen05,
+// the inner products as six MMAs over three exact bf16 planes per operand, top-k from TMEM) for k * dilation <= 27, and
+// knn_graph_kernel (round 1; fp32 FFMA2 on the CUDA cores, the [64 x M] distance tile in registers) for anything else.
+// The dense [B, N, M] tensor of the reference never exists in either.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -220,41 +221,18 @@ __global__ void __launch_bounds__(256) knn_graph_kernel(const float* __restrict_
 // rule (ascending distance, ties to the smaller index, every dilation-th neighbour kept) are those of knn_graph_kernel.
 //
 // One CTA = 128 queries of one image against all M <= 256 keys: D[128 x M] (TMEM, fp32) += X[128 x 16] * Y[M x 16]^T per 16
-// channels and plane pair.  Channels are staged 64 at a time: every thread converts fp32 -> three bf16 planes on the way into
-// shared memory, in the un-swizzled K-major core-matrix layout [plane][c/8][row][8] (8 rows x 16 B contiguous: SBO = 128 B,
-// LBO = rows * 16 B).  Cost: N*M*C*6 MACs at tensor rate -- 30 MMAs of 128 cycles per 128 queries for C = 80 -- against
-// N*M*C fp32 FMAs plus k*dilation warp arg-min rounds over a register tile before (23 % of the ChangeGNNV1 step).
+// channels and plane pair, operands in the un-swizzled K-major core-matrix layout [plane][c/8][row][8] (8 rows x 16 B
+// contiguous: SBO = 128 B, LBO = rows * 16 B).  Cost: N*M*C*6 MACs at tensor rate -- 30 MMAs of 128 cycles per 128 queries for
+// C = 80 -- against N*M*C fp32 FMAs plus k*dilation warp arg-min rounds over a register tile before (23 % of the ChangeGNNV1 step).
 // Epilogue: thread q of warps 0-3 owns query q (= TMEM lane q), walks its M distances in index order and keeps the KD
 // smallest in a sorted register list (insertion with strict '<': an equal distance stays behind the smaller index).
 constexpr int kKnnTQ = 128;    // queries per CTA (= MMA M)
-constexpr int kKnnKC = 64;     // channels staged per step
 
 __device__ __forceinline__ void split3_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo, __nv_bfloat16& lo2) {
   hi = __float2bfloat16_rn(v);
   const float r1 = v - __bfloat162float(hi);          // exact
   lo = __float2bfloat16_rn(r1);
   lo2 = __float2bfloat16_rn(r1 - __bfloat162float(lo));
-}
-
-// rows x 64 channels of a channel-major fp32 matrix src[c][n_total] (row index = n) -> three bf16 planes
-// dst[plane][c/8][row][8]; rows >= n_valid and channels >= C read as zero.
-__device__ __forceinline__ void knn_stage_planes(const float* __restrict__ src, size_t ld, int row0, int n_valid, int rows, int c0, int C,
-                                                 uint8_t* dst, uint32_t plane_bytes) {
-  for (int i = threadIdx.x; i < (kKnnKC / 8) * rows; i += blockDim.x) {
-    const int g = i / rows, r = i - g * rows;
-    const int n = row0 + r;
-    __align__(16) __nv_bfloat16 h[8], l[8], l2[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + g * 8 + j;
-      const float v = (n < n_valid && c < C) ? __ldg(src + static_cast<size_t>(c) * ld + n) : 0.f;
-      split3_bf16(v, h[j], l[j], l2[j]);
-    }
-    uint8_t* o = dst + (static_cast<size_t>(g) * rows + r) * 16;
-    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
-    *reinterpret_cast<uint4*>(o + plane_bytes) = *reinterpret_cast<const uint4*>(l);
-    *reinterpret_cast<uint4*>(o + 2 * static_cast<size_t>(plane_bytes)) = *reinterpret_cast<const uint4*>(l2);
-  }
 }
 
 __device__ __forceinline__ uint64_t knn_desc(uint32_t saddr, uint32_t lbo_bytes) {     // K-major, no swizzle, SBO = 128 B
@@ -266,153 +244,13 @@ __device__ __forceinline__ uint64_t knn_desc(uint32_t saddr, uint32_t lbo_bytes)
   return d;
 }
 
-// grid (ceil(N / 128), B), 256 threads, dynamic shared memory = 3 * 8 * (128 + MP) * 16 bytes (MP = M rounded up to 16)
-template <int KD>
-__global__ void __launch_bounds__(256) knn_mma_kernel(const float* __restrict__ xn, const float* __restrict__ yn,
-                                                      const float* __restrict__ relpos, int C, int N, int M, int k, int dilation,
-                                                      long long* __restrict__ nn_idx) {
-  extern __shared__ uint8_t knn_smem_raw[];
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_ysq[kKnnM];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(knn_smem_raw) + 127) & ~uintptr_t(127));
-  const int b = blockIdx.y, n0 = blockIdx.x * kKnnTQ;
-  const int warp = threadIdx.x >> 5;
-  const int MP = (M + 15) & ~15;
-  const uint32_t x_plane = (kKnnKC / 8) * kKnnTQ * 16, y_plane = (kKnnKC / 8) * static_cast<uint32_t>(MP) * 16;
-  uint8_t* xs = smem;
-  uint8_t* ys = smem + 3 * x_plane;
-  const float* xb = xn + static_cast<size_t>(b) * C * N;
-  const float* yb = yn + static_cast<size_t>(b) * C * M;
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < static_cast<uint32_t>(MP)) tmem_cols <<= 1;
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    tmem_alloc(&tmem_base_smem, tmem_cols);
-    tmem_relinquish();
-  }
-  // |y_j|^2 in channel order, like the reference's x_square / y_square (fp32)
-  for (int j = threadIdx.x; j < kKnnM; j += blockDim.x) {
-    float s = 0.f;
-    if (j < M)
-      for (int c = 0; c < C; ++c) {
-        const float v = __ldg(yb + static_cast<size_t>(c) * M + j);
-        s = fmaf(v, v, s);
-      }
-    s_ysq[j] = s;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_d = tmem_base_smem;
-  const uint32_t idesc = make_idesc_bf16(static_cast<uint32_t>(MP));
-  uint32_t parity = 0;
-  bool first = true;
-  for (int c0 = 0; c0 < C; c0 += kKnnKC) {
-    knn_stage_planes(xb, N, n0, N, kKnnTQ, c0, C, xs, x_plane);
-    knn_stage_planes(yb, M, 0, M, MP, c0, C, ys, y_plane);
-    fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (threadIdx.x == 0) {
-      const int ksteps = (min(kKnnKC, C - c0) + 15) >> 4;
-      const uint32_t xa = smem_u32(xs), ya = smem_u32(ys);
-      // plane pairs (x plane, y plane): hi*hi, hi*lo, lo*hi, lo*lo, hi*lo2, lo2*hi
-      const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
-      for (int ks = 0; ks < ksteps; ++ks) {
-#pragma unroll
-        for (int t = 0; t < 6; ++t) {
-          const uint64_t ad = knn_desc(xa + pa[t] * x_plane + ks * 2 * (kKnnTQ * 16), kKnnTQ * 16);
-          const uint64_t bd = knn_desc(ya + pb[t] * y_plane + ks * 2 * (MP * 16), static_cast<uint32_t>(MP) * 16);
-          umma_bf16(tmem_d, ad, bd, idesc, first ? 0u : 1u);
-          first = false;
-        }
-      }
-      umma_commit(&bar);
-    }
-    mbar_wait(&bar, parity);      // the MMAs of this chunk are done: shared memory may be overwritten, TMEM holds the sums
-    parity ^= 1;
-    tc_fence_after();
-  }
-  if (warp < 4) {
-    const int q = threadIdx.x, n = n0 + q;
-    float xsq = 0.f;
-    if (n < N)
-      for (int c = 0; c < C; ++c) {
-        const float v = __ldg(xb + static_cast<size_t>(c) * N + n);
-        xsq = fmaf(v, v, xsq);
-      }
-    float bv[KD];
-    int bi[KD];
-#pragma unroll
-    for (int t = 0; t < KD; ++t) {
-      bv[t] = CUDART_INF_F;
-      bi[t] = 0x7fffffff;
-    }
-    const uint32_t trow = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
-    const float* rp = (relpos != nullptr && n < N) ? relpos + static_cast<size_t>(n) * M : nullptr;
-    const bool rp_vec = ((M & 3) == 0) && ((reinterpret_cast<uintptr_t>(relpos) & 15) == 0);
-    for (int j0 = 0; j0 < MP; j0 += 16) {
-      uint32_t raw[16];
-      tmem_ld16(trow + j0, raw);
-      float rpv[16];          // this query's relative-position row, 16 keys at a time (requested under the TMEM load)
-      if (rp != nullptr && rp_vec && j0 + 16 <= M) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp + j0) + j);
-          rpv[4 * j] = r4.x, rpv[4 * j + 1] = r4.y, rpv[4 * j + 2] = r4.z, rpv[4 * j + 3] = r4.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) rpv[j] = (rp != nullptr && j0 + j < M) ? __ldg(rp + j0 + j) : 0.f;
-      }
-      tmem_wait_ld();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int key = j0 + j;
-        // the reference's order of operations: (x_sq + (-2 * inner)) + y_sq, then + relative_pos
-        float dv = __fadd_rn(__fadd_rn(xsq, -2.f * __uint_as_float(raw[j])), s_ysq[key]);
-        if (rp != nullptr) dv = __fadd_rn(dv, rpv[j]);
-        if (key >= M) dv = CUDART_INF_F;
-        if (dv < bv[KD - 1]) {          // strict: an equal distance stays behind the earlier (smaller) index
-          bv[KD - 1] = dv;
-          bi[KD - 1] = key;
-#pragma unroll
-          for (int t = KD - 1; t > 0; --t) {
-            const bool sw = bv[t] < bv[t - 1];
-            const float tv = sw ? bv[t - 1] : bv[t];
-            const int ti = sw ? bi[t - 1] : bi[t];
-            bv[t - 1] = sw ? bv[t] : bv[t - 1];
-            bi[t - 1] = sw ? bi[t] : bi[t - 1];
-            bv[t] = tv;
-            bi[t] = ti;
-          }
-        }
-      }
-    }
-    if (n < N) {
-      long long* o = nn_idx + (static_cast<size_t>(b) * N + n) * k;
-#pragma unroll
-      for (int t = 0; t < KD; ++t)
-        if (t % dilation == 0 && t / dilation < k) o[t / dilation] = bi[t];
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
-}
-
 // ------------------------------------------------------------------------------------------
-// Pipelined form of the tensor-core kNN: the operands are normalised and split into their three bf16 planes ONCE per graph op
-// by knn_prep_kernel (it replaces normalize_nodes_kernel on this path), stored in global memory in the shared-memory operand
-// layout, and knn_pipe_kernel only moves them: a producer warp issues 1-D bulk copies into a two-stage ring, an MMA warp
-// issues the six products per 16 channels, four epilogue warps select the neighbours from TMEM.  The first version staged
-// and converted fp32 inside the kernel, single-buffered, and re-read the squared norms from L2 per CTA: the tensor pipe
-// waited on serial load latency (C4: graph ops 4.46 -> 3.85 ms only).
+// The operands are normalised and split into their three bf16 planes ONCE per graph op by knn_prep_kernel (it replaces
+// normalize_nodes_kernel on this path), stored in global memory in the shared-memory operand layout, and knn_pipe_kernel
+// only moves them: a producer warp issues 1-D bulk copies into a two-stage ring, an MMA warp issues the six products per 16
+// channels, four epilogue warps select the neighbours from TMEM.  (A first version staged and converted fp32 inside the
+// kernel, single-buffered, and re-read the squared norms from L2 per CTA: the tensor pipe waited on serial load latency and
+// the ChangeGNNV1 graph ops only went 4.46 -> 3.85 ms; this form takes them to 2.96 ms.)
 //
 // planes: bf16 [B][3 planes][G_pad = groups of 8 channels, padded to a multiple of 4][R_pad rows][8]; sq: fp32 [B][R_pad]
 // (R_pad = rows rounded up to 128: queries are copied 128 at a time, keys MP = M rounded up to 16 at a time; y := x shares x's planes).

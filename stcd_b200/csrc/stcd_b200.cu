@@ -358,32 +358,10 @@ int launch_conv(const stcd_plan* plan, const ConvOp& op, int n_valid, float* con
   return STCD_OK;
 }
 
-// Dense dilated kNN: the tensor-core kernel (csrc/graph_kernels.cuh knn_mma_kernel) for k * dilation <= 27 (the Grapher's
-// 9 / 18 / 27), else -- or with STCD_KNN_MMA=0 -- the fp32 register-tile kernel.
+// Dense dilated kNN, fp32 register-tile kernel (k * dilation > 27, or STCD_KNN_MMA=0)
 int launch_knn(const float* xn, const float* yn, const float* relpos, int B, int C, int N, int M, int k, int dilation, long long* idx,
                cudaStream_t st) {
-  const int kd = k * dilation;
-  static const int use_mma = env_int("STCD_KNN_MMA", 1);
-  if (use_mma && kd <= 27 && M <= stcd::kKnnM) {
-    const int MP = (M + 15) & ~15;
-    const size_t smem = (size_t)3 * (stcd::kKnnKC / 8) * (stcd::kKnnTQ + MP) * 16 + 128;
-    const dim3 grid((N + stcd::kKnnTQ - 1) / stcd::kKnnTQ, B);
-#define STCD_KNN_LAUNCH(KD)                                                                                                   \
-    do {                                                                                                                       \
-      static bool attr_set = false;                                                                                            \
-      if (!attr_set) {                                                                                                         \
-        CUDA_TRY(cudaFuncSetAttribute(stcd::knn_mma_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));     \
-        attr_set = true;                                                                                                       \
-      }                                                                                                                        \
-      stcd::knn_mma_kernel<KD><<<grid, 256, smem, st>>>(xn, yn, relpos, C, N, M, k, dilation, idx);                            \
-    } while (0)
-    if (kd <= 9) STCD_KNN_LAUNCH(9);
-    else if (kd <= 18) STCD_KNN_LAUNCH(18);
-    else STCD_KNN_LAUNCH(27);
-#undef STCD_KNN_LAUNCH
-  } else {
-    stcd::knn_graph_kernel<<<dim3((N + stcd::kKnnQ - 1) / stcd::kKnnQ, B), 256, 0, st>>>(xn, yn, relpos, C, N, M, k, dilation, idx);
-  }
+  stcd::knn_graph_kernel<<<dim3((N + stcd::kKnnQ - 1) / stcd::kKnnQ, B), 256, 0, st>>>(xn, yn, relpos, C, N, M, k, dilation, idx);
   CUDA_TRY(cudaGetLastError());
   return STCD_OK;
 }
