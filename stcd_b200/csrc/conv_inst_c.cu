@@ -1,4 +1,4 @@
-// conv_ws_kernel instances, part C (see STCD_CONV_INSTANCES_C in conv_ws.cuh): one of five translation units
+// conv_ws_kernel instances, part C (see STCD_CONV_INSTANCES_C in conv_ws.cuh): one of six translation units
 // compiled in parallel.
 #include "conv_ws.cuh"
 

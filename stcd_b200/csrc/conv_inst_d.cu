@@ -1,4 +1,4 @@
-// conv_ws_kernel instances, part D (see STCD_CONV_INSTANCES_D in conv_ws.cuh): one of five translation units
+// conv_ws_kernel instances, part D (see STCD_CONV_INSTANCES_D in conv_ws.cuh): one of six translation units
 // compiled in parallel.
 #include "conv_ws.cuh"
 

@@ -46,6 +46,7 @@ constexpr int kMaxWStages = 16;
 constexpr int kMaxChunks = 128;  // A-stage loads per phase
 constexpr int kMaxTaps = 512;    // weight blocks per phase (split precision triples the K-program: 1024 channels x 9 taps / 64 x 3 = 432)
 constexpr int kConvThreads = 256;   // 8 warps: A producer, W producer, MMA issuer, 4 epilogue warps, residual producer
+constexpr int kConvThreads8 = 384;  // 12 warps: the same with 8 epilogue warps (one CTA per SM)
 constexpr int kFastMma = 36;     // per-chunk MMA offsets kept in the constant bank (9 taps x 4 K steps)
 constexpr int kMaxRSlots = 8;    // residual blocks in flight (TMA -> shared-memory ring)
 // Horizontally folded 3x3 convs (E_XF): the tile is 8 rows x 16 columns of INPUT positions, of which the inner 14 columns
@@ -220,9 +221,16 @@ struct ChunkMma {    // MMA issuer
 
 // MT = M tiles (images) per CTA pass sharing every weight block; MS = 2 when consecutive sub-tiles are
 // (T1, T2) Siamese pairs (the |f1 - f2| epilogue needs both), else 1.
-template <int MT, int MS, uint32_t EPI>
-__global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_constant__ TmapPack tm,
-                                                                  const __grid_constant__ ConvParams p) {
+// NE = epilogue warps: 4 (one per TMEM lane quarter; two CTAs per SM) or 8 (two per quarter, alternating 16-column steps;
+// 384 threads, one CTA per SM).  With one epilogue warp per scheduler every instruction of the step waits out its own latency
+// (ncu: 8.9 cycles per issued instruction, the MMA warp idle 58 % of the time on the short-K residual layers); plans that run
+// one CTA per SM anyway take the eight-warp instances where they exist.
+template <int MT, int MS, uint32_t EPI, int NE = 4>
+__global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 8 ? 1 : 2) conv_ws_kernel(const __grid_constant__ TmapPack tm,
+                                                                                                           const __grid_constant__ ConvParams p) {
+  static_assert(NE == 4 || NE == 8, "4 or 8 epilogue warps");
+  static_assert(NE == 4 || ((EPI & E_RSM) != 0 || (EPI & E_RES) == 0), "eight epilogue warps: residual through the ring only");
+  constexpr int kResWarp = 3 + NE;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
   __shared__ __align__(8) uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
@@ -328,11 +336,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], NE);
     }
     for (int s = 0; s < kMaxRSlots; ++s) {
       mbar_init(&r_full[s], 1);
-      mbar_init(&r_empty[s], 4);
+      mbar_init(&r_empty[s], NE);
     }
     fence_mbar_init();
   }
@@ -559,7 +567,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       }
     }
     __syncwarp();
-  } else if (warp == 7) {
+  } else if (warp == kResWarp) {
     // ============================== residual producer (TMA) ==============================
     if (p.res_slots) {
       const bool leader = elect_one();
@@ -596,7 +604,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
       }
       __syncwarp();
     }
-  } else if (warp < 7) {
+  } else if (warp < kResWarp) {
     // ============================== epilogue (warps 3..6) ==============================
     const bool has_raw = STCD_HAS(E_RAW, p.out_raw != nullptr);
     const bool has_aff2 = STCD_HAS(E_AFF2, p.scale2 != nullptr);
@@ -644,6 +652,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
     // written by the previous kernel without going through the A producer's dependency wait
     if (res_rg || (has_res && split)) pdl_wait();
     const int wq = warp & 3;  // TMEM lane quarter this warp may access
+    const int my_half = (warp - 3) >> 2;   // NE == 8: the two warps of a quarter take alternate 16-column steps
     // pixel of the tile this thread (= TMEM lane 32 * wq + lane) owns: 4 lines of 8 per warp, or (XF) 2 lines of 16
     const int ty = XF ? 2 * wq + (lane >> 4) : 4 * wq + (lane >> 3);
     const int tx = XF ? (lane & 15) : (lane & 7);
@@ -716,6 +725,21 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
         size_t im[MS];                       // image index of each sub-tile of this group
 #pragma unroll
         for (int m = 0; m < MS; ++m) im[m] = static_cast<size_t>(img + p.m_off[mb + m]);
+        // Per-(sub-tile) base pointers and per-step offsets that only ADD inside the channel loop: the 64-bit index products
+        // were recomputed every 16-column step (75 IMADs per step in the SASS of the residual instance -- dependent chains that
+        // one epilogue warp per scheduler cannot hide).
+        __nv_bfloat16* b_out0[MS];
+        __nv_bfloat16* b_raw[MS];
+        __nv_bfloat16* b_pool[MS];
+#pragma unroll
+        for (int m = 0; m < MS; ++m) {
+          b_out0[m] = has_out0 ? q_out0 + im[m] * p.out0_c8 * hw0 * 8 : nullptr;
+          b_raw[m] = has_raw ? q_raw + im[m] * p.out_raw_c8 * hw * 8 : nullptr;
+          b_pool[m] = has_pool ? q_pool + im[m] * p.out_pool_c8 * hw_pool * 8 : nullptr;
+        }
+        __nv_bfloat16* const b_diff = has_diff ? q_diff + im[0] * p.out_diff_c8 * hw * 8 : nullptr;
+        const size_t st_hw = static_cast<size_t>(hw) * 16, st_hw0 = static_cast<size_t>(hw0) * 16, st_pool = static_cast<size_t>(hw_pool) * 16;
+        size_t off_hw = 0, off_hw0 = 0, off_pool = 0;      // element offset of the step's first 8-channel group in planes of hw / hw0 / hw_pool pixels
         uint4 r_cur[MS][2], r_nxt[MS][2], r_pf[PF > 1 ? PF - 1 : 1][MS][2];
         auto load_res = [&](int c0, uint4 (&dst)[MS][2]) {
 #pragma unroll
@@ -792,6 +816,8 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
           const int ch = n0 + c0;
           if (ch >= p.cout) break;
           const bool two = (p.cout - ch) > 8;  // both 8-channel groups of this 16-column step are real
+          const bool mine = (NE == 4) || (((c0 >> 4) & 1) == my_half);   // NE == 8: the other warp of this quarter does the odd / even steps
+          if (mine) {
           if (res_rg && valid && c0 + 16 >= 16 * PF && c0 + 16 < c_lim && ch + 16 < p.cout) load_res(c0 + 16, r_nxt);
           uint32_t raw[MS][16];
           // Everything that comes from shared memory -- the column affines and, with the residual ring, the residual -- is
@@ -814,7 +840,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
           }
           if (res_sm) {
             // slot in shared memory: [MS sub-tiles][res_rb / 8][tile rows][tile px] x 16 B -- consecutive lanes, consecutive 16 B
-            if ((c0 & rb_mask) == 0) mbar_wait_relaxed(&r_full[ers], erpar);     // a new block of this group
+            if ((c0 & rb_mask) == 0 || (NE == 8 && (c0 & rb_mask) == 16)) mbar_wait_relaxed(&r_full[ers], erpar);     // a new block of this group (NE == 8: this warp's first step of it)
             const uint32_t rt = smem_u32(smem_r) + static_cast<uint32_t>(ers) * p.res_slot_bytes +
                                 (static_cast<uint32_t>((c0 & rb_mask) >> 3) * (TH * TW) + ty * TW + tx) * 16u;
 #pragma unroll
@@ -855,8 +881,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
               v[m][4 * j + 3] = fmaf(__uint_as_float(raw[m][4 * j + 3]), a_sc[j].w, a_sh[j].w);
             }
             if (has_raw && valid) {
-              __nv_bfloat16* o = q_raw + (im[m] * p.out_raw_c8 + g8) * hw * 8;
-              store16(o, static_cast<size_t>(hw) * 8, static_cast<size_t>(p.out_raw_c8 >> 1) * hw * 8, v[m], two);
+              store16(b_raw[m] + off_hw, static_cast<size_t>(hw) * 8, static_cast<size_t>(p.out_raw_c8 >> 1) * hw * 8, v[m], two);
             }
             if (has_aff2) {
               if (act_pre) apply_act(v[m]);
@@ -899,8 +924,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             }
             if ((has_out0 || has_pool) && split) {
               if (has_out0 && valid) {
-                __nv_bfloat16* o = q_out0 + (im[m] * p.out0_c8 + g8) * hw0 * 8;
-                store16(o, static_cast<size_t>(hw0) * 8, static_cast<size_t>(p.out0_c8 >> 1) * hw0 * 8, v[m], two);
+                store16(b_out0[m] + off_hw0, static_cast<size_t>(hw0) * 8, static_cast<size_t>(p.out0_c8 >> 1) * hw0 * 8, v[m], two);
               }
               if (has_pool) {
                 float vp[16];      // the pooled value must be formed in fp32: max does not commute with the (hi, lo) split
@@ -910,8 +934,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
                   vp[j] = fmaxf(a, __shfl_down_sync(0xffffffffu, a, XF ? 16 : 8));
                 }
                 if (valid && (XF ? ((lane & 17) == 1) : ((lane & 9) == 0))) {
-                  __nv_bfloat16* o = q_pool + (im[m] * p.out_pool_c8 + g8) * hw_pool * 8;
-                  store16(o, static_cast<size_t>(hw_pool) * 8, static_cast<size_t>(p.out_pool_c8 >> 1) * hw_pool * 8, vp, two);
+                  store16(b_pool[m] + off_pool, static_cast<size_t>(hw_pool) * 8, static_cast<size_t>(p.out_pool_c8 >> 1) * hw_pool * 8, vp, two);
                 }
               }
             } else if (has_out0 || has_pool) {
@@ -928,7 +951,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
                     if (p.fold_cout - chn > 8) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw) * 8) = hi;
                   }
                 } else {
-                  __nv_bfloat16* o = q_out0 + (im[m] * p.out0_c8 + g8) * hw0 * 8;
+                  __nv_bfloat16* o = b_out0[m] + off_hw0;
                   *reinterpret_cast<uint4*>(o) = lo;
                   if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw0) * 8) = hi;
                 }
@@ -939,7 +962,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
                 // output column of a tile is lane 1 (tile origins are even, so even output columns sit on odd lanes)
                 const uint4 plo = pool4_bf16x2<1, XF ? 16 : 8>(lo), phi = pool4_bf16x2<1, XF ? 16 : 8>(hi);
                 if (valid && (XF ? ((lane & 17) == 1) : ((lane & 9) == 0))) {
-                  __nv_bfloat16* o = q_pool + (im[m] * p.out_pool_c8 + g8) * hw_pool * 8;
+                  __nv_bfloat16* o = b_pool[m] + off_pool;
                   *reinterpret_cast<uint4*>(o) = plo;
                   if (two) *reinterpret_cast<uint4*>(o + static_cast<size_t>(hw_pool) * 8) = phi;
                 }
@@ -950,8 +973,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
             float d[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) d[j] = fabsf(v[0][j] - v[MS - 1][j]);
-            __nv_bfloat16* o = q_diff + (im[0] * p.out_diff_c8 + g8) * hw * 8;
-            store16(o, static_cast<size_t>(hw) * 8, static_cast<size_t>(p.out_diff_c8 >> 1) * hw * 8, d, two);
+            store16(b_diff + off_hw, static_cast<size_t>(hw) * 8, static_cast<size_t>(p.out_diff_c8 >> 1) * hw * 8, d, two);
           }
           if (res_rg) {
             const int nstep = (c0 >> 4) + 1;               // steps 1 .. PF-1 were prefetched with step 0
@@ -968,6 +990,10 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_ws_kernel(const __grid_c
               r_cur[m][1] = b;
             }
           }
+          }   // mine
+          off_hw += st_hw;
+          off_hw0 += st_hw0;
+          off_pool += st_pool;
           if (res_sm && (((c0 + 16) & rb_mask) == 0 || c0 + 16 >= n_ch_epi)) {
             // the last step of this residual block: hand the slot back to the residual producer
             __syncwarp();
@@ -1006,11 +1032,12 @@ struct ConvKernelEntry {
   int mt, ms;
   uint32_t epi;
   ConvKernelFn fn;
+  int ne;        // epilogue warps (4 or 8)
 };
 
 // Specialised instances for the (M tiles, pairing, epilogue) combinations the lowered nets use;
 // anything else runs the generic instance (same code, epilogue features read from ConvParams at
-// run time).  The instances are compiled in five translation units (conv_inst_{a..e}.cu, built in
+// run time).  The instances are compiled in six translation units (conv_inst_{a..f}.cu, built in
 // parallel); conv_kernel_table() in stcd_b200.cu concatenates their tables.  X(MT, MS, EPI)
 #define STCD_CONV_INSTANCES_A(X)                       \
   /* FC-Siam encoder (Siamese pairs) */                \
@@ -1106,19 +1133,32 @@ struct ConvKernelEntry {
   X(2, 1, E_XF | E_GENERIC)                            \
   X(4, 1, E_XF | E_GENERIC)
 
+#define STCD_CONV_INSTANCES_F(X)                       \
+  /* eight epilogue warps (one CTA per SM): the short-K residual layers of the nested blocks and of the ResNet encoders */ \
+  X(1, 1, E_RES | E_RSM | E_RELU | E_OUT0)             \
+  X(2, 1, E_RES | E_RSM | E_RELU | E_OUT0)             \
+  X(4, 1, E_RES | E_RSM | E_RELU | E_OUT0)             \
+  X(2, 2, E_RES | E_RSM | E_RELU | E_OUT0 | E_POOL)    \
+  X(4, 2, E_RES | E_RSM | E_RELU | E_OUT0 | E_POOL)    \
+  X(2, 2, E_RES | E_RSM | E_RELU | E_OUT0)             \
+  X(4, 2, E_RES | E_RSM | E_RELU | E_OUT0)
+
 // one table per translation unit
+const ConvKernelEntry* conv_kernel_table_f(int* n);
 const ConvKernelEntry* conv_kernel_table_e(int* n);
 const ConvKernelEntry* conv_kernel_table_a(int* n);
 const ConvKernelEntry* conv_kernel_table_b(int* n);
 const ConvKernelEntry* conv_kernel_table_c(int* n);
 const ConvKernelEntry* conv_kernel_table_d(int* n);
 
-#define STCD_DEFINE_CONV_TABLE(NAME, LIST)                                                   \
+#define STCD_DEFINE_CONV_TABLE_WITH(NAME, LIST, ENTRY)                                       \
   const ConvKernelEntry* NAME(int* n) {                                                      \
-    static const ConvKernelEntry table[] = {LIST(STCD_CONV_TABLE_ENTRY)};                    \
+    static const ConvKernelEntry table[] = {LIST(ENTRY)};                                    \
     *n = static_cast<int>(sizeof(table) / sizeof(table[0]));                                 \
     return table;                                                                            \
   }
-#define STCD_CONV_TABLE_ENTRY(MT_, MS_, EPI_) {MT_, MS_, (EPI_), conv_ws_kernel<MT_, MS_, (EPI_)>},
+#define STCD_DEFINE_CONV_TABLE(NAME, LIST) STCD_DEFINE_CONV_TABLE_WITH(NAME, LIST, STCD_CONV_TABLE_ENTRY)
+#define STCD_CONV_TABLE_ENTRY(MT_, MS_, EPI_) {MT_, MS_, (EPI_), conv_ws_kernel<MT_, MS_, (EPI_)>, 4},
+#define STCD_CONV_TABLE_ENTRY8(MT_, MS_, EPI_) {MT_, MS_, (EPI_), conv_ws_kernel<MT_, MS_, (EPI_), 8>, 8},
 
 }  // namespace stcd

@@ -84,6 +84,7 @@ struct ConvOp {
   int mt = 1;
   uint32_t epi = 0;
   stcd::ConvKernelFn fn = nullptr;
+  int threads = 256;           // 256 (four epilogue warps) or 384 (eight)
   long long* trace = nullptr;
 };
 
@@ -345,7 +346,7 @@ int launch_conv(const stcd_plan* plan, const ConvOp& op, int n_valid, float* con
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = op.grid;
-  cfg.blockDim = dim3(stcd::kConvThreads, 1, 1);
+  cfg.blockDim = dim3(op.threads, 1, 1);
   cfg.dynamicSmemBytes = op.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1533,7 +1534,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
   if (all_kernels.empty()) {
     using TableFn = const stcd::ConvKernelEntry* (*)(int*);
     for (TableFn fn : {stcd::conv_kernel_table_a, stcd::conv_kernel_table_b, stcd::conv_kernel_table_c, stcd::conv_kernel_table_d,
-                       stcd::conv_kernel_table_e}) {
+                       stcd::conv_kernel_table_e, stcd::conv_kernel_table_f}) {
       int n = 0;
       const stcd::ConvKernelEntry* t = fn(&n);
       all_kernels.insert(all_kernels.end(), t, t + n);
@@ -1799,8 +1800,16 @@ int stcd_plan_finalize(stcd_plan* plan) {
              (d.out_diff >= 0 ? stcd::E_DIFF : 0u) | (d.out_ext >= 0 ? stcd::E_F32 : 0u) |
              ((d.relu >= 2 || d.act_pre) ? stcd::E_ACTX : 0u) | (p.res_slots ? stcd::E_RSM : 0u) | (xf ? stcd::E_XF : 0u);
     op.fn = nullptr;
+    op.threads = stcd::kConvThreads;
+    // plans that run one CTA per SM anyway take the eight-epilogue-warp instance when there is one (>= 2 column steps to share)
+    const bool want8 = occ == 1 && d.n_tile >= 32 && env_int("STCD_EPI8", 1) != 0;
     for (int i = 0; i < n_kernels && !force_generic && !d.split; ++i)     // split precision lives in the generic instances
-      if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == op.epi) op.fn = kernels[i].fn;
+      if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == op.epi && (kernels[i].ne == 4 || want8)) {
+        if (op.fn && kernels[i].ne == 4) continue;       // an eight-warp instance found earlier wins
+        op.fn = kernels[i].fn;
+        op.threads = kernels[i].ne == 8 ? stcd::kConvThreads8 : stcd::kConvThreads;
+        if (kernels[i].ne == 8) break;
+      }
     for (int i = 0; i < n_kernels && !op.fn; ++i)
       if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == (stcd::E_GENERIC | (xf ? stcd::E_XF : 0u))) op.fn = kernels[i].fn;
     if (!op.fn) return fail(STCD_ERR_INVALID, "no conv kernel instance for mt=%d", op.mt);

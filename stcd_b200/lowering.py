@@ -765,7 +765,8 @@ def xf_taps(name: str, segs: Sequence[Segment], phase_taps, cout: int, pair: boo
     if pair:
         return None
     # Cost model (cycles per output pixel, measured MMA costs: tools/ubench/mma_n.cu).  The folded form reads 3x the accumulator
-    # columns from TMEM (64 B/clk per SM: 24 * cs cycles per tile) and shuffles them, so it only pays once the tile's MMAs
+    # columns from TMEM (tools/ubench/tmem_read.cu: one 32-lane x 16-column load per 43 cycles and warp) and shuffles them --
+    # an epilogue cost of ~24 * cs + 200 cycles per tile fits the measured crossovers -- so it only pays once the tile's MMAs
     # outlast that: e.g. Cout 32 from >= 48 input channels, Cout 16 from >= 32 (measured: SNUNet conv0_x.conv1, 128-224 input
     # channels, 907 -> 622 us; conv0_x.conv2, 32 input channels, 166 -> 222 us).
     k16 = sum((s.c_real + 15) // 16 for s in segs)
