@@ -413,22 +413,31 @@ __global__ void __launch_bounds__(192) knn_pipe_kernel(const __nv_bfloat16* __re
     const uint32_t trow = tmem_d + (static_cast<uint32_t>(warp * 32) << 16);
     const float* rp = (relpos != nullptr && n < N) ? relpos + static_cast<size_t>(n) * M : nullptr;
     const bool rp_vec = ((M & 3) == 0) && ((reinterpret_cast<uintptr_t>(relpos) & 15) == 0);
+    // this query's relative-position row, 16 keys at a time, fetched ONE CHUNK AHEAD (the first chunk before the accumulator
+    // is even complete): read at the point of use, every chunk exposed a full L2 round trip -- 16 of them per query
+    auto load_rp = [&](int j0, float (&dst)[16]) {
+      if (rp != nullptr && rp_vec && j0 + 16 <= M) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp + j0) + j);
+          dst[4 * j] = r4.x, dst[4 * j + 1] = r4.y, dst[4 * j + 2] = r4.z, dst[4 * j + 3] = r4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[j] = (rp != nullptr && j0 + j < M) ? __ldg(rp + j0 + j) : 0.f;
+      }
+    };
+    float rp_nxt[16];
+    load_rp(0, rp_nxt);
     mbar_wait_relaxed(&acc_full, 0);
     tc_fence_after();
     for (int j0 = 0; j0 < MP; j0 += 16) {
       uint32_t raw[16];
       tmem_ld16(trow + j0, raw);
-      float rpv[16];          // this query's relative-position row, 16 keys at a time (requested under the TMEM load)
-      if (rp != nullptr && rp_vec && j0 + 16 <= M) {
+      float rpv[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp + j0) + j);
-          rpv[4 * j] = r4.x, rpv[4 * j + 1] = r4.y, rpv[4 * j + 2] = r4.z, rpv[4 * j + 3] = r4.w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) rpv[j] = (rp != nullptr && j0 + j < M) ? __ldg(rp + j0 + j) : 0.f;
-      }
+      for (int j = 0; j < 16; ++j) rpv[j] = rp_nxt[j];
+      if (j0 + 16 < MP) load_rp(j0 + 16, rp_nxt);
       tmem_wait_ld();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {

@@ -10,7 +10,9 @@ from stcd_b200.plan import Plan
 
 H = W = 256
 chunk = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-net = synth.randomize_(siamunet.SiamUnet_diff(3, 2).eval(), gain=synth.GAINS["SiamUnet_diff"])
+from stcd_b200 import snunet
+which = os.environ.get("STCD_TRACE_NET", "siam")
+net = synth.prepare_(snunet.SNUNet_ECAM(3, 2).eval(), "SNUNet_ECAM") if which == "snunet" else synth.randomize_(siamunet.SiamUnet_diff(3, 2).eval(), gain=synth.GAINS["SiamUnet_diff"])
 prog = net.lower(H, W)
 plan = Plan(prog, chunk)
 x1, x2 = synth.image_pairs(chunk, H, W)
