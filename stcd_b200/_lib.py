@@ -239,7 +239,10 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if needs_build():
+    override = os.environ.get("STCD_LIB")      # development: A/B a previously built library (tools/r2_ab.sh); never set in tests / bench
+    if override:
+        handle = C.CDLL(override)
+    elif needs_build():
         try:
             build()
         except (StcdError, FileNotFoundError) as e:
@@ -251,7 +254,8 @@ def lib() -> C.CDLL:
                                 f"(set STCD_ALLOW_STALE=1 to load it anyway): {e}") from e
             import warnings
             warnings.warn(f"loading a STALE libstcd_b200.so (rebuild failed: {e})", RuntimeWarning)
-    handle = C.CDLL(str(LIB_PATH))
+    if not override:
+        handle = C.CDLL(str(LIB_PATH))
     for name, restype, argtypes in SYMBOLS:
         fn = getattr(handle, name)
         fn.restype = restype

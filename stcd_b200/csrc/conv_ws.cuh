@@ -162,6 +162,8 @@ struct ConvParams {
   uint32_t f_a_lo_lbo[kMaxPhase];    // A descriptor LBO field
   uint32_t f_b_chunk16[kMaxPhase];   // weight bytes per chunk >> 4
   alignas(16) uint32_t f_off[kMaxPhase][36];  // A offset (16 B units) | B offset inside the chunk's weights << 16
+  int32_t xf_fast;   // E_XF: 1 = this op's issuer runs the register-resident chunk loop (chosen per op by the plan)
+  int32_t xf_issuers;  // E_XF without a residual: 2 = the residual producer's warp issues the odd tiles (1: one issuer)
   int32_t dbg;       // diagnostics (STCD_DBG): bit0 skip MMAs
   long long* trace;  // diagnostics (STCD_TRACE=1): 16 clock stamps per CTA, else nullptr
 };
@@ -217,6 +219,11 @@ struct ChunkMma {    // MMA issuer
   uint32_t n_mma;      // MMAs (per M tile) this chunk feeds = taps * K steps
 };
 
+template <int N>
+struct IntC {
+  static constexpr int value = N;
+};
+
 #define STCD_HAS(flag, runtime_expr) ((EPI & E_GENERIC) ? (runtime_expr) : ((EPI & (flag)) != 0))
 
 // MT = M tiles (images) per CTA pass sharing every weight block; MS = 2 when consecutive sub-tiles are
@@ -251,6 +258,8 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
   long long* tr = p.trace ? p.trace + ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
   const long long clk0 = clock64();
 #define STCD_STAMP(i) do { if (tr) tr[i] = clock64() - clk0; } while (0)
+  // trace mode: cycles a role spends inside one of its waits, summed over the CTA's tiles (slots 12..15 of the trace record)
+#define STCD_TWAIT(call, counter) do { if (tr) { const long long w0_ = clock64(); call; counter += clock64() - w0_; } else { call; } } while (0)
   if (tr && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -274,7 +283,34 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
   const uint8_t* wsrc = p.wpack + (static_cast<size_t>(nt) * p.blocks_per_ntile + phase.w_block) * p.wblk_bytes;
   const int w_per = (phase.n_blocks + kMaxWStages - 1) / kMaxWStages;  // resident mode: blocks per barrier slot
 
-  if (threadIdx.x == 32) {
+  // CTA set-up, spread over the warps so that none of it is serial (trace, round 2: 4 500-4 900 cycles = 2.4 us per CTA when one
+  // thread initialised ~56 barriers after the table loop and the TMEM allocation came last; at 8 pairs every layer of the
+  // FC-Siam nets is 10-28 us, so the set-up is on the critical path 25 times per step): the dependent grid is released first
+  // (its own prologue does not read our outputs), warp 2 allocates TMEM, warp 3 initialises the barriers (<= 8 per lane), a
+  // thread of warp 4 prefetches the tensor maps, and every thread builds its share of the tables below.
+  pdl_launch_dependents();
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tmem_relinquish();
+  } else if (warp == 3) {
+    if (lane < p.a_stages) {
+      mbar_init(&a_full[lane], 1);
+      mbar_init(&a_empty[lane], 1);
+    }
+    if (lane < kMaxWStages) {
+      mbar_init(&w_full[lane], 1);
+      mbar_init(&w_empty[lane], 1);
+    }
+    if (lane < 2) {
+      mbar_init(&acc_full[lane], 1);
+      mbar_init(&acc_empty[lane], NE);
+    }
+    if (lane < kMaxRSlots) {
+      mbar_init(&r_full[lane], 1);
+      mbar_init(&r_empty[lane], NE);
+    }
+    fence_mbar_init();
+  } else if (threadIdx.x == 128) {
     for (int i = 0; i < p.n_src; ++i) tma_prefetch_desc(&tm.src[i]);
     if (p.res_slots) tma_prefetch_desc(&tm.res);
   }
@@ -325,44 +361,110 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
     s_aff[2][i] = p.scale2 ? p.scale2[n0 + i] : 1.f;
     s_aff[3][i] = p.shift2 ? p.shift2[n0 + i] : 0.f;
   }
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < p.a_stages; ++s) {
-      mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 1);
-    }
-    for (int s = 0; s < kMaxWStages; ++s) {
-      mbar_init(&w_full[s], 1);
-      mbar_init(&w_empty[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], NE);
-    }
-    for (int s = 0; s < kMaxRSlots; ++s) {
-      mbar_init(&r_full[s], 1);
-      mbar_init(&r_empty[s], NE);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(&tmem_base_smem, p.tmem_cols);
-    tmem_relinquish();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   if (threadIdx.x == 0) STCD_STAMP(1);
   // Programmatic dependent launch: everything above (tables, barriers, TMEM) and the weight loads
-  // below do not depend on the previous layer, so the next kernel may start its own prologue now;
-  // only the activation loads wait for the previous kernel to finish.
-  pdl_launch_dependents();
+  // below do not depend on the previous layer; only the activation loads wait for the previous kernel to finish.
+
+  long long tw_a = 0, tw_acc = 0;     // trace mode (issuer warp): cycles waited for operands / for a free accumulator
+  // ---- Horizontally folded layers: the issue loop, shared by the issuer warp(s).
+  // A chunk is one 16..64-channel block of one source = 3 filter rows x (1, 2 or 4) K steps.  ncu's source view
+  // (profiles/r2_src_conv0_4_conv1.txt) showed the issuer as a pacing role -- never waiting for an operand, ~86 instructions per
+  // 6-MMA chunk, two divergent regions and two constant-bank loads per chunk.  Here the chunk's operand offsets live in
+  // registers for the whole kernel, the chunk is ONE divergent region and the weight base advances by an add: conv0_2..4.conv1
+  // of SNUNet (4-6 chunks per tile) -5 .. -10 %, conv0_1.conv1 (3 chunks) +7 .. +13 % in the same A/B runs, so the plan switches
+  // it on from 4 chunks per tile (STCD_XF_FAST_MIN).  (The same loop measured 11-17 % SLOWER than the table loop on the Siamese
+  // 3x3 layers, so it stays with the folded instances.)
+  // TWO ISSUERS.  One warp retires a dependent instruction every ~10 cycles, so one issuer cannot keep the tensor pipe fed on
+  // these layers (pipe 53-59 % occupied, the issuer never idle).  Instances without a residual leave the residual producer's
+  // warp free: it issues the ODD tiles of the CTA (accumulator set 1) while warp 2 issues the even ones (set 0).  The A ring is
+  // split in two, one sub-ring per issuer, and the producer feeds tiles t and t + 1 chunk by chunk in turn -- two independent
+  // single-producer / single-consumer pipelines, so every barrier still has exactly one waiter that sees each of its phases
+  // (an issuer skipping the other's ring positions would wait on a phase parity it cannot tell from the one two laps earlier).
+  constexpr bool kTwoIssue = XF && (EPI & (E_RES | E_GENERIC)) == 0;
+  const bool xf_fast_ok = XF && p.w_resident != 0 && p.f_regular[ph] != 0 && p.xf_fast != 0 &&
+                          (p.f_nmma[ph] == 3 || p.f_nmma[ph] == 6 || p.f_nmma[ph] == 12);
+  const bool xf_two = kTwoIssue && xf_fast_ok && p.xf_issuers == 2 && p.a_stages >= 4;
+  const int ring0 = xf_two ? (p.a_stages + 1) >> 1 : p.a_stages;     // stages of the first sub-ring (the second takes the rest)
+  // t_first / t_step: the tiles this issuer takes; slot0 / n_slots: its part of the A ring
+  auto xf_issue = [&](auto NC, int t_first, int t_step, int slot0, int n_slots, bool primary) {
+    constexpr int NR = decltype(NC)::value;
+    const bool elected = elect_one();
+    const bool leader = elected && !(p.dbg & 1);      // dbg bit 1: no MMAs (the commits still arrive)
+    const uint32_t idesc = make_idesc_bf16(p.n_tile);
+    const uint32_t b_hi = (128u >> 4) | (1u << 14);   // SBO = 128 B, version 1
+    const uint32_t w_base16 = (smem_u32(smem_w) & 0x3FFFF) >> 4;
+    const uint32_t a_ring16 = (smem_u32(smem_a) & 0x3FFFF) >> 4;
+    const uint32_t a_stage16 = p.a_stage_bytes >> 4;
+    const uint32_t a_sub16 = p.a_sub_bytes >> 4;
+    const uint32_t n_tile_u = static_cast<uint32_t>(p.n_tile);
+    const uint32_t f_a_hi = p.f_a_hi[ph], f_a_lo_lbo = p.f_a_lo_lbo[ph], f_b_chunk16 = p.f_b_chunk16[ph];
+    const uint32_t b_lo_lbo = (n_tile_u & 0x3FFF) << 16;
+    for (int i = 0; i < kMaxWStages; ++i) {           // resident weights: requested before the dependency wait
+      if (i * w_per >= phase.n_blocks) break;
+      mbar_wait(&w_full[i], 0);
+    }
+    tc_fence_after();
+    uint32_t off[NR];            // A offset | B offset << 16, as in the table (unpacked copies spill)
+#pragma unroll
+    for (int i = 0; i < NR; ++i) off[i] = p.f_off[ph][i];
+    int s = slot0;
+    uint32_t a_par = 0;
+    const uint32_t a_first16 = a_ring16 + static_cast<uint32_t>(slot0) * a_stage16;
+    uint32_t a_base16 = a_first16;
+    bool stamp2 = primary && tr != nullptr;
+    for (int t = t_first; t < my_tiles; t += t_step) {
+      const int acc = t & 1;
+      if (primary) STCD_TWAIT(mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1), tw_acc);
+      else mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + acc * p.acc_cols;
+      uint32_t accum = 0;
+      uint32_t b0 = b_lo_lbo + w_base16;
+      for (int c = 0; c < phase.chunk_count; ++c) {
+        if (primary) STCD_TWAIT(mbar_wait(&a_full[s], a_par), tw_a);
+        else mbar_wait(&a_full[s], a_par);
+        tc_fence_after();
+        if (stamp2) {
+          if (elected) STCD_STAMP(2);
+          stamp2 = false;
+        }
+        const uint32_t a0 = f_a_lo_lbo + a_base16;
+        if (leader) {
+#pragma unroll
+          for (int i = 0; i < NR; ++i) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+              umma_bf16_lohi(d0 + m * n_tile_u, a0 + (off[i] & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (off[i] >> 16), b_hi, idesc, i == 0 ? accum : 1u);
+          }
+        }
+        accum = 1;
+        if (elected) umma_commit(&a_empty[s]);
+        b0 += f_b_chunk16;
+        a_base16 += a_stage16;
+        if (++s == slot0 + n_slots) {
+          s = slot0;
+          a_par ^= 1;
+          a_base16 = a_first16;
+        }
+      }
+      if (elected) {
+        umma_commit(&acc_full[acc]);
+        if (primary && t == 0) STCD_STAMP(4);
+        if (t == my_tiles - 1) STCD_STAMP(9);
+      }
+    }
+  };
 
   if (warp == 0) {
     // ============================== A producer (TMA) ==============================
     const bool leader = elect_one();
     int s = 0;
     uint32_t par = 1;  // parity to wait for on a_empty[s]: first pass through the ring never blocks
+    long long tw_prod = 0;
     pdl_wait();        // activations are written by the previous kernel(s)
     for (int t = 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
@@ -374,7 +476,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
       const int x0 = tile_x * XSTEP - XOFF, y0 = tile_y * TH;
       for (int c = 0; c < phase.chunk_count; ++c) {
         const ChunkLoad L = s_cload[c];
-        mbar_wait_relaxed(&a_empty[s], par);
+        STCD_TWAIT(mbar_wait_relaxed(&a_empty[s], par), tw_prod);
         if (leader) {
           mbar_expect_tx(&a_full[s], L.tx_bytes);
           if (t == 0 && c == 0) STCD_STAMP(8);
@@ -395,6 +497,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
         }
       }
     }
+    if (tr && leader) tr[15] = tw_prod;
     __syncwarp();
   } else if (warp == 1) {
     // ============================== W producer (bulk copies) ==============================
@@ -432,7 +535,8 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
     __syncwarp();
   } else if (warp == 2) {
     // ============================== MMA issuer ==============================
-    const bool leader = elect_one() && !(p.dbg & 1);
+    const bool elected = elect_one();
+    const bool leader = elected && !(p.dbg & 1);      // dbg bit 1: no MMAs (the commits still arrive)
     const uint32_t idesc = make_idesc_bf16(p.n_tile);
     const int ksteps = p.kc >> 4;                   // 1, 2 or 4
     const uint32_t b_hi = (128u >> 4) | (1u << 14);                                   // SBO = 128 B, version 1
@@ -459,9 +563,19 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
       }
       tc_fence_after();
     }
-    for (int t = 0; t < my_tiles; ++t) {
+    bool done = false;
+    if constexpr (XF) {
+      if (xf_fast_ok) {
+        const int n_iss = xf_two ? 2 : 1;
+        if (f_nmma == 3) xf_issue(IntC<3>{}, 0, n_iss, 0, ring0, true);
+        else if (f_nmma == 6) xf_issue(IntC<6>{}, 0, n_iss, 0, ring0, true);
+        else xf_issue(IntC<12>{}, 0, n_iss, 0, ring0, true);
+        done = true;
+      }
+    }
+    for (int t = 0; t < (done ? 0 : my_tiles); ++t) {
       const int acc = t & 1;
-      mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
+      STCD_TWAIT(mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1), tw_acc);
       tc_fence_after();
       const uint32_t d0 = tmem_base + acc * p.acc_cols;
       uint32_t accum = 0;
@@ -469,9 +583,9 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
       for (int c = 0; c < phase.chunk_count; ++c) {
         const ChunkMma M = s_cmma[c];
         const int n_mma = static_cast<int>(M.n_mma);
-        mbar_wait(&a_full[s], a_par);
+        STCD_TWAIT(mbar_wait(&a_full[s], a_par), tw_a);
         tc_fence_after();
-        if (t == 0 && c == 0 && leader) STCD_STAMP(2);
+        if (t == 0 && c == 0 && elected) STCD_STAMP(2);
         if (fast) {
           // regular phase: operand offsets come from the constant bank through uniform loads
           const uint32_t a0 = f_a_lo_lbo + a_base16;
@@ -544,7 +658,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
               }
               accum = 1;
             }
-            if (leader) umma_commit(&w_empty[ws]);
+            if (elected) umma_commit(&w_empty[ws]);
             if (++ws == p.w_stages) {
               ws = 0;
               w_par ^= 1;
@@ -552,7 +666,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
           }
         }
         mma_off += n_mma;
-        if (leader) umma_commit(&a_empty[s]);
+        if (elected) umma_commit(&a_empty[s]);
         a_base16 += a_stage16;
         if (++s == p.a_stages) {
           s = 0;
@@ -560,15 +674,27 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
           a_base16 = a_ring16;
         }
       }
-      if (leader) {
+      if (elected) {
         umma_commit(&acc_full[acc]);
         if (t == 0) STCD_STAMP(4);
         if (t == my_tiles - 1) STCD_STAMP(9);
       }
     }
+    if (tr && elected) {
+      tr[12] = tw_a;
+      tr[13] = tw_acc;
+    }
     __syncwarp();
   } else if (warp == kResWarp) {
-    // ============================== residual producer (TMA) ==============================
+    // ============================== residual producer (TMA) / second issuer of the folded layers ==============================
+    if constexpr (kTwoIssue) {
+      if (xf_two) {
+        const int f_nmma = p.f_nmma[ph];
+        if (f_nmma == 3) xf_issue(IntC<3>{}, 1, 2, ring0, p.a_stages - ring0, false);
+        else if (f_nmma == 6) xf_issue(IntC<6>{}, 1, 2, ring0, p.a_stages - ring0, false);
+        else xf_issue(IntC<12>{}, 1, 2, ring0, p.a_stages - ring0, false);
+      }
+    }
     if (p.res_slots) {
       const bool leader = elect_one();
       int rs = 0;
@@ -696,6 +822,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
     if (res_rg && my_tiles > 0) prefetch_unit(0, 0);
     int ers = 0;
     uint32_t erpar = 0;
+    long long tw_epi = 0;
     for (int t = 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
       if (p.reverse) tile = p.n_tiles - 1 - tile;
@@ -704,7 +831,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
       const int tile_y = tile % p.tiles_y;
       const int img = tile / p.tiles_y;
       const int gy = tile_y * TH + ty, gx = tile_x * XSTEP + tx - XOFF;
-      const bool valid = (gy < p.hg) && (gx < p.wg) && lane_out;
+      const bool valid = (gy < p.hg) && (gx < p.wg) && lane_out && !(p.dbg & 2);   // dbg bit 2: no epilogue stores (and no residual adds)
       const int oy = gy * p.osy + phase.oy, ox = gx * p.osx + phase.ox;
       const uint32_t pix = static_cast<uint32_t>(oy) * p.wo + ox;
       const uint32_t pix_pool = static_cast<uint32_t>(oy >> 1) * (p.wo >> 1) + (ox >> 1);
@@ -768,7 +895,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
         }
         if (mb == 0) {
           if (res_sm) mbar_wait_relaxed(&r_full[ers], erpar);   // the tile's first residual block: off the critical path here
-          mbar_wait_relaxed(&acc_full[acc], (t >> 1) & 1);
+          STCD_TWAIT(mbar_wait_relaxed(&acc_full[acc], (t >> 1) & 1), tw_epi);
           tc_fence_after();
           if (t == 0 && threadIdx.x == 96) STCD_STAMP(5);
         }
@@ -1013,6 +1140,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
         if (t == my_tiles - 1) STCD_STAMP(10);
       }
     }
+    if (tr && threadIdx.x == 96) tr[14] = tw_epi;
   }
 
   tc_fence_before();

@@ -1777,6 +1777,8 @@ int stcd_plan_finalize(stcd_plan* plan) {
     const int ctas = std::max(1, (n_sm * occ) / groups);
     op.grid = dim3((unsigned)std::min(p.n_tiles, ctas), (unsigned)p.n_ntiles, (unsigned)d.n_phase);
     p.dbg = env_int("STCD_DBG", 0);
+    p.xf_fast = (xf && d.n_phase == 1 && d.phase[0].chunk_count >= env_int("STCD_XF_FAST_MIN", 4)) ? 1 : 0;
+    p.xf_issuers = env_int("STCD_XF_ISSUERS", 2);
     p.reverse = (env_int("STCD_SERPENTINE", 1) && ((&op - &plan->convs[0]) & 1)) ? 1 : 0;
     if (env_int("STCD_TRACE", 0)) {
       const size_t nb = (size_t)op.grid.x * op.grid.y * op.grid.z * 16 * sizeof(long long);

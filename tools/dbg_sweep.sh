@@ -1,5 +1,5 @@
 #!/bin/bash
-# Which role binds each conv op?  STCD_DBG bits: 1 no MMAs, 2 no epilogue stores / residual loads, 4 no residual loads, 8 no activation (TMA) loads.
+# Which role binds each conv op?  STCD_DBG bits: 1 no MMAs (the commits still arrive), 2 no epilogue stores / residual adds.  (A build with bit 4 = no accumulator loads showed no op moving: profiles/r2_role_sweep.txt.)
 # Results are garbage by construction; only per_op_ms matters.
 mkdir -p gpurun_out
 ./tools/ubench/mma_rate.bin > gpurun_out/mma_rate_r2.log 2>&1

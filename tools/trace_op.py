@@ -21,7 +21,7 @@ for _ in range(3):
     plan.forward(x1, x2)
 torch.cuda.synchronize()
 lib = _lib.lib()
-names = ["gt", "setup", "mma:a0", "mma:w0", "mma:t0", "epi:t0beg", "epi:t0end", "exit", "prod:tma0", "mma:last", "epi:last", "tiles", "tap0", "tap1", "c0taps", "c0commit"]
+names = ["gt", "setup", "mma:a0", "mma:w0", "mma:t0", "epi:t0beg", "epi:t0end", "exit", "prod:tma0", "mma:last", "epi:last", "tiles", "mma:wait_a", "mma:wait_acc", "epi:wait_acc", "prod:wait_empty"]
 for i, op in enumerate(prog.ops):
     info = (C.c_int32 * 10)()
     buf = np.zeros(1 << 16, dtype=np.int64)
@@ -41,4 +41,6 @@ for i, op in enumerate(prog.ops):
     prev_end = end_ns - t_origin
     med = np.median(t, axis=0)
     print(f"{op.name:8s} grid=({info[0]},{info[1]}) smem={info[2]} aS={info[3]} wS={info[4]} res={info[5]} tmem={info[6]} tiles={info[7]} aB={info[8]} wB={info[9]} start-span={span_us:.1f}us")
-    print("     median cycles: " + " ".join(f"{names[k]}={int(med[k])}" for k in (1, 8, 2, 3, 12, 13, 14, 15, 4, 5, 6, 9, 10, 7, 11)))
+    print("     median cycles: " + " ".join(f"{names[k]}={int(med[k])}" for k in (1, 8, 2, 3, 4, 5, 6, 9, 10, 7, 11)))
+    run = max(1.0, med[7] - med[2])          # first operand -> exit
+    print("     share of (first operand -> exit) spent waiting: " + " ".join(f"{names[k]}={med[k] / run:.2f}" for k in (12, 13, 14, 15)))
