@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
   // Programmatic dependent launch: everything above (tables, barriers, TMEM) and the weight loads
   // below do not depend on the previous layer; only the activation loads wait for the previous kernel to finish.
 
-  long long tw_a = 0, tw_acc = 0;     // trace mode (issuer warp): cycles waited for operands / for a free accumulator
+  long long tw_a = 0, tw_acc = 0, tw_w = 0;     // trace mode (issuer warp): cycles waited for activations / a free accumulator / streamed weights
   // ---- Horizontally folded layers: the issue loop, shared by the issuer warp(s).
   // A chunk is one 16..64-channel block of one source = 3 filter rows x (1, 2 or 4) K steps.  ncu's source view
   // (profiles/r2_src_conv0_4_conv1.txt) showed the issuer as a pacing role -- never waiting for an operand, ~86 instructions per
@@ -466,7 +466,47 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
     uint32_t par = 1;  // parity to wait for on a_empty[s]: first pass through the ring never blocks
     long long tw_prod = 0;
     pdl_wait();        // activations are written by the previous kernel(s)
-    for (int t = 0; t < my_tiles; ++t) {
+    if (xf_two) {
+      // two issuers: tiles t (sub-ring 0) and t + 1 (sub-ring 1) are fed chunk by chunk in turn
+      int rs[2] = {0, ring0};
+      uint32_t rpar[2] = {1, 1};
+      for (int t = 0; t < my_tiles; t += 2) {
+        int x0[2], y0[2], img[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          int tile = blockIdx.x + min(t + r, my_tiles - 1) * gridDim.x;
+          if (p.reverse) tile = p.n_tiles - 1 - tile;
+          const int tile_x = tile % p.tiles_x;
+          tile /= p.tiles_x;
+          x0[r] = tile_x * XSTEP - XOFF;
+          y0[r] = (tile % p.tiles_y) * TH;
+          img[r] = tile / p.tiles_y;
+        }
+        for (int c = 0; c < phase.chunk_count; ++c) {
+          const ChunkLoad L = s_cload[c];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            if (t + r >= my_tiles) break;
+            const int st = rs[r];
+            STCD_TWAIT(mbar_wait_relaxed(&a_empty[st], rpar[r]), tw_prod);
+            if (leader) {
+              mbar_expect_tx(&a_full[st], L.tx_bytes);
+              if (t == 0 && c == 0 && r == 0) STCD_STAMP(8);
+              uint8_t* dst = smem_a + st * p.a_stage_bytes;
+              const CUtensorMap* map = &tm.src[L.src_merged & 0xff];
+              const int cx = x0[r] * L.xm + L.xa, cy = y0[r] * L.ym + L.ya, cn = img[r] + L.n_off;
+#pragma unroll
+              for (int m = 0; m < MT; ++m) tma_load_4d(dst + m * p.a_sub_bytes, map, &a_full[st], cx, cy, L.c8, cn + p.m_off[m]);   // folded ops read stride-1 sources
+            }
+            if (++rs[r] == (r ? p.a_stages : ring0)) {
+              rs[r] = r ? ring0 : 0;
+              rpar[r] ^= 1;
+            }
+          }
+        }
+      }
+    }
+    for (int t = xf_two ? my_tiles : 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
       if (p.reverse) tile = p.n_tiles - 1 - tile;
       const int tile_x = tile % p.tiles_x;
@@ -548,6 +588,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
     const bool resident = p.w_resident != 0;
     const uint32_t n_tile_u = static_cast<uint32_t>(p.n_tile);
     const bool fast = resident && p.f_regular[ph] != 0;
+    const bool fast_s = !resident && p.f_regular[ph] != 0 && (p.dbg & 8);       // dbg bit 8: streamed weights through the lean loop (A/B only, see below)
     const int f_nmma = p.f_nmma[ph];
     const uint32_t f_a_hi = p.f_a_hi[ph], f_a_lo_lbo = p.f_a_lo_lbo[ph], f_b_chunk16 = p.f_b_chunk16[ph];
     const uint32_t b_lo_lbo = (n_tile_u & 0x3FFF) << 16;
@@ -625,6 +666,67 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
             }
             accum = 1;
           }
+        } else if (fast_s) {
+          // Regular phase, weights STREAMED (one ring slot per tap) -- an experiment kept for A/B runs (STCD_DBG=8), NOT the default.
+          // The trace (round 2, tools/trace_op.py) shows the issuer "busy" 85 % of the time on every streamed layer of SNUNet /
+          // SegCD (4 % waiting for activations, 11 % for weights) with the tensor pipe 40 % occupied: ~96 cycles per MMA against
+          // 64 nominal.  This lean loop (a tap = one wait, one 16-byte constant load, ONE divergent region with all K steps x
+          // sub-tiles) measured 10-20 % SLOWER than the table loop below on SNUNet's conv1_x.conv1 / conv3_1 / conv4_0 and equal on
+          // SegCD: the issuer's time is back-pressure from the tensor pipe, not instructions.  An N = 128 SS-mode MMA reads
+          // A (4 KB) + B (4 KB) per 64 cycles = all 128 B/clk of shared-memory bandwidth, and the same banks take the streamed
+          // weights (16 KB per tap) and activation boxes as writes: these layers are shared-memory-bandwidth bound, which only a
+          // two-CTA MMA (cta_group::2: each SM reads and streams half of B) relieves.
+          const uint32_t a0 = f_a_lo_lbo + a_base16;
+          uint32_t b0 = b_lo_lbo + w_base16 + static_cast<uint32_t>(ws) * wblk16;
+          for (int i = 0; i < f_nmma; i += ksteps) {
+            STCD_TWAIT(mbar_wait(&w_full[ws], w_par), tw_w);
+            tc_fence_after();
+            if (ksteps == 4) {
+              const uint4 e = *reinterpret_cast<const uint4*>(&p.f_off[ph][i]);
+              if (leader) {
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                  umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.x & 0xFFFFu) + m * a_sub16, f_a_hi, b0, b_hi, idesc, accum);
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                  umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.y & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + 2u * n_tile_u, b_hi, idesc, 1u);
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                  umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.z & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + 4u * n_tile_u, b_hi, idesc, 1u);
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                  umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.w & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + 6u * n_tile_u, b_hi, idesc, 1u);
+              }
+            } else if (ksteps == 2) {
+              const uint2 e = *reinterpret_cast<const uint2*>(&p.f_off[ph][i]);
+              if (leader) {
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                  umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.x & 0xFFFFu) + m * a_sub16, f_a_hi, b0, b_hi, idesc, accum);
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                  umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.y & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + 2u * n_tile_u, b_hi, idesc, 1u);
+              }
+            } else {
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t e = p.f_off[ph][i + ks];
+                if (leader) {
+#pragma unroll
+                  for (int m = 0; m < MT; ++m)
+                    umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + static_cast<uint32_t>(ks) * 2u * n_tile_u, b_hi, idesc,
+                                   ks == 0 ? accum : 1u);
+                }
+              }
+            }
+            accum = 1;
+            if (elected) umma_commit(&w_empty[ws]);
+            b0 += wblk16;
+            if (++ws == p.w_stages) {
+              ws = 0;
+              w_par ^= 1;
+              b0 = b_lo_lbo + w_base16;
+            }
+          }
         } else if (resident) {
           // Lane i holds the descriptors of MMA i of this chunk; the issue loop only shuffles them
           // out, so its instructions are independent and pipeline instead of forming one chain.
@@ -646,7 +748,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
           }
         } else {
           for (int i = 0; i < n_mma; i += ksteps) {  // one weight block (tap) per ring slot
-            mbar_wait(&w_full[ws], w_par);
+            STCD_TWAIT(mbar_wait(&w_full[ws], w_par), tw_w);
             tc_fence_after();
             const uint32_t b_slot16 = w_base16 + static_cast<uint32_t>(ws) * wblk16;
             for (int ks = 0; ks < ksteps; ++ks) {
@@ -683,6 +785,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
     if (tr && elected) {
       tr[12] = tw_a;
       tr[13] = tw_acc;
+      tr[3] = tw_w;
     }
     __syncwarp();
   } else if (warp == kResWarp) {
@@ -1269,7 +1372,12 @@ struct ConvKernelEntry {
   X(2, 2, E_RES | E_RSM | E_RELU | E_OUT0 | E_POOL)    \
   X(4, 2, E_RES | E_RSM | E_RELU | E_OUT0 | E_POOL)    \
   X(2, 2, E_RES | E_RSM | E_RELU | E_OUT0)             \
-  X(4, 2, E_RES | E_RSM | E_RELU | E_OUT0)
+  X(4, 2, E_RES | E_RSM | E_RELU | E_OUT0)             \
+  /* horizontally folded layers at one CTA per SM: the 3x accumulator read + shuffles make their epilogue a pacing role */ \
+  X(1, 1, E_XF | E_RELU | E_OUT0)                      \
+  X(2, 1, E_XF | E_RELU | E_OUT0)                      \
+  X(1, 1, E_XF | E_RAW | E_AFF2 | E_RELU | E_OUT0)     \
+  X(2, 1, E_XF | E_RAW | E_AFF2 | E_RELU | E_OUT0)
 
 // one table per translation unit
 const ConvKernelEntry* conv_kernel_table_f(int* n);

@@ -1778,7 +1778,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
     op.grid = dim3((unsigned)std::min(p.n_tiles, ctas), (unsigned)p.n_ntiles, (unsigned)d.n_phase);
     p.dbg = env_int("STCD_DBG", 0);
     p.xf_fast = (xf && d.n_phase == 1 && d.phase[0].chunk_count >= env_int("STCD_XF_FAST_MIN", 4)) ? 1 : 0;
-    p.xf_issuers = env_int("STCD_XF_ISSUERS", 2);
+    p.xf_issuers = env_int("STCD_XF_ISSUERS", 1);    // 2 measured 5-20 % slower than 1 on SNUNet's level-0 layers (see conv_ws.cuh)
     p.reverse = (env_int("STCD_SERPENTINE", 1) && ((&op - &plan->convs[0]) & 1)) ? 1 : 0;
     if (env_int("STCD_TRACE", 0)) {
       const size_t nb = (size_t)op.grid.x * op.grid.y * op.grid.z * 16 * sizeof(long long);
@@ -1804,7 +1804,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
     op.fn = nullptr;
     op.threads = stcd::kConvThreads;
     // plans that run one CTA per SM anyway take the eight-epilogue-warp instance when there is one (>= 2 column steps to share)
-    const bool want8 = occ == 1 && d.n_tile >= 32 && env_int("STCD_EPI8", 1) != 0;
+    const bool want8 = occ == 1 && (xf ? (d.xf_cs >= 32 && env_int("STCD_XF_EPI8", 1) != 0) : d.n_tile >= 32) && env_int("STCD_EPI8", 1) != 0;
     for (int i = 0; i < n_kernels && !force_generic && !d.split; ++i)     // split precision lives in the generic instances
       if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == op.epi && (kernels[i].ne == 4 || want8)) {
         if (op.fn && kernels[i].ne == 4) continue;       // an eight-warp instance found earlier wins

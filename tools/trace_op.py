@@ -12,7 +12,12 @@ H = W = 256
 chunk = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 from stcd_b200 import snunet
 which = os.environ.get("STCD_TRACE_NET", "siam")
-net = synth.prepare_(snunet.SNUNet_ECAM(3, 2).eval(), "SNUNet_ECAM") if which == "snunet" else synth.randomize_(siamunet.SiamUnet_diff(3, 2).eval(), gain=synth.GAINS["SiamUnet_diff"])
+if which == "segcd":
+    from stcd_b200 import smp
+    H = W = 1024
+    net = synth.prepare_(smp.SegCD("resnet34", classes=1).eval(), "SegCD")
+else:
+    net = synth.prepare_(snunet.SNUNet_ECAM(3, 2).eval(), "SNUNet_ECAM") if which == "snunet" else synth.randomize_(siamunet.SiamUnet_diff(3, 2).eval(), gain=synth.GAINS["SiamUnet_diff"])
 prog = net.lower(H, W)
 plan = Plan(prog, chunk)
 x1, x2 = synth.image_pairs(chunk, H, W)
@@ -21,7 +26,7 @@ for _ in range(3):
     plan.forward(x1, x2)
 torch.cuda.synchronize()
 lib = _lib.lib()
-names = ["gt", "setup", "mma:a0", "mma:w0", "mma:t0", "epi:t0beg", "epi:t0end", "exit", "prod:tma0", "mma:last", "epi:last", "tiles", "mma:wait_a", "mma:wait_acc", "epi:wait_acc", "prod:wait_empty"]
+names = ["gt", "setup", "mma:a0", "mma:wait_w", "mma:t0", "epi:t0beg", "epi:t0end", "exit", "prod:tma0", "mma:last", "epi:last", "tiles", "mma:wait_a", "mma:wait_acc", "epi:wait_acc", "prod:wait_empty"]
 for i, op in enumerate(prog.ops):
     info = (C.c_int32 * 10)()
     buf = np.zeros(1 << 16, dtype=np.int64)
@@ -41,6 +46,6 @@ for i, op in enumerate(prog.ops):
     prev_end = end_ns - t_origin
     med = np.median(t, axis=0)
     print(f"{op.name:8s} grid=({info[0]},{info[1]}) smem={info[2]} aS={info[3]} wS={info[4]} res={info[5]} tmem={info[6]} tiles={info[7]} aB={info[8]} wB={info[9]} start-span={span_us:.1f}us")
-    print("     median cycles: " + " ".join(f"{names[k]}={int(med[k])}" for k in (1, 8, 2, 3, 4, 5, 6, 9, 10, 7, 11)))
+    print("     median cycles: " + " ".join(f"{names[k]}={int(med[k])}" for k in (1, 8, 2, 4, 5, 6, 9, 10, 7, 11)))
     run = max(1.0, med[7] - med[2])          # first operand -> exit
-    print("     share of (first operand -> exit) spent waiting: " + " ".join(f"{names[k]}={med[k] / run:.2f}" for k in (12, 13, 14, 15)))
+    print("     share of (first operand -> exit) spent waiting: " + " ".join(f"{names[k]}={med[k] / run:.2f}" for k in (12, 3, 13, 14, 15)))
