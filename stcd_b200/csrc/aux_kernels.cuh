@@ -62,6 +62,47 @@ __global__ void __launch_bounds__(256) input_pack_kernel(const float* __restrict
   }
 }
 
+// The same for cin <= 4 with four consecutive pixels per thread (hw % 4 == 0): one 16-byte load per channel plane and 64
+// contiguous bytes stored.  The one-pixel kernel keeps 12 bytes per thread in flight -- 24 KB per SM, 2.1 TB/s for the whole
+// chip at DRAM latency: 110 us for 128 images of 256 x 256 against a 36 us floor (round-2 floor table).
+template <int CIN>
+__global__ void __launch_bounds__(256) input_pack4_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                          __nv_bfloat16* __restrict__ dst, int chunk, int n_valid, int c8, int hw) {
+  const int hw4 = hw >> 2;
+  const size_t total = static_cast<size_t>(2) * chunk * hw4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i / hw4);
+    const int pix = static_cast<int>(i - static_cast<size_t>(n) * hw4) << 2;
+    const int s = n / chunk, b = n - s * chunk;
+    float4 v[CIN];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b < n_valid) {
+      const float* src = (s ? x2 : x1) + static_cast<size_t>(b) * CIN * hw + pix;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) v[c] = __ldg(reinterpret_cast<const float4*>(src + static_cast<size_t>(c) * hw));
+    }
+    uint4 o4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) f[c] = q == 0 ? v[c].x : q == 1 ? v[c].y : q == 2 ? v[c].z : v[c].w;
+      o4[q] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), 0u, 0u);
+    }
+    __nv_bfloat16* o = dst + (static_cast<size_t>(n) * c8 * hw + pix) * 8;
+    st_global_256(o, o4[0], o4[1]);
+    st_global_256(o + 16, o4[2], o4[3]);
+    for (int g = 1; g < c8; ++g) {      // stored channel groups beyond the first are zero
+      __nv_bfloat16* z = o + static_cast<size_t>(g) * hw * 8;
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      st_global_256(z, zero, zero);
+      st_global_256(z + 16, zero, zero);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // uint8 input pipeline: the reference's CD_Dataset (data/dataset.py:196-203) turns uint8 HWC
 // RGB into normalised fp32 CHW on the host -- ToTensor (x / 255) then Normalize ((x - mean) / std) -- and ships

@@ -92,6 +92,7 @@ struct Tap {
 };
 struct PhaseInfo {
   int32_t chunk_begin, chunk_count, oy, ox, w_block, n_blocks;
+  int32_t tap0;      // first entry of this phase in ConvParams::taps (= chunks[chunk_begin].tap_begin)
 };
 
 struct TmapPack {
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
   __shared__ __align__(16) ChunkLoad s_cload[kMaxChunks];
   __shared__ __align__(8) ChunkMma s_cmma[kMaxChunks];
   __shared__ __align__(16) float s_aff[4][256];      // scale, shift, scale2, shift2 of this CTA's N tile
+  __shared__ uint8_t s_blk_src[kMaxTaps];            // source index of each weight block's chunk (table set-up only)
 
   constexpr bool XF = (EPI & E_XF) != 0;
   constexpr int TH = XF ? kXfTileH : kTileH;      // tile rows
@@ -314,10 +316,21 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
     for (int i = 0; i < p.n_src; ++i) tma_prefetch_desc(&tm.src[i]);
     if (p.res_slots) tma_prefetch_desc(&tm.res);
   }
-  // ---- tile-invariant tables
+  // ---- tile-invariant tables.  Two passes so that no thread walks a list of dependent global loads (one thread per chunk
+  // looping over its taps cost 4 000-5 800 cycles of set-up on the 3x3 layers, 2 200-2 900 on the single-tap ones: n_taps
+  // serialised L2 round trips): every thread requests its chunk record AND its tap record(s) up front -- the phase's first
+  // tap index comes with the kernel parameters -- pass 1 files the per-chunk tables and the block -> chunk map, pass 2 the
+  // per-MMA descriptors, one thread per weight block.
   {
-    const int tap0 = p.chunks[phase.chunk_begin].tap_begin;
+    const int tap0 = phase.tap0;
     const uint32_t w_base16 = (smem_u32(smem_w) & 0x3FFFF) >> 4;
+    const int ksteps = p.kc >> 4;
+    Tap my_tap[kMaxTaps / kConvThreads];
+#pragma unroll
+    for (int j = 0; j < kMaxTaps / kConvThreads; ++j) {
+      const int blk = threadIdx.x + j * blockDim.x;
+      my_tap[j] = blk < phase.n_blocks ? p.taps[tap0 + blk] : Tap{0, 0};
+    }
     for (int c = threadIdx.x; c < phase.chunk_count; c += blockDim.x) {
       const Chunk ch = p.chunks[phase.chunk_begin + c];
       const int pw = p.src_pw[ch.src], phh = p.src_ph[ch.src];
@@ -332,18 +345,24 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
       L.tx_bytes = static_cast<uint32_t>(MT) * (p.kc / 8) * phh * pw * 16u;
       L.src_merged = ch.src | (merged << 8);
       s_cload[c] = L;
-      const int ksteps = p.kc >> 4;
       ChunkMma M;
       // SBO (next 8 rows of M): the next tile line, pw * 16 B; XF tiles have no horizontal halo and 16-pixel lines, so the
       // 8-pixel groups of a tile are 128 B apart throughout
       M.a_hi = (XF ? 8u : (static_cast<uint32_t>(pw) & 0x3FFF)) | (1u << 14);   // descriptor version 1
       M.n_mma = static_cast<uint32_t>(ch.n_taps * ksteps);
       s_cmma[c] = M;
-      const uint32_t a_lo_lbo = (static_cast<uint32_t>(pw * phh) & 0x3FFF) << 16;   // LBO = pw * ph * 16 B
-      const uint32_t b_lo_lbo = (static_cast<uint32_t>(p.n_tile) & 0x3FFF) << 16;  // LBO = n_tile * 16 B
-      for (int k = 0; k < ch.n_taps; ++k) {
-        const Tap tp = p.taps[ch.tap_begin + k];
-        const int blk = ch.tap_begin - tap0 + k;
+      for (int k = 0; k < ch.n_taps; ++k) s_blk_src[ch.tap_begin - tap0 + k] = static_cast<uint8_t>(ch.src);
+    }
+    __syncthreads();
+    const uint32_t b_lo_lbo = (static_cast<uint32_t>(p.n_tile) & 0x3FFF) << 16;  // LBO = n_tile * 16 B
+#pragma unroll
+    for (int j = 0; j < kMaxTaps / kConvThreads; ++j) {
+      const int blk = threadIdx.x + j * blockDim.x;
+      if (blk < phase.n_blocks) {
+        const int src = s_blk_src[blk];
+        const int pw = p.src_pw[src], phh = p.src_ph[src];
+        const uint32_t a_lo_lbo = (static_cast<uint32_t>(pw * phh) & 0x3FFF) << 16;   // LBO = pw * ph * 16 B
+        const Tap tp = my_tap[j];
         for (int ks = 0; ks < ksteps; ++ks) {
           uint2 e;
           e.x = a_lo_lbo + static_cast<uint32_t>(tp.ty * pw + tp.tx) + static_cast<uint32_t>(ks) * 2u * (pw * phh);

@@ -685,6 +685,15 @@ int run_chunk(stcd_plan* plan, const void* x1v, const void* x2v, int n_valid, fl
           case 3: stcd::input_pack_s2d_kernel<3><<<blocks, 256, 0, st>>>(x1, x2, dp, plan->chunk, n_valid, t.h, t.w); break;
           default: stcd::input_pack_s2d_kernel<4><<<blocks, 256, 0, st>>>(x1, x2, dp, plan->chunk, n_valid, t.h, t.w); break;
         }
+      } else if (!k.split && k.cin <= 4 && hw % 4 == 0 && (reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2)) % 16 == 0) {
+        __nv_bfloat16* dp = (__nv_bfloat16*)t.ptr;
+        const int blocks4 = (int)std::min<size_t>((total / 4 + 255) / 256, 148 * 8);
+        switch (k.cin) {
+          case 1: stcd::input_pack4_kernel<1><<<blocks4, 256, 0, st>>>(x1, x2, dp, plan->chunk, n_valid, t.c / 8, hw); break;
+          case 2: stcd::input_pack4_kernel<2><<<blocks4, 256, 0, st>>>(x1, x2, dp, plan->chunk, n_valid, t.c / 8, hw); break;
+          case 3: stcd::input_pack4_kernel<3><<<blocks4, 256, 0, st>>>(x1, x2, dp, plan->chunk, n_valid, t.c / 8, hw); break;
+          default: stcd::input_pack4_kernel<4><<<blocks4, 256, 0, st>>>(x1, x2, dp, plan->chunk, n_valid, t.c / 8, hw); break;
+        }
       } else
         stcd::input_pack_kernel<<<blocks, 256, 0, st>>>(x1, x2, (__nv_bfloat16*)t.ptr, plan->chunk, n_valid, k.cin, t.c / 8, hw, k.split);
       CUDA_TRY(cudaGetLastError());
@@ -1613,7 +1622,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
     int max_blocks = 0, blocks_total = 0;
     for (int ph = 0; ph < d.n_phase; ++ph) {
       p.phase[ph] = {d.phase[ph].chunk_begin, d.phase[ph].chunk_count, d.phase[ph].oy, d.phase[ph].ox, d.phase[ph].w_block,
-                     d.phase[ph].n_blocks};
+                     d.phase[ph].n_blocks, d.phase[ph].chunk_count > 0 ? op.chunks[d.phase[ph].chunk_begin].tap_begin : 0};
       max_blocks = std::max(max_blocks, d.phase[ph].n_blocks);
       blocks_total += d.phase[ph].n_blocks;
     }
