@@ -163,6 +163,7 @@ struct ConvParams {
   uint32_t f_a_lo_lbo[kMaxPhase];    // A descriptor LBO field
   uint32_t f_b_chunk16[kMaxPhase];   // weight bytes per chunk >> 4
   alignas(16) uint32_t f_off[kMaxPhase][36];  // A offset (16 B units) | B offset inside the chunk's weights << 16
+  int32_t ws;        // 1: the MT sub-tiles of a pass read each weight block from shared memory once (tcgen05.mma.ws + collector; N = 64 / 128 / 256)
   int32_t xf_fast;   // E_XF: 1 = this op's issuer runs the register-resident chunk loop (chosen per op by the plan)
   int32_t xf_issuers;  // E_XF without a residual: 2 = the residual producer's warp issues the odd tiles (1: one issuer)
   int32_t dbg;       // diagnostics (STCD_DBG): bit0 skip MMAs
@@ -607,6 +608,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
     const bool resident = p.w_resident != 0;
     const uint32_t n_tile_u = static_cast<uint32_t>(p.n_tile);
     const bool fast = resident && p.f_regular[ph] != 0;
+    const bool use_ws = p.ws != 0;  // sub-tiles share each weight block through the collector (tcgen05.mma.ws)
     const bool fast_s = !resident && p.f_regular[ph] != 0 && (p.dbg & 8);       // dbg bit 8: streamed weights through the lean loop (A/B only, see below)
     const int f_nmma = p.f_nmma[ph];
     const uint32_t f_a_hi = p.f_a_hi[ph], f_a_lo_lbo = p.f_a_lo_lbo[ph], f_b_chunk16 = p.f_b_chunk16[ph];
@@ -654,18 +656,10 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
           for (; i + 4 <= f_nmma; i += 4) {
             const uint4 e = *reinterpret_cast<const uint4*>(&p.f_off[ph][i]);   // one 16-byte constant load
             if (leader) {  // ONE divergent region per 4 (x MT) MMAs: the four operand chains overlap
-#pragma unroll
-              for (int m = 0; m < MT; ++m)
-                umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.x & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (e.x >> 16), b_hi, idesc, accum);
-#pragma unroll
-              for (int m = 0; m < MT; ++m)
-                umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.y & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (e.y >> 16), b_hi, idesc, 1u);
-#pragma unroll
-              for (int m = 0; m < MT; ++m)
-                umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.z & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (e.z >> 16), b_hi, idesc, 1u);
-#pragma unroll
-              for (int m = 0; m < MT; ++m)
-                umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.w & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (e.w >> 16), b_hi, idesc, 1u);
+              umma_group<MT>(use_ws, d0, n_tile_u, a0 + (e.x & 0xFFFFu), a_sub16, f_a_hi, b0 + (e.x >> 16), b_hi, idesc, accum);
+              umma_group<MT>(use_ws, d0, n_tile_u, a0 + (e.y & 0xFFFFu), a_sub16, f_a_hi, b0 + (e.y >> 16), b_hi, idesc, 1u);
+              umma_group<MT>(use_ws, d0, n_tile_u, a0 + (e.z & 0xFFFFu), a_sub16, f_a_hi, b0 + (e.z >> 16), b_hi, idesc, 1u);
+              umma_group<MT>(use_ws, d0, n_tile_u, a0 + (e.w & 0xFFFFu), a_sub16, f_a_hi, b0 + (e.w >> 16), b_hi, idesc, 1u);
             }
             accum = 1;
           }
@@ -676,10 +670,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
 #pragma unroll
               for (int r = 0; r < 3; ++r) {
                 if (i + r < f_nmma) {
-#pragma unroll
-                  for (int m = 0; m < MT; ++m)
-                    umma_bf16_lohi(d0 + m * n_tile_u, a0 + (ev[r] & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (ev[r] >> 16), b_hi, idesc,
-                                   (r == 0) ? accum : 1u);
+                  umma_group<MT>(use_ws, d0, n_tile_u, a0 + (ev[r] & 0xFFFFu), a_sub16, f_a_hi, b0 + (ev[r] >> 16), b_hi, idesc, (r == 0) ? accum : 1u);
                 }
               }
             }
@@ -758,10 +749,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
             for (int j = 0; j < cnt; ++j) {
               const uint32_t a_lo = __shfl_sync(0xffffffffu, my.x, j);
               const uint32_t b_lo = __shfl_sync(0xffffffffu, my.y, j);
-              if (leader) {
-#pragma unroll
-                for (int m = 0; m < MT; ++m) umma_bf16_lohi(d0 + m * n_tile_u, a_lo + m * a_sub16, M.a_hi, b_lo, b_hi, idesc, accum);
-              }
+              if (leader) umma_group<MT>(use_ws, d0, n_tile_u, a_lo, a_sub16, M.a_hi, b_lo, b_hi, idesc, accum);
               accum = 1;
             }
           }
@@ -772,11 +760,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
             const uint32_t b_slot16 = w_base16 + static_cast<uint32_t>(ws) * wblk16;
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint2 e = s_mma[mma_off + i + ks];
-              if (leader) {
-#pragma unroll
-                for (int m = 0; m < MT; ++m)
-                  umma_bf16_lohi(d0 + m * n_tile_u, e.x + a_base16 + m * a_sub16, M.a_hi, e.y + b_slot16, b_hi, idesc, accum);
-              }
+              if (leader) umma_group<MT>(use_ws, d0, n_tile_u, e.x + a_base16, a_sub16, M.a_hi, e.y + b_slot16, b_hi, idesc, accum);
               accum = 1;
             }
             if (elected) umma_commit(&w_empty[ws]);
