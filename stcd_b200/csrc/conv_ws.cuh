@@ -163,9 +163,7 @@ struct ConvParams {
   uint32_t f_a_lo_lbo[kMaxPhase];    // A descriptor LBO field
   uint32_t f_b_chunk16[kMaxPhase];   // weight bytes per chunk >> 4
   alignas(16) uint32_t f_off[kMaxPhase][36];  // A offset (16 B units) | B offset inside the chunk's weights << 16
-  int32_t ws;        // 1: the MT sub-tiles of a pass read each weight block from shared memory once (tcgen05.mma.ws + collector; N = 64 / 128 / 256)
   int32_t xf_fast;   // E_XF: 1 = this op's issuer runs the register-resident chunk loop (chosen per op by the plan)
-  int32_t xf_issuers;  // E_XF without a residual: 2 = the residual producer's warp issues the odd tiles (1: one issuer)
   int32_t dbg;       // diagnostics (STCD_DBG): bit0 skip MMAs
   long long* trace;  // diagnostics (STCD_TRACE=1): 16 clock stamps per CTA, else nullptr
 };
@@ -261,8 +259,14 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
   long long* tr = p.trace ? p.trace + ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
   const long long clk0 = clock64();
 #define STCD_STAMP(i) do { if (tr) tr[i] = clock64() - clk0; } while (0)
-  // trace mode: cycles a role spends inside one of its waits, summed over the CTA's tiles (slots 12..15 of the trace record)
+  // Trace builds (-DSTCD_TRACE_WAITS, tools/trace_build.sh): cycles a role spends inside each of its waits, summed over the CTA's
+  // tiles (slots 3, 12..15 of the trace record).  Compiled out of the product library: the run-time form of these checks alone
+  // cost SegCD 1-2 % (same-box A/B against the build without them, round 2).
+#ifdef STCD_TRACE_WAITS
 #define STCD_TWAIT(call, counter) do { if (tr) { const long long w0_ = clock64(); call; counter += clock64() - w0_; } else { call; } } while (0)
+#else
+#define STCD_TWAIT(call, counter) do { call; } while (0)
+#endif
   if (tr && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
   // below do not depend on the previous layer; only the activation loads wait for the previous kernel to finish.
 
   long long tw_a = 0, tw_acc = 0, tw_w = 0;     // trace mode (issuer warp): cycles waited for activations / a free accumulator / streamed weights
-  // ---- Horizontally folded layers: the issue loop, shared by the issuer warp(s).
+  // ---- Horizontally folded layers: the issuer's loop.
   // A chunk is one 16..64-channel block of one source = 3 filter rows x (1, 2 or 4) K steps.  ncu's source view
   // (profiles/r2_src_conv0_4_conv1.txt) showed the issuer as a pacing role -- never waiting for an operand, ~86 instructions per
   // 6-MMA chunk, two divergent regions and two constant-bank loads per chunk.  Here the chunk's operand offsets live in
@@ -398,19 +402,9 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
   // of SNUNet (4-6 chunks per tile) -5 .. -10 %, conv0_1.conv1 (3 chunks) +7 .. +13 % in the same A/B runs, so the plan switches
   // it on from 4 chunks per tile (STCD_XF_FAST_MIN).  (The same loop measured 11-17 % SLOWER than the table loop on the Siamese
   // 3x3 layers, so it stays with the folded instances.)
-  // TWO ISSUERS.  One warp retires a dependent instruction every ~10 cycles, so one issuer cannot keep the tensor pipe fed on
-  // these layers (pipe 53-59 % occupied, the issuer never idle).  Instances without a residual leave the residual producer's
-  // warp free: it issues the ODD tiles of the CTA (accumulator set 1) while warp 2 issues the even ones (set 0).  The A ring is
-  // split in two, one sub-ring per issuer, and the producer feeds tiles t and t + 1 chunk by chunk in turn -- two independent
-  // single-producer / single-consumer pipelines, so every barrier still has exactly one waiter that sees each of its phases
-  // (an issuer skipping the other's ring positions would wait on a phase parity it cannot tell from the one two laps earlier).
-  constexpr bool kTwoIssue = XF && (EPI & (E_RES | E_GENERIC)) == 0;
   const bool xf_fast_ok = XF && p.w_resident != 0 && p.f_regular[ph] != 0 && p.xf_fast != 0 &&
                           (p.f_nmma[ph] == 3 || p.f_nmma[ph] == 6 || p.f_nmma[ph] == 12);
-  const bool xf_two = kTwoIssue && xf_fast_ok && p.xf_issuers == 2 && p.a_stages >= 4;
-  const int ring0 = xf_two ? (p.a_stages + 1) >> 1 : p.a_stages;     // stages of the first sub-ring (the second takes the rest)
-  // t_first / t_step: the tiles this issuer takes; slot0 / n_slots: its part of the A ring
-  auto xf_issue = [&](auto NC, int t_first, int t_step, int slot0, int n_slots, bool primary) {
+  auto xf_issue = [&](auto NC) {
     constexpr int NR = decltype(NC)::value;
     const bool elected = elect_one();
     const bool leader = elected && !(p.dbg & 1);      // dbg bit 1: no MMAs (the commits still arrive)
@@ -431,22 +425,19 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
     uint32_t off[NR];            // A offset | B offset << 16, as in the table (unpacked copies spill)
 #pragma unroll
     for (int i = 0; i < NR; ++i) off[i] = p.f_off[ph][i];
-    int s = slot0;
+    int s = 0;
     uint32_t a_par = 0;
-    const uint32_t a_first16 = a_ring16 + static_cast<uint32_t>(slot0) * a_stage16;
-    uint32_t a_base16 = a_first16;
-    bool stamp2 = primary && tr != nullptr;
-    for (int t = t_first; t < my_tiles; t += t_step) {
+    uint32_t a_base16 = a_ring16;
+    bool stamp2 = tr != nullptr;
+    for (int t = 0; t < my_tiles; ++t) {
       const int acc = t & 1;
-      if (primary) STCD_TWAIT(mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1), tw_acc);
-      else mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);
+      STCD_TWAIT(mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1), tw_acc);
       tc_fence_after();
       const uint32_t d0 = tmem_base + acc * p.acc_cols;
       uint32_t accum = 0;
       uint32_t b0 = b_lo_lbo + w_base16;
       for (int c = 0; c < phase.chunk_count; ++c) {
-        if (primary) STCD_TWAIT(mbar_wait(&a_full[s], a_par), tw_a);
-        else mbar_wait(&a_full[s], a_par);
+        STCD_TWAIT(mbar_wait(&a_full[s], a_par), tw_a);
         tc_fence_after();
         if (stamp2) {
           if (elected) STCD_STAMP(2);
@@ -465,15 +456,15 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
         if (elected) umma_commit(&a_empty[s]);
         b0 += f_b_chunk16;
         a_base16 += a_stage16;
-        if (++s == slot0 + n_slots) {
-          s = slot0;
+        if (++s == p.a_stages) {
+          s = 0;
           a_par ^= 1;
-          a_base16 = a_first16;
+          a_base16 = a_ring16;
         }
       }
       if (elected) {
         umma_commit(&acc_full[acc]);
-        if (primary && t == 0) STCD_STAMP(4);
+        if (t == 0) STCD_STAMP(4);
         if (t == my_tiles - 1) STCD_STAMP(9);
       }
     }
@@ -486,47 +477,7 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
     uint32_t par = 1;  // parity to wait for on a_empty[s]: first pass through the ring never blocks
     long long tw_prod = 0;
     pdl_wait();        // activations are written by the previous kernel(s)
-    if (xf_two) {
-      // two issuers: tiles t (sub-ring 0) and t + 1 (sub-ring 1) are fed chunk by chunk in turn
-      int rs[2] = {0, ring0};
-      uint32_t rpar[2] = {1, 1};
-      for (int t = 0; t < my_tiles; t += 2) {
-        int x0[2], y0[2], img[2];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          int tile = blockIdx.x + min(t + r, my_tiles - 1) * gridDim.x;
-          if (p.reverse) tile = p.n_tiles - 1 - tile;
-          const int tile_x = tile % p.tiles_x;
-          tile /= p.tiles_x;
-          x0[r] = tile_x * XSTEP - XOFF;
-          y0[r] = (tile % p.tiles_y) * TH;
-          img[r] = tile / p.tiles_y;
-        }
-        for (int c = 0; c < phase.chunk_count; ++c) {
-          const ChunkLoad L = s_cload[c];
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            if (t + r >= my_tiles) break;
-            const int st = rs[r];
-            STCD_TWAIT(mbar_wait_relaxed(&a_empty[st], rpar[r]), tw_prod);
-            if (leader) {
-              mbar_expect_tx(&a_full[st], L.tx_bytes);
-              if (t == 0 && c == 0 && r == 0) STCD_STAMP(8);
-              uint8_t* dst = smem_a + st * p.a_stage_bytes;
-              const CUtensorMap* map = &tm.src[L.src_merged & 0xff];
-              const int cx = x0[r] * L.xm + L.xa, cy = y0[r] * L.ym + L.ya, cn = img[r] + L.n_off;
-#pragma unroll
-              for (int m = 0; m < MT; ++m) tma_load_4d(dst + m * p.a_sub_bytes, map, &a_full[st], cx, cy, L.c8, cn + p.m_off[m]);   // folded ops read stride-1 sources
-            }
-            if (++rs[r] == (r ? p.a_stages : ring0)) {
-              rs[r] = r ? ring0 : 0;
-              rpar[r] ^= 1;
-            }
-          }
-        }
-      }
-    }
-    for (int t = xf_two ? my_tiles : 0; t < my_tiles; ++t) {
+    for (int t = 0; t < my_tiles; ++t) {
       int tile = blockIdx.x + t * gridDim.x;
       if (p.reverse) tile = p.n_tiles - 1 - tile;
       const int tile_x = tile % p.tiles_x;
@@ -557,7 +508,9 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
         }
       }
     }
+#ifdef STCD_TRACE_WAITS
     if (tr && leader) tr[15] = tw_prod;
+#endif
     __syncwarp();
   } else if (warp == 1) {
     // ============================== W producer (bulk copies) ==============================
@@ -608,8 +561,6 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
     const bool resident = p.w_resident != 0;
     const uint32_t n_tile_u = static_cast<uint32_t>(p.n_tile);
     const bool fast = resident && p.f_regular[ph] != 0;
-    const bool use_ws = p.ws != 0;  // sub-tiles share each weight block through the collector (tcgen05.mma.ws)
-    const bool fast_s = !resident && p.f_regular[ph] != 0 && (p.dbg & 8);       // dbg bit 8: streamed weights through the lean loop (A/B only, see below)
     const int f_nmma = p.f_nmma[ph];
     const uint32_t f_a_hi = p.f_a_hi[ph], f_a_lo_lbo = p.f_a_lo_lbo[ph], f_b_chunk16 = p.f_b_chunk16[ph];
     const uint32_t b_lo_lbo = (n_tile_u & 0x3FFF) << 16;
@@ -628,10 +579,9 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
     bool done = false;
     if constexpr (XF) {
       if (xf_fast_ok) {
-        const int n_iss = xf_two ? 2 : 1;
-        if (f_nmma == 3) xf_issue(IntC<3>{}, 0, n_iss, 0, ring0, true);
-        else if (f_nmma == 6) xf_issue(IntC<6>{}, 0, n_iss, 0, ring0, true);
-        else xf_issue(IntC<12>{}, 0, n_iss, 0, ring0, true);
+        if (f_nmma == 3) xf_issue(IntC<3>{});
+        else if (f_nmma == 6) xf_issue(IntC<6>{});
+        else xf_issue(IntC<12>{});
         done = true;
       }
     }
@@ -656,10 +606,18 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
           for (; i + 4 <= f_nmma; i += 4) {
             const uint4 e = *reinterpret_cast<const uint4*>(&p.f_off[ph][i]);   // one 16-byte constant load
             if (leader) {  // ONE divergent region per 4 (x MT) MMAs: the four operand chains overlap
-              umma_group<MT>(use_ws, d0, n_tile_u, a0 + (e.x & 0xFFFFu), a_sub16, f_a_hi, b0 + (e.x >> 16), b_hi, idesc, accum);
-              umma_group<MT>(use_ws, d0, n_tile_u, a0 + (e.y & 0xFFFFu), a_sub16, f_a_hi, b0 + (e.y >> 16), b_hi, idesc, 1u);
-              umma_group<MT>(use_ws, d0, n_tile_u, a0 + (e.z & 0xFFFFu), a_sub16, f_a_hi, b0 + (e.z >> 16), b_hi, idesc, 1u);
-              umma_group<MT>(use_ws, d0, n_tile_u, a0 + (e.w & 0xFFFFu), a_sub16, f_a_hi, b0 + (e.w >> 16), b_hi, idesc, 1u);
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.x & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (e.x >> 16), b_hi, idesc, accum);
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.y & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (e.y >> 16), b_hi, idesc, 1u);
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.z & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (e.z >> 16), b_hi, idesc, 1u);
+#pragma unroll
+              for (int m = 0; m < MT; ++m)
+                umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.w & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (e.w >> 16), b_hi, idesc, 1u);
             }
             accum = 1;
           }
@@ -670,72 +628,14 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
 #pragma unroll
               for (int r = 0; r < 3; ++r) {
                 if (i + r < f_nmma) {
-                  umma_group<MT>(use_ws, d0, n_tile_u, a0 + (ev[r] & 0xFFFFu), a_sub16, f_a_hi, b0 + (ev[r] >> 16), b_hi, idesc, (r == 0) ? accum : 1u);
-                }
-              }
-            }
-            accum = 1;
-          }
-        } else if (fast_s) {
-          // Regular phase, weights STREAMED (one ring slot per tap) -- an experiment kept for A/B runs (STCD_DBG=8), NOT the default.
-          // The trace (round 2, tools/trace_op.py) shows the issuer "busy" 85 % of the time on every streamed layer of SNUNet /
-          // SegCD (4 % waiting for activations, 11 % for weights) with the tensor pipe 40 % occupied: ~96 cycles per MMA against
-          // 64 nominal.  This lean loop (a tap = one wait, one 16-byte constant load, ONE divergent region with all K steps x
-          // sub-tiles) measured 10-20 % SLOWER than the table loop below on SNUNet's conv1_x.conv1 / conv3_1 / conv4_0 and equal on
-          // SegCD: the issuer's time is back-pressure from the tensor pipe, not instructions.  An N = 128 SS-mode MMA reads
-          // A (4 KB) + B (4 KB) per 64 cycles = all 128 B/clk of shared-memory bandwidth, and the same banks take the streamed
-          // weights (16 KB per tap) and activation boxes as writes: these layers are shared-memory-bandwidth bound, which only a
-          // two-CTA MMA (cta_group::2: each SM reads and streams half of B) relieves.
-          const uint32_t a0 = f_a_lo_lbo + a_base16;
-          uint32_t b0 = b_lo_lbo + w_base16 + static_cast<uint32_t>(ws) * wblk16;
-          for (int i = 0; i < f_nmma; i += ksteps) {
-            STCD_TWAIT(mbar_wait(&w_full[ws], w_par), tw_w);
-            tc_fence_after();
-            if (ksteps == 4) {
-              const uint4 e = *reinterpret_cast<const uint4*>(&p.f_off[ph][i]);
-              if (leader) {
-#pragma unroll
-                for (int m = 0; m < MT; ++m)
-                  umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.x & 0xFFFFu) + m * a_sub16, f_a_hi, b0, b_hi, idesc, accum);
-#pragma unroll
-                for (int m = 0; m < MT; ++m)
-                  umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.y & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + 2u * n_tile_u, b_hi, idesc, 1u);
-#pragma unroll
-                for (int m = 0; m < MT; ++m)
-                  umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.z & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + 4u * n_tile_u, b_hi, idesc, 1u);
-#pragma unroll
-                for (int m = 0; m < MT; ++m)
-                  umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.w & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + 6u * n_tile_u, b_hi, idesc, 1u);
-              }
-            } else if (ksteps == 2) {
-              const uint2 e = *reinterpret_cast<const uint2*>(&p.f_off[ph][i]);
-              if (leader) {
-#pragma unroll
-                for (int m = 0; m < MT; ++m)
-                  umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.x & 0xFFFFu) + m * a_sub16, f_a_hi, b0, b_hi, idesc, accum);
-#pragma unroll
-                for (int m = 0; m < MT; ++m)
-                  umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e.y & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + 2u * n_tile_u, b_hi, idesc, 1u);
-              }
-            } else {
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t e = p.f_off[ph][i + ks];
-                if (leader) {
 #pragma unroll
                   for (int m = 0; m < MT; ++m)
-                    umma_bf16_lohi(d0 + m * n_tile_u, a0 + (e & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + static_cast<uint32_t>(ks) * 2u * n_tile_u, b_hi, idesc,
-                                   ks == 0 ? accum : 1u);
+                    umma_bf16_lohi(d0 + m * n_tile_u, a0 + (ev[r] & 0xFFFFu) + m * a_sub16, f_a_hi, b0 + (ev[r] >> 16), b_hi, idesc,
+                                   (r == 0) ? accum : 1u);
                 }
               }
             }
             accum = 1;
-            if (elected) umma_commit(&w_empty[ws]);
-            b0 += wblk16;
-            if (++ws == p.w_stages) {
-              ws = 0;
-              w_par ^= 1;
-              b0 = b_lo_lbo + w_base16;
-            }
           }
         } else if (resident) {
           // Lane i holds the descriptors of MMA i of this chunk; the issue loop only shuffles them
@@ -749,7 +649,10 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
             for (int j = 0; j < cnt; ++j) {
               const uint32_t a_lo = __shfl_sync(0xffffffffu, my.x, j);
               const uint32_t b_lo = __shfl_sync(0xffffffffu, my.y, j);
-              if (leader) umma_group<MT>(use_ws, d0, n_tile_u, a_lo, a_sub16, M.a_hi, b_lo, b_hi, idesc, accum);
+              if (leader) {
+#pragma unroll
+                for (int m = 0; m < MT; ++m) umma_bf16_lohi(d0 + m * n_tile_u, a_lo + m * a_sub16, M.a_hi, b_lo, b_hi, idesc, accum);
+              }
               accum = 1;
             }
           }
@@ -760,7 +663,11 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
             const uint32_t b_slot16 = w_base16 + static_cast<uint32_t>(ws) * wblk16;
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint2 e = s_mma[mma_off + i + ks];
-              if (leader) umma_group<MT>(use_ws, d0, n_tile_u, e.x + a_base16, a_sub16, M.a_hi, e.y + b_slot16, b_hi, idesc, accum);
+              if (leader) {
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                  umma_bf16_lohi(d0 + m * n_tile_u, e.x + a_base16 + m * a_sub16, M.a_hi, e.y + b_slot16, b_hi, idesc, accum);
+              }
               accum = 1;
             }
             if (elected) umma_commit(&w_empty[ws]);
@@ -785,22 +692,16 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
         if (t == my_tiles - 1) STCD_STAMP(9);
       }
     }
+#ifdef STCD_TRACE_WAITS
     if (tr && elected) {
       tr[12] = tw_a;
       tr[13] = tw_acc;
       tr[3] = tw_w;
     }
+#endif
     __syncwarp();
   } else if (warp == kResWarp) {
-    // ============================== residual producer (TMA) / second issuer of the folded layers ==============================
-    if constexpr (kTwoIssue) {
-      if (xf_two) {
-        const int f_nmma = p.f_nmma[ph];
-        if (f_nmma == 3) xf_issue(IntC<3>{}, 1, 2, ring0, p.a_stages - ring0, false);
-        else if (f_nmma == 6) xf_issue(IntC<6>{}, 1, 2, ring0, p.a_stages - ring0, false);
-        else xf_issue(IntC<12>{}, 1, 2, ring0, p.a_stages - ring0, false);
-      }
-    }
+    // ============================== residual producer (TMA) ==============================
     if (p.res_slots) {
       const bool leader = elect_one();
       int rs = 0;
@@ -1246,7 +1147,9 @@ __global__ void __launch_bounds__(NE == 8 ? kConvThreads8 : kConvThreads, NE == 
         if (t == my_tiles - 1) STCD_STAMP(10);
       }
     }
+#ifdef STCD_TRACE_WAITS
     if (tr && threadIdx.x == 96) tr[14] = tw_epi;
+#endif
   }
 
   tc_fence_before();

@@ -152,55 +152,6 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// Weight-stationary form: the B operand (here the weight block) is kept in the tensor core's collector buffer across the MMAs
-// of one group -- COLL 0 = fill (read B from shared memory and keep it), 1 = use, 2 = last use -- so the M sub-tiles of a CTA
-// pass that share a weight block read it from shared memory ONCE per K step (SASS: UTCHMMA.WS ... .B_KEEP / .B_REUSE).
-// N must be 64, 128 or 256.
-template <int COLL>
-__device__ __forceinline__ void umma_ws_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                                  uint32_t idesc, uint32_t accumulate) {
-  if constexpr (COLL == 0)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
-        "mov.b64 ad, {%1, %2};\n\t"
-        "mov.b64 bd, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill [%0], ad, bd, %5, p;\n\t}" ::"r"(tmem_d),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-  else if constexpr (COLL == 1)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
-        "mov.b64 ad, {%1, %2};\n\t"
-        "mov.b64 bd, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::use [%0], ad, bd, %5, p;\n\t}" ::"r"(tmem_d),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-  else
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
-        "mov.b64 ad, {%1, %2};\n\t"
-        "mov.b64 bd, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse [%0], ad, bd, %5, p;\n\t}" ::"r"(tmem_d),
-        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// the MT MMAs of one (tap, K step): sub-tile m accumulates at d0 + m * n_tile from the A block at a_lo + m * a_sub16; all share B
-template <int MT>
-__device__ __forceinline__ void umma_group(bool ws, uint32_t d0, uint32_t n_tile, uint32_t a_lo, uint32_t a_sub16, uint32_t a_hi,
-                                           uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
-  if (MT > 1 && ws) {
-    umma_ws_bf16_lohi<0>(d0, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
-#pragma unroll
-    for (int m = 1; m < MT - 1; ++m) umma_ws_bf16_lohi<1>(d0 + m * n_tile, a_lo + m * a_sub16, a_hi, b_lo, b_hi, idesc, accumulate);
-    umma_ws_bf16_lohi<2>(d0 + (MT - 1) * n_tile, a_lo + (MT - 1) * a_sub16, a_hi, b_lo, b_hi, idesc, accumulate);
-  } else {
-#pragma unroll
-    for (int m = 0; m < MT; ++m) umma_bf16_lohi(d0 + m * n_tile, a_lo + m * a_sub16, a_hi, b_lo, b_hi, idesc, accumulate);
-  }
-}
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

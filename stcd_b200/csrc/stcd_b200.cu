@@ -1787,8 +1787,6 @@ int stcd_plan_finalize(stcd_plan* plan) {
     op.grid = dim3((unsigned)std::min(p.n_tiles, ctas), (unsigned)p.n_ntiles, (unsigned)d.n_phase);
     p.dbg = env_int("STCD_DBG", 0);
     p.xf_fast = (xf && d.n_phase == 1 && d.phase[0].chunk_count >= env_int("STCD_XF_FAST_MIN", 4)) ? 1 : 0;
-    p.ws = (!xf && op.mt > 1 && (d.n_tile == 64 || d.n_tile == 128 || d.n_tile == 256) && env_int("STCD_WS", 1)) ? 1 : 0;
-    p.xf_issuers = env_int("STCD_XF_ISSUERS", 1);    // 2 measured 5-20 % slower than 1 on SNUNet's level-0 layers (see conv_ws.cuh)
     p.reverse = (env_int("STCD_SERPENTINE", 1) && ((&op - &plan->convs[0]) & 1)) ? 1 : 0;
     if (env_int("STCD_TRACE", 0)) {
       const size_t nb = (size_t)op.grid.x * op.grid.y * op.grid.z * 16 * sizeof(long long);

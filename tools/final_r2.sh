@@ -16,6 +16,17 @@ python tools/run_once.py SNUNet_ECAM 64 256 64 > $O/plain_src.log 2>&1 && {
   head -2 $O/r2b_src_conv0_4_conv1.txt; tail -8 $O/r2b_src_conv0_4_conv1.txt
   rm -f $O/prof_fin_conv0_4_conv1.ncu-rep
 }
+# per-role wait tables: the TRACE build of the same sources (tools/trace_build.sh; built before the call, travels with the snapshot)
+if [ -f stcd_b200/libstcd_b200_trace.so ]; then
+  export STCD_LIB=stcd_b200/libstcd_b200_trace.so
+  STCD_TRACE_NET=snunet python tools/trace_op.py 64 > $O/trace_fin_snunet64.log 2>&1
+  STCD_TRACE_NET=segcd python tools/trace_op.py 4 > $O/trace_fin_segcd4.log 2>&1
+  python tools/trace_op.py 8 > $O/trace_fin_siam8.log 2>&1
+  python tools/trace_op.py 64 > $O/trace_fin_siam64.log 2>&1
+  unset STCD_LIB
+  for t in snunet64 segcd4 siam8 siam64; do python tools/trace_table.py $O/trace_fin_$t.log > $O/r2_roles_$t.txt; done
+  tail -3 $O/r2_roles_siam8.txt
+fi
 python - <<'PY'
 import json
 for f in ("default", "long"):

@@ -1,4 +1,7 @@
-"""Per-CTA clock stamps of the conv ops of one SiamUnet_diff chunk (STCD_TRACE=1)."""
+"""Per-CTA clock stamps of the conv ops of one chunk (STCD_TRACE=1): SiamUnet_diff, or STCD_TRACE_NET=snunet / segcd.
+The per-role wait counters (issuer / epilogue / producer) are compiled into the TRACE build only:
+    bash tools/trace_build.sh && STCD_LIB=stcd_b200/libstcd_b200_trace.so python tools/trace_op.py 64
+(with the product library the stamps are there and the wait shares read 0)."""
 import os, sys
 os.environ["STCD_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
