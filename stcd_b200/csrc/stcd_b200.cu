@@ -1586,7 +1586,10 @@ int stcd_plan_finalize(stcd_plan* plan) {
   const int force_occ = env_int("STCD_FORCE_OCC", 0);
   const int min_stages_occ2 = std::max(2, env_int("STCD_MIN_STAGES_OCC2", 2));  // two CTAs per SM with 2 A stages each beat one CTA with 8
   const int force_stream = env_int("STCD_FORCE_WSTREAM", 0);
-  for (ConvOp& op : plan->convs) {
+  // One conv op -> tensor maps, shared-memory plan, kernel instance, grid.  mt_override > 0 forces the number of M sub-tiles per CTA
+  // pass (the autotuner below re-runs it per candidate); 0 = the heuristics.
+  // tune_flags: bit 0 flips the folded-layer issue-loop choice, bit 1 forbids the eight-epilogue-warp instance.
+  auto configure = [&](ConvOp& op, int mt_override, int tune_flags) -> int {
     const stcd_conv_desc& d = op.d;
     memset(&op.tm, 0, sizeof(op.tm));
     stcd::ConvParams& p = op.p;
@@ -1684,7 +1687,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
       return occ != 0;
     };
     {
-      const int force_mt = env_int("STCD_FORCE_MT", 0);
+      const int force_mt = mt_override > 0 ? mt_override : env_int("STCD_FORCE_MT", 0);
       bool ok = false;
       if (force_mt && force_mt % base_mt == 0) ok = try_plan(force_mt);
       if (!ok) {
@@ -1787,8 +1790,9 @@ int stcd_plan_finalize(stcd_plan* plan) {
     op.grid = dim3((unsigned)std::min(p.n_tiles, ctas), (unsigned)p.n_ntiles, (unsigned)d.n_phase);
     p.dbg = env_int("STCD_DBG", 0);
     p.xf_fast = (xf && d.n_phase == 1 && d.phase[0].chunk_count >= env_int("STCD_XF_FAST_MIN", 4)) ? 1 : 0;
+    if (xf && d.n_phase == 1 && (tune_flags & 1)) p.xf_fast ^= 1;
     p.reverse = (env_int("STCD_SERPENTINE", 1) && ((&op - &plan->convs[0]) & 1)) ? 1 : 0;
-    if (env_int("STCD_TRACE", 0)) {
+    if (env_int("STCD_TRACE", 0) && !op.trace) {
       const size_t nb = (size_t)op.grid.x * op.grid.y * op.grid.z * 16 * sizeof(long long);
       CUDA_TRY(cudaMalloc(&op.trace, nb));
       CUDA_TRY(cudaMemset(op.trace, 0, nb));
@@ -1812,7 +1816,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
     op.fn = nullptr;
     op.threads = stcd::kConvThreads;
     // plans that run one CTA per SM anyway take the eight-epilogue-warp instance when there is one (>= 2 column steps to share)
-    const bool want8 = occ == 1 && (xf ? (d.xf_cs >= 32 && env_int("STCD_XF_EPI8", 1) != 0) : d.n_tile >= 32) && env_int("STCD_EPI8", 1) != 0;
+    const bool want8 = !(tune_flags & 2) && occ == 1 && (xf ? (d.xf_cs >= 32 && env_int("STCD_XF_EPI8", 1) != 0) : d.n_tile >= 32) && env_int("STCD_EPI8", 1) != 0;
     for (int i = 0; i < n_kernels && !force_generic && !d.split; ++i)     // split precision lives in the generic instances
       if (kernels[i].mt == op.mt && kernels[i].ms == (d.pair ? 2 : 1) && kernels[i].epi == op.epi && (kernels[i].ne == 4 || want8)) {
         if (op.fn && kernels[i].ne == 4) continue;       // an eight-warp instance found earlier wins
@@ -1847,6 +1851,82 @@ int stcd_plan_finalize(stcd_plan* plan) {
       p.out_diff = (__nv_bfloat16*)plan->tensors[d.out_diff].ptr;
       p.out_diff_c8 = plan->tensors[d.out_diff].c / 8;
     }
+    return STCD_OK;
+  };
+  for (ConvOp& op : plan->convs) {
+    const int r = configure(op, 0, 0);
+    if (r) return r;
+  }
+  // ---- Autotune the M sub-tiles per CTA pass, then the folded-layer issue loop and the epilogue width (STCD_AUTOTUNE=0: off).  How many images share a weight block in one pass
+  // trades weight reuse and per-tile overheads against tile count, TMEM columns and occupancy, and no static rule gets every layer
+  // right: with the heuristic's choice forced to 2 or 4 instead, SNUNet's `conv1_x.conv2` / `conv4_0` run 14-19 % faster at 2,
+  // `conv0_0.conv1` 17 % and `conv1_x.conv1` / `Up1_x` 6-7 % faster at 4, while `conv0_x.conv2` and `Up1_x` lose 25-38 % at the other
+  // setting (round 2, per-op A/B on one box).  So each op is timed on the plan's own workspace with every admissible count (the data
+  // is whatever the workspace holds: the kernels' time does not depend on values) and keeps the fastest; a candidate must win by
+  // 4 % to displace the heuristic.  Results do not depend on the choice: a sub-tile's MMAs and epilogue are the same sequence.
+  if (env_int("STCD_AUTOTUNE", 1) && !env_int("STCD_FORCE_MT", 0) && !env_int("STCD_TRACE", 0)) {
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    cudaStream_t st = nullptr;
+    auto time_op = [&](const ConvOp& op, float* ms_out) -> int {
+      float best = 1e30f;
+      for (int rep = 0; rep < 4; ++rep) {               // first launch = warm-up
+        CUDA_TRY(cudaEventRecord(e0, st));
+        const int r = launch_conv(plan, op, plan->chunk, nullptr, st);
+        if (r) return r;
+        CUDA_TRY(cudaEventRecord(e1, st));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+      }
+      *ms_out = best;
+      return STCD_OK;
+    };
+    for (ConvOp& op : plan->convs) {
+      if (op.d.out_ext >= 0) continue;                  // writes a caller-owned buffer that does not exist yet
+      const int mt0 = op.mt;
+      float t0 = 0.f;
+      int r = time_op(op, &t0);
+      if (r) return r;
+      int best_mt = 0, best_flags = 0;                  // 0 / 0 = the heuristics' own choice
+      float best_t = t0 * 0.96f;
+      const int base_mt = op.d.pair ? 2 : 1;
+      for (int mt = base_mt; mt <= 4; mt <<= 1) {
+        if (mt == mt0) continue;
+        if (configure(op, mt, 0) != STCD_OK || op.mt != mt) continue;      // not admissible: the heuristics answered instead
+        float t = 0.f;
+        r = time_op(op, &t);
+        if (r) return r;
+        if (t < best_t) {
+          best_t = t;
+          best_mt = mt;
+        }
+      }
+      // with the pass width settled: the folded-layer issue loop the other way round, and four epilogue warps where eight were taken
+      for (int flag = 1; flag <= 2; flag <<= 1) {
+        if (configure(op, best_mt, best_flags) != STCD_OK) break;
+        if (flag == 1 && !(op.d.xf_cs > 0 && op.d.n_phase == 1)) continue;
+        if (flag == 2 && op.threads != stcd::kConvThreads8) continue;
+        if (configure(op, best_mt, best_flags | flag) != STCD_OK) continue;
+        float t = 0.f;
+        r = time_op(op, &t);
+        if (r) return r;
+        if (t < best_t) {
+          best_t = t;
+          best_flags |= flag;
+        }
+      }
+      r = configure(op, best_mt, best_flags);
+      if (r) return r;
+      if (env_int("STCD_AUTOTUNE_LOG", 0))
+        fprintf(stderr, "autotune conv %3d  mt %d -> %d flags %d (%.1f us -> %.1f us)\n", (int)(&op - &plan->convs[0]), mt0, op.mt, best_flags, t0 * 1e3f,
+                ((best_mt || best_flags) ? best_t : t0) * 1e3f);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CUDA_TRY(cudaDeviceSynchronize());
   }
   for (GraphOp& g : plan->graphs) {
     const Tensor& ts = plan->tensors[g.src];
