@@ -82,6 +82,7 @@ struct ConvOp {
   dim3 grid;
   size_t smem = 0;
   int mt = 1;
+  int occ = 0;                 // CTAs per SM the shared-memory plan was sized for
   uint32_t epi = 0;
   stcd::ConvKernelFn fn = nullptr;
   int threads = 256;           // 256 (four epilogue warps) or 384 (eight)
@@ -1583,13 +1584,15 @@ int stcd_plan_finalize(stcd_plan* plan) {
   int n_sm = 148;
   CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, plan->device));
 
-  const int force_occ = env_int("STCD_FORCE_OCC", 0);
+  const int force_occ_env = env_int("STCD_FORCE_OCC", 0);
   const int min_stages_occ2 = std::max(2, env_int("STCD_MIN_STAGES_OCC2", 2));  // two CTAs per SM with 2 A stages each beat one CTA with 8
   const int force_stream = env_int("STCD_FORCE_WSTREAM", 0);
   // One conv op -> tensor maps, shared-memory plan, kernel instance, grid.  mt_override > 0 forces the number of M sub-tiles per CTA
   // pass (the autotuner below re-runs it per candidate); 0 = the heuristics.
-  // tune_flags: bit 0 flips the folded-layer issue-loop choice, bit 1 forbids the eight-epilogue-warp instance.
+  // tune_flags: bit 0 flips the folded-layer issue-loop choice, bit 1 forbids the eight-epilogue-warp instance, bit 2 plans for ONE
+  // CTA per SM where two would fit (deeper rings, and the eight-epilogue-warp instances become eligible).
   auto configure = [&](ConvOp& op, int mt_override, int tune_flags) -> int {
+    const int force_occ = (tune_flags & 4) ? 1 : force_occ_env;
     const stcd_conv_desc& d = op.d;
     memset(&op.tm, 0, sizeof(op.tm));
     stcd::ConvParams& p = op.p;
@@ -1742,6 +1745,7 @@ int stcd_plan_finalize(stcd_plan* plan) {
         }
     }
     op.mt = p.mt;
+    op.occ = occ;
     {
       const int g = op.mt / base_mt;
       p.n_img = base_imgs / g;
@@ -1904,9 +1908,11 @@ int stcd_plan_finalize(stcd_plan* plan) {
           best_mt = mt;
         }
       }
-      // with the pass width settled: the folded-layer issue loop the other way round, and four epilogue warps where eight were taken
-      for (int flag = 1; flag <= 2; flag <<= 1) {
+      // with the pass width settled: one CTA per SM where two were planned, four epilogue warps where eight were taken, and the
+      // folded-layer issue loop the other way round
+      for (int flag = 4; flag >= 1; flag >>= 1) {       // occupancy first: it decides whether eight epilogue warps are on the table
         if (configure(op, best_mt, best_flags) != STCD_OK) break;
+        if (flag == 4 && op.occ != 2) continue;
         if (flag == 1 && !(op.d.xf_cs > 0 && op.d.n_phase == 1)) continue;
         if (flag == 2 && op.threads != stcd::kConvThreads8) continue;
         if (configure(op, best_mt, best_flags | flag) != STCD_OK) continue;
