@@ -5,7 +5,7 @@ M=gpu__time_duration.sum,sm__mem_tensor_writes_op_utcmma.sum,sm__inst_executed_p
 layers() {  # layers <tag> <run_once args...>
   local tag=$1; shift
   STCD_DUMP_OPS=$O/ops_$tag.json python tools/run_once.py "$@" > $O/plain_$tag.log 2>&1 || { echo "plain run failed: $tag"; tail -3 $O/plain_$tag.log; return 1; }
-  ncu --metrics $M --clock-control none --csv --log-file $O/ncu_$tag.csv python tools/run_once.py "$@" > $O/ncu_$tag.log 2>&1 || { echo "ncu failed: $tag"; tail -3 $O/ncu_$tag.log; return 1; }
+  STCD_PROFILE_RANGE=1 ncu --profile-from-start off --metrics $M --clock-control none --csv --log-file $O/ncu_$tag.csv python tools/run_once.py "$@" > $O/ncu_$tag.log 2>&1 || { echo "ncu failed: $tag"; tail -3 $O/ncu_$tag.log; return 1; }
   python tools/ncu_layers.py $O/ncu_$tag.csv $O/ops_$tag.json $O/r2_layers_$tag > /dev/null && tail -1 $O/r2_layers_$tag.txt
 }
 for spec in "$@"; do
