@@ -3,7 +3,7 @@
 # Results are garbage by construction; only per_op_ms matters.
 mkdir -p gpurun_out
 ./tools/ubench/mma_rate.bin > gpurun_out/mma_rate_r2.log 2>&1
-for d in 0 1 2 4 8 10 11; do
+for d in 0 1 2 3; do
   STCD_DBG=$d python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-also > gpurun_out/dbg_c2_$d.log 2>&1
 done
 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-also --workload siamunet_diff_256 > gpurun_out/r2_c1_b8_base.log 2>&1
@@ -11,7 +11,7 @@ python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-also --workload sia
 python - <<'PY'
 import json, glob
 tabs = {}
-for d in (0, 1, 2, 4, 8, 10, 11):
+for d in (0, 1, 2, 3):
     try:
         line = [l for l in open(f"gpurun_out/dbg_c2_{d}.log") if l.startswith("{")][-1]
         tabs[d] = dict((n, ms) for n, ms, *_ in json.loads(line)["per_op_ms"])
