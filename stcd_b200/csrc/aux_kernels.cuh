@@ -702,9 +702,16 @@ __global__ void __launch_bounds__(256) segcd_head_mma_kernel(const __nv_bfloat16
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const unsigned char* sb = reinterpret_cast<const unsigned char*>(s_head_dyn);
-  auto frag = [&](int s, int g, int py, int px) -> uint32_t {      // channels 8g + cq, +1 of pixel (py, px) of stream s
-    return *reinterpret_cast<const uint32_t*>(sb + ((static_cast<size_t>((s * C8 + g) * PH + py) * PW + px) * 16 + cq * 2));
+  // A fragments by ldmatrix: a staged pixel is one 16-byte row (8 channels), so the four 8 x 8 matrices of an m16n8k16 A operand
+  // -- pixels 0-7 / 8-15 x channel groups 0 / 1 -- are one ldmatrix.x4 (lane l gives row l & 7 of matrix l >> 3) instead of
+  // four 32-bit LDS per stream and tap: the kernel ran at 30 % of the HBM roof with the LSU as its busiest pipe.
+  const uint32_t sb32 = static_cast<uint32_t>(__cvta_generic_to_shared(s_head_dyn));
+  const uint32_t lane_off = static_cast<uint32_t>((((lane >> 4) * PH) * PW + ((lane >> 3) & 1) * 8 + (lane & 7)) * 16);
+  auto ldm4 = [&](int s, int py, int px0, uint32_t (&a)[4]) {      // pixels px0 .. px0 + 15 of row py, stream s, 16 channels
+    const uint32_t addr = sb32 + static_cast<uint32_t>(((s * C8 * PH + py) * PW + px0) * 16) + lane_off;
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+                 : "r"(addr));
   };
 #pragma unroll 1
   for (int i = 0; i < (kHeadTW / 16) * kHeadTH / 8; ++i) {         // 32 row segments of 16 pixels, 4 per warp
@@ -715,10 +722,10 @@ __global__ void __launch_bounds__(256) segcd_head_mma_kernel(const __nv_bfloat16
     for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int py = ty + ky, px = xw + r + kx;
+        const int py = ty + ky;
         uint32_t a1[4], a2[4], ad[4];
-        a1[0] = frag(0, 0, py, px), a1[1] = frag(0, 0, py, px + 8), a1[2] = frag(0, 1, py, px), a1[3] = frag(0, 1, py, px + 8);
-        a2[0] = frag(1, 0, py, px), a2[1] = frag(1, 0, py, px + 8), a2[2] = frag(1, 1, py, px), a2[3] = frag(1, 1, py, px + 8);
+        ldm4(0, py, xw + kx, a1);
+        ldm4(1, py, xw + kx, a2);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const __nv_bfloat162 df = __habs2(__hsub2(*reinterpret_cast<const __nv_bfloat162*>(&a1[e]), *reinterpret_cast<const __nv_bfloat162*>(&a2[e])));
