@@ -21,8 +21,12 @@
 //
 // Warp roles (8 warps): 0 = A producer (TMA), 1 = W producer (bulk copy), 2 = MMA issuer (also
 // owns TMEM alloc/dealloc), 3..6 = epilogue (TMEM -> registers -> folded BN / ReLU / residual /
-// |f1-f2| / 2x2 max-pool -> global), 7 = residual producer (TMA into a small ring, when the op has one).  Accumulators are double-buffered in TMEM so the epilogue
-// of tile i overlaps the MMAs of tile i+1; CTAs are persistent over their tiles.
+// |f1-f2| / 2x2 max-pool -> global), 7 = residual producer (TMA into a small ring, when the op has one).  The NE = 8 instances
+// (one CTA per SM: short-K residual layers, horizontally folded layers) have eight epilogue warps 3..10 -- two per TMEM lane
+// quarter, alternating 16-column steps -- and the residual producer is warp 11.  Accumulators are double-buffered in TMEM so the
+// epilogue of tile i overlaps the MMAs of tile i+1; CTAs are persistent over their tiles.  How many M sub-tiles (images) share a
+// weight block per pass, the epilogue width and the folded-layer issue loop are chosen per op by the plan, which times the
+// admissible variants on its own workspace (stcd_plan_finalize).
 //
 // Measured on B200 (tools/ubench, profiles/): a tcgen05.mma M=128 K=16 in SS mode costs ~45
 // cycles for N <= 64 (the 4 KB A read from shared memory), 64 for N=128 — and a single warp
